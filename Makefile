@@ -1,0 +1,35 @@
+# Builds the product library (CUDA, sm_100a) and the CPU oracle (test infrastructure).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+CC        ?= gcc
+PKG       := clarabel.rs_b200
+CSRC      := $(PKG)/csrc
+LIB       := $(PKG)/libclarabel_b200.so
+ORACLE    := oracle/liboracle.so
+GENCODE   := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC,-O3,-Wall -Xptxas -v
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
+CU_OBJS   := $(CU_SRCS:.cu=.o)
+CPP_OBJS  := $(CPP_SRCS:.cpp=.o)
+HDRS      := $(wildcard $(CSRC)/*.h) include/clarabel_b200.h
+ORACLE_SRCS := $(wildcard oracle/*.c)
+
+all: $(LIB) $(ORACLE)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(CSRC)/%.o: $(CSRC)/%.cpp $(HDRS)
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(CPP_OBJS)
+	$(NVCC) -shared $(GENCODE) -o $@ $^ -lcudart
+
+$(ORACLE): $(ORACLE_SRCS)
+	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -Wall -o $@ $^ -lm
+
+clean:
+	rm -f $(CSRC)/*.o $(LIB) $(ORACLE)
+
+.PHONY: all clean

@@ -1,0 +1,327 @@
+"""clarabel.rs_b200 -- B200-native KKT backend (host-side Python mirror).
+
+The product is the C-ABI shared library ``libclarabel_b200.so`` (CUDA, sm_100a;
+see ``include/clarabel_b200.h``).  This module is the thin ctypes binding used
+by the tests and the bench; it mirrors the reference's plugin interface names:
+
+* ``CudaLDLSolver``      <-> ``trait DirectLDLSolver`` + the qdldl adapter
+  (/root/reference/src/solver/core/kktsolvers/direct/quasidef/mod.rs:14-26,
+  .../ldlsolvers/qdldl.rs:19-107): ``update_values / scale_values /
+  offset_values / refactor / solve / linear_solver_info``.
+* ``SymbolicAnalysis``   host-only view of the ordering / supernodal analysis.
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device
+is present when a device object is constructed, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libclarabel_b200.so")
+_lib = None
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+CLDL_OK = 0
+CLDL_E_DIM, CLDL_E_EMPTY_COLUMN, CLDL_E_NOT_TRIU = -1, -2, -3
+CLDL_E_ZERO_PIVOT, CLDL_E_BAD_PERM = -4, -5
+CLDL_E_CUDA, CLDL_E_ARG, CLDL_E_NOT_FACTORED = -20, -21, -22
+ORDER_AMD, ORDER_ND, ORDER_BEST = 1, 2, 3
+
+_ERRNAMES = {
+    -1: "IncompatibleDimension", -2: "EmptyColumn", -3: "NotUpperTriangular",
+    -4: "ZeroPivot", -5: "InvalidPermutation", -20: "CudaFailure (no device / runtime error)",
+    -21: "BadArgument", -22: "NotFactored",
+}
+
+
+class cldl_opts(C.Structure):
+    _fields_ = [
+        ("regularize_eps", C.c_double),
+        ("regularize_delta", C.c_double),
+        ("regularize_enable", C.c_int32),
+        ("amd_dense_scale", C.c_double),
+        ("ordering", C.c_int32),
+        ("device", C.c_int32),
+        ("max_panel", C.c_int32),
+        ("nd_leaf", C.c_int32),
+    ]
+
+
+class cldl_info_t(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 16),
+        ("threads", C.c_uint32),
+        ("direct", C.c_int32),
+        ("nnzA", C.c_uint64),
+        ("nnzL", C.c_uint64),
+        ("nnzL_stored", C.c_uint64),
+        ("regularize_count", C.c_uint64),
+        ("positive_inertia", C.c_uint64),
+        ("n_supernodes", C.c_uint64),
+        ("n_levels", C.c_uint64),
+        ("flops", C.c_double),
+        ("ordering_used", C.c_int32),
+    ]
+
+
+# every symbol declared in include/clarabel_b200.h (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "cldl_default_opts", "cldl_create", "cldl_destroy", "cldl_update_values",
+    "cldl_scale_values", "cldl_offset_values", "cldl_refactor", "cldl_solve",
+    "cldl_info", "cldl_get_perm", "cldl_update_values_dev", "cldl_set_values_dev",
+    "cldl_refactor_dev", "cldl_solve_dev", "cldl_sync_status", "cldl_stream",
+    "cldl_values_dev", "cldl_time_refactor_ms", "cldl_time_solve_ms",
+]
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA shared library; fail loudly when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        raise BackendError(
+            f"{_LIBPATH} not found: build it with `make` (or __graft_entry__.build()); "
+            "this backend has no CPU fallback")
+    L = C.CDLL(_LIBPATH)
+    u64p, f64p, i8p, i32p = (C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                             C.POINTER(C.c_int8), C.POINTER(C.c_int32))
+    vp = C.c_void_p
+    L.cldl_default_opts.argtypes = [C.POINTER(cldl_opts)]
+    L.cldl_default_opts.restype = None
+    L.cldl_create.argtypes = [C.POINTER(vp), C.c_uint64, u64p, u64p, f64p, i8p,
+                              C.POINTER(cldl_opts), u64p]
+    L.cldl_create.restype = C.c_int
+    L.cldl_destroy.argtypes = [vp]
+    L.cldl_destroy.restype = None
+    L.cldl_update_values.argtypes = [vp, u64p, f64p, C.c_uint64]
+    L.cldl_scale_values.argtypes = [vp, u64p, C.c_uint64, C.c_double]
+    L.cldl_offset_values.argtypes = [vp, u64p, C.c_uint64, C.c_double, i8p]
+    L.cldl_refactor.argtypes = [vp]
+    L.cldl_solve.argtypes = [vp, f64p, f64p]
+    L.cldl_info.argtypes = [vp, C.POINTER(cldl_info_t)]
+    L.cldl_info.restype = None
+    L.cldl_get_perm.argtypes = [vp, u64p]
+    L.cldl_update_values_dev.argtypes = [vp, vp, vp, C.c_uint64]
+    L.cldl_set_values_dev.argtypes = [vp, vp]
+    L.cldl_refactor_dev.argtypes = [vp]
+    L.cldl_solve_dev.argtypes = [vp, vp, vp]
+    L.cldl_sync_status.argtypes = [vp]
+    L.cldl_stream.argtypes = [vp]
+    L.cldl_stream.restype = vp
+    L.cldl_values_dev.argtypes = [vp]
+    L.cldl_values_dev.restype = vp
+    L.cldl_time_refactor_ms.argtypes = [vp, C.c_int]
+    L.cldl_time_refactor_ms.restype = C.c_double
+    L.cldl_time_solve_ms.argtypes = [vp, C.c_int]
+    L.cldl_time_solve_ms.restype = C.c_double
+    # host-only symbolic API
+    L.csym_analyse.argtypes = [C.POINTER(vp), C.c_uint64, u64p, u64p, u64p, C.c_int,
+                               C.c_double, C.c_int, C.c_int]
+    L.csym_free.argtypes = [vp]
+    L.csym_free.restype = None
+    L.csym_scalar.argtypes = [vp, C.c_int]
+    L.csym_scalar.restype = C.c_int64
+    L.csym_flops.argtypes = [vp, C.c_int]
+    L.csym_flops.restype = C.c_double
+    L.csym_array.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.c_int64]
+    L.csym_array.restype = C.c_int64
+    L.csym_order.argtypes = [C.c_uint64, u64p, u64p, C.c_int, C.c_double, C.c_int, u64p]
+    _lib = L
+    return L
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise BackendError(f"{what} failed: {_ERRNAMES.get(rc, rc)}")
+    return rc
+
+
+@dataclass
+class LinearSolverInfo:
+    """Mirror of kktsolvers/mod.rs:24-38 plus factorisation counters."""
+    name: str
+    threads: int
+    direct: bool
+    nnzA: int
+    nnzL: int
+    nnzL_stored: int
+    regularize_count: int
+    positive_inertia: int
+    n_supernodes: int
+    n_levels: int
+    flops: float
+    ordering_used: int
+
+
+class CudaLDLSolver:
+    """Device LDL^T backend with the ``DirectLDLSolver`` method set.
+
+    ``KKT`` is (n, colptr, rowval, nzval) of the upper-triangular CSC KKT matrix.
+    Constructor arguments follow ``ldlsolvers/config.rs:19-20``:
+    (KKT, Dsigns, settings, perm).
+    """
+
+    required_matrix_shape = "triu"  # DirectLDLSolverReqs, ldlsolvers/qdldl.rs:54-56
+
+    def __init__(self, n, colptr, rowval, nzval, dsigns, *, perm=None,
+                 regularize_eps=1e-13, regularize_delta=2e-7, regularize_enable=True,
+                 amd_dense_scale=1.5, ordering=ORDER_BEST, device=0, max_panel=0, nd_leaf=0):
+        L = lib()
+        self._L = L
+        self.n = int(n)
+        o = cldl_opts()
+        L.cldl_default_opts(C.byref(o))
+        o.regularize_eps, o.regularize_delta = regularize_eps, regularize_delta
+        o.regularize_enable = 1 if regularize_enable else 0
+        o.amd_dense_scale, o.ordering, o.device = amd_dense_scale, ordering, device
+        o.max_panel, o.nd_leaf = max_panel, nd_leaf
+        cp, rv, nz = _u64(colptr), _u64(rowval), _f64(nzval)
+        ds = np.ascontiguousarray(dsigns, dtype=np.int8)
+        pm = _u64(perm) if perm is not None else None
+        h = C.c_void_p()
+        rc = L.cldl_create(C.byref(h), self.n, _p(cp, C.c_uint64), _p(rv, C.c_uint64),
+                           _p(nz, C.c_double), _p(ds, C.c_int8), C.byref(o),
+                           _p(pm, C.c_uint64) if pm is not None else None)
+        _check(rc, "cldl_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cldl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- DirectLDLSolver trait ---
+    def update_values(self, index, values):
+        idx, v = _u64(index), _f64(values)
+        assert idx.shape == v.shape
+        _check(self._L.cldl_update_values(self._h, _p(idx, C.c_uint64), _p(v, C.c_double), idx.size),
+               "update_values")
+
+    def scale_values(self, index, scale):
+        idx = _u64(index)
+        _check(self._L.cldl_scale_values(self._h, _p(idx, C.c_uint64), idx.size, float(scale)),
+               "scale_values")
+
+    def offset_values(self, index, offset, signs):
+        idx = _u64(index)
+        sg = np.ascontiguousarray(signs, dtype=np.int8)
+        assert idx.size == sg.size  # qdldl.rs:167
+        _check(self._L.cldl_offset_values(self._h, _p(idx, C.c_uint64), idx.size, float(offset),
+                                          _p(sg, C.c_int8)), "offset_values")
+
+    def refactor(self) -> bool:
+        return bool(_check(self._L.cldl_refactor(self._h), "refactor"))
+
+    def solve(self, b):
+        b = _f64(b)
+        assert b.size == self.n  # qdldl.rs:121
+        x = np.empty_like(b)
+        _check(self._L.cldl_solve(self._h, _p(x, C.c_double), _p(b, C.c_double)), "solve")
+        return x
+
+    def linear_solver_info(self) -> LinearSolverInfo:
+        i = cldl_info_t()
+        self._L.cldl_info(self._h, C.byref(i))
+        return LinearSolverInfo(i.name.decode(), i.threads, bool(i.direct), i.nnzA, i.nnzL,
+                                i.nnzL_stored, i.regularize_count, i.positive_inertia,
+                                i.n_supernodes, i.n_levels, i.flops, i.ordering_used)
+
+    def perm(self):
+        p = np.empty(self.n, dtype=np.uint64)
+        _check(self._L.cldl_get_perm(self._h, _p(p, C.c_uint64)), "get_perm")
+        return p.astype(np.int64)
+
+    # --- device-side helpers (bench) ---
+    def time_refactor_ms(self, reps):
+        return self._L.cldl_time_refactor_ms(self._h, int(reps))
+
+    def time_solve_ms(self, reps):
+        return self._L.cldl_time_solve_ms(self._h, int(reps))
+
+    def sync_status(self):
+        return self._L.cldl_sync_status(self._h)
+
+    def solve_dev(self, d_x_ptr, d_b_ptr):
+        _check(self._L.cldl_solve_dev(self._h, C.c_void_p(d_x_ptr), C.c_void_p(d_b_ptr)), "solve_dev")
+
+    def refactor_dev(self):
+        _check(self._L.cldl_refactor_dev(self._h), "refactor_dev")
+
+    def set_values_dev(self, d_ptr):
+        _check(self._L.cldl_set_values_dev(self._h, C.c_void_p(d_ptr)), "set_values_dev")
+
+    def stream_ptr(self):
+        return self._L.cldl_stream(self._h)
+
+
+_SYM_ARRAYS = ["perm", "parent", "colcount", "sn_first", "sn_rowptr", "sn_rows", "sn_parent",
+               "sn_level", "child_ptr", "child_list", "rel", "panel_off", "upd_off", "asm_ptr",
+               "asm_src", "asm_dst", "level_ptr", "level_tasks", "iperm"]
+
+
+class SymbolicAnalysis:
+    """Host-only ordering + supernodal analysis (no GPU needed)."""
+
+    def __init__(self, n, colptr, rowval, *, perm=None, ordering=ORDER_BEST,
+                 amd_dense_scale=1.5, max_panel=0, nd_leaf=0):
+        L = lib()
+        cp, rv = _u64(colptr), _u64(rowval)
+        pm = _u64(perm) if perm is not None else None
+        h = C.c_void_p()
+        rc = L.csym_analyse(C.byref(h), int(n), _p(cp, C.c_uint64), _p(rv, C.c_uint64),
+                            _p(pm, C.c_uint64) if pm is not None else None,
+                            0 if perm is not None else ordering, amd_dense_scale, max_panel, nd_leaf)
+        if rc:
+            raise BackendError(f"csym_analyse failed: {rc}")
+        try:
+            names = ["n", "nsup", "nlevels", "nnzL", "nnzL_stored", "upd_total", "ordering_used", "nnzA"]
+            for k, nm in enumerate(names):
+                setattr(self, nm, int(L.csym_scalar(h, k)))
+            self.flops = L.csym_flops(h, 0)
+            self.flops_stored = L.csym_flops(h, 1)
+            for k, nm in enumerate(_SYM_ARRAYS):
+                ln = L.csym_array(h, k, None, 0)
+                a = np.empty(max(ln, 1), dtype=np.int64)
+                L.csym_array(h, k, _p(a, C.c_int64), ln)
+                setattr(self, nm, a[:ln])
+        finally:
+            L.csym_free(h)
+
+
+def order(n, colptr, rowval, kind=ORDER_AMD, dense_scale=1.5, nd_leaf=200):
+    L = lib()
+    cp, rv = _u64(colptr), _u64(rowval)
+    out = np.empty(int(n), dtype=np.uint64)
+    rc = L.csym_order(int(n), _p(cp, C.c_uint64), _p(rv, C.c_uint64), kind, dense_scale, nd_leaf,
+                      _p(out, C.c_uint64))
+    if rc:
+        raise BackendError("ordering failed")
+    return out.astype(np.int64)

@@ -1,0 +1,653 @@
+// Device multifrontal LDL^T for quasidefinite KKT matrices (sm_100a) + the
+// cldl_* C-ABI (include/clarabel_b200.h).
+//
+// What it replaces in the reference (all file:line under /root/reference):
+//   numeric refactor  src/qdldl/qdldl.rs:469-669   (_factor_inner, up-looking, 1 thread)
+//   solve             src/qdldl/qdldl.rs:116-138, 708-768 (permute, L, D L^T, ipermute)
+//   value updates     src/qdldl/qdldl.rs:142-183
+//   adapter           src/solver/core/kktsolvers/direct/quasidef/ldlsolvers/qdldl.rs
+//
+// Design: host symbolic analysis builds a supernodal assembly
+// tree; every tree level is a batch of independent dense fronts.  A front's
+// panel ((ns+nr) x ns, column major) lives in the compact factor storage, its
+// update matrix (nr x nr) in a lifetime-managed arena.  Per level: assemble
+// (original entries + children's update matrices through relative indices),
+// dense LDL^T of the pivot block with the reference's sign-aware dynamic
+// regularisation rule (qdldl.rs:645-651) applied pivot by pivot in elimination
+// order, panel scaling, Schur update.  No atomics on floating point data:
+// every sum has a fixed order, so refactor/solve are bit-reproducible run to run.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/clarabel_b200.h"
+#include "ldl_device.h"
+#include "symbolic.h"
+
+namespace cb {
+
+// ------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------
+
+// Fused front kernel: one CTA per front.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_factor_level(LDLDev d, int task_base, int smem_cap) {
+  extern __shared__ double sm[];
+  __shared__ double s_inv;
+  __shared__ double sD[CB_MAX_PANEL];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  const int s = d.level_tasks[task_base + blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  double* __restrict__ P = d.L + d.panel_off[s];
+  double* __restrict__ U = d.U + d.upd_off[s];
+  const long long psz = (long long)ld * ns;
+  const bool use_sm = psz <= (long long)smem_cap;
+  double* W = use_sm ? sm : P;
+
+  for (long long i = tid; i < psz; i += NT) W[i] = 0.0;
+  for (int b = warp; b < nr; b += nwarp)
+    for (int a = b + lane; a < nr; a += 32) U[(long long)b * nr + a] = 0.0;
+  __syncthreads();
+
+  // original matrix entries (each lands in a distinct slot)
+  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += NT)
+    W[d.asm_dst[e]] = d.vals[d.asm_src[e]];
+  __syncthreads();
+
+  // extend-add of the children's update matrices, fixed child order
+  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
+    const int c = d.child_list[ci];
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* __restrict__ Uc = d.U + d.upd_off[c];
+    const int* __restrict__ relc = d.rel + crp;
+    for (int b = warp; b < nrc; b += nwarp) {
+      const int rb = relc[b];
+      for (int a = b + lane; a < nrc; a += 32) {
+        const int ra = relc[a];
+        const double v = Uc[(long long)b * nrc + a];
+        if (rb < ns) W[(long long)rb * ld + ra] += v;
+        else U[(long long)(rb - ns) * nr + (ra - ns)] += v;
+      }
+    }
+    __syncthreads();
+  }
+
+  // dense LDL^T of the panel, right-looking, pivot order = elimination order
+  for (int j = 0; j < ns; j++) {
+    if (tid == 0) {
+      double dj = W[(long long)j * ld + j];
+      if (d.reg_enable) {
+        const double sg = (double)d.dsigns[f + j];
+        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; atomicAdd(&d.status[ST_REGCOUNT], 1); }
+      }
+      if (dj == 0.0) atomicExch(&d.status[ST_ZEROPIV], 1);
+      if (dj > 0.0) atomicAdd(&d.status[ST_POSINERTIA], 1);
+      const double inv = 1.0 / dj;
+      if (!isfinite(inv)) atomicExch(&d.status[ST_NONFINITE], 1);
+      d.D[f + j] = dj;
+      d.Dinv[f + j] = inv;
+      W[(long long)j * ld + j] = dj;
+      s_inv = inv;
+      sD[j] = dj;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    const double* __restrict__ cj = W + (long long)j * ld;
+    for (int k = j + 1 + warp; k < ns; k += nwarp) {
+      const double wk = cj[k] * inv;
+      double* __restrict__ ck = W + (long long)k * ld;
+      for (int i = k + lane; i < ld; i += 32) ck[i] -= cj[i] * wk;
+    }
+    __syncthreads();
+    double* cjw = W + (long long)j * ld;
+    for (int i = j + 1 + tid; i < ld; i += NT) cjw[i] *= inv;
+  }
+  __syncthreads();
+
+  // Schur update of the lower triangle of U
+  for (int b = warp; b < nr; b += nwarp) {
+    for (int a = b + lane; a < nr; a += 32) {
+      double acc = 0.0;
+      for (int k = 0; k < ns; k++) {
+        const double* __restrict__ ck = W + (long long)k * ld + ns;
+        acc += ck[a] * (ck[b] * sD[k]);
+      }
+      U[(long long)b * nr + a] -= acc;
+    }
+  }
+  if (use_sm) {
+    for (long long i = tid; i < psz; i += NT) P[i] = W[i];
+  }
+}
+
+__global__ void k_permute_in(int n, const int* __restrict__ perm, const double* __restrict__ b,
+                             double* __restrict__ xp) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) xp[k] = b[perm[k]];
+}
+
+// forward: (L+I) y = b over one tree level
+template <int NT>
+__global__ void __launch_bounds__(NT) k_fwd_level(LDLDev d, int task_base, double* __restrict__ xp) {
+  __shared__ double sy[CB_MAX_PANEL];
+  const int tid = threadIdx.x;
+  const int s = d.level_tasks[task_base + blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* __restrict__ us = d.u + rp;
+
+  for (int a = tid; a < nr; a += NT) us[a] = 0.0;
+  __syncthreads();
+  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
+    const int c = d.child_list[ci];
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* __restrict__ uc = d.u + crp;
+    const int* __restrict__ relc = d.rel + crp;
+    for (int a = tid; a < nrc; a += NT) {
+      const int r = relc[a];
+      const double v = uc[a];
+      if (r < ns) xp[f + r] += v; else us[r - ns] += v;
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < ns; j += NT) sy[j] = xp[f + j];
+  __syncthreads();
+  for (int j = 0; j + 1 < ns; j++) {
+    const double xj = sy[j];
+    for (int i = j + 1 + tid; i < ns; i += NT) sy[i] -= P[(long long)j * ld + i] * xj;
+    __syncthreads();
+  }
+  for (int j = tid; j < ns; j += NT) xp[f + j] = sy[j];
+  for (int a = tid; a < nr; a += NT) {
+    double acc = 0.0;
+    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * sy[j];
+    us[a] -= acc;
+  }
+}
+
+// backward: D (L+I)^T x = y over one tree level, fused inverse permutation
+template <int NT>
+__global__ void __launch_bounds__(NT) k_bwd_level(LDLDev d, int task_base, double* __restrict__ xp,
+                                                   double* __restrict__ out) {
+  __shared__ double st[CB_MAX_PANEL];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  const int s = d.level_tasks[task_base + blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  const int* __restrict__ rows = d.sn_rows + rp;
+
+  for (int j = warp; j < ns; j += nwarp) {
+    const double* __restrict__ cj = P + (long long)j * ld + ns;
+    double acc = 0.0;
+    for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
+  }
+  __syncthreads();
+  for (int j = ns - 1; j > 0; j--) {
+    const double xj = st[j];
+    for (int i = tid; i < j; i += NT) st[i] -= P[(long long)i * ld + j] * xj;
+    __syncthreads();
+  }
+  for (int j = tid; j < ns; j += NT) {
+    const double v = st[j];
+    xp[f + j] = v;
+    out[d.perm[f + j]] = v;
+  }
+}
+
+__global__ void k_update_values(double* __restrict__ vals, const int* __restrict__ idx,
+                                const double* __restrict__ v, long long len) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) vals[idx[i]] = v[i];
+}
+__global__ void k_scale_values(double* __restrict__ vals, const int* __restrict__ idx, double s,
+                               long long len) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) vals[idx[i]] *= s;
+}
+__global__ void k_offset_values(double* __restrict__ vals, const int* __restrict__ idx, double off,
+                                const signed char* __restrict__ sg, long long len) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) {
+    const int s = sg[i];
+    if (s > 0) vals[idx[i]] += off;
+    else if (s < 0) vals[idx[i]] -= off;
+  }
+}
+
+// ------------------------------------------------------------------------
+// host object
+// ------------------------------------------------------------------------
+
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) {                                                         \
+      std::fprintf(stderr, "[clarabel_b200] CUDA error %s at %s:%d\n",              \
+                   cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+      return CLDL_E_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+template <class T>
+static int upload(T** dptr, const std::vector<T>& v) {
+  size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+  CK(cudaMalloc((void**)dptr, bytes));
+  if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* Ax,
+                    const int8_t* dsigns, const cldl_opts& o, const int* perm_in) {
+  n = n_;
+  opts = o;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    std::fprintf(stderr, "[clarabel_b200] no CUDA device: this backend has no CPU fallback\n");
+    return CLDL_E_CUDA;
+  }
+  device = o.device;
+  CK(cudaSetDevice(device));
+  SymbolicOptions so;
+  so.ordering = o.ordering ? o.ordering : ORDER_BEST;
+  so.amd_dense_scale = o.amd_dense_scale > 0 ? o.amd_dense_scale : 1.5;
+  if (o.max_panel > 0) so.max_panel = o.max_panel > CB_MAX_PANEL ? CB_MAX_PANEL : o.max_panel;
+  if (o.nd_leaf > 0) so.nd_leaf = o.nd_leaf;
+  int rc = analyse(n, Ap, Ai, perm_in, so, S);
+  if (rc == -2) return CLDL_E_EMPTY_COLUMN;
+  if (rc == -3) return CLDL_E_NOT_TRIU;
+  if (rc == -5) return CLDL_E_BAD_PERM;
+  if (rc) return CLDL_E_ARG;
+
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaMallocHost((void**)&h_status, ST_COUNT * sizeof(int)));
+
+  int* tmp_i = nullptr;
+  long long* tmp_l = nullptr;
+  auto to_ll = [](const std::vector<int64_t>& v) { return std::vector<long long>(v.begin(), v.end()); };
+  if ((rc = upload(&tmp_i, S.sn_first))) return rc; dev.sn_first = tmp_i;
+  if ((rc = upload(&tmp_l, to_ll(S.sn_rowptr)))) return rc; dev.sn_rowptr = tmp_l;
+  if ((rc = upload(&tmp_i, S.sn_rows))) return rc; dev.sn_rows = tmp_i;
+  if ((rc = upload(&tmp_l, to_ll(S.child_ptr)))) return rc; dev.child_ptr = tmp_l;
+  if ((rc = upload(&tmp_i, S.child_list))) return rc; dev.child_list = tmp_i;
+  if ((rc = upload(&tmp_i, S.rel))) return rc; dev.rel = tmp_i;
+  if ((rc = upload(&tmp_l, to_ll(S.panel_off)))) return rc; dev.panel_off = tmp_l;
+  if ((rc = upload(&tmp_l, to_ll(S.upd_off)))) return rc; dev.upd_off = tmp_l;
+  if ((rc = upload(&tmp_l, to_ll(S.asm_ptr)))) return rc; dev.asm_ptr = tmp_l;
+  if ((rc = upload(&tmp_i, S.asm_src))) return rc; dev.asm_src = tmp_i;
+  if ((rc = upload(&tmp_l, to_ll(S.asm_dst)))) return rc; dev.asm_dst = tmp_l;
+  if ((rc = upload(&tmp_i, S.level_tasks))) return rc; dev.level_tasks = tmp_i;
+  if ((rc = upload(&tmp_i, S.perm))) return rc; dev.perm = tmp_i;
+  {
+    std::vector<signed char> ds(n);
+    for (int k = 0; k < n; k++) ds[k] = dsigns ? (signed char)dsigns[S.perm[k]] : (signed char)1;
+    signed char* t = nullptr;
+    if ((rc = upload(&t, ds))) return rc;
+    dev.dsigns = t;
+  }
+  nnzA = Ap[n];
+  CK(cudaMalloc((void**)&dev.vals, (size_t)(nnzA ? nnzA : 1) * sizeof(double)));
+  CK(cudaMemcpy(dev.vals, Ax, (size_t)nnzA * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&dev.L, (size_t)(S.nnzL_stored ? S.nnzL_stored : 1) * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.U, (size_t)(S.upd_total ? S.upd_total : 1) * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.D, (size_t)n * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.Dinv, (size_t)n * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.u, (size_t)(S.sn_rows.size() ? S.sn_rows.size() : 1) * sizeof(double)));
+  CK(cudaMalloc((void**)&d_xp, (size_t)n * sizeof(double)));
+  CK(cudaMalloc((void**)&d_bx, (size_t)2 * n * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.status, ST_COUNT * sizeof(int)));
+  CK(cudaMemset(dev.status, 0, ST_COUNT * sizeof(int)));
+  dev.reg_enable = o.regularize_enable;
+  dev.reg_eps = o.regularize_eps;
+  dev.reg_delta = o.regularize_delta;
+
+  // per-level launch plan: split each level by shared-memory class of the panel
+  int max_optin = 0;
+  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const int cap_big = (max_optin - 2048) / 8;  // doubles
+  CK(cudaFuncSetAttribute(k_factor_level<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          cap_big * 8));
+  const long long classes[3] = {1024, 5632, cap_big};  // 8 KB, 44 KB, ~225 KB panels
+  plan.clear();
+  for (int l = 0; l < S.nlevels; l++) {
+    int b = S.level_ptr[l], e = S.level_ptr[l + 1];
+    // tasks are sorted by front size descending; classify by panel size
+    auto psz = [&](int t) {
+      int s = S.level_tasks[t];
+      long long ns = S.sn_first[s + 1] - S.sn_first[s];
+      long long nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+      return (ns + nr) * ns;
+    };
+    // stable partition into classes while keeping order: gather indices per class
+    std::vector<int> order[4];
+    for (int t = b; t < e; t++) {
+      long long p = psz(t);
+      int c = p <= classes[0] ? 0 : p <= classes[1] ? 1 : p <= classes[2] ? 2 : 3;
+      order[c].push_back(S.level_tasks[t]);
+    }
+    int pos = b;
+    for (int c = 3; c >= 0; c--) {
+      if (order[c].empty()) continue;
+      LaunchSeg seg;
+      seg.level = l;
+      seg.base = pos;
+      seg.count = (int)order[c].size();
+      seg.smem_doubles = c == 3 ? 0 : (int)classes[c];
+      seg.threads = c == 0 ? 64 : 256;
+      plan.push_back(seg);
+      for (int s : order[c]) S.level_tasks[pos++] = s;
+    }
+  }
+  // level_tasks was re-ordered inside levels: re-upload
+  CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
+                cudaMemcpyHostToDevice));
+  factored = false;
+  return CLDL_OK;
+}
+
+void LDLObject::release() {
+  cudaSetDevice(device);
+  auto fr = [](const void* p) { if (p) cudaFree((void*)p); };
+  fr(dev.sn_first); fr(dev.sn_rowptr); fr(dev.sn_rows); fr(dev.child_ptr); fr(dev.child_list);
+  fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
+  fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
+  fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn);
+  if (h_status) cudaFreeHost(h_status);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int LDLObject::refactor_async() {
+  CK(cudaSetDevice(device));
+  CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
+  for (const LaunchSeg& g : plan) {
+    if (g.threads == 64)
+      k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
+    else
+      k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  factored = true;
+  return CLDL_OK;
+}
+
+int LDLObject::sync_status() {
+  CK(cudaSetDevice(device));
+  CK(cudaStreamSynchronize(stream));
+  regularize_count = (uint64_t)h_status[ST_REGCOUNT];
+  positive_inertia = (uint64_t)h_status[ST_POSINERTIA];
+  if (h_status[ST_ZEROPIV] && !dev.reg_enable) return CLDL_E_ZERO_PIVOT;
+  return h_status[ST_NONFINITE] ? 0 : 1;
+}
+
+int LDLObject::solve_async(double* d_x, const double* d_b) {
+  if (!factored) return CLDL_E_NOT_FACTORED;
+  CK(cudaSetDevice(device));
+  k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
+  for (int l = 0; l < S.nlevels; l++) {
+    int b = S.level_ptr[l], cnt = S.level_ptr[l + 1] - b;
+    k_fwd_level<128><<<cnt, 128, 0, stream>>>(dev, b, d_xp);
+  }
+  for (int l = S.nlevels - 1; l >= 0; l--) {
+    int b = S.level_ptr[l], cnt = S.level_ptr[l + 1] - b;
+    k_bwd_level<128><<<cnt, 128, 0, stream>>>(dev, b, d_xp, d_x);
+  }
+  CK(cudaGetLastError());
+  return CLDL_OK;
+}
+
+int LDLObject::ensure_tmp(size_t len) {
+  if (len <= tmp_cap) return 0;
+  CK(cudaSetDevice(device));
+  if (d_tmp_idx) cudaFree(d_tmp_idx);
+  if (d_tmp_val) cudaFree(d_tmp_val);
+  if (d_tmp_sgn) cudaFree(d_tmp_sgn);
+  tmp_cap = len + len / 2 + 256;
+  CK(cudaMalloc((void**)&d_tmp_idx, tmp_cap * sizeof(int)));
+  CK(cudaMalloc((void**)&d_tmp_val, tmp_cap * sizeof(double)));
+  CK(cudaMalloc((void**)&d_tmp_sgn, tmp_cap));
+  return 0;
+}
+
+int LDLObject::stage_index(const uint64_t* index, uint64_t len) {
+  int rc = ensure_tmp(len);
+  if (rc) return rc;
+  h_idx.resize(len);
+  for (uint64_t i = 0; i < len; i++) {
+    if (index[i] >= (uint64_t)nnzA) return CLDL_E_ARG;
+    h_idx[i] = (int)index[i];
+  }
+  CK(cudaMemcpyAsync(d_tmp_idx, h_idx.data(), len * sizeof(int), cudaMemcpyHostToDevice, stream));
+  return 0;
+}
+
+}  // namespace cb
+
+// ------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------
+using cb::LDLObject;
+
+struct cldl_handle { LDLObject obj; };
+
+extern "C" {
+
+void cldl_default_opts(cldl_opts* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->regularize_eps = 1e-13;    // default/settings.rs:155-158
+  o->regularize_delta = 2e-7;   // default/settings.rs:159-161
+  o->regularize_enable = 1;
+  o->amd_dense_scale = 1.5;
+  o->ordering = CLDL_ORDER_BEST;
+  o->device = 0;
+  o->max_panel = 0;
+  o->nd_leaf = 0;
+}
+
+int cldl_create(cldl_t** out, uint64_t n, const uint64_t* colptr, const uint64_t* rowval,
+                const double* nzval, const int8_t* dsigns, const cldl_opts* opts,
+                const uint64_t* perm_or_null) {
+  if (!out) return CLDL_E_ARG;
+  *out = nullptr;
+  if (!colptr || !rowval || !nzval || n == 0 || n > 0x7fffffffu) return CLDL_E_DIM;
+  cldl_opts o;
+  if (opts) o = *opts; else cldl_default_opts(&o);
+  uint64_t nnz = colptr[n];
+  if (nnz > 0x7fffffffu) return CLDL_E_DIM;
+  std::vector<int64_t> Ap(n + 1);
+  std::vector<int32_t> Ai(nnz);
+  for (uint64_t j = 0; j <= n; j++) Ap[j] = (int64_t)colptr[j];
+  for (uint64_t p = 0; p < nnz; p++) {
+    if (rowval[p] >= n) return CLDL_E_DIM;
+    Ai[p] = (int32_t)rowval[p];
+  }
+  std::vector<int> perm;
+  if (perm_or_null) {
+    perm.resize(n);
+    for (uint64_t k = 0; k < n; k++) {
+      if (perm_or_null[k] >= n) return CLDL_E_BAD_PERM;
+      perm[k] = (int)perm_or_null[k];
+    }
+  }
+  cldl_handle* h = new (std::nothrow) cldl_handle();
+  if (!h) return CLDL_E_ARG;
+  int rc = h->obj.init((int)n, Ap.data(), Ai.data(), nzval, dsigns, o,
+                       perm_or_null ? perm.data() : nullptr);
+  if (rc != CLDL_OK) {
+    h->obj.release();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return CLDL_OK;
+}
+
+void cldl_destroy(cldl_t* h) {
+  if (!h) return;
+  h->obj.release();
+  delete h;
+}
+
+int cldl_update_values(cldl_t* h, const uint64_t* index, const double* values, uint64_t len) {
+  if (!h) return CLDL_E_ARG;
+  if (len == 0) return CLDL_OK;
+  LDLObject& o = h->obj;
+  if (cudaSetDevice(o.device) != cudaSuccess) return CLDL_E_CUDA;
+  int rc = o.stage_index(index, len);
+  if (rc) return rc;
+  if (cudaMemcpyAsync(o.d_tmp_val, values, len * sizeof(double), cudaMemcpyHostToDevice, o.stream) != cudaSuccess)
+    return CLDL_E_CUDA;
+  cb::k_update_values<<<(unsigned)((len + 255) / 256), 256, 0, o.stream>>>(o.dev.vals, o.d_tmp_idx, o.d_tmp_val, (long long)len);
+  return cudaStreamSynchronize(o.stream) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+}
+
+int cldl_scale_values(cldl_t* h, const uint64_t* index, uint64_t len, double scale) {
+  if (!h) return CLDL_E_ARG;
+  if (len == 0) return CLDL_OK;
+  LDLObject& o = h->obj;
+  if (cudaSetDevice(o.device) != cudaSuccess) return CLDL_E_CUDA;
+  int rc = o.stage_index(index, len);
+  if (rc) return rc;
+  cb::k_scale_values<<<(unsigned)((len + 255) / 256), 256, 0, o.stream>>>(o.dev.vals, o.d_tmp_idx, scale, (long long)len);
+  return cudaStreamSynchronize(o.stream) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+}
+
+int cldl_offset_values(cldl_t* h, const uint64_t* index, uint64_t len, double offset,
+                       const int8_t* signs) {
+  if (!h || !signs) return CLDL_E_ARG;
+  if (len == 0) return CLDL_OK;
+  LDLObject& o = h->obj;
+  if (cudaSetDevice(o.device) != cudaSuccess) return CLDL_E_CUDA;
+  int rc = o.stage_index(index, len);
+  if (rc) return rc;
+  if (cudaMemcpyAsync(o.d_tmp_sgn, signs, len, cudaMemcpyHostToDevice, o.stream) != cudaSuccess)
+    return CLDL_E_CUDA;
+  cb::k_offset_values<<<(unsigned)((len + 255) / 256), 256, 0, o.stream>>>(o.dev.vals, o.d_tmp_idx, offset, o.d_tmp_sgn, (long long)len);
+  return cudaStreamSynchronize(o.stream) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+}
+
+int cldl_refactor(cldl_t* h) {
+  if (!h) return CLDL_E_ARG;
+  int rc = h->obj.refactor_async();
+  if (rc) return rc;
+  return h->obj.sync_status();
+}
+
+int cldl_solve(cldl_t* h, double* x, const double* b) {
+  if (!h || !x || !b) return CLDL_E_ARG;
+  LDLObject& o = h->obj;
+  if (!o.factored) return CLDL_E_NOT_FACTORED;
+  if (cudaSetDevice(o.device) != cudaSuccess) return CLDL_E_CUDA;
+  size_t bytes = (size_t)o.n * sizeof(double);
+  if (cudaMemcpyAsync(o.d_bx, b, bytes, cudaMemcpyHostToDevice, o.stream) != cudaSuccess) return CLDL_E_CUDA;
+  int rc = o.solve_async(o.d_bx + o.n, o.d_bx);
+  if (rc) return rc;
+  if (cudaMemcpyAsync(x, o.d_bx + o.n, bytes, cudaMemcpyDeviceToHost, o.stream) != cudaSuccess) return CLDL_E_CUDA;
+  return cudaStreamSynchronize(o.stream) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+}
+
+void cldl_info(const cldl_t* h, cldl_info_t* info) {
+  if (!h || !info) return;
+  const LDLObject& o = h->obj;
+  std::memset(info, 0, sizeof(*info));
+  std::strncpy(info->name, "cudaldl", sizeof(info->name) - 1);
+  info->threads = 0;
+  info->direct = 1;
+  info->nnzA = (uint64_t)o.nnzA;
+  info->nnzL = (uint64_t)o.S.nnzL_simplicial;
+  info->nnzL_stored = (uint64_t)o.S.nnzL_stored;
+  info->regularize_count = o.regularize_count;
+  info->positive_inertia = o.positive_inertia;
+  info->n_supernodes = (uint64_t)o.S.nsup;
+  info->n_levels = (uint64_t)o.S.nlevels;
+  info->flops = o.S.flops_stored;
+  info->ordering_used = o.S.ordering_used;
+}
+
+int cldl_get_perm(const cldl_t* h, uint64_t* perm_out) {
+  if (!h || !perm_out) return CLDL_E_ARG;
+  for (int k = 0; k < h->obj.n; k++) perm_out[k] = (uint64_t)h->obj.S.perm[k];
+  return CLDL_OK;
+}
+
+int cldl_update_values_dev(cldl_t* h, const int32_t* d_index, const double* d_values, uint64_t len) {
+  if (!h) return CLDL_E_ARG;
+  if (len == 0) return CLDL_OK;
+  LDLObject& o = h->obj;
+  if (cudaSetDevice(o.device) != cudaSuccess) return CLDL_E_CUDA;
+  cb::k_update_values<<<(unsigned)((len + 255) / 256), 256, 0, o.stream>>>(o.dev.vals, d_index, d_values, (long long)len);
+  return CLDL_OK;
+}
+
+int cldl_set_values_dev(cldl_t* h, const double* d_nzval) {
+  if (!h) return CLDL_E_ARG;
+  LDLObject& o = h->obj;
+  if (cudaSetDevice(o.device) != cudaSuccess) return CLDL_E_CUDA;
+  return cudaMemcpyAsync(o.dev.vals, d_nzval, (size_t)o.nnzA * sizeof(double), cudaMemcpyDeviceToDevice, o.stream) == cudaSuccess
+             ? CLDL_OK : CLDL_E_CUDA;
+}
+
+int cldl_refactor_dev(cldl_t* h) { return h ? h->obj.refactor_async() : CLDL_E_ARG; }
+int cldl_solve_dev(cldl_t* h, double* d_x, const double* d_b) {
+  return h ? h->obj.solve_async(d_x, d_b) : CLDL_E_ARG;
+}
+int cldl_sync_status(cldl_t* h) { return h ? h->obj.sync_status() : CLDL_E_ARG; }
+void* cldl_stream(cldl_t* h) { return h ? (void*)h->obj.stream : nullptr; }
+double* cldl_values_dev(cldl_t* h) { return h ? h->obj.dev.vals : nullptr; }
+
+double cldl_time_refactor_ms(cldl_t* h, int reps) {
+  if (!h || reps <= 0) return -1.0;
+  LDLObject& o = h->obj;
+  cudaSetDevice(o.device);
+  cudaStreamSynchronize(o.stream);
+  cudaEventRecord(o.ev0, o.stream);
+  for (int r = 0; r < reps; r++) o.refactor_async();
+  cudaEventRecord(o.ev1, o.stream);
+  cudaEventSynchronize(o.ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, o.ev0, o.ev1);
+  return (double)ms / reps;
+}
+
+double cldl_time_solve_ms(cldl_t* h, int reps) {
+  if (!h || reps <= 0 || !h->obj.factored) return -1.0;
+  LDLObject& o = h->obj;
+  cudaSetDevice(o.device);
+  cudaStreamSynchronize(o.stream);
+  cudaEventRecord(o.ev0, o.stream);
+  for (int r = 0; r < reps; r++) o.solve_async(o.d_bx + o.n, o.d_bx);
+  cudaEventRecord(o.ev1, o.stream);
+  cudaEventSynchronize(o.ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, o.ev0, o.ev1);
+  return (double)ms / reps;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Device-side view and host object of the multifrontal LDL^T (internal header).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "../../include/clarabel_b200.h"
+#include "symbolic.h"
+
+#define CB_MAX_PANEL 128
+
+namespace cb {
+
+enum { ST_REGCOUNT = 0, ST_ZEROPIV = 1, ST_POSINERTIA = 2, ST_NONFINITE = 3, ST_COUNT = 8 };
+
+// Plain-pointer bundle passed by value to kernels.
+struct LDLDev {
+  const int* sn_first = nullptr;
+  const long long* sn_rowptr = nullptr;
+  const int* sn_rows = nullptr;
+  const long long* child_ptr = nullptr;
+  const int* child_list = nullptr;
+  const int* rel = nullptr;  // indexed like sn_rows
+  const long long* panel_off = nullptr;
+  const long long* upd_off = nullptr;
+  const long long* asm_ptr = nullptr;
+  const int* asm_src = nullptr;
+  const long long* asm_dst = nullptr;
+  const int* level_tasks = nullptr;
+  const int* perm = nullptr;
+  const signed char* dsigns = nullptr;  // permuted order
+  double* vals = nullptr;               // KKT values, caller's CSC order
+  double* L = nullptr;                  // dense panels
+  double* U = nullptr;                  // update-matrix arena
+  double* D = nullptr;
+  double* Dinv = nullptr;
+  double* u = nullptr;                  // per-front update vectors for the solves
+  int* status = nullptr;
+  double reg_eps = 1e-13, reg_delta = 2e-7;
+  int reg_enable = 1;
+};
+
+struct LaunchSeg {
+  int level, base, count, smem_doubles, threads;
+};
+
+class LDLObject {
+ public:
+  int n = 0;
+  int64_t nnzA = 0;
+  int device = 0;
+  cldl_opts opts{};
+  Symbolic S;
+  LDLDev dev;
+  std::vector<LaunchSeg> plan;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int* h_status = nullptr;
+  double* d_xp = nullptr;  // permuted work vector
+  double* d_bx = nullptr;  // staging for host-pointer solve: [b ; x]
+  int* d_tmp_idx = nullptr;
+  double* d_tmp_val = nullptr;
+  signed char* d_tmp_sgn = nullptr;
+  size_t tmp_cap = 0;
+  std::vector<int> h_idx;
+  bool factored = false;
+  uint64_t regularize_count = 0, positive_inertia = 0;
+
+  int init(int n, const int64_t* Ap, const int32_t* Ai, const double* Ax, const int8_t* dsigns,
+           const cldl_opts& o, const int* perm_in);
+  void release();
+  int refactor_async();
+  int sync_status();
+  int solve_async(double* d_x, const double* d_b);
+  int ensure_tmp(size_t len);
+  int stage_index(const uint64_t* index, uint64_t len);
+};
+
+}  // namespace cb

@@ -1,0 +1,492 @@
+// Fill-reducing orderings for the quasidefinite KKT matrix (host side, one-time).
+//
+// Replaces the reference's call into the third-party `amd` crate
+// (/root/reference/src/qdldl/qdldl.rs:905-917, dense scale 1.5 from
+// ldlsolvers/qdldl.rs:41).  Written from the published algorithm
+// (Amestoy, Davis, Duff, "An approximate minimum degree ordering algorithm",
+// SIMAX 1996): quotient graph, approximate external degrees, element
+// absorption, mass elimination and supervariable detection by hashing.
+//
+// On top of it: a nested-dissection driver (George's automatic ND with BFS
+// level structures) used to get a *short, bushy* elimination tree, which is
+// what the level-scheduled device factorisation and solves want.  The
+// reference has no equivalent; any valid permutation yields a valid LDL^T and
+// the parity tests run the oracle on the very same permutation.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+namespace cb {
+
+namespace {
+
+// Build the full symmetric adjacency (no diagonal, no duplicates) of a triu CSC.
+void full_adjacency(int n, const int64_t* Ap, const int32_t* Ai,
+                    std::vector<int64_t>& xadj, std::vector<int>& adj) {
+  std::vector<int64_t> cnt(n + 1, 0);
+  for (int j = 0; j < n; j++)
+    for (int64_t p = Ap[j]; p < Ap[j + 1]; p++) {
+      int i = Ai[p];
+      if (i != j) { cnt[i + 1]++; cnt[j + 1]++; }
+    }
+  xadj.assign(n + 1, 0);
+  for (int i = 0; i < n; i++) xadj[i + 1] = xadj[i] + cnt[i + 1];
+  adj.resize(xadj[n]);
+  std::vector<int64_t> pos(xadj.begin(), xadj.end() - 1);
+  for (int j = 0; j < n; j++)
+    for (int64_t p = Ap[j]; p < Ap[j + 1]; p++) {
+      int i = Ai[p];
+      if (i != j) { adj[pos[i]++] = j; adj[pos[j]++] = i; }
+    }
+  // sort + unique per row
+  std::vector<int64_t> nx(n + 1, 0);
+  int64_t w = 0;
+  for (int i = 0; i < n; i++) {
+    int64_t b = xadj[i], e = xadj[i + 1];
+    std::sort(adj.begin() + b, adj.begin() + e);
+    nx[i] = w;
+    int last = -1;
+    for (int64_t p = b; p < e; p++)
+      if (adj[p] != last) { adj[w++] = adj[p]; last = adj[p]; }
+  }
+  nx[n] = w;
+  adj.resize(w);
+  xadj.swap(nx);
+}
+
+enum : uint8_t { ST_VAR = 0, ST_ELEM = 1, ST_DEAD_ELEM = 2, ST_ABSORBED = 3, ST_DENSE = 4 };
+
+}  // namespace
+
+// Approximate minimum degree on a general undirected graph given as CSR
+// adjacency (xadj/adj).  `order` receives the elimination sequence (perm:
+// order[k] = vertex eliminated k-th).
+void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adjncy,
+               double dense_scale, std::vector<int>& order) {
+  order.clear();
+  order.reserve(n);
+  if (n == 0) return;
+
+  std::vector<std::vector<int>> adj(n), elems(n), Le(n);
+  std::vector<int> nv(n, 1), degree(n), esize(n, 0);
+  std::vector<uint8_t> status(n, ST_VAR);
+  std::vector<int> sv_next(n, -1), sv_tail(n);  // absorbed-variable chains
+  std::vector<int64_t> w(n, 0);
+  int64_t wflg = 1;
+  for (int i = 0; i < n; i++) sv_tail[i] = i;
+
+  // "dense" rows are withheld and ordered last (AMD's dense-row rule:
+  // threshold max(16, 10*scale*sqrt(n)))
+  double dense = 10.0 * dense_scale * std::sqrt((double)n);
+  if (dense < 16.0) dense = 16.0;
+  std::vector<int> dense_nodes;
+  for (int i = 0; i < n; i++) {
+    int d = (int)(xadj[i + 1] - xadj[i]);
+    if ((double)d > dense) { status[i] = ST_DENSE; dense_nodes.push_back(i); }
+  }
+  for (int i = 0; i < n; i++) {
+    if (status[i] == ST_DENSE) continue;
+    auto& a = adj[i];
+    a.reserve(xadj[i + 1] - xadj[i]);
+    for (int64_t p = xadj[i]; p < xadj[i + 1]; p++)
+      if (status[adjncy[p]] != ST_DENSE) a.push_back(adjncy[p]);
+    degree[i] = (int)a.size();
+  }
+
+  // degree buckets
+  std::vector<int> head(n + 1, -1), nxt(n, -1), prv(n, -1);
+  auto bucket_insert = [&](int i, int d) {
+    nxt[i] = head[d]; prv[i] = -1;
+    if (head[d] >= 0) prv[head[d]] = i;
+    head[d] = i;
+  };
+  auto bucket_remove = [&](int i, int d) {
+    if (prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[d] = nxt[i];
+    if (nxt[i] >= 0) prv[nxt[i]] = prv[i];
+  };
+  int nlive = 0;
+  for (int i = n - 1; i >= 0; i--)
+    if (status[i] == ST_VAR) { bucket_insert(i, degree[i]); nlive++; }
+
+  int nel = 0, mindeg = 0;
+  const int ntot = nlive;
+  std::vector<int> Lp, bucket_of_hash(n, -1), hnext(n, -1);
+  std::vector<unsigned> hashv(n, 0);
+  std::vector<int> touched_hash;
+  std::vector<int> tmp;
+
+  while (nel < ntot) {
+    while (mindeg <= n && head[mindeg] < 0) mindeg++;
+    int p = head[mindeg];
+    bucket_remove(p, mindeg);
+    int nvpiv = nv[p];
+    nel += nvpiv;
+    nv[p] = -nvpiv;
+
+    // ---- form the new element Lp ----
+    Lp.clear();
+    int degme = 0;
+    auto take = [&](int i) {
+      if (status[i] == ST_VAR && nv[i] > 0) {
+        degme += nv[i];
+        nv[i] = -nv[i];
+        Lp.push_back(i);
+        bucket_remove(i, degree[i]);
+      }
+    };
+    for (int i : adj[p]) take(i);
+    for (int e : elems[p])
+      if (status[e] == ST_ELEM) {
+        for (int i : Le[e]) take(i);
+        status[e] = ST_DEAD_ELEM;
+        std::vector<int>().swap(Le[e]);
+      }
+    status[p] = ST_ELEM;
+    std::vector<int>().swap(adj[p]);
+    std::vector<int>().swap(elems[p]);
+
+    // ---- |Le \ Lp| for every element touching Lp ----
+    if (wflg > (int64_t)4e18) { std::fill(w.begin(), w.end(), 0); wflg = 1; }
+    for (int i : Lp) {
+      int nvi = -nv[i];
+      for (int e : elems[i]) {
+        if (status[e] != ST_ELEM) continue;
+        if (w[e] >= wflg) w[e] -= nvi;
+        else w[e] = (int64_t)esize[e] + wflg - nvi;
+      }
+    }
+
+    // ---- degree update, pruning, hashing ----
+    touched_hash.clear();
+    for (int i : Lp) {
+      int nvi = -nv[i];
+      int64_t deg = 0;
+      unsigned h = 0;
+      auto& ei = elems[i];
+      size_t k = 0;
+      for (size_t t = 0; t < ei.size(); t++) {
+        int e = ei[t];
+        if (status[e] != ST_ELEM) continue;
+        int64_t dext = w[e] - wflg;
+        if (dext > 0) { deg += dext; ei[k++] = e; h += (unsigned)e; }
+        else { status[e] = ST_DEAD_ELEM; std::vector<int>().swap(Le[e]); }  // aggressive absorption
+      }
+      ei.resize(k);
+      auto& ai = adj[i];
+      k = 0;
+      for (size_t t = 0; t < ai.size(); t++) {
+        int j = ai[t];
+        if (status[j] == ST_VAR && nv[j] > 0) { deg += nv[j]; ai[k++] = j; h += (unsigned)j; }
+      }
+      ai.resize(k);
+      if (ei.empty() && ai.empty()) {
+        // mass elimination: i has no neighbours outside Lp
+        degme -= nvi; nvpiv += nvi; nel += nvi;
+        nv[i] = 0; status[i] = ST_ABSORBED;
+        sv_next[sv_tail[p]] = i; sv_tail[p] = sv_tail[i];
+      } else {
+        degree[i] = (int)std::min<int64_t>(degree[i], deg);
+        ei.push_back(p);
+        h += (unsigned)p;
+        h %= (unsigned)n;
+        hashv[i] = h;
+        if (bucket_of_hash[h] < 0) touched_hash.push_back((int)h);
+        hnext[i] = bucket_of_hash[h];
+        bucket_of_hash[h] = i;
+      }
+    }
+    wflg += (int64_t)n + 1;  // invalidate all w[e]
+
+    // ---- supervariable detection within hash buckets ----
+    for (int h : touched_hash) {
+      int i = bucket_of_hash[h];
+      bucket_of_hash[h] = -1;
+      for (; i >= 0; i = hnext[i]) {
+        if (nv[i] == 0) continue;
+        // tag i's lists
+        wflg++;
+        for (int e : elems[i]) w[e] = wflg;
+        for (int j : adj[i]) w[j] = wflg;
+        int prev = i;
+        for (int j = hnext[i]; j >= 0; j = hnext[j]) {
+          bool same = nv[j] != 0 && elems[j].size() == elems[i].size() &&
+                      adj[j].size() == adj[i].size();
+          if (same) for (int e : elems[j]) if (w[e] != wflg) { same = false; break; }
+          if (same) for (int v : adj[j]) if (w[v] != wflg) { same = false; break; }
+          if (same) {
+            nv[i] += nv[j];  // both negative here
+            nv[j] = 0; status[j] = ST_ABSORBED;
+            std::vector<int>().swap(adj[j]); std::vector<int>().swap(elems[j]);
+            sv_next[sv_tail[i]] = j; sv_tail[i] = sv_tail[j];
+            hnext[prev] = hnext[j];
+          } else prev = j;
+        }
+      }
+    }
+    wflg += (int64_t)n + 1;
+
+    // ---- finalise element p, restore degree lists ----
+    auto& Lpe = Le[p];
+    Lpe.clear();
+    for (int i : Lp) {
+      int nvi = -nv[i];
+      if (nvi <= 0) continue;
+      nv[i] = nvi;
+      int64_t deg = (int64_t)degree[i] + degme - nvi;
+      deg = std::min<int64_t>(deg, (int64_t)ntot - nel - nvi);
+      if (deg < 0) deg = 0;
+      degree[i] = (int)deg;
+      bucket_insert(i, degree[i]);
+      if (degree[i] < mindeg) mindeg = degree[i];
+      Lpe.push_back(i);
+    }
+    nv[p] = nvpiv;
+    esize[p] = degme;
+    if (degme == 0) { status[p] = ST_DEAD_ELEM; std::vector<int>().swap(Le[p]); }
+
+    // emit p and everything absorbed into it
+    for (int v = p; v >= 0; v = sv_next[v]) order.push_back(v);
+  }
+  // dense rows last, lowest degree first
+  std::sort(dense_nodes.begin(), dense_nodes.end(), [&](int a, int b) {
+    int64_t da = xadj[a + 1] - xadj[a], db = xadj[b + 1] - xadj[b];
+    return da != db ? da < db : a < b;
+  });
+  for (int v : dense_nodes) order.push_back(v);
+}
+
+void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
+               std::vector<int>& perm) {
+  std::vector<int64_t> xadj;
+  std::vector<int> adj;
+  full_adjacency(n, Ap, Ai, xadj, adj);
+  amd_graph(n, xadj, adj, dense_scale, perm);
+}
+
+// ---------------------------------------------------------------------------
+// Nested dissection (BFS level-structure bisection) with AMD on the leaves.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct NDWork {
+  const std::vector<int64_t>* xadj;
+  const std::vector<int>* adj;
+  std::vector<int> part;   // current region id per vertex (-1 = already ordered / separator)
+  std::vector<int> level;  // BFS scratch
+  std::vector<int> queue;
+  std::vector<int> local;  // global -> local index scratch
+};
+
+// BFS restricted to vertices with part[v]==region; returns eccentricity, fills
+// queue (visit order) and level[].
+int bfs(NDWork& W, int root, int region, const std::vector<int>& verts) {
+  const int stamp_base = 0;
+  for (int v : verts) W.level[v] = -1;
+  auto& q = W.queue;
+  q.clear();
+  q.push_back(root);
+  W.level[root] = stamp_base;
+  size_t headp = 0;
+  int maxl = stamp_base;
+  while (headp < q.size()) {
+    int v = q[headp++];
+    int lv = W.level[v];
+    for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+      int u = (*W.adj)[p];
+      if (W.part[u] == region && W.level[u] < stamp_base) {
+        W.level[u] = lv + 1;
+        if (lv + 1 > maxl) maxl = lv + 1;
+        q.push_back(u);
+      }
+    }
+  }
+  return maxl - stamp_base;
+}
+
+}  // namespace
+
+void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
+              int leaf_size, std::vector<int>& perm) {
+  std::vector<int64_t> xadj;
+  std::vector<int> adj;
+  full_adjacency(n, Ap, Ai, xadj, adj);
+  perm.clear();
+  perm.reserve(n);
+  if (n == 0) return;
+
+  // withhold dense rows exactly like AMD does; they go last
+  double dense = 10.0 * dense_scale * std::sqrt((double)n);
+  if (dense < 16.0) dense = 16.0;
+  NDWork W;
+  W.xadj = &xadj; W.adj = &adj;
+  W.part.assign(n, 0);
+  W.level.assign(n, -1);
+  W.local.assign(n, -1);
+  std::vector<int> dense_nodes;
+  for (int i = 0; i < n; i++)
+    if ((double)(xadj[i + 1] - xadj[i]) > dense) { W.part[i] = -1; dense_nodes.push_back(i); }
+
+  // Explicit recursion stack of regions.  Each region is a vertex list; the
+  // output is assembled as: [left..., right..., separator] per region, with
+  // separators emitted after both halves (post-order), so we build a tree of
+  // "emit" actions and flatten it at the end.
+  struct Node { std::vector<int> verts; int left = -1, right = -1; std::vector<int> sep; bool leaf = false; };
+  std::vector<Node> nodes;
+  int next_region = 1;
+  const int stamp = 0;
+
+  // initial connected components become independent roots
+  std::vector<int> roots;
+  {
+    std::vector<char> seen(n, 0);
+    for (int s = 0; s < n; s++) {
+      if (seen[s] || W.part[s] != 0) continue;
+      Node nd;
+      std::vector<int> st{s};
+      seen[s] = 1;
+      while (!st.empty()) {
+        int v = st.back(); st.pop_back();
+        nd.verts.push_back(v);
+        for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+          int u = adj[p];
+          if (!seen[u] && W.part[u] == 0) { seen[u] = 1; st.push_back(u); }
+        }
+      }
+      roots.push_back((int)nodes.size());
+      nodes.push_back(std::move(nd));
+    }
+  }
+
+  std::vector<int> work = roots;
+  while (!work.empty()) {
+    int id = work.back(); work.pop_back();
+    if ((int)nodes[id].verts.size() <= leaf_size) { nodes[id].leaf = true; continue; }
+    int region = next_region++;
+    for (int v : nodes[id].verts) W.part[v] = region;
+    // pseudo-peripheral root: a few BFS sweeps
+    int root = nodes[id].verts[0];
+    int ecc = -1;
+    for (int it = 0; it < 4; it++) {
+      int e = bfs(W, root, region, nodes[id].verts);
+      if ((int)W.queue.size() != (int)nodes[id].verts.size()) break;  // disconnected: handled below
+      if (e <= ecc) break;
+      ecc = e;
+      // farthest vertex of minimum degree in last level
+      int best = W.queue.back();
+      int64_t bestdeg = INT64_MAX;
+      for (size_t t = W.queue.size(); t-- > 0;) {
+        int v = W.queue[t];
+        if (W.level[v] - stamp != e) break;
+        int64_t d = xadj[v + 1] - xadj[v];
+        if (d < bestdeg) { bestdeg = d; best = v; }
+      }
+      root = best;
+    }
+    int e = bfs(W, root, region, nodes[id].verts);
+    size_t reached = W.queue.size();
+    size_t total = nodes[id].verts.size();
+    Node L, R;
+    std::vector<int> sep;
+    if (reached < total) {
+      // region fell apart (a separator disconnected it): split by component
+      for (int v : W.queue) { L.verts.push_back(v); W.part[v] = -2; }
+      for (int v : nodes[id].verts) if (W.part[v] == region) R.verts.push_back(v);
+    } else if (e < 2) {
+      nodes[id].leaf = true;  // clique-like, cannot bisect
+      continue;
+    } else {
+      // choose the level that balances vertex counts on both sides
+      std::vector<int64_t> cntl(e + 1, 0);
+      for (int v : W.queue) cntl[W.level[v] - stamp]++;
+      int64_t half = (int64_t)total / 2, acc = 0;
+      int cut = 1;
+      for (int l = 0; l <= e; l++) {
+        acc += cntl[l];
+        if (acc >= half) { cut = l; break; }
+      }
+      if (cut < 1) cut = 1;
+      if (cut > e - 1) cut = e - 1;
+      // pick the thinner of the neighbouring levels around the balance point
+      if (cut + 1 <= e - 1 && cntl[cut + 1] < cntl[cut]) {
+        int64_t below = acc;  // vertices in levels <= cut
+        if (std::llabs(2 * below - (int64_t)total) < (int64_t)total / 2) cut = cut + 1;
+      }
+      // separator = vertices of level `cut` that have a neighbour in level cut+1
+      for (int v : W.queue) {
+        int lv = W.level[v] - stamp;
+        if (lv < cut) L.verts.push_back(v);
+        else if (lv > cut) R.verts.push_back(v);
+        else {
+          bool touches = false;
+          for (int64_t p = xadj[v]; p < xadj[v + 1] && !touches; p++) {
+            int u = adj[p];
+            if (W.part[u] == region && W.level[u] - stamp == cut + 1) touches = true;
+          }
+          if (touches) sep.push_back(v); else L.verts.push_back(v);
+        }
+      }
+    }
+    for (int v : sep) W.part[v] = -1;
+    nodes[id].sep = std::move(sep);
+    std::vector<int>().swap(nodes[id].verts);
+    int li = (int)nodes.size(); nodes.push_back(std::move(L));
+    int ri = (int)nodes.size(); nodes.push_back(std::move(R));
+    nodes[id].left = li; nodes[id].right = ri;
+    // children regions need fresh part ids; mark their vertices as "unassigned" (0)
+    for (int v : nodes[li].verts) W.part[v] = 0;
+    for (int v : nodes[ri].verts) W.part[v] = 0;
+    work.push_back(li);
+    work.push_back(ri);
+  }
+
+  // order leaves with AMD on the induced subgraph; emit post-order
+  std::vector<int64_t> sx;
+  std::vector<int> sa, lorder;
+  auto emit_leaf = [&](const std::vector<int>& verts) {
+    int m = (int)verts.size();
+    if (m == 0) return;
+    if (m <= 2) { for (int v : verts) perm.push_back(v); return; }
+    for (int k = 0; k < m; k++) W.local[verts[k]] = k;
+    sx.assign(m + 1, 0);
+    sa.clear();
+    for (int k = 0; k < m; k++) {
+      int v = verts[k];
+      for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+        int u = adj[p];
+        if (W.local[u] >= 0) sa.push_back(W.local[u]);
+      }
+      sx[k + 1] = (int64_t)sa.size();
+    }
+    amd_graph(m, sx, sa, 1e9, lorder);
+    for (int k : lorder) perm.push_back(verts[k]);
+    for (int k = 0; k < m; k++) W.local[verts[k]] = -1;
+  };
+  // iterative post-order
+  struct Fr { int id; int stage; };
+  for (int r : roots) {
+    std::vector<Fr> st{{r, 0}};
+    while (!st.empty()) {
+      Fr f = st.back(); st.pop_back();
+      Node& nd = nodes[f.id];
+      if (nd.leaf || nd.left < 0) { emit_leaf(nd.verts); continue; }
+      if (f.stage == 0) {
+        st.push_back({f.id, 1});
+        st.push_back({nd.right, 0});
+        st.push_back({nd.left, 0});
+      } else {
+        emit_leaf(nd.sep);
+      }
+    }
+  }
+  std::sort(dense_nodes.begin(), dense_nodes.end(), [&](int a, int b) {
+    int64_t da = xadj[a + 1] - xadj[a], db = xadj[b + 1] - xadj[b];
+    return da != db ? da < db : a < b;
+  });
+  for (int v : dense_nodes) perm.push_back(v);
+}
+
+}  // namespace cb

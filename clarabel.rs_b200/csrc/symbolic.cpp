@@ -1,0 +1,436 @@
+// Symbolic analysis: see symbolic.h.  All integer work, host only, one-time.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <numeric>
+
+namespace cb {
+
+namespace {
+
+// Upper-triangular CSC pattern of P A P^T (columns sorted) from the caller's
+// triu CSC and iperm (old -> new).
+void permuted_upper(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<int>& iperm,
+                    std::vector<int64_t>& Up, std::vector<int>& Ui) {
+  Up.assign(n + 1, 0);
+  for (int c = 0; c < n; c++)
+    for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
+      int a = iperm[Ai[p]], b = iperm[c];
+      Up[(a > b ? a : b) + 1]++;
+    }
+  for (int j = 0; j < n; j++) Up[j + 1] += Up[j];
+  Ui.resize(Up[n]);
+  std::vector<int64_t> pos(Up.begin(), Up.end() - 1);
+  for (int c = 0; c < n; c++)
+    for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
+      int a = iperm[Ai[p]], b = iperm[c];
+      int col = a > b ? a : b, row = a > b ? b : a;
+      Ui[pos[col]++] = row;
+    }
+  for (int j = 0; j < n; j++) std::sort(Ui.begin() + Up[j], Ui.begin() + Up[j + 1]);
+}
+
+// Liu's elimination tree with path compression, from upper-triangular columns.
+void etree_upper(int n, const std::vector<int64_t>& Up, const std::vector<int>& Ui,
+                 std::vector<int>& parent) {
+  parent.assign(n, -1);
+  std::vector<int> anc(n, -1);
+  for (int k = 0; k < n; k++)
+    for (int64_t p = Up[k]; p < Up[k + 1]; p++) {
+      int i = Ui[p];
+      while (i != -1 && i < k) {
+        int nx = anc[i];
+        anc[i] = k;
+        if (nx == -1) parent[i] = k;
+        i = nx;
+      }
+    }
+}
+
+// Post-order of a forest; children visited in ascending subtree size so the
+// heaviest child ends up adjacent to its parent (longer supernode chains).
+void postorder(int n, const std::vector<int>& parent, std::vector<int>& post) {
+  std::vector<int> size(n, 1);
+  for (int j = 0; j < n; j++)
+    if (parent[j] >= 0) size[parent[j]] += size[j];  // valid: parent[j] > j
+  std::vector<int> cptr(n + 2, 0), clist(n);
+  for (int j = 0; j < n; j++) cptr[(parent[j] < 0 ? n : parent[j]) + 1]++;
+  for (int j = 0; j <= n; j++) cptr[j + 1] += cptr[j];
+  {
+    std::vector<int> pos(cptr.begin(), cptr.end() - 1);
+    for (int j = 0; j < n; j++) clist[pos[parent[j] < 0 ? n : parent[j]]++] = j;
+  }
+  for (int j = 0; j <= n; j++)
+    std::stable_sort(clist.begin() + cptr[j], clist.begin() + cptr[j + 1],
+                     [&](int a, int b) { return size[a] < size[b]; });
+  post.clear();
+  post.reserve(n);
+  std::vector<int> stack, it(n + 1, 0);
+  for (int r = cptr[n]; r < cptr[n + 1]; r++) {
+    stack.push_back(clist[r]);
+    while (!stack.empty()) {
+      int v = stack.back();
+      if (it[v] < cptr[v + 1] - cptr[v]) {
+        stack.push_back(clist[cptr[v] + it[v]++]);
+      } else {
+        post.push_back(v);
+        stack.pop_back();
+      }
+    }
+  }
+}
+
+// Gilbert-Ng-Peyton column counts for a post-ordered matrix (post == identity).
+// Lo_ptr/Lo_idx: for each column j the rows i > j with A_ij != 0.
+void colcounts_postordered(int n, const std::vector<int>& parent, const std::vector<int64_t>& Lo_ptr,
+                           const std::vector<int>& Lo_idx, std::vector<int>& cc) {
+  std::vector<int> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), anc(n);
+  std::vector<int64_t> delta(n, 0);
+  for (int k = 0; k < n; k++) {
+    int j = k;
+    delta[j] = (first[j] == -1) ? 1 : 0;
+    for (; j != -1 && first[j] == -1; j = parent[j]) first[j] = k;
+  }
+  std::iota(anc.begin(), anc.end(), 0);
+  for (int j = 0; j < n; j++) {
+    if (parent[j] != -1) delta[parent[j]]--;
+    for (int64_t p = Lo_ptr[j]; p < Lo_ptr[j + 1]; p++) {
+      int i = Lo_idx[p];
+      if (i <= j || first[j] <= maxfirst[i]) continue;
+      maxfirst[i] = first[j];
+      int jprev = prevleaf[i];
+      prevleaf[i] = j;
+      delta[j]++;
+      if (jprev != -1) {
+        int q = jprev;
+        while (q != anc[q]) q = anc[q];
+        for (int s = jprev; s != q;) { int sp = anc[s]; anc[s] = q; s = sp; }
+        delta[q]--;
+      }
+    }
+    if (parent[j] != -1) anc[j] = parent[j];
+  }
+  for (int j = 0; j < n; j++)
+    if (parent[j] != -1) delta[parent[j]] += delta[j];
+  cc.resize(n);
+  for (int j = 0; j < n; j++) cc[j] = (int)(delta[j] - 1);  // strictly-lower count
+}
+
+struct Eval { double flops; int64_t nnzL; };
+
+}  // namespace
+
+static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<int>& perm0,
+                 const SymbolicOptions& opt, Symbolic& S, bool stats_only) {
+  S.n = n;
+  S.nnzA = Ap[n];
+  std::vector<int> iperm0(n);
+  for (int k = 0; k < n; k++) iperm0[perm0[k]] = k;
+
+  std::vector<int64_t> Up;
+  std::vector<int> Ui, parent0, post;
+  permuted_upper(n, Ap, Ai, iperm0, Up, Ui);
+  etree_upper(n, Up, Ui, parent0);
+  postorder(n, parent0, post);
+  S.perm.resize(n);
+  S.iperm.resize(n);
+  for (int k = 0; k < n; k++) S.perm[k] = perm0[post[k]];
+  for (int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+
+  permuted_upper(n, Ap, Ai, S.iperm, Up, Ui);
+  etree_upper(n, Up, Ui, S.parent);
+  const std::vector<int>& parent = S.parent;
+
+  // strictly-lower pattern by columns (transpose of strict upper)
+  std::vector<int64_t> Lo_ptr(n + 1, 0);
+  for (int k = 0; k < n; k++)
+    for (int64_t p = Up[k]; p < Up[k + 1]; p++)
+      if (Ui[p] != k) Lo_ptr[Ui[p] + 1]++;
+  for (int j = 0; j < n; j++) Lo_ptr[j + 1] += Lo_ptr[j];
+  std::vector<int> Lo_idx(Lo_ptr[n]);
+  {
+    std::vector<int64_t> pos(Lo_ptr.begin(), Lo_ptr.end() - 1);
+    for (int k = 0; k < n; k++)
+      for (int64_t p = Up[k]; p < Up[k + 1]; p++)
+        if (Ui[p] != k) Lo_idx[pos[Ui[p]]++] = k;
+  }
+  colcounts_postordered(n, parent, Lo_ptr, Lo_idx, S.colcount);
+  S.nnzL_simplicial = 0;
+  S.flops_simplicial = 0;
+  for (int j = 0; j < n; j++) {
+    S.nnzL_simplicial += S.colcount[j];
+    S.flops_simplicial += (double)S.colcount[j] * ((double)S.colcount[j] + 3.0);
+  }
+
+  // ---- supernode partition: fundamental -> relaxed -> split ----
+  const std::vector<int>& cc = S.colcount;
+  std::vector<int> sfirst;  // start column of every supernode
+  {
+    // fundamental (structure-nested chains)
+    std::vector<int> fs;   // first col
+    for (int j = 0; j < n; j++) {
+      bool join = j > 0 && parent[j - 1] == j && cc[j] == cc[j - 1] - 1;
+      if (!join) fs.push_back(j);
+    }
+    int nf = (int)fs.size();
+    fs.push_back(n);
+    // relaxed amalgamation along "last child" links (contiguous columns)
+    std::vector<int> start(fs.begin(), fs.end() - 1);  // may move left on merge
+    std::vector<double> zeros(nf, 0.0);
+    std::vector<char> dead(nf, 0);
+    std::vector<int> col2f(n);
+    for (int s = 0; s < nf; s++)
+      for (int j = fs[s]; j < fs[s + 1]; j++) col2f[j] = s;
+    for (int p = 0; p < nf; p++) {
+      int lastcol = fs[p + 1] - 1;
+      int nr_p = cc[lastcol];
+      while (start[p] > 0) {
+        int c = col2f[start[p] - 1];        // supernode ending right before p
+        int c_last = fs[c + 1] - 1;
+        if (parent[c_last] < start[p] || parent[c_last] > lastcol) break;  // not a child of p
+        int ns_c = fs[c + 1] - start[c];
+        int ns_p = lastcol + 1 - start[p];
+        int nr_c = cc[c_last];              // rows below c's block (into p and beyond)
+        double newz = (double)ns_c * (double)(ns_p + nr_p - nr_c);
+        double z = zeros[p] + zeros[c] + newz;
+        int ns_m = ns_c + ns_p;
+        double size_m = (double)ns_m * (double)(ns_m + 1) * 0.5 + (double)ns_m * nr_p;
+        bool merge = (ns_m <= opt.relax_small) || (z <= opt.relax_zeros * size_m);
+        if (!merge) break;
+        zeros[p] = z;
+        start[p] = start[c];
+        dead[c] = 1;
+        // columns of c now belong to p
+        for (int j = start[c]; j < fs[c + 1]; j++) col2f[j] = p;
+      }
+    }
+    for (int s = 0; s < nf; s++) {
+      if (dead[s]) continue;
+      int b = start[s], e = fs[s + 1];
+      // split into panels of at most max_panel columns (balanced widths)
+      int w = e - b;
+      int np = (w + opt.max_panel - 1) / opt.max_panel;
+      for (int k = 0; k < np; k++) sfirst.push_back(b + (int)((int64_t)w * k / np));
+    }
+    std::sort(sfirst.begin(), sfirst.end());
+  }
+  int nsup = (int)sfirst.size();
+  S.nsup = nsup;
+  S.sn_first = sfirst;
+  S.sn_first.push_back(n);
+  S.col2sn.resize(n);
+  for (int s = 0; s < nsup; s++)
+    for (int j = S.sn_first[s]; j < S.sn_first[s + 1]; j++) S.col2sn[j] = s;
+
+  // ---- row structures by bottom-up union, parents by min row ----
+  S.sn_rowptr.assign(nsup + 1, 0);
+  S.sn_rows.clear();
+  S.sn_parent.assign(nsup, -1);
+  std::vector<std::vector<int>> kids(nsup);
+  {
+    std::vector<int> mark(n, -1), tmp;
+    for (int s = 0; s < nsup; s++) {
+      int f = S.sn_first[s], l = S.sn_first[s + 1];
+      tmp.clear();
+      for (int j = f; j < l; j++)
+        for (int64_t p = Lo_ptr[j]; p < Lo_ptr[j + 1]; p++) {
+          int i = Lo_idx[p];
+          if (i >= l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
+        }
+      for (int c : kids[s])
+        for (int64_t p = S.sn_rowptr[c]; p < S.sn_rowptr[c + 1]; p++) {
+          int i = S.sn_rows[p];
+          if (i >= l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
+        }
+      std::sort(tmp.begin(), tmp.end());
+      S.sn_rows.insert(S.sn_rows.end(), tmp.begin(), tmp.end());
+      S.sn_rowptr[s + 1] = (int64_t)S.sn_rows.size();
+      if (!tmp.empty()) {
+        int ps = S.col2sn[tmp[0]];
+        S.sn_parent[s] = ps;
+        kids[ps].push_back(s);
+      }
+    }
+  }
+
+  // ---- sizes, flops, levels ----
+  S.panel_off.assign(nsup + 1, 0);
+  S.flops_stored = 0;
+  for (int s = 0; s < nsup; s++) {
+    int64_t ns = S.sn_first[s + 1] - S.sn_first[s];
+    int64_t nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+    S.panel_off[s + 1] = S.panel_off[s] + (ns + nr) * ns;
+    S.flops_stored += (double)ns * ns * ns / 3.0 + (double)ns * ns * nr + (double)ns * nr * nr;
+  }
+  S.nnzL_stored = S.panel_off[nsup];
+  S.sn_level.assign(nsup, 0);
+  int nlev = 0;
+  for (int s = 0; s < nsup; s++) {
+    int p = S.sn_parent[s];
+    if (p >= 0 && S.sn_level[p] < S.sn_level[s] + 1) S.sn_level[p] = S.sn_level[s] + 1;
+    if (S.sn_level[s] + 1 > nlev) nlev = S.sn_level[s] + 1;
+  }
+  S.nlevels = nlev;
+  if (stats_only) return 0;
+
+  S.level_ptr.assign(nlev + 1, 0);
+  for (int s = 0; s < nsup; s++) S.level_ptr[S.sn_level[s] + 1]++;
+  for (int l = 0; l < nlev; l++) S.level_ptr[l + 1] += S.level_ptr[l];
+  S.level_tasks.resize(nsup);
+  {
+    std::vector<int> pos(S.level_ptr.begin(), S.level_ptr.end() - 1);
+    for (int s = 0; s < nsup; s++) S.level_tasks[pos[S.sn_level[s]]++] = s;
+    auto work = [&](int s) {
+      int64_t ns = S.sn_first[s + 1] - S.sn_first[s];
+      int64_t nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+      return (ns + nr) * (ns + nr);
+    };
+    for (int l = 0; l < nlev; l++)
+      std::stable_sort(S.level_tasks.begin() + S.level_ptr[l], S.level_tasks.begin() + S.level_ptr[l + 1],
+                       [&](int a, int b) { return work(a) > work(b); });
+  }
+
+  // ---- children CSR + relative index maps ----
+  S.child_ptr.assign(nsup + 1, 0);
+  for (int s = 0; s < nsup; s++) S.child_ptr[s + 1] = S.child_ptr[s] + (int64_t)kids[s].size();
+  S.child_list.resize(S.child_ptr[nsup]);
+  for (int s = 0; s < nsup; s++)
+    std::copy(kids[s].begin(), kids[s].end(), S.child_list.begin() + S.child_ptr[s]);
+  S.rel_ptr = S.sn_rowptr;
+  S.rel.assign(S.sn_rows.size(), -1);
+  for (int c = 0; c < nsup; c++) {
+    int p = S.sn_parent[c];
+    if (p < 0) continue;
+    int pf = S.sn_first[p], pl = S.sn_first[p + 1], pns = pl - pf;
+    int64_t q = S.sn_rowptr[p], qe = S.sn_rowptr[p + 1];
+    for (int64_t t = S.sn_rowptr[c]; t < S.sn_rowptr[c + 1]; t++) {
+      int r = S.sn_rows[t];
+      if (r < pl) { S.rel[t] = r - pf; continue; }
+      while (q < qe && S.sn_rows[q] < r) q++;
+      if (q >= qe || S.sn_rows[q] != r) { std::fprintf(stderr, "symbolic: rel map failure\n"); return -10; }
+      S.rel[t] = pns + (int)(q - S.sn_rowptr[p]);
+    }
+  }
+
+  // ---- assembly map of original entries ----
+  S.asm_ptr.assign(nsup + 1, 0);
+  int64_t nnz = Ap[n];
+  std::vector<int> ent_task(nnz);
+  std::vector<int64_t> ent_dst(nnz);
+  for (int c = 0; c < n; c++)
+    for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
+      int a = S.iperm[Ai[p]], b = S.iperm[c];
+      int col = a < b ? a : b, row = a < b ? b : a;  // lower-triangular position
+      int s = S.col2sn[col];
+      int f = S.sn_first[s], l = S.sn_first[s + 1];
+      int64_t ns = l - f, nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+      int64_t lrow;
+      if (row < l) lrow = row - f;
+      else {
+        auto b0 = S.sn_rows.begin() + S.sn_rowptr[s], e0 = S.sn_rows.begin() + S.sn_rowptr[s + 1];
+        auto it = std::lower_bound(b0, e0, row);
+        if (it == e0 || *it != row) { std::fprintf(stderr, "symbolic: asm map failure\n"); return -11; }
+        lrow = ns + (it - b0);
+      }
+      ent_task[p] = s;
+      ent_dst[p] = (int64_t)(col - f) * (ns + nr) + lrow;
+      S.asm_ptr[s + 1]++;
+    }
+  for (int s = 0; s < nsup; s++) S.asm_ptr[s + 1] += S.asm_ptr[s];
+  S.asm_src.resize(nnz);
+  S.asm_dst.resize(nnz);
+  {
+    std::vector<int64_t> pos(S.asm_ptr.begin(), S.asm_ptr.end() - 1);
+    for (int64_t p = 0; p < nnz; p++) {
+      int64_t d = pos[ent_task[p]]++;
+      S.asm_src[d] = (int)p;
+      S.asm_dst[d] = ent_dst[p];
+    }
+  }
+
+  // ---- update-matrix arena: lifetime-based allocation over the level schedule ----
+  // U_s is written at level(s) and last read at level(parent(s)).
+  S.upd_off.assign(nsup, 0);
+  {
+    std::multimap<int64_t, int64_t> freeb;  // size -> offset
+    int64_t top = 0;
+    auto alloc = [&](int64_t sz) -> int64_t {
+      if (sz == 0) return 0;
+      auto it = freeb.lower_bound(sz);
+      if (it != freeb.end() && it->first <= 2 * sz + 64) {
+        int64_t off = it->second, bs = it->first;
+        freeb.erase(it);
+        if (bs - sz >= 64) freeb.emplace(bs - sz, off + sz);
+        return off;
+      }
+      int64_t off = top;
+      top += sz;
+      return off;
+    };
+    for (int l = 0; l < nlev; l++) {
+      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+        int s = S.level_tasks[t];
+        int64_t nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+        S.upd_off[s] = alloc(nr * nr);
+      }
+      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+        int s = S.level_tasks[t];
+        for (int c : kids[s]) {
+          int64_t nr = S.sn_rowptr[c + 1] - S.sn_rowptr[c];
+          if (nr > 0) freeb.emplace(nr * nr, S.upd_off[c]);
+        }
+      }
+    }
+    S.upd_total = top;
+  }
+  return 0;
+}
+
+int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
+            const SymbolicOptions& opt, Symbolic& S) {
+  if (n <= 0) return -1;
+  for (int j = 0; j < n; j++) {
+    if (!(Ap[j] < Ap[j + 1])) return -2;  // empty column (qdldl.rs:222-225)
+    for (int64_t p = Ap[j]; p < Ap[j + 1]; p++)
+      if (Ai[p] > j || Ai[p] < 0) return -3;  // not upper triangular
+  }
+  std::vector<int> perm0;
+  int kind = opt.ordering;
+  if (perm_in) {
+    kind = ORDER_GIVEN;
+    perm0.assign(perm_in, perm_in + n);
+    std::vector<char> seen(n, 0);
+    for (int k = 0; k < n; k++) {
+      if (perm0[k] < 0 || perm0[k] >= n || seen[perm0[k]]) return -5;
+      seen[perm0[k]] = 1;
+    }
+  } else if (kind == ORDER_AMD) {
+    amd_order(n, Ap, Ai, opt.amd_dense_scale, perm0);
+  } else if (kind == ORDER_ND) {
+    nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, perm0);
+  } else {
+    // ORDER_BEST: evaluate both, pick by a simple device-time model
+    std::vector<int> pa, pn;
+    amd_order(n, Ap, Ai, opt.amd_dense_scale, pa);
+    nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, pn);
+    Symbolic Sa, Sn;
+    int ra = build(n, Ap, Ai, pa, opt, Sa, true);
+    int rn = build(n, Ap, Ai, pn, opt, Sn, true);
+    if (ra) return ra;
+    if (rn) return rn;
+    // model: dense flops at ~10 TF/s effective + memory at ~2 TB/s + 10 us per level
+    auto model = [](const Symbolic& s) {
+      return s.flops_stored / 1.0e13 + (double)s.nnzL_stored * 8.0 / 2.0e12 + 10e-6 * s.nlevels;
+    };
+    if (model(Sn) < model(Sa)) { perm0.swap(pn); kind = ORDER_ND; }
+    else { perm0.swap(pa); kind = ORDER_AMD; }
+  }
+  if ((int)perm0.size() != n) return -6;
+  S.ordering_used = kind;
+  return build(n, Ap, Ai, perm0, opt, S, false);
+}
+
+}  // namespace cb

@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure both shared libraries exist (build is idempotent and quick)."""
+    import subprocess
+    need = [os.path.join(ROOT, "clarabel.rs_b200", "libclarabel_b200.so"),
+            os.path.join(ROOT, "oracle", "liboracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "-j8"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+    yield
