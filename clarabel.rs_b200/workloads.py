@@ -1,0 +1,108 @@
+"""Deterministic synthetic conic problems (numpy / scipy, host side).
+
+These are the BASELINE.json configs as generators.  The
+reference ships no problem generators or benchmark inputs (SURVEY.md section
+4), so the shapes follow BASELINE.json's (n, m, nnz) and cone lists.
+
+Every generator returns a dict with scipy CSC ``P`` (upper triangle), ``A``,
+vectors ``q``, ``b`` and ``cones`` as a list of (kind, dim) with kind in
+{"zero", "nonneg", "soc", "psd"} -- the same vocabulary as the reference's
+SupportedConeT (/root/reference/src/solver/core/cones/supportedcone.rs:17-52).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def _sym_psd_sparse(n, nnz_off, rng, window=None):
+    """diag(U[0.1,1]) + nnz_off strictly-upper entries, made diagonally dominant."""
+    rows = rng.integers(0, n, size=nnz_off)
+    if window is None:
+        cols = rng.integers(0, n, size=nnz_off)
+    else:
+        cols = np.clip(rows + rng.integers(1, window + 1, size=nnz_off), 0, n - 1)
+    keep = rows != cols
+    r, c = np.minimum(rows[keep], cols[keep]), np.maximum(rows[keep], cols[keep])
+    v = 0.01 * rng.standard_normal(r.size)
+    off = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsc()
+    off.sum_duplicates()
+    absrow = np.asarray(abs(off).sum(axis=1)).ravel() + np.asarray(abs(off).sum(axis=0)).ravel()
+    d = rng.uniform(0.1, 1.0, size=n) + absrow
+    P = (off + sp.diags(d)).tocsc()
+    P.sort_indices()
+    return sp.triu(P, format="csc")
+
+
+def random_sparse_qp(n=100_000, m=200_000, nnz_per_row=5, seed=1, window=None, p_offdiag=None):
+    """Config C2: min 1/2 x'Px + q'x s.t. Ax + s = b, s >= 0  (Nonneg cone only).
+
+    ``window=None`` draws the column indices of every row of A uniformly from
+    all n columns (SURVEY 8d wording).  ``window=w`` draws them from a sliding
+    window of w columns centred on the row's position: same (n, m, nnz), but the
+    KKT graph then has locality (like discretised / staged / block-structured
+    QPs) instead of being an expander whose factor is essentially dense.
+    """
+    rng = np.random.default_rng(seed)
+    if p_offdiag is None:
+        p_offdiag = 2 * n
+    k = nnz_per_row
+    if window is None:
+        cols = rng.integers(0, n, size=(m, k))
+        # resample duplicates within a row (rare for n >> k)
+        for _ in range(8):
+            srt = np.sort(cols, axis=1)
+            dup = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
+            if not dup.any():
+                break
+            cols[dup] = rng.integers(0, n, size=(int(dup.sum()), k))
+    else:
+        centre = (np.arange(m, dtype=np.int64) * n) // m
+        lo = np.clip(centre - window // 2, 0, max(n - window, 0))
+        w = min(window, n)
+        # k distinct offsets per row inside the window
+        offs = np.argsort(rng.random((m, w)), axis=1)[:, :k] if w <= 64 else None
+        if offs is None:
+            offs = rng.integers(0, w, size=(m, k))
+            for _ in range(8):
+                srt = np.sort(offs, axis=1)
+                dup = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
+                if not dup.any():
+                    break
+                offs[dup] = rng.integers(0, w, size=(int(dup.sum()), k))
+        cols = lo[:, None] + offs
+    rows = np.repeat(np.arange(m), k)
+    vals = rng.standard_normal(m * k)
+    A = sp.coo_matrix((vals, (rows, cols.ravel())), shape=(m, n)).tocsc()
+    A.sum_duplicates()
+    A.sort_indices()
+    P = _sym_psd_sparse(n, p_offdiag, rng, window=None if window is None else max(window // 2, 2))
+    q = rng.standard_normal(n)
+    x0 = rng.standard_normal(n)
+    b = A @ x0 + rng.uniform(0.1, 1.0, size=m)
+    return dict(P=P, q=q, A=A, b=b, cones=[("nonneg", m)], name=f"random_sparse_qp(n={n},m={m},k={k},window={window},seed={seed})")
+
+
+def kkt_triu(P, A, hdiag):
+    """Upper-triangular CSC KKT matrix [[P, A'],[., -diag(hdiag)]] with a
+    structural diagonal everywhere, plus Dsigns.  Only for LDL-level tests with
+    diagonal scaling blocks; the general assembly is in the product (csrc/kkt)."""
+    n, m = P.shape[0], A.shape[0]
+    Pu = sp.triu(P, format="coo")
+    diag_missing = np.setdiff1d(np.arange(n), Pu.row[Pu.row == Pu.col])
+    r = np.concatenate([Pu.row, diag_missing])
+    c = np.concatenate([Pu.col, diag_missing])
+    v = np.concatenate([Pu.data, np.zeros(diag_missing.size)])
+    At = A.T.tocoo()
+    r = np.concatenate([r, At.row, n + np.arange(m)])
+    c = np.concatenate([c, n + At.col, n + np.arange(m)])
+    v = np.concatenate([v, At.data, -np.asarray(hdiag, dtype=float)])
+    # build CSC by hand so explicit zeros survive
+    order = np.lexsort((r, c))
+    r, c, v = r[order], c[order], v[order]
+    N = n + m
+    colptr = np.zeros(N + 1, dtype=np.int64)
+    np.add.at(colptr, c + 1, 1)
+    colptr = np.cumsum(colptr)
+    dsigns = np.concatenate([np.ones(n, dtype=np.int8), -np.ones(m, dtype=np.int8)])
+    return N, colptr, r.astype(np.int64), v.astype(np.float64), dsigns

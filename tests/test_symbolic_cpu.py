@@ -1,0 +1,117 @@
+"""CPU tests of the host symbolic analysis (ordering, supernodes, relative maps,
+level schedule): a numpy emulation of the device schedule (tests/mf_emulator.py)
+must reproduce the oracle's factors and solutions on the same permutation."""
+import numpy as np
+import pytest
+
+import clarabel_rs_b200 as cb
+from clarabel_rs_b200 import pkg  # noqa: F401
+import mf_emulator as mf
+from oracle import QDLDL
+
+import importlib.util, os, sys
+_wl = importlib.util.spec_from_file_location(
+    "workloads", os.path.join(os.path.dirname(cb.pkg.__file__), "workloads.py"))
+workloads = importlib.util.module_from_spec(_wl)
+_wl.loader.exec_module(workloads)
+
+
+def small_kkt(n, m, seed, window=None):
+    pr = workloads.random_sparse_qp(n=n, m=m, nnz_per_row=3, seed=seed, window=window, p_offdiag=n)
+    rng = np.random.default_rng(seed + 100)
+    h = rng.uniform(0.5, 2.0, size=m)
+    return workloads.kkt_triu(pr["P"], pr["A"], h)
+
+
+def check_perm(p, n):
+    assert sorted(p.tolist()) == list(range(n))
+
+
+@pytest.mark.parametrize("ordering", [cb.ORDER_AMD, cb.ORDER_ND, cb.ORDER_BEST])
+@pytest.mark.parametrize("n,m,window", [(30, 50, None), (200, 350, 20), (400, 300, None)])
+@pytest.mark.parametrize("max_panel", [4, 64])
+def test_emulated_schedule_matches_oracle(ordering, n, m, window, max_panel):
+    N, cp, rv, nz, ds = small_kkt(n, m, seed=n + m, window=window)
+    S = cb.SymbolicAnalysis(N, cp, rv, ordering=ordering, max_panel=max_panel, nd_leaf=16)
+    check_perm(S.perm, N)
+    assert np.all(S.iperm[S.perm] == np.arange(N))
+    # postordered etree: parent index larger than child
+    assert all(S.parent[j] == -1 or S.parent[j] > j for j in range(N))
+    # oracle on the same permutation
+    f = QDLDL((N, N), cp, rv, nz, S.perm, dsigns=ds, regularize_eps=1e-13, regularize_delta=2e-7)
+    assert f.nnzL == S.nnzL                      # simplicial column counts agree with qdldl's etree pass
+    assert np.all(np.diff(f.Lp) == S.colcount)
+    assert np.all(np.where(f.etree < 0, -1, f.etree) == S.parent)
+    Lpan, D, regc = mf.factor(S, nz, ds[S.perm])
+    assert regc == f.regularize_count
+    assert np.allclose(D, f.D, rtol=1e-10, atol=0)
+    # every oracle L entry must appear in the supernodal panels with the same value
+    Lp, Li, Lx = f.Lp, f.Li, f.Lx
+    col2sn = np.searchsorted(S.sn_first, np.arange(N), side="right") - 1
+    for j in range(N):
+        s = col2sn[j]
+        fcol, ns = S.sn_first[s], S.sn_first[s + 1] - S.sn_first[s]
+        nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s]
+        ld = ns + nr
+        rows = S.sn_rows[S.sn_rowptr[s]:S.sn_rowptr[s + 1]]
+        col = Lpan[S.panel_off[s] + (j - fcol) * ld: S.panel_off[s] + (j - fcol + 1) * ld]
+        for q in range(Lp[j], Lp[j + 1]):
+            i = Li[q]
+            li = i - fcol if i < fcol + ns else ns + np.searchsorted(rows, i)
+            assert abs(col[li] - Lx[q]) <= 1e-9 * max(1.0, abs(Lx[q]))
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(N)
+    x = mf.solve(S, Lpan, D, b)
+    xo = f.solve(b)
+    assert np.max(np.abs(x - xo)) <= 1e-9 * max(1.0, np.max(np.abs(xo)))
+
+
+def test_given_perm_is_respected_up_to_postorder():
+    N, cp, rv, nz, ds = small_kkt(40, 60, seed=3)
+    perm = np.random.default_rng(1).permutation(N)
+    S = cb.SymbolicAnalysis(N, cp, rv, perm=perm)
+    check_perm(S.perm, N)
+    assert S.ordering_used == 0
+    f = QDLDL((N, N), cp, rv, nz, perm, dsigns=ds)
+    assert f.nnzL == S.nnzL  # postordering never changes fill
+
+
+def test_structural_errors():
+    with pytest.raises(cb.BackendError):
+        cb.SymbolicAnalysis(3, [0, 1, 1, 3], [0, 0, 2])         # empty column
+    with pytest.raises(cb.BackendError):
+        cb.SymbolicAnalysis(3, [0, 2, 3, 4], [0, 2, 1, 2])      # entry below the diagonal
+    with pytest.raises(cb.BackendError):
+        cb.SymbolicAnalysis(3, [0, 1, 2, 3], [0, 1, 2], perm=[0, 0, 1])
+
+
+def test_amd_quality_on_arrow_and_grid():
+    # arrowhead: AMD must put the hub last (fill = 0 beyond the arrow itself)
+    n = 50
+    cp = [0, 1] + [1 + 2 * k for k in range(1, n)]
+    rv = [0] + sum(([0, k] for k in range(1, n)), [])
+    p = cb.order(n, cp, rv, cb.ORDER_AMD)
+    check_perm(p, n)
+    S = cb.SymbolicAnalysis(n, cp, rv, perm=p)
+    assert S.nnzL == n - 1
+    # 2-D grid Laplacian 30x30: AMD / ND fill far below the natural (banded) ordering
+    g = 30
+    idx = lambda i, j: i * g + j
+    ent = []
+    for i in range(g):
+        for j in range(g):
+            ent.append((idx(i, j), idx(i, j)))
+            if i + 1 < g: ent.append((idx(i, j), idx(i + 1, j)))
+            if j + 1 < g: ent.append((idx(i, j), idx(i, j + 1)))
+    ent.sort(key=lambda e: (e[1], e[0]))
+    N = g * g
+    cp = np.zeros(N + 1, dtype=np.int64)
+    for r, c in ent: cp[c + 1] += 1
+    cp = np.cumsum(cp)
+    rv = np.array([r for r, c in ent])
+    nat = cb.SymbolicAnalysis(N, cp, rv, perm=np.arange(N)).nnzL
+    amd = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_AMD)
+    nd = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_ND, nd_leaf=32)
+    assert amd.nnzL < 0.6 * nat
+    assert nd.nnzL < 0.8 * nat
+    assert nd.nlevels <= amd.nlevels * 2 + 50
