@@ -198,3 +198,237 @@ class QDLDL:
     @property
     def AtoPAPt(self):
         return self._arr("oq_AtoPAPt", self.nnzA, np.int64)
+
+
+# ---------------------------------------------------------------------------
+# IPM oracle (oracle/ipm_oracle.c)
+# ---------------------------------------------------------------------------
+CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3}
+STATUS_NAMES = ["Unsolved", "Solved", "PrimalInfeasible", "DualInfeasible", "AlmostSolved",
+                "AlmostPrimalInfeasible", "AlmostDualInfeasible", "MaxIterations", "MaxTime",
+                "NumericalError", "InsufficientProgress"]
+
+
+class Settings(C.Structure):
+    _fields_ = [
+        ("max_iter", C.c_int32), ("time_limit", C.c_double), ("max_step_fraction", C.c_double),
+        ("tol_gap_abs", C.c_double), ("tol_gap_rel", C.c_double), ("tol_feas", C.c_double),
+        ("tol_infeas_abs", C.c_double), ("tol_infeas_rel", C.c_double), ("tol_ktratio", C.c_double),
+        ("reduced_tol_gap_abs", C.c_double), ("reduced_tol_gap_rel", C.c_double),
+        ("reduced_tol_feas", C.c_double), ("reduced_tol_infeas_abs", C.c_double),
+        ("reduced_tol_infeas_rel", C.c_double), ("reduced_tol_ktratio", C.c_double),
+        ("equilibrate_enable", C.c_int32), ("equilibrate_max_iter", C.c_int32),
+        ("equilibrate_min_scaling", C.c_double), ("equilibrate_max_scaling", C.c_double),
+        ("min_terminate_step_length", C.c_double),
+        ("static_regularization_enable", C.c_int32),
+        ("static_regularization_constant", C.c_double),
+        ("static_regularization_proportional", C.c_double),
+        ("dynamic_regularization_enable", C.c_int32),
+        ("dynamic_regularization_eps", C.c_double), ("dynamic_regularization_delta", C.c_double),
+        ("iterative_refinement_enable", C.c_int32),
+        ("iterative_refinement_reltol", C.c_double), ("iterative_refinement_abstol", C.c_double),
+        ("iterative_refinement_max_iter", C.c_int32),
+        ("iterative_refinement_stop_ratio", C.c_double),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("iterations", C.c_int32),
+        ("cost_primal", C.c_double), ("cost_dual", C.c_double), ("res_primal", C.c_double),
+        ("res_dual", C.c_double), ("res_primal_inf", C.c_double), ("res_dual_inf", C.c_double),
+        ("gap_abs", C.c_double), ("gap_rel", C.c_double), ("ktratio", C.c_double), ("mu", C.c_double),
+        ("step_length", C.c_double), ("sigma", C.c_double),
+        ("solve_time", C.c_double), ("t_kkt_update", C.c_double), ("t_kkt_solve", C.c_double),
+        ("t_scale_cones", C.c_double),
+        ("n_refactor", C.c_int64), ("n_ldl_solve", C.c_int64), ("nnzL", C.c_int64), ("nnzK", C.c_int64),
+    ]
+
+    @property
+    def status_name(self):
+        return STATUS_NAMES[self.status]
+
+
+_ipm_ready = False
+
+
+def _ipm_lib():
+    global _ipm_ready
+    L = lib()
+    if not _ipm_ready:
+        vp = C.c_void_p
+        i32p = C.POINTER(C.c_int32)
+        L.oipm_default_settings.argtypes = [C.POINTER(Settings)]
+        L.oipm_default_settings.restype = None
+        L.oipm_new.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, i64p, i64p,
+                               f64p, f64p, C.c_int64, i32p, i64p, C.POINTER(Settings)]
+        L.oipm_free.argtypes = [vp]
+        L.oipm_free.restype = None
+        L.oipm_kkt_dim.argtypes = [vp]
+        L.oipm_kkt_dim.restype = C.c_int64
+        L.oipm_kkt_nnz.argtypes = [vp]
+        L.oipm_kkt_nnz.restype = C.c_int64
+        for nm in ["oipm_kkt_colptr", "oipm_kkt_rowval"]:
+            getattr(L, nm).argtypes = [vp]
+            getattr(L, nm).restype = i64p
+        L.oipm_kkt_nzval.argtypes = [vp]
+        L.oipm_kkt_nzval.restype = f64p
+        L.oipm_kkt_dsigns.argtypes = [vp]
+        L.oipm_kkt_dsigns.restype = i8p
+        L.oipm_map.argtypes = [vp, C.c_int, i64p]
+        L.oipm_map.restype = i64p
+        L.oipm_sparse_map.argtypes = [vp, C.c_int64, C.c_int, i64p]
+        L.oipm_sparse_map.restype = i64p
+        L.oipm_equil.argtypes = [vp, C.c_int]
+        L.oipm_equil.restype = f64p
+        L.oipm_scaled_data.argtypes = [vp, C.c_int]
+        L.oipm_scaled_data.restype = f64p
+        L.oipm_set_perm.argtypes = [vp, i64p]
+        L.oipm_solve.argtypes = [vp, f64p, C.c_int32]
+        L.oipm_get_solution.argtypes = [vp, f64p, f64p, f64p, f64p, f64p]
+        L.oipm_get_solution.restype = None
+        L.oipm_get_info.argtypes = [vp, C.POINTER(Info)]
+        L.oipm_get_info.restype = None
+        L.oipm_nHs.argtypes = [vp]
+        L.oipm_nHs.restype = C.c_int64
+        L.oipm_test_update_scaling.argtypes = [vp, f64p, f64p]
+        L.oipm_test_get_Hs.argtypes = [vp, f64p]
+        L.oipm_test_get_Hs.restype = None
+        L.oipm_test_mul_Hs.argtypes = [vp, f64p, f64p]
+        L.oipm_test_mul_Hs.restype = None
+        L.oipm_test_affine_ds.argtypes = [vp, f64p]
+        L.oipm_test_affine_ds.restype = None
+        L.oipm_test_combined_ds_shift.argtypes = [vp, f64p, f64p, f64p, C.c_double]
+        L.oipm_test_combined_ds_shift.restype = None
+        L.oipm_test_ds_from_dz_offset.argtypes = [vp, f64p, f64p, f64p]
+        L.oipm_test_ds_from_dz_offset.restype = None
+        L.oipm_test_step_length.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double]
+        L.oipm_test_step_length.restype = C.c_double
+        _ipm_ready = True
+    return L
+
+
+def default_settings(**kw):
+    s = Settings()
+    _ipm_lib().oipm_default_settings(C.byref(s))
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+class IPM:
+    """Oracle interior-point solver (mirrors DefaultSolver::new / solve()).
+
+    P is any scipy sparse symmetric or upper-triangular matrix (converted to
+    triu like problemdata.rs:79-81), A scipy sparse, cones a list of
+    (kind, dim) with kind in {"zero","nonneg","soc"}.
+    """
+
+    def __init__(self, P, q, A, b, cones, settings=None):
+        import scipy.sparse as sp
+        L = _ipm_lib()
+        self._L = L
+        P = sp.triu(sp.csc_matrix(P), format="csc")
+        P.sort_indices()
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        n, m = P.shape[0], A.shape[0]
+        self.n, self.m = n, m
+        ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
+        cd = I([d for _, d in cones])
+        self.settings = settings if settings is not None else default_settings()
+        h = C.c_void_p()
+        Pp, Pi, Px = I(P.indptr), I(P.indices), F(P.data)
+        Ap, Ai, Ax = I(A.indptr), I(A.indices), F(A.data)
+        rc = L.oipm_new(C.byref(h), n, m, P_(Pp), P_(Pi), P_(Px), P_(F(q)), P_(Ap), P_(Ai), P_(Ax), P_(F(b)),
+                        len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)), P_(cd), C.byref(self.settings))
+        if rc:
+            raise ValueError(f"oipm_new failed: {rc}")
+        self._h = h
+        self.N = int(L.oipm_kkt_dim(h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.oipm_free(self._h)
+            self._h = None
+
+    def kkt(self):
+        L, h = self._L, self._h
+        N, nnz = self.N, int(L.oipm_kkt_nnz(h))
+        cp = np.ctypeslib.as_array(L.oipm_kkt_colptr(h), shape=(N + 1,)).copy()
+        rv = np.ctypeslib.as_array(L.oipm_kkt_rowval(h), shape=(max(nnz, 1),))[:nnz].copy()
+        nz = np.ctypeslib.as_array(L.oipm_kkt_nzval(h), shape=(max(nnz, 1),))[:nnz].copy()
+        ds = np.ctypeslib.as_array(L.oipm_kkt_dsigns(h), shape=(N,)).copy()
+        return N, cp, rv, nz, ds
+
+    def map(self, which):
+        ln = C.c_int64()
+        p = self._L.oipm_map(self._h, {"P": 0, "A": 1, "Hsblocks": 2, "diagP": 3, "diag_full": 4}[which], C.byref(ln))
+        return np.ctypeslib.as_array(p, shape=(max(ln.value, 1),))[:ln.value].copy()
+
+    def sparse_map(self, k, which):
+        ln = C.c_int64()
+        p = self._L.oipm_sparse_map(self._h, k, {"u": 0, "v": 1, "D": 2}[which], C.byref(ln))
+        return np.ctypeslib.as_array(p, shape=(max(ln.value, 1),))[:ln.value].copy()
+
+    def equilibration(self):
+        L, h = self._L, self._h
+        d = np.ctypeslib.as_array(L.oipm_equil(h, 0), shape=(max(self.n, 1),))[:self.n].copy()
+        e = np.ctypeslib.as_array(L.oipm_equil(h, 1), shape=(max(self.m, 1),))[:self.m].copy()
+        c = float(L.oipm_equil(h, 2)[0])
+        return d, e, c
+
+    def set_perm(self, perm):
+        rc = self._L.oipm_set_perm(self._h, P_(I(perm)))
+        if rc:
+            raise QDLDLError(rc)
+
+    def solve(self, trace_cap=256):
+        tr = np.zeros((trace_cap, 6))
+        rc = self._L.oipm_solve(self._h, P_(tr.reshape(-1)), trace_cap)
+        if rc:
+            raise RuntimeError("oipm_solve: set_perm() first")
+        info = Info()
+        self._L.oipm_get_info(self._h, C.byref(info))
+        x, z, s = np.zeros(max(self.n, 1)), np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
+        obj, objd = C.c_double(), C.c_double()
+        self._L.oipm_get_solution(self._h, P_(x), P_(z), P_(s), C.byref(obj), C.byref(objd))
+        self.info = info
+        self.trace = tr[:min(info.iterations + 1, trace_cap)]
+        return dict(status=info.status_name, iterations=info.iterations, x=x[:self.n], z=z[:self.m], s=s[:self.m],
+                    obj_val=obj.value, obj_val_dual=objd.value, info=info)
+
+    # cone-level entry points for unit parity tests of the CUDA cone kernels
+    def update_scaling(self, s, z):
+        return bool(self._L.oipm_test_update_scaling(self._h, P_(F(s)), P_(F(z))))
+
+    def get_Hs(self):
+        out = np.zeros(max(int(self._L.oipm_nHs(self._h)), 1))
+        self._L.oipm_test_get_Hs(self._h, P_(out))
+        return out[:int(self._L.oipm_nHs(self._h))]
+
+    def mul_Hs(self, x):
+        y = np.zeros(max(self.m, 1))
+        self._L.oipm_test_mul_Hs(self._h, P_(y), P_(F(x)))
+        return y[:self.m]
+
+    def affine_ds(self):
+        y = np.zeros(max(self.m, 1))
+        self._L.oipm_test_affine_ds(self._h, P_(y))
+        return y[:self.m]
+
+    def combined_ds_shift(self, step_z, step_s, sigmamu):
+        sh, sz, ss = np.zeros(max(self.m, 1)), F(step_z).copy(), F(step_s).copy()
+        self._L.oipm_test_combined_ds_shift(self._h, P_(sh), P_(sz), P_(ss), float(sigmamu))
+        return sh[:self.m]
+
+    def ds_from_dz_offset(self, ds, z):
+        out = np.zeros(max(self.m, 1))
+        self._L.oipm_test_ds_from_dz_offset(self._h, P_(out), P_(F(ds)), P_(F(z)))
+        return out[:self.m]
+
+    def step_length(self, dz, ds, z, s, amax=1.0):
+        return float(self._L.oipm_test_step_length(self._h, P_(F(dz)), P_(F(ds)), P_(F(z)), P_(F(s)), amax))
+
+
+P_ = P

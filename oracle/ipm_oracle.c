@@ -1,0 +1,1175 @@
+/*
+ * ORACLE -- TEST INFRASTRUCTURE ONLY.  Not product code.
+ *
+ * CPU restatement (plain C, single thread, f64) of the callers of the LDL hot
+ * path: KKT assembly + index maps, the DirectLDLKKTSolver (static
+ * regularisation, refactor, iterative refinement), the Zero / Nonnegative /
+ * second-order cones, Ruiz equilibration and the interior-point main loop.
+ * It exists so that "same solver status / same iteration count / same
+ * solution" can be checked between the reference algorithm on the CPU and the
+ * CUDA backend, and as the timed CPU baseline.
+ *
+ * Pinned against the reference's end-to-end known answers
+ * (tests/basic_qp.rs, basic_lp.rs, basic_socp.rs, basic_eq_constrained.rs,
+ * basic_unconstrained.rs, presolve.rs data, examples/data/hs35.json) and the
+ * exact KKT patterns of kkt_assembly.rs:185-355 in tests/test_oracle_ipm.py.
+ * The reference holds NO unit-level known answers for cone numerics
+ * (SURVEY.md section 4): those are pinned end-to-end only.
+ *
+ * Not restated (documented gaps): the inf-bound presolve row elimination
+ * (presolver.rs) -- b is capped at 1e20 exactly as problemdata.rs:130-131 does
+ * but rows are not dropped; chordal decomposition; Exp/Pow/GenPow cones.
+ * The LDL ordering is passed in (see qdldl_oracle.c header).
+ *
+ * Function -> reference map (all under /root/reference/src)
+ *   collapse_cones               solver/core/cones/supportedcone.rs:105-161
+ *   kkt_assemble                 .../quasidef/kkt_assembly.rs:20-183, datamaps.rs:112-221,
+ *                                algebra/csc/utils.rs:16-307
+ *   fill_signs                   .../quasidef/directldlkktsolver.rs:392-405
+ *   kkt_update / regularize      directldlkktsolver.rs:134-158, 217-264, 324-329
+ *   kkt_solve / refine           directldlkktsolver.rs:168-189, 266-347
+ *   symv_triu                    algebra/csc/matrix_math.rs:178-208
+ *   quad_form_triu               algebra/csc/matrix_math.rs:212-257
+ *   nn_* / zero_* / soc_*        solver/core/cones/{nonnegativecone,zerocone,socone}.rs
+ *   combined_ds_shift_symmetric  solver/core/cones/symmetric_common.rs:53-84
+ *   equilibrate                  solver/implementations/default/problemdata.rs:229-349
+ *   residuals_update             .../default/residuals.rs:69-111
+ *   kktsystem_*                  .../default/kktsystem.rs:108-278
+ *   variables_*                  .../default/variables.rs:62-285
+ *   info_update/check_*          .../default/info.rs:112-389
+ *   oipm_solve                   solver/core/solver.rs:242-465, 525-665
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef int64_t idx;
+
+/* from qdldl_oracle.c */
+typedef struct oq_s oq_t;
+int oq_new(oq_t **out, idx nrows, idx ncols, const idx *Ap, const idx *Ai, const double *Ax,
+           const idx *perm, const int8_t *Dsigns, int logical, int reg_enable, double reg_eps,
+           double reg_delta);
+void oq_free(oq_t *f);
+int oq_refactor(oq_t *f);
+int oq_solve(oq_t *f, double *b);
+void oq_update_values(oq_t *f, const idx *index, const double *values, idx len);
+void oq_scale_values(oq_t *f, const idx *index, idx len, double scale);
+int oq_dinv_is_finite(const oq_t *f);
+idx oq_nnzL(const oq_t *f);
+idx oq_regularize_count(const oq_t *f);
+
+enum { CONE_ZERO = 0, CONE_NONNEG = 1, CONE_SOC = 2, CONE_PSD = 3 };
+enum { ST_UNSOLVED = 0, ST_SOLVED, ST_PRIMAL_INFEASIBLE, ST_DUAL_INFEASIBLE, ST_ALMOST_SOLVED,
+       ST_ALMOST_PRIMAL_INFEASIBLE, ST_ALMOST_DUAL_INFEASIBLE, ST_MAX_ITERATIONS, ST_MAX_TIME,
+       ST_NUMERICAL_ERROR, ST_INSUFFICIENT_PROGRESS };
+
+/* mirrors the fields of DefaultSettings the path reads (default/settings.rs:30-193) */
+typedef struct {
+    int32_t max_iter;
+    double time_limit;
+    double max_step_fraction;
+    double tol_gap_abs, tol_gap_rel, tol_feas, tol_infeas_abs, tol_infeas_rel, tol_ktratio;
+    double reduced_tol_gap_abs, reduced_tol_gap_rel, reduced_tol_feas, reduced_tol_infeas_abs,
+        reduced_tol_infeas_rel, reduced_tol_ktratio;
+    int32_t equilibrate_enable, equilibrate_max_iter;
+    double equilibrate_min_scaling, equilibrate_max_scaling;
+    double min_terminate_step_length;
+    int32_t static_regularization_enable;
+    double static_regularization_constant, static_regularization_proportional;
+    int32_t dynamic_regularization_enable;
+    double dynamic_regularization_eps, dynamic_regularization_delta;
+    int32_t iterative_refinement_enable;
+    double iterative_refinement_reltol, iterative_refinement_abstol;
+    int32_t iterative_refinement_max_iter;
+    double iterative_refinement_stop_ratio;
+} oipm_settings;
+
+void oipm_default_settings(oipm_settings *s)
+{
+    s->max_iter = 200; s->time_limit = INFINITY; s->max_step_fraction = 0.99;
+    s->tol_gap_abs = 1e-8; s->tol_gap_rel = 1e-8; s->tol_feas = 1e-8;
+    s->tol_infeas_abs = 1e-8; s->tol_infeas_rel = 1e-8; s->tol_ktratio = 1e-6;
+    s->reduced_tol_gap_abs = 5e-5; s->reduced_tol_gap_rel = 5e-5; s->reduced_tol_feas = 1e-4;
+    s->reduced_tol_infeas_abs = 5e-12; s->reduced_tol_infeas_rel = 5e-5; s->reduced_tol_ktratio = 1e-4;
+    s->equilibrate_enable = 1; s->equilibrate_max_iter = 10;
+    s->equilibrate_min_scaling = 1e-4; s->equilibrate_max_scaling = 1e4;
+    s->min_terminate_step_length = 1e-4;
+    s->static_regularization_enable = 1; s->static_regularization_constant = 1e-8;
+    s->static_regularization_proportional = 2.220446049250313e-16 * 2.220446049250313e-16;
+    s->dynamic_regularization_enable = 1; s->dynamic_regularization_eps = 1e-13;
+    s->dynamic_regularization_delta = 2e-7;
+    s->iterative_refinement_enable = 1; s->iterative_refinement_reltol = 1e-13;
+    s->iterative_refinement_abstol = 1e-12; s->iterative_refinement_max_iter = 10;
+    s->iterative_refinement_stop_ratio = 5.0;
+}
+
+typedef struct {
+    int32_t status, iterations;
+    double cost_primal, cost_dual, res_primal, res_dual, res_primal_inf, res_dual_inf;
+    double gap_abs, gap_rel, ktratio, mu, step_length, sigma;
+    double solve_time, t_kkt_update, t_kkt_solve, t_scale_cones;
+    int64_t n_refactor, n_ldl_solve, nnzL, nnzK;
+} oipm_info;
+
+typedef struct {
+    int type; idx dim, off, boff, blen;
+    double *w, *lam; double eta;
+    int sparse; double *u, *v; double d;
+    idx *map_u, *map_v; idx map_D[2];
+} cone_t;
+
+typedef struct { idx m, n; idx *colptr, *rowval; double *nzval; } csc;
+
+typedef struct {
+    idx n, m, p, N;
+    csc P, A;              /* internal (scaled) copies; P is triu */
+    double *q, *b;
+    double normq, normb;
+    idx ncones; cone_t *cones; idx degree;
+    /* equilibration */
+    double *d, *dinv, *e, *einv, c;
+    /* KKT */
+    csc K; idx *map_P, *map_A, *map_Hs, *map_diagP, *map_diag_full; idx nHs;
+    int8_t *dsigns; double *Hs;
+    double *kx, *kb, *kw1, *kw2;  /* x, b, work1, work2 of DirectLDLKKTSolver */
+    oq_t *ldl; idx *perm;
+    double diagonal_regularizer;
+    /* kktsystem */
+    double *x1, *z1, *x2, *z2, *workx, *workz, *work_conic;
+    /* variables: x s z tau kappa  (vars, step_lhs, step_rhs, prev) */
+    double *vx, *vs, *vz, vtau, vkap;
+    double *lx, *ls, *lz, ltau, lkap;
+    double *rx_, *rs_, *rz_, rtau_, rkap_;
+    double *px, *ps, *pz, ptau, pkap;
+    /* residuals */
+    double *rx, *rz, rtau, *rx_inf, *rz_inf, *Px; double dot_qx, dot_bz, dot_sz, dot_xPx;
+    oipm_settings set; oipm_info info;
+    double prev_cost_primal, prev_cost_dual, prev_res_primal, prev_res_dual, prev_gap_abs, prev_gap_rel;
+} oipm_t;
+
+/* ---------------------------------------------------------------- vectors */
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static double *dvec(idx n) { return (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double)); }
+static idx *ivec(idx n) { return (idx *)calloc((size_t)(n > 0 ? n : 1), sizeof(idx)); }
+static double vdot(const double *a, const double *b, idx n) { double s = 0; for (idx i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+static double vnorm_inf(const double *a, idx n)
+{ double o = 0; for (idx i = 0; i < n; i++) { if (isnan(a[i])) return NAN; double v = fabs(a[i]); if (v > o) o = v; } return o; }
+/* overflow-safe 2-norm, algebra/vecmath.rs:206-226 */
+typedef struct { double scale, sumsq; } sn_t;
+static inline void sn_add(sn_t *s, double xi)
+{
+    if (xi == 0.0) return;
+    double a = fabs(xi);
+    if (s->scale < a) { double r = s->scale / a; s->sumsq = 1.0 + s->sumsq * r * r; s->scale = a; }
+    else { double r = a / s->scale; s->sumsq += r * r; }
+}
+static double vnorm(const double *a, idx n) { sn_t s = {0.0, 1.0}; for (idx i = 0; i < n; i++) sn_add(&s, a[i]); return s.scale * sqrt(s.sumsq); }
+static double vnorm_scaled(const double *a, const double *v, idx n) { sn_t s = {0.0, 1.0}; for (idx i = 0; i < n; i++) sn_add(&s, a[i] * v[i]); return s.scale * sqrt(s.sumsq); }
+static double vmean(const double *a, idx n) { if (n == 0) return 0; double s = 0; for (idx i = 0; i < n; i++) s += a[i]; return s / (double)n; }
+static int vfinite(const double *a, idx n) { for (idx i = 0; i < n; i++) if (!isfinite(a[i])) return 0; return 1; }
+static double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* ------------------------------------------------------------ sparse ops */
+static void csc_copy(csc *dst, idx m, idx n, const idx *cp, const idx *rv, const double *nz)
+{
+    idx nnz = cp[n];
+    dst->m = m; dst->n = n; dst->colptr = ivec(n + 1); dst->rowval = ivec(nnz); dst->nzval = dvec(nnz);
+    memcpy(dst->colptr, cp, (size_t)(n + 1) * sizeof(idx));
+    memcpy(dst->rowval, rv, (size_t)nnz * sizeof(idx));
+    memcpy(dst->nzval, nz, (size_t)nnz * sizeof(double));
+}
+static void csc_free(csc *a) { free(a->colptr); free(a->rowval); free(a->nzval); }
+
+/* y = a*K*x + b*y, K symmetric stored as one triangle */
+static void symv_tri(const csc *A, double *y, const double *x, double a, double b)
+{
+    idx n = A->n;
+    for (idx i = 0; i < n; i++) y[i] *= b;
+    for (idx col = 0; col < n; col++) {
+        double xc = x[col];
+        for (idx p = A->colptr[col]; p < A->colptr[col + 1]; p++) {
+            idx row = A->rowval[p]; double v = A->nzval[p];
+            y[row] += a * v * xc;
+            if (row != col) y[col] += a * v * x[row];
+        }
+    }
+}
+static double quad_form_triu(const csc *M, const double *y, const double *x)
+{
+    double out = 0;
+    for (idx col = 0; col < M->n; col++) {
+        double t1 = 0, t2 = 0;
+        for (idx p = M->colptr[col]; p < M->colptr[col + 1]; p++) {
+            idx row = M->rowval[p]; double v = M->nzval[p];
+            if (row < col) { t1 += v * x[row]; t2 += v * y[row]; }
+            else if (row == col) out += v * x[col] * y[col];
+        }
+        out += t1 * y[col] + t2 * x[col];
+    }
+    return out;
+}
+static void scale_by_b(double *y, idx n, double b)
+{
+    if (b == 0.0) { for (idx i = 0; i < n; i++) y[i] = 0.0; }
+    else if (b == 1.0) { }
+    else if (b == -1.0) { for (idx i = 0; i < n; i++) y[i] = -y[i]; }
+    else for (idx i = 0; i < n; i++) y[i] *= b;
+}
+static void gemv_N(const csc *A, double *y, const double *x, double a, double b)
+{
+    scale_by_b(y, A->m, b);
+    if (a == 0.0) return;
+    for (idx j = 0; j < A->n; j++) {
+        double xj = x[j];
+        for (idx p = A->colptr[j]; p < A->colptr[j + 1]; p++) {
+            if (a == 1.0) y[A->rowval[p]] += A->nzval[p] * xj;
+            else if (a == -1.0) y[A->rowval[p]] -= A->nzval[p] * xj;
+            else y[A->rowval[p]] += a * A->nzval[p] * xj;
+        }
+    }
+}
+static void gemv_T(const csc *A, double *y, const double *x, double a, double b)
+{
+    scale_by_b(y, A->n, b);
+    if (a == 0.0) return;
+    for (idx j = 0; j < A->n; j++) {
+        double yj = y[j];
+        for (idx p = A->colptr[j]; p < A->colptr[j + 1]; p++) {
+            if (a == 1.0) yj += A->nzval[p] * x[A->rowval[p]];
+            else if (a == -1.0) yj -= A->nzval[p] * x[A->rowval[p]];
+            else yj += a * A->nzval[p] * x[A->rowval[p]];
+        }
+        y[j] = yj;
+    }
+}
+
+/* ------------------------------------------------------------------ cones */
+static double soc_residual(const double *z, idx n) { double t = vnorm(z + 1, n - 1); return (z[0] - t) * (z[0] + t); }
+static double soc_sqrt_residual(const double *z, idx n) { double r = soc_residual(z, n); return r > 0 ? sqrt(r) : 0.0; }
+
+static void soc_circ(double *x, const double *y, const double *z, idx n)
+{
+    double x0 = vdot(y, z, n); double y0 = y[0], z0 = z[0];
+    for (idx i = 1; i < n; i++) x[i] = y0 * z[i] + z0 * y[i];
+    x[0] = x0;
+}
+static void soc_mul_W(double *y, const double *x, double a, double b, const double *w, double eta, idx n)
+{
+    double zeta = vdot(w + 1, x + 1, n - 1);
+    double c = x[0] + zeta / (1.0 + w[0]);
+    y[0] = (a * eta) * (w[0] * x[0] + zeta) + b * y[0];
+    for (idx i = 1; i < n; i++) y[i] = (a * eta * c) * w[i] + b * y[i];
+    for (idx i = 1; i < n; i++) y[i] = (a * eta) * x[i] + y[i];
+}
+static void soc_mul_Winv(double *y, const double *x, double a, double b, const double *w, double eta, idx n)
+{
+    double zeta = vdot(w + 1, x + 1, n - 1);
+    double c = -x[0] + zeta / (1.0 + w[0]);
+    y[0] = (a / eta) * (w[0] * x[0] - zeta) + b * y[0];
+    for (idx i = 1; i < n; i++) y[i] = (a / eta * c) * w[i] + b * y[i];
+    for (idx i = 1; i < n; i++) y[i] = (a / eta) * x[i] + y[i];
+}
+static double soc_step_component(const double *x, const double *y, idx n, double amax)
+{
+    if (x[0] >= 0.0 && y[0] < 0.0) { double t = -x[0] / y[0]; if (t < amax) amax = t; }
+    double a = soc_residual(y, n);
+    double b = 2.0 * (x[0] * y[0] - vdot(x + 1, y + 1, n - 1));
+    double c = soc_residual(x, n); if (c < 0.0) c = 0.0;
+    double d = b * b - 4.0 * a * c;
+    if ((a > 0.0 && b > 0.0) || d < 0.0) return amax;
+    else if (a == 0.0) return amax;
+    else if (c == 0.0) return a >= 0.0 ? amax : 0.0;
+    double t = b >= 0.0 ? (-b - sqrt(d)) : (-b + sqrt(d));
+    double r1 = (2.0 * c) / t, r2 = t / (2.0 * a);
+    if (r1 < 0.0) r1 = INFINITY;
+    if (r2 < 0.0) r2 = INFINITY;
+    double r = r1 < r2 ? r1 : r2;
+    return amax < r ? amax : r;
+}
+
+static int cone_is_sparse(const cone_t *c) { return c->type == CONE_SOC && c->sparse; }
+static int cone_Hs_diag(const cone_t *c) { return c->type != CONE_SOC || c->sparse; }
+static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : 1); }
+
+static void cones_set_identity(oipm_t *S)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k];
+        if (c->type == CONE_NONNEG) for (idx i = 0; i < c->dim; i++) c->w[i] = 1.0;
+        else if (c->type == CONE_SOC) {
+            for (idx i = 0; i < c->dim; i++) c->w[i] = 0.0;
+            c->w[0] = 1.0; c->eta = 1.0;
+            if (c->sparse) {
+                c->d = 0.5;
+                for (idx i = 0; i < c->dim; i++) { c->u[i] = 0.0; c->v[i] = 0.0; }
+                c->u[0] = 0.70710678118654752440;
+            }
+        }
+    }
+}
+
+static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k];
+        const double *s = s_ + c->off, *z = z_ + c->off; idx n = c->dim;
+        if (c->type == CONE_NONNEG) {
+            for (idx i = 0; i < n; i++) { c->lam[i] = sqrt(s[i] * z[i]); c->w[i] = sqrt(s[i] / z[i]); }
+        } else if (c->type == CONE_SOC) {
+            double zscale = soc_sqrt_residual(z, n), sscale = soc_sqrt_residual(s, n);
+            if (zscale == 0.0 || sscale == 0.0) return 0;
+            c->eta = sqrt(sscale / zscale);
+            double *w = c->w;
+            double sinv = 1.0 / sscale;
+            for (idx i = 0; i < n; i++) w[i] = s[i] * sinv;
+            w[0] += z[0] / zscale;
+            double mz = -(1.0 / zscale);
+            for (idx i = 1; i < n; i++) w[i] = mz * z[i] + w[i];
+            double wscale = soc_sqrt_residual(w, n);
+            if (wscale == 0.0) return 0;
+            double winv = 1.0 / wscale;
+            for (idx i = 0; i < n; i++) w[i] *= winv;
+            double w1sq = vdot(w + 1, w + 1, n - 1);
+            w[0] = sqrt(1.0 + w1sq);
+            double g = 0.5 * wscale;
+            double *lam = c->lam;
+            lam[0] = g;
+            double ca = (g + z[0] / zscale) / sscale, cb = (g + s[0] / sscale) / zscale;
+            for (idx i = 1; i < n; i++) lam[i] = ca * s[i] + cb * z[i];
+            double den = 1.0 / (s[0] / sscale + z[0] / zscale + 2.0 * g);
+            for (idx i = 1; i < n; i++) lam[i] *= den;
+            double sq = sqrt(sscale * zscale);
+            for (idx i = 0; i < n; i++) lam[i] *= sq;
+            if (c->sparse) {
+                double alpha = 2.0 * w[0];
+                double wsq = w[0] * w[0] + w1sq;
+                double wsqinv = 1.0 / wsq;
+                c->d = 0.5 * wsqinv;
+                double u0 = sqrt(wsq - c->d);
+                double u1 = alpha / u0;
+                double v1 = sqrt(2.0 * (2.0 + wsqinv) / (2.0 * wsq - wsqinv));
+                c->u[0] = u0;
+                for (idx i = 1; i < n; i++) c->u[i] = u1 * w[i];
+                c->v[0] = 0.0;
+                for (idx i = 1; i < n; i++) c->v[i] = v1 * w[i];
+            }
+        }
+    }
+    return 1;
+}
+
+static void cones_get_Hs(const oipm_t *S, double *Hs)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        const cone_t *c = &S->cones[k]; double *H = Hs + c->boff; idx n = c->dim;
+        if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) H[i] = 0.0;
+        else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) H[i] = c->w[i] * c->w[i];
+        else if (c->type == CONE_SOC) {
+            double e2 = c->eta * c->eta;
+            if (c->sparse) { for (idx i = 0; i < n; i++) H[i] = e2; H[0] *= c->d; }
+            else {
+                const double *w = c->w;
+                H[0] = (1.4142135623730951 * w[0] - 1.0) * (1.4142135623730951 * w[0] + 1.0);
+                idx h = 1;
+                for (idx col = 1; col < n; col++) {
+                    for (idx row = 0; row <= col; row++) H[h++] = 2.0 * w[row] * w[col];
+                    H[h - 1] += 1.0;
+                }
+                for (idx i = 0; i < c->blen; i++) H[i] *= e2;
+            }
+        }
+    }
+}
+
+static void cones_mul_Hs(oipm_t *S, double *y_, const double *x_)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; double *y = y_ + c->off; const double *x = x_ + c->off; idx n = c->dim;
+        if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) y[i] = 0.0;
+        else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) y[i] = c->w[i] * (c->w[i] * x[i]);
+        else if (c->type == CONE_SOC) {
+            double cc = vdot(c->w, x, n) * 2.0;
+            for (idx i = 0; i < n; i++) y[i] = x[i];
+            y[0] = -x[0];
+            for (idx i = 0; i < n; i++) y[i] = cc * c->w[i] + y[i];
+            double e2 = c->eta * c->eta;
+            for (idx i = 0; i < n; i++) y[i] *= e2;
+        }
+    }
+}
+
+static void cones_affine_ds(const oipm_t *S, double *ds_)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        const cone_t *c = &S->cones[k]; double *ds = ds_ + c->off; idx n = c->dim;
+        if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) ds[i] = 0.0;
+        else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) ds[i] = c->lam[i] * c->lam[i];
+        else if (c->type == CONE_SOC) soc_circ(ds, c->lam, c->lam, n);
+    }
+}
+
+/* shift = (W^-T ds) o (W dz) - sigma*mu*e, steps modified in place */
+static void cones_combined_ds_shift(oipm_t *S, double *shift_, double *sz_, double *ss_, double sigmamu)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; idx n = c->dim;
+        double *shift = shift_ + c->off, *sz = sz_ + c->off, *ss = ss_ + c->off;
+        if (c->type == CONE_ZERO) { for (idx i = 0; i < n; i++) shift[i] = 0.0; continue; }
+        double *tmp = shift;
+        memcpy(tmp, sz, (size_t)n * sizeof(double));
+        if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) sz[i] = 1.0 * (tmp[i] * c->w[i]) + 0.0 * sz[i];
+        else soc_mul_W(sz, tmp, 1.0, 0.0, c->w, c->eta, n);
+        memcpy(tmp, ss, (size_t)n * sizeof(double));
+        if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) ss[i] = 1.0 * (tmp[i] / c->w[i]) + 0.0 * ss[i];
+        else soc_mul_Winv(ss, tmp, 1.0, 0.0, c->w, c->eta, n);
+        if (c->type == CONE_NONNEG) { for (idx i = 0; i < n; i++) shift[i] = ss[i] * sz[i]; for (idx i = 0; i < n; i++) shift[i] += -sigmamu; }
+        else { soc_circ(shift, ss, sz, n); shift[0] += -sigmamu; }
+    }
+}
+
+static void cones_ds_from_dz_offset(oipm_t *S, double *out_, const double *ds_, const double *z_)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; idx n = c->dim;
+        double *out = out_ + c->off; const double *ds = ds_ + c->off, *z = z_ + c->off;
+        if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) out[i] = 0.0;
+        else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) out[i] = ds[i] / z[i];
+        else {
+            double resz = soc_residual(z, n);
+            double l1ds1 = vdot(c->lam + 1, ds + 1, n - 1), w1ds1 = vdot(c->w + 1, ds + 1, n - 1);
+            for (idx i = 0; i < n; i++) out[i] = -z[i];
+            out[0] = z[0];
+            double cc = c->lam[0] * ds[0] - l1ds1;
+            double sc = cc / resz;
+            for (idx i = 0; i < n; i++) out[i] *= sc;
+            out[0] += c->eta * w1ds1;
+            for (idx i = 1; i < n; i++) out[i] += c->eta * (ds[i] + w1ds1 / (1.0 + c->w[0]) * c->w[i]);
+            double li = 1.0 / c->lam[0];
+            for (idx i = 0; i < n; i++) out[i] *= li;
+        }
+    }
+}
+
+static double cones_step_length(oipm_t *S, const double *dz_, const double *ds_, const double *z_, const double *s_, double amax)
+{
+    double alpha = amax;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; idx n = c->dim;
+        const double *dz = dz_ + c->off, *ds = ds_ + c->off, *z = z_ + c->off, *s = s_ + c->off;
+        double az = alpha, as = alpha;
+        if (c->type == CONE_NONNEG) {
+            for (idx i = 0; i < n; i++) {
+                if (dz[i] < 0.0) { double t = -z[i] / dz[i]; if (t < az) az = t; }
+                if (ds[i] < 0.0) { double t = -s[i] / ds[i]; if (t < as) as = t; }
+            }
+        } else if (c->type == CONE_SOC) {
+            az = soc_step_component(z, dz, n, alpha);
+            as = soc_step_component(s, ds, n, alpha);
+        }
+        double m = az < as ? az : as;
+        if (m < alpha) alpha = m;
+    }
+    return alpha;
+}
+
+static void cones_margins(oipm_t *S, const double *z_, double *amin, double *bsum)
+{
+    double a = 1.7976931348623157e308, b = 0.0;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; const double *z = z_ + c->off; idx n = c->dim;
+        double ai = 1.7976931348623157e308, bi = 0.0;
+        if (c->type == CONE_NONNEG) {
+            ai = INFINITY;
+            for (idx i = 0; i < n; i++) { if (z[i] < ai) ai = z[i]; bi += z[i] > 0.0 ? z[i] : 0.0; }
+        } else if (c->type == CONE_SOC) {
+            ai = z[0] - vnorm(z + 1, n - 1); bi = ai > 0.0 ? ai : 0.0;
+        }
+        if (ai < a) a = ai;
+        b += bi;
+    }
+    *amin = a; *bsum = b;
+}
+static void cones_scaled_unit_shift(oipm_t *S, double *z_, double alpha, int primal)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; double *z = z_ + c->off; idx n = c->dim;
+        if (c->type == CONE_ZERO) { if (primal) for (idx i = 0; i < n; i++) z[i] = 0.0; }
+        else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) z[i] += alpha;
+        else z[0] += alpha;
+    }
+}
+static void shift_to_cone_interior(oipm_t *S, double *z, int primal)
+{
+    double minm, posm;
+    cones_margins(S, z, &minm, &posm);
+    double target = (posm * 0.1) / (double)S->degree;
+    if (!(target > 1.0)) target = 1.0;   /* T::max(1, x): NaN-safe like f64::max */
+    if (minm <= 0.0) { cones_scaled_unit_shift(S, z, -minm, primal); cones_scaled_unit_shift(S, z, target, primal); }
+    else if (minm < target) cones_scaled_unit_shift(S, z, target - minm, primal);
+    else cones_scaled_unit_shift(S, z, 0.0, primal);
+}
+
+/* ------------------------------------------------------------ KKT matrix */
+static void kkt_assemble(oipm_t *S)
+{
+    idx n = S->n, m = S->m;
+    const csc *P = &S->P, *A = &S->A;
+    idx p = 0, nnz_vec = 0, nHs = 0;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k];
+        c->boff = nHs;
+        c->blen = cone_Hs_diag(c) ? c->dim : c->dim * (c->dim + 1) / 2;
+        nHs += c->blen;
+        if (cone_is_sparse(c)) { p += 2; nnz_vec += 2 * c->dim; }
+    }
+    S->p = p; S->nHs = nHs;
+    idx N = n + m + p; S->N = N;
+    idx ndiagP = 0;
+    for (idx i = 0; i < n; i++)
+        if (P->colptr[i + 1] != P->colptr[i] && P->rowval[P->colptr[i + 1] - 1] == i) ndiagP++;
+    idx nnzK = P->colptr[n] + n - ndiagP + A->colptr[n] + nHs + nnz_vec + p;
+    csc *K = &S->K;
+    K->m = K->n = N; K->colptr = ivec(N + 2); K->rowval = ivec(nnzK); K->nzval = dvec(nnzK);
+    S->map_P = ivec(P->colptr[n]); S->map_A = ivec(A->colptr[n]); S->map_Hs = ivec(nHs);
+    S->map_diagP = ivec(n); S->map_diag_full = ivec(N);
+    idx *cp = K->colptr;
+    /* column counts */
+    for (idx i = 0; i < n; i++) cp[i] += P->colptr[i + 1] - P->colptr[i];
+    for (idx i = 0; i < n; i++)
+        if (P->colptr[i] == P->colptr[i + 1] || P->rowval[P->colptr[i + 1] - 1] != i) cp[i] += 1;
+    for (idx q = 0; q < A->colptr[n]; q++) cp[n + A->rowval[q]] += 1;
+    idx pcol = m + n;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; idx row = c->off + n;
+        if (cone_Hs_diag(c)) for (idx i = 0; i < c->dim; i++) cp[row + i] += 1;
+        else for (idx i = 0; i < c->dim; i++) cp[row + i] += i + 1;
+        if (cone_is_sparse(c)) { cp[pcol] += c->dim; cp[pcol + 1] += c->dim; cp[pcol] += 1; cp[pcol + 1] += 1; pcol += 2; }
+    }
+    /* counts -> pointers (next-fill positions) */
+    { idx cur = 0; for (idx j = 0; j <= N; j++) { idx cnt = cp[j]; cp[j] = cur; cur += cnt; } }
+    /* fill P (N shape), missing diagonal, A transposed */
+    for (idx i = 0; i < n; i++)
+        for (idx q = P->colptr[i]; q < P->colptr[i + 1]; q++) {
+            idx dest = cp[i]++; K->rowval[dest] = P->rowval[q]; K->nzval[dest] = P->nzval[q]; S->map_P[q] = dest;
+        }
+    for (idx i = 0; i < n; i++)
+        if (P->colptr[i] == P->colptr[i + 1] || P->rowval[P->colptr[i + 1] - 1] != i) {
+            idx dest = cp[i]++; K->rowval[dest] = i; K->nzval[dest] = 0.0;
+        }
+    for (idx i = 0; i < A->n; i++)
+        for (idx q = A->colptr[i]; q < A->colptr[i + 1]; q++) {
+            idx col = A->rowval[q] + n; idx dest = cp[col]++;
+            K->rowval[dest] = i; K->nzval[dest] = A->nzval[q]; S->map_A[q] = dest;
+        }
+    pcol = m + n;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; idx row = c->off + n; idx *blk = S->map_Hs + c->boff;
+        if (cone_Hs_diag(c)) {
+            for (idx i = 0; i < c->dim; i++) { idx col = row + i; idx dest = cp[col]++; K->rowval[dest] = col; K->nzval[dest] = 0.0; blk[i] = dest; }
+        } else {
+            idx kidx = 0;
+            for (idx col = row; col < row + c->dim; col++)
+                for (idx r = row; r <= col; r++) { idx dest = cp[col]++; K->rowval[dest] = r; K->nzval[dest] = 0.0; blk[kidx++] = dest; }
+        }
+        if (cone_is_sparse(c)) {
+            c->map_u = ivec(c->dim); c->map_v = ivec(c->dim);
+            /* v is the first extra column, u the second (datamaps.rs:186-189) */
+            for (idx i = 0; i < c->dim; i++) { idx dest = cp[pcol]++; K->rowval[dest] = row + i; K->nzval[dest] = 0.0; c->map_v[i] = dest; }
+            for (idx i = 0; i < c->dim; i++) { idx dest = cp[pcol + 1]++; K->rowval[dest] = row + i; K->nzval[dest] = 0.0; c->map_u[i] = dest; }
+            for (idx i = 0; i < 2; i++) { idx col = pcol + i; idx dest = cp[col]++; K->rowval[dest] = col; K->nzval[dest] = 0.0; c->map_D[i] = dest; }
+            pcol += 2;
+        }
+    }
+    /* backshift */
+    for (idx j = N; j > 0; j--) cp[j] = cp[j - 1];
+    cp[0] = 0;
+    for (idx j = 0; j < N; j++) S->map_diag_full[j] = cp[j + 1] - 1;
+    for (idx j = 0; j < n; j++) S->map_diagP[j] = cp[j + 1] - 1;
+    /* signs */
+    S->dsigns = (int8_t *)malloc((size_t)N);
+    for (idx i = 0; i < N; i++) S->dsigns[i] = 1;
+    for (idx i = n; i < n + m; i++) S->dsigns[i] = -1;
+    idx pp = n + m;
+    for (idx k = 0; k < S->ncones; k++) if (cone_is_sparse(&S->cones[k])) { S->dsigns[pp] = -1; S->dsigns[pp + 1] = 1; pp += 2; }
+    S->info.nnzK = nnzK;
+}
+
+static void kkt_update_values(oipm_t *S, const idx *index, const double *v, idx len)
+{ for (idx i = 0; i < len; i++) S->K.nzval[index[i]] = v[i]; oq_update_values(S->ldl, index, v, len); }
+static void kkt_scale_values(oipm_t *S, const idx *index, idx len, double sc)
+{ for (idx i = 0; i < len; i++) S->K.nzval[index[i]] *= sc; oq_scale_values(S->ldl, index, len, sc); }
+
+static int kkt_regularize_and_refactor(oipm_t *S)
+{
+    double *diag_kkt = S->kw1, *diag_shift = S->kw2; idx N = S->N;
+    if (S->set.static_regularization_enable) {
+        for (idx i = 0; i < N; i++) diag_kkt[i] = S->K.nzval[S->map_diag_full[i]];
+        double eps = S->set.static_regularization_constant + S->set.static_regularization_proportional * vnorm_inf(diag_kkt, N);
+        for (idx i = 0; i < N; i++) diag_shift[i] = diag_kkt[i];
+        for (idx i = 0; i < N; i++) { if (S->dsigns[i] == 1) diag_shift[i] += eps; else diag_shift[i] -= eps; }
+        kkt_update_values(S, S->map_diag_full, diag_shift, N);
+        S->diagonal_regularizer = eps;
+    }
+    int rc = oq_refactor(S->ldl);
+    S->info.n_refactor++;
+    int ok = (rc == 0) && oq_dinv_is_finite(S->ldl);
+    if (S->set.static_regularization_enable)
+        for (idx i = 0; i < N; i++) S->K.nzval[S->map_diag_full[i]] = diag_kkt[i];
+    return ok;
+}
+
+static int kkt_update(oipm_t *S)
+{
+    cones_get_Hs(S, S->Hs);
+    for (idx i = 0; i < S->nHs; i++) S->Hs[i] = -S->Hs[i];
+    kkt_update_values(S, S->map_Hs, S->Hs, S->nHs);
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k];
+        if (!cone_is_sparse(c)) continue;
+        double e2 = c->eta * c->eta;
+        kkt_update_values(S, c->map_u, c->u, c->dim);
+        kkt_update_values(S, c->map_v, c->v, c->dim);
+        kkt_scale_values(S, c->map_u, c->dim, -e2);
+        kkt_scale_values(S, c->map_v, c->dim, -e2);
+        double dd[2] = {-e2, e2};
+        kkt_update_values(S, c->map_D, dd, 2);
+    }
+    return kkt_regularize_and_refactor(S);
+}
+
+static void kkt_setrhs(oipm_t *S, const double *rx, const double *rz)
+{
+    memcpy(S->kb, rx, (size_t)S->n * sizeof(double));
+    memcpy(S->kb + S->n, rz, (size_t)S->m * sizeof(double));
+    for (idx i = S->n + S->m; i < S->N; i++) S->kb[i] = 0.0;
+}
+
+static void ldl_solve(oipm_t *S, double *x, const double *b)
+{ memcpy(x, b, (size_t)S->N * sizeof(double)); oq_solve(S->ldl, x); S->info.n_ldl_solve++; }
+
+static double refine_error(oipm_t *S, double *e, const double *b, const double *xi)
+{ memcpy(e, b, (size_t)S->N * sizeof(double)); symv_tri(&S->K, e, xi, -1.0, 1.0); return vnorm_inf(e, S->N); }
+
+static int kkt_iterative_refinement(oipm_t *S)
+{
+    double *x = S->kx, *b = S->kb, *e = S->kw1, *dx = S->kw2; idx N = S->N;
+    double normb = vnorm_inf(b, N);
+    double norme = refine_error(S, e, b, x);
+    if (!isfinite(norme)) return 0;
+    for (int it = 0; it < S->set.iterative_refinement_max_iter; it++) {
+        if (norme <= S->set.iterative_refinement_abstol + S->set.iterative_refinement_reltol * normb) break;
+        double last = norme;
+        ldl_solve(S, dx, e);
+        for (idx i = 0; i < N; i++) dx[i] = 1.0 * x[i] + 1.0 * dx[i];
+        norme = refine_error(S, e, b, dx);
+        if (!isfinite(norme)) return 0;
+        double ratio = last / norme;
+        if (ratio < S->set.iterative_refinement_stop_ratio) {
+            if (ratio > 1.0) { double *t = x; x = dx; dx = t; }
+            break;
+        }
+        { double *t = x; x = dx; dx = t; }
+    }
+    if (x != S->kx) { S->kw2 = S->kx; S->kx = x; }  /* std::mem::swap of the buffers */
+    return 1;
+}
+
+static int kkt_solve(oipm_t *S, double *lhsx, double *lhsz)
+{
+    ldl_solve(S, S->kx, S->kb);
+    int ok = S->set.iterative_refinement_enable ? kkt_iterative_refinement(S) : vfinite(S->kx, S->N);
+    if (ok) {
+        if (lhsx) memcpy(lhsx, S->kx, (size_t)S->n * sizeof(double));
+        if (lhsz) memcpy(lhsz, S->kx + S->n, (size_t)S->m * sizeof(double));
+    }
+    return ok;
+}
+
+/* --------------------------------------------------------- equilibration */
+static void scale_data(oipm_t *S, const double *d, const double *e)
+{
+    csc *P = &S->P, *A = &S->A;
+    if (d) {
+        for (idx col = 0; col < P->n; col++) for (idx p = P->colptr[col]; p < P->colptr[col + 1]; p++) P->nzval[p] *= d[P->rowval[p]] * d[col];
+        for (idx col = 0; col < A->n; col++) for (idx p = A->colptr[col]; p < A->colptr[col + 1]; p++) A->nzval[p] *= e[A->rowval[p]] * d[col];
+        for (idx i = 0; i < S->n; i++) S->q[i] *= d[i];
+    } else {
+        for (idx p = 0; p < A->colptr[A->n]; p++) A->nzval[p] *= e[A->rowval[p]];
+    }
+    for (idx i = 0; i < S->m; i++) S->b[i] *= e[i];
+}
+
+static void equilibrate(oipm_t *S)
+{
+    idx n = S->n, m = S->m;
+    if (!S->set.equilibrate_enable) return;
+    double *d = S->d, *e = S->e, *dw = S->dinv, *ew = S->einv;
+    csc *P = &S->P, *A = &S->A;
+    double smin = S->set.equilibrate_min_scaling, smax = S->set.equilibrate_max_scaling;
+    for (int it = 0; it < S->set.equilibrate_max_iter; it++) {
+        for (idx i = 0; i < n; i++) dw[i] = 0.0;
+        for (idx i = 0; i < n; i++) for (idx p = P->colptr[i]; p < P->colptr[i + 1]; p++) {
+            double t = fabs(P->nzval[p]); idx r = P->rowval[p];
+            if (t > dw[i]) dw[i] = t;
+            if (t > dw[r]) dw[r] = t;
+        }
+        for (idx i = 0; i < n; i++) for (idx p = A->colptr[i]; p < A->colptr[i + 1]; p++) { double t = fabs(A->nzval[p]); if (t > dw[i]) dw[i] = t; }
+        for (idx i = 0; i < m; i++) ew[i] = 0.0;
+        for (idx p = 0; p < A->colptr[n]; p++) { double t = fabs(A->nzval[p]); idx r = A->rowval[p]; if (t > ew[r]) ew[r] = t; }
+        for (idx i = 0; i < n; i++) if (dw[i] == 0.0) dw[i] = 1.0;
+        for (idx i = 0; i < m; i++) if (ew[i] == 0.0) ew[i] = 1.0;
+        for (idx i = 0; i < n; i++) dw[i] = 1.0 / sqrt(dw[i]);
+        for (idx i = 0; i < m; i++) ew[i] = 1.0 / sqrt(ew[i]);
+        for (idx i = 0; i < n; i++) dw[i] = clipd(dw[i], smin / d[i], smax / d[i]);
+        for (idx i = 0; i < m; i++) ew[i] = clipd(ew[i], smin / e[i], smax / e[i]);
+        scale_data(S, dw, ew);
+        for (idx i = 0; i < n; i++) d[i] *= dw[i];
+        for (idx i = 0; i < m; i++) e[i] *= ew[i];
+        /* cost scaling: plain (non-symmetric) column norms of the triu P */
+        for (idx i = 0; i < n; i++) { double v = 0.0; for (idx p = P->colptr[i]; p < P->colptr[i + 1]; p++) { double t = fabs(P->nzval[p]); if (t > v) v = t; } dw[i] = v; }
+        double meanP = vmean(dw, n), infq = vnorm_inf(S->q, n);
+        if (meanP != 0.0 && infq != 0.0) {
+            double sc = infq > meanP ? infq : meanP;
+            double ct = clipd(1.0 / sc, smin / S->c, smax / S->c);
+            for (idx p = 0; p < P->colptr[n]; p++) P->nzval[p] *= ct;
+            for (idx i = 0; i < n; i++) S->q[i] *= ct;
+            S->c *= ct;
+        }
+    }
+    /* rectification: SOC cones need a scalar scaling (socone.rs:97-101) */
+    int changed = 0;
+    for (idx i = 0; i < m; i++) ew[i] = 1.0;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k];
+        if (c->type == CONE_SOC) {
+            double mean = vmean(e + c->off, c->dim);
+            for (idx i = 0; i < c->dim; i++) ew[c->off + i] = (1.0 / e[c->off + i]) * mean;
+            changed = 1;
+        }
+    }
+    if (changed) { scale_data(S, NULL, ew); for (idx i = 0; i < m; i++) e[i] *= ew[i]; }
+    for (idx i = 0; i < n; i++) S->dinv[i] = 1.0 / d[i];
+    for (idx i = 0; i < m; i++) S->einv[i] = 1.0 / e[i];
+}
+
+/* -------------------------------------------------------------- lifecycle */
+void oipm_free(oipm_t *S)
+{
+    if (!S) return;
+    csc_free(&S->P); csc_free(&S->A); free(S->q); free(S->b);
+    for (idx k = 0; k < S->ncones; k++) { cone_t *c = &S->cones[k]; free(c->w); free(c->lam); free(c->u); free(c->v); free(c->map_u); free(c->map_v); }
+    free(S->cones); free(S->d); free(S->dinv); free(S->e); free(S->einv);
+    if (S->K.colptr) csc_free(&S->K);
+    free(S->map_P); free(S->map_A); free(S->map_Hs); free(S->map_diagP); free(S->map_diag_full);
+    free(S->dsigns); free(S->Hs); free(S->kx); free(S->kb); free(S->kw1); free(S->kw2);
+    if (S->ldl) oq_free(S->ldl);
+    free(S->perm);
+    free(S->x1); free(S->z1); free(S->x2); free(S->z2); free(S->workx); free(S->workz); free(S->work_conic);
+    free(S->vx); free(S->vs); free(S->vz); free(S->lx); free(S->ls); free(S->lz);
+    free(S->rx_); free(S->rs_); free(S->rz_); free(S->px); free(S->ps); free(S->pz);
+    free(S->rx); free(S->rz); free(S->rx_inf); free(S->rz_inf); free(S->Px);
+    free(S);
+}
+
+/* P must be upper triangular CSC (the reference converts with to_triu,
+   problemdata.rs:79-81; the Python caller does the same). */
+int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
+             const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
+             idx ncones_in, const int32_t *ctype, const idx *cdim, const oipm_settings *set)
+{
+    *out = NULL;
+    oipm_t *S = (oipm_t *)calloc(1, sizeof(oipm_t));
+    if (set) S->set = *set; else oipm_default_settings(&S->set);
+    S->n = n; S->m = m;
+    csc_copy(&S->P, n, n, Pp, Pi, Px);
+    csc_copy(&S->A, m, n, Ap, Ai, Ax);
+    S->q = dvec(n); memcpy(S->q, q, (size_t)n * sizeof(double));
+    S->b = dvec(m); memcpy(S->b, b, (size_t)m * sizeof(double));
+    for (idx i = 0; i < m; i++) if (S->b[i] > 1e20) S->b[i] = 1e20;
+    /* collapse cones */
+    S->cones = (cone_t *)calloc((size_t)(ncones_in > 0 ? ncones_in : 1), sizeof(cone_t));
+    idx nc = 0, k = 0;
+    while (k < ncones_in) {
+        int t = ctype[k]; idx dm = cdim[k];
+        idx numel = (t == CONE_PSD) ? dm * (dm + 1) / 2 : dm;
+        if (numel == 0) { k++; continue; }
+        int collapsible = (t == CONE_NONNEG) || (t == CONE_SOC && dm == 1) || (t == CONE_PSD && dm == 1);
+        if (collapsible) {
+            idx tot = (t == CONE_NONNEG) ? dm : 1;
+            k++;
+            while (k < ncones_in) {
+                int t2 = ctype[k]; idx d2 = cdim[k];
+                idx ne2 = (t2 == CONE_PSD) ? d2 * (d2 + 1) / 2 : d2;
+                if (ne2 != 0) {
+                    if (t2 == CONE_NONNEG) tot += d2;
+                    else if ((t2 == CONE_SOC || t2 == CONE_PSD) && d2 == 1) tot += 1;
+                    else break;
+                }
+                k++;
+            }
+            S->cones[nc].type = CONE_NONNEG; S->cones[nc].dim = tot; nc++;
+        } else {
+            if (t == CONE_PSD) { oipm_free(S); return -3; }  /* PSD not in this oracle build */
+            if (t == CONE_SOC && dm < 2) { oipm_free(S); return -2; }
+            S->cones[nc].type = t; S->cones[nc].dim = dm; nc++; k++;
+        }
+    }
+    S->ncones = nc;
+    idx off = 0; S->degree = 0;
+    for (idx c = 0; c < nc; c++) {
+        cone_t *cn = &S->cones[c];
+        cn->off = off; off += cn->dim;
+        S->degree += cone_degree(cn);
+        if (cn->type != CONE_ZERO) { cn->w = dvec(cn->dim); cn->lam = dvec(cn->dim); }
+        if (cn->type == CONE_SOC && cn->dim > 4) { cn->sparse = 1; cn->u = dvec(cn->dim); cn->v = dvec(cn->dim); cn->d = 1.0; }
+    }
+    if (off != m) { oipm_free(S); return -1; }
+    S->normq = vnorm_inf(S->q, n); S->normb = vnorm_inf(S->b, m);
+    S->d = dvec(n); S->dinv = dvec(n); S->e = dvec(m); S->einv = dvec(m); S->c = 1.0;
+    for (idx i = 0; i < n; i++) { S->d[i] = 1.0; S->dinv[i] = 1.0; }
+    for (idx i = 0; i < m; i++) { S->e[i] = 1.0; S->einv[i] = 1.0; }
+    equilibrate(S);
+    kkt_assemble(S);
+    idx N = S->N;
+    S->Hs = dvec(S->nHs); S->kx = dvec(N); S->kb = dvec(N); S->kw1 = dvec(N); S->kw2 = dvec(N);
+    S->x1 = dvec(n); S->z1 = dvec(m); S->x2 = dvec(n); S->z2 = dvec(m);
+    S->workx = dvec(n); S->workz = dvec(m); S->work_conic = dvec(m);
+    S->vx = dvec(n); S->vs = dvec(m); S->vz = dvec(m); S->lx = dvec(n); S->ls = dvec(m); S->lz = dvec(m);
+    S->rx_ = dvec(n); S->rs_ = dvec(m); S->rz_ = dvec(m); S->px = dvec(n); S->ps = dvec(m); S->pz = dvec(m);
+    S->rx = dvec(n); S->rz = dvec(m); S->rx_inf = dvec(n); S->rz_inf = dvec(m); S->Px = dvec(n);
+    S->vtau = S->vkap = 1.0; S->rtau = 1.0;
+    *out = S;
+    return 0;
+}
+
+/* KKT pattern for the ordering step (caller computes a permutation of size N) */
+idx oipm_kkt_dim(const oipm_t *S) { return S->N; }
+idx oipm_kkt_nnz(const oipm_t *S) { return S->K.colptr[S->N]; }
+const idx *oipm_kkt_colptr(const oipm_t *S) { return S->K.colptr; }
+const idx *oipm_kkt_rowval(const oipm_t *S) { return S->K.rowval; }
+const double *oipm_kkt_nzval(const oipm_t *S) { return S->K.nzval; }
+const int8_t *oipm_kkt_dsigns(const oipm_t *S) { return S->dsigns; }
+const idx *oipm_map(const oipm_t *S, int which, idx *len)
+{
+    switch (which) {
+        case 0: *len = S->P.colptr[S->n]; return S->map_P;
+        case 1: *len = S->A.colptr[S->n]; return S->map_A;
+        case 2: *len = S->nHs; return S->map_Hs;
+        case 3: *len = S->n; return S->map_diagP;
+        case 4: *len = S->N; return S->map_diag_full;
+    }
+    *len = 0; return NULL;
+}
+/* sparse-cone maps: which = 0 u, 1 v, 2 D for the k-th sparse cone */
+const idx *oipm_sparse_map(const oipm_t *S, idx ksparse, int which, idx *len)
+{
+    idx cnt = 0;
+    for (idx k = 0; k < S->ncones; k++) {
+        const cone_t *c = &S->cones[k];
+        if (!cone_is_sparse(c)) continue;
+        if (cnt == ksparse) {
+            if (which == 0) { *len = c->dim; return c->map_u; }
+            if (which == 1) { *len = c->dim; return c->map_v; }
+            *len = 2; return c->map_D;
+        }
+        cnt++;
+    }
+    *len = 0; return NULL;
+}
+const double *oipm_equil(const oipm_t *S, int which) { return which == 0 ? S->d : (which == 1 ? S->e : &S->c); }
+const double *oipm_scaled_data(const oipm_t *S, int which)
+{ return which == 0 ? S->P.nzval : which == 1 ? S->A.nzval : which == 2 ? S->q : S->b; }
+
+int oipm_set_perm(oipm_t *S, const idx *perm)
+{
+    if (S->ldl) { oq_free(S->ldl); S->ldl = NULL; }
+    free(S->perm);
+    S->perm = ivec(S->N);
+    memcpy(S->perm, perm, (size_t)S->N * sizeof(idx));
+    int rc = oq_new(&S->ldl, S->N, S->N, S->K.colptr, S->K.rowval, S->K.nzval, S->perm, S->dsigns, 1, 1,
+                    S->set.dynamic_regularization_eps, S->set.dynamic_regularization_delta);
+    if (rc) return rc;
+    S->info.nnzL = oq_nnzL(S->ldl);
+    return 0;
+}
+
+/* ------------------------------------------------------------ IPM pieces */
+static void residuals_update(oipm_t *S)
+{
+    idx n = S->n, m = S->m;
+    double qx = vdot(S->q, S->vx, n), bz = vdot(S->b, S->vz, m), sz = vdot(S->vs, S->vz, m);
+    symv_tri(&S->P, S->Px, S->vx, 1.0, 0.0);
+    double xPx = vdot(S->vx, S->Px, n);
+    gemv_T(&S->A, S->rx_inf, S->vz, -1.0, 0.0);
+    memcpy(S->rz_inf, S->vs, (size_t)m * sizeof(double));
+    gemv_N(&S->A, S->rz_inf, S->vx, 1.0, 1.0);
+    for (idx i = 0; i < n; i++) S->rx[i] = -1.0 * S->Px[i] + (-S->vtau) * S->q[i];
+    for (idx i = 0; i < n; i++) S->rx[i] = 1.0 * S->rx_inf[i] + 1.0 * S->rx[i];
+    for (idx i = 0; i < m; i++) S->rz[i] = 1.0 * S->rz_inf[i] + (-S->vtau) * S->b[i];
+    S->rtau = qx + bz + S->vkap + xPx / S->vtau;
+    S->dot_qx = qx; S->dot_bz = bz; S->dot_sz = sz; S->dot_xPx = xPx;
+}
+
+static void info_update(oipm_t *S, double t0)
+{
+    idx n = S->n, m = S->m; oipm_info *I = &S->info;
+    double tinv = 1.0 / S->vtau, cinv = 1.0 / S->c;
+    double xPx2 = S->dot_xPx * tinv * tinv / 2.0;
+    I->cost_primal = (S->dot_qx * tinv + xPx2) * cinv;
+    I->cost_dual = (-S->dot_bz * tinv - xPx2) * cinv;
+    double normx = vnorm_scaled(S->vx, S->d, n), normz = vnorm_scaled(S->vz, S->e, m) * cinv, norms = vnorm_scaled(S->vs, S->einv, m);
+    I->res_primal_inf = (vnorm_scaled(S->rx_inf, S->dinv, n) * cinv) / fmax(1.0, normz);
+    I->res_dual_inf = fmax(vnorm_scaled(S->Px, S->dinv, n) / fmax(1.0, normx),
+                           vnorm_scaled(S->rz_inf, S->einv, m) / fmax(1.0, normx + norms));
+    normx *= tinv; normz *= tinv; norms *= tinv;
+    I->res_primal = vnorm_scaled(S->rz, S->einv, m) * tinv / fmax(1.0, S->normb + normx + norms);
+    I->res_dual = vnorm_scaled(S->rx, S->dinv, n) * tinv * cinv / fmax(1.0, S->normq + normx + normz);
+    I->gap_abs = fabs(I->cost_primal - I->cost_dual);
+    I->gap_rel = I->gap_abs / fmax(1.0, fmin(fabs(I->cost_primal), fabs(I->cost_dual)));
+    I->ktratio = S->vkap * tinv;
+    I->solve_time = now_s() - t0;
+}
+
+static void check_convergence(oipm_t *S, double tga, double tgr, double tf, double tia, double tir, double tkt,
+                              int st_solved, int st_pinf, int st_dinf)
+{
+    oipm_info *I = &S->info;
+    int solved = ((I->gap_abs < tga) || (I->gap_rel < tgr)) && (I->res_primal < tf) && (I->res_dual < tf);
+    if (I->ktratio <= 1.0 && solved) I->status = st_solved;
+    else if (I->ktratio > (1.0 / tkt) * 1000.0) {
+        if ((S->dot_bz < -tia) && (I->res_primal_inf < -tir * S->dot_bz)) I->status = st_pinf;
+        else if ((S->dot_qx < -tia) && (I->res_dual_inf < -tir * S->dot_qx)) I->status = st_dinf;
+    }
+}
+
+static int check_termination(oipm_t *S, int iter)
+{
+    oipm_info *I = &S->info; const oipm_settings *T = &S->set;
+    check_convergence(S, T->tol_gap_abs, T->tol_gap_rel, T->tol_feas, T->tol_infeas_abs, T->tol_infeas_rel,
+                      T->tol_ktratio, ST_SOLVED, ST_PRIMAL_INFEASIBLE, ST_DUAL_INFEASIBLE);
+    if (I->status == ST_UNSOLVED && iter > 1 &&
+        (I->res_dual > S->prev_res_dual || I->res_primal > S->prev_res_primal)) {
+        if (I->ktratio < 2.220446049250313e-16 * 100.0 &&
+            (S->prev_gap_abs < T->tol_gap_abs || S->prev_gap_rel < T->tol_gap_rel))
+            I->status = ST_INSUFFICIENT_PROGRESS;
+        if (I->ktratio < 1.0) {
+            if ((I->res_dual > T->tol_feas * 100.0 && I->res_dual > S->prev_res_dual * 100.0) ||
+                (I->res_primal > T->tol_feas * 100.0 && I->res_primal > S->prev_res_primal * 100.0))
+                I->status = ST_INSUFFICIENT_PROGRESS;
+        }
+    }
+    if (I->status == ST_UNSOLVED) {
+        if (T->max_iter == I->iterations) I->status = ST_MAX_ITERATIONS;
+        else if (I->solve_time > T->time_limit) I->status = ST_MAX_TIME;
+    }
+    return I->status != ST_UNSOLVED;
+}
+
+static int kktsystem_solve_constant_rhs(oipm_t *S)
+{
+    for (idx i = 0; i < S->n; i++) S->workx[i] = -1.0 * S->q[i] + 0.0 * S->workx[i];
+    kkt_setrhs(S, S->workx, S->b);
+    return kkt_solve(S, S->x2, S->z2);
+}
+static int kktsystem_update(oipm_t *S)
+{
+    double t = now_s();
+    int ok = kkt_update(S);
+    if (ok) ok = kktsystem_solve_constant_rhs(S);
+    S->info.t_kkt_update += now_s() - t;
+    return ok;
+}
+
+/* lhs <- solution of the reduced Newton system for rhs (step_rhs) */
+static int kktsystem_solve(oipm_t *S, int combined)
+{
+    double t0 = now_s();
+    idx n = S->n, m = S->m;
+    double *workx = S->workx, *workz = S->workz, *dsc = S->work_conic;
+    memcpy(workx, S->rx_, (size_t)n * sizeof(double));
+    if (!combined) memcpy(dsc, S->vs, (size_t)m * sizeof(double));
+    else cones_ds_from_dz_offset(S, dsc, S->rs_, S->vz);
+    for (idx i = 0; i < m; i++) workz[i] = 1.0 * dsc[i] + -1.0 * S->rz_[i];
+    kkt_setrhs(S, workx, workz);
+    int ok = kkt_solve(S, S->x1, S->z1);
+    if (!ok) { S->info.t_kkt_solve += now_s() - t0; return 0; }
+    double *xi = workx;
+    double tinv = 1.0 / S->vtau;
+    for (idx i = 0; i < n; i++) xi[i] = tinv * S->vx[i] + 0.0 * xi[i];
+    double tau_num = S->rtau_ - S->rkap_ / S->vtau + vdot(S->q, S->x1, n) + vdot(S->b, S->z1, m) +
+                     2.0 * quad_form_triu(&S->P, xi, S->x1);
+    for (idx i = 0; i < n; i++) xi[i] = -1.0 * S->x2[i] + 1.0 * xi[i];
+    double tau_den = S->vkap / S->vtau - vdot(S->q, S->x2, n) - vdot(S->b, S->z2, m);
+    tau_den += quad_form_triu(&S->P, xi, xi) - quad_form_triu(&S->P, S->x2, S->x2);
+    S->ltau = tau_num / tau_den;
+    for (idx i = 0; i < n; i++) S->lx[i] = 1.0 * S->x1[i] + S->ltau * S->x2[i];
+    for (idx i = 0; i < m; i++) S->lz[i] = 1.0 * S->z1[i] + S->ltau * S->z2[i];
+    cones_mul_Hs(S, S->ls, S->lz);
+    for (idx i = 0; i < m; i++) S->ls[i] = -1.0 * dsc[i] + -1.0 * S->ls[i];
+    S->lkap = -(S->rkap_ + S->vkap * S->ltau) / S->vtau;
+    S->info.t_kkt_solve += now_s() - t0;
+    return 1;
+}
+
+static int solve_initial_point(oipm_t *S)
+{
+    idx n = S->n, m = S->m; int ok;
+    if (S->P.colptr[n] == 0) {
+        for (idx i = 0; i < n; i++) S->workx[i] = 0.0;
+        memcpy(S->workz, S->b, (size_t)m * sizeof(double));
+        kkt_setrhs(S, S->workx, S->workz);
+        ok = kkt_solve(S, S->vx, S->vs);
+        for (idx i = 0; i < m; i++) S->vs[i] = -S->vs[i];
+        if (!ok) return ok;
+        for (idx i = 0; i < n; i++) S->workx[i] = -1.0 * S->q[i] + 0.0 * S->workx[i];
+        for (idx i = 0; i < m; i++) S->workz[i] = 0.0;
+        kkt_setrhs(S, S->workx, S->workz);
+        ok = kkt_solve(S, NULL, S->vz);
+    } else {
+        for (idx i = 0; i < n; i++) S->workx[i] = -S->q[i];
+        memcpy(S->workz, S->b, (size_t)m * sizeof(double));
+        kkt_setrhs(S, S->workx, S->workz);
+        ok = kkt_solve(S, S->vx, S->vz);
+        for (idx i = 0; i < m; i++) S->vs[i] = -S->vz[i];
+    }
+    return ok;
+}
+
+static double calc_step_length(oipm_t *S, int combined)
+{
+    double at = S->ltau < 0.0 ? -S->vtau / S->ltau : 1.7976931348623157e308;
+    double ak = S->lkap < 0.0 ? -S->vkap / S->lkap : 1.7976931348623157e308;
+    double a = fmin(fmin(at, ak), 1.0);
+    a = cones_step_length(S, S->lz, S->ls, S->vz, S->vs, a);
+    if (combined) a *= S->set.max_step_fraction;
+    return a;
+}
+
+static void save_prev(oipm_t *S)
+{
+    oipm_info *I = &S->info;
+    S->prev_cost_primal = I->cost_primal; S->prev_cost_dual = I->cost_dual;
+    S->prev_res_primal = I->res_primal; S->prev_res_dual = I->res_dual;
+    S->prev_gap_abs = I->gap_abs; S->prev_gap_rel = I->gap_rel;
+    memcpy(S->px, S->vx, (size_t)S->n * sizeof(double)); memcpy(S->ps, S->vs, (size_t)S->m * sizeof(double));
+    memcpy(S->pz, S->vz, (size_t)S->m * sizeof(double)); S->ptau = S->vtau; S->pkap = S->vkap;
+}
+static void reset_to_prev(oipm_t *S)
+{
+    oipm_info *I = &S->info;
+    I->cost_primal = S->prev_cost_primal; I->cost_dual = S->prev_cost_dual;
+    I->res_primal = S->prev_res_primal; I->res_dual = S->prev_res_dual;
+    I->gap_abs = S->prev_gap_abs; I->gap_rel = S->prev_gap_rel;
+    memcpy(S->vx, S->px, (size_t)S->n * sizeof(double)); memcpy(S->vs, S->ps, (size_t)S->m * sizeof(double));
+    memcpy(S->vz, S->pz, (size_t)S->m * sizeof(double)); S->vtau = S->ptau; S->vkap = S->pkap;
+}
+
+/* per-iteration trace for the parity tests: [mu, alpha, sigma, res_primal, res_dual, gap_abs] */
+#define OIPM_TRACE_W 6
+int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
+{
+    if (!S->ldl) return -1;
+    idx n = S->n, m = S->m;
+    oipm_info *I = &S->info;
+    int iter = 0; double sigma = 1.0, alpha = 0.0, mu = 0.0;
+    double t0 = now_s();
+    I->status = ST_UNSOLVED; I->iterations = 0;
+    I->t_kkt_update = I->t_kkt_solve = I->t_scale_cones = 0; I->n_refactor = I->n_ldl_solve = 0;
+    /* default start: all supported cones are symmetric */
+    cones_set_identity(S);
+    kktsystem_update(S);
+    solve_initial_point(S);
+    shift_to_cone_interior(S, S->vs, 1);
+    shift_to_cone_interior(S, S->vz, 0);
+    S->vtau = 1.0; S->vkap = 1.0;
+
+    for (;;) {
+        residuals_update(S);
+        mu = (S->dot_sz + S->vtau * S->vkap) / (double)(S->degree + 1);
+        I->mu = mu; I->step_length = alpha; I->sigma = sigma; I->iterations = iter;
+        info_update(S, t0);
+        if (trace && iter < trace_cap) {
+            double *tr = trace + (size_t)iter * OIPM_TRACE_W;
+            tr[0] = mu; tr[1] = alpha; tr[2] = sigma; tr[3] = I->res_primal; tr[4] = I->res_dual; tr[5] = I->gap_abs;
+        }
+        if (check_termination(S, iter)) {
+            if (I->status == ST_INSUFFICIENT_PROGRESS) reset_to_prev(S);
+            break;
+        }
+        double ts = now_s();
+        int okscale = cones_update_scaling(S, S->vs, S->vz);
+        I->t_scale_cones += now_s() - ts;
+        if (!okscale) { I->status = ST_NUMERICAL_ERROR; break; }
+        iter += 1;
+        int ok = kktsystem_update(S);
+        /* affine rhs */
+        memcpy(S->rx_, S->rx, (size_t)n * sizeof(double));
+        memcpy(S->rz_, S->rz, (size_t)m * sizeof(double));
+        cones_affine_ds(S, S->rs_);
+        S->rtau_ = S->rtau; S->rkap_ = S->vtau * S->vkap;
+        ok = ok && kktsystem_solve(S, 0);
+        if (ok) {
+            alpha = calc_step_length(S, 0);
+            sigma = (1.0 - alpha) * (1.0 - alpha) * (1.0 - alpha);
+            double mm = iter > 1 ? 1.0 : alpha;
+            double dsm = sigma * mu;
+            for (idx i = 0; i < n; i++) S->rx_[i] = (1.0 - sigma) * S->rx[i] + 0.0 * S->rx_[i];
+            S->rtau_ = (1.0 - sigma) * S->rtau;
+            S->rkap_ = -dsm + mm * S->ltau * S->lkap + S->vtau * S->vkap;
+            if (mm != 1.0) for (idx i = 0; i < m; i++) S->lz[i] *= mm;
+            cones_combined_ds_shift(S, S->rz_, S->lz, S->ls, dsm);
+            for (idx i = 0; i < m; i++) S->rs_[i] = 1.0 * S->rz_[i] + 1.0 * S->rs_[i];
+            for (idx i = 0; i < m; i++) S->rz_[i] = (1.0 - sigma) * S->rz[i] + 0.0 * S->rz_[i];
+            ok = kktsystem_solve(S, 1);
+        }
+        if (!ok) { I->status = ST_NUMERICAL_ERROR; alpha = 0.0; break; }
+        alpha = calc_step_length(S, 1);
+        if (alpha <= fmax(0.0, S->set.min_terminate_step_length)) { I->status = ST_INSUFFICIENT_PROGRESS; alpha = 0.0; break; }
+        save_prev(S);
+        for (idx i = 0; i < n; i++) S->vx[i] = alpha * S->lx[i] + 1.0 * S->vx[i];
+        for (idx i = 0; i < m; i++) S->vs[i] = alpha * S->ls[i] + 1.0 * S->vs[i];
+        for (idx i = 0; i < m; i++) S->vz[i] = alpha * S->lz[i] + 1.0 * S->vz[i];
+        S->vtau += alpha * S->ltau; S->vkap += alpha * S->lkap;
+    }
+    if (alpha == 0.0) { I->mu = mu; I->step_length = alpha; I->sigma = sigma; I->iterations = iter; }
+    /* post-process: "almost" statuses after an error / limit exit (info.rs:95-105) */
+    if (I->status == ST_NUMERICAL_ERROR || I->status == ST_INSUFFICIENT_PROGRESS ||
+        I->status == ST_MAX_ITERATIONS || I->status == ST_MAX_TIME) {
+        const oipm_settings *T = &S->set;
+        check_convergence(S, T->reduced_tol_gap_abs, T->reduced_tol_gap_rel, T->reduced_tol_feas,
+                          T->reduced_tol_infeas_abs, T->reduced_tol_infeas_rel, T->reduced_tol_ktratio,
+                          ST_ALMOST_SOLVED, ST_ALMOST_PRIMAL_INFEASIBLE, ST_ALMOST_DUAL_INFEASIBLE);
+    }
+    I->solve_time = now_s() - t0;
+    return 0;
+}
+
+/* unscaled solution (variables.rs:262-285, solution.rs:68-111) */
+void oipm_get_solution(oipm_t *S, double *x, double *z, double *s, double *obj, double *obj_dual)
+{
+    int st = S->info.status;
+    int infeas = (st == ST_PRIMAL_INFEASIBLE || st == ST_DUAL_INFEASIBLE ||
+                  st == ST_ALMOST_PRIMAL_INFEASIBLE || st == ST_ALMOST_DUAL_INFEASIBLE);
+    double scaleinv = infeas ? 1.0 / S->vkap : 1.0 / S->vtau;
+    double cinv = 1.0 / S->c;
+    for (idx i = 0; i < S->n; i++) x[i] = S->vx[i] * S->d[i] * scaleinv;
+    for (idx i = 0; i < S->m; i++) z[i] = S->vz[i] * S->e[i] * (scaleinv * cinv);
+    for (idx i = 0; i < S->m; i++) s[i] = S->vs[i] * S->einv[i] * scaleinv;
+    *obj = infeas ? NAN : S->info.cost_primal;
+    *obj_dual = infeas ? NAN : S->info.cost_dual;
+}
+void oipm_get_info(const oipm_t *S, oipm_info *out) { *out = S->info; }
+
+/* expose single pieces for unit-level parity tests of the CUDA cone kernels */
+int oipm_test_update_scaling(oipm_t *S, const double *s, const double *z) { return cones_update_scaling(S, s, z); }
+void oipm_test_get_Hs(oipm_t *S, double *Hs) { cones_get_Hs(S, Hs); }
+idx oipm_nHs(const oipm_t *S) { return S->nHs; }
+void oipm_test_mul_Hs(oipm_t *S, double *y, const double *x) { cones_mul_Hs(S, y, x); }
+void oipm_test_affine_ds(oipm_t *S, double *ds) { cones_affine_ds(S, ds); }
+void oipm_test_combined_ds_shift(oipm_t *S, double *shift, double *sz, double *ss, double sm) { cones_combined_ds_shift(S, shift, sz, ss, sm); }
+void oipm_test_ds_from_dz_offset(oipm_t *S, double *out, const double *ds, const double *z) { cones_ds_from_dz_offset(S, out, ds, z); }
+double oipm_test_step_length(oipm_t *S, const double *dz, const double *ds, const double *z, const double *s, double amax) { return cones_step_length(S, dz, ds, z, s, amax); }
