@@ -7,7 +7,7 @@ CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libclarabel_b200.so
 ORACLE    := oracle/liboracle.so
 GENCODE   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC,-O3,-Wall -Xptxas -v
+NVFLAGS   := -O3 -std=c++17 -lineinfo --extended-lambda $(GENCODE) -Xcompiler -fPIC,-O3,-Wall -Xptxas -v
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
 CU_OBJS   := $(CU_SRCS:.cu=.o)

@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: IPM iterations/s (and KKT-solve / refactor ms)
+on BASELINE.json config C2 (random sparse QP n=1e5, m=2e5, nnz(A)=1e6, Nonneg cone).
+
+A "step" is one interior-point iteration = one pass of the hot path: cone
+scaling update, KKT value update + static regularisation + numeric LDL^T
+refactor, constant-rhs solve, affine + combined KKT solves (each with iterative
+refinement), step lengths, iterate update.
+
+  python bench.py --gpus N --steps K --warmup W          our CUDA path
+  python bench.py --impl reference ...                   reference algorithm on the host CPU
+
+`value`  : K real iterations (after W untimed warm-up iterations) timed with CUDA
+           events on the solver's stream, problem resident in HBM.
+`e2e`    : the same metric through the public API from HOST buffers:
+           create (equilibrate + order + symbolic analysis + H2D) + solve + solution D2H.
+N > 1    : one process per GPU (torchrun), one independent problem per rank (seed+rank),
+           no data-path collective (replicas); value = N*K / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def load_workload(name, rank):
+    from helpers import workloads
+    if name == "c2":
+        pr = workloads.random_sparse_qp(n=100_000, m=200_000, nnz_per_row=5, seed=1 + rank, window=200)
+        desc = ("random sparse QP n=1e5 m=2e5 nnz(A)=1e6 (5/row, columns drawn inside a sliding 200-column "
+                "window), Nonneg(2e5), seed=%d" % (1 + rank))
+    elif name == "c2small":
+        pr = workloads.random_sparse_qp(n=10_000, m=20_000, nnz_per_row=5, seed=1 + rank, window=200)
+        desc = "random sparse QP n=1e4 m=2e4 nnz(A)=1e5, Nonneg, seed=%d" % (1 + rank)
+    elif name == "c3":
+        pr = workloads.portfolio_socp(seed=2 + rank)
+        desc = "portfolio SOCP 5000 assets, 200 SOC(26), seed=%d" % (2 + rank)
+    elif name == "c4":
+        pr = workloads.block_angular_qp(seed=3 + rank)
+        desc = "block-angular sparse QP n=1e6 m=1.5e6, seed=%d" % (3 + rank)
+    else:
+        raise SystemExit("unknown workload " + name)
+    return pr, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(li, N, nnzK):
+    """DESIGN.md 'roofline accounting': bytes one launch sequence must move at minimum."""
+    refactor = 20 * nnzK + 8 * li.nnzL_stored + 16 * N          # read values+maps, write panels, D, Dinv
+    solve = 2 * 8 * li.nnzL_stored + 40 * N                      # panels read in both sweeps + vectors/perm
+    return refactor, solve
+
+
+def run_ours(args, rank, world):
+    import torch
+    import clarabel_rs_b200 as cb
+    dev_index = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev_index)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev_index))
+    pr, desc = load_workload(args.workload, rank)
+    P, q, A, b, cones = pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"]
+    n, m = P.shape[0], A.shape[0]
+    h2d_bytes = (P.data.nbytes + P.indices.size * 4 + A.data.nbytes * 2 + A.indices.size * 8 + 8 * (n + m) * 2)
+
+    # ---------------- e2e through the public API from host buffers ----------------
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    solver = cb.CudaSolver(P, q, A, b, cones, ordering=cb.ORDER_ND, device=dev_index)
+    t_setup = time.perf_counter() - t0
+    res = solver.solve()                      # includes the D2H of (x, z, s)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    iters_e2e = res["iterations"]
+    li = solver.linear_solver_info()
+    info = solver.info
+    d2h_bytes = 8 * (n + 2 * m)
+
+    # ---------------- device-resident K iterations after W warm-up iterations ----------------
+    W, K = args.warmup, args.steps
+    clocks = ClockSampler(dev_index)
+    launches0 = cb.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    durations, launches_timed, first = [], 0, True
+    status_all = [res["status"]]
+    while len(durations) < K:
+        l0 = cb.launch_count()
+        r = solver.solve()
+        l1 = cb.launch_count()
+        status_all.append(r["status"])
+        d = np.diff(solver.iter_ms)[:r["iterations"]]      # per-iteration device time (ms)
+        if len(d) == 0:
+            raise SystemExit("solver made no iterations")
+        per_iter_launch = (l1 - l0) / max(len(d), 1)
+        if first:
+            d = d[W:] if len(d) > W else d[-1:]
+            first = False
+        take = d[:K - len(durations)]
+        durations.extend(take.tolist())
+        launches_timed += int(per_iter_launch * len(take))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    t_local = float(np.sum(durations)) / 1e3
+    t_max = t_local
+    if world > 1:
+        t = torch.tensor([t_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max = float(t.item())
+        te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        t_e2e = float(te.item())
+    value = world * K / t_max
+    e2e_value = world * iters_e2e / t_e2e
+
+    out = None
+    if rank == 0:
+        # ---------------- kernel-level timings + roofline (live, CUDA events) ----------------
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        refactor_ms = solver.time_ms("refactor", 5)
+        ldl_solve_ms = solver.time_ms("ldl_solve", 20)
+        kkt_solve_ms = solver.time_ms("kkt_solve", 5)
+        b_ref, b_sol = algorithmic_bytes(li, solver.N, int(info.nnzK))
+        solves_per_iter = info.n_ldl_solve / max(info.n_refactor, 1)
+        share_ref = refactor_ms
+        share_sol = ldl_solve_ms * solves_per_iter
+        rf_ref = {"kernel": "k_factor_level (numeric LDL^T refactor, all levels)", "bound": "hbm",
+                  "achieved": b_ref / (refactor_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": b_ref / (refactor_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                  "algorithmic_bytes": b_ref, "ms": refactor_ms, "share_of_step_ms": share_ref,
+                  "fp64_gflops": li.flops / (refactor_ms * 1e-3) / 1e9, "peak_source": peak_src}
+        rf_sol = {"kernel": "k_fwd_level + k_bwd_level (one LDL solve, all levels)", "bound": "hbm",
+                  "achieved": b_sol / (ldl_solve_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": b_sol / (ldl_solve_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                  "algorithmic_bytes": b_sol, "ms": ldl_solve_ms, "share_of_step_ms": share_sol,
+                  "peak_source": peak_src}
+        dominant, other = (rf_ref, rf_sol) if share_ref >= share_sol else (rf_sol, rf_ref)
+        cpu = cpu_baseline(pr, sample_iters=args.cpu_sample_iters) if (world == 1 and not args.no_cpu_baseline) else None
+        out = {
+            "metric": "ipm_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "n": n, "m": m, "nnzA": int(A.nnz), "nnzP_triu": int(P.nnz),
+                       "kkt_dim": solver.N, "nnzK": int(info.nnzK), "nnzL": int(li.nnzL),
+                       "nnzL_stored": int(li.nnzL_stored), "levels": int(li.n_levels),
+                       "supernodes": int(li.n_supernodes), "ordering": "nested dissection + AMD leaves",
+                       "cache": "working set larger than L2 (factor panels %.0f MB)" % (li.nnzL_stored * 8 / 1e6),
+                       "parallelism": "replicas x%d" % world},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d_bytes / max(iters_e2e, 1),
+                    "d2h_bytes_per_step": d2h_bytes / max(iters_e2e, 1), "setup_s": t_setup,
+                    "total_s": t_e2e, "iterations": iters_e2e,
+                    "note": "create (equilibrate+order+symbolic+H2D) + solve + solution D2H, from host numpy buffers"},
+            "gpu_launches": launches_timed,
+            "roofline": dominant, "roofline_other": other,
+            "kkt_solve_ms": kkt_solve_ms, "ldl_solve_ms": ldl_solve_ms, "refactor_ms": refactor_ms,
+            "ldl_solves_per_iteration": solves_per_iter,
+            "status": status_all[0], "iterations": iters_e2e,
+            "cpu_baseline": cpu,
+        }
+    solver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_solve(pr, max_iter):
+    """Reference algorithm on the host: oracle IPM + oracle qdldl, single thread, AMD ordering
+    (the reference orders with AMD at dense-scale 1.5; the `amd` crate is not vendored, ours stands in)."""
+    import clarabel_rs_b200 as cb
+    import oracle
+    t0 = time.perf_counter()
+    ipm = oracle.IPM(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"],
+                     settings=oracle.default_settings(max_iter=max_iter))
+    N, cp, rv, _, _ = ipm.kkt()
+    perm = cb.order(N, cp, rv, cb.ORDER_AMD, 1.5)
+    ipm.set_perm(perm)
+    t_setup = time.perf_counter() - t0
+    r = ipm.solve()
+    t_total = time.perf_counter() - t0
+    return ipm, r, t_setup, t_total
+
+
+def cpu_baseline(pr, sample_iters=3):
+    ipm, r, t_setup, t_total = cpu_solve(pr, sample_iters)
+    i = r["info"]
+    return {"value": r["iterations"] / i.solve_time, "unit": "iterations/s", "cores": 1, "kind": "port",
+            "sample": "first %d IPM iterations of the same problem (oracle IPM + oracle qdldl, AMD order, 1 thread)" % r["iterations"],
+            "host_cores_available": os.cpu_count(), "solve_s": i.solve_time, "setup_s": t_setup,
+            "refactor_ms": 1e3 * i.t_kkt_update / max(i.n_refactor, 1), "nnzL": int(i.nnzL),
+            "kkt_solve_ms": 1e3 * i.t_kkt_solve / max(2 * r["iterations"], 1)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    pr, desc = load_workload(args.workload, 0)
+    W, K = args.warmup, args.steps
+    ipm, r, t_setup, t_total = cpu_solve(pr, W + K)
+    i = r["info"]
+    iters = r["iterations"]
+    value = iters / i.solve_time
+    return {
+        "impl": "reference", "metric": "ipm_iterations_per_sec", "value": value, "unit": "iterations/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * i.solve_time / max(iters, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "n": ipm.n, "m": ipm.m, "kkt_dim": ipm.N, "nnzK": int(i.nnzK),
+                   "nnzL": int(i.nnzL), "ordering": "AMD (dense scale 1.5)", "parallelism": "1 host thread"},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port",
+                         "sample": "first %d IPM iterations (max_iter=W+K) of the same problem; the reference is Rust "
+                                   "and cannot be built here, so this is the line-faithful C port (oracle/)" % iters,
+                         "host_cores_available": os.cpu_count(), "setup_s": t_setup,
+                         "refactor_ms": 1e3 * i.t_kkt_update / max(i.n_refactor, 1)},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "iterations": iters, "status": r["status"],
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--cpu-sample-iters", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    import __graft_entry__
+    if not (os.path.exists(os.path.join(ROOT, "clarabel.rs_b200", "libclarabel_b200.so"))
+            and os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
+        if rank == 0:
+            __graft_entry__.build()
+    out = run_reference(args, rank, world) if args.impl == "reference" else run_ours(args, rank, world)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -325,3 +325,305 @@ def order(n, colptr, rowval, kind=ORDER_AMD, dense_scale=1.5, nd_leaf=200):
     if rc:
         raise BackendError("ordering failed")
     return out.astype(np.int64)
+
+
+# ===========================================================================
+# Level 2: device-resident solver (cipm_* / ckkt_* / ccone_*)
+# ===========================================================================
+CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3}
+STATUS_NAMES = ["Unsolved", "Solved", "PrimalInfeasible", "DualInfeasible", "AlmostSolved",
+                "AlmostPrimalInfeasible", "AlmostDualInfeasible", "MaxIterations", "MaxTime",
+                "NumericalError", "InsufficientProgress"]
+
+
+class cipm_settings(C.Structure):
+    """DefaultSettings fields read by the path (default/settings.rs:30-193)."""
+    _fields_ = [
+        ("max_iter", C.c_int32), ("time_limit", C.c_double), ("max_step_fraction", C.c_double),
+        ("tol_gap_abs", C.c_double), ("tol_gap_rel", C.c_double), ("tol_feas", C.c_double),
+        ("tol_infeas_abs", C.c_double), ("tol_infeas_rel", C.c_double), ("tol_ktratio", C.c_double),
+        ("reduced_tol_gap_abs", C.c_double), ("reduced_tol_gap_rel", C.c_double),
+        ("reduced_tol_feas", C.c_double), ("reduced_tol_infeas_abs", C.c_double),
+        ("reduced_tol_infeas_rel", C.c_double), ("reduced_tol_ktratio", C.c_double),
+        ("equilibrate_enable", C.c_int32), ("equilibrate_max_iter", C.c_int32),
+        ("equilibrate_min_scaling", C.c_double), ("equilibrate_max_scaling", C.c_double),
+        ("min_terminate_step_length", C.c_double),
+        ("static_regularization_enable", C.c_int32),
+        ("static_regularization_constant", C.c_double),
+        ("static_regularization_proportional", C.c_double),
+        ("dynamic_regularization_enable", C.c_int32),
+        ("dynamic_regularization_eps", C.c_double), ("dynamic_regularization_delta", C.c_double),
+        ("iterative_refinement_enable", C.c_int32),
+        ("iterative_refinement_reltol", C.c_double), ("iterative_refinement_abstol", C.c_double),
+        ("iterative_refinement_max_iter", C.c_int32),
+        ("iterative_refinement_stop_ratio", C.c_double),
+    ]
+
+
+class cipm_info(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("iterations", C.c_uint32),
+        ("cost_primal", C.c_double), ("cost_dual", C.c_double), ("res_primal", C.c_double),
+        ("res_dual", C.c_double), ("res_primal_inf", C.c_double), ("res_dual_inf", C.c_double),
+        ("gap_abs", C.c_double), ("gap_rel", C.c_double), ("ktratio", C.c_double), ("mu", C.c_double),
+        ("step_length", C.c_double), ("sigma", C.c_double),
+        ("solve_time", C.c_double), ("device_ms", C.c_double),
+        ("t_kkt_update", C.c_double), ("t_kkt_solve", C.c_double), ("t_scale_cones", C.c_double),
+        ("n_refactor", C.c_uint64), ("n_ldl_solve", C.c_uint64), ("n_ir_steps", C.c_uint64),
+        ("regularize_count", C.c_uint64),
+        ("nnzK", C.c_uint64), ("nnzL", C.c_uint64), ("kkt_dim", C.c_uint64),
+    ]
+
+    @property
+    def status_name(self):
+        return STATUS_NAMES[self.status]
+
+
+EXPORTED_SYMBOLS += [
+    "cipm_default_settings", "cipm_create", "cipm_destroy", "cipm_solve", "cipm_get_info",
+    "cipm_get_solution", "cipm_trace", "cipm_iter_ms", "cipm_launch_count", "cipm_time_ms", "cipm_kkt_dim", "cipm_kkt_nnz", "cipm_get_kkt",
+    "cipm_get_kkt_perm", "cipm_ldl_info", "ckkt_update", "ckkt_setrhs", "ckkt_solve", "ckkt_update_P",
+    "ckkt_update_A", "ckkt_get_values", "ccone_set_identity_scaling", "ccone_update_scaling",
+    "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
+    "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
+]
+
+_l2_ready = False
+
+
+def _lib2():
+    global _l2_ready
+    L = lib()
+    if _l2_ready:
+        return L
+    vp, u64p, f64p, i8p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_int8)
+    L.cipm_default_settings.argtypes = [C.POINTER(cipm_settings)]
+    L.cipm_default_settings.restype = None
+    L.cipm_create.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p, u64p, u64p, f64p,
+                              f64p, C.c_uint64, C.POINTER(C.c_int32), u64p, C.POINTER(cipm_settings),
+                              C.POINTER(cldl_opts), u64p]
+    L.cipm_destroy.argtypes = [vp]
+    L.cipm_destroy.restype = None
+    L.cipm_solve.argtypes = [vp]
+    L.cipm_get_info.argtypes = [vp, C.POINTER(cipm_info)]
+    L.cipm_get_info.restype = None
+    L.cipm_get_solution.argtypes = [vp, f64p, f64p, f64p]
+    L.cipm_trace.argtypes = [vp, f64p, C.c_uint64]
+    L.cipm_trace.restype = C.c_uint64
+    L.cipm_iter_ms.argtypes = [vp, f64p, C.c_uint64]
+    L.cipm_iter_ms.restype = C.c_uint64
+    L.cipm_launch_count.argtypes = []
+    L.cipm_launch_count.restype = C.c_uint64
+    L.cipm_time_ms.argtypes = [vp, C.c_int, C.c_int]
+    L.cipm_time_ms.restype = C.c_double
+    for nm in ["cipm_kkt_dim", "cipm_kkt_nnz", "ccone_Hs_len"]:
+        getattr(L, nm).argtypes = [vp]
+        getattr(L, nm).restype = C.c_uint64
+    L.cipm_get_kkt.argtypes = [vp, u64p, u64p, f64p, i8p]
+    L.cipm_get_kkt_perm.argtypes = [vp, u64p]
+    L.cipm_ldl_info.argtypes = [vp, C.POINTER(cldl_info_t)]
+    L.cipm_ldl_info.restype = None
+    L.ckkt_update.argtypes = [vp]
+    L.ckkt_setrhs.argtypes = [vp, f64p, f64p]
+    L.ckkt_solve.argtypes = [vp, f64p, f64p]
+    L.ckkt_update_P.argtypes = [vp, f64p]
+    L.ckkt_update_A.argtypes = [vp, f64p]
+    L.ckkt_get_values.argtypes = [vp, f64p]
+    L.ccone_set_identity_scaling.argtypes = [vp]
+    L.ccone_update_scaling.argtypes = [vp, f64p, f64p]
+    L.ccone_get_Hs.argtypes = [vp, f64p]
+    L.ccone_mul_Hs.argtypes = [vp, f64p, f64p]
+    L.ccone_affine_ds.argtypes = [vp, f64p]
+    L.ccone_combined_ds_shift.argtypes = [vp, f64p, f64p, f64p, C.c_double]
+    L.ccone_ds_from_dz_offset.argtypes = [vp, f64p, f64p, f64p]
+    L.ccone_step_length.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double, f64p]
+    L.ccone_margins.argtypes = [vp, f64p, f64p, f64p]
+    L.ccone_scaled_unit_shift.argtypes = [vp, f64p, C.c_double, C.c_int]
+    _l2_ready = True
+    return L
+
+
+def default_settings(**kw):
+    s = cipm_settings()
+    _lib2().cipm_default_settings(C.byref(s))
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+class CudaSolver:
+    """Device interior-point solver: mirrors ``DefaultSolver::new(P,q,A,b,cones,settings)``
+    and ``solve()`` (default/solver.rs:57-126, core/solver.rs:242-465).
+
+    P: scipy sparse (symmetric or upper triangle; converted to triu like
+    problemdata.rs:79-81); A: scipy sparse; cones: list of (kind, dim).
+    """
+
+    def __init__(self, P, q, A, b, cones, settings=None, *, ordering=ORDER_BEST, kkt_perm=None,
+                 device=0, max_panel=0, nd_leaf=0):
+        import scipy.sparse as sp
+        L = _lib2()
+        self._L = L
+        P = sp.triu(sp.csc_matrix(P), format="csc")
+        P.sort_indices()
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        self.n, self.m = P.shape[0], A.shape[0]
+        self.settings = settings if settings is not None else default_settings()
+        o = cldl_opts()
+        L.cldl_default_opts(C.byref(o))
+        o.ordering, o.device, o.max_panel, o.nd_leaf = ordering, device, max_panel, nd_leaf
+        ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
+        cd = _u64([d for _, d in cones])
+        Pp, Pi, Px = _u64(P.indptr), _u64(P.indices), _f64(P.data)
+        Ap, Ai, Ax = _u64(A.indptr), _u64(A.indices), _f64(A.data)
+        qq, bb = _f64(q), _f64(b)
+        pm = _u64(kkt_perm) if kkt_perm is not None else None
+        h = C.c_void_p()
+        rc = L.cipm_create(C.byref(h), self.n, self.m, _p(Pp, C.c_uint64), _p(Pi, C.c_uint64), _p(Px, C.c_double),
+                           _p(qq, C.c_double), _p(Ap, C.c_uint64), _p(Ai, C.c_uint64), _p(Ax, C.c_double),
+                           _p(bb, C.c_double), len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)),
+                           _p(cd, C.c_uint64), C.byref(self.settings), C.byref(o),
+                           _p(pm, C.c_uint64) if pm is not None else None)
+        _check(rc, "cipm_create")
+        self._h = h
+        self.N = int(L.cipm_kkt_dim(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cipm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self):
+        _check(self._L.cipm_solve(self._h), "cipm_solve")
+        info = cipm_info()
+        self._L.cipm_get_info(self._h, C.byref(info))
+        x, z, s = np.zeros(max(self.n, 1)), np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
+        _check(self._L.cipm_get_solution(self._h, _p(x, C.c_double), _p(z, C.c_double), _p(s, C.c_double)),
+               "cipm_get_solution")
+        rows = int(self._L.cipm_trace(self._h, None, 0))
+        tr = np.zeros((max(rows, 1), 6))
+        self._L.cipm_trace(self._h, _p(tr.reshape(-1), C.c_double), rows)
+        self.info, self.trace = info, tr[:rows]
+        k = int(self._L.cipm_iter_ms(self._h, None, 0))
+        it = np.zeros(max(k, 1))
+        self._L.cipm_iter_ms(self._h, _p(it, C.c_double), k)
+        self.iter_ms = it[:k]
+        infeas = "Infeasible" in info.status_name
+        return dict(status=info.status_name, iterations=int(info.iterations), x=x[:self.n], z=z[:self.m],
+                    s=s[:self.m], obj_val=float("nan") if infeas else info.cost_primal,
+                    obj_val_dual=float("nan") if infeas else info.cost_dual, info=info)
+
+    def time_ms(self, which, reps):
+        """which: 'refactor' | 'ldl_solve' | 'kkt_solve' (device time, CUDA events)."""
+        return self._L.cipm_time_ms(self._h, {'refactor': 0, 'ldl_solve': 1, 'kkt_solve': 2}[which], int(reps))
+
+    def kkt(self):
+        N, nnz = self.N, int(self._L.cipm_kkt_nnz(self._h))
+        cp, rv = np.zeros(N + 1, np.uint64), np.zeros(max(nnz, 1), np.uint64)
+        nz, ds = np.zeros(max(nnz, 1)), np.zeros(N, np.int8)
+        _check(self._L.cipm_get_kkt(self._h, _p(cp, C.c_uint64), _p(rv, C.c_uint64), _p(nz, C.c_double),
+                                    _p(ds, C.c_int8)), "get_kkt")
+        return N, cp.astype(np.int64), rv[:nnz].astype(np.int64), nz[:nnz], ds
+
+    def kkt_perm(self):
+        p = np.zeros(self.N, np.uint64)
+        _check(self._L.cipm_get_kkt_perm(self._h, _p(p, C.c_uint64)), "get_kkt_perm")
+        return p.astype(np.int64)
+
+    def kkt_values(self):
+        nz = np.zeros(max(int(self._L.cipm_kkt_nnz(self._h)), 1))
+        _check(self._L.ckkt_get_values(self._h, _p(nz, C.c_double)), "kkt_values")
+        return nz[:int(self._L.cipm_kkt_nnz(self._h))]
+
+    def linear_solver_info(self):
+        i = cldl_info_t()
+        self._L.cipm_ldl_info(self._h, C.byref(i))
+        return LinearSolverInfo(i.name.decode(), i.threads, bool(i.direct), i.nnzA, i.nnzL, i.nnzL_stored,
+                                i.regularize_count, i.positive_inertia, i.n_supernodes, i.n_levels, i.flops,
+                                i.ordering_used)
+
+    # ---- KKTSolver trait ----
+    def kkt_update(self):
+        return bool(_check(self._L.ckkt_update(self._h), "ckkt_update"))
+
+    def kkt_setrhs(self, rx, rz):
+        rx, rz = _f64(rx), _f64(rz)
+        _check(self._L.ckkt_setrhs(self._h, _p(rx, C.c_double), _p(rz, C.c_double)), "ckkt_setrhs")
+
+    def kkt_solve(self):
+        x, z = np.zeros(max(self.n, 1)), np.zeros(max(self.m, 1))
+        ok = _check(self._L.ckkt_solve(self._h, _p(x, C.c_double), _p(z, C.c_double)), "ckkt_solve")
+        return bool(ok), x[:self.n], z[:self.m]
+
+    # ---- Cone trait ----
+    def _m(self, a):
+        a = _f64(a)
+        assert a.size == self.m
+        return a
+
+    def cone_set_identity_scaling(self):
+        _check(self._L.ccone_set_identity_scaling(self._h), "set_identity_scaling")
+
+    def cone_update_scaling(self, s, z):
+        s, z = self._m(s), self._m(z)
+        return bool(_check(self._L.ccone_update_scaling(self._h, _p(s, C.c_double), _p(z, C.c_double)), "update_scaling"))
+
+    def cone_get_Hs(self):
+        ln = int(self._L.ccone_Hs_len(self._h))
+        out = np.zeros(max(ln, 1))
+        _check(self._L.ccone_get_Hs(self._h, _p(out, C.c_double)), "get_Hs")
+        return out[:ln]
+
+    def cone_mul_Hs(self, x):
+        x = self._m(x)
+        y = np.zeros(max(self.m, 1))
+        _check(self._L.ccone_mul_Hs(self._h, _p(y, C.c_double), _p(x, C.c_double)), "mul_Hs")
+        return y[:self.m]
+
+    def cone_affine_ds(self):
+        y = np.zeros(max(self.m, 1))
+        _check(self._L.ccone_affine_ds(self._h, _p(y, C.c_double)), "affine_ds")
+        return y[:self.m]
+
+    def cone_combined_ds_shift(self, step_z, step_s, sigmamu):
+        a, b = self._m(step_z), self._m(step_s)
+        y = np.zeros(max(self.m, 1))
+        _check(self._L.ccone_combined_ds_shift(self._h, _p(y, C.c_double), _p(a, C.c_double), _p(b, C.c_double),
+                                               float(sigmamu)), "combined_ds_shift")
+        return y[:self.m]
+
+    def cone_ds_from_dz_offset(self, ds, z):
+        a, b = self._m(ds), self._m(z)
+        y = np.zeros(max(self.m, 1))
+        _check(self._L.ccone_ds_from_dz_offset(self._h, _p(y, C.c_double), _p(a, C.c_double), _p(b, C.c_double)),
+               "ds_from_dz_offset")
+        return y[:self.m]
+
+    def cone_step_length(self, dz, ds, z, s, amax=1.0):
+        a, b, c, d = self._m(dz), self._m(ds), self._m(z), self._m(s)
+        out = C.c_double()
+        _check(self._L.ccone_step_length(self._h, _p(a, C.c_double), _p(b, C.c_double), _p(c, C.c_double),
+                                         _p(d, C.c_double), float(amax), C.byref(out)), "step_length")
+        return out.value
+
+    def cone_margins(self, z):
+        z = self._m(z)
+        a, b = C.c_double(), C.c_double()
+        _check(self._L.ccone_margins(self._h, _p(z, C.c_double), C.byref(a), C.byref(b)), "margins")
+        return a.value, b.value
+
+    def cone_scaled_unit_shift(self, z, alpha, primal):
+        z = self._m(z).copy()
+        _check(self._L.ccone_scaled_unit_shift(self._h, _p(z, C.c_double), float(alpha), 1 if primal else 0), "unit_shift")
+        return z
+
+
+def launch_count():
+    return int(_lib2().cipm_launch_count())

@@ -26,8 +26,11 @@
 #include "../../include/clarabel_b200.h"
 #include "ldl_device.h"
 #include "symbolic.h"
+#include "vec.cuh"
 
 namespace cb {
+
+unsigned long long g_launches = 0;
 
 // ------------------------------------------------------------------------
 // kernels
@@ -386,6 +389,7 @@ void LDLObject::release() {
 int LDLObject::refactor_async() {
   CK(cudaSetDevice(device));
   CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
+  g_launches += plan.size();
   for (const LaunchSeg& g : plan) {
     if (g.threads == 64)
       k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
@@ -410,6 +414,7 @@ int LDLObject::sync_status() {
 int LDLObject::solve_async(double* d_x, const double* d_b) {
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
+  g_launches += 1 + 2 * (unsigned long long)S.nlevels;
   k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
   for (int l = 0; l < S.nlevels; l++) {
     int b = S.level_ptr[l], cnt = S.level_ptr[l + 1] - b;

@@ -1,0 +1,118 @@
+// Device vector kernels and deterministic reductions (internal header).
+//
+// Counterpart of the reference's VectorMath trait
+// (/root/reference/src/algebra/vecmath.rs:83-226) for device-resident vectors.
+// Sums use a fixed two-level tree (per-block partials, then the last block to
+// finish folds them in index order) so results are bit-reproducible run to run;
+// max/min reductions use atomics on the IEEE bit pattern of non-negative
+// doubles, which are order independent (and propagate NaN like
+// vecmath.rs:132-141 does, because |NaN| orders above +inf).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace cb {
+
+// number of kernels launched by this library (bench.py reports it as gpu_launches)
+extern unsigned long long g_launches;
+
+constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
+constexpr int RED_THREADS = 256;
+
+struct ReduceWS {
+  double* partials = nullptr;    // [RED_BLOCKS * 4]
+  unsigned int* counter = nullptr;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; result valid in every thread. sh must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) { r = warp_sum(r); if (lane == 0) sh[0] = r; }
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  // NaN-propagating max for |.| values: compare bit patterns as unsigned.
+  atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_min_nonneg(double* addr, double v) {
+  atomicMin((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// out[0] = sum_i f(i), deterministic.  F is a device lambda/functor int -> double.
+template <class F>
+__global__ void __launch_bounds__(RED_THREADS) k_sum(int n, F f, ReduceWS ws, double* out) {
+  __shared__ double sh[32];
+  __shared__ bool last;
+  double acc = 0.0;
+  for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) acc += f(i);
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    ws.partials[blockIdx.x] = acc;
+    __threadfence();
+    unsigned t = atomicInc(ws.counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) a += ((volatile double*)ws.partials)[i];
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) out[0] = a;
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(RED_THREADS) k_max_nonneg(int n, F f, double* out) {
+  double m = 0.0;
+  bool nan = false;
+  for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
+    double v = fabs(f(i));
+    if (v != v) nan = true;
+    m = fmax(m, v);
+  }
+  m = warp_max(m);
+  nan = __any_sync(0xffffffffu, nan);
+  if ((threadIdx.x & 31) == 0) {
+    if (nan) atomic_max_nonneg(out, __longlong_as_double(0x7ff8000000000000LL));
+    else atomic_max_nonneg(out, m);
+  }
+}
+
+template <class F>
+__global__ void k_map(int n, F f) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+
+inline int red_grid(int n) {
+  int g = (n + RED_THREADS - 1) / RED_THREADS;
+  return g < 1 ? 1 : (g > RED_BLOCKS ? RED_BLOCKS : g);
+}
+
+}  // namespace cb

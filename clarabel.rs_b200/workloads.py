@@ -106,3 +106,93 @@ def kkt_triu(P, A, hdiag):
     colptr = np.cumsum(colptr)
     dsigns = np.concatenate([np.ones(n, dtype=np.int8), -np.ones(m, dtype=np.int8)])
     return N, colptr, r.astype(np.int64), v.astype(np.float64), dsigns
+
+
+def portfolio_socp(n_assets=5000, n_soc=200, soc_dim=26, block=100, seed=2):
+    """Config C3: min 1/2 x'Px - mu'x  s.t. 1'x = 1, x >= 0, ||G_k x_{S_k}|| <= sigma_k.
+
+    P = blockdiag of dense SPD blocks (F F'/block + 0.1 I); every SOC cone couples
+    soc_dim-1 contiguous assets through a dense G_k.
+    """
+    rng = np.random.default_rng(seed)
+    n = n_assets
+    blocks = []
+    for _ in range(n // block):
+        F = rng.standard_normal((block, block))
+        blocks.append(F @ F.T / block + 0.1 * np.eye(block))
+    rem = n - (n // block) * block
+    if rem:
+        F = rng.standard_normal((rem, rem))
+        blocks.append(F @ F.T / rem + 0.1 * np.eye(rem))
+    P = sp.triu(sp.block_diag(blocks, format="csc"), format="csc")
+    q = -rng.uniform(0.0, 0.1, size=n)
+    rows, cols, vals, b = [], [], [], []
+    # zero cone: sum x = 1
+    rows += [0] * n; cols += list(range(n)); vals += [1.0] * n; b.append(1.0)
+    r = 1
+    # nonneg: -x + s = 0
+    rows += list(range(r, r + n)); cols += list(range(n)); vals += [-1.0] * n; b += [0.0] * n
+    r += n
+    k = soc_dim - 1
+    for c in range(n_soc):
+        start = (c * (n - k)) // max(n_soc - 1, 1) if n_soc > 1 else 0
+        S = np.arange(start, start + k)
+        G = rng.standard_normal((k, k)) / 5.0
+        b.append(1.0)            # sigma_k ; first SOC row has no x dependence
+        r += 1
+        for i in range(k):
+            rows += [r + i] * k; cols += S.tolist(); vals += (-G[i]).tolist()
+        b += [0.0] * k
+        r += k
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(r, n)).tocsc()
+    A.sort_indices()
+    cones = [("zero", 1), ("nonneg", n)] + [("soc", soc_dim)] * n_soc
+    return dict(P=P, q=q, A=A, b=np.array(b), cones=cones,
+                name=f"portfolio_socp(assets={n},soc={n_soc}x{soc_dim},seed={seed})")
+
+
+def block_angular_qp(n=1_000_000, nblocks=64, rows_per_var=1.5, nlink=2000, link_blocks=16, window=64, seed=3):
+    """Config C4: block-angular sparse QP.  nblocks diagonal blocks; every ordinary
+    row touches 5-6 variables inside one block (within a sliding window, so the
+    blocks have locality), 1/6 of the rows are equalities; nlink linking rows touch
+    one variable in each of link_blocks random blocks."""
+    rng = np.random.default_rng(seed)
+    m = int(rows_per_var * n)
+    bs = n // nblocks
+    m_ord = m - nlink
+    blk = (np.arange(m_ord, dtype=np.int64) * nblocks) // m_ord
+    pos_in_blk = np.arange(m_ord, dtype=np.int64) - (blk * m_ord) // nblocks
+    rows_in_blk = np.maximum(((blk + 1) * m_ord) // nblocks - (blk * m_ord) // nblocks, 1)
+    centre = (pos_in_blk * bs) // rows_in_blk
+    k = 6
+    lo = np.clip(centre - window // 2, 0, max(bs - window, 0))
+    offs = rng.integers(0, min(window, bs), size=(m_ord, k))
+    cols = blk[:, None] * bs + lo[:, None] + offs
+    keep = np.ones((m_ord, k), dtype=bool)
+    keep[:, 5] = rng.random(m_ord) < 0.5        # 5 or 6 entries per row
+    r = np.repeat(np.arange(m_ord), k)[keep.ravel()]
+    cidx = cols.ravel()[keep.ravel()]
+    v = rng.standard_normal(cidx.size)
+    link_blocks = min(link_blocks, nblocks)
+    lr = np.repeat(np.arange(m_ord, m), link_blocks)
+    lb = np.stack([rng.choice(nblocks, size=link_blocks, replace=False) for _ in range(nlink)])
+    lc = (lb * bs + rng.integers(0, bs, size=(nlink, link_blocks))).ravel()
+    lv = rng.standard_normal(lc.size)
+    A = sp.coo_matrix((np.concatenate([v, lv]), (np.concatenate([r, lr]), np.concatenate([cidx, lc]))), shape=(m, n)).tocsc()
+    A.sum_duplicates(); A.sort_indices()
+    # P: diagonal + one off-diagonal per column inside its block
+    j = np.arange(n)
+    jn = np.minimum(j + 1, ((j // bs) + 1) * bs - 1)
+    off = sp.coo_matrix((0.05 * rng.standard_normal(n), (np.minimum(j, jn), np.maximum(j, jn))), shape=(n, n)).tocsc()
+    off = sp.triu(off, k=1, format="csc")
+    absr = np.asarray(abs(off).sum(axis=0)).ravel() + np.asarray(abs(off).sum(axis=1)).ravel()
+    P = (off + sp.diags(rng.uniform(0.1, 1.0, n) + absr)).tocsc()
+    P.sort_indices()
+    q = rng.standard_normal(n)
+    x0 = rng.standard_normal(n)
+    nz = m // 6
+    b = A @ x0
+    b[nz:] += rng.uniform(0.1, 1.0, size=m - nz)
+    cones = [("zero", nz), ("nonneg", m - nz)]
+    return dict(P=sp.triu(P, format="csc"), q=q, A=A, b=b, cones=cones,
+                name=f"block_angular_qp(n={n},blocks={nblocks},m={m},link={nlink},seed={seed})")

@@ -125,6 +125,117 @@ double *cldl_values_dev(cldl_t *h);                          /* device copy of n
 double cldl_time_refactor_ms(cldl_t *h, int reps);
 double cldl_time_solve_ms(cldl_t *h, int reps);
 
+
+/* ======================================================================
+ * LEVEL 2  (cipm_* / ckkt_* / ccone_*)  device-resident KKT system, cone
+ * engine and interior-point driver.  Replaces, for the symmetric cones
+ * (Zero / Nonnegative / SecondOrder):
+ *   trait KKTSolver      src/solver/core/kktsolvers/mod.rs:7-19
+ *     + DirectLDLKKTSolver .../direct/quasidef/directldlkktsolver.rs:18-405
+ *   trait Cone / CompositeCone  src/solver/core/cones/mod.rs:42-154,
+ *                               compositecone.rs:197-352
+ *   DefaultSolver::new / IPSolver::solve
+ *                        src/solver/implementations/default/solver.rs:57-126,
+ *                        src/solver/core/solver.rs:224-465
+ * One handle owns the equilibrated problem, the cone set, the KKT matrix and
+ * its LDL^T on one GPU.  Vectors never leave the device during a solve.
+ * ==================================================================== */
+typedef struct cipm_handle cipm_t;
+
+/* SupportedConeT tags (supportedcone.rs:17-52); PSD reserved. */
+enum { CIPM_CONE_ZERO = 0, CIPM_CONE_NONNEG = 1, CIPM_CONE_SOC = 2, CIPM_CONE_PSD = 3 };
+
+/* SolverStatus (src/solver/core/traits.rs / default/info.rs) */
+enum { CIPM_UNSOLVED = 0, CIPM_SOLVED, CIPM_PRIMAL_INFEASIBLE, CIPM_DUAL_INFEASIBLE, CIPM_ALMOST_SOLVED,
+       CIPM_ALMOST_PRIMAL_INFEASIBLE, CIPM_ALMOST_DUAL_INFEASIBLE, CIPM_MAX_ITERATIONS, CIPM_MAX_TIME,
+       CIPM_NUMERICAL_ERROR, CIPM_INSUFFICIENT_PROGRESS };
+
+/* The fields of DefaultSettings the path reads (default/settings.rs:30-193),
+ * same names, same defaults (cipm_default_settings). */
+typedef struct {
+  int32_t max_iter;
+  double time_limit;
+  double max_step_fraction;
+  double tol_gap_abs, tol_gap_rel, tol_feas, tol_infeas_abs, tol_infeas_rel, tol_ktratio;
+  double reduced_tol_gap_abs, reduced_tol_gap_rel, reduced_tol_feas, reduced_tol_infeas_abs,
+      reduced_tol_infeas_rel, reduced_tol_ktratio;
+  int32_t equilibrate_enable, equilibrate_max_iter;
+  double equilibrate_min_scaling, equilibrate_max_scaling;
+  double min_terminate_step_length;
+  int32_t static_regularization_enable;
+  double static_regularization_constant, static_regularization_proportional;
+  int32_t dynamic_regularization_enable;
+  double dynamic_regularization_eps, dynamic_regularization_delta;
+  int32_t iterative_refinement_enable;
+  double iterative_refinement_reltol, iterative_refinement_abstol;
+  int32_t iterative_refinement_max_iter;
+  double iterative_refinement_stop_ratio;
+} cipm_settings;
+
+/* DefaultInfo (default/info.rs:13-64) + timers of core/solver.rs:330-396 + counters */
+typedef struct {
+  int32_t status;
+  uint32_t iterations;
+  double cost_primal, cost_dual, res_primal, res_dual, res_primal_inf, res_dual_inf;
+  double gap_abs, gap_rel, ktratio, mu, step_length, sigma;
+  double solve_time;          /* host wall clock, seconds */
+  double device_ms;           /* CUDA events around the whole solve on the handle's stream */
+  double t_kkt_update, t_kkt_solve, t_scale_cones;   /* "kkt update" / "kkt solve" / "scale cones" */
+  uint64_t n_refactor, n_ldl_solve, n_ir_steps, regularize_count;
+  uint64_t nnzK, nnzL, kkt_dim;
+} cipm_info;
+
+void cipm_default_settings(cipm_settings *s);
+
+/* DefaultSolver::new(P, q, A, b, cones, settings).  P: n x n upper triangle CSC;
+ * A: m x n CSC; cones: parallel arrays (type tag, dimension).  Cones are
+ * collapsed, data equilibrated (Ruiz), KKT assembled and analysed here.
+ * kkt_perm_or_null: optional elimination order for the (n+m+p) KKT system. */
+int cipm_create(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colptr, const uint64_t *P_rowval,
+                const double *P_nzval, const double *q, const uint64_t *A_colptr, const uint64_t *A_rowval,
+                const double *A_nzval, const double *b, uint64_t ncones, const int32_t *cone_types,
+                const uint64_t *cone_dims, const cipm_settings *settings, const cldl_opts *ldl_opts,
+                const uint64_t *kkt_perm_or_null);
+void cipm_destroy(cipm_t *h);
+int cipm_solve(cipm_t *h);                                   /* IPSolver::solve */
+void cipm_get_info(const cipm_t *h, cipm_info *out);
+int cipm_get_solution(cipm_t *h, double *x, double *z, double *s);   /* unscaled, host buffers */
+uint64_t cipm_trace(const cipm_t *h, double *out, uint64_t cap_rows); /* rows of [mu,alpha,sigma,pres,dres,gap] */
+/* device timestamps (ms since solve() start, CUDA events on the handle's stream) taken at the start of
+ * every iteration; the last entry is the end of the solve. */
+uint64_t cipm_iter_ms(const cipm_t *h, double *out, uint64_t cap);
+uint64_t cipm_launch_count(void);
+/* device-timed (CUDA events) average ms of: 0 numeric refactor, 1 one LDL solve, 2 one KKT solve incl. IR */
+double cipm_time_ms(cipm_t *h, int which, int reps);                            /* kernels launched by this library so far */
+uint64_t cipm_kkt_dim(const cipm_t *h);
+uint64_t cipm_kkt_nnz(const cipm_t *h);
+int cipm_get_kkt(const cipm_t *h, uint64_t *colptr, uint64_t *rowval, double *nzval, int8_t *dsigns);
+int cipm_get_kkt_perm(const cipm_t *h, uint64_t *perm);
+void cipm_ldl_info(const cipm_t *h, cldl_info_t *info);
+
+/* KKTSolver trait on the handle's KKT object (host buffers; x has length n, z length m).
+ * ckkt_update / ckkt_solve return 1 (true) / 0 (false) like the trait's bools. */
+int ckkt_update(cipm_t *h);                                  /* KKTSolver::update(cones, settings) */
+int ckkt_setrhs(cipm_t *h, const double *rhsx, const double *rhsz);
+int ckkt_solve(cipm_t *h, double *lhsx, double *lhsz);       /* LDL solve + iterative refinement */
+int ckkt_update_P(cipm_t *h, const double *P_nzval_scaled);
+int ckkt_update_A(cipm_t *h, const double *A_nzval_scaled);
+int ckkt_get_values(cipm_t *h, double *nzval_out);           /* current (un-regularised) KKT values */
+
+/* Cone trait on the handle's composite cone (host buffers of length m). */
+int ccone_set_identity_scaling(cipm_t *h);
+int ccone_update_scaling(cipm_t *h, const double *s, const double *z);   /* bool */
+uint64_t ccone_Hs_len(const cipm_t *h);
+int ccone_get_Hs(cipm_t *h, double *Hs);
+int ccone_mul_Hs(cipm_t *h, double *y, const double *x);
+int ccone_affine_ds(cipm_t *h, double *ds);
+int ccone_combined_ds_shift(cipm_t *h, double *shift, const double *step_z, const double *step_s, double sigmamu);
+int ccone_ds_from_dz_offset(cipm_t *h, double *out, const double *ds, const double *z);
+int ccone_step_length(cipm_t *h, const double *dz, const double *ds, const double *z, const double *s,
+                      double alpha_max, double *alpha_out);
+int ccone_margins(cipm_t *h, const double *z, double *min_margin, double *pos_margin);
+int ccone_scaled_unit_shift(cipm_t *h, double *z, double alpha, int primal);
+
 #ifdef __cplusplus
 }
 #endif

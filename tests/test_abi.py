@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "clarabel_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(c(?:ldl|kkt|ipm)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(c(?:ldl|kkt|ipm|cone)_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_all_declared_symbols_exported():
