@@ -133,18 +133,217 @@ __global__ void __launch_bounds__(NT) k_factor_level(LDLDev d, int task_base, in
   }
 }
 
+// ------------------------------------------------------------------------
+// Big fronts: two kernels per level.
+//   k_panel_big   : one CTA per front.  Assembles the ns panel columns (original
+//                   entries + the children's update-matrix columns that fall inside
+//                   the pivot block), factors the ns x ns pivot block in shared
+//                   memory (same pivot-by-pivot regularisation rule), then solves
+//                   the nr rows below it (one thread per row, rows independent).
+//   k_update_tiles: one CTA per 64x64 tile of the front's update matrix:
+//                   U_tile = sum_children extend-add  -  L21_I * D * L21_J^T
+//                   with 4x4 register tiles; the extend-add is fused, so U is
+//                   written exactly once and never zero-filled.
+// ------------------------------------------------------------------------
+#define PB_NT 256
+#define TS 64
+
+__device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __restrict__ tasks) {
+  extern __shared__ double sm[];
+  double* sA = sm;                          // [ns][CB_PB_LD] pivot block, column major, padded
+  double* sW = sm + CB_PB_MAXNS * CB_PB_LD;  // [ns][PB_NT] per-thread rows of W = L21 * D
+  __shared__ double sDinv[CB_PB_MAXNS];
+  __shared__ double s_inv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PB_NT >> 5;
+  const int s = tasks[blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  double* __restrict__ P = d.L + d.panel_off[s];
+  const long long psz = (long long)ld * ns;
+
+  for (long long i = tid; i < psz; i += PB_NT) P[i] = 0.0;
+  __syncthreads();
+  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += PB_NT) P[d.asm_dst[e]] = d.vals[d.asm_src[e]];
+  __syncthreads();
+  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
+    const int c = d.child_list[ci];
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* __restrict__ Uc = d.U + d.upd_off[c];
+    const int* __restrict__ relc = d.rel + crp;
+    const int nb = lower_bound_dev(relc, nrc, ns);   // child columns landing inside the pivot block
+    for (int b = warp; b < nb; b += nwarp) {
+      double* __restrict__ col = P + (long long)relc[b] * ld;
+      for (int a = b + lane; a < nrc; a += 32) col[relc[a]] += Uc[(long long)b * nrc + a];
+    }
+    __syncthreads();
+  }
+  // pivot block -> shared
+  for (int idx = tid; idx < ns * ns; idx += PB_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    sA[j * CB_PB_LD + i] = P[(long long)j * ld + i];
+  }
+  __syncthreads();
+  for (int j = 0; j < ns; j++) {
+    if (tid == 0) {
+      double dj = sA[j * CB_PB_LD + j];
+      if (d.reg_enable) {
+        const double sg = (double)d.dsigns[f + j];
+        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; atomicAdd(&d.status[ST_REGCOUNT], 1); }
+      }
+      if (dj == 0.0) atomicExch(&d.status[ST_ZEROPIV], 1);
+      if (dj > 0.0) atomicAdd(&d.status[ST_POSINERTIA], 1);
+      const double inv = 1.0 / dj;
+      if (!isfinite(inv)) atomicExch(&d.status[ST_NONFINITE], 1);
+      d.D[f + j] = dj;
+      d.Dinv[f + j] = inv;
+      sA[j * CB_PB_LD + j] = dj;
+      sDinv[j] = inv;
+      s_inv = inv;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    const double* cj = sA + j * CB_PB_LD;
+    for (int k = j + 1 + warp; k < ns; k += nwarp) {
+      const double wk = cj[k] * inv;
+      double* ck = sA + k * CB_PB_LD;
+      for (int i = k + lane; i < ns; i += 32) ck[i] -= cj[i] * wk;
+    }
+    __syncthreads();
+    for (int i = j + 1 + tid; i < ns; i += PB_NT) sA[j * CB_PB_LD + i] *= inv;
+    // column j is final; the next pivot only reads column j+1
+  }
+  __syncthreads();
+  // write the unit-lower pivot block back
+  for (int idx = tid; idx < ns * ns; idx += PB_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    if (i >= j) P[(long long)j * ld + i] = sA[j * CB_PB_LD + i];
+  }
+  // rows below: W L11^T = F21 ;  L21 = W D^-1   (one thread per row)
+  double* myW = sW + tid;
+  for (int r0 = 0; r0 < nr; r0 += PB_NT) {
+    const int r = r0 + tid;
+    if (r < nr) {
+      double* __restrict__ prow = P + ns + r;
+      for (int j = 0; j < ns; j++) {
+        double t = prow[(long long)j * ld];
+        const double* lj = sA + j;   // L11[j][k] = sA[k*LD + j]
+        for (int k = 0; k < j; k++) t -= myW[k * PB_NT] * lj[k * CB_PB_LD];
+        myW[j * PB_NT] = t;
+        prow[(long long)j * ld] = t * sDinv[j];
+      }
+    }
+  }
+}
+
+// tile descriptor: x = task, y = tile row, z = tile column (ti >= tj)
+__global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __restrict__ tiles) {
+  extern __shared__ double sm[];
+  double* sAt = sm;                    // [ns][TS]   L21 rows of tile-row I
+  double* sBt = sm + CB_PB_MAXNS * TS;  // [ns][TS]   L21 rows of tile-row J scaled by D
+  double* sC = sm + 2 * CB_PB_MAXNS * TS;  // [TS][TS+1] children's contributions
+  __shared__ int s_rng[4];
+  const int4 td = tiles[blockIdx.x];
+  const int s = td.x, ti = td.y, tj = td.z;
+  const int tid = threadIdx.x;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* __restrict__ U = d.U + d.upd_off[s];
+  const int i0 = ti * TS, j0 = tj * TS;
+  const int ni = min(TS, nr - i0), nj = min(TS, nr - j0);
+
+  for (int idx = tid; idx < ns * TS; idx += 256) {
+    const int k = idx / TS, r = idx - k * TS;
+    sAt[idx] = (r < ni) ? P[(long long)k * ld + ns + i0 + r] : 0.0;
+    sBt[idx] = (r < nj) ? P[(long long)k * ld + ns + j0 + r] * d.D[f + k] : 0.0;
+  }
+  for (int idx = tid; idx < TS * (TS + 1); idx += 256) sC[idx] = 0.0;
+  __syncthreads();
+  // extend-add (fixed child order; distinct destinations inside one child)
+  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
+    const int c = d.child_list[ci];
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const int* __restrict__ relc = d.rel + crp;
+    if (tid < 4) {
+      const int key = ns + ((tid & 2) ? j0 : i0) + ((tid & 1) ? TS : 0);
+      s_rng[tid] = lower_bound_dev(relc, nrc, key);
+    }
+    __syncthreads();
+    const int a0 = s_rng[0], a1 = s_rng[1], b0 = s_rng[2], b1 = s_rng[3];
+    const int na = a1 - a0, nb = b1 - b0;
+    if (na > 0 && nb > 0) {
+      const double* __restrict__ Uc = d.U + d.upd_off[c];
+      for (int idx = tid; idx < na * nb; idx += 256) {
+        const int bb = idx / na, aa = idx - bb * na;
+        const int a = a0 + aa, b = b0 + bb;
+        if (a >= b) sC[(relc[a] - ns - i0) * (TS + 1) + (relc[b] - ns - j0)] += Uc[(long long)b * nrc + a];
+      }
+    }
+    __syncthreads();
+  }
+  // 4x4 register tile per thread
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+  for (int k = 0; k < ns; k++) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a[i] = sAt[k * TS + tx + 16 * i]; b[i] = sBt[k * TS + ty + 16 * i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = tx + 16 * i;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = ty + 16 * j;
+      if (r < ni && c < nj && (i0 + r >= j0 + c))
+        U[(long long)(j0 + c) * nr + (i0 + r)] = sC[r * (TS + 1) + c] - acc[i][j];
+    }
+  }
+}
+
 __global__ void k_permute_in(int n, const int* __restrict__ perm, const double* __restrict__ b,
                              double* __restrict__ xp) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) xp[k] = b[perm[k]];
 }
 
-// forward: (L+I) y = b over one tree level
-template <int NT>
-__global__ void __launch_bounds__(NT) k_fwd_level(LDLDev d, int task_base, double* __restrict__ xp) {
-  __shared__ double sy[CB_MAX_PANEL];
-  const int tid = threadIdx.x;
-  const int s = d.level_tasks[task_base + blockIdx.x];
+// ------------------------------------------------------------------------
+// Triangular solves.  Per tree level: fronts with a narrow pivot block
+// (ns <= CB_SOLVE_SMALL_NS) get one warp each; wider ones one CTA each with the
+// pivot block staged in shared memory so the ns sequential substitution steps
+// never wait on global memory.
+// ------------------------------------------------------------------------
+#define SV_NT 256
+
+// forward, small fronts: one warp per front
+__global__ void __launch_bounds__(SV_NT) k_fwd_small(LDLDev d, const int* __restrict__ tasks, int count,
+                                                     double* __restrict__ xp) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (SV_NT / 32) + (threadIdx.x >> 5);
+  if (wid >= count) return;
+  const int s = tasks[wid];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -152,8 +351,51 @@ __global__ void __launch_bounds__(NT) k_fwd_level(LDLDev d, int task_base, doubl
   const int ld = ns + nr;
   const double* __restrict__ P = d.L + d.panel_off[s];
   double* __restrict__ us = d.u + rp;
+  for (int a = lane; a < nr; a += 32) us[a] = 0.0;
+  __syncwarp();
+  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
+    const int c = d.child_list[ci];
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* __restrict__ uc = d.u + crp;
+    const int* __restrict__ relc = d.rel + crp;
+    for (int a = lane; a < nrc; a += 32) {
+      const int r = relc[a];
+      const double v = uc[a];
+      if (r < ns) xp[f + r] += v; else us[r - ns] += v;
+    }
+    __syncwarp();
+  }
+  for (int j = 0; j + 1 < ns; j++) {
+    const double xj = xp[f + j];
+    for (int i = j + 1 + lane; i < ns; i += 32) xp[f + i] -= P[(long long)j * ld + i] * xj;
+    __syncwarp();
+  }
+  for (int a = lane; a < nr; a += 32) {
+    double acc = 0.0;
+    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * xp[f + j];
+    us[a] -= acc;
+  }
+}
 
-  for (int a = tid; a < nr; a += NT) us[a] = 0.0;
+// forward, big fronts: one CTA per front
+__global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int* __restrict__ tasks, double* __restrict__ xp) {
+  __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
+  __shared__ double sy[CB_PB_MAXNS];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int s = tasks[blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* __restrict__ us = d.u + rp;
+  for (int a = tid; a < nr; a += SV_NT) us[a] = 0.0;
+  for (int idx = tid; idx < ns * ns; idx += SV_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
+  }
   __syncthreads();
   for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
     const int c = d.child_list[ci];
@@ -161,36 +403,43 @@ __global__ void __launch_bounds__(NT) k_fwd_level(LDLDev d, int task_base, doubl
     const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
     const double* __restrict__ uc = d.u + crp;
     const int* __restrict__ relc = d.rel + crp;
-    for (int a = tid; a < nrc; a += NT) {
+    for (int a = tid; a < nrc; a += SV_NT) {
       const int r = relc[a];
       const double v = uc[a];
       if (r < ns) xp[f + r] += v; else us[r - ns] += v;
     }
     __syncthreads();
   }
-  for (int j = tid; j < ns; j += NT) sy[j] = xp[f + j];
-  __syncthreads();
-  for (int j = 0; j + 1 < ns; j++) {
-    const double xj = sy[j];
-    for (int i = j + 1 + tid; i < ns; i += NT) sy[i] -= P[(long long)j * ld + i] * xj;
-    __syncthreads();
+  if (tid < 32) {
+    // ns <= 64: each lane owns entries lane and lane+32
+    double y0 = lane < ns ? xp[f + lane] : 0.0;
+    double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
+    for (int j = 0; j < ns; j++) {
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+      const double* lj = sL + j * CB_PB_LD;
+      if (lane > j && lane < ns) y0 -= lj[lane] * xj;
+      if (lane + 32 > j && lane + 32 < ns) y1 -= lj[lane + 32] * xj;
+    }
+    if (lane < ns) { sy[lane] = y0; xp[f + lane] = y0; }
+    if (lane + 32 < ns) { sy[lane + 32] = y1; xp[f + lane + 32] = y1; }
   }
-  for (int j = tid; j < ns; j += NT) xp[f + j] = sy[j];
-  for (int a = tid; a < nr; a += NT) {
+  __syncthreads();
+  for (int a = tid; a < nr; a += SV_NT) {
+    const double* __restrict__ pa = P + ns + a;
     double acc = 0.0;
-    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * sy[j];
+#pragma unroll 4
+    for (int j = 0; j < ns; j++) acc += pa[(long long)j * ld] * sy[j];
     us[a] -= acc;
   }
 }
 
-// backward: D (L+I)^T x = y over one tree level, fused inverse permutation
-template <int NT>
-__global__ void __launch_bounds__(NT) k_bwd_level(LDLDev d, int task_base, double* __restrict__ xp,
-                                                   double* __restrict__ out) {
-  __shared__ double st[CB_MAX_PANEL];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
-  const int s = d.level_tasks[task_base + blockIdx.x];
+// backward, small fronts: one warp per front
+__global__ void __launch_bounds__(SV_NT) k_bwd_small(LDLDev d, const int* __restrict__ tasks, int count,
+                                                     double* __restrict__ xp, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (SV_NT / 32) + (threadIdx.x >> 5);
+  if (wid >= count) return;
+  const int s = tasks[wid];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -198,25 +447,66 @@ __global__ void __launch_bounds__(NT) k_bwd_level(LDLDev d, int task_base, doubl
   const int ld = ns + nr;
   const double* __restrict__ P = d.L + d.panel_off[s];
   const int* __restrict__ rows = d.sn_rows + rp;
-
-  for (int j = warp; j < ns; j += nwarp) {
+  for (int j = 0; j < ns; j++) {
     const double* __restrict__ cj = P + (long long)j * ld + ns;
     double acc = 0.0;
     for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+  }
+  __syncwarp();
+  for (int j = ns - 1; j > 0; j--) {
+    const double xj = xp[f + j];
+    for (int i = lane; i < j; i += 32) xp[f + i] -= P[(long long)i * ld + j] * xj;
+    __syncwarp();
+  }
+  for (int j = lane; j < ns; j += 32) out[d.perm[f + j]] = xp[f + j];
+}
+
+// backward, big fronts: one CTA per front
+__global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int* __restrict__ tasks, double* __restrict__ xp,
+                                                   double* __restrict__ out) {
+  __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
+  __shared__ double st[CB_PB_MAXNS];
+  __shared__ double sx[CB_SOLVE_STAGE];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SV_NT >> 5;
+  const int s = tasks[blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  const int* __restrict__ rows = d.sn_rows + rp;
+  for (int idx = tid; idx < ns * ns; idx += SV_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
+  }
+  const bool staged = nr <= CB_SOLVE_STAGE;
+  if (staged) for (int a = tid; a < nr; a += SV_NT) sx[a] = xp[rows[a]];
+  __syncthreads();
+  for (int j = warp; j < ns; j += nwarp) {
+    const double* __restrict__ cj = P + (long long)j * ld + ns;
+    double acc = 0.0;
+    if (staged) for (int a = lane; a < nr; a += 32) acc += cj[a] * sx[a];
+    else for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
   }
   __syncthreads();
-  for (int j = ns - 1; j > 0; j--) {
-    const double xj = st[j];
-    for (int i = tid; i < j; i += NT) st[i] -= P[(long long)i * ld + j] * xj;
-    __syncthreads();
-  }
-  for (int j = tid; j < ns; j += NT) {
-    const double v = st[j];
-    xp[f + j] = v;
-    out[d.perm[f + j]] = v;
+  if (tid < 32) {
+    double y0 = lane < ns ? st[lane] : 0.0;
+    double y1 = lane + 32 < ns ? st[lane + 32] : 0.0;
+    for (int j = ns - 1; j > 0; j--) {
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+      // L11[j][i] = sL[i*LD + j]
+      if (lane < j) y0 -= sL[lane * CB_PB_LD + j] * xj;
+      if (lane + 32 < j) y1 -= sL[(lane + 32) * CB_PB_LD + j] * xj;
+    }
+    if (lane < ns) { xp[f + lane] = y0; out[d.perm[f + lane]] = y0; }
+    if (lane + 32 < ns) { xp[f + lane + 32] = y1; out[d.perm[f + lane + 32]] = y1; }
   }
 }
 
@@ -276,7 +566,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   SymbolicOptions so;
   so.ordering = o.ordering ? o.ordering : ORDER_BEST;
   so.amd_dense_scale = o.amd_dense_scale > 0 ? o.amd_dense_scale : 1.5;
-  if (o.max_panel > 0) so.max_panel = o.max_panel > CB_MAX_PANEL ? CB_MAX_PANEL : o.max_panel;
+  if (o.max_panel > 0) so.max_panel = o.max_panel > CB_PB_MAXNS ? CB_PB_MAXNS : o.max_panel;
   if (o.nd_leaf > 0) so.nd_leaf = o.nd_leaf;
   int rc = analyse(n, Ap, Ai, perm_in, so, S);
   if (rc == -2) return CLDL_E_EMPTY_COLUMN;
@@ -328,34 +618,44 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   dev.reg_eps = o.regularize_eps;
   dev.reg_delta = o.regularize_delta;
 
-  // per-level launch plan: split each level by shared-memory class of the panel
+  // per-level launch plan.  Small fronts: one fused CTA each, grouped by the shared-memory class of
+  // their panel.  Big fronts (nr >= CB_BIG_NR): panel kernel + tiled update kernel.
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   const int cap_big = (max_optin - 2048) / 8;  // doubles
-  CK(cudaFuncSetAttribute(k_factor_level<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          cap_big * 8));
+  CK(cudaFuncSetAttribute(k_factor_level<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_big * 8));
+  const size_t smem_panel = (size_t)(CB_PB_MAXNS * CB_PB_LD + CB_PB_MAXNS * PB_NT) * 8;
+  const size_t smem_tiles = (size_t)(2 * CB_PB_MAXNS * TS + TS * (TS + 1)) * 8;
+  CK(cudaFuncSetAttribute(k_panel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel));
+  CK(cudaFuncSetAttribute(k_update_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiles));
   const long long classes[3] = {1024, 5632, cap_big};  // 8 KB, 44 KB, ~225 KB panels
   plan.clear();
+  std::vector<int> big_tasks;
+  std::vector<int4> tiles;
   for (int l = 0; l < S.nlevels; l++) {
     int b = S.level_ptr[l], e = S.level_ptr[l + 1];
-    // tasks are sorted by front size descending; classify by panel size
-    auto psz = [&](int t) {
-      int s = S.level_tasks[t];
-      long long ns = S.sn_first[s + 1] - S.sn_first[s];
-      long long nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
-      return (ns + nr) * ns;
-    };
-    // stable partition into classes while keeping order: gather indices per class
     std::vector<int> order[4];
+    const size_t big0 = big_tasks.size(), tile0 = tiles.size();
     for (int t = b; t < e; t++) {
-      long long p = psz(t);
+      const int s = S.level_tasks[t];
+      const long long ns = S.sn_first[s + 1] - S.sn_first[s];
+      const long long nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+      if (nr >= CB_BIG_NR && ns <= CB_PB_MAXNS) {
+        big_tasks.push_back(s);
+        const int nt = (int)((nr + TS - 1) / TS);
+        for (int ti = 0; ti < nt; ti++)
+          for (int tj = 0; tj <= ti; tj++) tiles.push_back(make_int4(s, ti, tj, 0));
+        continue;
+      }
+      const long long p = (ns + nr) * ns;
       int c = p <= classes[0] ? 0 : p <= classes[1] ? 1 : p <= classes[2] ? 2 : 3;
-      order[c].push_back(S.level_tasks[t]);
+      order[c].push_back(s);
     }
     int pos = b;
     for (int c = 3; c >= 0; c--) {
       if (order[c].empty()) continue;
       LaunchSeg seg;
+      seg.kind = 0;
       seg.level = l;
       seg.base = pos;
       seg.count = (int)order[c].size();
@@ -364,6 +664,49 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       plan.push_back(seg);
       for (int s : order[c]) S.level_tasks[pos++] = s;
     }
+    for (size_t k = big0; k < big_tasks.size(); k++) S.level_tasks[pos++] = big_tasks[k];
+    if (big_tasks.size() > big0) {
+      LaunchSeg seg;
+      seg.kind = 1; seg.level = l; seg.base = (int)big0; seg.count = (int)(big_tasks.size() - big0);
+      seg.smem_doubles = (int)(smem_panel / 8); seg.threads = PB_NT;
+      plan.push_back(seg);
+      seg.kind = 2; seg.base = (int)tile0; seg.count = (int)(tiles.size() - tile0);
+      seg.smem_doubles = (int)(smem_tiles / 8); seg.threads = 256;
+      plan.push_back(seg);
+    }
+  }
+  {
+    int* t1 = nullptr;
+    if ((rc = upload(&t1, big_tasks))) return rc;
+    d_big_tasks = t1;
+    int4* t4 = nullptr;
+    CK(cudaMalloc((void**)&t4, (tiles.size() ? tiles.size() : 1) * sizeof(int4)));
+    if (!tiles.empty()) CK(cudaMemcpy(t4, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    d_tiles = t4;
+    n_tiles = (int64_t)tiles.size();
+  }
+  // solve plan: per level, narrow-pivot fronts first (one warp each) then the wide ones (one CTA each)
+  {
+    std::vector<int> st(S.level_tasks.size());
+    splan.assign(S.nlevels, SolveSeg());
+    solve_launches = 0;
+    for (int l = 0; l < S.nlevels; l++) {
+      int b = S.level_ptr[l], e = S.level_ptr[l + 1], pos = b;
+      for (int pass = 0; pass < 2; pass++)
+        for (int t = b; t < e; t++) {
+          const int s = S.level_tasks[t];
+          const int ns = S.sn_first[s + 1] - S.sn_first[s];
+          const bool small = ns <= CB_SOLVE_SMALL_NS;
+          if ((pass == 0) == small) st[pos++] = s;
+          if (pass == 0 && small) splan[l].nsmall++;
+        }
+      splan[l].base = b;
+      splan[l].nbig = (e - b) - splan[l].nsmall;
+      solve_launches += 2 * ((splan[l].nsmall ? 1 : 0) + (splan[l].nbig ? 1 : 0));
+    }
+    int* t1 = nullptr;
+    if ((rc = upload(&t1, st))) return rc;
+    d_solve_tasks = t1;
   }
   // level_tasks was re-ordered inside levels: re-upload
   CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
@@ -379,7 +722,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -391,7 +734,11 @@ int LDLObject::refactor_async() {
   CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
   g_launches += plan.size();
   for (const LaunchSeg& g : plan) {
-    if (g.threads == 64)
+    if (g.kind == 1)
+      k_panel_big<<<g.count, PB_NT, (size_t)g.smem_doubles * 8, stream>>>(dev, d_big_tasks + g.base);
+    else if (g.kind == 2)
+      k_update_tiles<<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, d_tiles + g.base);
+    else if (g.threads == 64)
       k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
     else
       k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
@@ -414,15 +761,17 @@ int LDLObject::sync_status() {
 int LDLObject::solve_async(double* d_x, const double* d_b) {
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
-  g_launches += 1 + 2 * (unsigned long long)S.nlevels;
+  g_launches += 1 + solve_launches;
   k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
   for (int l = 0; l < S.nlevels; l++) {
-    int b = S.level_ptr[l], cnt = S.level_ptr[l + 1] - b;
-    k_fwd_level<128><<<cnt, 128, 0, stream>>>(dev, b, d_xp);
+    const SolveSeg& g = splan[l];
+    if (g.nsmall) k_fwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp);
+    if (g.nbig) k_fwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base + g.nsmall, d_xp);
   }
   for (int l = S.nlevels - 1; l >= 0; l--) {
-    int b = S.level_ptr[l], cnt = S.level_ptr[l + 1] - b;
-    k_bwd_level<128><<<cnt, 128, 0, stream>>>(dev, b, d_xp, d_x);
+    const SolveSeg& g = splan[l];
+    if (g.nsmall) k_bwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp, d_x);
+    if (g.nbig) k_bwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base + g.nsmall, d_xp, d_x);
   }
   CK(cudaGetLastError());
   return CLDL_OK;

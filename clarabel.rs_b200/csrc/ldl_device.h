@@ -9,6 +9,11 @@
 #include "symbolic.h"
 
 #define CB_MAX_PANEL 128
+#define CB_PB_MAXNS 64     /* widest panel (columns) of a front */
+#define CB_PB_LD 65        /* padded leading dimension of the pivot block in shared memory */
+#define CB_SOLVE_SMALL_NS 8 /* solves: fronts with at most this many pivots get one warp, wider ones one CTA */
+#define CB_SOLVE_STAGE 1536  /* doubles of gathered x staged in shared memory by k_bwd_big */
+#define CB_BIG_NR 96       /* fronts with at least this many rows below the pivot block use the multi-CTA path */
 
 namespace cb {
 
@@ -42,11 +47,19 @@ struct LDLDev {
 };
 
 struct LaunchSeg {
+  int kind = 0;  // 0 fused small fronts, 1 big-front panels, 2 big-front update tiles
   int level, base, count, smem_doubles, threads;
+};
+
+struct SolveSeg {
+  int base = 0, nsmall = 0, nbig = 0;
 };
 
 class LDLObject {
  public:
+  std::vector<SolveSeg> splan;
+  int* d_solve_tasks = nullptr;
+  unsigned long long solve_launches = 0;
   int n = 0;
   int64_t nnzA = 0;
   int device = 0;
@@ -63,6 +76,9 @@ class LDLObject {
   double* d_tmp_val = nullptr;
   signed char* d_tmp_sgn = nullptr;
   size_t tmp_cap = 0;
+  int* d_big_tasks = nullptr;
+  int4* d_tiles = nullptr;
+  int64_t n_tiles = 0;
   std::vector<int> h_idx;
   bool factored = false;
   uint64_t regularize_count = 0, positive_inertia = 0;
