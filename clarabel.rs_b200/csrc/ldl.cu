@@ -154,12 +154,44 @@ __device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int n,
   return lo;
 }
 
+// Ordered compaction of the children of front s that satisfy `pred`: every thread
+// evaluates up to one child per round; the surviving child ids are appended to
+// s_list in child_list order (so sums keep a fixed order).  Returns the count.
+template <class Pred>
+__device__ __forceinline__ int compact_children(const LDLDev& d, int s, int* s_list, int cap, int* s_wcnt, Pred pred) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const long long c0 = d.child_ptr[s], c1 = d.child_ptr[s + 1];
+  int total = 0;
+  for (long long base = c0; base < c1; base += blockDim.x) {
+    const long long ci = base + tid;
+    int c = -1;
+    bool ok = false;
+    if (ci < c1) { c = d.child_list[ci]; ok = pred(c); }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = total;
+    for (int w = 0; w < warp; w++) off += s_wcnt[w];
+    int add = 0;
+    for (int w = 0; w < nwarp; w++) add += s_wcnt[w];
+    if (ok) {
+      const int p = off + __popc(bal & ((1u << lane) - 1u));
+      if (p < cap) s_list[p] = c;
+    }
+    total += add;
+    __syncthreads();
+  }
+  return total;
+}
+
+#define CB_CHILD_CAP 1024
+
 __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __restrict__ tasks) {
-  extern __shared__ double sm[];
-  double* sA = sm;                          // [ns][CB_PB_LD] pivot block, column major, padded
-  double* sW = sm + CB_PB_MAXNS * CB_PB_LD;  // [ns][PB_NT] per-thread rows of W = L21 * D
-  __shared__ double sDinv[CB_PB_MAXNS];
+  __shared__ double sA[CB_PB_MAXNS * CB_PB_LD];   // pivot block, column major, padded
+  __shared__ double sDinv[CB_PB_MAXNS], sDval[CB_PB_MAXNS], sSign[CB_PB_MAXNS];
   __shared__ double s_inv;
+  __shared__ int s_list[CB_CHILD_CAP];
+  __shared__ int s_wcnt[PB_NT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PB_NT >> 5;
   const int s = tasks[blockIdx.x];
   const int f = d.sn_first[s];
@@ -171,16 +203,21 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
   const long long psz = (long long)ld * ns;
 
   for (long long i = tid; i < psz; i += PB_NT) P[i] = 0.0;
+  if (tid < ns) sSign[tid] = (double)d.dsigns[f + tid];
+  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0; });
   __syncthreads();
   for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += PB_NT) P[d.asm_dst[e]] = d.vals[d.asm_src[e]];
   __syncthreads();
-  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
-    const int c = d.child_list[ci];
+  const bool overflow = ncontrib > CB_CHILD_CAP;
+  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
+  for (int q = 0; q < nloop; q++) {
+    const int c = overflow ? d.child_list[d.child_ptr[s] + q] : s_list[q];
+    const int nb = d.child_nb[c];   // child columns landing inside the pivot block (host precomputed)
+    if (nb == 0) continue;
     const long long crp = d.sn_rowptr[c];
     const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
     const double* __restrict__ Uc = d.U + d.upd_off[c];
     const int* __restrict__ relc = d.rel + crp;
-    const int nb = lower_bound_dev(relc, nrc, ns);   // child columns landing inside the pivot block
     for (int b = warp; b < nb; b += nwarp) {
       double* __restrict__ col = P + (long long)relc[b] * ld;
       for (int a = b + lane; a < nrc; a += 32) col[relc[a]] += Uc[(long long)b * nrc + a];
@@ -193,19 +230,19 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
     sA[j * CB_PB_LD + i] = P[(long long)j * ld + i];
   }
   __syncthreads();
+  int c_reg = 0, c_pos = 0, c_zero = 0, c_nonf = 0;   // thread 0 only
   for (int j = 0; j < ns; j++) {
     if (tid == 0) {
       double dj = sA[j * CB_PB_LD + j];
       if (d.reg_enable) {
-        const double sg = (double)d.dsigns[f + j];
-        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; atomicAdd(&d.status[ST_REGCOUNT], 1); }
+        const double sg = sSign[j];
+        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; c_reg++; }
       }
-      if (dj == 0.0) atomicExch(&d.status[ST_ZEROPIV], 1);
-      if (dj > 0.0) atomicAdd(&d.status[ST_POSINERTIA], 1);
+      if (dj == 0.0) c_zero = 1;
+      if (dj > 0.0) c_pos++;
       const double inv = 1.0 / dj;
-      if (!isfinite(inv)) atomicExch(&d.status[ST_NONFINITE], 1);
-      d.D[f + j] = dj;
-      d.Dinv[f + j] = inv;
+      if (!isfinite(inv)) c_nonf = 1;
+      sDval[j] = dj;
       sA[j * CB_PB_LD + j] = dj;
       sDinv[j] = inv;
       s_inv = inv;
@@ -223,24 +260,46 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
     // column j is final; the next pivot only reads column j+1
   }
   __syncthreads();
+  if (tid == 0) {
+    if (c_reg) atomicAdd(&d.status[ST_REGCOUNT], c_reg);
+    if (c_pos) atomicAdd(&d.status[ST_POSINERTIA], c_pos);
+    if (c_zero) atomicExch(&d.status[ST_ZEROPIV], 1);
+    if (c_nonf) atomicExch(&d.status[ST_NONFINITE], 1);
+  }
+  if (tid < ns) { d.D[f + tid] = sDval[tid]; d.Dinv[f + tid] = sDinv[tid]; }
   // write the unit-lower pivot block back
   for (int idx = tid; idx < ns * ns; idx += PB_NT) {
     const int j = idx / ns, i = idx - j * ns;
     if (i >= j) P[(long long)j * ld + i] = sA[j * CB_PB_LD + i];
   }
-  // rows below: W L11^T = F21 ;  L21 = W D^-1   (one thread per row)
-  double* myW = sW + tid;
+  // rows below:  W L11^T = F21,  L21 = W D^-1.  One thread per row, 16 columns at a time in
+  // registers; W of earlier column blocks is re-read from the panel (L21 * D), coalesced.
+  constexpr int JB = 16;
   for (int r0 = 0; r0 < nr; r0 += PB_NT) {
     const int r = r0 + tid;
-    if (r < nr) {
-      double* __restrict__ prow = P + ns + r;
-      for (int j = 0; j < ns; j++) {
-        double t = prow[(long long)j * ld];
-        const double* lj = sA + j;   // L11[j][k] = sA[k*LD + j]
-        for (int k = 0; k < j; k++) t -= myW[k * PB_NT] * lj[k * CB_PB_LD];
-        myW[j * PB_NT] = t;
-        prow[(long long)j * ld] = t * sDinv[j];
+    if (r >= nr) continue;
+    double* __restrict__ prow = P + ns + r;
+    for (int jb = 0; jb < ns; jb += JB) {
+      const int nj = min(JB, ns - jb);
+      double t[JB];
+#pragma unroll
+      for (int jj = 0; jj < JB; jj++) t[jj] = jj < nj ? prow[(long long)(jb + jj) * ld] : 0.0;
+      for (int k = 0; k < jb; k++) {
+        const double wk = prow[(long long)k * ld] * sDval[k];
+        const double* lk = sA + k * CB_PB_LD + jb;   // L11[jb+jj][k]
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) t[jj] -= wk * lk[jj];
       }
+#pragma unroll
+      for (int jj = 0; jj < JB; jj++) {
+        if (jj < nj) {
+          const double* lk = sA + (jb + jj) * CB_PB_LD + jb;   // column jb+jj: rows jb+jj+1.. hold L11[.][jb+jj]
+#pragma unroll
+          for (int j2 = jj + 1; j2 < JB; j2++) t[j2] -= t[jj] * lk[j2];
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < JB; jj++) if (jj < nj) prow[(long long)(jb + jj) * ld] = t[jj] * sDinv[jb + jj];
     }
   }
 }
@@ -272,9 +331,22 @@ __global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __re
   }
   for (int idx = tid; idx < TS * (TS + 1); idx += 256) sC[idx] = 0.0;
   __syncthreads();
-  // extend-add (fixed child order; distinct destinations inside one child)
-  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
-    const int c = d.child_list[ci];
+  // extend-add (fixed child order; distinct destinations inside one child).  Only children whose
+  // rows can reach both tile rows are visited.
+  __shared__ int s_list[CB_CHILD_CAP];
+  __shared__ int s_wcnt[8];
+  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) {
+    const int2 tr = d.child_trange[c];
+    return !(ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y);
+  });
+  const bool overflow = ncontrib > CB_CHILD_CAP;
+  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
+  for (int q = 0; q < nloop; q++) {
+    const int c = overflow ? d.child_list[d.child_ptr[s] + q] : s_list[q];
+    if (overflow) {
+      const int2 tr = d.child_trange[c];
+      if (ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y) continue;
+    }
     const long long crp = d.sn_rowptr[c];
     const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
     const int* __restrict__ relc = d.rel + crp;
@@ -351,21 +423,16 @@ __global__ void __launch_bounds__(SV_NT) k_fwd_small(LDLDev d, const int* __rest
   const int ld = ns + nr;
   const double* __restrict__ P = d.L + d.panel_off[s];
   double* __restrict__ us = d.u + rp;
-  for (int a = lane; a < nr; a += 32) us[a] = 0.0;
-  __syncwarp();
-  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
-    const int c = d.child_list[ci];
-    const long long crp = d.sn_rowptr[c];
-    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
-    const double* __restrict__ uc = d.u + crp;
-    const int* __restrict__ relc = d.rel + crp;
-    for (int a = lane; a < nrc; a += 32) {
-      const int r = relc[a];
-      const double v = uc[a];
-      if (r < ns) xp[f + r] += v; else us[r - ns] += v;
+  {
+    // children's update vectors, gathered per destination slot in fixed order
+    const int* __restrict__ gp = d.gat_ptr + (f + rp);
+    for (int p = lane; p < ld; p += 32) {
+      double acc = 0.0;
+      for (int e = gp[p]; e < gp[p + 1]; e++) acc += d.u[d.gat_src[e]];
+      if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
     }
-    __syncwarp();
   }
+  __syncwarp();
   for (int j = 0; j + 1 < ns; j++) {
     const double xj = xp[f + j];
     for (int i = j + 1 + lane; i < ns; i += 32) xp[f + i] -= P[(long long)j * ld + i] * xj;
@@ -391,25 +458,19 @@ __global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int* __restri
   const int ld = ns + nr;
   const double* __restrict__ P = d.L + d.panel_off[s];
   double* __restrict__ us = d.u + rp;
-  for (int a = tid; a < nr; a += SV_NT) us[a] = 0.0;
   for (int idx = tid; idx < ns * ns; idx += SV_NT) {
     const int j = idx / ns, i = idx - j * ns;
     sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
   }
-  __syncthreads();
-  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
-    const int c = d.child_list[ci];
-    const long long crp = d.sn_rowptr[c];
-    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
-    const double* __restrict__ uc = d.u + crp;
-    const int* __restrict__ relc = d.rel + crp;
-    for (int a = tid; a < nrc; a += SV_NT) {
-      const int r = relc[a];
-      const double v = uc[a];
-      if (r < ns) xp[f + r] += v; else us[r - ns] += v;
+  {
+    const int* __restrict__ gp = d.gat_ptr + (f + rp);
+    for (int p = tid; p < ld; p += SV_NT) {
+      double acc = 0.0;
+      for (int e = gp[p]; e < gp[p + 1]; e++) acc += d.u[d.gat_src[e]];
+      if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (tid < 32) {
     // ns <= 64: each lane owns entries lane and lane+32
     double y0 = lane < ns ? xp[f + lane] : 0.0;
@@ -618,15 +679,49 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   dev.reg_eps = o.regularize_eps;
   dev.reg_delta = o.regularize_delta;
 
+  // per-child constants for the big-front kernels and the per-destination gather lists for the solves
+  {
+    std::vector<int> child_nb(S.nsup, 0);
+    std::vector<int2> child_tr(S.nsup, make_int2(1, 0));
+    std::vector<int> gptr((size_t)n + S.sn_rows.size() + 1, 0);
+    for (int c = 0; c < S.nsup; c++) {
+      const int p = S.sn_parent[c];
+      if (p < 0) continue;
+      const int pns = S.sn_first[p + 1] - S.sn_first[p];
+      const int64_t pbase = (int64_t)S.sn_first[p] + S.sn_rowptr[p];
+      const int64_t b0 = S.sn_rowptr[c], e0 = S.sn_rowptr[c + 1];
+      int nb = 0;
+      for (int64_t t = b0; t < e0; t++) { if (S.rel[t] < pns) nb++; gptr[pbase + S.rel[t] + 1]++; }
+      child_nb[c] = nb;
+      if (b0 + nb < e0) child_tr[c] = make_int2((S.rel[b0 + nb] - pns) / TS, (S.rel[e0 - 1] - pns) / TS);
+    }
+    for (size_t i = 0; i + 1 < gptr.size(); i++) gptr[i + 1] += gptr[i];
+    std::vector<int> gsrc(S.sn_rows.size() ? S.sn_rows.size() : 1, 0), pos(gptr.begin(), gptr.end() - 1);
+    // children in child_list order so that every destination sums in a fixed, reproducible order
+    for (int p = 0; p < S.nsup; p++) {
+      const int64_t pbase = (int64_t)S.sn_first[p] + S.sn_rowptr[p];
+      for (int64_t ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ci++) {
+        const int c = S.child_list[ci];
+        for (int64_t t = S.sn_rowptr[c]; t < S.sn_rowptr[c + 1]; t++) gsrc[pos[pbase + S.rel[t]]++] = (int)t;
+      }
+    }
+    int* t1 = nullptr;
+    if ((rc = upload(&t1, child_nb))) return rc; dev.child_nb = t1;
+    if ((rc = upload(&t1, gptr))) return rc; dev.gat_ptr = t1;
+    if ((rc = upload(&t1, gsrc))) return rc; dev.gat_src = t1;
+    int2* t2 = nullptr;
+    CK(cudaMalloc((void**)&t2, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int2)));
+    CK(cudaMemcpy(t2, child_tr.data(), (size_t)S.nsup * sizeof(int2), cudaMemcpyHostToDevice));
+    dev.child_trange = t2;
+  }
   // per-level launch plan.  Small fronts: one fused CTA each, grouped by the shared-memory class of
   // their panel.  Big fronts (nr >= CB_BIG_NR): panel kernel + tiled update kernel.
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   const int cap_big = (max_optin - 2048) / 8;  // doubles
   CK(cudaFuncSetAttribute(k_factor_level<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_big * 8));
-  const size_t smem_panel = (size_t)(CB_PB_MAXNS * CB_PB_LD + CB_PB_MAXNS * PB_NT) * 8;
+  const size_t smem_panel = 0;   // static shared memory only
   const size_t smem_tiles = (size_t)(2 * CB_PB_MAXNS * TS + TS * (TS + 1)) * 8;
-  CK(cudaFuncSetAttribute(k_panel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel));
   CK(cudaFuncSetAttribute(k_update_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiles));
   const long long classes[3] = {1024, 5632, cap_big};  // 8 KB, 44 KB, ~225 KB panels
   plan.clear();
@@ -722,7 +817,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);

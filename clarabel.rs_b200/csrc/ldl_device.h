@@ -10,7 +10,7 @@
 
 #define CB_MAX_PANEL 128
 #define CB_PB_MAXNS 64     /* widest panel (columns) of a front */
-#define CB_PB_LD 65        /* padded leading dimension of the pivot block in shared memory */
+#define CB_PB_LD 66        /* padded leading dimension of the pivot block in shared memory */
 #define CB_SOLVE_SMALL_NS 8 /* solves: fronts with at most this many pivots get one warp, wider ones one CTA */
 #define CB_SOLVE_STAGE 1536  /* doubles of gathered x staged in shared memory by k_bwd_big */
 #define CB_BIG_NR 96       /* fronts with at least this many rows below the pivot block use the multi-CTA path */
@@ -33,6 +33,10 @@ struct LDLDev {
   const int* asm_src = nullptr;
   const long long* asm_dst = nullptr;
   const int* level_tasks = nullptr;
+  const int* child_nb = nullptr;      // per front: rows that land inside its parent's pivot block
+  const int2* child_trange = nullptr; // per front: [first,last] 64-row tile of the parent's update matrix it touches
+  const int* gat_ptr = nullptr;       // solves: per front slot, CSR of contributing child update-vector entries
+  const int* gat_src = nullptr;
   const int* perm = nullptr;
   const signed char* dsigns = nullptr;  // permuted order
   double* vals = nullptr;               // KKT values, caller's CSC order
