@@ -100,6 +100,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def aggregate_over_ranks(dist, world, steps_local, seconds_local, device=None):
+    """Whole-job throughput: units processed by all ranks / max-over-ranks time (bench contract).
+    Works with any torch.distributed backend (nccl on GPUs, gloo in the CPU tests)."""
+    if world <= 1 or dist is None:
+        return steps_local / seconds_local, seconds_local, steps_local
+    import torch
+    t = torch.tensor([seconds_local], dtype=torch.float64, device=device)
+    k = torch.tensor([float(steps_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(k, op=dist.ReduceOp.SUM)
+    return float(k.item()) / float(t.item()), float(t.item()), float(k.item())
+
+
 def algorithmic_bytes(li, N, nnzK):
     """DESIGN.md 'roofline accounting': bytes one launch sequence must move at minimum."""
     refactor = 20 * nnzK + 8 * li.nnzL_stored + 16 * N          # read values+maps, write panels, D, Dinv
@@ -166,16 +179,8 @@ def run_ours(args, rank, world):
         dist.barrier()
     clk = clocks.stop()
     t_local = float(np.sum(durations)) / 1e3
-    t_max = t_local
-    if world > 1:
-        t = torch.tensor([t_local], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_max = float(t.item())
-        te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        t_e2e = float(te.item())
-    value = world * K / t_max
-    e2e_value = world * iters_e2e / t_e2e
+    value, t_max, _ = aggregate_over_ranks(dist, world, K, t_local, "cuda")
+    e2e_value, t_e2e, _ = aggregate_over_ranks(dist, world, iters_e2e, t_e2e, "cuda")
 
     out = None
     if rank == 0:

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(NT) k_factor_level(LDLDev d, int task_base, in
 // ------------------------------------------------------------------------
 #define PB_NT 256
 #define TS 64
+#define KC 32   /* pivots staged per chunk by k_update_tiles */
 
 __device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int n, int key) {
   int lo = 0, hi = n;
@@ -184,10 +185,32 @@ __device__ __forceinline__ int compact_children(const LDLDev& d, int s, int* s_l
   return total;
 }
 
+// Adds U-arena values into `dst_base` through a (src,dst) entry list sorted by dst.  Every thread takes a
+// contiguous slice; slice borders are moved forward to the next change of dst so that one destination is
+// only ever touched by one thread, in list order (deterministic, no atomics, no barriers).
+__device__ __forceinline__ void apply_sorted_entries(double* __restrict__ dst_base, const double* __restrict__ U,
+                                                     const int* __restrict__ esrc, const int* __restrict__ edst,
+                                                     int e0, int e1, int nthreads) {
+  const int cnt = e1 - e0;
+  if (cnt <= 0) return;
+  const int per = (cnt + nthreads - 1) / nthreads;
+  int b = e0 + threadIdx.x * per, e = min(e1, b + per);
+  if (b >= e1) return;
+  if (b > e0) { while (b < e1 && edst[b] == edst[b - 1]) b++; }
+  if (e < e1) { while (e < e1 && edst[e] == edst[e - 1]) e++; }
+  int i = b;
+  while (i < e) {
+    const int dd = edst[i];
+    double acc = 0.0;
+    while (i < e && edst[i] == dd) { acc += U[esrc[i]]; i++; }
+    dst_base[dd] += acc;
+  }
+}
+
 #define CB_CHILD_CAP 1024
 
-__global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __restrict__ tasks) {
-  __shared__ double sA[CB_PB_MAXNS * CB_PB_LD];   // pivot block, column major, padded
+__global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __restrict__ tasks, int task_off) {
+  __shared__ __align__(16) double sA[CB_PB_MAXNS * CB_PB_LD];   // pivot block, column major, padded
   __shared__ double sDinv[CB_PB_MAXNS], sDval[CB_PB_MAXNS], sSign[CB_PB_MAXNS];
   __shared__ double s_inv;
   __shared__ int s_list[CB_CHILD_CAP];
@@ -204,7 +227,7 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
 
   for (long long i = tid; i < psz; i += PB_NT) P[i] = 0.0;
   if (tid < ns) sSign[tid] = (double)d.dsigns[f + tid];
-  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0; });
+  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0 && !d.child_small[c]; });
   __syncthreads();
   for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += PB_NT) P[d.asm_dst[e]] = d.vals[d.asm_src[e]];
   __syncthreads();
@@ -213,17 +236,36 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
   for (int q = 0; q < nloop; q++) {
     const int c = overflow ? d.child_list[d.child_ptr[s] + q] : s_list[q];
     const int nb = d.child_nb[c];   // child columns landing inside the pivot block (host precomputed)
-    if (nb == 0) continue;
+    if (nb == 0 || d.child_small[c]) continue;
     const long long crp = d.sn_rowptr[c];
     const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
     const double* __restrict__ Uc = d.U + d.upd_off[c];
     const int* __restrict__ relc = d.rel + crp;
     for (int b = warp; b < nb; b += nwarp) {
       double* __restrict__ col = P + (long long)relc[b] * ld;
-      for (int a = b + lane; a < nrc; a += 32) col[relc[a]] += Uc[(long long)b * nrc + a];
+      const double* __restrict__ ucol = Uc + (long long)b * nrc;
+      // destinations inside one child column are distinct: batch the read-modify-writes so that
+      // 8 independent global round trips are in flight per lane
+      int a = b + lane;
+      for (; a + 7 * 32 < nrc; a += 8 * 32) {
+        int r[8];
+        double u[8], pv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { r[q] = relc[a + q * 32]; u[q] = ucol[a + q * 32]; }
+#pragma unroll
+        for (int q = 0; q < 8; q++) pv[q] = col[r[q]];
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; q++) col[r[q]] = pv[q] + u[q];
+      }
+      for (; a < nrc; a += 32) col[relc[a]] += ucol[a];
     }
     __syncthreads();
   }
+  // all small children at once (sorted entry list, conflict free)
+  apply_sorted_entries(P, d.U, d.sc_panel_src, d.sc_panel_dst, d.sc_panel_ptr[blockIdx.x + task_off],
+                       d.sc_panel_ptr[blockIdx.x + task_off + 1], PB_NT);
+  __syncthreads();
   // pivot block -> shared
   for (int idx = tid; idx < ns * ns; idx += PB_NT) {
     const int j = idx / ns, i = idx - j * ns;
@@ -284,11 +326,21 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
       double t[JB];
 #pragma unroll
       for (int jj = 0; jj < JB; jj++) t[jj] = jj < nj ? prow[(long long)(jb + jj) * ld] : 0.0;
-      for (int k = 0; k < jb; k++) {
-        const double wk = prow[(long long)k * ld] * sDval[k];
-        const double* lk = sA + k * CB_PB_LD + jb;   // L11[jb+jj][k]
+      for (int kb = 0; kb < jb; kb += JB) {
+        double wv[JB];
 #pragma unroll
-        for (int jj = 0; jj < JB; jj++) t[jj] -= wk * lk[jj];
+        for (int kk = 0; kk < JB; kk++) wv[kk] = prow[(long long)(kb + kk) * ld];   // 16 loads in flight
+#pragma unroll
+        for (int kk = 0; kk < JB; kk++) {
+          const double wk = wv[kk] * sDval[kb + kk];
+          const double2* lk2 = reinterpret_cast<const double2*>(sA + (kb + kk) * CB_PB_LD + jb);   // L11[jb+jj][k]
+#pragma unroll
+          for (int j2 = 0; j2 < JB / 2; j2++) {
+            const double2 l = lk2[j2];
+            t[2 * j2] -= wk * l.x;
+            t[2 * j2 + 1] -= wk * l.y;
+          }
+        }
       }
 #pragma unroll
       for (int jj = 0; jj < JB; jj++) {
@@ -305,12 +357,11 @@ __global__ void __launch_bounds__(PB_NT) k_panel_big(LDLDev d, const int* __rest
 }
 
 // tile descriptor: x = task, y = tile row, z = tile column (ti >= tj)
-__global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __restrict__ tiles) {
+__global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __restrict__ tiles, int tile_off) {
   extern __shared__ double sm[];
-  double* sAt = sm;                    // [ns][TS]   L21 rows of tile-row I
-  double* sBt = sm + CB_PB_MAXNS * TS;  // [ns][TS]   L21 rows of tile-row J scaled by D
-  double* sC = sm + 2 * CB_PB_MAXNS * TS;  // [TS][TS+1] children's contributions
-  __shared__ int s_rng[4];
+  double* sAt = sm;                 // [KC][TS]   L21 rows of tile-row I   (KC pivots at a time)
+  double* sBt = sm + KC * TS;        // [KC][TS]   L21 rows of tile-row J scaled by D
+  double* sC = sm + 2 * KC * TS;     // [TS][TS+1] children's contributions
   const int4 td = tiles[blockIdx.x];
   const int s = td.x, ti = td.y, tj = td.z;
   const int tid = threadIdx.x;
@@ -324,11 +375,6 @@ __global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __re
   const int i0 = ti * TS, j0 = tj * TS;
   const int ni = min(TS, nr - i0), nj = min(TS, nr - j0);
 
-  for (int idx = tid; idx < ns * TS; idx += 256) {
-    const int k = idx / TS, r = idx - k * TS;
-    sAt[idx] = (r < ni) ? P[(long long)k * ld + ns + i0 + r] : 0.0;
-    sBt[idx] = (r < nj) ? P[(long long)k * ld + ns + j0 + r] * d.D[f + k] : 0.0;
-  }
   for (int idx = tid; idx < TS * (TS + 1); idx += 256) sC[idx] = 0.0;
   __syncthreads();
   // extend-add (fixed child order; distinct destinations inside one child).  Only children whose
@@ -337,7 +383,7 @@ __global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __re
   __shared__ int s_wcnt[8];
   const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) {
     const int2 tr = d.child_trange[c];
-    return !(ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y);
+    return !(ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y) && !d.child_small[c];
   });
   const bool overflow = ncontrib > CB_CHILD_CAP;
   const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
@@ -345,17 +391,15 @@ __global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __re
     const int c = overflow ? d.child_list[d.child_ptr[s] + q] : s_list[q];
     if (overflow) {
       const int2 tr = d.child_trange[c];
-      if (ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y) continue;
+      if (ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y || d.child_small[c]) continue;
     }
     const long long crp = d.sn_rowptr[c];
     const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
     const int* __restrict__ relc = d.rel + crp;
-    if (tid < 4) {
-      const int key = ns + ((tid & 2) ? j0 : i0) + ((tid & 1) ? TS : 0);
-      s_rng[tid] = lower_bound_dev(relc, nrc, key);
-    }
-    __syncthreads();
-    const int a0 = s_rng[0], a1 = s_rng[1], b0 = s_rng[2], b1 = s_rng[3];
+    // first child row falling into tile row t is tp[t - tlo] (host precomputed, uniform loads)
+    const int* __restrict__ tp = d.child_tptr + d.child_tptr_off[c];
+    const int tlo = d.child_trange[c].x;
+    const int a0 = tp[ti - tlo], a1 = tp[ti - tlo + 1], b0 = tp[tj - tlo], b1 = tp[tj - tlo + 1];
     const int na = a1 - a0, nb = b1 - b0;
     if (na > 0 && nb > 0) {
       const double* __restrict__ Uc = d.U + d.upd_off[c];
@@ -367,6 +411,9 @@ __global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __re
     }
     __syncthreads();
   }
+  // all small children of this tile at once
+  apply_sorted_entries(sC, d.U, d.sc_tile_src, d.sc_tile_dst, d.sc_tile_ptr[blockIdx.x + tile_off],
+                       d.sc_tile_ptr[blockIdx.x + tile_off + 1], 256);
   // 4x4 register tile per thread
   const int tx = tid & 15, ty = tid >> 4;
   double acc[4][4];
@@ -374,14 +421,26 @@ __global__ void __launch_bounds__(256) k_update_tiles(LDLDev d, const int4* __re
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-  for (int k = 0; k < ns; k++) {
-    double a[4], b[4];
+  for (int k0 = 0; k0 < ns; k0 += KC) {
+    const int kc = min(KC, ns - k0);
+    __syncthreads();   // previous chunk fully consumed
+    for (int idx = tid; idx < kc * TS; idx += 256) {
+      const int k = idx / TS, r = idx - k * TS;
+      const long long col = (long long)(k0 + k) * ld + ns;
+      sAt[idx] = (r < ni) ? P[col + i0 + r] : 0.0;
+      sBt[idx] = (r < nj) ? P[col + j0 + r] * d.D[f + k0 + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kc; k++) {
+      double a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { a[i] = sAt[k * TS + tx + 16 * i]; b[i] = sBt[k * TS + ty + 16 * i]; }
+      for (int i = 0; i < 4; i++) { a[i] = sAt[k * TS + tx + 16 * i]; b[i] = sBt[k * TS + ty + 16 * i]; }
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+        for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -485,11 +544,21 @@ __global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int* __restri
     if (lane + 32 < ns) { sy[lane + 32] = y1; xp[f + lane + 32] = y1; }
   }
   __syncthreads();
+  // u = -L21 * y : every thread owns rows, 16 panel columns are fetched per batch so that many
+  // independent (coalesced) loads are in flight
   for (int a = tid; a < nr; a += SV_NT) {
     const double* __restrict__ pa = P + ns + a;
     double acc = 0.0;
-#pragma unroll 4
-    for (int j = 0; j < ns; j++) acc += pa[(long long)j * ld] * sy[j];
+    int j0 = 0;
+    for (; j0 + 16 <= ns; j0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; jj++) v[jj] = pa[(long long)(j0 + jj) * ld];
+      asm volatile("" ::: "memory");   // keep all 16 loads in flight before the first use
+#pragma unroll
+      for (int jj = 0; jj < 16; jj++) acc += v[jj] * sy[j0 + jj];
+    }
+    for (; j0 < ns; j0++) acc += pa[(long long)j0 * ld] * sy[j0];
     us[a] -= acc;
   }
 }
@@ -550,8 +619,20 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int* __restri
   for (int j = warp; j < ns; j += nwarp) {
     const double* __restrict__ cj = P + (long long)j * ld + ns;
     double acc = 0.0;
-    if (staged) for (int a = lane; a < nr; a += 32) acc += cj[a] * sx[a];
-    else for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
+    if (staged) {
+      int a0 = 0;
+      for (; a0 + 256 <= nr; a0 += 256) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = cj[a0 + q * 32 + lane];
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc += v[q] * sx[a0 + q * 32 + lane];
+      }
+      for (int a = a0 + lane; a < nr; a += 32) acc += cj[a] * sx[a];
+    } else {
+      for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
@@ -705,7 +786,23 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
         for (int64_t t = S.sn_rowptr[c]; t < S.sn_rowptr[c + 1]; t++) gsrc[pos[pbase + S.rel[t]]++] = (int)t;
       }
     }
+    std::vector<int> tptr_off(S.nsup + 1, 0), tptr;
+    for (int c = 0; c < S.nsup; c++) {
+      tptr_off[c] = (int)tptr.size();
+      const int p = S.sn_parent[c];
+      if (p < 0 || child_tr[c].x > child_tr[c].y) continue;
+      const int pns = S.sn_first[p + 1] - S.sn_first[p];
+      const int64_t b0 = S.sn_rowptr[c], e0 = S.sn_rowptr[c + 1];
+      int64_t t = b0 + child_nb[c];
+      for (int tile = child_tr[c].x; tile <= child_tr[c].y + 1; tile++) {
+        while (t < e0 && S.rel[t] < pns + tile * TS) t++;
+        tptr.push_back((int)(t - b0));
+      }
+    }
+    tptr_off[S.nsup] = (int)tptr.size();
     int* t1 = nullptr;
+    if ((rc = upload(&t1, tptr_off))) return rc; dev.child_tptr_off = t1;
+    if ((rc = upload(&t1, tptr))) return rc; dev.child_tptr = t1;
     if ((rc = upload(&t1, child_nb))) return rc; dev.child_nb = t1;
     if ((rc = upload(&t1, gptr))) return rc; dev.gat_ptr = t1;
     if ((rc = upload(&t1, gsrc))) return rc; dev.gat_src = t1;
@@ -721,7 +818,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   const int cap_big = (max_optin - 2048) / 8;  // doubles
   CK(cudaFuncSetAttribute(k_factor_level<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_big * 8));
   const size_t smem_panel = 0;   // static shared memory only
-  const size_t smem_tiles = (size_t)(2 * CB_PB_MAXNS * TS + TS * (TS + 1)) * 8;
+  const size_t smem_tiles = (size_t)(2 * KC * TS + TS * (TS + 1)) * 8;
   CK(cudaFuncSetAttribute(k_update_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiles));
   const long long classes[3] = {1024, 5632, cap_big};  // 8 KB, 44 KB, ~225 KB panels
   plan.clear();
@@ -780,6 +877,57 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     d_tiles = t4;
     n_tiles = (int64_t)tiles.size();
   }
+  // small children (nr <= CB_SMALL_CHILD) of big fronts: one dst-sorted (src,dst) list per panel and per tile
+  {
+    std::vector<int> big_pos(S.nsup, -1), tile_base(S.nsup, -1);
+    for (size_t k = 0; k < big_tasks.size(); k++) big_pos[big_tasks[k]] = (int)k;
+    for (size_t k = 0; k < tiles.size(); k++) if (tile_base[tiles[k].x] < 0) tile_base[tiles[k].x] = (int)k;
+    std::vector<signed char> small(S.nsup, 0);
+    struct Ent { int key; int dst; int src; };
+    std::vector<Ent> pe, te;
+    for (int c = 0; c < S.nsup; c++) {
+      const int p = S.sn_parent[c];
+      if (p < 0 || big_pos[p] < 0) continue;
+      const int64_t b0 = S.sn_rowptr[c];
+      const int nrc = (int)(S.sn_rowptr[c + 1] - b0);
+      if (nrc > CB_SMALL_CHILD) continue;
+      if (S.upd_off[c] + (int64_t)nrc * nrc > 0x7fffffffLL) continue;   // int32 source indices
+      small[c] = 1;
+      const int pns = S.sn_first[p + 1] - S.sn_first[p];
+      const int pld = pns + (int)(S.sn_rowptr[p + 1] - S.sn_rowptr[p]);
+      for (int b = 0; b < nrc; b++)
+        for (int a = b; a < nrc; a++) {
+          const int ra = S.rel[b0 + a], rb = S.rel[b0 + b];
+          const int64_t src = S.upd_off[c] + (int64_t)b * nrc + a;
+          if (rb < pns) pe.push_back({big_pos[p], rb * pld + ra, (int)src});
+          else {
+            const int ti = (ra - pns) / TS, tj = (rb - pns) / TS;
+            te.push_back({tile_base[p] + ti * (ti + 1) / 2 + tj,
+                          (ra - pns - ti * TS) * (TS + 1) + (rb - pns - tj * TS), (int)src});
+          }
+        }
+    }
+    auto build = [&](std::vector<Ent>& v, size_t nkeys, std::vector<int>& ptr, std::vector<int>& src, std::vector<int>& dst) {
+      std::stable_sort(v.begin(), v.end(), [](const Ent& x, const Ent& y) { return x.key != y.key ? x.key < y.key : x.dst < y.dst; });
+      ptr.assign(nkeys + 1, 0);
+      for (auto& e : v) ptr[e.key + 1]++;
+      for (size_t i = 0; i < nkeys; i++) ptr[i + 1] += ptr[i];
+      src.resize(v.size() ? v.size() : 1); dst.resize(v.size() ? v.size() : 1);
+      for (size_t i = 0; i < v.size(); i++) { src[i] = v[i].src; dst[i] = v[i].dst; }
+    };
+    std::vector<int> ptr, src, dst;
+    int* t1 = nullptr;
+    build(pe, big_tasks.size(), ptr, src, dst);
+    if ((rc = upload(&t1, ptr))) return rc; dev.sc_panel_ptr = t1;
+    if ((rc = upload(&t1, src))) return rc; dev.sc_panel_src = t1;
+    if ((rc = upload(&t1, dst))) return rc; dev.sc_panel_dst = t1;
+    build(te, tiles.size(), ptr, src, dst);
+    if ((rc = upload(&t1, ptr))) return rc; dev.sc_tile_ptr = t1;
+    if ((rc = upload(&t1, src))) return rc; dev.sc_tile_src = t1;
+    if ((rc = upload(&t1, dst))) return rc; dev.sc_tile_dst = t1;
+    signed char* t8 = nullptr;
+    if ((rc = upload(&t8, small))) return rc; dev.child_small = t8;
+  }
   // solve plan: per level, narrow-pivot fronts first (one warp each) then the wide ones (one CTA each)
   {
     std::vector<int> st(S.level_tasks.size());
@@ -817,7 +965,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -830,9 +978,9 @@ int LDLObject::refactor_async() {
   g_launches += plan.size();
   for (const LaunchSeg& g : plan) {
     if (g.kind == 1)
-      k_panel_big<<<g.count, PB_NT, (size_t)g.smem_doubles * 8, stream>>>(dev, d_big_tasks + g.base);
+      k_panel_big<<<g.count, PB_NT, (size_t)g.smem_doubles * 8, stream>>>(dev, d_big_tasks + g.base, g.base);
     else if (g.kind == 2)
-      k_update_tiles<<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, d_tiles + g.base);
+      k_update_tiles<<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, d_tiles + g.base, g.base);
     else if (g.threads == 64)
       k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
     else

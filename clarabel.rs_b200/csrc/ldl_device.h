@@ -13,6 +13,7 @@
 #define CB_PB_LD 66        /* padded leading dimension of the pivot block in shared memory */
 #define CB_SOLVE_SMALL_NS 8 /* solves: fronts with at most this many pivots get one warp, wider ones one CTA */
 #define CB_SOLVE_STAGE 1536  /* doubles of gathered x staged in shared memory by k_bwd_big */
+#define CB_SMALL_CHILD 16  /* children of big fronts with at most this many rows go through sorted entry lists */
 #define CB_BIG_NR 96       /* fronts with at least this many rows below the pivot block use the multi-CTA path */
 
 namespace cb {
@@ -35,6 +36,11 @@ struct LDLDev {
   const int* level_tasks = nullptr;
   const int* child_nb = nullptr;      // per front: rows that land inside its parent's pivot block
   const int2* child_trange = nullptr; // per front: [first,last] 64-row tile of the parent's update matrix it touches
+  const int* child_tptr_off = nullptr; // per front: offset into child_tptr
+  const int* child_tptr = nullptr;     // first own row falling into each parent tile row (tlo..thi+1)
+  const signed char* child_small = nullptr;  // 1: child of a big front handled through the sorted entry lists
+  const int *sc_panel_ptr = nullptr, *sc_panel_src = nullptr, *sc_panel_dst = nullptr;  // per big front
+  const int *sc_tile_ptr = nullptr, *sc_tile_src = nullptr, *sc_tile_dst = nullptr;     // per update tile
   const int* gat_ptr = nullptr;       // solves: per front slot, CSR of contributing child update-vector entries
   const int* gat_src = nullptr;
   const int* perm = nullptr;

@@ -169,10 +169,28 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   const std::vector<int>& cc = S.colcount;
   std::vector<int> sfirst;  // start column of every supernode
   {
-    // fundamental (structure-nested chains)
+    // (1) whole small subtrees become one dense front each: in a post-ordered tree the subtree of r is
+    //     the contiguous column range [r - size(r) + 1, r] and every row it reaches beyond r is in
+    //     struct(L(:,r)), so the merged front is size(r) pivots by colcount[r] rows.  This trades a few
+    //     explicit zeros at the leaves for far fewer fronts / children / tree levels.
+    std::vector<int> sub(n, 1);
+    for (int j = 0; j < n; j++) if (parent[j] >= 0) sub[parent[j]] += sub[j];
+    std::vector<char> in_small(n, 0), small_root(n, 0);
+    if (opt.relax_subtree > 1)
+      for (int r = 0; r < n; r++) {
+        const bool fits = sub[r] <= opt.relax_subtree;
+        const bool top = parent[r] < 0 || sub[parent[r]] > opt.relax_subtree;
+        if (fits && top && sub[r] > 1) {
+          small_root[r] = 1;
+          for (int j = r - sub[r] + 1; j <= r; j++) in_small[j] = 1;
+        }
+      }
+    // (2) fundamental supernodes (structure-nested chains) for everything else
     std::vector<int> fs;   // first col
     for (int j = 0; j < n; j++) {
       bool join = j > 0 && parent[j - 1] == j && cc[j] == cc[j - 1] - 1;
+      if (in_small[j]) join = !(j == 0 || !in_small[j - 1] || small_root[j - 1]);
+      else if (j > 0 && in_small[j - 1]) join = false;
       if (!join) fs.push_back(j);
     }
     int nf = (int)fs.size();
@@ -390,8 +408,10 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
 }
 
 int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
-            const SymbolicOptions& opt, Symbolic& S) {
+            const SymbolicOptions& opt_in, Symbolic& S) {
   if (n <= 0) return -1;
+  SymbolicOptions opt = opt_in;
+  if (const char* e = std::getenv("CB_RELAX_SUBTREE")) opt.relax_subtree = std::atoi(e);   // tuning knob
   for (int j = 0; j < n; j++) {
     if (!(Ap[j] < Ap[j + 1])) return -2;  // empty column (qdldl.rs:222-225)
     for (int64_t p = Ap[j]; p < Ap[j + 1]; p++)
