@@ -120,6 +120,8 @@ typedef struct {
     double *w, *lam; double eta;
     int sparse; double *u, *v; double d;
     idx *map_u, *map_v; idx map_D[2];
+    /* PSD triangle cone (psdtrianglecone.rs:12-60): matrix dimension and dense work data */
+    idx psd_n; double *R, *Rinv, *lisqrt, *HsM, *W1, *W2, *W3, *wv;
 } cone_t;
 
 typedef struct { idx m, n; idx *colptr, *rowval; double *nzval; } csc;
@@ -291,9 +293,202 @@ static double soc_step_component(const double *x, const double *y, idx n, double
     return amax < r ? amax : r;
 }
 
+
+/* ------------------------------------------------ PSD triangle cone helpers
+ * Dense column-major n x n work; restates psdtrianglecone.rs with the LAPACK
+ * calls (dpotrf, dgesdd, dsyevr -- third-party, not under /root/reference)
+ * replaced by textbook algorithms: Cholesky, one-sided Jacobi SVD (Hestenes),
+ * cyclic Jacobi eigenvalues.  Results are pinned end-to-end on tests/basic_sdp.rs
+ * and against numpy's LAPACK in tests/test_oracle_psd.py. */
+#define MAT(A, n, i, j) (A)[(size_t)(j) * (size_t)(n) + (size_t)(i)]
+static idx tri_index(idx k) { return (k * (k + 3)) >> 1; }
+
+static void svec_to_mat(double *M, idx n, const double *x)
+{   /* dense/matrix_math.rs:165-183 */
+    idx t = 0;
+    for (idx col = 0; col < n; col++) for (idx row = 0; row <= col; row++) {
+        if (row == col) MAT(M, n, row, col) = x[t];
+        else { MAT(M, n, row, col) = x[t] * 0.70710678118654752440; MAT(M, n, col, row) = x[t] * 0.70710678118654752440; }
+        t++;
+    }
+}
+static void mat_to_svec(double *x, const double *M, idx n)
+{   /* dense/matrix_math.rs:186-203 */
+    idx t = 0;
+    for (idx col = 0; col < n; col++) for (idx row = 0; row <= col; row++) {
+        x[t] = (row == col) ? MAT(M, n, row, col) : (MAT(M, n, row, col) + MAT(M, n, col, row)) * 0.70710678118654752440;
+        t++;
+    }
+}
+/* lower Cholesky factor of the symmetric A into L (upper part zero); -1 if not positive definite */
+static int chol_lower(double *L, const double *A, idx n)
+{
+    for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) MAT(L, n, i, j) = 0.0;
+    for (idx j = 0; j < n; j++) {
+        double d = MAT(A, n, j, j);
+        for (idx k = 0; k < j; k++) d -= MAT(L, n, j, k) * MAT(L, n, j, k);
+        if (!(d > 0.0)) return -1;
+        d = sqrt(d);
+        MAT(L, n, j, j) = d;
+        for (idx i = j + 1; i < n; i++) {
+            double v = MAT(A, n, i, j);
+            for (idx k = 0; k < j; k++) v -= MAT(L, n, i, k) * MAT(L, n, j, k);
+            MAT(L, n, i, j) = v / d;
+        }
+    }
+    return 0;
+}
+/* eigenvalues of a symmetric matrix (destroyed) by cyclic Jacobi */
+static void sym_eigvals(double *A, idx n, double *lam)
+{
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, dg = 0.0;
+        for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) { double v = MAT(A, n, i, j); if (i == j) dg += v * v; else off += v * v; }
+        if (off <= 1e-32 * (dg + off) || off == 0.0) break;
+        for (idx p = 0; p < n - 1; p++) for (idx q = p + 1; q < n; q++) {
+            double apq = MAT(A, n, p, q);
+            if (apq == 0.0) continue;
+            double theta = (MAT(A, n, q, q) - MAT(A, n, p, p)) / (2.0 * apq);
+            double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            for (idx k = 0; k < n; k++) { double akp = MAT(A, n, k, p), akq = MAT(A, n, k, q); MAT(A, n, k, p) = c * akp - sn * akq; MAT(A, n, k, q) = sn * akp + c * akq; }
+            for (idx k = 0; k < n; k++) { double apk = MAT(A, n, p, k), aqk = MAT(A, n, q, k); MAT(A, n, p, k) = c * apk - sn * aqk; MAT(A, n, q, k) = sn * apk + c * aqk; }
+        }
+    }
+    for (idx i = 0; i < n; i++) lam[i] = MAT(A, n, i, i);
+}
+/* M = U diag(s) V^T by one-sided Jacobi; singular values sorted descending like LAPACK */
+static void jacobi_svd(const double *M, idx n, double *U, double *sv, double *V)
+{
+    memcpy(U, M, (size_t)(n * n) * sizeof(double));
+    for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) MAT(V, n, i, j) = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotated = 0;
+        for (idx p = 0; p < n - 1; p++) for (idx q = p + 1; q < n; q++) {
+            double a = 0, b = 0, g = 0;
+            for (idx k = 0; k < n; k++) { double up = MAT(U, n, k, p), uq = MAT(U, n, k, q); a += up * up; b += uq * uq; g += up * uq; }
+            if (fabs(g) <= 1e-15 * sqrt(a * b) || g == 0.0) continue;
+            rotated = 1;
+            double zeta = (b - a) / (2.0 * g);
+            double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+            for (idx k = 0; k < n; k++) { double up = MAT(U, n, k, p), uq = MAT(U, n, k, q); MAT(U, n, k, p) = c * up - sn * uq; MAT(U, n, k, q) = sn * up + c * uq; }
+            for (idx k = 0; k < n; k++) { double vp = MAT(V, n, k, p), vq = MAT(V, n, k, q); MAT(V, n, k, p) = c * vp - sn * vq; MAT(V, n, k, q) = sn * vp + c * vq; }
+        }
+        if (!rotated) break;
+    }
+    for (idx j = 0; j < n; j++) {
+        double nn = 0; for (idx k = 0; k < n; k++) nn += MAT(U, n, k, j) * MAT(U, n, k, j);
+        sv[j] = sqrt(nn);
+        if (sv[j] > 0) for (idx k = 0; k < n; k++) MAT(U, n, k, j) /= sv[j];
+    }
+    for (idx a = 0; a < n - 1; a++) {       /* selection sort, descending */
+        idx m = a; for (idx b = a + 1; b < n; b++) if (sv[b] > sv[m]) m = b;
+        if (m != a) {
+            double t = sv[a]; sv[a] = sv[m]; sv[m] = t;
+            for (idx k = 0; k < n; k++) { t = MAT(U, n, k, a); MAT(U, n, k, a) = MAT(U, n, k, m); MAT(U, n, k, m) = t; t = MAT(V, n, k, a); MAT(V, n, k, a) = MAT(V, n, k, m); MAT(V, n, k, m) = t; }
+        }
+    }
+}
+/* C = alpha * op(A) op(B) + beta * C, all n x n */
+static void gemm_nn(double *C, const double *A, int ta, const double *B, int tb, idx n, double alpha, double beta)
+{
+    for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) {
+        double acc = 0.0;
+        for (idx k = 0; k < n; k++) acc += (ta ? MAT(A, n, k, i) : MAT(A, n, i, k)) * (tb ? MAT(B, n, j, k) : MAT(B, n, k, j));
+        MAT(C, n, i, j) = alpha * acc + (beta == 0.0 ? 0.0 : beta * MAT(C, n, i, j));
+    }
+}
+/* psdtrianglecone.rs:364-396 */
+static void psd_mul_Wx(const cone_t *c, int transpose, double *y, const double *x, double alpha, double beta, const double *Rx)
+{
+    idx n = c->psd_n; double *X = c->W1, *Y = c->W2, *tmp = c->W3;
+    svec_to_mat(X, n, x); svec_to_mat(Y, n, y);
+    if (transpose) { gemm_nn(tmp, X, 0, Rx, 1, n, 1.0, 0.0); gemm_nn(Y, Rx, 0, tmp, 0, n, alpha, beta); }
+    else { gemm_nn(tmp, Rx, 1, X, 0, n, 1.0, 0.0); gemm_nn(Y, tmp, 0, Rx, 0, n, alpha, beta); }
+    mat_to_svec(y, Y, n);
+}
+/* psdtrianglecone.rs:467-509 : upper triangle of the symmetric Kronecker product A (x)_s A */
+static void psd_skron(double *out, idx N, const double *A, idx n)
+{
+    const double sqrt2 = 1.4142135623730951;
+    idx col = 0;
+    for (idx l = 0; l < n; l++) for (idx k = 0; k <= l; k++) {
+        idx row = 0; int kl_eq = (k == l);
+        for (idx j = 0; j < n && row <= col; j++) {
+            double Ajl = MAT(A, n, j, l), Ajk = MAT(A, n, j, k);
+            for (idx i = 0; i <= j; i++) {
+                if (row > col) break;
+                int ij_eq = (i == j);
+                double v;
+                if (!ij_eq && !kl_eq) v = MAT(A, n, i, k) * Ajl + MAT(A, n, i, l) * Ajk;
+                else if (ij_eq && !kl_eq) v = sqrt2 * Ajl * Ajk;
+                else if (!ij_eq && kl_eq) v = sqrt2 * MAT(A, n, i, l) * Ajk;
+                else v = Ajl * Ajl;
+                MAT(out, N, row, col) = v;
+                row++;
+            }
+        }
+        col++;
+    }
+}
+static int psd_update_scaling(cone_t *c, const double *s, const double *z)
+{   /* psdtrianglecone.rs:144-204 */
+    idx n = c->psd_n; if (n == 0) return 1;
+    double *S = c->W1, *Z = c->W2;
+    double *L1 = dvec(n * n), *L2 = dvec(n * n), *M = dvec(n * n), *U = dvec(n * n), *V = dvec(n * n), *sv = dvec(n);
+    int ok = 1;
+    svec_to_mat(S, n, s); svec_to_mat(Z, n, z);
+    if (chol_lower(L1, S, n) || chol_lower(L2, Z, n)) ok = 0;
+    if (ok) {
+        gemm_nn(M, L2, 1, L1, 0, n, 1.0, 0.0);           /* L2' L1 */
+        jacobi_svd(M, n, U, sv, V);
+        for (idx i = 0; i < n; i++) { c->lam[i] = sv[i]; c->lisqrt[i] = 1.0 / sqrt(sv[i]); }
+        gemm_nn(c->R, L1, 0, V, 0, n, 1.0, 0.0);          /* R = L1 V Lambda^-1/2 */
+        for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) MAT(c->R, n, i, j) *= c->lisqrt[j];
+        gemm_nn(c->Rinv, U, 1, L2, 1, n, 1.0, 0.0);       /* Rinv = Lambda^-1/2 U' L2' */
+        for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) MAT(c->Rinv, n, i, j) *= c->lisqrt[i];
+        gemm_nn(c->W1, c->R, 0, c->R, 1, n, 1.0, 0.0);    /* R R' */
+        psd_skron(c->HsM, c->dim, c->W1, n);
+    }
+    free(L1); free(L2); free(M); free(U); free(V); free(sv);
+    return ok;
+}
+static double psd_step_component(cone_t *c, const double *d, double amax)
+{   /* psdtrianglecone.rs:437-463 */
+    idx n = c->psd_n; if (n == 0) return amax;
+    double *Wk = c->W1;
+    svec_to_mat(Wk, n, d);
+    for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) MAT(Wk, n, i, j) *= c->lisqrt[i] * c->lisqrt[j];
+    double *ev = dvec(n);
+    sym_eigvals(Wk, n, ev);
+    double g = INFINITY; for (idx i = 0; i < n; i++) if (ev[i] < g) g = ev[i];
+    free(ev);
+    if (g < 0.0) { double t = -(1.0 / g); return t < amax ? t : amax; }
+    return amax;
+}
+static void psd_circ(cone_t *c, double *x, const double *y, const double *z)
+{   /* psdtrianglecone.rs:406-420: X = (YZ + ZY)/2 */
+    idx n = c->psd_n; double *Y = c->W1, *Z = c->W2, *X = c->W3;
+    svec_to_mat(Y, n, y); svec_to_mat(Z, n, z);
+    for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) {
+        double acc = 0.0;
+        for (idx k = 0; k < n; k++) acc += MAT(Y, n, i, k) * MAT(Z, n, k, j) + MAT(Z, n, i, k) * MAT(Y, n, k, j);
+        MAT(X, n, i, j) = 0.5 * acc;
+    }
+    mat_to_svec(x, X, n);
+}
+static void psd_lambda_inv_circ(cone_t *c, double *x, const double *z)
+{   /* psdtrianglecone.rs:317-332 */
+    idx n = c->psd_n; double *X = c->W1, *Z = c->W2;
+    svec_to_mat(Z, n, z);
+    for (idx i = 0; i < n; i++) for (idx j = 0; j < n; j++) MAT(X, n, i, j) = (2.0 * MAT(Z, n, i, j)) / (c->lam[i] + c->lam[j]);
+    mat_to_svec(x, X, n);
+}
+
 static int cone_is_sparse(const cone_t *c) { return c->type == CONE_SOC && c->sparse; }
-static int cone_Hs_diag(const cone_t *c) { return c->type != CONE_SOC || c->sparse; }
-static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : 1); }
+static int cone_Hs_diag(const cone_t *c) { return c->type == CONE_ZERO || c->type == CONE_NONNEG || (c->type == CONE_SOC && c->sparse); }
+static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : (c->type == CONE_PSD ? c->psd_n : 1)); }
 
 static void cones_set_identity(oipm_t *S)
 {
@@ -308,6 +503,10 @@ static void cones_set_identity(oipm_t *S)
                 for (idx i = 0; i < c->dim; i++) { c->u[i] = 0.0; c->v[i] = 0.0; }
                 c->u[0] = 0.70710678118654752440;
             }
+        } else if (c->type == CONE_PSD) {
+            idx n = c->psd_n, N = c->dim;
+            for (idx j = 0; j < n; j++) for (idx i = 0; i < n; i++) { MAT(c->R, n, i, j) = (i == j); MAT(c->Rinv, n, i, j) = (i == j); }
+            for (idx j = 0; j < N; j++) for (idx i = 0; i < N; i++) MAT(c->HsM, N, i, j) = (i == j);
         }
     }
 }
@@ -357,6 +556,8 @@ static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_)
                 c->v[0] = 0.0;
                 for (idx i = 1; i < n; i++) c->v[i] = v1 * w[i];
             }
+        } else if (c->type == CONE_PSD) {
+            if (!psd_update_scaling(c, s, z)) return 0;
         }
     }
     return 1;
@@ -381,6 +582,9 @@ static void cones_get_Hs(const oipm_t *S, double *Hs)
                 }
                 for (idx i = 0; i < c->blen; i++) H[i] *= e2;
             }
+        } else if (c->type == CONE_PSD) {
+            idx N = c->dim, t = 0;     /* pack_triu, dense/types.rs:187-201 */
+            for (idx col = 0; col < N; col++) for (idx row = 0; row <= col; row++) H[t++] = MAT(c->HsM, N, row, col);
         }
     }
 }
@@ -398,6 +602,9 @@ static void cones_mul_Hs(oipm_t *S, double *y_, const double *x_)
             for (idx i = 0; i < n; i++) y[i] = cc * c->w[i] + y[i];
             double e2 = c->eta * c->eta;
             for (idx i = 0; i < n; i++) y[i] *= e2;
+        } else if (c->type == CONE_PSD) {
+            psd_mul_Wx(c, 0, c->wv, x, 1.0, 0.0, c->R);     /* work = W x  */
+            psd_mul_Wx(c, 1, y, c->wv, 1.0, 0.0, c->R);     /* y = W' work */
         }
     }
 }
@@ -409,6 +616,7 @@ static void cones_affine_ds(const oipm_t *S, double *ds_)
         if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) ds[i] = 0.0;
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) ds[i] = c->lam[i] * c->lam[i];
         else if (c->type == CONE_SOC) soc_circ(ds, c->lam, c->lam, n);
+        else if (c->type == CONE_PSD) { for (idx i = 0; i < n; i++) ds[i] = 0.0; for (idx k = 0; k < c->psd_n; k++) ds[tri_index(k)] = c->lam[k] * c->lam[k]; }
     }
 }
 
@@ -420,6 +628,13 @@ static void cones_combined_ds_shift(oipm_t *S, double *shift_, double *sz_, doub
         double *shift = shift_ + c->off, *sz = sz_ + c->off, *ss = ss_ + c->off;
         if (c->type == CONE_ZERO) { for (idx i = 0; i < n; i++) shift[i] = 0.0; continue; }
         double *tmp = shift;
+        if (c->type == CONE_PSD) {
+            memcpy(tmp, sz, (size_t)n * sizeof(double)); psd_mul_Wx(c, 0, sz, tmp, 1.0, 0.0, c->R);
+            memcpy(tmp, ss, (size_t)n * sizeof(double)); psd_mul_Wx(c, 1, ss, tmp, 1.0, 0.0, c->Rinv);
+            psd_circ(c, shift, ss, sz);
+            for (idx k = 0; k < c->psd_n; k++) shift[tri_index(k)] += -sigmamu;
+            continue;
+        }
         memcpy(tmp, sz, (size_t)n * sizeof(double));
         if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) sz[i] = 1.0 * (tmp[i] * c->w[i]) + 0.0 * sz[i];
         else soc_mul_W(sz, tmp, 1.0, 0.0, c->w, c->eta, n);
@@ -438,6 +653,7 @@ static void cones_ds_from_dz_offset(oipm_t *S, double *out_, const double *ds_, 
         double *out = out_ + c->off; const double *ds = ds_ + c->off, *z = z_ + c->off;
         if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) out[i] = 0.0;
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) out[i] = ds[i] / z[i];
+        else if (c->type == CONE_PSD) { psd_lambda_inv_circ(c, c->wv, ds); psd_mul_Wx(c, 1, out, c->wv, 1.0, 0.0, c->R); }
         else {
             double resz = soc_residual(z, n);
             double l1ds1 = vdot(c->lam + 1, ds + 1, n - 1), w1ds1 = vdot(c->w + 1, ds + 1, n - 1);
@@ -469,6 +685,9 @@ static double cones_step_length(oipm_t *S, const double *dz_, const double *ds_,
         } else if (c->type == CONE_SOC) {
             az = soc_step_component(z, dz, n, alpha);
             as = soc_step_component(s, ds, n, alpha);
+        } else if (c->type == CONE_PSD) {
+            psd_mul_Wx(c, 0, c->wv, dz, 1.0, 0.0, c->R);      az = psd_step_component(c, c->wv, alpha);
+            psd_mul_Wx(c, 1, c->wv, ds, 1.0, 0.0, c->Rinv);   as = psd_step_component(c, c->wv, alpha);
         }
         double m = az < as ? az : as;
         if (m < alpha) alpha = m;
@@ -487,6 +706,12 @@ static void cones_margins(oipm_t *S, const double *z_, double *amin, double *bsu
             for (idx i = 0; i < n; i++) { if (z[i] < ai) ai = z[i]; bi += z[i] > 0.0 ? z[i] : 0.0; }
         } else if (c->type == CONE_SOC) {
             ai = z[0] - vnorm(z + 1, n - 1); bi = ai > 0.0 ? ai : 0.0;
+        } else if (c->type == CONE_PSD && c->psd_n > 0) {
+            double *ev = dvec(c->psd_n);
+            svec_to_mat(c->W1, c->psd_n, z); sym_eigvals(c->W1, c->psd_n, ev);
+            ai = INFINITY;
+            for (idx i = 0; i < c->psd_n; i++) { if (ev[i] < ai) ai = ev[i]; bi += ev[i] > 0.0 ? ev[i] : 0.0; }
+            free(ev);
         }
         if (ai < a) a = ai;
         b += bi;
@@ -499,6 +724,7 @@ static void cones_scaled_unit_shift(oipm_t *S, double *z_, double alpha, int pri
         cone_t *c = &S->cones[k]; double *z = z_ + c->off; idx n = c->dim;
         if (c->type == CONE_ZERO) { if (primal) for (idx i = 0; i < n; i++) z[i] = 0.0; }
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) z[i] += alpha;
+        else if (c->type == CONE_PSD) for (idx k = 0; k < c->psd_n; k++) z[tri_index(k)] += alpha;
         else z[0] += alpha;
     }
 }
@@ -745,7 +971,7 @@ static void equilibrate(oipm_t *S)
     for (idx i = 0; i < m; i++) ew[i] = 1.0;
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k];
-        if (c->type == CONE_SOC) {
+        if (c->type == CONE_SOC || c->type == CONE_PSD) {
             double mean = vmean(e + c->off, c->dim);
             for (idx i = 0; i < c->dim; i++) ew[c->off + i] = (1.0 / e[c->off + i]) * mean;
             changed = 1;
@@ -761,7 +987,8 @@ void oipm_free(oipm_t *S)
 {
     if (!S) return;
     csc_free(&S->P); csc_free(&S->A); free(S->q); free(S->b);
-    for (idx k = 0; k < S->ncones; k++) { cone_t *c = &S->cones[k]; free(c->w); free(c->lam); free(c->u); free(c->v); free(c->map_u); free(c->map_v); }
+    for (idx k = 0; k < S->ncones; k++) { cone_t *c = &S->cones[k]; free(c->w); free(c->lam); free(c->u); free(c->v); free(c->map_u); free(c->map_v);
+        free(c->R); free(c->Rinv); free(c->lisqrt); free(c->HsM); free(c->W1); free(c->W2); free(c->W3); free(c->wv); }
     free(S->cones); free(S->d); free(S->dinv); free(S->e); free(S->einv);
     if (S->K.colptr) csc_free(&S->K);
     free(S->map_P); free(S->map_A); free(S->map_Hs); free(S->map_diagP); free(S->map_diag_full);
@@ -813,9 +1040,9 @@ int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const dou
             }
             S->cones[nc].type = CONE_NONNEG; S->cones[nc].dim = tot; nc++;
         } else {
-            if (t == CONE_PSD) { oipm_free(S); return -3; }  /* PSD not in this oracle build */
             if (t == CONE_SOC && dm < 2) { oipm_free(S); return -2; }
-            S->cones[nc].type = t; S->cones[nc].dim = dm; nc++; k++;
+            S->cones[nc].type = t; S->cones[nc].dim = (t == CONE_PSD) ? dm * (dm + 1) / 2 : dm;
+            S->cones[nc].psd_n = (t == CONE_PSD) ? dm : 0; nc++; k++;
         }
     }
     S->ncones = nc;
@@ -825,6 +1052,11 @@ int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const dou
         cn->off = off; off += cn->dim;
         S->degree += cone_degree(cn);
         if (cn->type != CONE_ZERO) { cn->w = dvec(cn->dim); cn->lam = dvec(cn->dim); }
+        if (cn->type == CONE_PSD) {
+            idx n2 = cn->psd_n * cn->psd_n;
+            cn->R = dvec(n2); cn->Rinv = dvec(n2); cn->lisqrt = dvec(cn->psd_n); cn->HsM = dvec(cn->dim * cn->dim);
+            cn->W1 = dvec(n2); cn->W2 = dvec(n2); cn->W3 = dvec(n2); cn->wv = dvec(cn->dim);
+        }
         if (cn->type == CONE_SOC && cn->dim > 4) { cn->sparse = 1; cn->u = dvec(cn->dim); cn->v = dvec(cn->dim); cn->d = 1.0; }
     }
     if (off != m) { oipm_free(S); return -1; }
