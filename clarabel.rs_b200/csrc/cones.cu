@@ -388,10 +388,11 @@ int ConeSet::collapse(const int32_t* types, const uint64_t* dims, uint64_t n, st
         }
         k++;
       }
-      out.push_back({CT_NONNEG, (int)tot});
+      out.push_back({CT_NONNEG, (int)tot, 0});
     } else {
       if (t == CT_SOC && d < 2) return -21;
-      out.push_back({t, (int)d});
+      if (t == CT_PSD) { if (d > (uint64_t)CB_PSD_MAX_N) return -21; out.push_back({t, (int)(d * (d + 1) / 2), (int)d}); }
+      else out.push_back({t, (int)d, 0});
       k++;
     }
   }
@@ -419,14 +420,14 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
   for (int k = 0; k < nc; k++) {
     type[k] = cs[k].type; dim[k] = cs[k].dim;
     off[k] = m; boff[k] = nHs;
-    if (cs[k].type == CT_PSD) return -21;  // PSD cones: not in this build
     const bool sp = cs[k].type == CT_SOC && cs[k].dim > SOC_NO_EXPANSION_MAX_SIZE;
     sparse_flag[k] = sp ? 1 : 0;
-    const bool diag = cs[k].type != CT_SOC || sp;
+    const bool diag = cs[k].type == CT_ZERO || cs[k].type == CT_NONNEG || sp;
     nHs += diag ? cs[k].dim : cs[k].dim * (cs[k].dim + 1) / 2;
     m += cs[k].dim;
-    degree += cs[k].type == CT_ZERO ? 0 : (cs[k].type == CT_NONNEG ? cs[k].dim : 1);
+    degree += cs[k].type == CT_ZERO ? 0 : (cs[k].type == CT_NONNEG ? cs[k].dim : (cs[k].type == CT_PSD ? cs[k].psd_n : 1));
     if (cs[k].type == CT_SOC) soc_list.push_back(k);
+    if (cs[k].type == CT_PSD) psd_list.push_back(k);
     if (sp) p += 2;
   }
   std::vector<signed char> tag(m);
@@ -452,7 +453,25 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
   CCK(cudaMalloc((void**)&ws.partials, (size_t)(RED_BLOCKS + 64) * 4 * 8));
   CCK(cudaMalloc((void**)&ws.counter, sizeof(unsigned)));
   CCK(cudaMemset(ws.counter, 0, sizeof(unsigned)));
-  const size_t np = (size_t)RED_BLOCKS + soc_list.size() + 8;
+  {
+    std::vector<int> pn(nc, 0);
+    std::vector<long long> mo(nc, 0);
+    long long tot = 0;
+    psd_nmax = 0; psd_numel_max = 0;
+    for (int k = 0; k < nc; k++)
+      if (cs[k].type == CT_PSD) {
+        pn[k] = cs[k].psd_n; mo[k] = tot; tot += (long long)cs[k].psd_n * cs[k].psd_n;
+        if (cs[k].psd_n > psd_nmax) psd_nmax = cs[k].psd_n;
+        if (cs[k].dim > psd_numel_max) psd_numel_max = cs[k].dim;
+      }
+    dev.npsd = (int)psd_list.size();
+    if (up(&dev.psd_list, psd_list) || up(&dev.psd_n, pn) || up(&dev.psd_moff, mo)) return -20;
+    const size_t tb = (size_t)(tot ? tot : 1) * 8;
+    CCK(cudaMalloc((void**)&dev.psd_R, tb)); CCK(cudaMalloc((void**)&dev.psd_Rinv, tb)); CCK(cudaMalloc((void**)&dev.psd_RRt, tb));
+    CCK(cudaMemset(dev.psd_R, 0, tb)); CCK(cudaMemset(dev.psd_Rinv, 0, tb)); CCK(cudaMemset(dev.psd_RRt, 0, tb));
+    if (dev.npsd && psd_prepare()) return -20;
+  }
+  const size_t np = (size_t)RED_BLOCKS + soc_list.size() + psd_list.size() + 8;
   CCK(cudaMalloc((void**)&d_pmin, np * 8)); CCK(cudaMalloc((void**)&d_psum, np * 8));
   (void)g_row2blk_dummy;
   return 0;
@@ -463,6 +482,7 @@ void ConeSet::release() {
   fr(dev.type); fr(dev.off); fr(dev.dim); fr(dev.boff); fr(dev.sparse); fr(dev.soc_list); fr(dev.rowtag);
   fr(dev.w); fr(dev.lam); fr(dev.u); fr(dev.v); fr(dev.eta); fr(dev.dd); fr(dev.fail);
   fr(ws.partials); fr(ws.counter); fr(row2blk_dev); fr(d_pmin); fr(d_psum);
+  fr(dev.psd_list); fr(dev.psd_n); fr(dev.psd_moff); fr(dev.psd_R); fr(dev.psd_Rinv); fr(dev.psd_RRt);
 }
 
 #define EW_GRID ((m + 255) / 256)
@@ -472,12 +492,14 @@ void ConeSet::set_identity_scaling() {
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_set_identity<<<EW_GRID, 256, 0, stream>>>(dev);
   if (dev.nsoc) k_soc_set_identity<<<(dev.nsoc + 127) / 128, 128, 0, stream>>>(dev);
+  psd_set_identity();
 }
 void ConeSet::update_scaling(const double* s, const double* z) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_update_scaling<<<EW_GRID, 256, 0, stream>>>(dev, s, z);
   if (dev.nsoc) k_soc_update_scaling<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, s, z);
+  psd_update_scaling(s, z);
 }
 void ConeSet::get_Hs(double* Hs, bool negate) {
   if (m == 0) return;
@@ -485,49 +507,57 @@ void ConeSet::get_Hs(double* Hs, bool negate) {
   const double sg = negate ? -1.0 : 1.0;
   k_ew_get_Hs<<<EW_GRID, 256, 0, stream>>>(dev, Hs, sg, row2blk_dev);
   if (dev.nsoc) k_soc_get_Hs<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, Hs, sg);
+  psd_get_Hs(Hs, sg);
 }
 void ConeSet::mul_Hs(double* y, const double* x) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_mul_Hs<<<EW_GRID, 256, 0, stream>>>(dev, y, x);
   if (dev.nsoc) k_soc_mul_Hs<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, y, x);
+  psd_apply(0, y, const_cast<double*>(x), nullptr, 0.0);
 }
 void ConeSet::affine_ds(double* ds) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_affine_ds<<<EW_GRID, 256, 0, stream>>>(dev, ds);
   if (dev.nsoc) k_soc_affine_ds<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, ds);
+  psd_apply(1, ds, nullptr, nullptr, 0.0);
 }
 void ConeSet::combined_ds_shift(double* shift, double* step_z, double* step_s, double sigmamu) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_combined_shift<<<EW_GRID, 256, 0, stream>>>(dev, shift, step_z, step_s, sigmamu);
   if (dev.nsoc) k_soc_combined_shift<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, shift, step_z, step_s, sigmamu);
+  psd_apply(2, shift, step_z, step_s, sigmamu);
 }
 void ConeSet::ds_from_dz_offset(double* out, const double* ds, const double* z) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_ds_offset<<<EW_GRID, 256, 0, stream>>>(dev, out, ds, z);
   if (dev.nsoc) k_soc_ds_offset<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, out, ds, z);
+  psd_apply(3, out, const_cast<double*>(ds), nullptr, 0.0);
 }
 void ConeSet::step_length(const double* dz, const double* ds, const double* z, const double* s, double* alpha_slot) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_step_length<<<red_grid(m), RED_THREADS, 0, stream>>>(dev, dz, ds, z, s, alpha_slot);
   if (dev.nsoc) k_soc_step_length<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, dz, ds, z, s, alpha_slot);
+  psd_step_length(dz, ds, alpha_slot);
 }
 void ConeSet::margins(const double* z, double* out2) {
   const int g = m ? red_grid(m) : 0;
   g_launches += 1 + (g ? 1 : 0) + (dev.nsoc ? 1 : 0);
   if (g) k_ew_margins<<<g, RED_THREADS, 0, stream>>>(dev, z, d_pmin, d_psum);
   if (dev.nsoc) k_soc_margins<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, z, d_pmin + g, d_psum + g);
-  k_margins_final<<<1, 32, 0, stream>>>(d_pmin, d_psum, g, dev.nsoc, out2);
+  psd_margins(z, d_pmin + g + dev.nsoc, d_psum + g + dev.nsoc);
+  k_margins_final<<<1, 32, 0, stream>>>(d_pmin, d_psum, g, dev.nsoc + dev.npsd, out2);
 }
 void ConeSet::scaled_unit_shift(double* z, double alpha, bool primal) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_unit_shift<<<EW_GRID, 256, 0, stream>>>(dev, z, alpha, primal ? 1 : 0);
   if (dev.nsoc) k_soc_unit_shift<<<(dev.nsoc + 127) / 128, 128, 0, stream>>>(dev, z, alpha);
+  psd_apply(4, z, nullptr, nullptr, alpha);
 }
 
 }  // namespace cb

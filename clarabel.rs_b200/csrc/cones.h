@@ -35,9 +35,18 @@ struct ConeDev {
   double* v = nullptr;    // [m]
   double* dd = nullptr;   // [ncones]
   int* fail = nullptr;    // scaling failure flag
+  // PSD triangle cones (matrix dimension <= CB_PSD_MAX_N)
+  int npsd = 0;
+  const int* psd_list = nullptr;   // cone ids
+  const int* psd_n = nullptr;      // [ncones] matrix dimension (0 for other cones)
+  const long long* psd_moff = nullptr;  // [ncones] offset into the n x n matrix arenas
+  double *psd_R = nullptr, *psd_Rinv = nullptr, *psd_RRt = nullptr;
 };
 
-struct ConeSpec { int type; int dim; };
+constexpr int CB_PSD_MAX_N = 32;
+
+// dim = number of rows the cone occupies (numel); psd_n = matrix dimension of a PSD cone
+struct ConeSpec { int type; int dim; int psd_n = 0; };
 
 class ConeSet {
  public:
@@ -68,6 +77,17 @@ class ConeSet {
   // out2[0] = min margin, out2[1] = sum of positive margins
   void margins(const double* z, double* out2);
   void scaled_unit_shift(double* z, double alpha, bool primal);
+
+  // PSD pieces (cones_psd.cu)
+  std::vector<int> psd_list;
+  int psd_nmax = 0, psd_numel_max = 0;
+  int psd_prepare();
+  void psd_set_identity();
+  void psd_update_scaling(const double* s, const double* z);
+  void psd_get_Hs(double* Hs, double sign);
+  void psd_apply(int op, double* out, double* a, double* b, double scalar);
+  void psd_step_length(const double* dz, const double* ds, double* alpha_slot);
+  void psd_margins(const double* z, double* pmin, double* psum);
 };
 
 }  // namespace cb

@@ -230,7 +230,7 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
   for (int k = 0; k < nc; k++) {
     const ConeSpec& c = cones->cones[k];
     const int row = n + cones->off[k];
-    const bool diag = c.type != CT_SOC || cones->sparse_flag[k];
+    const bool diag = c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k];
     for (int i = 0; i < c.dim; i++) cnt[row + i] += diag ? 1 : i + 1;
     if (cones->sparse_flag[k]) { cnt[pcol] += c.dim + 1; cnt[pcol + 1] += c.dim + 1; pcol += 2; }
   }
@@ -265,7 +265,7 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
     const ConeSpec& c = cones->cones[k];
     const int row = n + cones->off[k];
     int* blk = map_Hs.data() + cones->boff[k];
-    const bool diag = c.type != CT_SOC || cones->sparse_flag[k];
+    const bool diag = c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k];
     if (diag) {
       for (int i = 0; i < c.dim; i++) { int64_t d = nxt[row + i]++; Ki[d] = row + i; blk[i] = (int)d; }
     } else {
@@ -545,7 +545,7 @@ void IPM::equilibrate() {
   bool changed = false;
   std::fill(ew.begin(), ew.end(), 1.0);
   for (size_t k = 0; k < cones.cones.size(); k++)
-    if (cones.cones[k].type == CT_SOC) {  // scalar scaling inside a SOC (socone.rs:97-101)
+    if (cones.cones[k].type == CT_SOC || cones.cones[k].type == CT_PSD) {  // scalar scaling inside SOC / PSD cones (socone.rs:97-101, psdtrianglecone.rs:98-101)
       const int o = cones.off[k], dm = cones.cones[k].dim;
       double mean = 0.0;
       for (int i = 0; i < dm; i++) mean += e[o + i];
@@ -902,7 +902,7 @@ int IPM::solve() {
     SCK(cudaMemsetAsync(cones.dev.fail, 0, sizeof(int), st));
     cones.update_scaling(s, z);
     int failflag = 0;
-    if (cones.dev.nsoc) {  // only SOC scalings can fail
+    if (cones.dev.nsoc || cones.dev.npsd) {  // only SOC / PSD scalings can fail
       SCK(cudaMemcpyAsync(&failflag, cones.dev.fail, sizeof(int), cudaMemcpyDeviceToHost, st));
       SCK(cudaStreamSynchronize(st));
     }

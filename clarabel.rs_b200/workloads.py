@@ -196,3 +196,44 @@ def block_angular_qp(n=1_000_000, nblocks=64, rows_per_var=1.5, nlink=2000, link
     cones = [("zero", nz), ("nonneg", m - nz)]
     return dict(P=sp.triu(P, format="csc"), q=q, A=A, b=b, cones=cones,
                 name=f"block_angular_qp(n={n},blocks={nblocks},m={m},link={nlink},seed={seed})")
+
+
+def block_sdp(n=20_000, n_psd=500, psd_dim=20, nnz_per_row=10, window=400, n_nonneg=2000, seed=4):
+    """Config C5: block-diagonal SDP.  n_psd PSD(psd_dim) cones; every PSD row touches ~nnz_per_row variables of
+    a window of `window` variables belonging to that cone; one trace-normalisation equality per cone; a few bound rows.
+    min 0.005 x'x + q'x  s.t.  svec(F_k0) - A_k x in PSD,  a_k'x = b_k,  G x <= h."""
+    rng = np.random.default_rng(seed)
+    numel = psd_dim * (psd_dim + 1) // 2
+    rows, cols, vals, b = [], [], [], []
+    r = 0
+    # zero cone rows
+    for k in range(n_psd):
+        lo = (k * max(n - window, 1)) // max(n_psd - 1, 1) if n_psd > 1 else 0
+        cc = lo + rng.choice(min(window, n), size=min(nnz_per_row, n), replace=False)
+        rows += [r] * cc.size; cols += cc.tolist(); vals += rng.standard_normal(cc.size).tolist()
+        b.append(rng.standard_normal() * 0.1)
+        r += 1
+    nz = r
+    # nonneg rows:  g'x + s = h, strictly feasible at x = 0
+    for k in range(n_nonneg):
+        cc = rng.choice(n, size=3, replace=False)
+        rows += [r] * 3; cols += cc.tolist(); vals += rng.standard_normal(3).tolist()
+        b.append(rng.uniform(0.5, 1.5))
+        r += 1
+    # PSD rows:  s = svec(F0) - A x  with F0 = identity-ish (strictly feasible at x = 0)
+    diag_idx = [k * (k + 3) // 2 for k in range(psd_dim)]
+    for k in range(n_psd):
+        lo = (k * max(n - window, 1)) // max(n_psd - 1, 1) if n_psd > 1 else 0
+        for t in range(numel):
+            cc = lo + rng.choice(min(window, n), size=min(nnz_per_row, n), replace=False)
+            rows += [r + t] * cc.size; cols += cc.tolist(); vals += (0.3 * rng.standard_normal(cc.size)).tolist()
+        bb = np.zeros(numel); bb[diag_idx] = 1.0
+        b += bb.tolist()
+        r += numel
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(r, n)).tocsc()
+    A.sum_duplicates(); A.sort_indices()
+    P = sp.identity(n, format="csc") * 0.01
+    q = rng.standard_normal(n) * 0.1
+    cones = [("zero", nz), ("nonneg", n_nonneg)] + [("psd", psd_dim)] * n_psd
+    return dict(P=P, q=q, A=A, b=np.array(b), cones=cones,
+                name=f"block_sdp(n={n},psd={n_psd}x{psd_dim},seed={seed})")
