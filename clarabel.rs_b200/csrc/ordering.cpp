@@ -19,8 +19,14 @@
 #include <cstdint>
 #include <numeric>
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cb {
+static double onow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define OMARK(label) do { if (std::getenv("CB_TIMING")) { double t_ = onow(); std::fprintf(stderr, "[cb timing]   nd: %-22s %.3f s\n", label, t_ - ot_last); ot_last = t_; } } while (0)
+
 
 namespace {
 
@@ -66,7 +72,7 @@ enum : uint8_t { ST_VAR = 0, ST_ELEM = 1, ST_DEAD_ELEM = 2, ST_ABSORBED = 3, ST_
 // adjacency (xadj/adj).  `order` receives the elimination sequence (perm:
 // order[k] = vertex eliminated k-th).
 void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adjncy,
-               double dense_scale, std::vector<int>& order) {
+               double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first) {
   order.clear();
   order.reserve(n);
   if (n == 0) return;
@@ -86,7 +92,7 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
   std::vector<int> dense_nodes;
   for (int i = 0; i < n; i++) {
     int d = (int)(xadj[i + 1] - xadj[i]);
-    if ((double)d > dense) { status[i] = ST_DENSE; dense_nodes.push_back(i); }
+    if ((double)d > dense && !(forced_first && (*forced_first)[i])) { status[i] = ST_DENSE; dense_nodes.push_back(i); }
   }
   for (int i = 0; i < n; i++) {
     if (status[i] == ST_DENSE) continue;
@@ -94,7 +100,7 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
     a.reserve(xadj[i + 1] - xadj[i]);
     for (int64_t p = xadj[i]; p < xadj[i + 1]; p++)
       if (status[adjncy[p]] != ST_DENSE) a.push_back(adjncy[p]);
-    degree[i] = (int)a.size();
+    degree[i] = (forced_first && (*forced_first)[i]) ? 0 : (int)a.size();   // forced vertices are eliminated first
   }
 
   // degree buckets
@@ -311,9 +317,11 @@ int bfs(NDWork& W, int root, int region, const std::vector<int>& verts) {
 
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
               int leaf_size, std::vector<int>& perm) {
+  double ot_last = onow();
   std::vector<int64_t> xadj;
   std::vector<int> adj;
   full_adjacency(n, Ap, Ai, xadj, adj);
+  OMARK("adjacency");
   perm.clear();
   perm.reserve(n);
   if (n == 0) return;
@@ -334,7 +342,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
   // output is assembled as: [left..., right..., separator] per region, with
   // separators emitted after both halves (post-order), so we build a tree of
   // "emit" actions and flatten it at the end.
-  struct Node { std::vector<int> verts; int left = -1, right = -1; std::vector<int> sep; bool leaf = false; };
+  struct Node { std::vector<int> verts; std::vector<int> kids; std::vector<int> sep; bool leaf = false; };
   std::vector<Node> nodes;
   int next_region = 1;
   const int stamp = 0;
@@ -370,7 +378,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     // pseudo-peripheral root: a few BFS sweeps
     int root = nodes[id].verts[0];
     int ecc = -1;
-    for (int it = 0; it < 4; it++) {
+    for (int it = 0; it < 1; it++) {   // one sweep to find a far vertex, then the structure is rooted there
       int e = bfs(W, root, region, nodes[id].verts);
       if ((int)W.queue.size() != (int)nodes[id].verts.size()) break;  // disconnected: handled below
       if (e <= ecc) break;
@@ -392,9 +400,44 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     Node L, R;
     std::vector<int> sep;
     if (reached < total) {
-      // region fell apart (a separator disconnected it): split by component
-      for (int v : W.queue) { L.verts.push_back(v); W.part[v] = -2; }
-      for (int v : nodes[id].verts) if (W.part[v] == region) R.verts.push_back(v);
+      // region fell apart (a separator disconnected it): label ALL components in one pass.  Big components
+      // become child regions of their own; the small ones are independent of each other, so they are packed
+      // together into leaves (AMD handles a union of disconnected pieces at no extra cost).
+      std::vector<int> verts;
+      verts.swap(nodes[id].verts);
+      for (int v : verts) W.level[v] = -1;
+      std::vector<int> small_pack;
+      std::vector<int> kids;
+      auto flush_pack = [&]() {
+        if (small_pack.empty()) return;
+        Node nd; nd.leaf = true; nd.verts.swap(small_pack);
+        for (int v : nd.verts) W.part[v] = 0;
+        kids.push_back((int)nodes.size()); nodes.push_back(std::move(nd));
+      };
+      std::vector<int> comp;
+      for (int sv : verts) {
+        if (W.level[sv] >= 0) continue;
+        comp.clear(); comp.push_back(sv); W.level[sv] = 0;
+        for (size_t h = 0; h < comp.size(); h++) {
+          const int v = comp[h];
+          for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+            const int u = adj[p];
+            if (W.part[u] == region && W.level[u] < 0) { W.level[u] = 0; comp.push_back(u); }
+          }
+        }
+        if ((int)comp.size() > leaf_size) {
+          Node nd; nd.verts = comp;
+          for (int v : nd.verts) W.part[v] = 0;
+          const int ci = (int)nodes.size(); nodes.push_back(std::move(nd));
+          kids.push_back(ci); work.push_back(ci);
+        } else {
+          small_pack.insert(small_pack.end(), comp.begin(), comp.end());
+          if ((int)small_pack.size() >= 4 * leaf_size) flush_pack();
+        }
+      }
+      flush_pack();
+      nodes[id].kids = kids;
+      continue;
     } else if (e < 2) {
       nodes[id].leaf = true;  // clique-like, cannot bisect
       continue;
@@ -435,7 +478,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     std::vector<int>().swap(nodes[id].verts);
     int li = (int)nodes.size(); nodes.push_back(std::move(L));
     int ri = (int)nodes.size(); nodes.push_back(std::move(R));
-    nodes[id].left = li; nodes[id].right = ri;
+    nodes[id].kids = {li, ri};
     // children regions need fresh part ids; mark their vertices as "unassigned" (0)
     for (int v : nodes[li].verts) W.part[v] = 0;
     for (int v : nodes[ri].verts) W.part[v] = 0;
@@ -443,6 +486,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     work.push_back(ri);
   }
 
+  OMARK("bisection");
   // order leaves with AMD on the induced subgraph; emit post-order
   std::vector<int64_t> sx;
   std::vector<int> sa, lorder;
@@ -472,11 +516,10 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     while (!st.empty()) {
       Fr f = st.back(); st.pop_back();
       Node& nd = nodes[f.id];
-      if (nd.leaf || nd.left < 0) { emit_leaf(nd.verts); continue; }
+      if (nd.leaf || nd.kids.empty()) { emit_leaf(nd.verts); continue; }
       if (f.stage == 0) {
         st.push_back({f.id, 1});
-        st.push_back({nd.right, 0});
-        st.push_back({nd.left, 0});
+        for (size_t k = nd.kids.size(); k-- > 0;) st.push_back({nd.kids[k], 0});
       } else {
         emit_leaf(nd.sep);
       }
@@ -487,6 +530,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     return da != db ? da < db : a < b;
   });
   for (int v : dense_nodes) perm.push_back(v);
+  OMARK("leaf AMD + emit");
 }
 
 }  // namespace cb

@@ -300,6 +300,29 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
   o.regularize_eps = s.dynamic_regularization_eps;
   o.regularize_delta = s.dynamic_regularization_delta;
   o.regularize_enable = 1;  // the reference adapter ignores dynamic_regularization_enable (ldlsolvers/qdldl.rs:38)
+  // Dense cone blocks (PSD, dense SOC): contract every block to one vertex for the ordering
+  // (order_with_groups in symbolic.cpp), unless the caller fixed the permutation.
+  std::vector<int> perm_grp;
+  if (!perm) {
+    std::vector<int> group(N, -1);
+    int ngroups = 0;
+    for (size_t k = 0; k < cones->cones.size(); k++) {
+      const ConeSpec& c = cones->cones[k];
+      if (c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k] || c.dim <= 8) continue;
+      for (int i = 0; i < c.dim; i++) group[n + cones->off[k] + i] = ngroups;
+      ngroups++;
+    }
+    if (ngroups > 0) {
+      SymbolicOptions so;
+      so.ordering = o.ordering ? o.ordering : ORDER_BEST;
+      if (o.nd_leaf > 0) so.nd_leaf = o.nd_leaf;
+      if (o.max_panel > 0) so.max_panel = o.max_panel > CB_PB_MAXNS ? CB_PB_MAXNS : o.max_panel;
+      int kind = 0;
+      rc = order_with_groups(N, Kp.data(), Ki32.data(), group.data(), ngroups, so, perm_grp, &kind);
+      if (rc) return CLDL_E_ARG;
+      perm = perm_grp.data();
+    }
+  }
   rc = ldl.init(N, Kp.data(), Ki32.data(), Kx.data(), dsigns.data(), o, perm);
   if (rc) return rc;
   st = ldl.stream;

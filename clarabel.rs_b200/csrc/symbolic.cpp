@@ -6,8 +6,13 @@
 #include <cstdlib>
 #include <map>
 #include <numeric>
+#include <chrono>
 
 namespace cb {
+
+static double tnow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool timing_on() { static int v = -1; if (v < 0) v = std::getenv("CB_TIMING") ? 1 : 0; return v == 1; }
+#define TMARK(label) do { if (timing_on()) { double t_ = tnow(); std::fprintf(stderr, "[cb timing] %-28s %.3f s\n", label, t_ - t_last); t_last = t_; } } while (0)
 
 namespace {
 
@@ -125,6 +130,7 @@ struct Eval { double flops; int64_t nnzL; };
 
 static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<int>& perm0,
                  const SymbolicOptions& opt, Symbolic& S, bool stats_only) {
+  double t_last = tnow();
   S.n = n;
   S.nnzA = Ap[n];
   std::vector<int> iperm0(n);
@@ -165,6 +171,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
     S.flops_simplicial += (double)S.colcount[j] * ((double)S.colcount[j] + 3.0);
   }
 
+  TMARK("sym: etree+postorder+colcount");
   // ---- supernode partition: fundamental -> relaxed -> split ----
   const std::vector<int>& cc = S.colcount;
   std::vector<int> sfirst;  // start column of every supernode
@@ -243,6 +250,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   for (int s = 0; s < nsup; s++)
     for (int j = S.sn_first[s]; j < S.sn_first[s + 1]; j++) S.col2sn[j] = s;
 
+  TMARK("sym: supernode partition");
   // ---- row structures by bottom-up union, parents by min row ----
   S.sn_rowptr.assign(nsup + 1, 0);
   S.sn_rows.clear();
@@ -274,6 +282,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
     }
   }
 
+  TMARK("sym: row structures");
   // ---- sizes, flops, levels ----
   S.panel_off.assign(nsup + 1, 0);
   S.flops_stored = 0;
@@ -333,6 +342,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
     }
   }
 
+  TMARK("sym: levels+children+rel");
   // ---- assembly map of original entries ----
   S.asm_ptr.assign(nsup + 1, 0);
   int64_t nnz = Ap[n];
@@ -369,6 +379,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
     }
   }
 
+  TMARK("sym: assembly map");
   // ---- update-matrix arena: lifetime-based allocation over the level schedule ----
   // U_s is written at level(s) and last read at level(parent(s)).
   S.upd_off.assign(nsup, 0);
@@ -404,6 +415,88 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
     }
     S.upd_total = top;
   }
+  TMARK("sym: arena");
+  return 0;
+}
+
+// Ordering for KKT matrices with dense diagonal blocks (PSD / dense SOC cones).  Minimum degree is myopic
+// there: a dense block inflates the degree of its rows, so the coupling variables are eliminated first and
+// the blocks smear into each other (measured on config C5: nnzL 4.9e9 instead of ~1e8).  Here every dense
+// block is contracted to ONE vertex of the ordering graph; for AMD these vertices are forced to be
+// eliminated first (each turns into an element = the clique it induces on the coupling variables, which is
+// exactly what eliminating the block does), for ND they are ordinary vertices.  The contracted order is
+// expanded back (a block vertex becomes its rows, in natural order) and both candidates are judged on the
+// TRUE pattern with the device-time model.
+int order_with_groups(int n, const int64_t* Ap, const int32_t* Ai, const int* group, int ngroups,
+                      const SymbolicOptions& opt, std::vector<int>& perm_out, int* kind_out) {
+  // contracted vertex ids: singletons first (in index order), then one per group
+  std::vector<int> cid(n, -1);
+  int nc = 0;
+  for (int v = 0; v < n; v++) if (group[v] < 0) cid[v] = nc++;
+  const int ns = nc;
+  for (int v = 0; v < n; v++) if (group[v] >= 0) cid[v] = ns + group[v];
+  nc = ns + ngroups;
+  // contracted upper-triangular CSC (duplicates removed)
+  std::vector<std::vector<int>> cols(nc);
+  for (int j = 0; j < n; j++)
+    for (int64_t p = Ap[j]; p < Ap[j + 1]; p++) {
+      int a = cid[Ai[p]], b = cid[j];
+      if (a == b) continue;
+      if (a > b) std::swap(a, b);
+      cols[b].push_back(a);
+    }
+  std::vector<int64_t> Cp(nc + 1, 0);
+  std::vector<int32_t> Ci;
+  for (int j = 0; j < nc; j++) {
+    auto& c = cols[j];
+    std::sort(c.begin(), c.end());
+    c.erase(std::unique(c.begin(), c.end()), c.end());
+    for (int a : c) Ci.push_back(a);
+    Ci.push_back(j);   // structural diagonal (the orderings ignore it)
+    Cp[j + 1] = (int64_t)Ci.size();
+    std::vector<int>().swap(c);
+  }
+  // full adjacency for AMD with forced-first group vertices
+  std::vector<int64_t> xadj(nc + 1, 0);
+  for (int j = 0; j < nc; j++)
+    for (int64_t p = Cp[j]; p < Cp[j + 1]; p++) if (Ci[p] != j) { xadj[Ci[p] + 1]++; xadj[j + 1]++; }
+  for (int j = 0; j < nc; j++) xadj[j + 1] += xadj[j];
+  std::vector<int> adj(xadj[nc]);
+  {
+    std::vector<int64_t> pos(xadj.begin(), xadj.end() - 1);
+    for (int j = 0; j < nc; j++)
+      for (int64_t p = Cp[j]; p < Cp[j + 1]; p++) if (Ci[p] != j) { adj[pos[Ci[p]]++] = j; adj[pos[j]++] = Ci[p]; }
+  }
+  std::vector<char> forced(nc, 0);
+  for (int g = 0; g < ngroups; g++) forced[ns + g] = 1;
+  std::vector<int> oa, on;
+  amd_graph(nc, xadj, adj, opt.amd_dense_scale, oa, &forced);
+  nd_order(nc, Cp.data(), Ci.data(), opt.amd_dense_scale, opt.nd_leaf, on);
+  if ((int)oa.size() != nc || (int)on.size() != nc) return -6;
+  // expand
+  std::vector<std::vector<int>> members(ngroups);
+  std::vector<int> single(ns);
+  for (int v = 0; v < n; v++) { if (group[v] >= 0) members[group[v]].push_back(v); else single[cid[v]] = v; }
+  auto expand = [&](const std::vector<int>& o, std::vector<int>& out) {
+    out.clear(); out.reserve(n);
+    for (int c : o) { if (c < ns) out.push_back(single[c]); else for (int v : members[c - ns]) out.push_back(v); }
+  };
+  std::vector<int> pa, pn;
+  expand(oa, pa); expand(on, pn);
+  if ((int)pa.size() != n || (int)pn.size() != n) return -6;
+  Symbolic Sa, Sn;
+  int ra = build(n, Ap, Ai, pa, opt, Sa, true);
+  int rn = build(n, Ap, Ai, pn, opt, Sn, true);
+  if (ra) return ra;
+  if (rn) return rn;
+  auto model = [](const Symbolic& s) {
+    return s.flops_stored / 1.0e13 + (double)s.nnzL_stored * 8.0 / 2.0e12 + 10e-6 * s.nlevels;
+  };
+  if (timing_on()) std::fprintf(stderr, "[cb timing] grouped ordering: AMD nnzL %.3e flops %.3e levels %d | ND nnzL %.3e flops %.3e levels %d\n",
+                                (double)Sa.nnzL_stored, Sa.flops_stored, Sa.nlevels, (double)Sn.nnzL_stored, Sn.flops_stored, Sn.nlevels);
+  const bool use_nd = (opt.ordering == ORDER_ND) || (opt.ordering != ORDER_AMD && model(Sn) < model(Sa));
+  perm_out = use_nd ? pn : pa;
+  if (kind_out) *kind_out = use_nd ? ORDER_ND : ORDER_AMD;
   return 0;
 }
 
@@ -430,7 +523,9 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
   } else if (kind == ORDER_AMD) {
     amd_order(n, Ap, Ai, opt.amd_dense_scale, perm0);
   } else if (kind == ORDER_ND) {
+    double t_last = tnow();
     nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, perm0);
+    TMARK("ordering: ND");
   } else {
     // ORDER_BEST: evaluate both, pick by a simple device-time model
     std::vector<int> pa, pn;

@@ -14,7 +14,7 @@ namespace cb {
 
 // ---- orderings (ordering.cpp) ----
 void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adj,
-               double dense_scale, std::vector<int>& order);
+               double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first = nullptr);
 void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
                std::vector<int>& perm);
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
@@ -76,6 +76,10 @@ struct Symbolic {
   double flops_stored = 0;      // dense flops actually executed
   int ordering_used = 0;
 };
+
+// see symbolic.cpp: ordering for matrices with dense diagonal blocks (group[v] = block id or -1)
+int order_with_groups(int n, const int64_t* Ap, const int32_t* Ai, const int* group, int ngroups,
+                      const SymbolicOptions& opt, std::vector<int>& perm_out, int* kind_out);
 
 // Ap/Ai: triu CSC pattern of the KKT matrix (caller's order), n x n.
 // perm_in: optional user permutation (length n) or nullptr.

@@ -94,6 +94,23 @@ int64_t csym_array(const csym_handle* h, int which, int64_t* out, int64_t cap) {
   return -2;
 }
 
+// ordering for matrices with dense diagonal blocks (group[v] = block id or -1); returns the kind chosen
+int csym_order_groups(uint64_t n, const uint64_t* colptr, const uint64_t* rowval, const int32_t* group,
+                      int32_t ngroups, int ordering, uint64_t* perm_out) {
+  std::vector<int64_t> Ap(n + 1);
+  std::vector<int32_t> Ai(colptr[n]);
+  for (uint64_t j = 0; j <= n; j++) Ap[j] = (int64_t)colptr[j];
+  for (uint64_t p = 0; p < colptr[n]; p++) Ai[p] = (int32_t)rowval[p];
+  cb::SymbolicOptions so;
+  so.ordering = ordering ? ordering : cb::ORDER_BEST;
+  std::vector<int> perm;
+  int kind = 0;
+  int rc = cb::order_with_groups((int)n, Ap.data(), Ai.data(), group, ngroups, so, perm, &kind);
+  if (rc) return rc;
+  for (uint64_t k = 0; k < n; k++) perm_out[k] = (uint64_t)perm[k];
+  return kind;
+}
+
 // stand-alone orderings (perm_out length n)
 int csym_order(uint64_t n, const uint64_t* colptr, const uint64_t* rowval, int kind,
                double dense_scale, int nd_leaf, uint64_t* perm_out) {

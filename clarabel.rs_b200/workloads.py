@@ -216,7 +216,8 @@ def block_sdp(n=20_000, n_psd=500, psd_dim=20, nnz_per_row=10, window=400, n_non
     nz = r
     # nonneg rows:  g'x + s = h, strictly feasible at x = 0
     for k in range(n_nonneg):
-        cc = rng.choice(n, size=3, replace=False)
+        lo = int(rng.integers(0, max(n - window, 1)))
+        cc = lo + rng.choice(min(window, n), size=3, replace=False)   # local bound rows
         rows += [r] * 3; cols += cc.tolist(); vals += rng.standard_normal(3).tolist()
         b.append(rng.uniform(0.5, 1.5))
         r += 1

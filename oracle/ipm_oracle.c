@@ -843,6 +843,7 @@ static int kkt_regularize_and_refactor(oipm_t *S)
     int rc = oq_refactor(S->ldl);
     S->info.n_refactor++;
     int ok = (rc == 0) && oq_dinv_is_finite(S->ldl);
+    if (!ok && getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] refactor failed rc=%d finite=%d regcount=%lld\n", rc, oq_dinv_is_finite(S->ldl), (long long)oq_regularize_count(S->ldl));
     if (S->set.static_regularization_enable)
         for (idx i = 0; i < N; i++) S->K.nzval[S->map_diag_full[i]] = diag_kkt[i];
     return ok;
@@ -885,7 +886,7 @@ static int kkt_iterative_refinement(oipm_t *S)
     double *x = S->kx, *b = S->kb, *e = S->kw1, *dx = S->kw2; idx N = S->N;
     double normb = vnorm_inf(b, N);
     double norme = refine_error(S, e, b, x);
-    if (!isfinite(norme)) return 0;
+    if (!isfinite(norme)) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] IR: initial residual not finite (normb %g)\n", normb); return 0; }
     for (int it = 0; it < S->set.iterative_refinement_max_iter; it++) {
         if (norme <= S->set.iterative_refinement_abstol + S->set.iterative_refinement_reltol * normb) break;
         double last = norme;
@@ -1329,13 +1330,14 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
             tr[0] = mu; tr[1] = alpha; tr[2] = sigma; tr[3] = I->res_primal; tr[4] = I->res_dual; tr[5] = I->gap_abs;
         }
         if (check_termination(S, iter)) {
+            if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] terminated status %d at iter %d (gap_abs %g gap_rel %g pres %g dres %g kt %g)\n", I->status, iter, I->gap_abs, I->gap_rel, I->res_primal, I->res_dual, I->ktratio);
             if (I->status == ST_INSUFFICIENT_PROGRESS) reset_to_prev(S);
             break;
         }
         double ts = now_s();
         int okscale = cones_update_scaling(S, S->vs, S->vz);
         I->t_scale_cones += now_s() - ts;
-        if (!okscale) { I->status = ST_NUMERICAL_ERROR; break; }
+        if (!okscale) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] scaling failed at iter %d\n", iter); I->status = ST_NUMERICAL_ERROR; break; }
         iter += 1;
         int ok = kktsystem_update(S);
         /* affine rhs */
@@ -1358,9 +1360,9 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
             for (idx i = 0; i < m; i++) S->rz_[i] = (1.0 - sigma) * S->rz[i] + 0.0 * S->rz_[i];
             ok = kktsystem_solve(S, 1);
         }
-        if (!ok) { I->status = ST_NUMERICAL_ERROR; alpha = 0.0; break; }
+        if (!ok) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] kkt failure at iter %d\n", iter); I->status = ST_NUMERICAL_ERROR; alpha = 0.0; break; }
         alpha = calc_step_length(S, 1);
-        if (alpha <= fmax(0.0, S->set.min_terminate_step_length)) { I->status = ST_INSUFFICIENT_PROGRESS; alpha = 0.0; break; }
+        if (alpha <= fmax(0.0, S->set.min_terminate_step_length)) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] small step %g at iter %d\n", alpha, iter); I->status = ST_INSUFFICIENT_PROGRESS; alpha = 0.0; break; }
         save_prev(S);
         for (idx i = 0; i < n; i++) S->vx[i] = alpha * S->lx[i] + 1.0 * S->vx[i];
         for (idx i = 0; i < m; i++) S->vs[i] = alpha * S->ls[i] + 1.0 * S->vs[i];
