@@ -473,6 +473,12 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
         }
       }
     }
+    // a level-structure cut is only worth keeping when it is thin and roughly balanced; small-world graphs
+    // (hub rows) give neither, and the region is then left to AMD as a whole
+    {
+      const size_t smaller = std::min(L.verts.size(), R.verts.size());
+      if (sep.size() * 5 > total || smaller * 20 < total) { nodes[id].leaf = true; continue; }
+    }
     for (int v : sep) W.part[v] = -1;
     nodes[id].sep = std::move(sep);
     std::vector<int>().swap(nodes[id].verts);

@@ -128,8 +128,10 @@ struct Eval { double flops; int64_t nnzL; };
 
 }  // namespace
 
+// flop_cap > 0: give up (return 1) right after the column counts when the simplicial flop count exceeds it --
+// used when comparing candidate orderings so that a hopeless candidate costs O(nnz), not O(nnz(L)).
 static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<int>& perm0,
-                 const SymbolicOptions& opt, Symbolic& S, bool stats_only) {
+                 const SymbolicOptions& opt, Symbolic& S, bool stats_only, double flop_cap = 0.0) {
   double t_last = tnow();
   S.n = n;
   S.nnzA = Ap[n];
@@ -172,6 +174,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   }
 
   TMARK("sym: etree+postorder+colcount");
+  if (flop_cap > 0.0 && S.flops_simplicial > flop_cap) return 1;
   // ---- supernode partition: fundamental -> relaxed -> split ----
   const std::vector<int>& cc = S.colcount;
   std::vector<int> sfirst;  // start column of every supernode
@@ -486,9 +489,10 @@ int order_with_groups(int n, const int64_t* Ap, const int32_t* Ai, const int* gr
   if ((int)pa.size() != n || (int)pn.size() != n) return -6;
   Symbolic Sa, Sn;
   int ra = build(n, Ap, Ai, pa, opt, Sa, true);
-  int rn = build(n, Ap, Ai, pn, opt, Sn, true);
   if (ra) return ra;
-  if (rn) return rn;
+  int rn = build(n, Ap, Ai, pn, opt, Sn, true, 30.0 * Sa.flops_simplicial + 1e9);
+  if (rn < 0) return rn;
+  if (rn == 1) { Sn.flops_stored = 1e300; Sn.nnzL_stored = 0; Sn.nlevels = 0; }
   auto model = [](const Symbolic& s) {
     return s.flops_stored / 1.0e13 + (double)s.nnzL_stored * 8.0 / 2.0e12 + 10e-6 * s.nlevels;
   };
@@ -533,9 +537,10 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
     nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, pn);
     Symbolic Sa, Sn;
     int ra = build(n, Ap, Ai, pa, opt, Sa, true);
-    int rn = build(n, Ap, Ai, pn, opt, Sn, true);
     if (ra) return ra;
-    if (rn) return rn;
+    int rn = build(n, Ap, Ai, pn, opt, Sn, true, 30.0 * Sa.flops_simplicial + 1e9);
+    if (rn < 0) return rn;
+    if (rn == 1) { Sn.flops_stored = 1e300; Sn.nnzL_stored = 0; Sn.nlevels = 0; }   // hopeless: rejected early
     // model: dense flops at ~10 TF/s effective + memory at ~2 TB/s + 10 us per level
     auto model = [](const Symbolic& s) {
       return s.flops_stored / 1.0e13 + (double)s.nnzL_stored * 8.0 / 2.0e12 + 10e-6 * s.nlevels;

@@ -81,7 +81,7 @@ def test_c3_full_size_with_oracle_parity():
 
 def test_c4_full_size():
     pr = workloads.block_angular_qp()
-    dev = cb.CudaSolver(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"], ordering=cb.ORDER_ND)
+    dev = cb.CudaSolver(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"])
     r = dev.solve()
     assert r["status"] == "Solved"
     check_optimality(pr, r)
