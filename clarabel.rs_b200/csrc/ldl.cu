@@ -505,11 +505,15 @@ __global__ void __launch_bounds__(SV_NT) k_fwd_small(LDLDev d, const int* __rest
 }
 
 // forward, big fronts: one CTA per front
-__global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int* __restrict__ tasks, double* __restrict__ xp) {
+// `chains[blockIdx.x]` = (first front, number of fronts): consecutive panels of one supernode whose row
+// sets nest exactly are swept by ONE CTA back to back, so a chain costs one launch instead of one per panel.
+__global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int2* __restrict__ chains, double* __restrict__ xp) {
   __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
   __shared__ double sy[CB_PB_MAXNS];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int s = tasks[blockIdx.x];
+  const int2 ch = chains[blockIdx.x];
+  for (int ci = 0; ci < ch.y; ci++) {
+  const int s = ch.x + ci;
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -561,6 +565,8 @@ __global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int* __restri
     for (; j0 < ns; j0++) acc += pa[(long long)j0 * ld] * sy[j0];
     us[a] -= acc;
   }
+  __syncthreads();   // u and xp of this front are visible to the next panel of the chain
+  }
 }
 
 // backward, small fronts: one warp per front
@@ -595,13 +601,15 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_small(LDLDev d, const int* __rest
 }
 
 // backward, big fronts: one CTA per front
-__global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int* __restrict__ tasks, double* __restrict__ xp,
+__global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restrict__ chains, double* __restrict__ xp,
                                                    double* __restrict__ out) {
   __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
   __shared__ double st[CB_PB_MAXNS];
   __shared__ double sx[CB_SOLVE_STAGE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SV_NT >> 5;
-  const int s = tasks[blockIdx.x];
+  const int2 ch = chains[blockIdx.x];
+  for (int ci = ch.y - 1; ci >= 0; ci--) {
+  const int s = ch.x + ci;
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -649,6 +657,8 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int* __restri
     }
     if (lane < ns) { xp[f + lane] = y0; out[d.perm[f + lane]] = y0; }
     if (lane + 32 < ns) { xp[f + lane + 32] = y1; out[d.perm[f + lane + 32]] = y1; }
+  }
+  __syncthreads();
   }
 }
 
@@ -928,28 +938,74 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     signed char* t8 = nullptr;
     if ((rc = upload(&t8, small))) return rc; dev.child_small = t8;
   }
-  // solve plan: per level, narrow-pivot fronts first (one warp each) then the wide ones (one CTA each)
+  // solve plan.  Chains: consecutive panels s, s+1 with parent(s) == s+1 and rows(s) == cols(s+1) + rows(s+1)
+  // are swept by one CTA, so the schedule is levelled over chains, not over panels.  Single narrow fronts
+  // (ns <= CB_SOLVE_SMALL_NS) keep the warp-per-front kernels.
   {
-    std::vector<int> st(S.level_tasks.size());
-    splan.assign(S.nlevels, SolveSeg());
-    solve_launches = 0;
-    for (int l = 0; l < S.nlevels; l++) {
-      int b = S.level_ptr[l], e = S.level_ptr[l + 1], pos = b;
-      for (int pass = 0; pass < 2; pass++)
-        for (int t = b; t < e; t++) {
-          const int s = S.level_tasks[t];
-          const int ns = S.sn_first[s + 1] - S.sn_first[s];
-          const bool small = ns <= CB_SOLVE_SMALL_NS;
-          if ((pass == 0) == small) st[pos++] = s;
-          if (pass == 0 && small) splan[l].nsmall++;
+    const int ns_ = S.nsup;
+    std::vector<int> chain_of(ns_, -1), chain_first, chain_cnt;
+    for (int s = 0; s < ns_; s++) {
+      if (chain_of[s] >= 0) continue;
+      const int id = (int)chain_first.size();
+      chain_first.push_back(s);
+      int t = s, cnt = 1;
+      chain_of[s] = id;
+      while (t + 1 < ns_ && S.sn_parent[t] == t + 1 &&
+             (S.sn_rowptr[t + 1] - S.sn_rowptr[t]) ==
+                 (int64_t)(S.sn_first[t + 2] - S.sn_first[t + 1]) + (S.sn_rowptr[t + 2] - S.sn_rowptr[t + 1]) &&
+             (S.sn_first[t + 1] - S.sn_first[t]) > CB_SOLVE_SMALL_NS && cnt < 64) {
+        t++; cnt++;
+        chain_of[t] = id;
+      }
+      chain_cnt.push_back(cnt);
+    }
+    const int nchain = (int)chain_first.size();
+    std::vector<int> clevel(nchain, 0);
+    int nlev = 0;
+    for (int s = 0; s < ns_; s++) {       // tasks are numbered children-before-parents
+      const int p = S.sn_parent[s];
+      if (p >= 0 && chain_of[p] != chain_of[s] && clevel[chain_of[p]] < clevel[chain_of[s]] + 1)
+        clevel[chain_of[p]] = clevel[chain_of[s]] + 1;
+    }
+    // a later member of a chain may have raised the chain's level after an earlier external child was seen;
+    // iterate to a fixed point (levels only grow, tree depth bounds the number of sweeps)
+    for (bool changed = true; changed;) {
+      changed = false;
+      for (int s = 0; s < ns_; s++) {
+        const int p = S.sn_parent[s];
+        if (p >= 0 && chain_of[p] != chain_of[s] && clevel[chain_of[p]] < clevel[chain_of[s]] + 1) {
+          clevel[chain_of[p]] = clevel[chain_of[s]] + 1; changed = true;
         }
-      splan[l].base = b;
-      splan[l].nbig = (e - b) - splan[l].nsmall;
+      }
+    }
+    for (int c = 0; c < nchain; c++) nlev = std::max(nlev, clevel[c] + 1);
+    splan.assign(nlev, SolveSeg());
+    std::vector<std::vector<int>> small(nlev), big(nlev);
+    for (int c = 0; c < nchain; c++) {
+      const int s = chain_first[c];
+      const bool is_small = chain_cnt[c] == 1 && (S.sn_first[s + 1] - S.sn_first[s]) <= CB_SOLVE_SMALL_NS;
+      (is_small ? small : big)[clevel[c]].push_back(c);
+    }
+    std::vector<int> st;
+    std::vector<int2> chains;
+    solve_launches = 0;
+    for (int l = 0; l < nlev; l++) {
+      splan[l].base = (int)st.size();
+      splan[l].cbase = (int)chains.size();
+      splan[l].nsmall = (int)small[l].size();
+      splan[l].nbig = (int)big[l].size();
+      for (int c : small[l]) st.push_back(chain_first[c]);
+      for (int c : big[l]) chains.push_back(make_int2(chain_first[c], chain_cnt[c]));
       solve_launches += 2 * ((splan[l].nsmall ? 1 : 0) + (splan[l].nbig ? 1 : 0));
     }
+    solve_levels = nlev;
     int* t1 = nullptr;
     if ((rc = upload(&t1, st))) return rc;
     d_solve_tasks = t1;
+    int2* t2 = nullptr;
+    CK(cudaMalloc((void**)&t2, (chains.size() ? chains.size() : 1) * sizeof(int2)));
+    if (!chains.empty()) CK(cudaMemcpy(t2, chains.data(), chains.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    d_solve_chains = t2;
   }
   // level_tasks was re-ordered inside levels: re-upload
   CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
@@ -965,7 +1021,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1006,15 +1062,15 @@ int LDLObject::solve_async(double* d_x, const double* d_b) {
   CK(cudaSetDevice(device));
   g_launches += 1 + solve_launches;
   k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
-  for (int l = 0; l < S.nlevels; l++) {
+  for (int l = 0; l < solve_levels; l++) {
     const SolveSeg& g = splan[l];
     if (g.nsmall) k_fwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp);
-    if (g.nbig) k_fwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base + g.nsmall, d_xp);
+    if (g.nbig) k_fwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_chains + g.cbase, d_xp);
   }
-  for (int l = S.nlevels - 1; l >= 0; l--) {
+  for (int l = solve_levels - 1; l >= 0; l--) {
     const SolveSeg& g = splan[l];
+    if (g.nbig) k_bwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_chains + g.cbase, d_xp, d_x);
     if (g.nsmall) k_bwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp, d_x);
-    if (g.nbig) k_bwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base + g.nsmall, d_xp, d_x);
   }
   CK(cudaGetLastError());
   return CLDL_OK;

@@ -62,13 +62,15 @@ struct LaunchSeg {
 };
 
 struct SolveSeg {
-  int base = 0, nsmall = 0, nbig = 0;
+  int base = 0, cbase = 0, nsmall = 0, nbig = 0;
 };
 
 class LDLObject {
  public:
   std::vector<SolveSeg> splan;
   int* d_solve_tasks = nullptr;
+  int2* d_solve_chains = nullptr;
+  int solve_levels = 0;
   unsigned long long solve_launches = 0;
   int n = 0;
   int64_t nnzA = 0;
