@@ -21,10 +21,10 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(CSRC)/%.o: $(CSRC)/%.cpp $(HDRS)
-	$(CXX) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -pthread -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(CPP_OBJS)
-	$(NVCC) -shared $(GENCODE) -o $@ $^ -lcudart
+	$(NVCC) -shared $(GENCODE) -o $@ $^ -lcudart -lpthread
 
 $(ORACLE): $(ORACLE_SRCS)
 	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -Wall -o $@ $^ -lm

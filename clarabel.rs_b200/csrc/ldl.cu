@@ -720,7 +720,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   so.amd_dense_scale = o.amd_dense_scale > 0 ? o.amd_dense_scale : 1.5;
   if (o.max_panel > 0) so.max_panel = o.max_panel > CB_PB_MAXNS ? CB_PB_MAXNS : o.max_panel;
   if (o.nd_leaf > 0) so.nd_leaf = o.nd_leaf;
+  cb_tmark(nullptr);
   int rc = analyse(n, Ap, Ai, perm_in, so, S);
+  cb_tmark("ldl: ordering + symbolic");
   if (rc == -2) return CLDL_E_EMPTY_COLUMN;
   if (rc == -3) return CLDL_E_NOT_TRIU;
   if (rc == -5) return CLDL_E_BAD_PERM;
@@ -770,6 +772,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   dev.reg_eps = o.regularize_eps;
   dev.reg_delta = o.regularize_delta;
 
+  cb_tmark("ldl: uploads + device alloc");
   // per-child constants for the big-front kernels and the per-destination gather lists for the solves
   {
     std::vector<int> child_nb(S.nsup, 0);
@@ -821,6 +824,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     CK(cudaMemcpy(t2, child_tr.data(), (size_t)S.nsup * sizeof(int2), cudaMemcpyHostToDevice));
     dev.child_trange = t2;
   }
+  cb_tmark("ldl: child consts + gather lists");
   // per-level launch plan.  Small fronts: one fused CTA each, grouped by the shared-memory class of
   // their panel.  Big fronts (nr >= CB_BIG_NR): panel kernel + tiled update kernel.
   int max_optin = 0;
@@ -887,6 +891,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     d_tiles = t4;
     n_tiles = (int64_t)tiles.size();
   }
+  cb_tmark("ldl: launch plan + tiles");
   // small children (nr <= CB_SMALL_CHILD) of big fronts: one dst-sorted (src,dst) list per panel and per tile
   {
     std::vector<int> big_pos(S.nsup, -1), tile_base(S.nsup, -1);
@@ -938,11 +943,16 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     signed char* t8 = nullptr;
     if ((rc = upload(&t8, small))) return rc; dev.child_small = t8;
   }
+  cb_tmark("ldl: small-child entry lists");
   // solve plan.  Chains: consecutive panels s, s+1 with parent(s) == s+1 and rows(s) == cols(s+1) + rows(s+1)
   // are swept by one CTA, so the schedule is levelled over chains, not over panels.  Single narrow fronts
   // (ns <= CB_SOLVE_SMALL_NS) keep the warp-per-front kernels.
   {
     const int ns_ = S.nsup;
+    // Level-synchronous sweeps pay for the LONGEST chain of every level, so long chains lose against
+    // per-panel levels (measured on C2: 3.98 ms with unbounded chains vs 2.84 ms without).  Default: off.
+    int chain_max = 1;
+    if (const char* e = std::getenv("CB_SOLVE_CHAIN_MAX")) chain_max = std::max(1, std::atoi(e));
     std::vector<int> chain_of(ns_, -1), chain_first, chain_cnt;
     for (int s = 0; s < ns_; s++) {
       if (chain_of[s] >= 0) continue;
@@ -953,7 +963,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       while (t + 1 < ns_ && S.sn_parent[t] == t + 1 &&
              (S.sn_rowptr[t + 1] - S.sn_rowptr[t]) ==
                  (int64_t)(S.sn_first[t + 2] - S.sn_first[t + 1]) + (S.sn_rowptr[t + 2] - S.sn_rowptr[t + 1]) &&
-             (S.sn_first[t + 1] - S.sn_first[t]) > CB_SOLVE_SMALL_NS && cnt < 64) {
+             (S.sn_first[t + 1] - S.sn_first[t]) > CB_SOLVE_SMALL_NS && cnt < chain_max) {
         t++; cnt++;
         chain_of[t] = id;
       }
@@ -1010,6 +1020,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   // level_tasks was re-ordered inside levels: re-upload
   CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
                 cudaMemcpyHostToDevice));
+  cb_tmark("ldl: solve plan");
   factored = false;
   return CLDL_OK;
 }

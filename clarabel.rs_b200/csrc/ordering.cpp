@@ -19,6 +19,9 @@
 #include <cstdint>
 #include <numeric>
 #include <vector>
+#include <atomic>
+#include <future>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -275,42 +278,164 @@ void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
 
 // ---------------------------------------------------------------------------
 // Nested dissection (BFS level-structure bisection) with AMD on the leaves.
+// Recursive; the two halves of the first few bisections are ordered by separate
+// host threads (disjoint vertex sets, so the shared per-vertex scratch arrays
+// are written without conflicts).
 // ---------------------------------------------------------------------------
 namespace {
 
-struct NDWork {
+struct NDShared {
   const std::vector<int64_t>* xadj;
   const std::vector<int>* adj;
-  std::vector<int> part;   // current region id per vertex (-1 = already ordered / separator)
+  std::vector<int> part;   // region id per vertex (-1 = separator / withheld)
   std::vector<int> level;  // BFS scratch
-  std::vector<int> queue;
-  std::vector<int> local;  // global -> local index scratch
+  std::vector<int> local;  // global -> local index scratch for the leaf AMD
+  std::atomic<int> next_region{1};
+  int leaf_size = 200;
+  int par_depth = 0;
 };
 
-// BFS restricted to vertices with part[v]==region; returns eccentricity, fills
-// queue (visit order) and level[].
-int bfs(NDWork& W, int root, int region, const std::vector<int>& verts) {
-  const int stamp_base = 0;
+// BFS restricted to vertices with part[v]==region; returns eccentricity, fills queue and level[].
+int nd_bfs(NDShared& W, int root, int region, const std::vector<int>& verts, std::vector<int>& q) {
   for (int v : verts) W.level[v] = -1;
-  auto& q = W.queue;
   q.clear();
   q.push_back(root);
-  W.level[root] = stamp_base;
+  W.level[root] = 0;
   size_t headp = 0;
-  int maxl = stamp_base;
+  int maxl = 0;
   while (headp < q.size()) {
-    int v = q[headp++];
-    int lv = W.level[v];
+    const int v = q[headp++];
+    const int lv = W.level[v];
     for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
-      int u = (*W.adj)[p];
-      if (W.part[u] == region && W.level[u] < stamp_base) {
+      const int u = (*W.adj)[p];
+      if (W.part[u] == region && W.level[u] < 0) {
         W.level[u] = lv + 1;
         if (lv + 1 > maxl) maxl = lv + 1;
         q.push_back(u);
       }
     }
   }
-  return maxl - stamp_base;
+  return maxl;
+}
+
+void nd_leaf(NDShared& W, const std::vector<int>& verts, std::vector<int>& out) {
+  const int m = (int)verts.size();
+  if (m == 0) return;
+  if (m <= 2) { for (int v : verts) out.push_back(v); return; }
+  for (int k = 0; k < m; k++) W.local[verts[k]] = k;
+  std::vector<int64_t> sx(m + 1, 0);
+  std::vector<int> sa, lorder;
+  for (int k = 0; k < m; k++) {
+    const int v = verts[k];
+    for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+      const int u = (*W.adj)[p];
+      if (W.local[u] >= 0) sa.push_back(W.local[u]);
+    }
+    sx[k + 1] = (int64_t)sa.size();
+  }
+  // neighbours outside `verts` have local == -1 only if they were never in a concurrently processed leaf:
+  // leaves handled by different threads are vertex-disjoint AND separated, so no edge joins them.
+  amd_graph(m, sx, sa, 1e9, lorder);
+  for (int k : lorder) out.push_back(verts[k]);
+  for (int k = 0; k < m; k++) W.local[verts[k]] = -1;
+}
+
+void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& out) {
+  const size_t total = verts.size();
+  if ((int)total <= W.leaf_size) { nd_leaf(W, verts, out); return; }
+  const int region = W.next_region.fetch_add(1);
+  for (int v : verts) W.part[v] = region;
+  std::vector<int> q;
+  q.reserve(total);
+  // one sweep to find a far vertex, then the level structure is rooted there
+  int root = verts[0];
+  int e = nd_bfs(W, root, region, verts, q);
+  if (q.size() == total) {
+    int best = q.back();
+    int64_t bestdeg = INT64_MAX;
+    for (size_t t = q.size(); t-- > 0;) {
+      const int v = q[t];
+      if (W.level[v] != e) break;
+      const int64_t d = (*W.xadj)[v + 1] - (*W.xadj)[v];
+      if (d < bestdeg) { bestdeg = d; best = v; }
+    }
+    root = best;
+    e = nd_bfs(W, root, region, verts, q);
+  }
+  if (q.size() < total) {
+    // the region is disconnected: label all components in one pass; big ones recurse, the small ones are
+    // packed together into leaves (independent pieces cost AMD nothing extra)
+    for (int v : verts) W.level[v] = -1;
+    std::vector<int> pack, comp;
+    for (int sv : verts) {
+      if (W.level[sv] >= 0) continue;
+      comp.clear(); comp.push_back(sv); W.level[sv] = 0;
+      for (size_t h = 0; h < comp.size(); h++) {
+        const int v = comp[h];
+        for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+          const int u = (*W.adj)[p];
+          if (W.part[u] == region && W.level[u] < 0) { W.level[u] = 0; comp.push_back(u); }
+        }
+      }
+      if ((int)comp.size() > W.leaf_size) {
+        std::vector<int> sub = comp;
+        nd_rec(W, sub, depth + 1, out);
+      } else {
+        pack.insert(pack.end(), comp.begin(), comp.end());
+        if ((int)pack.size() >= 4 * W.leaf_size) { nd_leaf(W, pack, out); pack.clear(); }
+      }
+    }
+    if (!pack.empty()) nd_leaf(W, pack, out);
+    return;
+  }
+  if (e < 2) { nd_leaf(W, verts, out); return; }   // clique-like, cannot bisect
+  // choose the level that balances vertex counts on both sides
+  std::vector<int64_t> cntl(e + 1, 0);
+  for (int v : q) cntl[W.level[v]]++;
+  const int64_t half = (int64_t)total / 2;
+  int64_t acc = 0;
+  int cut = 1;
+  for (int l = 0; l <= e; l++) { acc += cntl[l]; if (acc >= half) { cut = l; break; } }
+  if (cut < 1) cut = 1;
+  if (cut > e - 1) cut = e - 1;
+  if (cut + 1 <= e - 1 && cntl[cut + 1] < cntl[cut]) {
+    const int64_t below = acc;
+    if (std::llabs(2 * below - (int64_t)total) < (int64_t)total / 2) cut = cut + 1;
+  }
+  std::vector<int> L, R, sep;
+  for (int v : q) {
+    const int lv = W.level[v];
+    if (lv < cut) L.push_back(v);
+    else if (lv > cut) R.push_back(v);
+    else {
+      bool touches = false;
+      for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1] && !touches; p++) {
+        const int u = (*W.adj)[p];
+        if (W.part[u] == region && W.level[u] == cut + 1) touches = true;
+      }
+      if (touches) sep.push_back(v); else L.push_back(v);
+    }
+  }
+  // a level-structure cut is only worth keeping when it is thin and roughly balanced; small-world graphs
+  // (hub rows) give neither, and the region is then left to AMD as a whole
+  const size_t smaller = std::min(L.size(), R.size());
+  if (sep.size() * 5 > total || smaller * 20 < total) { nd_leaf(W, verts, out); return; }
+  for (int v : sep) W.part[v] = -1;
+  std::vector<int>().swap(verts);
+  std::vector<int>().swap(q);
+  if (depth < W.par_depth) {
+    std::vector<int> outL;
+    auto fut = std::async(std::launch::async, [&]() { nd_rec(W, L, depth + 1, outL); });
+    std::vector<int> outR;
+    nd_rec(W, R, depth + 1, outR);
+    fut.get();
+    out.insert(out.end(), outL.begin(), outL.end());
+    out.insert(out.end(), outR.begin(), outR.end());
+  } else {
+    nd_rec(W, L, depth + 1, out);
+    nd_rec(W, R, depth + 1, out);
+  }
+  nd_leaf(W, sep, out);
 }
 
 }  // namespace
@@ -329,214 +454,45 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
   // withhold dense rows exactly like AMD does; they go last
   double dense = 10.0 * dense_scale * std::sqrt((double)n);
   if (dense < 16.0) dense = 16.0;
-  NDWork W;
+  NDShared W;
   W.xadj = &xadj; W.adj = &adj;
   W.part.assign(n, 0);
   W.level.assign(n, -1);
   W.local.assign(n, -1);
+  W.leaf_size = leaf_size;
+  {
+    unsigned hc = std::thread::hardware_concurrency();
+    int d = 0;
+    while ((2u << d) <= hc && d < 5) d++;   // up to 32 concurrent subtrees
+    W.par_depth = (n >= 20000) ? d : 0;
+    if (const char* e = std::getenv("CB_ND_THREADS_DEPTH")) W.par_depth = std::atoi(e);
+  }
   std::vector<int> dense_nodes;
   for (int i = 0; i < n; i++)
     if ((double)(xadj[i + 1] - xadj[i]) > dense) { W.part[i] = -1; dense_nodes.push_back(i); }
-
-  // Explicit recursion stack of regions.  Each region is a vertex list; the
-  // output is assembled as: [left..., right..., separator] per region, with
-  // separators emitted after both halves (post-order), so we build a tree of
-  // "emit" actions and flatten it at the end.
-  struct Node { std::vector<int> verts; std::vector<int> kids; std::vector<int> sep; bool leaf = false; };
-  std::vector<Node> nodes;
-  int next_region = 1;
-  const int stamp = 0;
-
-  // initial connected components become independent roots
-  std::vector<int> roots;
+  // connected components of the rest are independent roots
   {
     std::vector<char> seen(n, 0);
     for (int s = 0; s < n; s++) {
       if (seen[s] || W.part[s] != 0) continue;
-      Node nd;
-      std::vector<int> st{s};
+      std::vector<int> comp{s};
       seen[s] = 1;
-      while (!st.empty()) {
-        int v = st.back(); st.pop_back();
-        nd.verts.push_back(v);
+      for (size_t h = 0; h < comp.size(); h++) {
+        const int v = comp[h];
         for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
-          int u = adj[p];
-          if (!seen[u] && W.part[u] == 0) { seen[u] = 1; st.push_back(u); }
+          const int u = adj[p];
+          if (!seen[u] && W.part[u] == 0) { seen[u] = 1; comp.push_back(u); }
         }
       }
-      roots.push_back((int)nodes.size());
-      nodes.push_back(std::move(nd));
+      nd_rec(W, comp, 0, perm);
     }
   }
-
-  std::vector<int> work = roots;
-  while (!work.empty()) {
-    int id = work.back(); work.pop_back();
-    if ((int)nodes[id].verts.size() <= leaf_size) { nodes[id].leaf = true; continue; }
-    int region = next_region++;
-    for (int v : nodes[id].verts) W.part[v] = region;
-    // pseudo-peripheral root: a few BFS sweeps
-    int root = nodes[id].verts[0];
-    int ecc = -1;
-    for (int it = 0; it < 1; it++) {   // one sweep to find a far vertex, then the structure is rooted there
-      int e = bfs(W, root, region, nodes[id].verts);
-      if ((int)W.queue.size() != (int)nodes[id].verts.size()) break;  // disconnected: handled below
-      if (e <= ecc) break;
-      ecc = e;
-      // farthest vertex of minimum degree in last level
-      int best = W.queue.back();
-      int64_t bestdeg = INT64_MAX;
-      for (size_t t = W.queue.size(); t-- > 0;) {
-        int v = W.queue[t];
-        if (W.level[v] - stamp != e) break;
-        int64_t d = xadj[v + 1] - xadj[v];
-        if (d < bestdeg) { bestdeg = d; best = v; }
-      }
-      root = best;
-    }
-    int e = bfs(W, root, region, nodes[id].verts);
-    size_t reached = W.queue.size();
-    size_t total = nodes[id].verts.size();
-    Node L, R;
-    std::vector<int> sep;
-    if (reached < total) {
-      // region fell apart (a separator disconnected it): label ALL components in one pass.  Big components
-      // become child regions of their own; the small ones are independent of each other, so they are packed
-      // together into leaves (AMD handles a union of disconnected pieces at no extra cost).
-      std::vector<int> verts;
-      verts.swap(nodes[id].verts);
-      for (int v : verts) W.level[v] = -1;
-      std::vector<int> small_pack;
-      std::vector<int> kids;
-      auto flush_pack = [&]() {
-        if (small_pack.empty()) return;
-        Node nd; nd.leaf = true; nd.verts.swap(small_pack);
-        for (int v : nd.verts) W.part[v] = 0;
-        kids.push_back((int)nodes.size()); nodes.push_back(std::move(nd));
-      };
-      std::vector<int> comp;
-      for (int sv : verts) {
-        if (W.level[sv] >= 0) continue;
-        comp.clear(); comp.push_back(sv); W.level[sv] = 0;
-        for (size_t h = 0; h < comp.size(); h++) {
-          const int v = comp[h];
-          for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
-            const int u = adj[p];
-            if (W.part[u] == region && W.level[u] < 0) { W.level[u] = 0; comp.push_back(u); }
-          }
-        }
-        if ((int)comp.size() > leaf_size) {
-          Node nd; nd.verts = comp;
-          for (int v : nd.verts) W.part[v] = 0;
-          const int ci = (int)nodes.size(); nodes.push_back(std::move(nd));
-          kids.push_back(ci); work.push_back(ci);
-        } else {
-          small_pack.insert(small_pack.end(), comp.begin(), comp.end());
-          if ((int)small_pack.size() >= 4 * leaf_size) flush_pack();
-        }
-      }
-      flush_pack();
-      nodes[id].kids = kids;
-      continue;
-    } else if (e < 2) {
-      nodes[id].leaf = true;  // clique-like, cannot bisect
-      continue;
-    } else {
-      // choose the level that balances vertex counts on both sides
-      std::vector<int64_t> cntl(e + 1, 0);
-      for (int v : W.queue) cntl[W.level[v] - stamp]++;
-      int64_t half = (int64_t)total / 2, acc = 0;
-      int cut = 1;
-      for (int l = 0; l <= e; l++) {
-        acc += cntl[l];
-        if (acc >= half) { cut = l; break; }
-      }
-      if (cut < 1) cut = 1;
-      if (cut > e - 1) cut = e - 1;
-      // pick the thinner of the neighbouring levels around the balance point
-      if (cut + 1 <= e - 1 && cntl[cut + 1] < cntl[cut]) {
-        int64_t below = acc;  // vertices in levels <= cut
-        if (std::llabs(2 * below - (int64_t)total) < (int64_t)total / 2) cut = cut + 1;
-      }
-      // separator = vertices of level `cut` that have a neighbour in level cut+1
-      for (int v : W.queue) {
-        int lv = W.level[v] - stamp;
-        if (lv < cut) L.verts.push_back(v);
-        else if (lv > cut) R.verts.push_back(v);
-        else {
-          bool touches = false;
-          for (int64_t p = xadj[v]; p < xadj[v + 1] && !touches; p++) {
-            int u = adj[p];
-            if (W.part[u] == region && W.level[u] - stamp == cut + 1) touches = true;
-          }
-          if (touches) sep.push_back(v); else L.verts.push_back(v);
-        }
-      }
-    }
-    // a level-structure cut is only worth keeping when it is thin and roughly balanced; small-world graphs
-    // (hub rows) give neither, and the region is then left to AMD as a whole
-    {
-      const size_t smaller = std::min(L.verts.size(), R.verts.size());
-      if (sep.size() * 5 > total || smaller * 20 < total) { nodes[id].leaf = true; continue; }
-    }
-    for (int v : sep) W.part[v] = -1;
-    nodes[id].sep = std::move(sep);
-    std::vector<int>().swap(nodes[id].verts);
-    int li = (int)nodes.size(); nodes.push_back(std::move(L));
-    int ri = (int)nodes.size(); nodes.push_back(std::move(R));
-    nodes[id].kids = {li, ri};
-    // children regions need fresh part ids; mark their vertices as "unassigned" (0)
-    for (int v : nodes[li].verts) W.part[v] = 0;
-    for (int v : nodes[ri].verts) W.part[v] = 0;
-    work.push_back(li);
-    work.push_back(ri);
-  }
-
-  OMARK("bisection");
-  // order leaves with AMD on the induced subgraph; emit post-order
-  std::vector<int64_t> sx;
-  std::vector<int> sa, lorder;
-  auto emit_leaf = [&](const std::vector<int>& verts) {
-    int m = (int)verts.size();
-    if (m == 0) return;
-    if (m <= 2) { for (int v : verts) perm.push_back(v); return; }
-    for (int k = 0; k < m; k++) W.local[verts[k]] = k;
-    sx.assign(m + 1, 0);
-    sa.clear();
-    for (int k = 0; k < m; k++) {
-      int v = verts[k];
-      for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
-        int u = adj[p];
-        if (W.local[u] >= 0) sa.push_back(W.local[u]);
-      }
-      sx[k + 1] = (int64_t)sa.size();
-    }
-    amd_graph(m, sx, sa, 1e9, lorder);
-    for (int k : lorder) perm.push_back(verts[k]);
-    for (int k = 0; k < m; k++) W.local[verts[k]] = -1;
-  };
-  // iterative post-order
-  struct Fr { int id; int stage; };
-  for (int r : roots) {
-    std::vector<Fr> st{{r, 0}};
-    while (!st.empty()) {
-      Fr f = st.back(); st.pop_back();
-      Node& nd = nodes[f.id];
-      if (nd.leaf || nd.kids.empty()) { emit_leaf(nd.verts); continue; }
-      if (f.stage == 0) {
-        st.push_back({f.id, 1});
-        for (size_t k = nd.kids.size(); k-- > 0;) st.push_back({nd.kids[k], 0});
-      } else {
-        emit_leaf(nd.sep);
-      }
-    }
-  }
+  OMARK("dissection + leaf AMD");
   std::sort(dense_nodes.begin(), dense_nodes.end(), [&](int a, int b) {
     int64_t da = xadj[a + 1] - xadj[a], db = xadj[b + 1] - xadj[b];
     return da != db ? da < db : a < b;
   });
   for (int v : dense_nodes) perm.push_back(v);
-  OMARK("leaf AMD + emit");
 }
 
 }  // namespace cb

@@ -295,6 +295,7 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
   n = P.n; m = A.m; cones = cs; set = s; sc = scal;
   int rc = assemble(P, A);
   if (rc) return rc;
+  cb_tmark("kkt: assemble");
   std::vector<int32_t> Ki32(Ki.begin(), Ki.end());
   cldl_opts o = lo;
   o.regularize_eps = s.dynamic_regularization_eps;
@@ -648,15 +649,20 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   normb = 0; for (double v : b) normb = std::max(normb, std::fabs(v));
   // cone set needs a stream: borrow the LDL's once it exists -> create ours first
   SCK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cb_tmark(nullptr);
   if ((rc = cones.init(cs, st))) return rc;
+  cb_tmark("ipm: cone set init");
   equilibrate();
+  cb_tmark("ipm: equilibrate");
   if ((rc = sc.init(st))) return rc;
   if ((rc = kkt.init(P, A, &cones, set, lo, perm, st, &sc))) return rc;
   // single stream for everything: adopt the LDL object's stream
   cudaStreamDestroy(st);
   st = kkt.st;
   cones.stream = st; sc.st = st; V.st = st; V.ws = cones.ws;
+  cb_tmark("ipm: kkt init total");
   if ((rc = upload_problem())) return rc;
+  cb_tmark("ipm: upload problem");
   auto al = [&](double** pp, int len) { return cudaMalloc((void**)pp, (size_t)(len ? len : 1) * 8) == cudaSuccess && cudaMemset(*pp, 0, (size_t)(len ? len : 1) * 8) == cudaSuccess; };
   bool ok = al(&x, n) && al(&s, m) && al(&z, m) && al(&lx, n) && al(&ls, m) && al(&lz, m) && al(&rhx, n) &&
             al(&rhs_, m) && al(&rhz, m) && al(&px, n) && al(&ps, m) && al(&pz, m) && al(&rx, n) && al(&rz, m) &&

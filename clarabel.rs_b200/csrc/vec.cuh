@@ -12,7 +12,21 @@
 
 #include <cstdint>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace cb {
+
+// setup-phase timing to stderr when CB_TIMING is set
+inline void cb_tmark(const char* label) {
+  static double last = -1.0;
+  static const bool on = std::getenv("CB_TIMING") != nullptr;
+  if (!on) return;
+  const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (label && last >= 0.0) std::fprintf(stderr, "[cb timing] %-34s %.3f s\n", label, t - last);
+  last = t;
+}
 
 // number of kernels launched by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launches;
