@@ -21,6 +21,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/clarabel_b200.h"
@@ -662,6 +664,244 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restr
   }
 }
 
+// ------------------------------------------------------------------------
+// Dataflow triangular solves: ONE persistent kernel per sweep.  CTAs pull tasks from a queue in
+// topological (level) order; a task waits on a counter (forward: number of unfinished child fronts;
+// backward: parent's done flag) instead of on a kernel boundary, so independent branches of the tree
+// overlap across levels and a level never waits for its slowest front.  A task is one wide front
+// (whole CTA) or a batch of up to 8 narrow fronts (one warp each).  Data that crosses fronts is read
+// with ld.global.cg (L2), written once before its consumers are released (threadfence + atomic).
+// No floating-point atomics: results are bit-identical to the level-synchronous kernels.
+// ------------------------------------------------------------------------
+__device__ __forceinline__ void df_wait_zero(volatile int* p) {
+  unsigned ns = 20;
+  while (*p > 0) { __nanosleep(ns); if (ns < 640) ns <<= 1; }
+}
+__device__ __forceinline__ void df_wait_set(volatile int* p) {
+  unsigned ns = 20;
+  while (*p == 0) { __nanosleep(ns); if (ns < 640) ns <<= 1; }
+}
+
+__device__ void df_fwd_small(const LDLDev& d, int s, double* __restrict__ xp, int lane) {
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* us = d.u + rp;
+  const int* __restrict__ gp = d.gat_ptr + (f + rp);
+  for (int p = lane; p < ld; p += 32) {
+    double acc = 0.0;
+    for (int e = gp[p]; e < gp[p + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
+    if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
+  }
+  __syncwarp();
+  for (int j = 0; j + 1 < ns; j++) {
+    const double xj = xp[f + j];
+    for (int i = j + 1 + lane; i < ns; i += 32) xp[f + i] -= P[(long long)j * ld + i] * xj;
+    __syncwarp();
+  }
+  for (int a = lane; a < nr; a += 32) {
+    double acc = 0.0;
+    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * xp[f + j];
+    us[a] -= acc;
+  }
+}
+
+__device__ void df_fwd_big(const LDLDev& d, int s, double* __restrict__ xp, double* sL, double* sy) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* us = d.u + rp;
+  {
+    const int* __restrict__ gp = d.gat_ptr + (f + rp);
+    for (int p = tid; p < ld; p += SV_NT) {
+      double acc = 0.0;
+      for (int e = gp[p]; e < gp[p + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
+      if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double y0 = lane < ns ? xp[f + lane] : 0.0;
+    double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
+    for (int j = 0; j < ns; j++) {
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+      const double* lj = sL + j * CB_PB_LD;
+      if (lane > j && lane < ns) y0 -= lj[lane] * xj;
+      if (lane + 32 > j && lane + 32 < ns) y1 -= lj[lane + 32] * xj;
+    }
+    if (lane < ns) { sy[lane] = y0; xp[f + lane] = y0; }
+    if (lane + 32 < ns) { sy[lane + 32] = y1; xp[f + lane + 32] = y1; }
+  }
+  __syncthreads();
+  for (int a = tid; a < nr; a += SV_NT) {
+    const double* __restrict__ pa = P + ns + a;
+    double acc = 0.0;
+    int j0 = 0;
+    for (; j0 + 16 <= ns; j0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; jj++) v[jj] = pa[(long long)(j0 + jj) * ld];
+      asm volatile("" ::: "memory");
+#pragma unroll
+      for (int jj = 0; jj < 16; jj++) acc += v[jj] * sy[j0 + jj];
+    }
+    for (; j0 < ns; j0++) acc += pa[(long long)j0 * ld] * sy[j0];
+    us[a] -= acc;
+  }
+}
+
+__device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, double* __restrict__ out, int lane) {
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  const int* __restrict__ rows = d.sn_rows + rp;
+  for (int j = 0; j < ns; j++) {
+    const double* __restrict__ cj = P + (long long)j * ld + ns;
+    double acc = 0.0;
+    for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+  }
+  __syncwarp();
+  for (int j = ns - 1; j > 0; j--) {
+    const double xj = xp[f + j];
+    for (int i = lane; i < j; i += 32) xp[f + i] -= P[(long long)i * ld + j] * xj;
+    __syncwarp();
+  }
+  for (int j = lane; j < ns; j += 32) out[d.perm[f + j]] = xp[f + j];
+}
+
+__device__ void df_bwd_big(const LDLDev& d, int s, double* __restrict__ xp, double* __restrict__ out,
+                           double* sL, double* st, double* sx) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SV_NT >> 5;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  const int* __restrict__ rows = d.sn_rows + rp;
+  const bool staged = nr <= CB_SOLVE_STAGE;
+  if (staged) for (int a = tid; a < nr; a += SV_NT) sx[a] = __ldcg(xp + rows[a]);
+  __syncthreads();
+  for (int j = warp; j < ns; j += nwarp) {
+    const double* __restrict__ cj = P + (long long)j * ld + ns;
+    double acc = 0.0;
+    if (staged) {
+      int a0 = 0;
+      for (; a0 + 256 <= nr; a0 += 256) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = cj[a0 + q * 32 + lane];
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc += v[q] * sx[a0 + q * 32 + lane];
+      }
+      for (int a = a0 + lane; a < nr; a += 32) acc += cj[a] * sx[a];
+    } else {
+      for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double y0 = lane < ns ? st[lane] : 0.0;
+    double y1 = lane + 32 < ns ? st[lane + 32] : 0.0;
+    for (int j = ns - 1; j > 0; j--) {
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+      if (lane < j) y0 -= sL[lane * CB_PB_LD + j] * xj;
+      if (lane + 32 < j) y1 -= sL[(lane + 32) * CB_PB_LD + j] * xj;
+    }
+    if (lane < ns) { xp[f + lane] = y0; out[d.perm[f + lane]] = y0; }
+    if (lane + 32 < ns) { xp[f + lane + 32] = y1; out[d.perm[f + lane + 32]] = y1; }
+  }
+}
+
+// load the unit-lower pivot block of front s into shared memory (static data: can run before the wait)
+__device__ __forceinline__ void df_load_pivot(const LDLDev& d, int s, double* sL) {
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const int ld = ns + (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  for (int idx = threadIdx.x; idx < ns * ns; idx += SV_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
+  }
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* __restrict__ xp, double* __restrict__ out) {
+  __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
+  __shared__ double sv[CB_PB_MAXNS];
+  __shared__ double sx[CB_SOLVE_STAGE];
+  __shared__ int s_task;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_task = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
+    __syncthreads();
+    const int qi = s_task;
+    if (qi >= q.ntask) break;
+    const int k = FWD ? qi : q.ntask - 1 - qi;
+    const int first = q.task_first[k], cnt = q.task_cnt[k], kind = q.task_kind[k];
+    if (kind == 1) {
+      const int s = q.fronts[first];
+      df_load_pivot(d, s, sL);                     // overlaps with the wait below
+      if (tid == 0) {
+        if (FWD) df_wait_zero(q.pend + k);
+        else { const int p = q.parent[s]; if (p >= 0) df_wait_set(q.done + p); }
+        __threadfence();
+      }
+      __syncthreads();
+      if (FWD) df_fwd_big(d, s, xp, sL, sv);
+      else df_bwd_big(d, s, xp, out, sL, sv, sx);
+      __threadfence();   // every thread publishes its own global writes before the release below
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        if (FWD) { const int p = q.parent[s]; if (p >= 0) atomicSub(q.pend + q.front2task[p], 1); }
+        else atomicExch(q.done + s, 1);
+      }
+    } else {
+      if (FWD) {
+        if (tid == 0) { df_wait_zero(q.pend + k); __threadfence(); }
+        __syncthreads();
+        if (warp < cnt) df_fwd_small(d, q.fronts[first + warp], xp, lane);
+        __threadfence();
+        __syncthreads();
+        if (tid < cnt) {
+          __threadfence();
+          const int p = q.parent[q.fronts[first + tid]];
+          if (p >= 0) atomicSub(q.pend + q.front2task[p], 1);
+        }
+      } else {
+        if (warp < cnt) {
+          const int s = q.fronts[first + warp];
+          if (lane == 0) { const int p = q.parent[s]; if (p >= 0) df_wait_set(q.done + p); __threadfence(); }
+          __syncwarp();
+          df_bwd_small(d, s, xp, out, lane);
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) { __threadfence(); atomicExch(q.done + s, 1); }
+        }
+      }
+    }
+  }
+}
+
 __global__ void k_update_values(double* __restrict__ vals, const int* __restrict__ idx,
                                 const double* __restrict__ v, long long len) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -922,13 +1162,27 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
           }
         }
     }
+    // bucket by key (counting sort keeps the child order inside a key), then order every bucket by dst with a
+    // stable sort; buckets are independent, so host threads share them
     auto build = [&](std::vector<Ent>& v, size_t nkeys, std::vector<int>& ptr, std::vector<int>& src, std::vector<int>& dst) {
-      std::stable_sort(v.begin(), v.end(), [](const Ent& x, const Ent& y) { return x.key != y.key ? x.key < y.key : x.dst < y.dst; });
       ptr.assign(nkeys + 1, 0);
       for (auto& e : v) ptr[e.key + 1]++;
       for (size_t i = 0; i < nkeys; i++) ptr[i + 1] += ptr[i];
-      src.resize(v.size() ? v.size() : 1); dst.resize(v.size() ? v.size() : 1);
-      for (size_t i = 0; i < v.size(); i++) { src[i] = v[i].src; dst[i] = v[i].dst; }
+      std::vector<Ent> w(v.size());
+      {
+        std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+        for (auto& e : v) w[pos[e.key]++] = e;
+      }
+      const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < hc; t++)
+        th.emplace_back([&, t]() {
+          for (size_t k = t; k < nkeys; k += hc)
+            std::stable_sort(w.begin() + ptr[k], w.begin() + ptr[k + 1], [](const Ent& x, const Ent& y) { return x.dst < y.dst; });
+        });
+      for (auto& x : th) x.join();
+      src.resize(w.size() ? w.size() : 1); dst.resize(w.size() ? w.size() : 1);
+      for (size_t i = 0; i < w.size(); i++) { src[i] = w[i].src; dst[i] = w[i].dst; }
     };
     std::vector<int> ptr, src, dst;
     int* t1 = nullptr;
@@ -1020,6 +1274,50 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   // level_tasks was re-ordered inside levels: re-upload
   CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
                 cudaMemcpyHostToDevice));
+  // dataflow solve plan: tasks in level order; narrow fronts batched 8 per task
+  {
+    std::vector<int> t_first, t_cnt, t_kind, fronts, f2t(S.nsup, -1);
+    std::vector<std::vector<int>> lev_small(S.nlevels), lev_big(S.nlevels);
+    for (int s = 0; s < S.nsup; s++) {
+      const int ns = S.sn_first[s + 1] - S.sn_first[s];
+      (ns <= CB_SOLVE_SMALL_NS ? lev_small : lev_big)[S.sn_level[s]].push_back(s);
+    }
+    const int per = SV_NT / 32;
+    for (int l = 0; l < S.nlevels; l++) {
+      for (size_t i = 0; i < lev_small[l].size(); i += per) {
+        const int c = (int)std::min<size_t>(per, lev_small[l].size() - i);
+        t_first.push_back((int)fronts.size()); t_cnt.push_back(c); t_kind.push_back(0);
+        for (int k = 0; k < c; k++) { f2t[lev_small[l][i + k]] = (int)t_first.size() - 1; fronts.push_back(lev_small[l][i + k]); }
+      }
+      for (int s : lev_big[l]) {
+        t_first.push_back((int)fronts.size()); t_cnt.push_back(1); t_kind.push_back(1);
+        f2t[s] = (int)t_first.size() - 1; fronts.push_back(s);
+      }
+    }
+    const int nt = (int)t_first.size();
+    std::vector<int> pend(nt, 0);
+    for (int s = 0; s < S.nsup; s++) if (S.sn_parent[s] >= 0) pend[f2t[S.sn_parent[s]]]++;
+    int* t1 = nullptr;
+    if ((rc = upload(&t1, t_first))) return rc; df.task_first = t1;
+    if ((rc = upload(&t1, t_cnt))) return rc; df.task_cnt = t1;
+    if ((rc = upload(&t1, t_kind))) return rc; df.task_kind = t1;
+    if ((rc = upload(&t1, fronts))) return rc; df.fronts = t1;
+    if ((rc = upload(&t1, f2t))) return rc; df.front2task = t1;
+    if ((rc = upload(&t1, S.sn_parent))) return rc; df.parent = t1;
+    if ((rc = upload(&t1, pend))) return rc; d_pend_init = t1;
+    CK(cudaMalloc((void**)&df.pend, (size_t)(nt ? nt : 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&df.done, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&df.qhead, 2 * sizeof(int)));
+    df.ntask = nt;
+    int nsm = 0, occ = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true>, SV_NT, 0));
+    int occ2 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false>, SV_NT, 0));
+    occ = std::max(1, std::min(occ, occ2));
+    df_grid = nsm * occ;
+    use_dataflow = std::getenv("CB_SOLVE_LEVELSYNC") == nullptr;
+  }
   cb_tmark("ldl: solve plan");
   factored = false;
   return CLDL_OK;
@@ -1032,7 +1330,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(d_pend_init); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1073,6 +1371,17 @@ int LDLObject::solve_async(double* d_x, const double* d_b) {
   CK(cudaSetDevice(device));
   g_launches += 1 + solve_launches;
   k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
+  if (use_dataflow) {
+    g_launches -= solve_launches;
+    g_launches += 2;
+    CK(cudaMemcpyAsync(df.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(df.done, 0, (size_t)S.nsup * sizeof(int), stream));
+    CK(cudaMemsetAsync(df.qhead, 0, 2 * sizeof(int), stream));
+    k_solve_df<true><<<df_grid, SV_NT, 0, stream>>>(dev, df, d_xp, d_x);
+    k_solve_df<false><<<df_grid, SV_NT, 0, stream>>>(dev, df, d_xp, d_x);
+    CK(cudaGetLastError());
+    return CLDL_OK;
+  }
   for (int l = 0; l < solve_levels; l++) {
     const SolveSeg& g = splan[l];
     if (g.nsmall) k_fwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp);

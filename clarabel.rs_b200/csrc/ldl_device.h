@@ -61,6 +61,21 @@ struct LaunchSeg {
   int level, base, count, smem_doubles, threads;
 };
 
+// dataflow solve plan (see k_solve_df in ldl.cu)
+struct DFPlan {
+  int ntask = 0;
+  const int* task_first = nullptr;   // into fronts[]
+  const int* task_cnt = nullptr;
+  const int* task_kind = nullptr;    // 0 = batch of narrow fronts, 1 = one wide front
+  const int* fronts = nullptr;
+  const int* front2task = nullptr;
+  const int* parent = nullptr;       // sn_parent
+  int* pend = nullptr;               // forward counters (reset from pend_init before every sweep)
+  int* done = nullptr;               // backward: per front done flag
+  int* qhead = nullptr;              // [2] queue heads (forward, backward)
+};
+
+
 struct SolveSeg {
   int base = 0, cbase = 0, nsmall = 0, nbig = 0;
 };
@@ -70,6 +85,10 @@ class LDLObject {
   std::vector<SolveSeg> splan;
   int* d_solve_tasks = nullptr;
   int2* d_solve_chains = nullptr;
+  DFPlan df;
+  int* d_pend_init = nullptr;
+  int df_grid = 0;
+  bool use_dataflow = true;
   int solve_levels = 0;
   unsigned long long solve_launches = 0;
   int n = 0;
