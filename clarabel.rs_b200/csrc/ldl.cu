@@ -860,6 +860,15 @@ __global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* 
     if (kind == 1) {
       const int s = q.fronts[first];
       df_load_pivot(d, s, sL);                     // overlaps with the wait below
+      {
+        // pull the (static) rows-below part of the panel towards L2 while the dependencies resolve
+        const int ns_ = d.sn_first[s + 1] - d.sn_first[s];
+        const long long ld_ = ns_ + (d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+        const char* pb = (const char*)(d.L + d.panel_off[s]);
+        const long long bytes = ld_ * ns_ * 8;
+        for (long long o = (long long)tid * 128; o < bytes; o += (long long)SV_NT * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
+      }
       if (tid == 0) {
         if (FWD) df_wait_zero(q.pend + k);
         else { const int p = q.parent[s]; if (p >= 0) df_wait_set(q.done + p); }
