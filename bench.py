@@ -311,9 +311,18 @@ def main():
             and os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
         if rank == 0:
             __graft_entry__.build()
-    out = run_reference(args, rank, world) if args.impl == "reference" else run_ours(args, rank, world)
+    # libraries (NCCL, torchrun) may write banners to stdout: keep fd 1 clean for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_reference(args, rank, world) if args.impl == "reference" else run_ours(args, rank, world)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if rank == 0 and out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
