@@ -911,6 +911,461 @@ __global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* 
   }
 }
 
+// ------------------------------------------------------------------------
+// Dataflow numeric factorisation: ONE persistent kernel for everything above tree level 0.
+// Task kinds (queue in level order, so every dependency sits earlier in the queue):
+//   F  small front, fused (as k_factor_level)                 waits: all children complete
+//   D  big front: assemble + factor the ns x ns pivot block    waits: all children complete
+//   R  big front: 256 rows below the pivot block (assemble + triangular solve)   waits: D
+//   T  big front: one 64x64 tile of the update matrix (extend-add + Schur update) waits: all R of the front
+// A front is complete when its last tile (or its F task) finishes; that releases its parent.  Data
+// produced by other CTAs inside this kernel is read with ld.global.cg (L1 is not coherent across SMs and
+// the update-matrix arena is recycled along the schedule).  Same arithmetic, same summation orders as the
+// level-synchronous kernels: results are bit-identical.
+// ------------------------------------------------------------------------
+#define DF_NT 256
+#define DF_SMEM_DOUBLES (2 * KC * TS + TS * (TS + 1))   /* 8256 doubles = 66 KB: the tile task is the largest */
+
+__device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
+
+// (src,dst) list sorted by dst, applied to `base` with an index filter/transform:
+//   keep(dst) -> new index or -1.  One destination is only touched by one thread, in list order.
+template <class Map>
+__device__ __forceinline__ void df_apply_sorted(double* base, const double* __restrict__ U,
+                                                const int* __restrict__ esrc, const int* __restrict__ edst,
+                                                int e0, int e1, Map map) {
+  const int cnt = e1 - e0;
+  if (cnt <= 0) return;
+  const int per = (cnt + DF_NT - 1) / DF_NT;
+  int b = e0 + threadIdx.x * per, e = min(e1, b + per);
+  if (b >= e1) return;
+  if (b > e0) { while (b < e1 && edst[b] == edst[b - 1]) b++; }
+  if (e < e1) { while (e < e1 && edst[e] == edst[e - 1]) e++; }
+  int i = b;
+  while (i < e) {
+    const int dd = edst[i];
+    double acc = 0.0;
+    while (i < e && edst[i] == dd) { acc += __ldcg(U + esrc[i]); i++; }
+    const long long t = map(dd);
+    if (t >= 0) base[t] += acc;
+  }
+}
+
+__device__ __forceinline__ void df_front_complete(const DFFactor& q, int s) {
+  const int p = q.parent[s];
+  if (p >= 0) atomicSub(q.pend + p, 1);
+}
+
+// ---- F: small front, everything fused (mirrors k_factor_level<256>) ----
+__device__ void dff_small(const LDLDev& d, int s, double* sm, int* s_flag) {
+  __shared__ double s_inv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = DF_NT >> 5;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  double* P = d.L + d.panel_off[s];
+  double* U = d.U + d.upd_off[s];
+  const long long psz = (long long)ld * ns;
+  double* sD = sm;                       // [CB_MAX_PANEL]
+  double* Wsm = sm + CB_MAX_PANEL;
+  const bool use_sm = psz <= (long long)(DF_SMEM_DOUBLES - CB_MAX_PANEL);
+  double* W = use_sm ? Wsm : P;
+  (void)s_flag;
+  for (long long i = tid; i < psz; i += DF_NT) W[i] = 0.0;
+  for (int b = warp; b < nr; b += nwarp)
+    for (int a = b + lane; a < nr; a += 32) U[(long long)b * nr + a] = 0.0;
+  __syncthreads();
+  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += DF_NT) W[d.asm_dst[e]] = d.vals[d.asm_src[e]];
+  __syncthreads();
+  for (long long ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ci++) {
+    const int c = d.child_list[ci];
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* Uc = d.U + d.upd_off[c];
+    const int* __restrict__ relc = d.rel + crp;
+    for (int b = warp; b < nrc; b += nwarp) {
+      const int rb = relc[b];
+      for (int a = b + lane; a < nrc; a += 32) {
+        const int ra = relc[a];
+        const double v = __ldcg(Uc + (long long)b * nrc + a);
+        if (rb < ns) W[(long long)rb * ld + ra] += v;
+        else U[(long long)(rb - ns) * nr + (ra - ns)] += v;
+      }
+    }
+    __syncthreads();
+  }
+  int c_reg = 0, c_pos = 0, c_zero = 0, c_nonf = 0;
+  for (int j = 0; j < ns; j++) {
+    if (tid == 0) {
+      double dj = W[(long long)j * ld + j];
+      if (d.reg_enable) {
+        const double sg = (double)d.dsigns[f + j];
+        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; c_reg++; }
+      }
+      if (dj == 0.0) c_zero = 1;
+      if (dj > 0.0) c_pos++;
+      const double inv = 1.0 / dj;
+      if (!isfinite(inv)) c_nonf = 1;
+      d.D[f + j] = dj;
+      d.Dinv[f + j] = inv;
+      W[(long long)j * ld + j] = dj;
+      s_inv = inv;
+      sD[j] = dj;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    const double* cj = W + (long long)j * ld;
+    for (int k = j + 1 + warp; k < ns; k += nwarp) {
+      const double wk = cj[k] * inv;
+      double* ck = W + (long long)k * ld;
+      for (int i = k + lane; i < ld; i += 32) ck[i] -= cj[i] * wk;
+    }
+    __syncthreads();
+    double* cjw = W + (long long)j * ld;
+    for (int i = j + 1 + tid; i < ld; i += DF_NT) cjw[i] *= inv;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (c_reg) atomicAdd(&d.status[ST_REGCOUNT], c_reg);
+    if (c_pos) atomicAdd(&d.status[ST_POSINERTIA], c_pos);
+    if (c_zero) atomicExch(&d.status[ST_ZEROPIV], 1);
+    if (c_nonf) atomicExch(&d.status[ST_NONFINITE], 1);
+  }
+  for (int b = warp; b < nr; b += nwarp)
+    for (int a = b + lane; a < nr; a += 32) {
+      double acc = 0.0;
+      for (int k = 0; k < ns; k++) {
+        const double* ck = W + (long long)k * ld + ns;
+        acc += ck[a] * (ck[b] * sD[k]);
+      }
+      U[(long long)b * nr + a] -= acc;
+    }
+  if (use_sm) for (long long i = tid; i < psz; i += DF_NT) P[i] = W[i];
+}
+
+// ---- D: pivot block of a big front ----
+__device__ void dff_diag(const LDLDev& d, const DFFactor& q, int s, double* sm, int* s_list, int* s_wcnt) {
+  __shared__ double s_inv2;
+  double* sA = sm;                                     // [64][CB_PB_LD]
+  double* sDval = sm + CB_PB_MAXNS * CB_PB_LD;
+  double* sDinv = sDval + CB_PB_MAXNS;
+  double* sSign = sDinv + CB_PB_MAXNS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = DF_NT >> 5;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const int nr = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  const int ld = ns + nr;
+  double* P = d.L + d.panel_off[s];
+  for (int i = tid; i < CB_PB_MAXNS * CB_PB_LD; i += DF_NT) sA[i] = 0.0;
+  if (tid < ns) sSign[tid] = (double)d.dsigns[f + tid];
+  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0 && !d.child_small[c]; });
+  __syncthreads();
+  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += DF_NT) {
+    const long long dst = d.asm_dst[e];
+    const int col = (int)(dst / ld), row = (int)(dst - (long long)col * ld);
+    if (row < ns) sA[col * CB_PB_LD + row] = d.vals[d.asm_src[e]];
+  }
+  __syncthreads();
+  const bool overflow = ncontrib > CB_CHILD_CAP;
+  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
+  for (int qi = 0; qi < nloop; qi++) {
+    const int c = overflow ? d.child_list[d.child_ptr[s] + qi] : s_list[qi];
+    const int nb = d.child_nb[c];
+    if (nb == 0 || d.child_small[c]) continue;
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* Uc = d.U + d.upd_off[c];
+    const int* __restrict__ relc = d.rel + crp;
+    for (int b = warp; b < nb; b += nwarp) {
+      const int rb = relc[b];
+      for (int a = b + lane; a < nb; a += 32) sA[rb * CB_PB_LD + relc[a]] += __ldcg(Uc + (long long)b * nrc + a);
+    }
+    __syncthreads();
+  }
+  {
+    const int bp = q.big_pos[s];
+    df_apply_sorted(sA, d.U, d.sc_panel_src, d.sc_panel_dst, d.sc_panel_ptr[bp], d.sc_panel_ptr[bp + 1],
+                    [&](int dd) -> long long { const int col = dd / ld, row = dd - col * ld; return row < ns ? (long long)col * CB_PB_LD + row : -1; });
+  }
+  __syncthreads();
+  int c_reg = 0, c_pos = 0, c_zero = 0, c_nonf = 0;
+  for (int j = 0; j < ns; j++) {
+    if (tid == 0) {
+      double dj = sA[j * CB_PB_LD + j];
+      if (d.reg_enable) {
+        const double sg = sSign[j];
+        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; c_reg++; }
+      }
+      if (dj == 0.0) c_zero = 1;
+      if (dj > 0.0) c_pos++;
+      const double inv = 1.0 / dj;
+      if (!isfinite(inv)) c_nonf = 1;
+      sDval[j] = dj;
+      sA[j * CB_PB_LD + j] = dj;
+      sDinv[j] = inv;
+      s_inv2 = inv;
+    }
+    __syncthreads();
+    const double inv = s_inv2;
+    const double* cj = sA + j * CB_PB_LD;
+    for (int k = j + 1 + warp; k < ns; k += nwarp) {
+      const double wk = cj[k] * inv;
+      double* ck = sA + k * CB_PB_LD;
+      for (int i = k + lane; i < ns; i += 32) ck[i] -= cj[i] * wk;
+    }
+    __syncthreads();
+    for (int i = j + 1 + tid; i < ns; i += DF_NT) sA[j * CB_PB_LD + i] *= inv;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (c_reg) atomicAdd(&d.status[ST_REGCOUNT], c_reg);
+    if (c_pos) atomicAdd(&d.status[ST_POSINERTIA], c_pos);
+    if (c_zero) atomicExch(&d.status[ST_ZEROPIV], 1);
+    if (c_nonf) atomicExch(&d.status[ST_NONFINITE], 1);
+  }
+  if (tid < ns) { d.D[f + tid] = sDval[tid]; d.Dinv[f + tid] = sDinv[tid]; }
+  for (int idx = tid; idx < ns * ns; idx += DF_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    P[(long long)j * ld + i] = (i >= j) ? sA[j * CB_PB_LD + i] : 0.0;
+  }
+}
+
+// ---- R: 256 rows below the pivot block ----
+__device__ void dff_rows(const LDLDev& d, const DFFactor& q, int s, int blk, double* sm, int* s_list, int* s_wcnt) {
+  double* sA = sm;
+  double* sDval = sm + CB_PB_MAXNS * CB_PB_LD;
+  double* sDinv = sDval + CB_PB_MAXNS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = DF_NT >> 5;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const int nr = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  const int ld = ns + nr;
+  double* P = d.L + d.panel_off[s];
+  const int r0 = blk * DF_NT, r1 = min(nr, r0 + DF_NT);       // rows-below index range
+  const int g0 = ns + r0, g1 = ns + r1;                        // front index range
+  const int r = r0 + tid;
+  if (r < r1) for (int j = 0; j < ns; j++) P[(long long)j * ld + ns + r] = 0.0;
+  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0 && !d.child_small[c]; });
+  __syncthreads();
+  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += DF_NT) {
+    const long long dst = d.asm_dst[e];
+    const int col = (int)(dst / ld), row = (int)(dst - (long long)col * ld);
+    if (row >= g0 && row < g1) P[dst] = d.vals[d.asm_src[e]];
+  }
+  __syncthreads();
+  const bool overflow = ncontrib > CB_CHILD_CAP;
+  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
+  for (int qi = 0; qi < nloop; qi++) {
+    const int c = overflow ? d.child_list[d.child_ptr[s] + qi] : s_list[qi];
+    const int nb = d.child_nb[c];
+    if (nb == 0 || d.child_small[c]) continue;
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const double* Uc = d.U + d.upd_off[c];
+    const int* __restrict__ relc = d.rel + crp;
+    const int alo = lower_bound_dev(relc, nrc, g0), ahi = lower_bound_dev(relc, nrc, g1);
+    if (ahi > alo) {
+      for (int b = warp; b < nb; b += nwarp) {
+        double* col = P + (long long)relc[b] * ld;
+        const double* ucol = Uc + (long long)b * nrc;
+        for (int a = alo + lane; a < ahi; a += 32) col[relc[a]] += __ldcg(ucol + a);
+      }
+    }
+    __syncthreads();
+  }
+  {
+    const int bp = q.big_pos[s];
+    df_apply_sorted(P, d.U, d.sc_panel_src, d.sc_panel_dst, d.sc_panel_ptr[bp], d.sc_panel_ptr[bp + 1],
+                    [&](int dd) -> long long { const int col = dd / ld, row = dd - col * ld; return (row >= g0 && row < g1) ? (long long)dd : -1; });
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) { df_wait_set(q.diag_done + s); __threadfence(); }
+  __syncthreads();
+  for (int idx = tid; idx < ns * ns; idx += DF_NT) {
+    const int j = idx / ns, i = idx - j * ns;
+    sA[j * CB_PB_LD + i] = __ldcg(P + (long long)j * ld + i);
+  }
+  if (tid < ns) { sDval[tid] = __ldcg(d.D + f + tid); sDinv[tid] = __ldcg(d.Dinv + f + tid); }
+  __syncthreads();
+  constexpr int JB = 16;
+  if (r < r1) {
+    double* prow = P + ns + r;
+    for (int jb = 0; jb < ns; jb += JB) {
+      const int nj = min(JB, ns - jb);
+      double t[JB];
+#pragma unroll
+      for (int jj = 0; jj < JB; jj++) t[jj] = jj < nj ? prow[(long long)(jb + jj) * ld] : 0.0;
+      for (int kb = 0; kb < jb; kb += JB) {
+        double wv[JB];
+#pragma unroll
+        for (int kk = 0; kk < JB; kk++) wv[kk] = prow[(long long)(kb + kk) * ld];
+#pragma unroll
+        for (int kk = 0; kk < JB; kk++) {
+          const double wk = wv[kk] * sDval[kb + kk];
+          const double2* lk2 = reinterpret_cast<const double2*>(sA + (kb + kk) * CB_PB_LD + jb);
+#pragma unroll
+          for (int j2 = 0; j2 < JB / 2; j2++) { const double2 l = lk2[j2]; t[2 * j2] -= wk * l.x; t[2 * j2 + 1] -= wk * l.y; }
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < JB; jj++) {
+        if (jj < nj) {
+          const double* lk = sA + (jb + jj) * CB_PB_LD + jb;
+#pragma unroll
+          for (int j2 = jj + 1; j2 < JB; j2++) t[j2] -= t[jj] * lk[j2];
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < JB; jj++) if (jj < nj) prow[(long long)(jb + jj) * ld] = t[jj] * sDinv[jb + jj];
+    }
+  }
+}
+
+// ---- T: one tile of the update matrix ----
+__device__ void dff_tile(const LDLDev& d, const DFFactor& q, int s, int ti, int tj, double* sm, int* s_list, int* s_wcnt) {
+  double* sAt = sm;
+  double* sBt = sm + KC * TS;
+  double* sC = sm + 2 * KC * TS;
+  const int tid = threadIdx.x;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const int nr = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  const int ld = ns + nr;
+  const double* P = d.L + d.panel_off[s];
+  double* U = d.U + d.upd_off[s];
+  const int i0 = ti * TS, j0 = tj * TS;
+  const int ni = min(TS, nr - i0), nj = min(TS, nr - j0);
+  for (int idx = tid; idx < TS * (TS + 1); idx += DF_NT) sC[idx] = 0.0;
+  __syncthreads();
+  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) {
+    const int2 tr = d.child_trange[c];
+    return !(ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y) && !d.child_small[c];
+  });
+  const bool overflow = ncontrib > CB_CHILD_CAP;
+  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
+  for (int qi = 0; qi < nloop; qi++) {
+    const int c = overflow ? d.child_list[d.child_ptr[s] + qi] : s_list[qi];
+    if (overflow) {
+      const int2 tr = d.child_trange[c];
+      if (ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y || d.child_small[c]) continue;
+    }
+    const long long crp = d.sn_rowptr[c];
+    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
+    const int* __restrict__ relc = d.rel + crp;
+    const int* __restrict__ tp = d.child_tptr + d.child_tptr_off[c];
+    const int tlo = d.child_trange[c].x;
+    const int a0 = tp[ti - tlo], a1 = tp[ti - tlo + 1], b0 = tp[tj - tlo], b1 = tp[tj - tlo + 1];
+    const int na = a1 - a0, nb = b1 - b0;
+    if (na > 0 && nb > 0) {
+      const double* Uc = d.U + d.upd_off[c];
+      for (int idx = tid; idx < na * nb; idx += DF_NT) {
+        const int bb = idx / na, aa = idx - bb * na;
+        const int a = a0 + aa, b = b0 + bb;
+        if (a >= b) sC[(relc[a] - ns - i0) * (TS + 1) + (relc[b] - ns - j0)] += __ldcg(Uc + (long long)b * nrc + a);
+      }
+    }
+    __syncthreads();
+  }
+  {
+    const int t = q.tile_base[s] + ti * (ti + 1) / 2 + tj;
+    df_apply_sorted(sC, d.U, d.sc_tile_src, d.sc_tile_dst, d.sc_tile_ptr[t], d.sc_tile_ptr[t + 1],
+                    [&](int dd) -> long long { return dd; });
+  }
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < ns; k0 += KC) {
+    const int kc = min(KC, ns - k0);
+    __syncthreads();
+    for (int idx = tid; idx < kc * TS; idx += DF_NT) {
+      const int k = idx / TS, rr = idx - k * TS;
+      const long long col = (long long)(k0 + k) * ld + ns;
+      sAt[idx] = (rr < ni) ? __ldcg(P + col + i0 + rr) : 0.0;
+      sBt[idx] = (rr < nj) ? __ldcg(P + col + j0 + rr) * __ldcg(d.D + f + k0 + k) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kc; k++) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a[i] = sAt[k * TS + tx + 16 * i]; b[i] = sBt[k * TS + ty + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int rr = tx + 16 * i;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int cc = ty + 16 * j;
+      if (rr < ni && cc < nj && (i0 + rr >= j0 + cc))
+        U[(long long)(j0 + cc) * nr + (i0 + rr)] = sC[rr * (TS + 1) + cc] - acc[i][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DF_NT, 2) k_factor_df(LDLDev d, DFFactor q) {
+  extern __shared__ __align__(16) double dfsm[];
+  __shared__ int s_list[CB_CHILD_CAP];
+  __shared__ int s_wcnt[DF_NT / 32];
+  __shared__ int4 s_task;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const int qi = atomicAdd(q.qhead, 1);
+      s_task = (qi < q.ntask) ? q.tasks[qi] : make_int4(-1, 0, 0, 0);
+    }
+    __syncthreads();
+    const int4 t = s_task;
+    if (t.x < 0) break;
+    const int s = t.y;
+    if (t.x == 0) {
+      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); }
+      __syncthreads();
+      dff_small(d, s, dfsm, nullptr);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) { __threadfence(); df_front_complete(q, s); }
+    } else if (t.x == 1) {
+      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); }
+      __syncthreads();
+      dff_diag(d, q, s, dfsm, s_list, s_wcnt);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) { __threadfence(); atomicExch(q.diag_done + s, 1); }
+    } else if (t.x == 2) {
+      // children are complete once the pivot-block task has started; it is earlier in the queue, but it
+      // may still be waiting: the row task needs the children's data too, so it waits on the same counter
+      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); }
+      __syncthreads();
+      dff_rows(d, q, s, t.z, dfsm, s_list, s_wcnt);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) { __threadfence(); atomicSub(q.rows_left + s, 1); }
+    } else {
+      if (tid == 0) { df_wait_zero(q.rows_left + s); __threadfence(); }
+      __syncthreads();
+      dff_tile(d, q, s, t.z, t.w, dfsm, s_list, s_wcnt);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        if (atomicSub(q.tiles_left + s, 1) == 1) df_front_complete(q, s);
+      }
+    }
+  }
+}
+
 __global__ void k_update_values(double* __restrict__ vals, const int* __restrict__ idx,
                                 const double* __restrict__ v, long long len) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1327,6 +1782,63 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     df_grid = nsm * occ;
     use_dataflow = std::getenv("CB_SOLVE_LEVELSYNC") == nullptr;
   }
+  // dataflow factorisation plan (k_factor_df): level 0's small fronts keep their level-synchronous launch
+  // (no dependencies, ~10^5 tiny CTAs); everything else becomes queue tasks in level order
+  {
+    std::vector<int> big_pos(S.nsup, -1), tile_base(S.nsup, -1);
+    for (size_t k = 0; k < big_tasks.size(); k++) big_pos[big_tasks[k]] = (int)k;
+    for (size_t k = 0; k < tiles.size(); k++) if (tile_base[tiles[k].x] < 0) tile_base[tiles[k].x] = (int)k;
+    std::vector<int4> tk;
+    std::vector<int> cnt_init(4 * (size_t)S.nsup, 0);   // [pend | diag_done | rows_left | tiles_left]
+    int* pend = cnt_init.data();
+    int* rows_left = cnt_init.data() + 2 * (size_t)S.nsup;
+    int* tiles_left = cnt_init.data() + 3 * (size_t)S.nsup;
+    auto is_big = [&](int s) { return big_pos[s] >= 0; };
+    for (int s = 0; s < S.nsup; s++) {
+      const int p = S.sn_parent[s];
+      const bool presolved = (S.sn_level[s] == 0 && !is_big(s));
+      if (p >= 0 && !presolved) pend[p]++;
+    }
+    std::vector<std::vector<int>> lev(S.nlevels);
+    for (int s = 0; s < S.nsup; s++) lev[S.sn_level[s]].push_back(s);
+    for (int l = 0; l < S.nlevels; l++) {
+      for (int s : lev[l]) if (!is_big(s) && l > 0) tk.push_back(make_int4(0, s, 0, 0));
+      for (int s : lev[l]) if (is_big(s)) tk.push_back(make_int4(1, s, 0, 0));
+      for (int s : lev[l]) if (is_big(s)) {
+        const int nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
+        const int nb = (nr + DF_NT - 1) / DF_NT;
+        rows_left[s] = nb;
+        for (int b = 0; b < nb; b++) tk.push_back(make_int4(2, s, b, 0));
+      }
+      for (int s : lev[l]) if (is_big(s)) {
+        const int nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
+        const int nt = (nr + TS - 1) / TS;
+        tiles_left[s] = nt * (nt + 1) / 2;
+        for (int ti = 0; ti < nt; ti++) for (int tj = 0; tj <= ti; tj++) tk.push_back(make_int4(3, s, ti, tj));
+      }
+    }
+    dff.ntask = (int)tk.size();
+    int4* t4 = nullptr;
+    CK(cudaMalloc((void**)&t4, (tk.size() ? tk.size() : 1) * sizeof(int4)));
+    if (!tk.empty()) CK(cudaMemcpy(t4, tk.data(), tk.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    dff.tasks = t4;
+    int* t1 = nullptr;
+    if ((rc = upload(&t1, cnt_init))) return rc; d_dff_init = t1;
+    CK(cudaMalloc((void**)&d_dff_cnt, cnt_init.size() * sizeof(int) + 16));
+    dff.pend = d_dff_cnt; dff.diag_done = d_dff_cnt + S.nsup; dff.rows_left = d_dff_cnt + 2 * (size_t)S.nsup;
+    dff.tiles_left = d_dff_cnt + 3 * (size_t)S.nsup;
+    CK(cudaMalloc((void**)&dff.qhead, sizeof(int)));
+    if ((rc = upload(&t1, S.sn_parent))) return rc; dff.parent = t1;
+    if ((rc = upload(&t1, big_pos))) return rc; dff.big_pos = t1;
+    if ((rc = upload(&t1, tile_base))) return rc; dff.tile_base = t1;
+    CK(cudaFuncSetAttribute(k_factor_df, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_DOUBLES * 8));
+    int nsm = 0, occ = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_df, DF_NT, (size_t)DF_SMEM_DOUBLES * 8));
+    dff_grid = nsm * std::max(1, occ);
+    dff_nsup4 = 4 * (size_t)S.nsup;
+    factor_dataflow = std::getenv("CB_FACTOR_LEVELSYNC") == nullptr;
+  }
   cb_tmark("ldl: solve plan");
   factored = false;
   return CLDL_OK;
@@ -1339,7 +1851,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(d_pend_init); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(d_pend_init); fr(dff.tasks); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1349,6 +1861,24 @@ void LDLObject::release() {
 int LDLObject::refactor_async() {
   CK(cudaSetDevice(device));
   CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
+  if (factor_dataflow) {
+    CK(cudaMemcpyAsync(d_dff_cnt, d_dff_init, dff_nsup4 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(dff.qhead, 0, sizeof(int), stream));
+    for (const LaunchSeg& g : plan) {
+      if (g.level != 0 || g.kind != 0) continue;
+      g_launches++;
+      if (g.threads == 64)
+        k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
+      else
+        k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
+    }
+    g_launches++;
+    k_factor_df<<<dff_grid, DF_NT, (size_t)DF_SMEM_DOUBLES * 8, stream>>>(dev, dff);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    factored = true;
+    return CLDL_OK;
+  }
   g_launches += plan.size();
   for (const LaunchSeg& g : plan) {
     if (g.kind == 1)

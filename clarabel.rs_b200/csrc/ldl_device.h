@@ -76,6 +76,21 @@ struct DFPlan {
 };
 
 
+// dataflow factorisation plan (see k_factor_df in ldl.cu)
+struct DFFactor {
+  int ntask = 0;
+  const int4* tasks = nullptr;      // x kind, y front, z a, w b
+  int* pend = nullptr;              // [nsup] children still running
+  int* diag_done = nullptr;         // [nsup]
+  int* rows_left = nullptr;         // [nsup]
+  int* tiles_left = nullptr;        // [nsup]
+  int* qhead = nullptr;
+  const int* parent = nullptr;
+  const int* big_pos = nullptr;     // [nsup] index into sc_panel_ptr (position in the big-front list) or -1
+  const int* tile_base = nullptr;   // [nsup] first global tile id of the front or -1
+};
+
+
 struct SolveSeg {
   int base = 0, cbase = 0, nsmall = 0, nbig = 0;
 };
@@ -86,6 +101,11 @@ class LDLObject {
   int* d_solve_tasks = nullptr;
   int2* d_solve_chains = nullptr;
   DFPlan df;
+  DFFactor dff;
+  int *d_dff_init = nullptr, *d_dff_cnt = nullptr;
+  int dff_grid = 0;
+  size_t dff_nsup4 = 0;
+  bool factor_dataflow = true;
   int* d_pend_init = nullptr;
   int df_grid = 0;
   bool use_dataflow = true;
