@@ -383,39 +383,55 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   }
 
   TMARK("sym: assembly map");
-  // ---- update-matrix arena: lifetime-based allocation over the level schedule ----
-  // U_s is written at level(s) and last read at level(parent(s)).
+  // ---- update-matrix arena ----
+  // U_s is written by front s and read by parent(s).  The numeric phase runs as a dataflow graph (a front
+  // starts as soon as its children are complete, with no level barrier), so a block may only be reused by a
+  // front that is ordered AFTER its last reader by the dependency graph itself: U_c (c a child of s) is dead
+  // once s completes, and exactly the proper ancestors of s start after that.  Every front therefore hands
+  // the blocks of its subtree that are dead at its completion to its parent (free lists merged small into
+  // large); a front allocates from the lists of its children before growing the arena.
   S.upd_off.assign(nsup, 0);
   {
-    std::multimap<int64_t, int64_t> freeb;  // size -> offset
+    typedef std::multimap<int64_t, int64_t> FreeList;  // size -> offset
+    std::vector<FreeList*> fl(nsup, nullptr);
     int64_t top = 0;
-    auto alloc = [&](int64_t sz) -> int64_t {
-      if (sz == 0) return 0;
-      auto it = freeb.lower_bound(sz);
-      if (it != freeb.end() && it->first <= 2 * sz + 64) {
-        int64_t off = it->second, bs = it->first;
-        freeb.erase(it);
-        if (bs - sz >= 64) freeb.emplace(bs - sz, off + sz);
-        return off;
+    for (int s = 0; s < nsup; s++) {  // supernodes are numbered in postorder: children first
+      FreeList* mine = nullptr;
+      for (int c : kids[s]) {
+        FreeList* fc = fl[c];
+        fl[c] = nullptr;
+        if (!fc) continue;
+        if (!mine) { mine = fc; continue; }
+        if (fc->size() > mine->size()) std::swap(fc, mine);
+        mine->insert(fc->begin(), fc->end());
+        delete fc;
       }
-      int64_t off = top;
-      top += sz;
-      return off;
-    };
-    for (int l = 0; l < nlev; l++) {
-      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
-        int s = S.level_tasks[t];
-        int64_t nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
-        S.upd_off[s] = alloc(nr * nr);
+      const int64_t nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+      const int64_t sz = nr * nr;
+      if (sz > 0) {
+        bool got = false;
+        if (mine) {
+          auto it = mine->lower_bound(sz);
+          if (it != mine->end() && it->first <= 2 * sz + 64) {
+            const int64_t off = it->second, bs = it->first;
+            mine->erase(it);
+            if (bs - sz >= 64) mine->emplace(bs - sz, off + sz);
+            S.upd_off[s] = off;
+            got = true;
+          }
+        }
+        if (!got) { S.upd_off[s] = top; top += sz; }
       }
-      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
-        int s = S.level_tasks[t];
-        for (int c : kids[s]) {
-          int64_t nr = S.sn_rowptr[c + 1] - S.sn_rowptr[c];
-          if (nr > 0) freeb.emplace(nr * nr, S.upd_off[c]);
+      for (int c : kids[s]) {
+        const int64_t nrc = S.sn_rowptr[c + 1] - S.sn_rowptr[c];
+        if (nrc > 0) {
+          if (!mine) mine = new FreeList();
+          mine->emplace(nrc * nrc, S.upd_off[c]);
         }
       }
+      fl[s] = mine;
     }
+    for (FreeList* f : fl) delete f;
     S.upd_total = top;
   }
   TMARK("sym: arena");
