@@ -305,6 +305,7 @@ class SymbolicAnalysis:
             names = ["n", "nsup", "nlevels", "nnzL", "nnzL_stored", "upd_total", "ordering_used", "nnzA"]
             for k, nm in enumerate(names):
                 setattr(self, nm, int(L.csym_scalar(h, k)))
+            self.L_alloc = int(L.csym_scalar(h, 10))
             self.flops = L.csym_flops(h, 0)
             self.flops_stored = L.csym_flops(h, 1)
             for k, nm in enumerate(_SYM_ARRAYS):

@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* 
 // level-synchronous kernels: results are bit-identical.
 // ------------------------------------------------------------------------
 #define DF_NT 256
-#define DF_SMEM_DOUBLES (2 * KC * TS + TS * (TS + 1))   /* 8256 doubles = 66 KB: the tile task is the largest */
+#define DF_SMEM_DOUBLES (CB_PB_MAXNS * CB_PB_LD + 2 * CB_PB_MAXNS + CB_PB_MAXNS * 128)   /* 12544 doubles = 98 KB (R task); T needs 12352 */
 
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
 
@@ -951,6 +951,14 @@ __device__ __forceinline__ void df_apply_sorted(double* base, const double* __re
   }
 }
 
+__device__ __forceinline__ unsigned long long df_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__shared__ int df_cur_qi;
+#define DF_STAMP(q, slot) do { if ((q).trace && threadIdx.x == 0) (q).trace[10 * (size_t)df_cur_qi + (slot)] = df_gtime(); } while (0)
 __device__ __forceinline__ void df_front_complete(const DFFactor& q, int s) {
   const int p = q.parent[s];
   if (p >= 0) atomicSub(q.pend + p, 1);
@@ -1045,145 +1053,314 @@ __device__ void dff_small(const LDLDev& d, int s, double* sm, int* s_flag) {
   if (use_sm) for (long long i = tid; i < psz; i += DF_NT) P[i] = W[i];
 }
 
-// ---- D: pivot block of a big front ----
-__device__ void dff_diag(const LDLDev& d, const DFFactor& q, int s, double* sm, int* s_list, int* s_wcnt) {
-  __shared__ double s_inv2;
-  double* sA = sm;                                     // [64][CB_PB_LD]
-  double* sDval = sm + CB_PB_MAXNS * CB_PB_LD;
-  double* sDinv = sDval + CB_PB_MAXNS;
-  double* sSign = sDinv + CB_PB_MAXNS;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = DF_NT >> 5;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const int nr = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-  const int ld = ns + nr;
-  double* P = d.L + d.panel_off[s];
-  for (int i = tid; i < CB_PB_MAXNS * CB_PB_LD; i += DF_NT) sA[i] = 0.0;
-  if (tid < ns) sSign[tid] = (double)d.dsigns[f + tid];
-  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0 && !d.child_small[c]; });
-  __syncthreads();
-  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += DF_NT) {
-    const long long dst = d.asm_dst[e];
-    const int col = (int)(dst / ld), row = (int)(dst - (long long)col * ld);
-    if (row < ns) sA[col * CB_PB_LD + row] = d.vals[d.asm_src[e]];
-  }
-  __syncthreads();
-  const bool overflow = ncontrib > CB_CHILD_CAP;
-  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
-  for (int qi = 0; qi < nloop; qi++) {
-    const int c = overflow ? d.child_list[d.child_ptr[s] + qi] : s_list[qi];
-    const int nb = d.child_nb[c];
-    if (nb == 0 || d.child_small[c]) continue;
-    const long long crp = d.sn_rowptr[c];
-    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
-    const double* Uc = d.U + d.upd_off[c];
-    const int* __restrict__ relc = d.rel + crp;
-    for (int b = warp; b < nb; b += nwarp) {
-      const int rb = relc[b];
-      for (int a = b + lane; a < nb; a += 32) sA[rb * CB_PB_LD + relc[a]] += __ldcg(Uc + (long long)b * nrc + a);
-    }
-    __syncthreads();
-  }
-  {
-    const int bp = q.big_pos[s];
-    df_apply_sorted(sA, d.U, d.sc_panel_src, d.sc_panel_dst, d.sc_panel_ptr[bp], d.sc_panel_ptr[bp + 1],
-                    [&](int dd) -> long long { const int col = dd / ld, row = dd - col * ld; return row < ns ? (long long)col * CB_PB_LD + row : -1; });
-  }
-  __syncthreads();
-  int c_reg = 0, c_pos = 0, c_zero = 0, c_nonf = 0;
-  for (int j = 0; j < ns; j++) {
-    if (tid == 0) {
-      double dj = sA[j * CB_PB_LD + j];
-      if (d.reg_enable) {
-        const double sg = sSign[j];
-        if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; c_reg++; }
+// ---- task / child records built by the host (LDLObject::init) ----
+// DFTask   (16 ints): kind, s, a, b, ns, nr, f, d0, d1, e0, e1, -, panel_off (2), upd_off (2)
+// DFChild  (12 ints): U offset (2), rel offset (2), nrc, a0, a1, b0, b1, -, -, -
+//   rows a0..a1 and columns b0..b1 (child-local indices) of the child's update matrix land in this task's
+//   target (pivot block / row block / tile); only a >= b is stored.
+struct DFChildRec { long long uoff, relp; int nrc, a0, a1, b0, b1, p0, p1, p2; };
+#define DF_DCAP 32          /* child records staged per round */
+#define DF_RB 128           /* rows per R task */
+
+// One child's block added into a shared-memory target.  The 8 warps own the target COLUMNS (column & 7), so no
+// two warps ever touch the same element and a warp meets the children in list order: sums keep a fixed order
+// without barriers between children.  Inside a warp lane = (owned column, row phase): at most 8 of the <= 64
+// target columns of a block belong to one warp.
+template <int NH>
+__device__ __forceinline__ void df_add_child(const LDLDev& d, const DFChildRec& ch, double* dst, int rowoff,
+                                             int rstride, int coloff, int cstride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int* __restrict__ relc = d.rel + ch.relp;
+  const double* Uc = d.U + ch.uoff;
+  if (ch.p0 == 3) {
+    // rows and columns of the block are contiguous in the target (the previous panel of the same separator,
+    // dense children): no index loads, warp-wide coalesced reads down the columns this warp owns
+    const int r0 = ch.p1 - rowoff - ch.a0, c0 = ch.p2 - coloff - ch.b0;   // target row of a: r0 + a, column of b: c0 + b
+    const int bfirst = ch.b0 + ((warp - (c0 + ch.b0)) & 7);
+    const int a1 = ch.a1, b1 = ch.b1;
+    for (int ab = ch.a0; ab < a1; ab += 32 * NH) {
+      double v[8][NH];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const int b = bfirst + 8 * c;
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+          const int a = ab + lane + 32 * h;
+          v[c][h] = (b < b1 && a < a1 && a >= b) ? __ldcg(Uc + (long long)b * ch.nrc + a) : 0.0;
+        }
       }
-      if (dj == 0.0) c_zero = 1;
-      if (dj > 0.0) c_pos++;
-      const double inv = 1.0 / dj;
-      if (!isfinite(inv)) c_nonf = 1;
-      sDval[j] = dj;
-      sA[j * CB_PB_LD + j] = dj;
-      sDinv[j] = inv;
-      s_inv2 = inv;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const int b = bfirst + 8 * c;
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+          const int a = ab + lane + 32 * h;
+          if (b < b1 && a < a1 && a >= b) dst[(r0 + a) * rstride + (c0 + b) * cstride] += v[c][h];
+        }
+      }
     }
-    __syncthreads();
-    const double inv = s_inv2;
-    const double* cj = sA + j * CB_PB_LD;
-    for (int k = j + 1 + warp; k < ns; k += nwarp) {
-      const double wk = cj[k] * inv;
-      double* ck = sA + k * CB_PB_LD;
-      for (int i = k + lane; i < ns; i += 32) ck[i] -= cj[i] * wk;
+    __syncwarp();
+    return;
+  }
+  const int bl = ch.b0 + lane, bh = bl + 32;
+  const int dc0 = bl < ch.b1 ? relc[bl] - coloff : -1;
+  const int dc1 = bh < ch.b1 ? relc[bh] - coloff : -1;
+  unsigned m0 = __ballot_sync(0xffffffffu, dc0 >= 0 && (dc0 & 7) == warp);
+  unsigned m1 = __ballot_sync(0xffffffffu, dc1 >= 0 && (dc1 & 7) == warp);
+  const int cnt0 = __popc(m0), cnt = cnt0 + __popc(m1);
+  const int oc = lane >> 2, ar = lane & 3;
+  int pos = -1;
+  if (oc < cnt) {
+    unsigned m = oc < cnt0 ? m0 : m1;
+    const int skip = oc < cnt0 ? oc : oc - cnt0;
+    for (int k = 0; k < skip; k++) m &= m - 1;
+    pos = __ffs(m) - 1 + (oc < cnt0 ? 0 : 32);
+  }
+  const int srcl = pos < 0 ? 0 : (pos & 31);
+  const int x0 = __shfl_sync(0xffffffffu, dc0, srcl), x1 = __shfl_sync(0xffffffffu, dc1, srcl);
+  if (pos >= 0) {
+    const int dcc = (pos < 32 ? x0 : x1) * cstride;
+    const int b = ch.b0 + pos;
+    const double* ucol = Uc + (long long)b * ch.nrc;
+    const int a1 = ch.a1;
+    for (int a = max(ch.a0, b) + ar; a < a1; a += 32) {
+      double v[8];
+      int r[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int aa = a + 4 * u;
+        const bool ok = aa < a1;
+        v[u] = ok ? __ldcg(ucol + aa) : 0.0;
+        r[u] = ok ? relc[aa] : rowoff;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (a + 4 * u < a1) dst[(r[u] - rowoff) * rstride + dcc] += v[u];
     }
-    __syncthreads();
-    for (int i = j + 1 + tid; i < ns; i += DF_NT) sA[j * CB_PB_LD + i] *= inv;
+  }
+  __syncwarp();
+}
+
+// Sorted (src,dst) entries with the loads hoisted: df_ent_issue starts the loads at the top of a task (they
+// overlap the panel / child-record loads), df_ent_apply adds them after the children, in list order, one
+// destination per thread (same sums as df_apply_sorted).  Lists longer than 2*DF_NT take the plain path.
+#define DF_ENT_FAST (2 * DF_NT)
+struct DFEnt { int dd[2]; double v[2]; };
+__device__ __forceinline__ void df_ent_issue(const double* __restrict__ U, const int* __restrict__ esrc,
+                                             const int* __restrict__ edst, int e0, int e1, DFEnt& pe) {
+  const int cnt = e1 - e0;
+  pe.dd[0] = pe.dd[1] = -1;
+  pe.v[0] = pe.v[1] = 0.0;
+  if (cnt > DF_ENT_FAST) return;
+  int src[2] = {0, 0};
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int i = threadIdx.x + u * DF_NT;
+    if (i < cnt) { pe.dd[u] = edst[e0 + i]; src[u] = esrc[e0 + i]; }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; u++)
+    if (threadIdx.x + u * DF_NT < cnt) pe.v[u] = __ldcg(U + src[u]);
+}
+template <class Map>
+__device__ __forceinline__ void df_ent_apply(double* base, const double* __restrict__ U, const int* __restrict__ esrc,
+                                             const int* __restrict__ edst, int e0, int e1, const DFEnt& pe,
+                                             int* s_ed, double* s_ev, Map map) {
+  const int cnt = e1 - e0;
+  if (cnt <= 0) return;
+  if (cnt > DF_ENT_FAST) { df_apply_sorted(base, U, esrc, edst, e0, e1, map); return; }
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int i = threadIdx.x + u * DF_NT;
+    if (i < cnt) { s_ed[i] = pe.dd[u]; s_ev[i] = pe.v[u]; }
   }
   __syncthreads();
-  if (tid == 0) {
-    if (c_reg) atomicAdd(&d.status[ST_REGCOUNT], c_reg);
-    if (c_pos) atomicAdd(&d.status[ST_POSINERTIA], c_pos);
-    if (c_zero) atomicExch(&d.status[ST_ZEROPIV], 1);
-    if (c_nonf) atomicExch(&d.status[ST_NONFINITE], 1);
-  }
-  if (tid < ns) { d.D[f + tid] = sDval[tid]; d.Dinv[f + tid] = sDinv[tid]; }
-  for (int idx = tid; idx < ns * ns; idx += DF_NT) {
-    const int j = idx / ns, i = idx - j * ns;
-    P[(long long)j * ld + i] = (i >= j) ? sA[j * CB_PB_LD + i] : 0.0;
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    int i = threadIdx.x + u * DF_NT;
+    if (i < cnt) {
+      const int dd = pe.dd[u];
+      if (i == 0 || s_ed[i - 1] != dd) {
+        double acc = 0.0;
+        while (i < cnt && s_ed[i] == dd) { acc += s_ev[i]; i++; }
+        const long long t = map(dd);
+        if (t >= 0) base[t] += acc;
+      }
+    }
   }
 }
 
-// ---- R: 256 rows below the pivot block ----
-__device__ void dff_rows(const LDLDev& d, const DFFactor& q, int s, int blk, double* sm, int* s_list, int* s_wcnt) {
-  double* sA = sm;
-  double* sDval = sm + CB_PB_MAXNS * CB_PB_LD;
-  double* sDinv = sDval + CB_PB_MAXNS;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = DF_NT >> 5;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const int nr = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-  const int ld = ns + nr;
-  double* P = d.L + d.panel_off[s];
-  const int r0 = blk * DF_NT, r1 = min(nr, r0 + DF_NT);       // rows-below index range
-  const int g0 = ns + r0, g1 = ns + r1;                        // front index range
-  const int r = r0 + tid;
-  if (r < r1) for (int j = 0; j < ns; j++) P[(long long)j * ld + ns + r] = 0.0;
-  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) { return d.child_nb[c] > 0 && !d.child_small[c]; });
-  __syncthreads();
-  for (long long e = d.asm_ptr[s] + tid; e < d.asm_ptr[s + 1]; e += DF_NT) {
-    const long long dst = d.asm_dst[e];
-    const int col = (int)(dst / ld), row = (int)(dst - (long long)col * ld);
-    if (row >= g0 && row < g1) P[dst] = d.vals[d.asm_src[e]];
-  }
-  __syncthreads();
-  const bool overflow = ncontrib > CB_CHILD_CAP;
-  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
-  for (int qi = 0; qi < nloop; qi++) {
-    const int c = overflow ? d.child_list[d.child_ptr[s] + qi] : s_list[qi];
-    const int nb = d.child_nb[c];
-    if (nb == 0 || d.child_small[c]) continue;
-    const long long crp = d.sn_rowptr[c];
-    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
-    const double* Uc = d.U + d.upd_off[c];
-    const int* __restrict__ relc = d.rel + crp;
-    const int alo = lower_bound_dev(relc, nrc, g0), ahi = lower_bound_dev(relc, nrc, g1);
-    if (ahi > alo) {
-      for (int b = warp; b < nb; b += nwarp) {
-        double* col = P + (long long)relc[b] * ld;
-        const double* ucol = Uc + (long long)b * nrc;
-        for (int a = alo + lane; a < ahi; a += 32) col[relc[a]] += __ldcg(ucol + a);
-      }
+// The front's own KKT entries (assembly map), 4 per thread in flight
+template <class Put>
+__device__ __forceinline__ void df_scatter_asm(const LDLDev& d, int s, Put put) {
+  const long long e0 = d.asm_ptr[s], e1 = d.asm_ptr[s + 1];
+  for (long long e = e0 + threadIdx.x; e < e1; e += 4 * DF_NT) {
+    long long dst[4];
+    int src[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long ee = e + (long long)u * DF_NT;
+      const bool ok = ee < e1;
+      dst[u] = ok ? (long long)d.asm_dst[ee] : -1;
+      src[u] = ok ? d.asm_src[ee] : 0;
     }
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = dst[u] >= 0 ? d.vals[src[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (dst[u] >= 0) put(dst[u], v[u]);
+  }
+}
+
+template <class F>
+__device__ __forceinline__ void df_children(const DFFactor& q, int d0, int d1, int* s_desc, F f) {
+  for (int base = d0; base < d1; base += DF_DCAP) {
+    const int cnt = min(DF_DCAP, d1 - base);
+    for (int i = threadIdx.x; i < cnt * 12; i += DF_NT) s_desc[i] = q.desc[(size_t)base * 12 + i];
+    __syncthreads();
+    const DFChildRec* rec = reinterpret_cast<const DFChildRec*>(s_desc);
+    for (int k = 0; k < cnt; k++) f(rec[k]);
     __syncthreads();
   }
-  {
-    const int bp = q.big_pos[s];
-    df_apply_sorted(P, d.U, d.sc_panel_src, d.sc_panel_dst, d.sc_panel_ptr[bp], d.sc_panel_ptr[bp + 1],
-                    [&](int dd) -> long long { const int col = dd / ld, row = dd - col * ld; return (row >= g0 && row < g1) ? (long long)dd : -1; });
-  }
-  __threadfence();
+}
+
+// ---- D: pivot block of a big front ----
+// Assembly in shared memory, then a right-looking LDL^T with the block held in REGISTERS: thread (bi, bj)
+// owns the 4x4 block (rows 4bi.., columns 4bj..) of the lower triangle; per pivot the owners of the pivot
+// column publish it through a double-buffered shared column (one barrier per pivot), the owner of the diagonal
+// element applies the sign test / regularisation and the reciprocal.
+__device__ void dff_diag(const LDLDev& d, const DFFactor& q, const int* tk, double* sm, int* s_desc, int* s_ed, double* s_ev) {
+  double* sA = sm;                                     // [64][CB_PB_LD]
+  double* sSign = sm + CB_PB_MAXNS * CB_PB_LD;         // [64]
+  double* colbuf = sSign + CB_PB_MAXNS;                // [2][72]: column, then dj, 1/dj
+  const int tid = threadIdx.x;
+  const int s = tk[1], ns = tk[4], nr = tk[5], f = tk[6];
+  const int ld = ns + nr;
+  const long long poff = *reinterpret_cast<const long long*>(tk + 12);
+  double* P = d.L + poff;
+  DFEnt pe;
+  df_ent_issue(d.U, d.sc_panel_src, d.sc_panel_dst, tk[9], tk[10], pe);
+  for (int i = tid; i < CB_PB_MAXNS * CB_PB_LD; i += DF_NT) sA[i] = 0.0;
+  if (tid < CB_PB_MAXNS) sSign[tid] = tid < ns ? (double)d.dsigns[f + tid] : 1.0;
   __syncthreads();
+  df_scatter_asm(d, s, [&](long long dst, double v) {
+    const int col = (int)(dst / ld), row = (int)(dst - (long long)col * ld);
+    if (row < ns) sA[col * CB_PB_LD + row] = v;
+  });
+  __syncthreads();
+  df_children(q, tk[7], tk[8], s_desc, [&](const DFChildRec& ch) { df_add_child<2>(d, ch, sA, 0, 1, 0, CB_PB_LD); });
+  df_ent_apply(sA, d.U, d.sc_panel_src, d.sc_panel_dst, tk[9], tk[10], pe, s_ed, s_ev,
+               [&](int dd) -> long long { const int col = dd / ld, row = dd - col * ld; return row < ns ? (long long)col * CB_PB_LD + row : -1; });
+  __syncthreads();
+  DF_STAMP(q, 4);
+  const int bi = tid & 15, bj = tid >> 4;
+  const bool active = bi >= bj;
+  double a[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i][k] = active ? sA[(4 * bj + k) * CB_PB_LD + 4 * bi + i] : 0.0;
+  int c_reg = 0, c_pos = 0, c_zero = 0, c_nonf = 0;
+  const int nJ = (ns + 3) >> 2;
+  for (int J = 0; J < nJ; J++) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = 4 * J + jj;
+      if (j >= ns) break;
+      double* buf = colbuf + (j & 1) * 72;
+      if (bj == J && active) {
+        if (bi == J) {
+          double dj = a[jj][jj];
+          if (d.reg_enable) {
+            const double sg = sSign[j];
+            if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; c_reg++; }
+          }
+          if (dj == 0.0) c_zero = 1;
+          if (dj > 0.0) c_pos++;
+          const double inv = __drcp_rn(dj);
+          if (!isfinite(inv)) c_nonf = 1;
+          a[jj][jj] = dj;
+          buf[64] = dj;
+          buf[65] = inv;
+          d.D[f + j] = dj;
+          d.Dinv[f + j] = inv;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) buf[4 * bi + i] = a[i][jj];
+      }
+      __syncthreads();
+      if (active && bj >= J) {
+        const double inv = buf[65];
+        double li[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) li[i] = buf[4 * bi + i];
+        if (bj > J) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const double wk = buf[4 * bj + k] * inv;
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i][k] -= li[i] * wk;
+          }
+        } else {
+#pragma unroll
+          for (int k = jj + 1; k < 4; k++) {
+            const double wk = buf[4 * bj + k] * inv;
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i][k] -= li[i] * wk;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (4 * bi + i > j) a[i][jj] *= inv;
+        }
+      }
+    }
+  }
+  if (c_reg) atomicAdd(&d.status[ST_REGCOUNT], c_reg);
+  if (c_pos) atomicAdd(&d.status[ST_POSINERTIA], c_pos);
+  if (c_zero) atomicExch(&d.status[ST_ZEROPIV], 1);
+  if (c_nonf) atomicExch(&d.status[ST_NONFINITE], 1);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int col = 4 * bj + k;
+    if (col < ns) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int row = 4 * bi + i;
+        if (row < ns) P[(long long)col * ld + row] = row >= col ? a[i][k] : 0.0;
+      }
+    }
+  }
+}
+
+// ---- R: DF_RB rows below the pivot block: assemble in shared memory, wait for D, triangular solve ----
+__device__ void dff_rows(const LDLDev& d, const DFFactor& q, const int* tk, double* sm, int* s_desc, int* s_ed, double* s_ev) {
+  double* sA = sm;                                     // [64][CB_PB_LD]  L11 (unit lower, column major)
+  double* sDval = sm + CB_PB_MAXNS * CB_PB_LD;
+  double* sDinv = sDval + CB_PB_MAXNS;
+  double* sR = sDinv + CB_PB_MAXNS;                    // [64][DF_RB]  the rows, column major
+  const int tid = threadIdx.x;
+  const int s = tk[1], blk = tk[2], ns = tk[4], nr = tk[5], f = tk[6];
+  const int ld = ns + nr;
+  double* P = d.L + *reinterpret_cast<const long long*>(tk + 12);
+  const int r0 = blk * DF_RB, r1 = min(nr, r0 + DF_RB);
+  const int g0 = ns + r0, g1 = ns + r1;
+  DFEnt pe;
+  df_ent_issue(d.U, d.sc_panel_src, d.sc_panel_dst, tk[9], tk[10], pe);
+  for (int i = tid; i < CB_PB_MAXNS * DF_RB; i += DF_NT) sR[i] = 0.0;
+  __syncthreads();
+  df_scatter_asm(d, s, [&](long long dst, double v) {
+    const int col = (int)(dst / ld), row = (int)(dst - (long long)col * ld);
+    if (row >= g0 && row < g1) sR[col * DF_RB + row - g0] = v;
+  });
+  __syncthreads();
+  df_children(q, tk[7], tk[8], s_desc, [&](const DFChildRec& ch) { df_add_child<4>(d, ch, sR, g0, 1, 0, DF_RB); });
+  df_ent_apply(sR, d.U, d.sc_panel_src, d.sc_panel_dst, tk[9], tk[10], pe, s_ed, s_ev,
+               [&](int dd) -> long long { const int col = dd / ld, row = dd - col * ld; return (row >= g0 && row < g1) ? (long long)col * DF_RB + row - g0 : -1; });
+  __syncthreads();
+  DF_STAMP(q, 4);
   if (tid == 0) { df_wait_set(q.diag_done + s); __threadfence(); }
   __syncthreads();
+  DF_STAMP(q, 5);
   for (int idx = tid; idx < ns * ns; idx += DF_NT) {
     const int j = idx / ns, i = idx - j * ns;
     sA[j * CB_PB_LD + i] = __ldcg(P + (long long)j * ld + i);
@@ -1191,20 +1368,18 @@ __device__ void dff_rows(const LDLDev& d, const DFFactor& q, int s, int blk, dou
   if (tid < ns) { sDval[tid] = __ldcg(d.D + f + tid); sDinv[tid] = __ldcg(d.Dinv + f + tid); }
   __syncthreads();
   constexpr int JB = 16;
-  if (r < r1) {
-    double* prow = P + ns + r;
+  const int r = tid;
+  if (r < r1 - r0) {
+    double* prow = sR + r;
     for (int jb = 0; jb < ns; jb += JB) {
       const int nj = min(JB, ns - jb);
       double t[JB];
 #pragma unroll
-      for (int jj = 0; jj < JB; jj++) t[jj] = jj < nj ? prow[(long long)(jb + jj) * ld] : 0.0;
+      for (int jj = 0; jj < JB; jj++) t[jj] = jj < nj ? prow[(jb + jj) * DF_RB] : 0.0;
       for (int kb = 0; kb < jb; kb += JB) {
-        double wv[JB];
-#pragma unroll
-        for (int kk = 0; kk < JB; kk++) wv[kk] = prow[(long long)(kb + kk) * ld];
 #pragma unroll
         for (int kk = 0; kk < JB; kk++) {
-          const double wk = wv[kk] * sDval[kb + kk];
+          const double wk = prow[(kb + kk) * DF_RB] * sDval[kb + kk];
           const double2* lk2 = reinterpret_cast<const double2*>(sA + (kb + kk) * CB_PB_LD + jb);
 #pragma unroll
           for (int j2 = 0; j2 < JB / 2; j2++) { const double2 l = lk2[j2]; t[2 * j2] -= wk * l.x; t[2 * j2 + 1] -= wk * l.y; }
@@ -1219,88 +1394,80 @@ __device__ void dff_rows(const LDLDev& d, const DFFactor& q, int s, int blk, dou
         }
       }
 #pragma unroll
-      for (int jj = 0; jj < JB; jj++) if (jj < nj) prow[(long long)(jb + jj) * ld] = t[jj] * sDinv[jb + jj];
+      for (int jj = 0; jj < JB; jj++) if (jj < nj) prow[(jb + jj) * DF_RB] = t[jj] * sDinv[jb + jj];
     }
+  }
+  __syncthreads();
+  const int nrow = r1 - r0;
+  for (int idx = tid; idx < ns * DF_RB; idx += DF_NT) {
+    const int j = idx / DF_RB, rr = idx - j * DF_RB;
+    if (rr < nrow) P[(long long)j * ld + g0 + rr] = sR[idx];
   }
 }
 
-// ---- T: one tile of the update matrix ----
-__device__ void dff_tile(const LDLDev& d, const DFFactor& q, int s, int ti, int tj, double* sm, int* s_list, int* s_wcnt) {
-  double* sAt = sm;
-  double* sBt = sm + KC * TS;
-  double* sC = sm + 2 * KC * TS;
+// ---- T: one 64x64 tile of the update matrix ----
+__device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, double* sm, int* s_desc, int* s_ed, double* s_ev) {
+  double* sAt = sm;                      // [ns][TS]  L21 rows of tile-row I
+  double* sBt = sm + TS * TS;            // [ns][TS]  L21 rows of tile-row J, scaled by D
+  double* sC = sm + 2 * TS * TS;         // [TS][TS+1] children's contributions
+  double* sD = sC + TS * (TS + 1);       // [ns]
   const int tid = threadIdx.x;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const int nr = (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  const int ti = tk[2], tj = tk[3], ns = tk[4], nr = tk[5], f = tk[6];
   const int ld = ns + nr;
-  const double* P = d.L + d.panel_off[s];
-  double* U = d.U + d.upd_off[s];
+  const double* P = d.L + *reinterpret_cast<const long long*>(tk + 12);
+  double* U = d.U + *reinterpret_cast<const long long*>(tk + 14);
   const int i0 = ti * TS, j0 = tj * TS;
   const int ni = min(TS, nr - i0), nj = min(TS, nr - j0);
+  // every independent load of the task is issued up front (sorted entries, child records, the whole K range
+  // of both panels) so that the task pays ~3 dependent memory round trips instead of one per stage
+  DFEnt pe;
+  df_ent_issue(d.U, d.sc_tile_src, d.sc_tile_dst, tk[9], tk[10], pe);
+  {
+    // finished panels are immutable for the rest of the launch and start on sector boundaries, so they may
+    // travel through L1: 8-byte cp.async straight into shared memory, no registers, no issue stall
+    const int rr = tid & (TS - 1), kq = tid >> 6;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sAt), sb = (unsigned)__cvta_generic_to_shared(sBt);
+    const unsigned za = rr < ni ? 8u : 0u, zb = rr < nj ? 8u : 0u;
+    const double* pa = P + ns + i0 + (rr < ni ? rr : 0);
+    const double* pb = P + ns + j0 + (rr < nj ? rr : 0);
+#pragma unroll 4
+    for (int k = kq; k < ns; k += 4) {
+      const long long col = (long long)k * ld;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa + (unsigned)(k * TS + rr) * 8u), "l"(pa + col), "r"(za) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sb + (unsigned)(k * TS + rr) * 8u), "l"(pb + col), "r"(zb) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid < ns) sD[tid] = __ldcg(d.D + f + tid);
+  }
+  DF_STAMP(q, 6);
   for (int idx = tid; idx < TS * (TS + 1); idx += DF_NT) sC[idx] = 0.0;
   __syncthreads();
-  const int ncontrib = compact_children(d, s, s_list, CB_CHILD_CAP, s_wcnt, [&](int c) {
-    const int2 tr = d.child_trange[c];
-    return !(ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y) && !d.child_small[c];
-  });
-  const bool overflow = ncontrib > CB_CHILD_CAP;
-  const int nloop = overflow ? (int)(d.child_ptr[s + 1] - d.child_ptr[s]) : ncontrib;
-  for (int qi = 0; qi < nloop; qi++) {
-    const int c = overflow ? d.child_list[d.child_ptr[s] + qi] : s_list[qi];
-    if (overflow) {
-      const int2 tr = d.child_trange[c];
-      if (ti < tr.x || ti > tr.y || tj < tr.x || tj > tr.y || d.child_small[c]) continue;
-    }
-    const long long crp = d.sn_rowptr[c];
-    const int nrc = (int)(d.sn_rowptr[c + 1] - crp);
-    const int* __restrict__ relc = d.rel + crp;
-    const int* __restrict__ tp = d.child_tptr + d.child_tptr_off[c];
-    const int tlo = d.child_trange[c].x;
-    const int a0 = tp[ti - tlo], a1 = tp[ti - tlo + 1], b0 = tp[tj - tlo], b1 = tp[tj - tlo + 1];
-    const int na = a1 - a0, nb = b1 - b0;
-    if (na > 0 && nb > 0) {
-      const double* Uc = d.U + d.upd_off[c];
-      for (int idx = tid; idx < na * nb; idx += DF_NT) {
-        const int bb = idx / na, aa = idx - bb * na;
-        const int a = a0 + aa, b = b0 + bb;
-        if (a >= b) sC[(relc[a] - ns - i0) * (TS + 1) + (relc[b] - ns - j0)] += __ldcg(Uc + (long long)b * nrc + a);
-      }
-    }
-    __syncthreads();
-  }
-  {
-    const int t = q.tile_base[s] + ti * (ti + 1) / 2 + tj;
-    df_apply_sorted(sC, d.U, d.sc_tile_src, d.sc_tile_dst, d.sc_tile_ptr[t], d.sc_tile_ptr[t + 1],
-                    [&](int dd) -> long long { return dd; });
-  }
+  DF_STAMP(q, 7);
+  df_children(q, tk[7], tk[8], s_desc, [&](const DFChildRec& ch) { df_add_child<2>(d, ch, sC, ns + i0, TS + 1, ns + j0, 1); });
+  DF_STAMP(q, 8);
+  df_ent_apply(sC, d.U, d.sc_tile_src, d.sc_tile_dst, tk[9], tk[10], pe, s_ed, s_ev, [&](int dd) -> long long { return dd; });
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int idx = tid; idx < ns * TS; idx += DF_NT) sBt[idx] *= sD[idx >> 6];
+  __syncthreads();
+  DF_STAMP(q, 4);
   const int tx = tid & 15, ty = tid >> 4;
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < ns; k0 += KC) {
-    const int kc = min(KC, ns - k0);
-    __syncthreads();
-    for (int idx = tid; idx < kc * TS; idx += DF_NT) {
-      const int k = idx / TS, rr = idx - k * TS;
-      const long long col = (long long)(k0 + k) * ld + ns;
-      sAt[idx] = (rr < ni) ? __ldcg(P + col + i0 + rr) : 0.0;
-      sBt[idx] = (rr < nj) ? __ldcg(P + col + j0 + rr) * __ldcg(d.D + f + k0 + k) : 0.0;
-    }
-    __syncthreads();
 #pragma unroll 4
-    for (int k = 0; k < kc; k++) {
-      double a[4], b[4];
+  for (int k = 0; k < ns; k++) {
+    double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) { a[i] = sAt[k * TS + tx + 16 * i]; b[i] = sBt[k * TS + ty + 16 * i]; }
+    for (int i = 0; i < 4; i++) { a[i] = sAt[k * TS + tx + 16 * i]; b[i] = sBt[k * TS + ty + 16 * i]; }
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
-    }
+      for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
   }
+  DF_STAMP(q, 5);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int rr = tx + 16 * i;
@@ -1315,48 +1482,55 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, int s, int ti, int 
 
 __global__ void __launch_bounds__(DF_NT, 2) k_factor_df(LDLDev d, DFFactor q) {
   extern __shared__ __align__(16) double dfsm[];
-  __shared__ int s_list[CB_CHILD_CAP];
-  __shared__ int s_wcnt[DF_NT / 32];
-  __shared__ int4 s_task;
+  __shared__ __align__(16) int s_desc[DF_DCAP * 12];
+  __shared__ __align__(16) int s_task[16];
+  __shared__ int s_ed[DF_ENT_FAST];
+  __shared__ double s_ev[DF_ENT_FAST];
   const int tid = threadIdx.x;
+  if (tid == 0) df_cur_qi = -1;
   for (;;) {
     __syncthreads();
     if (tid == 0) {
+      if (q.trace && df_cur_qi >= 0) q.trace[10 * (size_t)df_cur_qi + 2] = df_gtime();
       const int qi = atomicAdd(q.qhead, 1);
-      s_task = (qi < q.ntask) ? q.tasks[qi] : make_int4(-1, 0, 0, 0);
+      df_cur_qi = qi < q.ntask ? qi : -1;
+      if (q.trace && df_cur_qi >= 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        q.trace[10 * (size_t)qi] = df_gtime();
+        q.trace[10 * (size_t)qi + 3] = smid;
+      }
     }
     __syncthreads();
-    const int4 t = s_task;
-    if (t.x < 0) break;
-    const int s = t.y;
-    if (t.x == 0) {
-      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); }
+    const int qi = df_cur_qi;
+    if (qi < 0) break;
+    if (tid < 4) reinterpret_cast<int4*>(s_task)[tid] = q.tasks[4 * (size_t)qi + tid];
+    __syncthreads();
+    const int kind = s_task[0], s = s_task[1];
+    if (kind == 0) {
+      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); if (q.trace) q.trace[10 * (size_t)qi + 1] = df_gtime(); }
       __syncthreads();
       dff_small(d, s, dfsm, nullptr);
-      __threadfence();
       __syncthreads();
       if (tid == 0) { __threadfence(); df_front_complete(q, s); }
-    } else if (t.x == 1) {
-      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); }
+    } else if (kind == 1) {
+      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); if (q.trace) q.trace[10 * (size_t)qi + 1] = df_gtime(); }
       __syncthreads();
-      dff_diag(d, q, s, dfsm, s_list, s_wcnt);
-      __threadfence();
+      dff_diag(d, q, s_task, dfsm, s_desc, s_ed, s_ev);
       __syncthreads();
       if (tid == 0) { __threadfence(); atomicExch(q.diag_done + s, 1); }
-    } else if (t.x == 2) {
-      // children are complete once the pivot-block task has started; it is earlier in the queue, but it
-      // may still be waiting: the row task needs the children's data too, so it waits on the same counter
-      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); }
+    } else if (kind == 2) {
+      // the row task needs the children's data as well as the pivot block: it waits on the children counter
+      // first, assembles, and only then waits for the D task of the front
+      if (tid == 0) { df_wait_zero(q.pend + s); __threadfence(); if (q.trace) q.trace[10 * (size_t)qi + 1] = df_gtime(); }
       __syncthreads();
-      dff_rows(d, q, s, t.z, dfsm, s_list, s_wcnt);
-      __threadfence();
+      dff_rows(d, q, s_task, dfsm, s_desc, s_ed, s_ev);
       __syncthreads();
       if (tid == 0) { __threadfence(); atomicSub(q.rows_left + s, 1); }
     } else {
-      if (tid == 0) { df_wait_zero(q.rows_left + s); __threadfence(); }
+      if (tid == 0) { df_wait_zero(q.rows_left + s); __threadfence(); if (q.trace) q.trace[10 * (size_t)qi + 1] = df_gtime(); }
       __syncthreads();
-      dff_tile(d, q, s, t.z, t.w, dfsm, s_list, s_wcnt);
-      __threadfence();
+      dff_tile(d, q, s_task, dfsm, s_desc, s_ed, s_ev);
       __syncthreads();
       if (tid == 0) {
         __threadfence();
@@ -1463,7 +1637,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   nnzA = Ap[n];
   CK(cudaMalloc((void**)&dev.vals, (size_t)(nnzA ? nnzA : 1) * sizeof(double)));
   CK(cudaMemcpy(dev.vals, Ax, (size_t)nnzA * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMalloc((void**)&dev.L, (size_t)(S.nnzL_stored ? S.nnzL_stored : 1) * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.L, (size_t)(S.L_alloc ? S.L_alloc : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&dev.U, (size_t)(S.upd_total ? S.upd_total : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&dev.D, (size_t)n * sizeof(double)));
   CK(cudaMalloc((void**)&dev.Dinv, (size_t)n * sizeof(double)));
@@ -1478,8 +1652,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
 
   cb_tmark("ldl: uploads + device alloc");
   // per-child constants for the big-front kernels and the per-destination gather lists for the solves
+  std::vector<int> h_child_nb(S.nsup, 0);
   {
-    std::vector<int> child_nb(S.nsup, 0);
+    std::vector<int>& child_nb = h_child_nb;
     std::vector<int2> child_tr(S.nsup, make_int2(1, 0));
     std::vector<int> gptr((size_t)n + S.sn_rows.size() + 1, 0);
     for (int c = 0; c < S.nsup; c++) {
@@ -1597,11 +1772,14 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   }
   cb_tmark("ldl: launch plan + tiles");
   // small children (nr <= CB_SMALL_CHILD) of big fronts: one dst-sorted (src,dst) list per panel and per tile
+  std::vector<signed char> small_child;
+  std::vector<int> h_sc_panel_ptr, h_sc_tile_ptr;
   {
     std::vector<int> big_pos(S.nsup, -1), tile_base(S.nsup, -1);
     for (size_t k = 0; k < big_tasks.size(); k++) big_pos[big_tasks[k]] = (int)k;
     for (size_t k = 0; k < tiles.size(); k++) if (tile_base[tiles[k].x] < 0) tile_base[tiles[k].x] = (int)k;
-    std::vector<signed char> small(S.nsup, 0);
+    std::vector<signed char>& small = small_child;
+    small.assign(S.nsup, 0);
     struct Ent { int key; int dst; int src; };
     std::vector<Ent> pe, te;
     for (int c = 0; c < S.nsup; c++) {
@@ -1651,10 +1829,12 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     std::vector<int> ptr, src, dst;
     int* t1 = nullptr;
     build(pe, big_tasks.size(), ptr, src, dst);
+    h_sc_panel_ptr = ptr;
     if ((rc = upload(&t1, ptr))) return rc; dev.sc_panel_ptr = t1;
     if ((rc = upload(&t1, src))) return rc; dev.sc_panel_src = t1;
     if ((rc = upload(&t1, dst))) return rc; dev.sc_panel_dst = t1;
     build(te, tiles.size(), ptr, src, dst);
+    h_sc_tile_ptr = ptr;
     if ((rc = upload(&t1, ptr))) return rc; dev.sc_tile_ptr = t1;
     if ((rc = upload(&t1, src))) return rc; dev.sc_tile_src = t1;
     if ((rc = upload(&t1, dst))) return rc; dev.sc_tile_dst = t1;
@@ -1783,12 +1963,15 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     use_dataflow = std::getenv("CB_SOLVE_LEVELSYNC") == nullptr;
   }
   // dataflow factorisation plan (k_factor_df): level 0's small fronts keep their level-synchronous launch
-  // (no dependencies, ~10^5 tiny CTAs); everything else becomes queue tasks in level order
+  // (no dependencies, ~10^5 tiny CTAs); everything else becomes queue tasks in level order.  Every task
+  // record carries the front's constants and the range of its child records, so a task starts with two
+  // dependent loads (record, child records) instead of walking the tree arrays.
   {
     std::vector<int> big_pos(S.nsup, -1), tile_base(S.nsup, -1);
     for (size_t k = 0; k < big_tasks.size(); k++) big_pos[big_tasks[k]] = (int)k;
     for (size_t k = 0; k < tiles.size(); k++) if (tile_base[tiles[k].x] < 0) tile_base[tiles[k].x] = (int)k;
-    std::vector<int4> tk;
+    std::vector<int> tk;       // 16 ints per task
+    std::vector<int> desc;     // 12 ints per child record
     std::vector<int> cnt_init(4 * (size_t)S.nsup, 0);   // [pend | diag_done | rows_left | tiles_left]
     int* pend = cnt_init.data();
     int* rows_left = cnt_init.data() + 2 * (size_t)S.nsup;
@@ -1799,30 +1982,106 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       const bool presolved = (S.sn_level[s] == 0 && !is_big(s));
       if (p >= 0 && !presolved) pend[p]++;
     }
+    auto push_task = [&](int kind, int s, int a, int b, int d0, int d1, int e0, int e1) {
+      const size_t o = tk.size();
+      tk.resize(o + 16, 0);
+      int* t = tk.data() + o;
+      t[0] = kind; t[1] = s; t[2] = a; t[3] = b;
+      t[4] = S.sn_first[s + 1] - S.sn_first[s];
+      t[5] = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
+      t[6] = S.sn_first[s];
+      t[7] = d0; t[8] = d1; t[9] = e0; t[10] = e1;
+      const long long po = S.panel_off[s], uo = S.upd_off[s];
+      std::memcpy(t + 12, &po, 8);
+      std::memcpy(t + 14, &uo, 8);
+    };
+    auto push_desc = [&](int c, int a0, int a1, int b0, int b1) {
+      const size_t o = desc.size();
+      desc.resize(o + 12, 0);
+      int* t = desc.data() + o;
+      const long long uo = S.upd_off[c], rp = S.sn_rowptr[c];
+      std::memcpy(t, &uo, 8);
+      std::memcpy(t + 2, &rp, 8);
+      t[4] = (int)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
+      t[5] = a0; t[6] = a1; t[7] = b0; t[8] = b1;
+      const int* rl = S.rel.data() + rp;
+      const bool rc_ = rl[a1 - 1] - rl[a0] == a1 - 1 - a0, cc_ = rl[b1 - 1] - rl[b0] == b1 - 1 - b0;
+      t[9] = (rc_ ? 1 : 0) | (cc_ ? 2 : 0);
+      t[10] = rl[a0];
+      t[11] = rl[b0];
+    };
     std::vector<std::vector<int>> lev(S.nlevels);
     for (int s = 0; s < S.nsup; s++) lev[S.sn_level[s]].push_back(s);
+    std::vector<int> kidsbuf, tp;
     for (int l = 0; l < S.nlevels; l++) {
-      for (int s : lev[l]) if (!is_big(s) && l > 0) tk.push_back(make_int4(0, s, 0, 0));
-      for (int s : lev[l]) if (is_big(s)) tk.push_back(make_int4(1, s, 0, 0));
+      for (int s : lev[l]) if (!is_big(s) && l > 0) push_task(0, s, 0, 0, 0, 0, 0, 0);
+      // the children of a big front that go through child records (the small ones use the sorted entry lists)
+      auto heavy_kids = [&](int s) {
+        kidsbuf.clear();
+        for (int64_t ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ci++) {
+          const int c = S.child_list[ci];
+          if (!small_child[c] && S.sn_rowptr[c + 1] > S.sn_rowptr[c]) kidsbuf.push_back(c);
+        }
+      };
       for (int s : lev[l]) if (is_big(s)) {
-        const int nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
-        const int nb = (nr + DF_NT - 1) / DF_NT;
-        rows_left[s] = nb;
-        for (int b = 0; b < nb; b++) tk.push_back(make_int4(2, s, b, 0));
+        heavy_kids(s);
+        const int d0 = (int)(desc.size() / 12);
+        for (int c : kidsbuf) if (h_child_nb[c] > 0) push_desc(c, 0, h_child_nb[c], 0, h_child_nb[c]);
+        push_task(1, s, 0, 0, d0, (int)(desc.size() / 12), h_sc_panel_ptr[big_pos[s]], h_sc_panel_ptr[big_pos[s] + 1]);
       }
       for (int s : lev[l]) if (is_big(s)) {
+        heavy_kids(s);
+        const int ns = S.sn_first[s + 1] - S.sn_first[s];
+        const int nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
+        const int nb = (nr + DF_RB - 1) / DF_RB;
+        rows_left[s] = nb;
+        for (int b = 0; b < nb; b++) {
+          const int g0 = ns + b * DF_RB, g1 = std::min(ns + nr, g0 + DF_RB);
+          const int d0 = (int)(desc.size() / 12);
+          for (int c : kidsbuf) {
+            if (h_child_nb[c] == 0) continue;
+            const int* rb = S.rel.data() + S.sn_rowptr[c];
+            const int* re = S.rel.data() + S.sn_rowptr[c + 1];
+            const int alo = (int)(std::lower_bound(rb, re, g0) - rb), ahi = (int)(std::lower_bound(rb, re, g1) - rb);
+            if (ahi > alo) push_desc(c, alo, ahi, 0, h_child_nb[c]);
+          }
+          push_task(2, s, b, 0, d0, (int)(desc.size() / 12), h_sc_panel_ptr[big_pos[s]], h_sc_panel_ptr[big_pos[s] + 1]);
+        }
+      }
+      for (int s : lev[l]) if (is_big(s)) {
+        heavy_kids(s);
+        const int ns = S.sn_first[s + 1] - S.sn_first[s];
         const int nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
         const int nt = (nr + TS - 1) / TS;
         tiles_left[s] = nt * (nt + 1) / 2;
-        for (int ti = 0; ti < nt; ti++) for (int tj = 0; tj <= ti; tj++) tk.push_back(make_int4(3, s, ti, tj));
+        // per child: first child row of every tile row
+        std::vector<std::vector<int>> ctp(kidsbuf.size());
+        for (size_t k = 0; k < kidsbuf.size(); k++) {
+          const int c = kidsbuf[k];
+          const int* rb = S.rel.data() + S.sn_rowptr[c];
+          const int* re = S.rel.data() + S.sn_rowptr[c + 1];
+          ctp[k].resize(nt + 1);
+          for (int t = 0; t <= nt; t++) ctp[k][t] = (int)(std::lower_bound(rb, re, ns + t * TS) - rb);
+        }
+        for (int ti = 0; ti < nt; ti++)
+          for (int tj = 0; tj <= ti; tj++) {
+            const int d0 = (int)(desc.size() / 12);
+            for (size_t k = 0; k < kidsbuf.size(); k++) {
+              const int a0 = ctp[k][ti], a1 = ctp[k][ti + 1], b0 = ctp[k][tj], b1 = ctp[k][tj + 1];
+              if (a1 > a0 && b1 > b0) push_desc(kidsbuf[k], a0, a1, b0, b1);
+            }
+            const int t = tile_base[s] + ti * (ti + 1) / 2 + tj;
+            push_task(3, s, ti, tj, d0, (int)(desc.size() / 12), h_sc_tile_ptr[t], h_sc_tile_ptr[t + 1]);
+          }
       }
     }
-    dff.ntask = (int)tk.size();
+    dff.ntask = (int)(tk.size() / 16);
     int4* t4 = nullptr;
-    CK(cudaMalloc((void**)&t4, (tk.size() ? tk.size() : 1) * sizeof(int4)));
-    if (!tk.empty()) CK(cudaMemcpy(t4, tk.data(), tk.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&t4, (tk.size() ? tk.size() : 16) * sizeof(int)));
+    if (!tk.empty()) CK(cudaMemcpy(t4, tk.data(), tk.size() * sizeof(int), cudaMemcpyHostToDevice));
     dff.tasks = t4;
     int* t1 = nullptr;
+    if ((rc = upload(&t1, desc))) return rc; dff.desc = t1;
     if ((rc = upload(&t1, cnt_init))) return rc; d_dff_init = t1;
     CK(cudaMalloc((void**)&d_dff_cnt, cnt_init.size() * sizeof(int) + 16));
     dff.pend = d_dff_cnt; dff.diag_done = d_dff_cnt + S.nsup; dff.rows_left = d_dff_cnt + 2 * (size_t)S.nsup;
@@ -1838,6 +2097,11 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     dff_grid = nsm * std::max(1, occ);
     dff_nsup4 = 4 * (size_t)S.nsup;
     factor_dataflow = std::getenv("CB_FACTOR_LEVELSYNC") == nullptr;
+    if (std::getenv("CB_DF_TRACE") && dff.ntask > 0) {
+      h_dff_tasks = tk;
+      CK(cudaMalloc((void**)&dff.trace, (size_t)dff.ntask * 10 * sizeof(unsigned long long)));
+      CK(cudaMemset(dff.trace, 0, (size_t)dff.ntask * 10 * sizeof(unsigned long long)));
+    }
   }
   cb_tmark("ldl: solve plan");
   factored = false;
@@ -1851,7 +2115,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(d_pend_init); fr(dff.tasks); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1901,6 +2165,17 @@ int LDLObject::sync_status() {
   CK(cudaStreamSynchronize(stream));
   regularize_count = (uint64_t)h_status[ST_REGCOUNT];
   positive_inertia = (uint64_t)h_status[ST_POSINERTIA];
+  if (dff.trace && factor_dataflow) {  // diagnostic: CB_DF_TRACE=<file> dumps the last refactor's task timeline
+    std::vector<unsigned long long> tr((size_t)dff.ntask * 10);
+    CK(cudaMemcpy(tr.data(), dff.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* fp = std::fopen(std::getenv("CB_DF_TRACE"), "wb")) {
+      const long long nt = dff.ntask;
+      std::fwrite(&nt, sizeof(nt), 1, fp);
+      std::fwrite(h_dff_tasks.data(), sizeof(int), (size_t)nt * 16, fp);
+      std::fwrite(tr.data(), sizeof(unsigned long long), tr.size(), fp);
+      std::fclose(fp);
+    }
+  }
   if (h_status[ST_ZEROPIV] && !dev.reg_enable) return CLDL_E_ZERO_PIVOT;
   return h_status[ST_NONFINITE] ? 0 : 1;
 }

@@ -79,7 +79,8 @@ struct DFPlan {
 // dataflow factorisation plan (see k_factor_df in ldl.cu)
 struct DFFactor {
   int ntask = 0;
-  const int4* tasks = nullptr;      // x kind, y front, z a, w b
+  const int4* tasks = nullptr;      // 4 x int4 per task: see DFTask in ldl.cu
+  const int* desc = nullptr;        // 12 ints per child record
   int* pend = nullptr;              // [nsup] children still running
   int* diag_done = nullptr;         // [nsup]
   int* rows_left = nullptr;         // [nsup]
@@ -88,6 +89,7 @@ struct DFFactor {
   const int* parent = nullptr;
   const int* big_pos = nullptr;     // [nsup] index into sc_panel_ptr (position in the big-front list) or -1
   const int* tile_base = nullptr;   // [nsup] first global tile id of the front or -1
+  unsigned long long* trace = nullptr;  // optional [ntask][4]: grab, ready, end (globaltimer ns), smid
 };
 
 
@@ -103,6 +105,7 @@ class LDLObject {
   DFPlan df;
   DFFactor dff;
   int *d_dff_init = nullptr, *d_dff_cnt = nullptr;
+  std::vector<int> h_dff_tasks;
   int dff_grid = 0;
   size_t dff_nsup4 = 0;
   bool factor_dataflow = true;

@@ -289,13 +289,17 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   // ---- sizes, flops, levels ----
   S.panel_off.assign(nsup + 1, 0);
   S.flops_stored = 0;
+  S.nnzL_stored = 0;
   for (int s = 0; s < nsup; s++) {
     int64_t ns = S.sn_first[s + 1] - S.sn_first[s];
     int64_t nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
-    S.panel_off[s + 1] = S.panel_off[s] + (ns + nr) * ns;
+    // panels start on 32-byte boundaries: a memory sector never holds entries of two fronts (the dataflow
+    // factorisation reads finished panels through L1 while other fronts are still being written)
+    S.panel_off[s + 1] = (S.panel_off[s] + (ns + nr) * ns + 3) & ~(int64_t)3;
+    S.nnzL_stored += (ns + nr) * ns;
     S.flops_stored += (double)ns * ns * ns / 3.0 + (double)ns * ns * nr + (double)ns * nr * nr;
   }
-  S.nnzL_stored = S.panel_off[nsup];
+  S.L_alloc = S.panel_off[nsup];
   S.sn_level.assign(nsup, 0);
   int nlev = 0;
   for (int s = 0; s < nsup; s++) {

@@ -61,6 +61,7 @@ struct Symbolic {
   std::vector<int64_t> upd_off;    // [nsup] doubles; update matrix nr x nr column major
   int64_t upd_total = 0;           // doubles needed for the update-matrix arena
   int64_t nnzL_stored = 0;         // panel entries actually stored
+  int64_t L_alloc = 0;             // doubles to allocate for the panels (32-byte aligned starts)
 
   // assembly of the original entries: per task CSR list of (src entry in caller
   // order, destination offset inside the task's panel)

@@ -54,6 +54,7 @@ int64_t csym_scalar(const csym_handle* h, int which) {
     case 7: return S.nnzA;
     case 8: return (int64_t)S.sn_rows.size();
     case 9: return (int64_t)S.child_list.size();
+    case 10: return S.L_alloc;
   }
   return -1;
 }

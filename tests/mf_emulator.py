@@ -6,7 +6,7 @@ import numpy as np
 
 def factor(S, vals, dsigns_perm, eps=1e-13, delta=2e-7, reg=True):
     n, nsup = S.n, S.nsup
-    Lpan = np.zeros(S.nnzL_stored)
+    Lpan = np.zeros(S.L_alloc)
     U = np.zeros(max(S.upd_total, 1))
     D = np.zeros(n)
     regcount = 0

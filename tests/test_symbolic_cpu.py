@@ -115,3 +115,38 @@ def test_amd_quality_on_arrow_and_grid():
     assert amd.nnzL < 0.6 * nat
     assert nd.nnzL < 0.8 * nat
     assert nd.nlevels <= amd.nlevels * 2 + 50
+
+
+@pytest.mark.parametrize("ordering", [cb.ORDER_AMD, cb.ORDER_ND])
+def test_update_arena_is_safe_without_level_barriers(ordering):
+    """Two update matrices may share arena space only if one front is a proper ancestor of the other's PARENT
+    (then the dependency graph itself orders the reuse after the last read): the numeric phase runs as a
+    dataflow graph with no level barriers."""
+    N, cp, rv, nz, ds = small_kkt(1500, 2500, seed=5, window=40)
+    S = cb.SymbolicAnalysis(N, cp, rv, ordering=ordering, max_panel=16, nd_leaf=32)
+    nr = np.diff(S.sn_rowptr)
+    size = nr * nr
+    live = np.where(size > 0)[0]
+    order = live[np.argsort(S.upd_off[live], kind="stable")]
+    assert S.upd_total >= int((S.upd_off[live] + size[live]).max())
+
+    def is_proper_ancestor(a, s):      # a above s
+        s = S.sn_parent[s]
+        while s >= 0:
+            if s == a:
+                return True
+            s = S.sn_parent[s]
+        return False
+
+    active = []                        # sweep over offsets
+    overlaps = 0
+    for s in order:
+        lo, hi = S.upd_off[s], S.upd_off[s] + size[s]
+        active = [t for t in active if S.upd_off[t] + size[t] > lo]
+        for t in active:
+            overlaps += 1
+            pt, ps = S.sn_parent[t], S.sn_parent[s]
+            ok = (pt >= 0 and is_proper_ancestor(s, pt)) or (ps >= 0 and is_proper_ancestor(t, ps))
+            assert ok, (s, t)
+        active.append(s)
+    assert overlaps > 0                # the arena does recycle space
