@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int2* __restr
     // ns <= 64: each lane owns entries lane and lane+32
     double y0 = lane < ns ? xp[f + lane] : 0.0;
     double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
+    __syncwarp();   // the shuffles below need a converged warp: a diverged one takes the slow per-thread path
     for (int j = 0; j < ns; j++) {
       const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
       const double* lj = sL + j * CB_PB_LD;
@@ -589,6 +590,7 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_small(LDLDev d, const int* __rest
     const double* __restrict__ cj = P + (long long)j * ld + ns;
     double acc = 0.0;
     for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
+    __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
@@ -643,6 +645,7 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restr
     } else {
       for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
     }
+    __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
@@ -651,6 +654,7 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restr
   if (tid < 32) {
     double y0 = lane < ns ? st[lane] : 0.0;
     double y1 = lane + 32 < ns ? st[lane + 32] : 0.0;
+    __syncwarp();   // the shuffles below need a converged warp: a diverged one takes the slow per-thread path
     for (int j = ns - 1; j > 0; j--) {
       const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
       // L11[j][i] = sL[i*LD + j]
@@ -673,6 +677,11 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restr
 // with ld.global.cg (L2), written once before its consumers are released (threadfence + atomic).
 // No floating-point atomics: results are bit-identical to the level-synchronous kernels.
 // ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long df_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void df_wait_zero(volatile int* p) {
   unsigned ns = 20;
   while (*p > 0) { __nanosleep(ns); if (ns < 640) ns <<= 1; }
@@ -682,6 +691,8 @@ __device__ __forceinline__ void df_wait_set(volatile int* p) {
   while (*p == 0) { __nanosleep(ns); if (ns < 640) ns <<= 1; }
 }
 
+__shared__ unsigned long long* df_trk;
+#define SV_STAMP(slot) do { if (threadIdx.x == 0 && df_trk) df_trk[slot] = df_gtime(); } while (0)
 __device__ void df_fwd_small(const LDLDev& d, int s, double* __restrict__ xp, int lane) {
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
@@ -709,54 +720,6 @@ __device__ void df_fwd_small(const LDLDev& d, int s, double* __restrict__ xp, in
   }
 }
 
-__device__ void df_fwd_big(const LDLDev& d, int s, double* __restrict__ xp, double* sL, double* sy) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  double* us = d.u + rp;
-  {
-    const int* __restrict__ gp = d.gat_ptr + (f + rp);
-    for (int p = tid; p < ld; p += SV_NT) {
-      double acc = 0.0;
-      for (int e = gp[p]; e < gp[p + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
-      if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
-    }
-  }
-  __syncthreads();
-  if (tid < 32) {
-    double y0 = lane < ns ? xp[f + lane] : 0.0;
-    double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
-    for (int j = 0; j < ns; j++) {
-      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
-      const double* lj = sL + j * CB_PB_LD;
-      if (lane > j && lane < ns) y0 -= lj[lane] * xj;
-      if (lane + 32 > j && lane + 32 < ns) y1 -= lj[lane + 32] * xj;
-    }
-    if (lane < ns) { sy[lane] = y0; xp[f + lane] = y0; }
-    if (lane + 32 < ns) { sy[lane + 32] = y1; xp[f + lane + 32] = y1; }
-  }
-  __syncthreads();
-  for (int a = tid; a < nr; a += SV_NT) {
-    const double* __restrict__ pa = P + ns + a;
-    double acc = 0.0;
-    int j0 = 0;
-    for (; j0 + 16 <= ns; j0 += 16) {
-      double v[16];
-#pragma unroll
-      for (int jj = 0; jj < 16; jj++) v[jj] = pa[(long long)(j0 + jj) * ld];
-      asm volatile("" ::: "memory");
-#pragma unroll
-      for (int jj = 0; jj < 16; jj++) acc += v[jj] * sy[j0 + jj];
-    }
-    for (; j0 < ns; j0++) acc += pa[(long long)j0 * ld] * sy[j0];
-    us[a] -= acc;
-  }
-}
-
 __device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, double* __restrict__ out, int lane) {
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
@@ -769,6 +732,7 @@ __device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, do
     const double* __restrict__ cj = P + (long long)j * ld + ns;
     double acc = 0.0;
     for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
+    __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
@@ -782,9 +746,99 @@ __device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, do
   for (int j = lane; j < ns; j += 32) out[d.perm[f + j]] = xp[f + j];
 }
 
-__device__ void df_bwd_big(const LDLDev& d, int s, double* __restrict__ xp, double* __restrict__ out,
-                           double* sL, double* st, double* sx) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SV_NT >> 5;
+// ---- wide fronts, pipelined along supernode chains ----
+// A wide front publishes its update vector in blocks of 64 rows (prog[s] = blocks finished).  The parent of a
+// chain child (rows(child) == cols(parent) + rows(parent)) follows that counter instead of waiting for the whole
+// child: it can factor out its pivot block as soon as the child's first rows are final, so a chain of D panels
+// with B row blocks costs ~(D + B) block steps instead of D * B.  The backward sweep does the same in the other
+// direction: a front folds in the rows owned by far ancestors while the near ones are still being solved; only
+// the last 64 rows and the pivot block sit on the critical path.
+#define SV_RB 64
+
+__device__ __forceinline__ void df_wait_ge(volatile int* p, int v) {
+  unsigned ns = 20;
+  while (*p < v) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
+}
+
+__device__ void df_fwd_wide(const LDLDev& d, const DFPlan& q, int s, int k, double* __restrict__ xp, double* sL,
+                            double* sy, double* sred) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* us = d.u + rp;
+  const int* __restrict__ gp = d.gat_ptr + (f + rp);
+  const int c = q.chain_child[s];
+  int cblk = 0;
+  if (c >= 0) cblk = ((int)(d.sn_rowptr[c + 1] - d.sn_rowptr[c]) + SV_RB - 1) / SV_RB;
+  if (tid == 0) {
+    df_wait_zero(q.pend + k);
+    if (c >= 0) df_wait_ge(q.prog + c, min(cblk, (ns - 1) / SV_RB + 1));
+    __threadfence();
+    if (df_trk) df_trk[1] = df_gtime();
+  }
+  __syncthreads();
+  if (tid < ns) {
+    double acc = 0.0;
+    for (int e = gp[tid]; e < gp[tid + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
+    xp[f + tid] += acc;
+  }
+  __syncthreads();
+  SV_STAMP(3);
+  if (tid < 32) {
+    double y0 = lane < ns ? xp[f + lane] : 0.0;
+    double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
+    __syncwarp();
+    for (int j = 0; j < ns; j++) {
+      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+      const double* lj = sL + j * CB_PB_LD;
+      if (lane > j && lane < ns) y0 -= lj[lane] * xj;
+      if (lane + 32 > j && lane + 32 < ns) y1 -= lj[lane + 32] * xj;
+    }
+    sy[lane] = lane < ns ? y0 : 0.0;
+    sy[lane + 32] = lane + 32 < ns ? y1 : 0.0;
+    if (lane < ns) xp[f + lane] = y0;
+    if (lane + 32 < ns) xp[f + lane + 32] = y1;
+  }
+  __syncthreads();
+  SV_STAMP(4);
+  const int r = tid & (SV_RB - 1), cq = tid >> 6;      // row of the block, quarter of the pivot columns
+  const int nblk = (nr + SV_RB - 1) / SV_RB;
+  int seen = 0;                                         // thread 0: chain child's progress already observed
+  for (int b = 0; b < nblk; b++) {
+    const int r0 = b * SV_RB;
+    const int a = r0 + r;
+    // the panel is static: its loads go out before the wait on the child
+    double v[16];
+    const double* __restrict__ pa = P + ns + a + (long long)(16 * cq) * ld;
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++) v[jj] = (a < nr && 16 * cq + jj < ns) ? pa[(long long)jj * ld] : 0.0;
+    if (c >= 0) {
+      const int need = min(cblk, (ns + min(nr, r0 + SV_RB) - 1) / SV_RB + 1);
+      if (tid == 0 && seen < need) { df_wait_ge(q.prog + c, need); seen = need; __threadfence(); }
+      __syncthreads();
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++) part += v[jj] * sy[(16 * cq + jj) & (CB_PB_MAXNS - 1)];
+    double g = 0.0;
+    if (cq == 0 && a < nr) {
+      for (int e = gp[ns + a]; e < gp[ns + a + 1]; e++) g += __ldcg(d.u + d.gat_src[e]);
+    }
+    sred[cq * SV_RB + r] = part;
+    __syncthreads();
+    if (cq == 0 && a < nr) us[a] = g - (((sred[r] + sred[SV_RB + r]) + sred[2 * SV_RB + r]) + sred[3 * SV_RB + r]);
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicExch(q.prog + s, b + 1); }
+  }
+}
+
+__device__ void df_bwd_wide(const LDLDev& d, const DFPlan& q, int s, double* __restrict__ xp, double* __restrict__ out,
+                            double* sLt, double* st, double* sred) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -792,45 +846,74 @@ __device__ void df_bwd_big(const LDLDev& d, int s, double* __restrict__ xp, doub
   const int ld = ns + nr;
   const double* __restrict__ P = d.L + d.panel_off[s];
   const int* __restrict__ rows = d.sn_rows + rp;
-  const bool staged = nr <= CB_SOLVE_STAGE;
-  if (staged) for (int a = tid; a < nr; a += SV_NT) sx[a] = __ldcg(xp + rows[a]);
-  __syncthreads();
-  for (int j = warp; j < ns; j += nwarp) {
-    const double* __restrict__ cj = P + (long long)j * ld + ns;
-    double acc = 0.0;
-    if (staged) {
-      int a0 = 0;
-      for (; a0 + 256 <= nr; a0 += 256) {
-        double v[8];
+  const int r = tid & (SV_RB - 1), cq = tid >> 6;
+  const int nblk = (nr + SV_RB - 1) / SV_RB;
+  const int* __restrict__ own = q.blk_owner + q.blk_ptr[s];
+  double acc[16];
 #pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = cj[a0 + q * 32 + lane];
-        asm volatile("" ::: "memory");
+  for (int jj = 0; jj < 16; jj++) acc[jj] = 0.0;
+  int last_owner = -1;
+  bool stamped = false;
+  for (int b = nblk - 1; b >= 0; b--) {
+    const int a = b * SV_RB + r;
+    double v[16];
+    const double* __restrict__ pa = P + ns + a + (long long)(16 * cq) * ld;
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc += v[q] * sx[a0 + q * 32 + lane];
-      }
-      for (int a = a0 + lane; a < nr; a += 32) acc += cj[a] * sx[a];
-    } else {
-      for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
+    for (int jj = 0; jj < 16; jj++) v[jj] = (a < nr && 16 * cq + jj < ns) ? pa[(long long)jj * ld] : 0.0;
+    const int row = a < nr ? rows[a] : 0;
+    const int o = own[b];
+    if (o != last_owner) {
+      if (tid == 0) { df_wait_set(q.done + o); __threadfence(); if (df_trk && !stamped) df_trk[1] = df_gtime(); }
+      stamped = true;
+      last_owner = o;
+      __syncthreads();
     }
+    const double xv = a < nr ? __ldcg(xp + row) : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
+    for (int jj = 0; jj < 16; jj++) acc[jj] += v[jj] * xv;
+  }
+  if (nblk == 0 && tid == 0) {
+    const int p = q.parent[s];
+    if (p >= 0) df_wait_set(q.done + p);
+    __threadfence();
+    if (df_trk) df_trk[1] = df_gtime();
+  }
+  SV_STAMP(3);
+  // column sums: butterfly over the 32 rows a warp holds, then the two row halves through shared memory
+  __syncwarp();
+#pragma unroll
+  for (int jj = 0; jj < 16; jj++) {
+    double t = acc[jj];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    acc[jj] = t;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++) sred[(warp & 1) * CB_PB_MAXNS + 16 * cq + jj] = acc[jj];
   }
   __syncthreads();
+  if (tid < ns) st[tid] = __ldcg(xp + f + tid) * d.Dinv[f + tid] - (sred[tid] + sred[CB_PB_MAXNS + tid]);
+  __syncthreads();
+  SV_STAMP(4);
   if (tid < 32) {
     double y0 = lane < ns ? st[lane] : 0.0;
     double y1 = lane + 32 < ns ? st[lane + 32] : 0.0;
+    __syncwarp();
     for (int j = ns - 1; j > 0; j--) {
       const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
-      if (lane < j) y0 -= sL[lane * CB_PB_LD + j] * xj;
-      if (lane + 32 < j) y1 -= sL[(lane + 32) * CB_PB_LD + j] * xj;
+      const double* lj = sLt + j * CB_PB_LD;     // row j of L11: L[j][i], i < j
+      if (lane < j) y0 -= lj[lane] * xj;
+      if (lane + 32 < j) y1 -= lj[lane + 32] * xj;
     }
     if (lane < ns) { xp[f + lane] = y0; out[d.perm[f + lane]] = y0; }
     if (lane + 32 < ns) { xp[f + lane + 32] = y1; out[d.perm[f + lane + 32]] = y1; }
   }
 }
 
-// load the unit-lower pivot block of front s into shared memory (static data: can run before the wait)
+// load the unit-lower pivot block of front s into shared memory (static data: can run before the wait);
+// TRANS stores row-major (sL[i][j] = L[i][j]) for the backward sweep, which walks rows
+template <bool TRANS>
 __device__ __forceinline__ void df_load_pivot(const LDLDev& d, int s, double* sL) {
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
@@ -838,7 +921,8 @@ __device__ __forceinline__ void df_load_pivot(const LDLDev& d, int s, double* sL
   const double* __restrict__ P = d.L + d.panel_off[s];
   for (int idx = threadIdx.x; idx < ns * ns; idx += SV_NT) {
     const int j = idx / ns, i = idx - j * ns;
-    sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
+    if (TRANS) sL[i * CB_PB_LD + j] = P[(long long)j * ld + i];
+    else sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
   }
 }
 
@@ -846,50 +930,42 @@ template <bool FWD>
 __global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* __restrict__ xp, double* __restrict__ out) {
   __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
   __shared__ double sv[CB_PB_MAXNS];
-  __shared__ double sx[CB_SOLVE_STAGE];
-  __shared__ int s_task;
+  __shared__ double sred[4 * SV_RB];
+  __shared__ int s_task, s_prev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_prev = -1;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_task = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
+    if (tid == 0) {
+      if (q.trace && s_prev >= 0) q.trace[6 * ((size_t)(FWD ? 0 : q.ntask) + s_prev) + 2] = df_gtime();
+      s_task = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
+      s_prev = s_task < q.ntask ? (FWD ? s_task : q.ntask - 1 - s_task) : -1;
+      if (q.trace && s_prev >= 0) q.trace[6 * ((size_t)(FWD ? 0 : q.ntask) + s_prev)] = df_gtime();
+    }
     __syncthreads();
     const int qi = s_task;
     if (qi >= q.ntask) break;
     const int k = FWD ? qi : q.ntask - 1 - qi;
+    if (tid == 0) df_trk = q.trace ? q.trace + 6 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
+    unsigned long long* trk = q.trace ? q.trace + 6 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
     const int first = q.task_first[k], cnt = q.task_cnt[k], kind = q.task_kind[k];
     if (kind == 1) {
       const int s = q.fronts[first];
-      df_load_pivot(d, s, sL);                     // overlaps with the wait below
-      {
-        // pull the (static) rows-below part of the panel towards L2 while the dependencies resolve
-        const int ns_ = d.sn_first[s + 1] - d.sn_first[s];
-        const long long ld_ = ns_ + (d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-        const char* pb = (const char*)(d.L + d.panel_off[s]);
-        const long long bytes = ld_ * ns_ * 8;
-        for (long long o = (long long)tid * 128; o < bytes; o += (long long)SV_NT * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
-      }
-      if (tid == 0) {
-        if (FWD) df_wait_zero(q.pend + k);
-        else { const int p = q.parent[s]; if (p >= 0) df_wait_set(q.done + p); }
-        __threadfence();
-      }
+      df_load_pivot<!FWD>(d, s, sL);               // overlaps with the waits inside
       __syncthreads();
-      if (FWD) df_fwd_big(d, s, xp, sL, sv);
-      else df_bwd_big(d, s, xp, out, sL, sv, sx);
-      __threadfence();   // every thread publishes its own global writes before the release below
+      if (FWD) df_fwd_wide(d, q, s, k, xp, sL, sv, sred);
+      else df_bwd_wide(d, q, s, xp, out, sL, sv, sred);
       __syncthreads();
       if (tid == 0) {
         __threadfence();
-        if (FWD) { const int p = q.parent[s]; if (p >= 0) atomicSub(q.pend + q.front2task[p], 1); }
+        if (FWD) { const int p = q.parent[s]; if (p >= 0 && q.chain_child[p] != s) atomicSub(q.pend + q.front2task[p], 1); }
         else atomicExch(q.done + s, 1);
       }
     } else {
       if (FWD) {
-        if (tid == 0) { df_wait_zero(q.pend + k); __threadfence(); }
+        if (tid == 0) { df_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
         __syncthreads();
         if (warp < cnt) df_fwd_small(d, q.fronts[first + warp], xp, lane);
-        __threadfence();
         __syncthreads();
         if (tid < cnt) {
           __threadfence();
@@ -902,7 +978,6 @@ __global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* 
           if (lane == 0) { const int p = q.parent[s]; if (p >= 0) df_wait_set(q.done + p); __threadfence(); }
           __syncwarp();
           df_bwd_small(d, s, xp, out, lane);
-          __threadfence();
           __syncwarp();
           if (lane == 0) { __threadfence(); atomicExch(q.done + s, 1); }
         }
@@ -949,12 +1024,6 @@ __device__ __forceinline__ void df_apply_sorted(double* base, const double* __re
     const long long t = map(dd);
     if (t >= 0) base[t] += acc;
   }
-}
-
-__device__ __forceinline__ unsigned long long df_gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
 }
 
 __shared__ int df_cur_qi;
@@ -1072,6 +1141,7 @@ __device__ __forceinline__ void df_add_child(const LDLDev& d, const DFChildRec& 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int* __restrict__ relc = d.rel + ch.relp;
   const double* Uc = d.U + ch.uoff;
+  __syncwarp();
   if (ch.p0 == 3) {
     // rows and columns of the block are contiguous in the target (the previous panel of the same separator,
     // dense children): no index loads, warp-wide coalesced reads down the columns this warp owns
@@ -1939,8 +2009,30 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       }
     }
     const int nt = (int)t_first.size();
+    // chain children of wide fronts (followed block by block instead of awaited), block owners for the
+    // backward sweep
+    std::vector<int> chain_child(S.nsup, -1), col2sn(n, 0), blk_ptr(S.nsup + 1, 0), blk_owner;
+    for (int s = 0; s < S.nsup; s++)
+      for (int j = S.sn_first[s]; j < S.sn_first[s + 1]; j++) col2sn[j] = s;
+    auto wide = [&](int s) { return S.sn_first[s + 1] - S.sn_first[s] > CB_SOLVE_SMALL_NS; };
+    for (int c = 0; c < S.nsup; c++) {
+      const int p = S.sn_parent[c];
+      if (p < 0 || !wide(c) || !wide(p) || chain_child[p] >= 0) continue;
+      const int64_t nrc = S.sn_rowptr[c + 1] - S.sn_rowptr[c];
+      const int64_t nsp = S.sn_first[p + 1] - S.sn_first[p], nrp = S.sn_rowptr[p + 1] - S.sn_rowptr[p];
+      if (nrc == nsp + nrp) chain_child[p] = c;       // rows(c) is a subset of cols(p)+rows(p): equal sizes = equal sets
+    }
+    for (int s = 0; s < S.nsup; s++) {
+      blk_ptr[s] = (int)blk_owner.size();
+      if (!wide(s)) continue;
+      for (int64_t t = S.sn_rowptr[s]; t < S.sn_rowptr[s + 1]; t += 64) blk_owner.push_back(col2sn[S.sn_rows[t]]);
+    }
+    blk_ptr[S.nsup] = (int)blk_owner.size();
     std::vector<int> pend(nt, 0);
-    for (int s = 0; s < S.nsup; s++) if (S.sn_parent[s] >= 0) pend[f2t[S.sn_parent[s]]]++;
+    for (int s = 0; s < S.nsup; s++) {
+      const int p = S.sn_parent[s];
+      if (p >= 0 && chain_child[p] != s) pend[f2t[p]]++;
+    }
     int* t1 = nullptr;
     if ((rc = upload(&t1, t_first))) return rc; df.task_first = t1;
     if ((rc = upload(&t1, t_cnt))) return rc; df.task_cnt = t1;
@@ -1949,6 +2041,10 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     if ((rc = upload(&t1, f2t))) return rc; df.front2task = t1;
     if ((rc = upload(&t1, S.sn_parent))) return rc; df.parent = t1;
     if ((rc = upload(&t1, pend))) return rc; d_pend_init = t1;
+    if ((rc = upload(&t1, chain_child))) return rc; df.chain_child = t1;
+    if ((rc = upload(&t1, blk_ptr))) return rc; df.blk_ptr = t1;
+    if ((rc = upload(&t1, blk_owner))) return rc; df.blk_owner = t1;
+    CK(cudaMalloc((void**)&df.prog, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
     CK(cudaMalloc((void**)&df.pend, (size_t)(nt ? nt : 1) * sizeof(int)));
     CK(cudaMalloc((void**)&df.done, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
     CK(cudaMalloc((void**)&df.qhead, 2 * sizeof(int)));
@@ -1960,7 +2056,15 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false>, SV_NT, 0));
     occ = std::max(1, std::min(occ, occ2));
     df_grid = nsm * occ;
+    if (const char* e = std::getenv("CB_DF_GRID")) df_grid = std::max(1, std::atoi(e));
     use_dataflow = std::getenv("CB_SOLVE_LEVELSYNC") == nullptr;
+    if (std::getenv("CB_DF_TRACE_SOLVE") && nt > 0) {
+      CK(cudaMalloc((void**)&df.trace, (size_t)nt * 12 * sizeof(unsigned long long)));
+      CK(cudaMemset(df.trace, 0, (size_t)nt * 12 * sizeof(unsigned long long)));
+      h_df_fronts_first.resize(nt);
+      for (int i = 0; i < nt; i++) h_df_fronts_first[i] = fronts[t_first[i]];
+      h_df_kind = t_kind;
+    }
   }
   // dataflow factorisation plan (k_factor_df): level 0's small fronts keep their level-synchronous launch
   // (no dependencies, ~10^5 tiny CTAs); everything else becomes queue tasks in level order.  Every task
@@ -2115,7 +2219,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(df.trace); fr(df.chain_child); fr(df.blk_ptr); fr(df.blk_owner); fr(df.prog); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -2190,6 +2294,7 @@ int LDLObject::solve_async(double* d_x, const double* d_b) {
     g_launches += 2;
     CK(cudaMemcpyAsync(df.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemsetAsync(df.done, 0, (size_t)S.nsup * sizeof(int), stream));
+    CK(cudaMemsetAsync(df.prog, 0, (size_t)S.nsup * sizeof(int), stream));
     CK(cudaMemsetAsync(df.qhead, 0, 2 * sizeof(int), stream));
     k_solve_df<true><<<df_grid, SV_NT, 0, stream>>>(dev, df, d_xp, d_x);
     k_solve_df<false><<<df_grid, SV_NT, 0, stream>>>(dev, df, d_xp, d_x);
@@ -2357,7 +2462,20 @@ int cldl_solve(cldl_t* h, double* x, const double* b) {
   int rc = o.solve_async(o.d_bx + o.n, o.d_bx);
   if (rc) return rc;
   if (cudaMemcpyAsync(x, o.d_bx + o.n, bytes, cudaMemcpyDeviceToHost, o.stream) != cudaSuccess) return CLDL_E_CUDA;
-  return cudaStreamSynchronize(o.stream) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+  if (cudaStreamSynchronize(o.stream) != cudaSuccess) return CLDL_E_CUDA;
+  if (o.df.trace && o.use_dataflow) {   // diagnostic: CB_DF_TRACE_SOLVE=<file> dumps the last solve's task timeline
+    const long long nt = o.df.ntask;
+    std::vector<unsigned long long> tr((size_t)nt * 12);
+    cudaMemcpy(tr.data(), o.df.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (FILE* fp = std::fopen(std::getenv("CB_DF_TRACE_SOLVE"), "wb")) {
+      std::fwrite(&nt, sizeof(nt), 1, fp);
+      std::fwrite(o.h_df_fronts_first.data(), sizeof(int), (size_t)nt, fp);
+      std::fwrite(o.h_df_kind.data(), sizeof(int), (size_t)nt, fp);
+      std::fwrite(tr.data(), sizeof(unsigned long long), tr.size(), fp);
+      std::fclose(fp);
+    }
+  }
+  return CLDL_OK;
 }
 
 void cldl_info(const cldl_t* h, cldl_info_t* info) {

@@ -73,6 +73,11 @@ struct DFPlan {
   int* pend = nullptr;               // forward counters (reset from pend_init before every sweep)
   int* done = nullptr;               // backward: per front done flag
   int* qhead = nullptr;              // [2] queue heads (forward, backward)
+  const int* chain_child = nullptr;  // [nsup] wide child whose rows are exactly cols+rows of this front, or -1
+  int* prog = nullptr;               // [nsup] forward: 64-row blocks of the update vector already final
+  const int* blk_ptr = nullptr;      // [nsup+1] into blk_owner
+  const int* blk_owner = nullptr;    // per 64-row block of a wide front: front owning the block's first row
+  unsigned long long* trace = nullptr;  // optional [2][ntask][4]: grab, ready, end (globaltimer ns), mid
 };
 
 
@@ -106,6 +111,7 @@ class LDLObject {
   DFFactor dff;
   int *d_dff_init = nullptr, *d_dff_cnt = nullptr;
   std::vector<int> h_dff_tasks;
+  std::vector<int> h_df_fronts_first, h_df_kind;
   int dff_grid = 0;
   size_t dff_nsup4 = 0;
   bool factor_dataflow = true;

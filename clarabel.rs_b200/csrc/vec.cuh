@@ -40,16 +40,19 @@ struct ReduceWS {
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
+  __syncwarp();   // a diverged warp takes the slow shuffle path
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 __device__ __forceinline__ double warp_max(double v) {
+  __syncwarp();   // a diverged warp takes the slow shuffle path
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ double warp_min(double v) {
+  __syncwarp();   // a diverged warp takes the slow shuffle path
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
