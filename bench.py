@@ -135,11 +135,21 @@ def run_ours(args, rank, world):
     h2d_bytes = (P.data.nbytes + P.indices.size * 4 + A.data.nbytes * 2 + A.indices.size * 8 + 8 * (n + m) * 2)
 
     # ---------------- e2e through the public API from host buffers ----------------
+    # warm the process (CUDA module load, allocator pools) on a tiny problem so that the end-to-end number below
+    # is the cost of a new problem in a running process, not of the first CUDA call
+    from helpers import workloads as _wl
+    _pw = _wl.random_sparse_qp(n=300, m=500, nnz_per_row=4, seed=99, window=40)
+    for _ in range(2):
+        _sw = cb.CudaSolver(_pw["P"], _pw["q"], _pw["A"], _pw["b"], _pw["cones"], device=dev_index)
+        _sw.solve()
+        _sw.close()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    solver = cb.CudaSolver(P, q, A, b, cones, ordering=cb.ORDER_ND, device=dev_index)
+    # C2's sliding-window structure is a nested-dissection case; the other configs let the backend compare AMD and ND
+    ordering = cb.ORDER_ND if args.workload.startswith("c2") else cb.ORDER_BEST
+    solver = cb.CudaSolver(P, q, A, b, cones, ordering=ordering, device=dev_index)
     t_setup = time.perf_counter() - t0
     res = solver.solve()                      # includes the D2H of (x, z, s)
     torch.cuda.synchronize()
@@ -199,16 +209,25 @@ def run_ours(args, rank, world):
         solves_per_iter = info.n_ldl_solve / max(info.n_refactor, 1)
         share_ref = refactor_ms
         share_sol = ldl_solve_ms * solves_per_iter
-        rf_ref = {"kernel": "k_factor_level (numeric LDL^T refactor, all levels)", "bound": "hbm",
+        rf_ref = {"kernel": "k_factor_df (+ k_factor_level for tree level 0): numeric LDL^T refactor", "bound": "hbm",
                   "achieved": b_ref / (refactor_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                   "frac": b_ref / (refactor_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                   "algorithmic_bytes": b_ref, "ms": refactor_ms, "share_of_step_ms": share_ref,
                   "fp64_gflops": li.flops / (refactor_ms * 1e-3) / 1e9, "peak_source": peak_src}
-        rf_sol = {"kernel": "k_fwd_level + k_bwd_level (one LDL solve, all levels)", "bound": "hbm",
+        rf_sol = {"kernel": "k_solve_df<fwd> + k_solve_df<bwd>: one LDL solve (both sweeps)", "bound": "hbm",
                   "achieved": b_sol / (ldl_solve_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                   "frac": b_sol / (ldl_solve_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                   "algorithmic_bytes": b_sol, "ms": ldl_solve_ms, "share_of_step_ms": share_sol,
                   "peak_source": peak_src}
+        # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/), if any
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr.get("workload") == args.workload:
+                rf_ref["traffic"] = tr.get("refactor_dram_bytes")
+                rf_sol["traffic"] = tr.get("solve_dram_bytes")
+                rf_ref["traffic_source"] = rf_sol["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
         dominant, other = (rf_ref, rf_sol) if share_ref >= share_sol else (rf_sol, rf_ref)
         cpu = cpu_baseline(pr, sample_iters=args.cpu_sample_iters) if (world == 1 and not args.no_cpu_baseline) else None
         out = {
