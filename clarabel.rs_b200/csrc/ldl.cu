@@ -1677,6 +1677,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   if (rc) return CLDL_E_ARG;
 
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
   CK(cudaMallocHost((void**)&h_status, ST_COUNT * sizeof(int)));
@@ -1713,6 +1716,8 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   CK(cudaMalloc((void**)&dev.Dinv, (size_t)n * sizeof(double)));
   CK(cudaMalloc((void**)&dev.u, (size_t)(S.sn_rows.size() ? S.sn_rows.size() : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&d_xp, (size_t)n * sizeof(double)));
+  CK(cudaMalloc((void**)&d_xp2, (size_t)n * sizeof(double)));
+  CK(cudaMalloc((void**)&d_u2, (size_t)(S.sn_rows.size() ? S.sn_rows.size() : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&d_bx, (size_t)2 * n * sizeof(double)));
   CK(cudaMalloc((void**)&dev.status, ST_COUNT * sizeof(int)));
   CK(cudaMemset(dev.status, 0, ST_COUNT * sizeof(int)));
@@ -2045,6 +2050,10 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     if ((rc = upload(&t1, blk_ptr))) return rc; df.blk_ptr = t1;
     if ((rc = upload(&t1, blk_owner))) return rc; df.blk_owner = t1;
     CK(cudaMalloc((void**)&df.prog, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&df2_prog, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&df2_done, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&df2_pend, (size_t)(nt ? nt : 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&df2_qhead, 2 * sizeof(int)));
     CK(cudaMalloc((void**)&df.pend, (size_t)(nt ? nt : 1) * sizeof(int)));
     CK(cudaMalloc((void**)&df.done, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
     CK(cudaMalloc((void**)&df.qhead, 2 * sizeof(int)));
@@ -2219,10 +2228,13 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(df.trace); fr(df.chain_child); fr(df.blk_ptr); fr(df.blk_owner); fr(df.prog); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(df.trace); fr(d_xp2); fr(d_u2); fr(df2_pend); fr(df2_done); fr(df2_prog); fr(df2_qhead); fr(df.chain_child); fr(df.blk_ptr); fr(df.blk_owner); fr(df.prog); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -2284,23 +2296,45 @@ int LDLObject::sync_status() {
   return h_status[ST_NONFINITE] ? 0 : 1;
 }
 
-int LDLObject::solve_async(double* d_x, const double* d_b) {
+int LDLObject::fork_slot1() {
+  CK(cudaEventRecord(ev_fork, stream));
+  CK(cudaStreamWaitEvent(stream2, ev_fork, 0));
+  return CLDL_OK;
+}
+int LDLObject::join_slot1() {
+  CK(cudaEventRecord(ev_join, stream2));
+  CK(cudaStreamWaitEvent(stream, ev_join, 0));
+  return CLDL_OK;
+}
+
+int LDLObject::solve_async(double* d_x, const double* d_b, int slot, bool half) {
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
-  g_launches += 1 + solve_launches;
-  k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
   if (use_dataflow) {
-    g_launches -= solve_launches;
-    g_launches += 2;
-    CK(cudaMemcpyAsync(df.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-    CK(cudaMemsetAsync(df.done, 0, (size_t)S.nsup * sizeof(int), stream));
-    CK(cudaMemsetAsync(df.prog, 0, (size_t)S.nsup * sizeof(int), stream));
-    CK(cudaMemsetAsync(df.qhead, 0, 2 * sizeof(int), stream));
-    k_solve_df<true><<<df_grid, SV_NT, 0, stream>>>(dev, df, d_xp, d_x);
-    k_solve_df<false><<<df_grid, SV_NT, 0, stream>>>(dev, df, d_xp, d_x);
+    cudaStream_t sst = slot ? stream2 : stream;
+    LDLDev dv = dev;
+    DFPlan qv = df;
+    double* xp = d_xp;
+    if (slot) {
+      dv.u = d_u2; xp = d_xp2;
+      qv.pend = df2_pend; qv.done = df2_done; qv.prog = df2_prog; qv.qhead = df2_qhead; qv.trace = nullptr;
+    }
+    const int grid = half ? std::max(1, df_grid / 2) : df_grid;
+    g_launches += 3;
+    k_permute_in<<<(n + 255) / 256, 256, 0, sst>>>(n, dev.perm, d_b, xp);
+    CK(cudaMemcpyAsync(qv.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, sst));
+    CK(cudaMemsetAsync(qv.done, 0, (size_t)S.nsup * sizeof(int), sst));
+    CK(cudaMemsetAsync(qv.prog, 0, (size_t)S.nsup * sizeof(int), sst));
+    CK(cudaMemsetAsync(qv.qhead, 0, 2 * sizeof(int), sst));
+    k_solve_df<true><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+    k_solve_df<false><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
     CK(cudaGetLastError());
     return CLDL_OK;
   }
+  // level-synchronous fallback: one context only, slot 1 simply runs on the main stream after slot 0
+  if (slot) { CK(cudaStreamSynchronize(stream2)); }
+  g_launches += 1 + solve_launches;
+  k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
   for (int l = 0; l < solve_levels; l++) {
     const SolveSeg& g = splan[l];
     if (g.nsmall) k_fwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp);

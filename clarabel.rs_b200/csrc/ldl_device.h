@@ -148,7 +148,16 @@ class LDLObject {
   void release();
   int refactor_async();
   int sync_status();
-  int solve_async(double* d_x, const double* d_b);
+  // slot 1 is a second, independent solve context (own stream, work vectors and dataflow counters): two
+  // right-hand sides can be in flight at once; `half` launches the sweeps on half of the co-resident CTAs so
+  // that two concurrent solves share the machine instead of queueing behind each other
+  int solve_async(double* d_x, const double* d_b, int slot = 0, bool half = false);
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double *d_xp2 = nullptr, *d_u2 = nullptr;
+  int *df2_pend = nullptr, *df2_done = nullptr, *df2_prog = nullptr, *df2_qhead = nullptr;
+  int fork_slot1();   // stream2 waits for everything issued on `stream` so far
+  int join_slot1();   // `stream` waits for everything issued on stream2 so far
   int ensure_tmp(size_t len);
   int stage_index(const uint64_t* index, uint64_t len);
 };

@@ -111,7 +111,7 @@ static void dfree(const void* p) { if (p) cudaFree((void*)p); }
 // scalar slots shared between device reductions and the host
 enum Slot { S_NORMB = 0, S_NORME, S_MAXDIAG, S_QX, S_BZ, S_SZ, S_XPX, S_ALPHA, S_MARG0, S_MARG1,
             S_D0, S_D1, S_D2, S_D3, S_D4, S_D5, S_D6, S_D7, S_N0, S_N1, S_N2, S_N3, S_N4, S_N5, S_N6, S_N7,
-            S_COUNT = 32 };
+            S_NORMB2, S_NORME2, S_COUNT = 32 };
 
 struct Scalars {
   double* d = nullptr;  // device [S_COUNT]
@@ -199,6 +199,7 @@ class KKTDevice {
   double* d_sval = nullptr;
   int64_t nnzS = 0;
   double *d_Hs = nullptr, *d_x = nullptr, *d_b = nullptr, *d_w1 = nullptr, *d_w2 = nullptr;
+  double *d_x2 = nullptr, *d_b2 = nullptr, *d_w1b = nullptr, *d_w2b = nullptr;   // second right-hand side in flight
   int64_t n_refactor = 0, n_ldl_solve = 0, n_ir_steps = 0;
 
   int assemble(const HostCsc& P, const HostCsc& A);
@@ -207,7 +208,11 @@ class KKTDevice {
   void release();
   int update();                                      // -> 1 ok / 0 failed / <0 error
   void setrhs(const double* rx, const double* rz);
+  void setrhs2(const double* rx, const double* rz);  // right-hand side of the second system of solve2
   int solve(double* lhsx, double* lhsz);             // -> 1 ok / 0 failed / <0 error
+  // two systems with the same matrix at once (rhs from setrhs / setrhs2): the LDL sweeps of both run
+  // concurrently on two streams, iterative refinement proceeds in lockstep with one host round trip per round
+  int solve2(double* ax, double* az, double* bx, double* bz);
   void update_vals(const int* d_map, const double* d_src, int len);
   CsrDev symK() const { CsrDev M; M.nrows = N; M.rowptr = d_srow; M.col = d_scol; M.val = d_sval; return M; }
 };
@@ -356,6 +361,8 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
   SCK(cudaMalloc((void**)&d_Hs, (size_t)(cones->nHs ? cones->nHs : 1) * 8));
   SCK(cudaMalloc((void**)&d_x, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_b, (size_t)N * 8));
   SCK(cudaMalloc((void**)&d_w1, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_w2, (size_t)N * 8));
+  SCK(cudaMalloc((void**)&d_x2, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_b2, (size_t)N * 8));
+  SCK(cudaMalloc((void**)&d_w1b, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_w2b, (size_t)N * 8));
   SCK(cudaMemset(d_x, 0, (size_t)N * 8)); SCK(cudaMemset(d_b, 0, (size_t)N * 8));
   return 0;
 }
@@ -364,6 +371,7 @@ void KKTDevice::release() {
   dfree(d_map_P); dfree(d_map_A); dfree(d_map_Hs); dfree(d_map_u); dfree(d_map_v); dfree(d_map_D);
   dfree(d_map_diag); dfree(d_dsigns); dfree(d_srow); dfree(d_scol); dfree(d_sidx); dfree(d_sval);
   dfree(d_Hs); dfree(d_x); dfree(d_b); dfree(d_w1); dfree(d_w2);
+  dfree(d_x2); dfree(d_b2); dfree(d_w1b); dfree(d_w2b);
   ldl.release();
 }
 
@@ -452,6 +460,93 @@ int KKTDevice::solve(double* lhsx, double* lhsz) {
   return 1;
 }
 
+void KKTDevice::setrhs2(const double* rx, const double* rz) {
+  V.copy(d_b2, rx, n);
+  V.copy(d_b2 + n, rz, m);
+  V.zero(d_b2 + n + m, p);
+}
+
+int KKTDevice::solve2(double* ax, double* az, double* bx, double* bz) {
+  if (!set.iterative_refinement_enable || !ldl.use_dataflow) {   // plain path: one after the other
+    int ok = solve(ax, az);
+    if (ok != 1) return ok;
+    std::swap(d_b, d_b2);
+    ok = solve(bx, bz);
+    std::swap(d_b, d_b2);
+    return ok;
+  }
+  int rc;
+  // per-system state: k = 0 uses (d_b, d_x, d_w1, d_w2), k = 1 the second set
+  double* B[2] = {d_b, d_b2};
+  double* X[2] = {d_x, d_x2};
+  double* DX[2] = {d_w2, d_w2b};
+  double* E[2] = {d_w1, d_w1b};
+  const int SB[2] = {S_NORMB, S_NORMB2}, SE[2] = {S_NORME, S_NORME2};
+  const CsrDev K = symK();
+  const unsigned grid = (N + 127) / 128;
+  // first solves, concurrently
+  if ((rc = ldl.fork_slot1())) return rc;
+  if ((rc = ldl.solve_async(X[0], B[0], 0, true))) return rc;
+  if ((rc = ldl.solve_async(X[1], B[1], 1, true))) return rc;
+  if ((rc = ldl.join_slot1())) return rc;
+  n_ldl_solve += 2;
+  for (int k = 0; k < 2; k++) {
+    V.norm_inf(B[k], N, sc->d + SB[k]);
+    g_launches++;
+    k_kkt_residual<<<grid, 128, 0, st>>>(K, E[k], B[k], X[k]);
+    V.norm_inf(E[k], N, sc->d + SE[k]);
+  }
+  if ((rc = sc->fetch())) return rc;
+  double normb[2] = {sc->h[SB[0]], sc->h[SB[1]]}, norme[2] = {sc->h[SE[0]], sc->h[SE[1]]};
+  bool ok[2] = {true, true}, active[2] = {true, true};
+  for (int k = 0; k < 2; k++) if (!std::isfinite(norme[k])) { ok[k] = false; active[k] = false; }
+  for (int it = 0; it < set.iterative_refinement_max_iter; it++) {
+    for (int k = 0; k < 2; k++)
+      if (active[k] && norme[k] <= set.iterative_refinement_abstol + set.iterative_refinement_reltol * normb[k]) active[k] = false;
+    if (!active[0] && !active[1]) break;
+    const double last[2] = {norme[0], norme[1]};
+    if (active[0] && active[1]) {
+      if ((rc = ldl.fork_slot1())) return rc;
+      if ((rc = ldl.solve_async(DX[0], E[0], 0, true))) return rc;
+      if ((rc = ldl.solve_async(DX[1], E[1], 1, true))) return rc;
+      if ((rc = ldl.join_slot1())) return rc;
+    } else {
+      const int k = active[0] ? 0 : 1;
+      if ((rc = ldl.solve_async(DX[k], E[k], 0, false))) return rc;
+    }
+    for (int k = 0; k < 2; k++) {
+      if (!active[k]) continue;
+      n_ldl_solve++; n_ir_steps++;
+      V.axpby(DX[k], 1.0, X[k], 1.0, N);
+      g_launches++;
+      k_kkt_residual<<<grid, 128, 0, st>>>(K, E[k], B[k], DX[k]);
+      V.norm_inf(E[k], N, sc->d + SE[k]);
+    }
+    if ((rc = sc->fetch())) return rc;
+    for (int k = 0; k < 2; k++) {
+      if (!active[k]) continue;
+      norme[k] = sc->h[SE[k]];
+      if (!std::isfinite(norme[k])) { ok[k] = false; active[k] = false; continue; }
+      const double ratio = last[k] / norme[k];
+      if (ratio < set.iterative_refinement_stop_ratio) {
+        if (ratio > 1.0) std::swap(X[k], DX[k]);
+        active[k] = false;
+        continue;
+      }
+      std::swap(X[k], DX[k]);
+    }
+  }
+  // keep the buffer roles consistent for the next call (as in solve)
+  if (X[0] != d_x) { d_w2 = d_x; d_x = X[0]; }
+  if (X[1] != d_x2) { d_w2b = d_x2; d_x2 = X[1]; }
+  if (!ok[0] || !ok[1]) return 0;
+  if (ax) V.copy(ax, d_x, n);
+  if (az) V.copy(az, d_x + n, m);
+  if (bx) V.copy(bx, d_x2, n);
+  if (bz) V.copy(bz, d_x2 + n, m);
+  return 1;
+}
+
 // ------------------------------------------------------------------ the IPM
 enum { IST_UNSOLVED = 0, IST_SOLVED, IST_PINF, IST_DINF, IST_ALMOST_SOLVED, IST_ALMOST_PINF, IST_ALMOST_DINF,
        IST_MAXIT, IST_MAXTIME, IST_NUMERR, IST_INSUFF };
@@ -506,7 +601,9 @@ class IPM {
   void info_update(double t0);
   void check_convergence(double tga, double tgr, double tf, double tia, double tir, double tkt, int s1, int s2, int s3);
   bool check_termination(int iter);
-  int kkt_update();
+  int kkt_update(bool with_affine = false);
+  bool affine_presolved = false;
+  bool pair_solves = std::getenv("CB_NO_PAIRED_SOLVES") == nullptr;
   int kkt_solve_step(bool combined);
   int solve_initial_point();
   int shift_to_interior(double* v, bool primal);
@@ -771,14 +868,26 @@ bool IPM::check_termination(int iter) {
   return info.status != IST_UNSOLVED;
 }
 
-int IPM::kkt_update() {
-  // kktsystem.rs:108-125, 266-278
+int IPM::kkt_update(bool with_affine) {
+  // kktsystem.rs:108-125, 266-278.  with_affine: the affine step's system (kktsystem.rs:127-150) does not depend
+  // on the constant-rhs solution, so both go through the factorisation together (KKTDevice::solve2); the
+  // arithmetic per system is the one of two separate solves.
   const double t = wall();
   int ok = kkt.update();
+  affine_presolved = false;
   if (ok == 1) {
     V.scale_copy(workx, -1.0, dq, n);
     kkt.setrhs(workx, db);
-    ok = kkt.solve(x2, z2);
+    if (with_affine) {
+      V.copy(workx, rhx, n);
+      V.copy(work_conic, s, m);
+      V.waxpby(workz, 1.0, work_conic, -1.0, rhz, m);
+      kkt.setrhs2(workx, workz);
+      ok = kkt.solve2(x2, z2, x1, z1);
+      affine_presolved = ok == 1;
+    } else {
+      ok = kkt.solve(x2, z2);
+    }
     if (ok == 1) {
       // constants of the delta-tau formula that only depend on (x2, z2)
       spmv(Psym, tmpn, x2, 1.0, 0.0);
@@ -798,13 +907,17 @@ int IPM::kkt_update() {
 int IPM::kkt_solve_step(bool combined) {
   // kktsystem.rs:127-209
   const double t0 = wall();
-  V.copy(workx, rhx, n);
-  if (!combined) V.copy(work_conic, s, m);
-  else cones.ds_from_dz_offset(work_conic, rhs_, z);
-  V.waxpby(workz, 1.0, work_conic, -1.0, rhz, m);
-  kkt.setrhs(workx, workz);
-  int ok = kkt.solve(x1, z1);
-  if (ok != 1) { info.t_kkt_solve += wall() - t0; return ok; }
+  if (!combined && affine_presolved) {
+    affine_presolved = false;      // (x1, z1) and work_conic = s were produced together with the constant-rhs solve
+  } else {
+    V.copy(workx, rhx, n);
+    if (!combined) V.copy(work_conic, s, m);
+    else cones.ds_from_dz_offset(work_conic, rhs_, z);
+    V.waxpby(workz, 1.0, work_conic, -1.0, rhz, m);
+    kkt.setrhs(workx, workz);
+    int ok = kkt.solve(x1, z1);
+    if (ok != 1) { info.t_kkt_solve += wall() - t0; return ok; }
+  }
   // xi = x / tau ;  2 xi'P x1  and  (xi - x2)'P(xi - x2)
   double* xi = workx;
   V.scale_copy(xi, 1.0 / tau, x, n);
@@ -938,13 +1051,13 @@ int IPM::solve() {
     info.t_scale_cones += wall() - ts;
     if (failflag) { info.status = IST_NUMERR; break; }
     iter += 1;
-    int ok = kkt_update();
-    if (ok < 0) return ok;
     // affine right-hand side (variables.rs:67-78)
     V.copy(rhx, rx, n);
     V.copy(rhz, rz, m);
     cones.affine_ds(rhs_);
     rhtau = rtau; rhkap = tau * kap;
+    int ok = kkt_update(pair_solves);
+    if (ok < 0) return ok;
     if (ok == 1) { ok = kkt_solve_step(false); if (ok < 0) return ok; }
     if (ok == 1) {
       if ((rc = step_length(false, &alpha))) return rc;
