@@ -728,14 +728,38 @@ __device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, do
   const int ld = ns + nr;
   const double* __restrict__ P = d.L + d.panel_off[s];
   const int* __restrict__ rows = d.sn_rows + rp;
-  for (int j = 0; j < ns; j++) {
-    const double* __restrict__ cj = P + (long long)j * ld + ns;
-    double acc = 0.0;
-    for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
-    __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
+  if (nr <= 8 * 32) {
+    // the ancestors' solution entries this front needs are fetched once (index -> value is a dependent pair of
+    // loads; doing it per pivot column put 2*ns round trips on every narrow front)
+    double xv[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+    for (int q8 = 0; q8 < 8; q8++) {
+      const int a = lane + 32 * q8;
+      xv[q8] = a < nr ? __ldcg(xp + rows[a]) : 0.0;
+    }
+    for (int j = 0; j < ns; j++) {
+      const double* __restrict__ cj = P + (long long)j * ld + ns;
+      double acc = 0.0;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; q8++) {
+        const int a = lane + 32 * q8;
+        if (a < nr) acc += cj[a] * xv[q8];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+    }
+  } else {
+    for (int j = 0; j < ns; j++) {
+      const double* __restrict__ cj = P + (long long)j * ld + ns;
+      double acc = 0.0;
+      for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
+      __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+    }
   }
   __syncwarp();
   for (int j = ns - 1; j > 0; j--) {
@@ -781,9 +805,12 @@ __device__ void df_fwd_wide(const LDLDev& d, const DFPlan& q, int s, int k, doub
     if (df_trk) df_trk[1] = df_gtime();
   }
   __syncthreads();
+  const bool pure = q.pure_chain[s] != 0;       // only child = chain child: its row i is this front's index i
+  const double* uc = pure ? d.u + d.sn_rowptr[c] : nullptr;
   if (tid < ns) {
     double acc = 0.0;
-    for (int e = gp[tid]; e < gp[tid + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
+    if (pure) acc = __ldcg(uc + tid);
+    else for (int e = gp[tid]; e < gp[tid + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
     xp[f + tid] += acc;
   }
   __syncthreads();
@@ -826,7 +853,8 @@ __device__ void df_fwd_wide(const LDLDev& d, const DFPlan& q, int s, int k, doub
     for (int jj = 0; jj < 16; jj++) part += v[jj] * sy[(16 * cq + jj) & (CB_PB_MAXNS - 1)];
     double g = 0.0;
     if (cq == 0 && a < nr) {
-      for (int e = gp[ns + a]; e < gp[ns + a + 1]; e++) g += __ldcg(d.u + d.gat_src[e]);
+      if (pure) g = __ldcg(uc + ns + a);
+      else for (int e = gp[ns + a]; e < gp[ns + a + 1]; e++) g += __ldcg(d.u + d.gat_src[e]);
     }
     sred[cq * SV_RB + r] = part;
     __syncthreads();
@@ -1510,18 +1538,50 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
     if (tid < ns) sD[tid] = __ldcg(d.D + f + tid);
   }
   DF_STAMP(q, 6);
-  for (int idx = tid; idx < TS * (TS + 1); idx += DF_NT) sC[idx] = 0.0;
-  __syncthreads();
-  DF_STAMP(q, 7);
-  df_children(q, tk[7], tk[8], s_desc, [&](const DFChildRec& ch) { df_add_child<2>(d, ch, sC, ns + i0, TS + 1, ns + j0, 1); });
-  DF_STAMP(q, 8);
-  df_ent_apply(sC, d.U, d.sc_tile_src, d.sc_tile_dst, tk[9], tk[10], pe, s_ed, s_ev, [&](int dd) -> long long { return dd; });
+  // children that are contiguous in this tile (the previous panel of the same separator) are added in
+  // registers, straight from their update matrix: thread (tx, ty) owns rows tx+16i, columns ty+16j of the tile
+  const int tx = tid & 15, ty = tid >> 4;
+  double creg[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) creg[i][j] = 0.0;
+  const int ndense = tk[11];
+  for (int kd = 0; kd < ndense; kd++) {
+    const int* rec = q.desc + (size_t)(tk[7] + kd) * 12;
+    const long long uoff = *reinterpret_cast<const long long*>(rec);
+    const int nrc = rec[4], a0 = rec[5], a1 = rec[6], b0 = rec[7], b1 = rec[8];
+    const int ra = a0 - (rec[10] - (ns + i0)), rb = b0 - (rec[11] - (ns + j0));   // child index = tile index + ra / rb
+    const double* Uc = d.U + uoff;
+    double v[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int b = ty + 16 * j + rb;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int a = tx + 16 * i + ra;
+        v[i][j] = (a >= a0 && a < a1 && b >= b0 && b < b1 && a >= b) ? __ldcg(Uc + (long long)b * nrc + a) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) creg[i][j] += v[i][j];
+  }
+  const bool use_sc = (tk[8] - tk[7] > ndense) || (tk[10] > tk[9]);
+  if (use_sc) {
+    for (int idx = tid; idx < TS * (TS + 1); idx += DF_NT) sC[idx] = 0.0;
+    __syncthreads();
+    DF_STAMP(q, 7);
+    df_children(q, tk[7] + ndense, tk[8], s_desc, [&](const DFChildRec& ch) { df_add_child<2>(d, ch, sC, ns + i0, TS + 1, ns + j0, 1); });
+    DF_STAMP(q, 8);
+    df_ent_apply(sC, d.U, d.sc_tile_src, d.sc_tile_dst, tk[9], tk[10], pe, s_ed, s_ev, [&](int dd) -> long long { return dd; });
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int idx = tid; idx < ns * TS; idx += DF_NT) sBt[idx] *= sD[idx >> 6];
   __syncthreads();
   DF_STAMP(q, 4);
-  const int tx = tid & 15, ty = tid >> 4;
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -1545,7 +1605,7 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
     for (int j = 0; j < 4; j++) {
       const int cc = ty + 16 * j;
       if (rr < ni && cc < nj && (i0 + rr >= j0 + cc))
-        U[(long long)(j0 + cc) * nr + (i0 + rr)] = sC[rr * (TS + 1) + cc] - acc[i][j];
+        U[(long long)(j0 + cc) * nr + (i0 + rr)] = (use_sc ? creg[i][j] + sC[rr * (TS + 1) + cc] : creg[i][j]) - acc[i][j];
     }
   }
 }
@@ -2027,6 +2087,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       const int64_t nsp = S.sn_first[p + 1] - S.sn_first[p], nrp = S.sn_rowptr[p + 1] - S.sn_rowptr[p];
       if (nrc == nsp + nrp) chain_child[p] = c;       // rows(c) is a subset of cols(p)+rows(p): equal sizes = equal sets
     }
+    std::vector<signed char> pure_chain(S.nsup, 0);
+    for (int s = 0; s < S.nsup; s++)
+      if (chain_child[s] >= 0 && S.child_ptr[s + 1] - S.child_ptr[s] == 1) pure_chain[s] = 1;
     for (int s = 0; s < S.nsup; s++) {
       blk_ptr[s] = (int)blk_owner.size();
       if (!wide(s)) continue;
@@ -2047,6 +2110,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     if ((rc = upload(&t1, S.sn_parent))) return rc; df.parent = t1;
     if ((rc = upload(&t1, pend))) return rc; d_pend_init = t1;
     if ((rc = upload(&t1, chain_child))) return rc; df.chain_child = t1;
+    { signed char* t8 = nullptr; if ((rc = upload(&t8, pure_chain))) return rc; df.pure_chain = t8; }
     if ((rc = upload(&t1, blk_ptr))) return rc; df.blk_ptr = t1;
     if ((rc = upload(&t1, blk_owner))) return rc; df.blk_owner = t1;
     CK(cudaMalloc((void**)&df.prog, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
@@ -2179,12 +2243,21 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
         for (int ti = 0; ti < nt; ti++)
           for (int tj = 0; tj <= ti; tj++) {
             const int d0 = (int)(desc.size() / 12);
-            for (size_t k = 0; k < kidsbuf.size(); k++) {
-              const int a0 = ctp[k][ti], a1 = ctp[k][ti + 1], b0 = ctp[k][tj], b1 = ctp[k][tj + 1];
-              if (a1 > a0 && b1 > b0) push_desc(kidsbuf[k], a0, a1, b0, b1);
-            }
+            // children whose block is contiguous in the tile go first: the tile task adds them in registers
+            int ndense = 0;
+            for (int pass = 0; pass < 2; pass++)
+              for (size_t k = 0; k < kidsbuf.size(); k++) {
+                const int a0 = ctp[k][ti], a1 = ctp[k][ti + 1], b0 = ctp[k][tj], b1 = ctp[k][tj + 1];
+                if (!(a1 > a0 && b1 > b0)) continue;
+                const int* rl = S.rel.data() + S.sn_rowptr[kidsbuf[k]];
+                const bool dense = rl[a1 - 1] - rl[a0] == a1 - 1 - a0 && rl[b1 - 1] - rl[b0] == b1 - 1 - b0;
+                if (dense != (pass == 0)) continue;
+                push_desc(kidsbuf[k], a0, a1, b0, b1);
+                if (dense) ndense++;
+              }
             const int t = tile_base[s] + ti * (ti + 1) / 2 + tj;
             push_task(3, s, ti, tj, d0, (int)(desc.size() / 12), h_sc_tile_ptr[t], h_sc_tile_ptr[t + 1]);
+            tk[tk.size() - 16 + 11] = ndense;
           }
       }
     }
@@ -2228,7 +2301,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(df.trace); fr(d_xp2); fr(d_u2); fr(df2_pend); fr(df2_done); fr(df2_prog); fr(df2_qhead); fr(df.chain_child); fr(df.blk_ptr); fr(df.blk_owner); fr(df.prog); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(df.trace); fr(d_xp2); fr(d_u2); fr(df2_pend); fr(df2_done); fr(df2_prog); fr(df2_qhead); fr(df.chain_child); fr(df.pure_chain); fr(df.blk_ptr); fr(df.blk_owner); fr(df.prog); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);

@@ -75,6 +75,7 @@ struct DFPlan {
   int* qhead = nullptr;              // [2] queue heads (forward, backward)
   const int* chain_child = nullptr;  // [nsup] wide child whose rows are exactly cols+rows of this front, or -1
   int* prog = nullptr;               // [nsup] forward: 64-row blocks of the update vector already final
+  const signed char* pure_chain = nullptr;  // [nsup] 1: the chain child is the only child (gather = shifted copy)
   const int* blk_ptr = nullptr;      // [nsup+1] into blk_owner
   const int* blk_owner = nullptr;    // per 64-row block of a wide front: front owning the block's first row
   unsigned long long* trace = nullptr;  // optional [2][ntask][4]: grab, ready, end (globaltimer ns), mid

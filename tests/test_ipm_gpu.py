@@ -157,3 +157,22 @@ def test_kkt_solver_trait_residual():
     # Hs block went in negated: diagonal of the (2,2) block equals -w^2 = -s/z
     diag = nz[cp[1:] - 1]
     assert np.allclose(diag[dev.n:dev.n + dev.m], -(s / z), rtol=1e-13)
+
+
+def test_paired_solves_are_bitwise_the_unpaired_ones(monkeypatch):
+    """The constant-rhs and the affine systems of an iteration share one factorisation and are independent, so
+    they run concurrently on two solve contexts (KKTDevice::solve2).  Per system the arithmetic is that of the
+    plain path: identical iterates, bit for bit."""
+    pr = workloads.random_sparse_qp(n=3000, m=5000, nnz_per_row=4, seed=11, window=60)
+    args = (pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"])
+    monkeypatch.delenv("CB_NO_PAIRED_SOLVES", raising=False)
+    a = cb.CudaSolver(*args)
+    ra = a.solve()
+    monkeypatch.setenv("CB_NO_PAIRED_SOLVES", "1")
+    b = cb.CudaSolver(*args, kkt_perm=a.kkt_perm())
+    rb = b.solve()
+    assert ra["status"] == rb["status"] == "Solved"
+    assert ra["iterations"] == rb["iterations"]
+    assert np.array_equal(ra["x"], rb["x"]) and np.array_equal(ra["z"], rb["z"]) and np.array_equal(ra["s"], rb["s"])
+    ia, ib = a.info, b.info
+    assert ia.n_ldl_solve == ib.n_ldl_solve and ia.n_refactor == ib.n_refactor
