@@ -21,6 +21,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <thread>
 
 #include "../../include/clarabel_b200.h"
 #include "cones.h"
@@ -203,6 +204,8 @@ class KKTDevice {
   int64_t n_refactor = 0, n_ldl_solve = 0, n_ir_steps = 0;
 
   int assemble(const HostCsc& P, const HostCsc& A);
+  bool defer_values = false;   // assemble the pattern only; set_PA_values() fills P and A later
+  int set_PA_values(const HostCsc& P, const HostCsc& A);
   int init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_settings& s, const cldl_opts& lo,
            const int* perm, cudaStream_t stream_unused, Scalars* scal);
   void release();
@@ -255,7 +258,7 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
   for (int i = 0; i < n; i++) {
     for (int64_t q = P.colptr[i]; q < P.colptr[i + 1]; q++) {
       int64_t d = nxt[i]++;
-      Ki[d] = P.rowval[q]; Kx[d] = P.nzval[q]; map_P[q] = (int)d;
+      Ki[d] = P.rowval[q]; Kx[d] = defer_values ? 0.0 : P.nzval[q]; map_P[q] = (int)d;
     }
     if (!has_diag(i)) { int64_t d = nxt[i]++; Ki[d] = i; Kx[d] = 0.0; }
   }
@@ -263,7 +266,7 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
     for (int64_t q = A.colptr[i]; q < A.colptr[i + 1]; q++) {
       const int col = n + A.rowval[q];
       int64_t d = nxt[col]++;
-      Ki[d] = i; Kx[d] = A.nzval[q]; map_A[q] = (int)d;
+      Ki[d] = i; Kx[d] = defer_values ? 0.0 : A.nzval[q]; map_A[q] = (int)d;
     }
   pcol = n + m;
   for (int k = 0; k < nc; k++) {
@@ -364,6 +367,14 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
   SCK(cudaMalloc((void**)&d_x2, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_b2, (size_t)N * 8));
   SCK(cudaMalloc((void**)&d_w1b, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_w2b, (size_t)N * 8));
   SCK(cudaMemset(d_x, 0, (size_t)N * 8)); SCK(cudaMemset(d_b, 0, (size_t)N * 8));
+  return 0;
+}
+
+int KKTDevice::set_PA_values(const HostCsc& P, const HostCsc& A) {
+  for (size_t q = 0; q < map_P.size(); q++) Kx[map_P[q]] = P.nzval[q];
+  for (size_t q = 0; q < map_A.size(); q++) Kx[map_A[q]] = A.nzval[q];
+  SCK(cudaMemcpyAsync(ldl.dev.vals, Kx.data(), (size_t)nnzK * 8, cudaMemcpyHostToDevice, st));
+  SCK(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -749,10 +760,18 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   cb_tmark(nullptr);
   if ((rc = cones.init(cs, st))) return rc;
   cb_tmark("ipm: cone set init");
-  equilibrate();
-  cb_tmark("ipm: equilibrate");
+  // Ruiz equilibration only rescales values: it runs on a host thread next to the pattern work of the KKT
+  // layer (assembly maps, ordering, symbolic analysis, plans); the values go in afterwards
   if ((rc = sc.init(st))) return rc;
-  if ((rc = kkt.init(P, A, &cones, set, lo, perm, st, &sc))) return rc;
+  {
+    std::thread eq([this]() { equilibrate(); });
+    kkt.defer_values = true;
+    rc = kkt.init(P, A, &cones, set, lo, perm, st, &sc);
+    eq.join();
+    if (rc) return rc;
+    if ((rc = kkt.set_PA_values(P, A))) return rc;
+  }
+  cb_tmark("ipm: equilibrate || kkt init");
   // single stream for everything: adopt the LDL object's stream
   cudaStreamDestroy(st);
   st = kkt.st;

@@ -2,6 +2,7 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -19,7 +20,7 @@ namespace {
 // Upper-triangular CSC pattern of P A P^T (columns sorted) from the caller's
 // triu CSC and iperm (old -> new).
 void permuted_upper(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<int>& iperm,
-                    std::vector<int64_t>& Up, std::vector<int>& Ui) {
+                    std::vector<int64_t>& Up, std::vector<int>& Ui, bool sorted = true) {
   Up.assign(n + 1, 0);
   for (int c = 0; c < n; c++)
     for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
@@ -35,7 +36,8 @@ void permuted_upper(int n, const int64_t* Ap, const int32_t* Ai, const std::vect
       int col = a > b ? a : b, row = a > b ? b : a;
       Ui[pos[col]++] = row;
     }
-  for (int j = 0; j < n; j++) std::sort(Ui.begin() + Up[j], Ui.begin() + Up[j + 1]);
+  if (sorted)
+    for (int j = 0; j < n; j++) std::sort(Ui.begin() + Up[j], Ui.begin() + Up[j + 1]);
 }
 
 // Liu's elimination tree with path compression, from upper-triangular columns.
@@ -140,7 +142,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
 
   std::vector<int64_t> Up;
   std::vector<int> Ui, parent0, post;
-  permuted_upper(n, Ap, Ai, iperm0, Up, Ui);
+  permuted_upper(n, Ap, Ai, iperm0, Up, Ui, false);   // the elimination tree does not need sorted columns
   etree_upper(n, Up, Ui, parent0);
   postorder(n, parent0, post);
   S.perm.resize(n);
@@ -149,7 +151,13 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   for (int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
 
   permuted_upper(n, Ap, Ai, S.iperm, Up, Ui);
-  etree_upper(n, Up, Ui, S.parent);
+  {
+    // the tree of the post-ordered matrix is the old tree relabelled
+    std::vector<int> ipost(n);
+    for (int k = 0; k < n; k++) ipost[post[k]] = k;
+    S.parent.assign(n, -1);
+    for (int j = 0; j < n; j++) if (parent0[j] >= 0) S.parent[ipost[j]] = ipost[parent0[j]];
+  }
   const std::vector<int>& parent = S.parent;
 
   // strictly-lower pattern by columns (transpose of strict upper)
@@ -355,25 +363,42 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   int64_t nnz = Ap[n];
   std::vector<int> ent_task(nnz);
   std::vector<int64_t> ent_dst(nnz);
-  for (int c = 0; c < n; c++)
-    for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
-      int a = S.iperm[Ai[p]], b = S.iperm[c];
-      int col = a < b ? a : b, row = a < b ? b : a;  // lower-triangular position
-      int s = S.col2sn[col];
-      int f = S.sn_first[s], l = S.sn_first[s + 1];
-      int64_t ns = l - f, nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
-      int64_t lrow;
-      if (row < l) lrow = row - f;
-      else {
-        auto b0 = S.sn_rows.begin() + S.sn_rowptr[s], e0 = S.sn_rows.begin() + S.sn_rowptr[s + 1];
-        auto it = std::lower_bound(b0, e0, row);
-        if (it == e0 || *it != row) { std::fprintf(stderr, "symbolic: asm map failure\n"); return -11; }
-        lrow = ns + (it - b0);
-      }
-      ent_task[p] = s;
-      ent_dst[p] = (int64_t)(col - f) * (ns + nr) + lrow;
-      S.asm_ptr[s + 1]++;
+  {
+    // entries are independent: host threads take column ranges (one binary search per entry)
+    const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned nth = nnz < 200000 ? 1u : hc;
+    std::vector<int> bad(nth, 0);
+    auto work = [&](unsigned t) {
+      const int c0 = (int)((int64_t)n * t / nth), c1 = (int)((int64_t)n * (t + 1) / nth);
+      for (int c = c0; c < c1; c++)
+        for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
+          int a = S.iperm[Ai[p]], b = S.iperm[c];
+          int col = a < b ? a : b, row = a < b ? b : a;  // lower-triangular position
+          int s = S.col2sn[col];
+          int f = S.sn_first[s], l = S.sn_first[s + 1];
+          int64_t ns = l - f, nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+          int64_t lrow;
+          if (row < l) lrow = row - f;
+          else {
+            auto b0 = S.sn_rows.begin() + S.sn_rowptr[s], e0 = S.sn_rows.begin() + S.sn_rowptr[s + 1];
+            auto it = std::lower_bound(b0, e0, row);
+            if (it == e0 || *it != row) { bad[t] = 1; return; }
+            lrow = ns + (it - b0);
+          }
+          ent_task[p] = s;
+          ent_dst[p] = (int64_t)(col - f) * (ns + nr) + lrow;
+        }
+    };
+    if (nth == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nth; t++) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
     }
+    for (unsigned t = 0; t < nth; t++)
+      if (bad[t]) { std::fprintf(stderr, "symbolic: asm map failure\n"); return -11; }
+    for (int64_t p = 0; p < nnz; p++) S.asm_ptr[ent_task[p] + 1]++;
+  }
   for (int s = 0; s < nsup; s++) S.asm_ptr[s + 1] += S.asm_ptr[s];
   S.asm_src.resize(nnz);
   S.asm_dst.resize(nnz);
