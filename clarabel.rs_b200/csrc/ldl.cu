@@ -954,8 +954,8 @@ __device__ __forceinline__ void df_load_pivot(const LDLDev& d, int s, double* sL
   }
 }
 
-template <bool FWD>
-__global__ void __launch_bounds__(SV_NT) k_solve_df(LDLDev d, DFPlan q, double* __restrict__ xp, double* __restrict__ out) {
+template <bool FWD, int MINB>
+__global__ void __launch_bounds__(SV_NT, MINB) k_solve_df(LDLDev d, DFPlan q, double* __restrict__ xp, double* __restrict__ out) {
   __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
   __shared__ double sv[CB_PB_MAXNS];
   __shared__ double sred[4 * SV_RB];
@@ -1788,7 +1788,11 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   cb_tmark("ldl: uploads + device alloc");
   // per-child constants for the big-front kernels and the per-destination gather lists for the solves
   std::vector<int> h_child_nb(S.nsup, 0);
-  {
+  // (runs on a host thread next to the launch plan and the small-child lists below; it only reads the symbolic
+  // structure and writes its own device arrays)
+  auto build_child_consts = [&]() -> int {
+    int rc = 0;
+    if (cudaSetDevice(device) != cudaSuccess) return CLDL_E_CUDA;
     std::vector<int>& child_nb = h_child_nb;
     std::vector<int2> child_tr(S.nsup, make_int2(1, 0));
     std::vector<int> gptr((size_t)n + S.sn_rows.size() + 1, 0);
@@ -1837,7 +1841,11 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     CK(cudaMalloc((void**)&t2, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int2)));
     CK(cudaMemcpy(t2, child_tr.data(), (size_t)S.nsup * sizeof(int2), cudaMemcpyHostToDevice));
     dev.child_trange = t2;
-  }
+      return rc;
+  };
+  int rc_child = 0;
+  std::thread th_child([&]() { rc_child = build_child_consts(); });
+  struct ThJoin { std::thread* t; ~ThJoin() { if (t->joinable()) t->join(); } } th_child_guard{&th_child};
   cb_tmark("ldl: child consts + gather lists");
   // per-level launch plan.  Small fronts: one fused CTA each, grouped by the shared-memory class of
   // their panel.  Big fronts (nr >= CB_BIG_NR): panel kernel + tiled update kernel.
@@ -1976,6 +1984,8 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     signed char* t8 = nullptr;
     if ((rc = upload(&t8, small))) return rc; dev.child_small = t8;
   }
+  th_child.join();
+  if (rc_child) return rc_child;
   cb_tmark("ldl: small-child entry lists");
   // solve plan.  Chains: consecutive panels s, s+1 with parent(s) == s+1 and rows(s) == cols(s+1) + rows(s+1)
   // are swept by one CTA, so the schedule is levelled over chains, not over panels.  Single narrow fronts
@@ -2124,9 +2134,17 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     df.ntask = nt;
     int nsm = 0, occ = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true>, SV_NT, 0));
+    // resident CTAs per SM of the sweep kernels: more CTAs keep more fronts in flight while others wait on
+    // their dependencies (the register budget is set through the launch bounds of the instantiation)
+    solve_minb = 4;   // C2: 2 / 3 / 4 resident CTAs per SM -> 1.56 / 1.38 / 1.32 ms per solve
+    if (const char* e = std::getenv("CB_SOLVE_MINB")) solve_minb = std::min(4, std::max(2, std::atoi(e)));
+    if (solve_minb == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true, 2>, SV_NT, 0));
+    else if (solve_minb == 3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true, 3>, SV_NT, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true, 4>, SV_NT, 0));
     int occ2 = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false>, SV_NT, 0));
+    if (solve_minb == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false, 2>, SV_NT, 0));
+    else if (solve_minb == 3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false, 3>, SV_NT, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false, 4>, SV_NT, 0));
     occ = std::max(1, std::min(occ, occ2));
     df_grid = nsm * occ;
     if (const char* e = std::getenv("CB_DF_GRID")) df_grid = std::max(1, std::atoi(e));
@@ -2399,8 +2417,16 @@ int LDLObject::solve_async(double* d_x, const double* d_b, int slot, bool half) 
     CK(cudaMemsetAsync(qv.done, 0, (size_t)S.nsup * sizeof(int), sst));
     CK(cudaMemsetAsync(qv.prog, 0, (size_t)S.nsup * sizeof(int), sst));
     CK(cudaMemsetAsync(qv.qhead, 0, 2 * sizeof(int), sst));
-    k_solve_df<true><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-    k_solve_df<false><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+    if (solve_minb == 2) {
+      k_solve_df<true, 2><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+      k_solve_df<false, 2><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+    } else if (solve_minb == 3) {
+      k_solve_df<true, 3><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+      k_solve_df<false, 3><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+    } else {
+      k_solve_df<true, 4><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+      k_solve_df<false, 4><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
+    }
     CK(cudaGetLastError());
     return CLDL_OK;
   }

@@ -118,6 +118,7 @@ class LDLObject {
   bool factor_dataflow = true;
   int* d_pend_init = nullptr;
   int df_grid = 0;
+  int solve_minb = 4;
   bool use_dataflow = true;
   int solve_levels = 0;
   unsigned long long solve_launches = 0;

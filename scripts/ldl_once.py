@@ -14,3 +14,4 @@ for _ in range(3):
     assert s.refactor()
 x = s.solve(np.ones(N))
 print("ok", s.time_refactor_ms(3))
+print("solve_ms", s.time_solve_ms(20))
