@@ -383,7 +383,7 @@ class cipm_info(C.Structure):
 EXPORTED_SYMBOLS += [
     "cipm_default_settings", "cipm_create", "cipm_destroy", "cipm_solve", "cipm_get_info",
     "cipm_get_solution", "cipm_trace", "cipm_iter_ms", "cipm_launch_count", "cipm_time_ms", "cipm_kkt_dim", "cipm_kkt_nnz", "cipm_get_kkt",
-    "cipm_get_kkt_perm", "cipm_ldl_info", "ckkt_update", "ckkt_setrhs", "ckkt_solve", "ckkt_update_P",
+    "cipm_get_kkt_perm", "cipm_ldl_info", "cipm_update_data", "ckkt_update", "ckkt_setrhs", "ckkt_solve", "ckkt_update_P",
     "ckkt_update_A", "ckkt_get_values", "ccone_set_identity_scaling", "ccone_update_scaling",
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
@@ -427,6 +427,8 @@ def _lib2():
     L.ckkt_update.argtypes = [vp]
     L.ckkt_setrhs.argtypes = [vp, f64p, f64p]
     L.ckkt_solve.argtypes = [vp, f64p, f64p]
+    L.cipm_update_data.argtypes = [vp, f64p, f64p, f64p, f64p]
+    L.cipm_update_data.restype = C.c_int
     L.ckkt_update_P.argtypes = [vp, f64p]
     L.ckkt_update_A.argtypes = [vp, f64p]
     L.ckkt_get_values.argtypes = [vp, f64p]
@@ -489,6 +491,25 @@ class CudaSolver:
         _check(rc, "cipm_create")
         self._h = h
         self.N = int(L.cipm_kkt_dim(h))
+
+    def update_data(self, P=None, q=None, A=None, b=None):
+        """DefaultSolver::update_data (data_updating.rs:68-163): new values on the same sparsity patterns; the
+        symbolic analysis, the device plans and the equilibration scalings of the handle are reused."""
+        import scipy.sparse as sp
+
+        def vals(M, triu):
+            if M is None:
+                return None
+            if sp.issparse(M):
+                M = sp.csc_matrix(sp.triu(M, format="csc") if triu else M)
+                M.sort_indices()
+                return _f64(M.data)
+            return _f64(M)
+        Pv, Av = vals(P, True), vals(A, False)
+        qv = _f64(q) if q is not None else None
+        bv = _f64(b) if b is not None else None
+        f = lambda a: _p(a, C.c_double) if a is not None else None
+        _check(self._L.cipm_update_data(self._h, f(Pv), f(qv), f(Av), f(bv)), "cipm_update_data")
 
     def close(self):
         if getattr(self, "_h", None):

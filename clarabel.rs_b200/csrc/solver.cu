@@ -613,6 +613,7 @@ class IPM {
   void check_convergence(double tga, double tgr, double tf, double tia, double tir, double tkt, int s1, int s2, int s3);
   bool check_termination(int iter);
   int kkt_update(bool with_affine = false);
+  int update_data(const double* Pnz, const double* qv, const double* Anz, const double* bv);
   bool affine_presolved = false;
   bool pair_solves = std::getenv("CB_NO_PAIRED_SOLVES") == nullptr;
   int kkt_solve_step(bool combined);
@@ -727,6 +728,57 @@ int IPM::upload_problem() {
     Psym.nrows = n; Psym.rowptr = dPr; Psym.col = dPc; Psym.val = dPv;
   }
   if (upv(&dq, q) || upv(&db, b) || upv(&dd, d) || upv(&ddinv, dinv) || upv(&de, e) || upv(&deinv, einv)) return CLDL_E_CUDA;
+  return 0;
+}
+
+// DefaultSolver::update_data (implementations/default/data_updating.rs:68-163): new values on the same sparsity
+// patterns go through the STORED equilibration (P <- c D P D, A <- E A D, q <- c D q, b <- E b), the KKT values are
+// overwritten through the assembly maps, symbolic analysis and plans are kept.  Null pointer = unchanged.
+int IPM::update_data(const double* Pnz, const double* qv, const double* Anz, const double* bv) {
+  SCK(cudaSetDevice(kkt.ldl.device));
+  if (Pnz) {
+    for (int j = 0; j < n; j++)
+      for (int64_t t = P.colptr[j]; t < P.colptr[j + 1]; t++) P.nzval[t] = Pnz[t] * d[P.rowval[t]] * d[j] * c;
+    // same traversal as upload_problem: values of the full symmetric CSR
+    std::vector<int> cnt(n + 1, 0);
+    for (int j = 0; j < n; j++)
+      for (int64_t t = P.colptr[j]; t < P.colptr[j + 1]; t++) { cnt[P.rowval[t] + 1]++; if (P.rowval[t] != j) cnt[j + 1]++; }
+    for (int i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+    std::vector<double> val(cnt[n]);
+    for (int j = 0; j < n; j++)
+      for (int64_t t = P.colptr[j]; t < P.colptr[j + 1]; t++) {
+        const int i = P.rowval[t];
+        val[pos[i]++] = P.nzval[t];
+        if (i != j) val[pos[j]++] = P.nzval[t];
+      }
+    if (!val.empty()) SCK(cudaMemcpy((void*)dPv, val.data(), val.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (Anz) {
+    for (int j = 0; j < n; j++)
+      for (int64_t t = A.colptr[j]; t < A.colptr[j + 1]; t++) A.nzval[t] = Anz[t] * e[A.rowval[t]] * d[j];
+    std::vector<int> rp, ci; std::vector<double> vv;
+    csc_to_csr(A, rp, ci, vv);
+    if (!vv.empty()) {
+      SCK(cudaMemcpy((void*)dAv, vv.data(), vv.size() * 8, cudaMemcpyHostToDevice));
+      SCK(cudaMemcpy((void*)dAtv, A.nzval.data(), A.nzval.size() * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  if (Pnz || Anz) {
+    int rc = kkt.set_PA_values(P, A);     // kktsystem.update_P / update_A -> KKT value array
+    if (rc) return rc;
+  }
+  if (qv) {
+    normq = 0;
+    for (int i = 0; i < n; i++) { q[i] = qv[i] * d[i] * c; normq = std::max(normq, std::fabs(q[i] * dinv[i])); }
+    normq /= c;                           // problemdata.rs:147-189: unscaled norm recomputed from the scaled data
+    if (n) SCK(cudaMemcpy((void*)dq, q.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  }
+  if (bv) {
+    normb = 0;
+    for (int i = 0; i < m; i++) { b[i] = bv[i] * e[i]; normb = std::max(normb, std::fabs(b[i] * einv[i])); }
+    if (m) SCK(cudaMemcpy((void*)db, b.data(), (size_t)m * 8, cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -1314,6 +1366,10 @@ int ckkt_solve(cipm_t* h, double* lhsx, double* lhsz) {
   cudaStreamSynchronize(I.st);
   if ((lhsx && d2h(lhsx, I.x1, I.n)) || (lhsz && d2h(lhsz, I.z1, I.m))) return CLDL_E_CUDA;
   return 1;
+}
+int cipm_update_data(cipm_t* h, const double* P_nzval, const double* q, const double* A_nzval, const double* b) {
+  if (!h) return CLDL_E_ARG;
+  return h->ipm.update_data(P_nzval, q, A_nzval, b);
 }
 int ckkt_update_P(cipm_t* h, const double* P_nzval_scaled) {
   if (!h) return CLDL_E_ARG;

@@ -213,6 +213,11 @@ int cipm_get_kkt(const cipm_t *h, uint64_t *colptr, uint64_t *rowval, double *nz
 int cipm_get_kkt_perm(const cipm_t *h, uint64_t *perm);
 void cipm_ldl_info(const cipm_t *h, cldl_info_t *info);
 
+/* DefaultSolver::update_data (src/solver/implementations/default/data_updating.rs:68-163): overwrite the values of
+ * P (triu, same pattern), q, A (same pattern), b in an existing solver; the stored equilibration is applied, symbolic
+ * analysis and device plans are reused, the next cipm_solve starts from the default initial point.  NULL = unchanged. */
+int cipm_update_data(cipm_t *h, const double *P_nzval, const double *q, const double *A_nzval, const double *b);
+
 /* KKTSolver trait on the handle's KKT object (host buffers; x has length n, z length m).
  * ckkt_update / ckkt_solve return 1 (true) / 0 (false) like the trait's bools. */
 int ckkt_update(cipm_t *h);                                  /* KKTSolver::update(cones, settings) */

@@ -176,3 +176,42 @@ def test_paired_solves_are_bitwise_the_unpaired_ones(monkeypatch):
     assert np.array_equal(ra["x"], rb["x"]) and np.array_equal(ra["z"], rb["z"]) and np.array_equal(ra["s"], rb["s"])
     ia, ib = a.info, b.info
     assert ia.n_ldl_solve == ib.n_ldl_solve and ia.n_refactor == ib.n_refactor
+
+
+def test_update_data_then_solve_matches_fresh_solver():
+    """DefaultSolver::update_data (data_updating.rs:68-163, tests/data_updating.rs): overwriting P, q, A, b in an
+    existing solver and solving again gives the solution of a solver built from the new data (the handle keeps its
+    symbolic analysis, plans and equilibration scalings, so the iterates differ but the optimum does not)."""
+    pr = workloads.random_sparse_qp(n=400, m=700, nnz_per_row=4, seed=5, window=40)
+    P, q, A, b, cones = pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"]
+    dev = cb.CudaSolver(P, q, A, b, cones)
+    r0 = dev.solve()
+    assert r0["status"] == "Solved"
+    rng = np.random.default_rng(1)
+    P2 = P.copy(); P2.data = P2.data * 1.3
+    A2 = A.copy(); A2.data = A2.data * (1.0 + 0.05 * rng.standard_normal(A2.data.size))
+    q2 = q + 0.1 * rng.standard_normal(q.size)
+    b2 = b + 0.05 * np.abs(rng.standard_normal(b.size))
+    dev.update_data(P=P2, q=q2, A=A2, b=b2)
+    r1 = dev.solve()
+    fresh = cb.CudaSolver(P2, q2, A2, b2, cones)
+    rf = fresh.solve()
+    ora = oracle.IPM(P2, q2, A2, b2, cones)
+    ora.set_perm(fresh.kkt_perm())
+    ro = ora.solve()
+    assert r1["status"] == rf["status"] == ro["status"] == "Solved"
+    # different equilibration scalings => different iterates; the optimum agrees to the solver's tolerances
+    sc = max(1.0, np.max(np.abs(ro["x"])))
+    assert np.max(np.abs(rf["x"] - ro["x"])) <= 1e-7 * sc          # same data, same permutation: same trajectory
+    assert np.max(np.abs(r1["x"] - ro["x"])) <= 1e-4 * sc
+    assert abs(r1["obj_val"] - ro["obj_val"]) <= 1e-6 * max(1.0, abs(ro["obj_val"]))
+    # partial update: only q; everything else keeps its current (updated) value
+    q3 = q2 * 0.5
+    dev.update_data(q=q3)
+    r2 = dev.solve()
+    ora3 = oracle.IPM(P2, q3, A2, b2, cones)
+    ora3.set_perm(fresh.kkt_perm())
+    ro3 = ora3.solve()
+    assert r2["status"] == ro3["status"] == "Solved"
+    assert np.max(np.abs(r2["x"] - ro3["x"])) <= 1e-4 * max(1.0, np.max(np.abs(ro3["x"])))
+    assert abs(r2["obj_val"] - ro3["obj_val"]) <= 1e-6 * max(1.0, abs(ro3["obj_val"]))
