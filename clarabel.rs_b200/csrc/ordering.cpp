@@ -389,33 +389,119 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
     return;
   }
   if (e < 2) { nd_leaf(W, verts, out); return; }   // clique-like, cannot bisect
-  // choose the level that balances vertex counts on both sides
+  // Candidate cuts: the levels around the one that balances the vertex counts.  For a cut between levels c and
+  // c+1 every crossing edge joins the two boundary sets A (level c) and B (level c+1); the smallest vertex
+  // separator inside A u B is a minimum vertex cover of that bipartite graph (Koenig: from a maximum matching,
+  // Hopcroft-Karp).  It is never larger than the one-sided choice "all of A" and often much smaller.
   std::vector<int64_t> cntl(e + 1, 0);
   for (int v : q) cntl[W.level[v]]++;
+  std::vector<int64_t> pre(e + 2, 0);
+  for (int l = 0; l <= e; l++) pre[l + 1] = pre[l] + cntl[l];
   const int64_t half = (int64_t)total / 2;
-  int64_t acc = 0;
-  int cut = 1;
-  for (int l = 0; l <= e; l++) { acc += cntl[l]; if (acc >= half) { cut = l; break; } }
-  if (cut < 1) cut = 1;
-  if (cut > e - 1) cut = e - 1;
-  if (cut + 1 <= e - 1 && cntl[cut + 1] < cntl[cut]) {
-    const int64_t below = acc;
-    if (std::llabs(2 * below - (int64_t)total) < (int64_t)total / 2) cut = cut + 1;
-  }
-  std::vector<int> L, R, sep;
-  for (int v : q) {
-    const int lv = W.level[v];
-    if (lv < cut) L.push_back(v);
-    else if (lv > cut) R.push_back(v);
-    else {
+  int cut = 0;
+  while (cut < e - 1 && pre[cut + 1] < half) cut++;      // levels 0..cut hold at least half (or cut = e-1)
+  std::vector<int> sep, bestsep;
+  int bestc = -1;
+  double bestscore = 1e300;
+  std::vector<int> A, B, matchA, matchB, dist, stk;
+  std::vector<std::vector<int>> nbr;
+  for (int c = std::max(0, cut - 2); c <= std::min(e - 1, cut + 2); c++) {
+    const int64_t below = pre[c + 1], above = (int64_t)total - below;
+    if (std::min(below, above) * 5 < (int64_t)total && c != cut) continue;    // keep candidates roughly balanced
+    A.clear(); B.clear();
+    // local ids through W.local (reset below); boundary vertices only
+    for (int v : q) {
+      const int lv = W.level[v];
+      if (lv != c && lv != c + 1) continue;
       bool touches = false;
       for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1] && !touches; p++) {
         const int u = (*W.adj)[p];
-        if (W.part[u] == region && W.level[u] == cut + 1) touches = true;
+        if (W.part[u] == region && W.level[u] == (lv == c ? c + 1 : c)) touches = true;
       }
-      if (touches) sep.push_back(v); else L.push_back(v);
+      if (!touches) continue;
+      if (lv == c) { W.local[v] = (int)A.size(); A.push_back(v); }
+      else { W.local[v] = (int)B.size(); B.push_back(v); }
     }
+    const int na = (int)A.size(), nb = (int)B.size();
+    nbr.assign(na, std::vector<int>());
+    for (int i = 0; i < na; i++) {
+      const int v = A[i];
+      for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+        const int u = (*W.adj)[p];
+        if (W.part[u] == region && W.level[u] == c + 1) nbr[i].push_back(W.local[u]);
+      }
+    }
+    for (int v : A) W.local[v] = -1;
+    for (int v : B) W.local[v] = -1;
+    // Hopcroft-Karp
+    matchA.assign(na, -1); matchB.assign(nb, -1); dist.assign(na, 0);
+    for (;;) {
+      std::vector<int> bq;
+      for (int i = 0; i < na; i++) { if (matchA[i] < 0) { dist[i] = 0; bq.push_back(i); } else dist[i] = -1; }
+      bool found = false;
+      for (size_t h = 0; h < bq.size(); h++) {
+        const int i = bq[h];
+        for (int j : nbr[i]) {
+          const int i2 = matchB[j];
+          if (i2 < 0) found = true;
+          else if (dist[i2] < 0) { dist[i2] = dist[i] + 1; bq.push_back(i2); }
+        }
+      }
+      if (!found) break;
+      // iterative DFS along the layering
+      std::vector<int> it(na, 0);
+      for (int r = 0; r < na; r++) {
+        if (matchA[r] >= 0) continue;
+        stk.clear(); stk.push_back(r);
+        while (!stk.empty()) {
+          const int i = stk.back();
+          if (it[i] >= (int)nbr[i].size()) { dist[i] = -2; stk.pop_back(); continue; }
+          const int j = nbr[i][it[i]++];
+          const int i2 = matchB[j];
+          if (i2 < 0) {
+            // augment along the stack
+            int jj = j;
+            for (size_t t = stk.size(); t-- > 0;) { const int ii = stk[t]; const int pj = matchA[ii]; matchA[ii] = jj; matchB[jj] = ii; jj = pj; }
+            break;
+          }
+          if (dist[i2] == dist[i] + 1) stk.push_back(i2);
+        }
+      }
+    }
+    // Koenig: Z = reachable from unmatched A by alternating paths; cover = (A \ Z) u (B n Z)
+    std::vector<char> za(na, 0), zb(nb, 0);
+    {
+      std::vector<int> bq;
+      for (int i = 0; i < na; i++) if (matchA[i] < 0) { za[i] = 1; bq.push_back(i); }
+      for (size_t h = 0; h < bq.size(); h++) {
+        const int i = bq[h];
+        for (int j : nbr[i]) {
+          if (zb[j] || matchA[i] == j) continue;
+          zb[j] = 1;
+          const int i2 = matchB[j];
+          if (i2 >= 0 && !za[i2]) { za[i2] = 1; bq.push_back(i2); }
+        }
+      }
+    }
+    sep.clear();
+    for (int i = 0; i < na; i++) if (!za[i]) sep.push_back(A[i]);
+    for (int j = 0; j < nb; j++) if (zb[j]) sep.push_back(B[j]);
+    int64_t sl = 0;                                        // separator vertices taken from the lower side
+    for (int i = 0; i < na; i++) if (!za[i]) sl++;
+    const int64_t nl = below - sl, nrr = above - ((int64_t)sep.size() - sl);
+    const double imb = (double)std::llabs(nl - nrr) / (double)total;
+    const double score = (double)sep.size() * (1.0 + 2.0 * imb * imb) + 1e-9 * std::abs(c - cut);
+    if (score < bestscore) { bestscore = score; bestc = c; bestsep = sep; }
   }
+  if (bestc < 0) { nd_leaf(W, verts, out); return; }
+  sep.swap(bestsep);
+  for (int v : sep) W.local[v] = -2;                       // mark
+  std::vector<int> L, R;
+  for (int v : q) {
+    if (W.local[v] == -2) continue;
+    if (W.level[v] <= bestc) L.push_back(v); else R.push_back(v);
+  }
+  for (int v : sep) W.local[v] = -1;
   // a level-structure cut is only worth keeping when it is thin and roughly balanced; small-world graphs
   // (hub rows) give neither, and the region is then left to AMD as a whole
   const size_t smaller = std::min(L.size(), R.size());

@@ -554,6 +554,7 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
   if (n <= 0) return -1;
   SymbolicOptions opt = opt_in;
   if (const char* e = std::getenv("CB_RELAX_SUBTREE")) opt.relax_subtree = std::atoi(e);   // tuning knob
+  if (const char* e = std::getenv("CB_ND_LEAF")) opt.nd_leaf = std::atoi(e);               // tuning knob (overrides the caller)
   for (int j = 0; j < n; j++) {
     if (!(Ap[j] < Ap[j + 1])) return -2;  // empty column (qdldl.rs:222-225)
     for (int64_t p = Ap[j]; p < Ap[j + 1]; p++)

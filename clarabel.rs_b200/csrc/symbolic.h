@@ -25,7 +25,7 @@ enum OrderingKind { ORDER_GIVEN = 0, ORDER_AMD = 1, ORDER_ND = 2, ORDER_BEST = 3
 struct SymbolicOptions {
   int ordering = ORDER_BEST;
   double amd_dense_scale = 1.5;  // reference value, ldlsolvers/qdldl.rs:41
-  int nd_leaf = 3200;     // regions below this size are ordered by AMD (C2 sweep 200..12800: refactor 7.35/6.98/6.37/6.21/6.83 ms at 200/1600/3200/6400/12800, solve best up to 3200)
+  int nd_leaf = 1600;     // regions below this size are ordered by AMD (C2 sweeps on the GPU: 200..12800, best 1600-3200)
   int max_panel = 64;     // widest supernode panel (columns) handled as one task
   int relax_subtree = 64; // merge every etree subtree with at most this many columns into one front (C2 sweep: 16/32/64 -> solve 1.76/1.66/1.58 ms)
   int relax_small = 8;    // always merge a child chain if the merged width stays <= this
