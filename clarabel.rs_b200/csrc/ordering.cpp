@@ -405,7 +405,9 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
   double bestscore = 1e300;
   std::vector<int> A, B, matchA, matchB, dist, stk;
   std::vector<std::vector<int>> nbr;
-  for (int c = std::max(0, cut - 2); c <= std::min(e - 1, cut + 2); c++) {
+  int cwin = 2;
+  if (const char* ev = std::getenv("CB_ND_CUTWIN")) cwin = std::atoi(ev);
+  for (int c = std::max(0, cut - cwin); c <= std::min(e - 1, cut + cwin); c++) {
     const int64_t below = pre[c + 1], above = (int64_t)total - below;
     if (std::min(below, above) * 5 < (int64_t)total && c != cut) continue;    // keep candidates roughly balanced
     A.clear(); B.clear();
