@@ -26,8 +26,8 @@ $(CSRC)/%.o: $(CSRC)/%.cpp $(HDRS)
 $(LIB): $(CU_OBJS) $(CPP_OBJS)
 	$(NVCC) -shared $(GENCODE) -o $@ $^ -lcudart -lpthread
 
-$(ORACLE): $(ORACLE_SRCS)
-	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -Wall -o $@ $^ -lm
+$(ORACLE): $(ORACLE_SRCS) $(wildcard oracle/*.h)
+	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS) -lm
 
 clean:
 	rm -f $(CSRC)/*.o $(LIB) $(ORACLE)

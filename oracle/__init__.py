@@ -203,7 +203,7 @@ class QDLDL:
 # ---------------------------------------------------------------------------
 # IPM oracle (oracle/ipm_oracle.c)
 # ---------------------------------------------------------------------------
-CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3}
+CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3, "exp": 4, "pow": 5}
 STATUS_NAMES = ["Unsolved", "Solved", "PrimalInfeasible", "DualInfeasible", "AlmostSolved",
                 "AlmostPrimalInfeasible", "AlmostDualInfeasible", "MaxIterations", "MaxTime",
                 "NumericalError", "InsufficientProgress"]
@@ -229,6 +229,7 @@ class Settings(C.Structure):
         ("iterative_refinement_reltol", C.c_double), ("iterative_refinement_abstol", C.c_double),
         ("iterative_refinement_max_iter", C.c_int32),
         ("iterative_refinement_stop_ratio", C.c_double),
+        ("linesearch_backtrack_step", C.c_double), ("min_switch_step_length", C.c_double),
     ]
 
 
@@ -262,8 +263,21 @@ def _ipm_lib():
         L.oipm_default_settings.restype = None
         L.oipm_new.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, i64p, i64p,
                                f64p, f64p, C.c_int64, i32p, i64p, C.POINTER(Settings)]
+        L.oipm_new_ex.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, i64p, i64p,
+                                  f64p, f64p, C.c_int64, i32p, i64p, f64p, C.POINTER(Settings)]
         L.oipm_free.argtypes = [vp]
         L.oipm_free.restype = None
+        L.oipm_test_update_scaling_ex.argtypes = [vp, f64p, f64p, C.c_double, C.c_int]
+        L.oipm_test_compute_barrier.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double]
+        L.oipm_test_compute_barrier.restype = C.c_double
+        L.oipm_test_unit_initialization.argtypes = [vp, f64p, f64p]
+        L.oipm_test_unit_initialization.restype = None
+        L.oipm_test_wright_omega.argtypes = [C.c_double]
+        L.oipm_test_wright_omega.restype = C.c_double
+        L.oipm_test_ns3_state.argtypes = [vp, C.c_int64, f64p]
+        L.oipm_test_ns3_state.restype = None
+        L.oipm_test_affine_ds_ex.argtypes = [vp, f64p, f64p]
+        L.oipm_test_affine_ds_ex.restype = None
         L.oipm_kkt_dim.argtypes = [vp]
         L.oipm_kkt_dim.restype = C.c_int64
         L.oipm_kkt_nnz.argtypes = [vp]
@@ -321,7 +335,8 @@ class IPM:
 
     P is any scipy sparse symmetric or upper-triangular matrix (converted to
     triu like problemdata.rs:79-81), A scipy sparse, cones a list of
-    (kind, dim) with kind in {"zero","nonneg","soc"}.
+    (kind, dim) with kind in {"zero","nonneg","soc","psd"}, ("exp", 3) for an
+    ExponentialConeT() or ("pow", alpha) for a PowerConeT(alpha).
     """
 
     def __init__(self, P, q, A, b, cones, settings=None):
@@ -335,13 +350,15 @@ class IPM:
         n, m = P.shape[0], A.shape[0]
         self.n, self.m = n, m
         ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
-        cd = I([d for _, d in cones])
+        cd = I([3 if k in ("exp", "pow") else d for k, d in cones])
+        cpar = F([float(d) if k == "pow" else 0.0 for k, d in cones])
         self.settings = settings if settings is not None else default_settings()
         h = C.c_void_p()
         Pp, Pi, Px = I(P.indptr), I(P.indices), F(P.data)
         Ap, Ai, Ax = I(A.indptr), I(A.indices), F(A.data)
-        rc = L.oipm_new(C.byref(h), n, m, P_(Pp), P_(Pi), P_(Px), P_(F(q)), P_(Ap), P_(Ai), P_(Ax), P_(F(b)),
-                        len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)), P_(cd), C.byref(self.settings))
+        rc = L.oipm_new_ex(C.byref(h), n, m, P_(Pp), P_(Pi), P_(Px), P_(F(q)), P_(Ap), P_(Ai), P_(Ax), P_(F(b)),
+                           len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)), P_(cd), P_(cpar),
+                           C.byref(self.settings))
         if rc:
             raise ValueError(f"oipm_new failed: {rc}")
         self._h = h
@@ -401,6 +418,28 @@ class IPM:
     # cone-level entry points for unit parity tests of the CUDA cone kernels
     def update_scaling(self, s, z):
         return bool(self._L.oipm_test_update_scaling(self._h, P_(F(s)), P_(F(z))))
+
+    def update_scaling_ex(self, s, z, mu, strategy):
+        """strategy: 0 primal-dual, 1 dual (ScalingStrategy, cones/mod.rs)"""
+        return bool(self._L.oipm_test_update_scaling_ex(self._h, P_(F(s)), P_(F(z)), float(mu), int(strategy)))
+
+    def ns3_state(self, k):
+        out = np.zeros(18)
+        self._L.oipm_test_ns3_state(self._h, int(k), P_(out))
+        return dict(H_dual=out[:6].copy(), Hs=out[6:12].copy(), grad=out[12:15].copy(), z=out[15:18].copy())
+
+    def compute_barrier(self, z, s, dz, ds, alpha):
+        return float(self._L.oipm_test_compute_barrier(self._h, P_(F(z)), P_(F(s)), P_(F(dz)), P_(F(ds)), float(alpha)))
+
+    def unit_initialization(self):
+        z, s = np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
+        self._L.oipm_test_unit_initialization(self._h, P_(z), P_(s))
+        return z[:self.m], s[:self.m]
+
+    def affine_ds_ex(self, s):
+        y = np.zeros(max(self.m, 1))
+        self._L.oipm_test_affine_ds_ex(self._h, P_(y), P_(F(s)))
+        return y[:self.m]
 
     def get_Hs(self):
         out = np.zeros(max(int(self._L.oipm_nHs(self._h)), 1))

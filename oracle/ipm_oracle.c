@@ -18,7 +18,11 @@
  *
  * Not restated (documented gaps): the inf-bound presolve row elimination
  * (presolver.rs) -- b is capped at 1e20 exactly as problemdata.rs:130-131 does
- * but rows are not dropped; chordal decomposition; Exp/Pow/GenPow cones.
+ * but rows are not dropped; chordal decomposition; the GenPow cone.
+ * The exponential and 3-D power cones (nonsymmetric path: unit initialisation,
+ * dual / primal-dual scaling, third-order correction, backtracking step
+ * length, barrier line search, strategy checkpoints) live in nonsym_oracle.h
+ * and are pinned on tests/basic_expcone.rs, basic_powcone.rs, mixed_conic.rs.
  * The LDL ordering is passed in (see qdldl_oracle.c header).
  *
  * Function -> reference map (all under /root/reference/src)
@@ -47,6 +51,8 @@
 #include <time.h>
 
 typedef int64_t idx;
+static double vnorm(const double *a, idx n);
+#include "nonsym_oracle.h"
 
 /* from qdldl_oracle.c */
 typedef struct oq_s oq_t;
@@ -62,7 +68,8 @@ int oq_dinv_is_finite(const oq_t *f);
 idx oq_nnzL(const oq_t *f);
 idx oq_regularize_count(const oq_t *f);
 
-enum { CONE_ZERO = 0, CONE_NONNEG = 1, CONE_SOC = 2, CONE_PSD = 3 };
+enum { CONE_ZERO = 0, CONE_NONNEG = 1, CONE_SOC = 2, CONE_PSD = 3, CONE_EXP = 4, CONE_POW = 5 };
+enum { SCALING_PRIMAL_DUAL = 0, SCALING_DUAL = 1 };
 enum { ST_UNSOLVED = 0, ST_SOLVED, ST_PRIMAL_INFEASIBLE, ST_DUAL_INFEASIBLE, ST_ALMOST_SOLVED,
        ST_ALMOST_PRIMAL_INFEASIBLE, ST_ALMOST_DUAL_INFEASIBLE, ST_MAX_ITERATIONS, ST_MAX_TIME,
        ST_NUMERICAL_ERROR, ST_INSUFFICIENT_PROGRESS };
@@ -86,6 +93,8 @@ typedef struct {
     double iterative_refinement_reltol, iterative_refinement_abstol;
     int32_t iterative_refinement_max_iter;
     double iterative_refinement_stop_ratio;
+    /* nonsymmetric cones only (settings.rs:114-124) */
+    double linesearch_backtrack_step, min_switch_step_length;
 } oipm_settings;
 
 void oipm_default_settings(oipm_settings *s)
@@ -105,6 +114,7 @@ void oipm_default_settings(oipm_settings *s)
     s->iterative_refinement_enable = 1; s->iterative_refinement_reltol = 1e-13;
     s->iterative_refinement_abstol = 1e-12; s->iterative_refinement_max_iter = 10;
     s->iterative_refinement_stop_ratio = 5.0;
+    s->linesearch_backtrack_step = 0.8; s->min_switch_step_length = 0.1;
 }
 
 typedef struct {
@@ -122,6 +132,8 @@ typedef struct {
     idx *map_u, *map_v; idx map_D[2];
     /* PSD triangle cone (psdtrianglecone.rs:12-60): matrix dimension and dense work data */
     idx psd_n; double *R, *Rinv, *lisqrt, *HsM, *W1, *W2, *W3, *wv;
+    /* exponential / 3-D power cone state */
+    ns3_t *ns;
 } cone_t;
 
 typedef struct { idx m, n; idx *colptr, *rowval; double *nzval; } csc;
@@ -131,7 +143,7 @@ typedef struct {
     csc P, A;              /* internal (scaled) copies; P is triu */
     double *q, *b;
     double normq, normb;
-    idx ncones; cone_t *cones; idx degree;
+    idx ncones; cone_t *cones; idx degree; int all_symmetric;
     /* equilibration */
     double *d, *dinv, *e, *einv, c;
     /* KKT */
@@ -488,7 +500,29 @@ static void psd_lambda_inv_circ(cone_t *c, double *x, const double *z)
 
 static int cone_is_sparse(const cone_t *c) { return c->type == CONE_SOC && c->sparse; }
 static int cone_Hs_diag(const cone_t *c) { return c->type == CONE_ZERO || c->type == CONE_NONNEG || (c->type == CONE_SOC && c->sparse); }
-static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : (c->type == CONE_PSD ? c->psd_n : 1)); }
+static int cone_is_ns3(const cone_t *c) { return c->type == CONE_EXP || c->type == CONE_POW; }
+static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : (c->type == CONE_PSD ? c->psd_n : (cone_is_ns3(c) ? 3 : 1))); }
+
+/* Cone::unit_initialization of every cone type (zerocone.rs:71-74, nonnegativecone.rs:68-71, socone.rs:114-119,
+   psdtrianglecone.rs:131-136, expcone.rs:88-94, powcone.rs:79-87) */
+static void cones_unit_initialization(oipm_t *S, double *z_, double *s_)
+{
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; double *z = z_ + c->off, *s = s_ + c->off; idx n = c->dim;
+        for (idx i = 0; i < n; i++) { s[i] = 0.0; z[i] = 0.0; }
+        if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) { z[i] = 1.0; s[i] = 1.0; }
+        else if (c->type == CONE_SOC) { s[0] += 1.0; z[0] += 1.0; }
+        else if (c->type == CONE_PSD) for (idx j = 0; j < c->psd_n; j++) { s[(j * (j + 3)) >> 1] += 1.0; z[(j * (j + 3)) >> 1] += 1.0; }
+        else if (c->type == CONE_EXP) {
+            s[0] = -1.051383945322714; s[1] = 0.556409619469370; s[2] = 1.258967884768947;
+            z[0] = s[0]; z[1] = s[1]; z[2] = s[2];
+        } else if (c->type == CONE_POW) {
+            double a = c->ns->alpha;
+            s[0] = sqrt(1.0 + a); s[1] = sqrt(1.0 + (1.0 - a)); s[2] = 0.0;
+            z[0] = s[0]; z[1] = s[1]; z[2] = s[2];
+        }
+    }
+}
 
 static void cones_set_identity(oipm_t *S)
 {
@@ -511,7 +545,7 @@ static void cones_set_identity(oipm_t *S)
     }
 }
 
-static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_)
+static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_, double mu, int strategy)
 {
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k];
@@ -558,6 +592,17 @@ static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_)
             }
         } else if (c->type == CONE_PSD) {
             if (!psd_update_scaling(c, s, z)) return 0;
+        } else if (cone_is_ns3(c)) {
+            /* expcone.rs:103-120, powcone.rs:96-113, nonsymmetric_common.rs:53-64 */
+            ns3_t *K = c->ns;
+            if (c->type == CONE_EXP) exp_update_dual_grad_H(K, z); else pow_update_dual_grad_H(K, z);
+            if (strategy == SCALING_DUAL) ns3_use_dual_scaling(K, mu);
+            else {
+                double zt[3];
+                if (c->type == CONE_EXP) exp_gradient_primal(s, zt); else pow_gradient_primal(s, K->alpha, zt);
+                ns3_use_primal_dual_scaling(K, s, z, zt);
+            }
+            K->z[0] = z[0]; K->z[1] = z[1]; K->z[2] = z[2];
         }
     }
     return 1;
@@ -585,7 +630,7 @@ static void cones_get_Hs(const oipm_t *S, double *Hs)
         } else if (c->type == CONE_PSD) {
             idx N = c->dim, t = 0;     /* pack_triu, dense/types.rs:187-201 */
             for (idx col = 0; col < N; col++) for (idx row = 0; row <= col; row++) H[t++] = MAT(c->HsM, N, row, col);
-        }
+        } else if (cone_is_ns3(c)) for (int i = 0; i < 6; i++) H[i] = c->ns->Hs[i];   /* expcone.rs:126-129 */
     }
 }
 
@@ -605,11 +650,11 @@ static void cones_mul_Hs(oipm_t *S, double *y_, const double *x_)
         } else if (c->type == CONE_PSD) {
             psd_mul_Wx(c, 0, c->wv, x, 1.0, 0.0, c->R);     /* work = W x  */
             psd_mul_Wx(c, 1, y, c->wv, 1.0, 0.0, c->R);     /* y = W' work */
-        }
+        } else if (cone_is_ns3(c)) sym3_mul(c->ns->Hs, y, x);
     }
 }
 
-static void cones_affine_ds(const oipm_t *S, double *ds_)
+static void cones_affine_ds(const oipm_t *S, double *ds_, const double *s_)
 {
     for (idx k = 0; k < S->ncones; k++) {
         const cone_t *c = &S->cones[k]; double *ds = ds_ + c->off; idx n = c->dim;
@@ -617,6 +662,7 @@ static void cones_affine_ds(const oipm_t *S, double *ds_)
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) ds[i] = c->lam[i] * c->lam[i];
         else if (c->type == CONE_SOC) soc_circ(ds, c->lam, c->lam, n);
         else if (c->type == CONE_PSD) { for (idx i = 0; i < n; i++) ds[i] = 0.0; for (idx k = 0; k < c->psd_n; k++) ds[tri_index(k)] = c->lam[k] * c->lam[k]; }
+        else if (cone_is_ns3(c)) for (idx i = 0; i < n; i++) ds[i] = s_[c->off + i];      /* expcone.rs:135-137 */
     }
 }
 
@@ -627,6 +673,13 @@ static void cones_combined_ds_shift(oipm_t *S, double *shift_, double *sz_, doub
         cone_t *c = &S->cones[k]; idx n = c->dim;
         double *shift = shift_ + c->off, *sz = sz_ + c->off, *ss = ss_ + c->off;
         if (c->type == CONE_ZERO) { for (idx i = 0; i < n; i++) shift[i] = 0.0; continue; }
+        if (cone_is_ns3(c)) {
+            /* expcone.rs:139-148: third-order correction with the scaling-point z, inputs step_s, step_z */
+            double eta[3] = {0, 0, 0};
+            if (c->type == CONE_EXP) exp_higher_correction(c->ns, eta, ss, sz); else pow_higher_correction(c->ns, eta, ss, sz);
+            for (int i = 0; i < 3; i++) shift[i] = c->ns->grad[i] * sigmamu - eta[i];
+            continue;
+        }
         double *tmp = shift;
         if (c->type == CONE_PSD) {
             memcpy(tmp, sz, (size_t)n * sizeof(double)); psd_mul_Wx(c, 0, sz, tmp, 1.0, 0.0, c->R);
@@ -654,6 +707,7 @@ static void cones_ds_from_dz_offset(oipm_t *S, double *out_, const double *ds_, 
         if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) out[i] = 0.0;
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) out[i] = ds[i] / z[i];
         else if (c->type == CONE_PSD) { psd_lambda_inv_circ(c, c->wv, ds); psd_mul_Wx(c, 1, out, c->wv, 1.0, 0.0, c->R); }
+        else if (cone_is_ns3(c)) for (idx i = 0; i < n; i++) out[i] = ds[i];              /* expcone.rs:150-152 */
         else {
             double resz = soc_residual(z, n);
             double l1ds1 = vdot(c->lam + 1, ds + 1, n - 1), w1ds1 = vdot(c->w + 1, ds + 1, n - 1);
@@ -670,11 +724,29 @@ static void cones_ds_from_dz_offset(oipm_t *S, double *out_, const double *ds_, 
     }
 }
 
+/* nonsymmetric_common.rs:160-189 */
+static double ns3_backtrack_search(const cone_t *c, const double *dq, const double *q, double a_init, double a_min,
+                                   double step, int dual)
+{
+    double a = a_init, work[3];
+    for (;;) {
+        for (int i = 0; i < 3; i++) work[i] = 1.0 * q[i] + a * dq[i];
+        int ok = c->type == CONE_EXP ? (dual ? exp_is_dual_feasible(work) : exp_is_primal_feasible(work))
+                                     : (dual ? pow_is_dual_feasible(work, c->ns->alpha) : pow_is_primal_feasible(work, c->ns->alpha));
+        if (ok) break;
+        a *= step;
+        if (a < a_min) { a = 0.0; break; }
+    }
+    return a;
+}
+
+/* compositecone.rs:289-332: symmetric cones first, then back off from a full step, then the nonsymmetric ones */
 static double cones_step_length(oipm_t *S, const double *dz_, const double *ds_, const double *z_, const double *s_, double amax)
 {
     double alpha = amax;
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k]; idx n = c->dim;
+        if (cone_is_ns3(c)) continue;
         const double *dz = dz_ + c->off, *ds = ds_ + c->off, *z = z_ + c->off, *s = s_ + c->off;
         double az = alpha, as = alpha;
         if (c->type == CONE_NONNEG) {
@@ -692,7 +764,61 @@ static double cones_step_length(oipm_t *S, const double *dz_, const double *ds_,
         double m = az < as ? az : as;
         if (m < alpha) alpha = m;
     }
+    if (!S->all_symmetric) {
+        double ceil_ = 1.0 - sqrt(NS_EPS);
+        if (ceil_ < alpha) alpha = ceil_;
+        for (idx k = 0; k < S->ncones; k++) {
+            cone_t *c = &S->cones[k];
+            if (!cone_is_ns3(c)) continue;
+            const double *dz = dz_ + c->off, *ds = ds_ + c->off, *z = z_ + c->off, *s = s_ + c->off;
+            /* expcone.rs:154-174 */
+            double az = ns3_backtrack_search(c, dz, z, alpha, S->set.min_terminate_step_length, S->set.linesearch_backtrack_step, 1);
+            double as = ns3_backtrack_search(c, ds, s, alpha, S->set.min_terminate_step_length, S->set.linesearch_backtrack_step, 0);
+            double m = az < as ? az : as;
+            if (m < alpha) alpha = m;
+        }
+    }
     return alpha;
+}
+
+/* Cone::compute_barrier summed over the cones (compositecone.rs:334-345; nonnegativecone.rs:155-166,
+   socone.rs:304-314, zerocone.rs:129-131, psdtrianglecone.rs:281-306, expcone.rs:176-187) */
+static double cones_compute_barrier(oipm_t *S, const double *z_, const double *s_, const double *dz_, const double *ds_, double a)
+{
+    double barrier = 0.0;
+    for (idx k = 0; k < S->ncones; k++) {
+        cone_t *c = &S->cones[k]; idx n = c->dim;
+        const double *dz = dz_ + c->off, *ds = ds_ + c->off, *z = z_ + c->off, *s = s_ + c->off;
+        if (c->type == CONE_NONNEG) {
+            double b = 0.0;
+            for (idx i = 0; i < n; i++) { double si = s[i] + a * ds[i], zi = z[i] + a * dz[i]; b -= logsafe(si * zi); }
+            barrier += b;
+        } else if (c->type == CONE_SOC) {
+            /* _soc_residual_shifted (socone.rs:410-417) */
+            double rs, rz;
+            { double x0 = s[0] + a * ds[0]; double *t = dvec(n); for (idx i = 1; i < n; i++) t[i - 1] = s[i] + a * ds[i]; double nm = vnorm(t, n - 1); free(t); rs = (x0 - nm) * (x0 + nm); }
+            { double x0 = z[0] + a * dz[0]; double *t = dvec(n); for (idx i = 1; i < n; i++) t[i - 1] = z[i] + a * dz[i]; double nm = vnorm(t, n - 1); free(t); rz = (x0 - nm) * (x0 + nm); }
+            barrier += (rs > 0.0 && rz > 0.0) ? -logsafe(rs * rz) * 0.5 : INFINITY;
+        } else if (c->type == CONE_PSD) {
+            double b = 0.0;
+            for (int pass = 0; pass < 2; pass++) {
+                const double *x = pass == 0 ? z : s, *dx = pass == 0 ? dz : ds;
+                for (idx i = 0; i < n; i++) c->wv[i] = 1.0 * x[i] + a * dx[i];
+                svec_to_mat(c->W1, c->psd_n, c->wv);
+                if (chol_lower(c->W2, c->W1, c->psd_n)) { double ld = 0.0; for (idx i = 0; i < c->psd_n; i++) ld += logsafe(MAT(c->W2, c->psd_n, i, i)); b -= 2.0 * ld; }
+                else b -= INFINITY;
+            }
+            barrier += b;
+        } else if (cone_is_ns3(c)) {
+            double cz[3] = {z[0] + a * dz[0], z[1] + a * dz[1], z[2] + a * dz[2]};
+            double cs[3] = {s[0] + a * ds[0], s[1] + a * ds[1], s[2] + a * ds[2]};
+            double b = 0.0;
+            if (c->type == CONE_EXP) { b += exp_barrier_dual(cz); b += exp_barrier_primal(cs); }
+            else { b += pow_barrier_dual(cz, c->ns->alpha); b += pow_barrier_primal(cs, c->ns->alpha); }
+            barrier += b;
+        }
+    }
+    return barrier;
 }
 
 static void cones_margins(oipm_t *S, const double *z_, double *amin, double *bsum)
@@ -972,7 +1098,7 @@ static void equilibrate(oipm_t *S)
     for (idx i = 0; i < m; i++) ew[i] = 1.0;
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k];
-        if (c->type == CONE_SOC || c->type == CONE_PSD) {
+        if (c->type == CONE_SOC || c->type == CONE_PSD || cone_is_ns3(c)) {
             double mean = vmean(e + c->off, c->dim);
             for (idx i = 0; i < c->dim; i++) ew[c->off + i] = (1.0 / e[c->off + i]) * mean;
             changed = 1;
@@ -989,7 +1115,7 @@ void oipm_free(oipm_t *S)
     if (!S) return;
     csc_free(&S->P); csc_free(&S->A); free(S->q); free(S->b);
     for (idx k = 0; k < S->ncones; k++) { cone_t *c = &S->cones[k]; free(c->w); free(c->lam); free(c->u); free(c->v); free(c->map_u); free(c->map_v);
-        free(c->R); free(c->Rinv); free(c->lisqrt); free(c->HsM); free(c->W1); free(c->W2); free(c->W3); free(c->wv); }
+        free(c->R); free(c->Rinv); free(c->lisqrt); free(c->HsM); free(c->W1); free(c->W2); free(c->W3); free(c->wv); free(c->ns); }
     free(S->cones); free(S->d); free(S->dinv); free(S->e); free(S->einv);
     if (S->K.colptr) csc_free(&S->K);
     free(S->map_P); free(S->map_A); free(S->map_Hs); free(S->map_diagP); free(S->map_diag_full);
@@ -1005,9 +1131,19 @@ void oipm_free(oipm_t *S)
 
 /* P must be upper triangular CSC (the reference converts with to_triu,
    problemdata.rs:79-81; the Python caller does the same). */
+int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
+                const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
+                idx ncones_in, const int32_t *ctype, const idx *cdim, const double *cparam, const oipm_settings *set);
 int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
              const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
              idx ncones_in, const int32_t *ctype, const idx *cdim, const oipm_settings *set)
+{
+    return oipm_new_ex(out, n, m, Pp, Pi, Px, q, Ap, Ai, Ax, b, ncones_in, ctype, cdim, NULL, set);
+}
+/* cparam[k]: the exponent of a PowerConeT(alpha) (supportedcone.rs:36-38), ignored for the other cones */
+int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
+                const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
+                idx ncones_in, const int32_t *ctype, const idx *cdim, const double *cparam, const oipm_settings *set)
 {
     *out = NULL;
     oipm_t *S = (oipm_t *)calloc(1, sizeof(oipm_t));
@@ -1023,6 +1159,7 @@ int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const dou
     idx nc = 0, k = 0;
     while (k < ncones_in) {
         int t = ctype[k]; idx dm = cdim[k];
+        if (t == CONE_EXP || t == CONE_POW) dm = 3;
         idx numel = (t == CONE_PSD) ? dm * (dm + 1) / 2 : dm;
         if (numel == 0) { k++; continue; }
         int collapsible = (t == CONE_NONNEG) || (t == CONE_SOC && dm == 1) || (t == CONE_PSD && dm == 1);
@@ -1043,16 +1180,23 @@ int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const dou
         } else {
             if (t == CONE_SOC && dm < 2) { oipm_free(S); return -2; }
             S->cones[nc].type = t; S->cones[nc].dim = (t == CONE_PSD) ? dm * (dm + 1) / 2 : dm;
-            S->cones[nc].psd_n = (t == CONE_PSD) ? dm : 0; nc++; k++;
+            S->cones[nc].psd_n = (t == CONE_PSD) ? dm : 0;
+            if (t == CONE_EXP || t == CONE_POW) {
+                S->cones[nc].ns = (ns3_t *)calloc(1, sizeof(ns3_t));
+                S->cones[nc].ns->alpha = (t == CONE_POW && cparam) ? cparam[k] : 0.5;
+                if (t == CONE_POW && !(S->cones[nc].ns->alpha > 0.0 && S->cones[nc].ns->alpha < 1.0)) { oipm_free(S); return -3; }
+            }
+            nc++; k++;
         }
     }
     S->ncones = nc;
-    idx off = 0; S->degree = 0;
+    idx off = 0; S->degree = 0; S->all_symmetric = 1;
     for (idx c = 0; c < nc; c++) {
         cone_t *cn = &S->cones[c];
+        if (cone_is_ns3(cn)) S->all_symmetric = 0;
         cn->off = off; off += cn->dim;
         S->degree += cone_degree(cn);
-        if (cn->type != CONE_ZERO) { cn->w = dvec(cn->dim); cn->lam = dvec(cn->dim); }
+        if (cn->type != CONE_ZERO && !cone_is_ns3(cn)) { cn->w = dvec(cn->dim); cn->lam = dvec(cn->dim); }
         if (cn->type == CONE_PSD) {
             idx n2 = cn->psd_n * cn->psd_n;
             cn->R = dvec(n2); cn->Rinv = dvec(n2); cn->lisqrt = dvec(cn->psd_n); cn->HsM = dvec(cn->dim * cn->dim);
@@ -1282,6 +1426,33 @@ static double calc_step_length(oipm_t *S, int combined)
     return a;
 }
 
+/* variables.rs:205-228 */
+static double variables_barrier(oipm_t *S, double a)
+{
+    double central_coef = (double)(S->degree + 1);
+    double cur_tau = S->vtau + a * S->ltau, cur_kap = S->vkap + a * S->lkap;
+    double sz = 0.0;
+    for (idx i = 0; i < S->m; i++) { double si = S->vs[i] + a * S->ls[i], zi = S->vz[i] + a * S->lz[i]; sz += si * zi; }
+    double mu = (sz + cur_tau * cur_kap) / central_coef;
+    double barrier = central_coef * logsafe(mu) - logsafe(cur_tau) - logsafe(cur_kap);
+    barrier += cones_compute_barrier(S, S->vz, S->vs, S->lz, S->ls, a);
+    return barrier;
+}
+/* core/solver.rs:548-584 */
+static double get_step_length(oipm_t *S, int combined, int scaling)
+{
+    double a = calc_step_length(S, combined);
+    if (!S->all_symmetric && combined && scaling == SCALING_DUAL) {
+        double step = S->set.linesearch_backtrack_step;
+        for (int it = 0; it < 50; it++) {
+            double barrier = variables_barrier(S, a);
+            if (barrier < 1.0) return a;
+            a = step * a;
+        }
+    }
+    return a;
+}
+
 static void save_prev(oipm_t *S)
 {
     oipm_info *I = &S->info;
@@ -1312,13 +1483,20 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
     double t0 = now_s();
     I->status = ST_UNSOLVED; I->iterations = 0;
     I->t_kkt_update = I->t_kkt_solve = I->t_scale_cones = 0; I->n_refactor = I->n_ldl_solve = 0;
-    /* default start: all supported cones are symmetric */
-    cones_set_identity(S);
-    kktsystem_update(S);
-    solve_initial_point(S);
-    shift_to_cone_interior(S, S->vs, 1);
-    shift_to_cone_interior(S, S->vz, 0);
+    /* default start (core/solver.rs:525-541) */
+    if (S->all_symmetric) {
+        cones_set_identity(S);
+        kktsystem_update(S);
+        solve_initial_point(S);
+        shift_to_cone_interior(S, S->vs, 1);
+        shift_to_cone_interior(S, S->vz, 0);
+    } else {
+        cones_unit_initialization(S, S->vz, S->vs);     /* variables.rs:173-179 */
+        for (idx i = 0; i < n; i++) S->vx[i] = 0.0;
+    }
     S->vtau = 1.0; S->vkap = 1.0;
+    /* every cone built here allows primal-dual scaling (only GenPow does not) */
+    int scaling = SCALING_PRIMAL_DUAL;
 
     for (;;) {
         residuals_update(S);
@@ -1331,11 +1509,14 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
         }
         if (check_termination(S, iter)) {
             if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] terminated status %d at iter %d (gap_abs %g gap_rel %g pres %g dres %g kt %g)\n", I->status, iter, I->gap_abs, I->gap_rel, I->res_primal, I->res_dual, I->ktratio);
-            if (I->status == ST_INSUFFICIENT_PROGRESS) reset_to_prev(S);
+            /* strategy_checkpoint_insufficient_progress (core/solver.rs:586-611) */
+            if (I->status != ST_INSUFFICIENT_PROGRESS) break;
+            reset_to_prev(S);
+            if (!S->all_symmetric && scaling == SCALING_PRIMAL_DUAL) { I->status = ST_UNSOLVED; scaling = SCALING_DUAL; continue; }
             break;
         }
         double ts = now_s();
-        int okscale = cones_update_scaling(S, S->vs, S->vz);
+        int okscale = cones_update_scaling(S, S->vs, S->vz, mu, scaling);
         I->t_scale_cones += now_s() - ts;
         if (!okscale) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] scaling failed at iter %d\n", iter); I->status = ST_NUMERICAL_ERROR; break; }
         iter += 1;
@@ -1343,11 +1524,11 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
         /* affine rhs */
         memcpy(S->rx_, S->rx, (size_t)n * sizeof(double));
         memcpy(S->rz_, S->rz, (size_t)m * sizeof(double));
-        cones_affine_ds(S, S->rs_);
+        cones_affine_ds(S, S->rs_, S->vs);
         S->rtau_ = S->rtau; S->rkap_ = S->vtau * S->vkap;
         ok = ok && kktsystem_solve(S, 0);
         if (ok) {
-            alpha = calc_step_length(S, 0);
+            alpha = get_step_length(S, 0, scaling);
             sigma = (1.0 - alpha) * (1.0 - alpha) * (1.0 - alpha);
             double mm = iter > 1 ? 1.0 : alpha;
             double dsm = sigma * mu;
@@ -1360,8 +1541,12 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
             for (idx i = 0; i < m; i++) S->rz_[i] = (1.0 - sigma) * S->rz[i] + 0.0 * S->rz_[i];
             ok = kktsystem_solve(S, 1);
         }
+        /* strategy_checkpoint_numerical_error (core/solver.rs:613-631) */
+        if (!ok && !S->all_symmetric && scaling == SCALING_PRIMAL_DUAL) { alpha = 0.0; scaling = SCALING_DUAL; continue; }
         if (!ok) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] kkt failure at iter %d\n", iter); I->status = ST_NUMERICAL_ERROR; alpha = 0.0; break; }
-        alpha = calc_step_length(S, 1);
+        alpha = get_step_length(S, 1, scaling);
+        /* strategy_checkpoint_small_step (core/solver.rs:633-651) */
+        if (!S->all_symmetric && scaling == SCALING_PRIMAL_DUAL && alpha < S->set.min_switch_step_length) { alpha = 0.0; scaling = SCALING_DUAL; continue; }
         if (alpha <= fmax(0.0, S->set.min_terminate_step_length)) { if (getenv("OIPM_DEBUG")) fprintf(stderr, "[oipm] small step %g at iter %d\n", alpha, iter); I->status = ST_INSUFFICIENT_PROGRESS; alpha = 0.0; break; }
         save_prev(S);
         for (idx i = 0; i < n; i++) S->vx[i] = alpha * S->lx[i] + 1.0 * S->vx[i];
@@ -1399,11 +1584,24 @@ void oipm_get_solution(oipm_t *S, double *x, double *z, double *s, double *obj, 
 void oipm_get_info(const oipm_t *S, oipm_info *out) { *out = S->info; }
 
 /* expose single pieces for unit-level parity tests of the CUDA cone kernels */
-int oipm_test_update_scaling(oipm_t *S, const double *s, const double *z) { return cones_update_scaling(S, s, z); }
+int oipm_test_update_scaling(oipm_t *S, const double *s, const double *z) { return cones_update_scaling(S, s, z, 0.0, SCALING_PRIMAL_DUAL); }
+int oipm_test_update_scaling_ex(oipm_t *S, const double *s, const double *z, double mu, int strategy) { return cones_update_scaling(S, s, z, mu, strategy); }
+double oipm_test_compute_barrier(oipm_t *S, const double *z, const double *s, const double *dz, const double *ds, double a) { return cones_compute_barrier(S, z, s, dz, ds, a); }
+void oipm_test_unit_initialization(oipm_t *S, double *z, double *s) { cones_unit_initialization(S, z, s); }
+double oipm_test_wright_omega(double z) { return wright_omega(z); }
+/* per-cone state after update_scaling: out = [H_dual(6), Hs(6), grad(3), z(3)] */
+void oipm_test_ns3_state(const oipm_t *S, idx k, double *out)
+{
+    const ns3_t *K = S->cones[k].ns;
+    if (!K) return;
+    for (int i = 0; i < 6; i++) { out[i] = K->H_dual[i]; out[6 + i] = K->Hs[i]; }
+    for (int i = 0; i < 3; i++) { out[12 + i] = K->grad[i]; out[15 + i] = K->z[i]; }
+}
 void oipm_test_get_Hs(oipm_t *S, double *Hs) { cones_get_Hs(S, Hs); }
 idx oipm_nHs(const oipm_t *S) { return S->nHs; }
 void oipm_test_mul_Hs(oipm_t *S, double *y, const double *x) { cones_mul_Hs(S, y, x); }
-void oipm_test_affine_ds(oipm_t *S, double *ds) { cones_affine_ds(S, ds); }
+void oipm_test_affine_ds(oipm_t *S, double *ds) { cones_affine_ds(S, ds, S->vs); }
+void oipm_test_affine_ds_ex(oipm_t *S, double *ds, const double *s) { cones_affine_ds(S, ds, s); }
 void oipm_test_combined_ds_shift(oipm_t *S, double *shift, double *sz, double *ss, double sm) { cones_combined_ds_shift(S, shift, sz, ss, sm); }
 void oipm_test_ds_from_dz_offset(oipm_t *S, double *out, const double *ds, const double *z) { cones_ds_from_dz_offset(S, out, ds, z); }
 double oipm_test_step_length(oipm_t *S, const double *dz, const double *ds, const double *z, const double *s, double amax) { return cones_step_length(S, dz, ds, z, s, amax); }

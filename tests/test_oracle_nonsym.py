@@ -1,0 +1,150 @@
+"""Pins the oracle's exponential / 3-D power cone path (oracle/nonsym_oracle.h + the nonsymmetric branches of
+oracle/ipm_oracle.c) against the reference's own known answers: tests/basic_expcone.rs, tests/basic_powcone.rs,
+tests/mixed_conic.rs, the Wright-omega points of expcone.rs:459-472 and the 3x3 kernels' tests
+(dense3x3/core.rs:96-117, cholesky.rs:69-93).  CPU only."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+
+
+def solve(P, q, A, b, cones, **kw):
+    ipm = oracle.IPM(P, q, A, b, cones, settings=oracle.default_settings(**kw) if kw else None)
+    ipm.set_perm(np.arange(ipm.N))
+    return ipm, ipm.solve()
+
+
+def expcone_data():  # basic_expcone.rs:5-36
+    P = sp.csc_matrix((3, 3))
+    c = np.array([-1., 0., 0.])
+    A1 = -sp.identity(3, format="csc")
+    A2 = sp.csc_matrix(np.array([[0., 1., 0.], [0., 0., 1.]]))
+    A = sp.vstack([A1, A2]).tocsc()
+    b = np.array([0., 0., 0., 1., np.exp(5.)])
+    return P, c, A, b, [("exp", 3), ("zero", 2)]
+
+
+def test_wright_omega():  # expcone.rs:459-472
+    L = oracle._ipm_lib()
+    for z in [1e-7, 1e-5, 1e-3, 1e-1, 1e1, 1e3, 1e5, 1e7, 1e9]:
+        y = L.oipm_test_wright_omega(z)
+        assert abs(z - (y + np.log(y))) / z < 1e-9
+
+
+def test_expcone_feasible():  # basic_expcone.rs:38-55
+    _, r = solve(*expcone_data())
+    assert r["status"] == "Solved"
+    assert np.linalg.norm(r["x"] - [5.0, 1.0, np.exp(5.0)]) <= 1e-6
+    assert abs(r["obj_val"] + 5.0) <= 1e-6
+
+
+def test_expcone_primal_infeasible():  # basic_expcone.rs:57-72
+    P, c, A, b, cones = expcone_data()
+    b = b.copy(); b[4] = -1.
+    _, r = solve(P, c, A, b, cones)
+    assert r["status"] == "PrimalInfeasible"
+
+
+def test_expcone_dual_infeasible():  # basic_expcone.rs:74-91
+    P = sp.csc_matrix((3, 3))
+    _, r = solve(P, [-1., 0., 0.], -sp.identity(3, format="csc"), np.zeros(3), [("exp", 3)])
+    assert r["status"] == "DualInfeasible"
+
+
+def test_powcone():  # basic_powcone.rs:5-52
+    n = 6
+    P = sp.csc_matrix((n, n))
+    c = np.array([0., 0., -1., 0., 0., -1.])
+    A2 = sp.csc_matrix(np.array([[1., 2., 0., 3., 0., 0.], [0., 0., 0., 0., 1., 0.]]))
+    A = sp.vstack([-sp.identity(n, format="csc"), A2]).tocsc()
+    b = np.concatenate([np.zeros(n), [3., 1.]])
+    _, r = solve(P, c, A, b, [("pow", 0.6), ("pow", 0.1), ("zero", 2)])
+    assert r["status"] == "Solved"
+    assert abs(r["obj_val"] + 1.8458) <= 1e-3
+
+
+def mixed_conic_data():  # mixed_conic.rs:5-27
+    n = 3
+    I3 = sp.identity(n, format="csc")
+    A = sp.vstack([I3] * 5).tocsc()
+    cones = [("zero", 3), ("nonneg", 3), ("soc", 3), ("pow", 0.5), ("exp", 3)]
+    return sp.identity(n, format="csc"), np.ones(3), A, np.zeros(5 * n), cones
+
+
+def test_mixed_conic_feasible():  # mixed_conic.rs:29-35
+    _, r = solve(*mixed_conic_data())
+    assert r["status"] == "Solved"
+    assert abs(r["obj_val"]) <= 1e-8
+
+
+def test_mixed_conic_dual_scaling_strategy():  # mixed_conic.rs:37-46 (min_switch_step_length forces the dual strategy)
+    _, r = solve(*mixed_conic_data(), min_switch_step_length=0.999)
+    assert r["status"] == "Solved"
+    assert abs(r["obj_val"]) <= 1e-8
+
+
+# ---- consistency of the cone kernels themselves (properties the barrier calculus guarantees) ----
+def _one_cone(kind, par):
+    P = sp.csc_matrix((3, 3))
+    ipm = oracle.IPM(P, np.zeros(3), -sp.identity(3, format="csc"), np.zeros(3), [(kind, par)])
+    return ipm
+
+
+def _sym3(d):
+    return np.array([[d[0], d[1], d[3]], [d[1], d[2], d[4]], [d[3], d[4], d[5]]])
+
+
+@pytest.mark.parametrize("kind,par", [("exp", 3), ("pow", 0.6), ("pow", 0.1), ("pow", 0.5)])
+def test_dual_gradient_and_hessian_match_finite_differences(kind, par):
+    ipm = _one_cone(kind, par)
+    z0, s0 = ipm.unit_initialization()
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        z = z0 + 0.1 * rng.standard_normal(3)
+        s = s0 + 0.1 * rng.standard_normal(3)
+        assert ipm.update_scaling_ex(s, z, 1.0, 1)
+        st = ipm.ns3_state(0)
+        zero = np.zeros(3)
+        # barrier(z,s,.,.,0) = f*(z) + f(s); differentiate in z with s fixed
+        f = lambda zz: ipm.compute_barrier(zz, s, zero, zero, 0.0)
+        h = 1e-5
+        g = np.array([(f(z + h * e) - f(z - h * e)) / (2 * h) for e in np.eye(3)])
+        assert np.allclose(g, st["grad"], rtol=1e-6, atol=1e-6)
+        H = np.array([[(f(z + h * a + h * b) - f(z + h * a - h * b) - f(z - h * a + h * b) + f(z - h * a - h * b)) / (4 * h * h)
+                       for b in np.eye(3)] for a in np.eye(3)])
+        assert np.allclose(H, _sym3(st["H_dual"]), rtol=2e-4, atol=2e-4)
+        # dual scaling: Hs = mu * H
+        assert np.allclose(st["Hs"], st["H_dual"])
+
+
+@pytest.mark.parametrize("kind,par", [("exp", 3), ("pow", 0.6), ("pow", 0.25)])
+def test_primal_dual_scaling_secant_equations(kind, par):
+    """The primal-dual scaling satisfies Hs z = s and Hs zt = st (nonsymmetric_common.rs:72-143)."""
+    ipm = _one_cone(kind, par)
+    z0, s0 = ipm.unit_initialization()
+    rng = np.random.default_rng(5)
+    hits = 0
+    for _ in range(10):
+        z = z0 + 0.15 * rng.standard_normal(3)
+        s = s0 + 0.15 * rng.standard_normal(3)
+        assert ipm.update_scaling_ex(s, z, 1.0, 0)
+        st = ipm.ns3_state(0)
+        Hs = _sym3(st["Hs"])
+        if np.allclose(st["Hs"], (s @ z / 3.0) * st["H_dual"]):
+            continue        # fell back to the dual scaling
+        hits += 1
+        assert np.allclose(Hs @ z, s, rtol=1e-9, atol=1e-9)
+        assert np.all(np.linalg.eigvalsh(Hs) > 0)
+    assert hits >= 5
+
+
+def test_unit_initialization_is_interior_and_central():
+    for kind, par in [("exp", 3), ("pow", 0.3)]:
+        ipm = _one_cone(kind, par)
+        z, s = ipm.unit_initialization()
+        assert ipm.step_length(np.zeros(3), np.zeros(3), z, s, 1.0) > 0.9
+        # on the central path s = -mu g*(z) with mu = <s,z>/3
+        assert ipm.update_scaling_ex(s, z, 1.0, 1)
+        g = ipm.ns3_state(0)["grad"]
+        assert np.allclose(s, -(s @ z / 3.0) * g, atol=1e-6)
