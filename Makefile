@@ -30,6 +30,12 @@ $(ORACLE): $(ORACLE_SRCS) $(wildcard oracle/*.h)
 	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS) -lm
 
 clean:
-	rm -f $(CSRC)/*.o $(LIB) $(ORACLE)
+	rm -f $(CSRC)/*.o $(LIB) $(ORACLE) tests/host_harness/*.so
 
 .PHONY: all clean
+
+# host build of the nonsymmetric cones' thread bodies (test infrastructure, see tests/host_harness/ns3_host.cpp)
+HARNESS := tests/host_harness/libns3_host.so
+$(HARNESS): tests/host_harness/ns3_host.cpp $(CSRC)/cones_nonsym.cuh
+	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -o $@ $<
+all: $(HARNESS)

@@ -331,7 +331,8 @@ def order(n, colptr, rowval, kind=ORDER_AMD, dense_scale=1.5, nd_leaf=200):
 # ===========================================================================
 # Level 2: device-resident solver (cipm_* / ckkt_* / ccone_*)
 # ===========================================================================
-CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3}
+CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3, "exp": 4, "pow": 5}
+SCALING_PRIMAL_DUAL, SCALING_DUAL = 0, 1
 STATUS_NAMES = ["Unsolved", "Solved", "PrimalInfeasible", "DualInfeasible", "AlmostSolved",
                 "AlmostPrimalInfeasible", "AlmostDualInfeasible", "MaxIterations", "MaxTime",
                 "NumericalError", "InsufficientProgress"]
@@ -358,6 +359,7 @@ class cipm_settings(C.Structure):
         ("iterative_refinement_reltol", C.c_double), ("iterative_refinement_abstol", C.c_double),
         ("iterative_refinement_max_iter", C.c_int32),
         ("iterative_refinement_stop_ratio", C.c_double),
+        ("linesearch_backtrack_step", C.c_double), ("min_switch_step_length", C.c_double),
     ]
 
 
@@ -387,6 +389,8 @@ EXPORTED_SYMBOLS += [
     "ckkt_update_A", "ckkt_get_values", "ccone_set_identity_scaling", "ccone_update_scaling",
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
+    "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
+    "ccone_affine_ds_ex", "ccone_compute_barrier",
 ]
 
 _l2_ready = False
@@ -403,6 +407,14 @@ def _lib2():
     L.cipm_create.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p, u64p, u64p, f64p,
                               f64p, C.c_uint64, C.POINTER(C.c_int32), u64p, C.POINTER(cipm_settings),
                               C.POINTER(cldl_opts), u64p]
+    L.cipm_create_ex.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p, u64p, u64p, f64p,
+                                 f64p, C.c_uint64, C.POINTER(C.c_int32), u64p, f64p, C.POINTER(cipm_settings),
+                                 C.POINTER(cldl_opts), u64p]
+    L.ccone_is_symmetric.argtypes = [vp]
+    L.ccone_unit_initialization.argtypes = [vp, f64p, f64p]
+    L.ccone_update_scaling_ex.argtypes = [vp, f64p, f64p, C.c_double, C.c_int]
+    L.ccone_affine_ds_ex.argtypes = [vp, f64p, f64p]
+    L.ccone_compute_barrier.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double, f64p]
     L.cipm_destroy.argtypes = [vp]
     L.cipm_destroy.restype = None
     L.cipm_solve.argtypes = [vp]
@@ -459,7 +471,9 @@ class CudaSolver:
     and ``solve()`` (default/solver.rs:57-126, core/solver.rs:242-465).
 
     P: scipy sparse (symmetric or upper triangle; converted to triu like
-    problemdata.rs:79-81); A: scipy sparse; cones: list of (kind, dim).
+    problemdata.rs:79-81); A: scipy sparse; cones: list of (kind, dim) with kind in
+    {"zero", "nonneg", "soc", "psd"}, ("exp", 3) for an ExponentialConeT() and
+    ("pow", alpha) for a PowerConeT(alpha).
     """
 
     def __init__(self, P, q, A, b, cones, settings=None, *, ordering=ORDER_BEST, kkt_perm=None,
@@ -477,18 +491,19 @@ class CudaSolver:
         L.cldl_default_opts(C.byref(o))
         o.ordering, o.device, o.max_panel, o.nd_leaf = ordering, device, max_panel, nd_leaf
         ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
-        cd = _u64([d for _, d in cones])
+        cd = _u64([3 if k in ("exp", "pow") else d for k, d in cones])
+        cpar = _f64([float(d) if k == "pow" else 0.0 for k, d in cones])
         Pp, Pi, Px = _u64(P.indptr), _u64(P.indices), _f64(P.data)
         Ap, Ai, Ax = _u64(A.indptr), _u64(A.indices), _f64(A.data)
         qq, bb = _f64(q), _f64(b)
         pm = _u64(kkt_perm) if kkt_perm is not None else None
         h = C.c_void_p()
-        rc = L.cipm_create(C.byref(h), self.n, self.m, _p(Pp, C.c_uint64), _p(Pi, C.c_uint64), _p(Px, C.c_double),
-                           _p(qq, C.c_double), _p(Ap, C.c_uint64), _p(Ai, C.c_uint64), _p(Ax, C.c_double),
-                           _p(bb, C.c_double), len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)),
-                           _p(cd, C.c_uint64), C.byref(self.settings), C.byref(o),
-                           _p(pm, C.c_uint64) if pm is not None else None)
-        _check(rc, "cipm_create")
+        rc = L.cipm_create_ex(C.byref(h), self.n, self.m, _p(Pp, C.c_uint64), _p(Pi, C.c_uint64), _p(Px, C.c_double),
+                              _p(qq, C.c_double), _p(Ap, C.c_uint64), _p(Ai, C.c_uint64), _p(Ax, C.c_double),
+                              _p(bb, C.c_double), len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)),
+                              _p(cd, C.c_uint64), _p(cpar, C.c_double), C.byref(self.settings), C.byref(o),
+                              _p(pm, C.c_uint64) if pm is not None else None)
+        _check(rc, "cipm_create_ex")
         self._h = h
         self.N = int(L.cipm_kkt_dim(h))
 
@@ -596,6 +611,32 @@ class CudaSolver:
     def cone_update_scaling(self, s, z):
         s, z = self._m(s), self._m(z)
         return bool(_check(self._L.ccone_update_scaling(self._h, _p(s, C.c_double), _p(z, C.c_double)), "update_scaling"))
+
+    def cone_is_symmetric(self):
+        return bool(_check(self._L.ccone_is_symmetric(self._h), "is_symmetric"))
+
+    def cone_unit_initialization(self):
+        z, s = np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
+        _check(self._L.ccone_unit_initialization(self._h, _p(z, C.c_double), _p(s, C.c_double)), "unit_initialization")
+        return z[:self.m], s[:self.m]
+
+    def cone_update_scaling_ex(self, s, z, mu, strategy):
+        s, z = self._m(s), self._m(z)
+        return bool(_check(self._L.ccone_update_scaling_ex(self._h, _p(s, C.c_double), _p(z, C.c_double), float(mu),
+                                                           int(strategy)), "update_scaling_ex"))
+
+    def cone_affine_ds_ex(self, s):
+        s = self._m(s)
+        y = np.zeros(max(self.m, 1))
+        _check(self._L.ccone_affine_ds_ex(self._h, _p(y, C.c_double), _p(s, C.c_double)), "affine_ds_ex")
+        return y[:self.m]
+
+    def cone_compute_barrier(self, z, s, dz, ds, alpha):
+        a, b, c, d = self._m(z), self._m(s), self._m(dz), self._m(ds)
+        out = C.c_double()
+        _check(self._L.ccone_compute_barrier(self._h, _p(a, C.c_double), _p(b, C.c_double), _p(c, C.c_double),
+                                             _p(d, C.c_double), float(alpha), C.byref(out)), "compute_barrier")
+        return out.value
 
     def cone_get_Hs(self):
         ln = int(self._L.ccone_Hs_len(self._h))

@@ -365,14 +365,22 @@ k_soc_step_length(ConeDev c, const double* __restrict__ dz_, const double* __res
 // --------------------------------------------------------------------- host
 #define CCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "[clarabel_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -20; } } while (0)
 
-int ConeSet::collapse(const int32_t* types, const uint64_t* dims, uint64_t n, std::vector<ConeSpec>& out) {
+int ConeSet::collapse(const int32_t* types, const uint64_t* dims, uint64_t n, std::vector<ConeSpec>& out,
+                      const double* params) {
   out.clear();
   uint64_t k = 0;
   auto numel = [](int t, uint64_t d) { return t == CT_PSD ? d * (d + 1) / 2 : d; };
   while (k < n) {
     const int t = types[k];
+    if (t < 0 || t > CT_POW) return -21;
+    if (t == CT_EXP || t == CT_POW) {   // 3 rows each, never merged (supportedcone.rs:105-161)
+      const double a = (t == CT_POW && params) ? params[k] : 0.0;
+      if (t == CT_POW && !(a > 0.0 && a < 1.0)) return -21;
+      out.push_back({t, 3, 0, a});
+      k++;
+      continue;
+    }
     const uint64_t d = dims[k];
-    if (t < 0 || t > CT_PSD) return -21;
     if (numel(t, d) == 0) { k++; continue; }
     const bool coll = (t == CT_NONNEG) || ((t == CT_SOC || t == CT_PSD) && d == 1);
     if (coll) {
@@ -414,7 +422,7 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
   cones = cs;
   stream = st;
   const int nc = (int)cs.size();
-  off.assign(nc, 0); boff.assign(nc, 0); sparse_flag.assign(nc, 0); soc_list.clear();
+  off.assign(nc, 0); boff.assign(nc, 0); sparse_flag.assign(nc, 0); soc_list.clear(); ns_list.clear(); all_symmetric = true;
   m = 0; nHs = 0; degree = 0; p = 0;
   std::vector<int> type(nc), dim(nc);
   for (int k = 0; k < nc; k++) {
@@ -425,7 +433,9 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
     const bool diag = cs[k].type == CT_ZERO || cs[k].type == CT_NONNEG || sp;
     nHs += diag ? cs[k].dim : cs[k].dim * (cs[k].dim + 1) / 2;
     m += cs[k].dim;
-    degree += cs[k].type == CT_ZERO ? 0 : (cs[k].type == CT_NONNEG ? cs[k].dim : (cs[k].type == CT_PSD ? cs[k].psd_n : 1));
+    const bool ns3c = cs[k].type == CT_EXP || cs[k].type == CT_POW;
+    degree += cs[k].type == CT_ZERO ? 0 : (cs[k].type == CT_NONNEG ? cs[k].dim : (cs[k].type == CT_PSD ? cs[k].psd_n : (ns3c ? 3 : 1)));
+    if (ns3c) { ns_list.push_back(k); all_symmetric = false; }
     if (cs[k].type == CT_SOC) soc_list.push_back(k);
     if (cs[k].type == CT_PSD) psd_list.push_back(k);
     if (sp) p += 2;
@@ -471,6 +481,11 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
     CCK(cudaMemset(dev.psd_R, 0, tb)); CCK(cudaMemset(dev.psd_Rinv, 0, tb)); CCK(cudaMemset(dev.psd_RRt, 0, tb));
     if (dev.npsd && psd_prepare()) return -20;
   }
+  {
+    std::vector<double> al(nc, 0.0);
+    for (int k = 0; k < nc; k++) al[k] = cs[k].param;
+    if (ns_prepare(al)) return -20;
+  }
   const size_t np = (size_t)RED_BLOCKS + soc_list.size() + psd_list.size() + 8;
   CCK(cudaMalloc((void**)&d_pmin, np * 8)); CCK(cudaMalloc((void**)&d_psum, np * 8));
   (void)g_row2blk_dummy;
@@ -483,6 +498,7 @@ void ConeSet::release() {
   fr(dev.w); fr(dev.lam); fr(dev.u); fr(dev.v); fr(dev.eta); fr(dev.dd); fr(dev.fail);
   fr(ws.partials); fr(ws.counter); fr(row2blk_dev); fr(d_pmin); fr(d_psum);
   fr(dev.psd_list); fr(dev.psd_n); fr(dev.psd_moff); fr(dev.psd_R); fr(dev.psd_Rinv); fr(dev.psd_RRt);
+  ns_release();
 }
 
 #define EW_GRID ((m + 255) / 256)
@@ -494,12 +510,13 @@ void ConeSet::set_identity_scaling() {
   if (dev.nsoc) k_soc_set_identity<<<(dev.nsoc + 127) / 128, 128, 0, stream>>>(dev);
   psd_set_identity();
 }
-void ConeSet::update_scaling(const double* s, const double* z) {
+void ConeSet::update_scaling(const double* s, const double* z, double mu, int strategy) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_update_scaling<<<EW_GRID, 256, 0, stream>>>(dev, s, z);
   if (dev.nsoc) k_soc_update_scaling<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, s, z);
   psd_update_scaling(s, z);
+  ns_update_scaling(s, z, mu, strategy);
 }
 void ConeSet::get_Hs(double* Hs, bool negate) {
   if (m == 0) return;
@@ -508,6 +525,7 @@ void ConeSet::get_Hs(double* Hs, bool negate) {
   k_ew_get_Hs<<<EW_GRID, 256, 0, stream>>>(dev, Hs, sg, row2blk_dev);
   if (dev.nsoc) k_soc_get_Hs<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, Hs, sg);
   psd_get_Hs(Hs, sg);
+  ns_get_Hs(Hs, sg);
 }
 void ConeSet::mul_Hs(double* y, const double* x) {
   if (m == 0) return;
@@ -515,13 +533,15 @@ void ConeSet::mul_Hs(double* y, const double* x) {
   k_ew_mul_Hs<<<EW_GRID, 256, 0, stream>>>(dev, y, x);
   if (dev.nsoc) k_soc_mul_Hs<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, y, x);
   psd_apply(0, y, const_cast<double*>(x), nullptr, 0.0);
+  ns_mul_Hs(y, x);
 }
-void ConeSet::affine_ds(double* ds) {
+void ConeSet::affine_ds(double* ds, const double* s) {
   if (m == 0) return;
   g_launches += 1 + (dev.nsoc ? 1 : 0);
   k_ew_affine_ds<<<EW_GRID, 256, 0, stream>>>(dev, ds);
   if (dev.nsoc) k_soc_affine_ds<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, ds);
   psd_apply(1, ds, nullptr, nullptr, 0.0);
+  if (s) ns_copy_rows(ds, s);      // expcone.rs:135-137
 }
 void ConeSet::combined_ds_shift(double* shift, double* step_z, double* step_s, double sigmamu) {
   if (m == 0) return;
@@ -529,6 +549,7 @@ void ConeSet::combined_ds_shift(double* shift, double* step_z, double* step_s, d
   k_ew_combined_shift<<<EW_GRID, 256, 0, stream>>>(dev, shift, step_z, step_s, sigmamu);
   if (dev.nsoc) k_soc_combined_shift<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, shift, step_z, step_s, sigmamu);
   psd_apply(2, shift, step_z, step_s, sigmamu);
+  ns_combined_shift(shift, step_z, step_s, sigmamu);
 }
 void ConeSet::ds_from_dz_offset(double* out, const double* ds, const double* z) {
   if (m == 0) return;
@@ -536,6 +557,7 @@ void ConeSet::ds_from_dz_offset(double* out, const double* ds, const double* z) 
   k_ew_ds_offset<<<EW_GRID, 256, 0, stream>>>(dev, out, ds, z);
   if (dev.nsoc) k_soc_ds_offset<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, out, ds, z);
   psd_apply(3, out, const_cast<double*>(ds), nullptr, 0.0);
+  ns_copy_rows(out, ds);           // expcone.rs:150-152
 }
 void ConeSet::step_length(const double* dz, const double* ds, const double* z, const double* s, double* alpha_slot) {
   if (m == 0) return;
@@ -543,6 +565,7 @@ void ConeSet::step_length(const double* dz, const double* ds, const double* z, c
   k_ew_step_length<<<red_grid(m), RED_THREADS, 0, stream>>>(dev, dz, ds, z, s, alpha_slot);
   if (dev.nsoc) k_soc_step_length<<<dev.nsoc, SOC_NT, 0, stream>>>(dev, dz, ds, z, s, alpha_slot);
   psd_step_length(dz, ds, alpha_slot);
+  ns_step_length(dz, ds, z, s, alpha_slot);   // symmetric cones first, nonsymmetric last (compositecone.rs:289-332)
 }
 void ConeSet::margins(const double* z, double* out2) {
   const int g = m ? red_grid(m) : 0;

@@ -1,4 +1,5 @@
-// Device cone engine (internal header): Zero / Nonnegative / second-order cones.
+// Device cone engine (internal header): Zero / Nonnegative / second-order / PSD-triangle cones and the
+// nonsymmetric exponential and 3-D power cones.
 //
 // Device counterpart of the reference's `Cone` trait and CompositeCone dispatch
 // (/root/reference/src/solver/core/cones/mod.rs:42-154, compositecone.rs:197-352).
@@ -16,7 +17,8 @@
 
 namespace cb {
 
-enum { CT_ZERO = 0, CT_NONNEG = 1, CT_SOC = 2, CT_PSD = 3 };
+enum { CT_ZERO = 0, CT_NONNEG = 1, CT_SOC = 2, CT_PSD = 3, CT_EXP = 4, CT_POW = 5 };
+enum { SCALING_PRIMAL_DUAL = 0, SCALING_DUAL = 1 };   // ScalingStrategy (cones/mod.rs)
 constexpr int SOC_NO_EXPANSION_MAX_SIZE = 4;  // socone.rs:46
 
 struct ConeDev {
@@ -41,12 +43,20 @@ struct ConeDev {
   const int* psd_n = nullptr;      // [ncones] matrix dimension (0 for other cones)
   const long long* psd_moff = nullptr;  // [ncones] offset into the n x n matrix arenas
   double *psd_R = nullptr, *psd_Rinv = nullptr, *psd_RRt = nullptr;
+  // exponential / 3-D power cones (cones_nonsym.cu): state in structure-of-arrays form, component j of the
+  // k-th nonsymmetric cone at [j*nns + k]
+  int nns = 0;
+  const int* ns_list = nullptr;      // cone ids
+  const double* ns_alpha = nullptr;  // [nns] exponent of a power cone
+  double *ns_Hd = nullptr, *ns_Hs = nullptr;     // [6*nns] dual Hessian, scaling block (packed triu)
+  double *ns_grad = nullptr, *ns_z = nullptr;    // [3*nns] dual gradient, z at the scaling point
+  int* ns_jmax = nullptr;            // backtracking count of the composite step length
 };
 
 constexpr int CB_PSD_MAX_N = 32;
 
 // dim = number of rows the cone occupies (numel); psd_n = matrix dimension of a PSD cone
-struct ConeSpec { int type; int dim; int psd_n = 0; };
+struct ConeSpec { int type; int dim; int psd_n = 0; double param = 0.0; };   // param: exponent of a power cone
 
 class ConeSet {
  public:
@@ -61,15 +71,17 @@ class ConeSet {
   double* d_psum = nullptr;
 
   // collapse like SupportedConeT::new_collapsed (supportedcone.rs:105-161)
-  static int collapse(const int32_t* types, const uint64_t* dims, uint64_t n, std::vector<ConeSpec>& out);
+  static int collapse(const int32_t* types, const uint64_t* dims, uint64_t n, std::vector<ConeSpec>& out,
+                      const double* params = nullptr);
   int init(const std::vector<ConeSpec>& cs, cudaStream_t st);
   void release();
 
   void set_identity_scaling();
-  void update_scaling(const double* s, const double* z);  // failure -> dev.fail
+  // failure -> dev.fail; mu and the scaling strategy only matter to the nonsymmetric cones
+  void update_scaling(const double* s, const double* z, double mu = 0.0, int strategy = SCALING_PRIMAL_DUAL);
   void get_Hs(double* Hs, bool negate);
   void mul_Hs(double* y, const double* x);
-  void affine_ds(double* ds);
+  void affine_ds(double* ds, const double* s = nullptr);   // s: current iterate, read by the nonsymmetric cones
   void combined_ds_shift(double* shift, double* step_z, double* step_s, double sigmamu);
   void ds_from_dz_offset(double* out, const double* ds, const double* z);
   // alpha slot must be pre-set to alpha_max by the caller (device double)
@@ -77,6 +89,23 @@ class ConeSet {
   // out2[0] = min margin, out2[1] = sum of positive margins
   void margins(const double* z, double* out2);
   void scaled_unit_shift(double* z, double alpha, bool primal);
+
+  // nonsymmetric pieces (cones_nonsym.cu)
+  std::vector<int> ns_list;
+  bool all_symmetric = true;
+  double ns_amin = 1e-4, ns_step = 0.8;   // min_terminate_step_length, linesearch_backtrack_step
+  int ns_prepare(const std::vector<double>& alpha_per_cone);
+  void ns_release();
+  void unit_initialization(double* z, double* s);
+  void ns_update_scaling(const double* s, const double* z, double mu, int strategy);
+  void ns_get_Hs(double* Hs, double sign);
+  void ns_mul_Hs(double* y, const double* x);
+  void ns_copy_rows(double* out, const double* in);
+  void ns_combined_shift(double* shift, const double* step_z, const double* step_s, double sigmamu);
+  void ns_step_length(const double* dz, const double* ds, const double* z, const double* s, double* alpha_slot);
+  // out[0] = sum of the cones' barrier functions at (z + alpha dz, s + alpha ds); partial = 4 doubles of scratch
+  void compute_barrier(const double* z, const double* s, const double* dz, const double* ds, double alpha,
+                       double* partial, double* out);
 
   // PSD pieces (cones_psd.cu)
   std::vector<int> psd_list;

@@ -112,7 +112,7 @@ static void dfree(const void* p) { if (p) cudaFree((void*)p); }
 // scalar slots shared between device reductions and the host
 enum Slot { S_NORMB = 0, S_NORME, S_MAXDIAG, S_QX, S_BZ, S_SZ, S_XPX, S_ALPHA, S_MARG0, S_MARG1,
             S_D0, S_D1, S_D2, S_D3, S_D4, S_D5, S_D6, S_D7, S_N0, S_N1, S_N2, S_N3, S_N4, S_N5, S_N6, S_N7,
-            S_NORMB2, S_NORME2, S_COUNT = 32 };
+            S_NORMB2, S_NORME2, S_BARR, S_BP0, S_BP1, S_BP2, S_BP3, S_SZSH, S_COUNT = 40 };
 
 struct Scalars {
   double* d = nullptr;  // device [S_COUNT]
@@ -598,7 +598,7 @@ class IPM {
   int init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const double* Pxv, const double* q_,
            const uint64_t* Ap, const uint64_t* Ai, const double* Axv, const double* b_, uint64_t ncones,
            const int32_t* ctype, const uint64_t* cdim, const cipm_settings& s, const cldl_opts& lo,
-           const int* perm);
+           const int* perm, const double* cparam = nullptr);
   void release();
   void equilibrate();
   int upload_problem();
@@ -619,7 +619,8 @@ class IPM {
   int kkt_solve_step(bool combined);
   int solve_initial_point();
   int shift_to_interior(double* v, bool primal);
-  int step_length(bool combined, double* alpha);
+  int step_length(bool combined, double* alpha, int scaling = SCALING_PRIMAL_DUAL);
+  int variables_barrier(double a, double* out);
 };
 
 void IPM::equilibrate() {
@@ -678,7 +679,8 @@ void IPM::equilibrate() {
   bool changed = false;
   std::fill(ew.begin(), ew.end(), 1.0);
   for (size_t k = 0; k < cones.cones.size(); k++)
-    if (cones.cones[k].type == CT_SOC || cones.cones[k].type == CT_PSD) {  // scalar scaling inside SOC / PSD cones (socone.rs:97-101, psdtrianglecone.rs:98-101)
+    if (cones.cones[k].type == CT_SOC || cones.cones[k].type == CT_PSD || cones.cones[k].type == CT_EXP ||
+        cones.cones[k].type == CT_POW) {  // scalar scaling inside these cones (socone.rs:97-101, psdtrianglecone.rs:98-101, expcone.rs:71-74, powcone.rs:63-66)
       const int o = cones.off[k], dm = cones.cones[k].dim;
       double mean = 0.0;
       for (int i = 0; i < dm; i++) mean += e[o + i];
@@ -785,7 +787,7 @@ int IPM::update_data(const double* Pnz, const double* qv, const double* Anz, con
 int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const double* Pxv, const double* q_,
               const uint64_t* Ap, const uint64_t* Ai, const double* Axv, const double* b_, uint64_t ncones,
               const int32_t* ctype, const uint64_t* cdim, const cipm_settings& s_, const cldl_opts& lo,
-              const int* perm) {
+              const int* perm, const double* cparam) {
   n = n_; m = m_; set = s_;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -800,8 +802,9 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   q.assign(q_, q_ + n); b.assign(b_, b_ + m);
   for (auto& v : b) v = std::min(v, 1e20);  // problemdata.rs:130-131
   std::vector<ConeSpec> cs;
-  int rc = ConeSet::collapse(ctype, cdim, ncones, cs);
+  int rc = ConeSet::collapse(ctype, cdim, ncones, cs, cparam);
   if (rc) return rc;
+  cones.ns_amin = set.min_terminate_step_length; cones.ns_step = set.linesearch_backtrack_step;
   int tot = 0;
   for (auto& cc : cs) tot += cc.dim;
   if (tot != m) return CLDL_E_DIM;
@@ -1054,8 +1057,27 @@ int IPM::shift_to_interior(double* v, bool primal) {
   return 0;
 }
 
-int IPM::step_length(bool combined, double* alpha) {
-  // variables.rs:117-154
+int IPM::variables_barrier(double a, double* out) {
+  // variables.rs:205-228
+  const double central_coef = (double)(cones.degree + 1);
+  const double cur_tau = tau + a * ltau, cur_kap = kap + a * lkap;
+  const double *zz = z, *ss = s, *dz = lz, *ds = ls;
+  if (m) {
+    g_launches++;
+    k_sum<<<red_grid(m), RED_THREADS, 0, st>>>(m, [=] __device__(int i) { return (ss[i] + a * ds[i]) * (zz[i] + a * dz[i]); },
+                                              V.ws, sc.d + S_SZSH);
+  } else SCK(cudaMemsetAsync(sc.d + S_SZSH, 0, 8, st));
+  cones.compute_barrier(z, s, lz, ls, a, sc.d + S_BP0, sc.d + S_BARR);
+  int rc = sc.fetch();
+  if (rc) return rc;
+  auto lsafe = [](double v) { return v <= 0.0 ? -INFINITY : std::log(v); };
+  const double mu_a = (sc.h[S_SZSH] + cur_tau * cur_kap) / central_coef;
+  *out = central_coef * lsafe(mu_a) - lsafe(cur_tau) - lsafe(cur_kap) + sc.h[S_BARR];
+  return 0;
+}
+
+int IPM::step_length(bool combined, double* alpha, int scaling) {
+  // variables.rs:117-154, core/solver.rs:548-584
   const double at = ltau < 0.0 ? -tau / ltau : 1.7976931348623157e308;
   const double ak = lkap < 0.0 ? -kap / lkap : 1.7976931348623157e308;
   double a = std::fmin(std::fmin(at, ak), 1.0);
@@ -1067,6 +1089,16 @@ int IPM::step_length(bool combined, double* alpha) {
     a = sc.h[S_ALPHA];
   }
   if (combined) a *= set.max_step_fraction;
+  if (!cones.all_symmetric && combined && scaling == SCALING_DUAL) {
+    // backtrack_step_to_barrier (core/solver.rs:570-584)
+    for (int it = 0; it < 50; it++) {
+      double barrier = 0.0;
+      int rc = variables_barrier(a, &barrier);
+      if (rc) return rc;
+      if (barrier < 1.0) break;
+      a = set.linesearch_backtrack_step * a;
+    }
+  }
   *alpha = a;
   return 0;
 }
@@ -1083,13 +1115,21 @@ int IPM::solve() {
   cudaEvent_t e0 = kkt.ldl.ev0, e1 = kkt.ldl.ev1;
   SCK(cudaEventRecord(e0, st));
 
-  // default start (core/solver.rs:525-541): all supported cones are symmetric
-  cones.set_identity_scaling();
-  if ((rc = kkt_update()) < 0) return rc;
-  if ((rc = solve_initial_point()) < 0) return rc;
-  if ((rc = shift_to_interior(s, true))) return rc;
-  if ((rc = shift_to_interior(z, false))) return rc;
+  // default start (core/solver.rs:525-541)
+  if (cones.all_symmetric) {
+    cones.set_identity_scaling();
+    if ((rc = kkt_update()) < 0) return rc;
+    if ((rc = solve_initial_point()) < 0) return rc;
+    if ((rc = shift_to_interior(s, true))) return rc;
+    if ((rc = shift_to_interior(z, false))) return rc;
+  } else {
+    cones.unit_initialization(z, s);      // variables.rs:173-179
+    V.zero(x, n);
+  }
   tau = 1.0; kap = 1.0;
+  // every cone built here allows primal-dual scaling (only GenPow does not): core/solver.rs:277-280
+  int scaling = SCALING_PRIMAL_DUAL;
+  const bool nonsym = !cones.all_symmetric;
 
   n_iter_ev = 0;
   for (;;) {
@@ -1101,19 +1141,22 @@ int IPM::solve() {
     mu = (dot_sz + tau * kap) / (double)(cones.degree + 1);
     info.mu = mu; info.step_length = alpha; info.sigma = sigma; info.iterations = (uint32_t)iter;
     info_update(t0);
-    trace.insert(trace.end(), {mu, alpha, sigma, info.res_primal, info.res_dual, info.gap_abs});
+    trace.resize((size_t)(iter + 1) * 6);     // one row per iteration; a strategy switch re-enters the same row
+    { double* tr = trace.data() + (size_t)iter * 6; tr[0] = mu; tr[1] = alpha; tr[2] = sigma; tr[3] = info.res_primal; tr[4] = info.res_dual; tr[5] = info.gap_abs; }
     if (check_termination(iter)) {
       if (info.status == IST_INSUFF) {  // recover the previous iterate (core/solver.rs:586-611)
         info.cost_primal = prev_cost_primal; info.cost_dual = prev_cost_dual;
         info.res_primal = prev_res_primal; info.res_dual = prev_res_dual;
         info.gap_abs = prev_gap_abs; info.gap_rel = prev_gap_rel;
         V.copy(x, px, n); V.copy(s, ps, m); V.copy(z, pz, m); tau = ptau; kap = pkap;
+        // nonsymmetric problems get a second chance with the dual-only scaling
+        if (nonsym && scaling == SCALING_PRIMAL_DUAL) { info.status = IST_UNSOLVED; scaling = SCALING_DUAL; continue; }
       }
       break;
     }
     const double ts = wall();
     SCK(cudaMemsetAsync(cones.dev.fail, 0, sizeof(int), st));
-    cones.update_scaling(s, z);
+    cones.update_scaling(s, z, mu, scaling);
     int failflag = 0;
     if (cones.dev.nsoc || cones.dev.npsd) {  // only SOC / PSD scalings can fail
       SCK(cudaMemcpyAsync(&failflag, cones.dev.fail, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1125,13 +1168,13 @@ int IPM::solve() {
     // affine right-hand side (variables.rs:67-78)
     V.copy(rhx, rx, n);
     V.copy(rhz, rz, m);
-    cones.affine_ds(rhs_);
+    cones.affine_ds(rhs_, s);
     rhtau = rtau; rhkap = tau * kap;
     int ok = kkt_update(pair_solves);
     if (ok < 0) return ok;
     if (ok == 1) { ok = kkt_solve_step(false); if (ok < 0) return ok; }
     if (ok == 1) {
-      if ((rc = step_length(false, &alpha))) return rc;
+      if ((rc = step_length(false, &alpha, scaling))) return rc;
       sigma = (1.0 - alpha) * (1.0 - alpha) * (1.0 - alpha);
       const double mm = iter > 1 ? 1.0 : alpha;
       const double dsm = sigma * mu;
@@ -1146,8 +1189,11 @@ int IPM::solve() {
       ok = kkt_solve_step(true);
       if (ok < 0) return ok;
     }
+    // strategy checkpoints (core/solver.rs:613-651)
+    if (ok != 1 && nonsym && scaling == SCALING_PRIMAL_DUAL) { alpha = 0.0; scaling = SCALING_DUAL; continue; }
     if (ok != 1) { info.status = IST_NUMERR; alpha = 0.0; break; }
-    if ((rc = step_length(true, &alpha))) return rc;
+    if ((rc = step_length(true, &alpha, scaling))) return rc;
+    if (nonsym && scaling == SCALING_PRIMAL_DUAL && alpha < set.min_switch_step_length) { alpha = 0.0; scaling = SCALING_DUAL; continue; }
     if (alpha <= std::fmax(0.0, set.min_terminate_step_length)) { info.status = IST_INSUFF; alpha = 0.0; break; }
     prev_cost_primal = info.cost_primal; prev_cost_dual = info.cost_dual;
     prev_res_primal = info.res_primal; prev_res_dual = info.res_dual;
@@ -1206,6 +1252,7 @@ void cipm_default_settings(cipm_settings* s) {
   s->iterative_refinement_enable = 1; s->iterative_refinement_reltol = 1e-13;
   s->iterative_refinement_abstol = 1e-12; s->iterative_refinement_max_iter = 10;
   s->iterative_refinement_stop_ratio = 5.0;
+  s->linesearch_backtrack_step = 0.8; s->min_switch_step_length = 0.1;
 }
 
 int cipm_create(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, const uint64_t* P_rowval,
@@ -1213,6 +1260,15 @@ int cipm_create(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, 
                 const double* A_nzval, const double* b, uint64_t ncones, const int32_t* cone_types,
                 const uint64_t* cone_dims, const cipm_settings* settings, const cldl_opts* ldl_opts,
                 const uint64_t* kkt_perm_or_null) {
+  return cipm_create_ex(out, n, m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones, cone_types,
+                        cone_dims, nullptr, settings, ldl_opts, kkt_perm_or_null);
+}
+
+int cipm_create_ex(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, const uint64_t* P_rowval,
+                   const double* P_nzval, const double* q, const uint64_t* A_colptr, const uint64_t* A_rowval,
+                   const double* A_nzval, const double* b, uint64_t ncones, const int32_t* cone_types,
+                   const uint64_t* cone_dims, const double* cone_params, const cipm_settings* settings,
+                   const cldl_opts* ldl_opts, const uint64_t* kkt_perm_or_null) {
   if (!out) return CLDL_E_ARG;
   *out = nullptr;
   if (n == 0 || n > 0x7fffffffu || m > 0x7fffffffu) return CLDL_E_DIM;
@@ -1233,13 +1289,13 @@ int cipm_create(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, 
   // dimension of the KKT system must be known to slice the permutation: do a dry collapse
   if (kkt_perm_or_null) {
     std::vector<cb::ConeSpec> cs;
-    if (cb::ConeSet::collapse(cone_types, cone_dims, ncones, cs)) { delete h; return CLDL_E_ARG; }
+    if (cb::ConeSet::collapse(cone_types, cone_dims, ncones, cs, cone_params)) { delete h; return CLDL_E_ARG; }
     uint64_t p = 0;
     for (auto& c : cs) if (c.type == cb::CT_SOC && c.dim > cb::SOC_NO_EXPANSION_MAX_SIZE) p += 2;
     perm.resize(n + m + p);
   }
   int rc = h->ipm.init((int)n, (int)m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones,
-                       cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr);
+                       cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr, cone_params);
   if (rc) { h->ipm.release(); delete h; return rc; }
   *out = h;
   return CLDL_OK;
@@ -1422,6 +1478,38 @@ int ccone_update_scaling(cipm_t* h, const double* s, const double* z) {
   if (cudaMemcpy(&fail, I.cones.dev.fail, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return CLDL_E_CUDA;
   return fail ? 0 : 1;
 }
+int ccone_update_scaling_ex(cipm_t* h, const double* s, const double* z, double mu, int strategy) {
+  CONE_PRE
+  if (h2d(I.ps, s, m) || h2d(I.pz, z, m)) return CLDL_E_CUDA;
+  cudaMemsetAsync(I.cones.dev.fail, 0, sizeof(int), I.st);
+  I.cones.update_scaling(I.ps, I.pz, mu, strategy);
+  int fail = 0;
+  cudaStreamSynchronize(I.st);
+  if (cudaMemcpy(&fail, I.cones.dev.fail, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return CLDL_E_CUDA;
+  return fail ? 0 : 1;
+}
+int ccone_unit_initialization(cipm_t* h, double* z, double* s) {
+  CONE_PRE
+  I.cones.unit_initialization(I.pz, I.ps);
+  cudaStreamSynchronize(I.st);
+  return d2h(z, I.pz, m) || d2h(s, I.ps, m) ? CLDL_E_CUDA : 0;
+}
+int ccone_affine_ds_ex(cipm_t* h, double* ds, const double* s) {
+  CONE_PRE
+  if (h2d(I.pz, s, m)) return CLDL_E_CUDA;
+  I.cones.affine_ds(I.ps, I.pz);
+  cudaStreamSynchronize(I.st);
+  return d2h(ds, I.ps, m);
+}
+int ccone_compute_barrier(cipm_t* h, const double* z, const double* s, const double* dz, const double* ds,
+                          double alpha, double* barrier_out) {
+  CONE_PRE
+  if (h2d(I.ps, z, m) || h2d(I.pz, s, m) || h2d(I.workz, dz, m) || h2d(I.work_conic, ds, m)) return CLDL_E_CUDA;
+  I.cones.compute_barrier(I.ps, I.pz, I.workz, I.work_conic, alpha, I.sc.d + cb::S_BP0, I.sc.d + cb::S_BARR);
+  cudaStreamSynchronize(I.st);
+  return d2h(barrier_out, I.sc.d + cb::S_BARR, 1);
+}
+int ccone_is_symmetric(const cipm_t* h) { return h ? (h->ipm.cones.all_symmetric ? 1 : 0) : CLDL_E_ARG; }
 uint64_t ccone_Hs_len(const cipm_t* h) { return h ? (uint64_t)h->ipm.cones.nHs : 0; }
 int ccone_get_Hs(cipm_t* h, double* Hs) {
   CONE_PRE (void)m;

@@ -238,3 +238,51 @@ def block_sdp(n=20_000, n_psd=500, psd_dim=20, nnz_per_row=10, window=400, n_non
     cones = [("zero", nz), ("nonneg", n_nonneg)] + [("psd", psd_dim)] * n_psd
     return dict(P=P, q=q, A=A, b=np.array(b), cones=cones,
                 name=f"block_sdp(n={n},psd={n_psd}x{psd_dim},seed={seed})")
+
+
+def entropy_power_mix(k_exp=200, k_pow=100, n_eq=10, seed=6):
+    """Nonsymmetric-cone workload: entropy maximisation over a probability vector with linear moment constraints
+    (k_exp exponential cones) next to a weighted geometric-mean allocation (k_pow 3-D power cones with exponents
+    drawn from (0.1, 0.9)), sharing one budget row.
+
+        max  sum_i t_i + sum_j c_j y_j
+        s.t. (t_i, p_i, 1) in K_exp                  (t_i <= -p_i log p_i)
+             sum p = 1,  F p = F p0                  (zero cone, p0 the uniform distribution perturbed)
+             (u_j, w_j, y_j) in K_pow(alpha_j)       (|y_j| <= u_j^alpha_j w_j^(1-alpha_j))
+             sum u + sum w + s = k_pow, s >= 0       (budget, nonnegative cone)
+
+    cones use the vocabulary of the reference's SupportedConeT (supportedcone.rs:17-52): ("exp", 3), ("pow", alpha).
+    """
+    rng = np.random.default_rng(seed)
+    n = 2 * k_exp + 3 * k_pow
+    ip, it = 0, k_exp                       # p, t
+    iu, iw, iy = 2 * k_exp, 2 * k_exp + k_pow, 2 * k_exp + 2 * k_pow
+    rows, cols, vals, b, cones = [], [], [], [], []
+    r = 0
+    # equality rows
+    p0 = rng.uniform(0.5, 1.5, k_exp); p0 /= p0.sum()
+    rows += [r] * k_exp; cols += list(range(ip, ip + k_exp)); vals += [1.0] * k_exp; b.append(1.0); r += 1
+    F = rng.standard_normal((n_eq, k_exp))
+    for e in range(n_eq):
+        rows += [r] * k_exp; cols += list(range(ip, ip + k_exp)); vals += F[e].tolist(); b.append(float(F[e] @ p0)); r += 1
+    cones.append(("zero", 1 + n_eq))
+    # budget row
+    rows += [r] * (2 * k_pow); cols += list(range(iu, iu + 2 * k_pow)); vals += [1.0] * (2 * k_pow); b.append(float(k_pow)); r += 1
+    cones.append(("nonneg", 1))
+    # exponential cones: s = b - A x = (t_i, p_i, 1)
+    for i in range(k_exp):
+        rows += [r, r + 1]; cols += [it + i, ip + i]; vals += [-1.0, -1.0]; b += [0.0, 0.0, 1.0]; r += 3
+        cones.append(("exp", 3))
+    # power cones: s = (u_j, w_j, y_j)
+    alphas = rng.uniform(0.1, 0.9, k_pow)
+    for j in range(k_pow):
+        rows += [r, r + 1, r + 2]; cols += [iu + j, iw + j, iy + j]; vals += [-1.0, -1.0, -1.0]; b += [0.0, 0.0, 0.0]; r += 3
+        cones.append(("pow", float(alphas[j])))
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(r, n)).tocsc()
+    A.sum_duplicates(); A.sort_indices()
+    q = np.zeros(n)
+    q[it:it + k_exp] = -1.0
+    q[iy:iy + k_pow] = -rng.uniform(0.5, 1.5, k_pow)
+    P = sp.csc_matrix((n, n))
+    return dict(P=P, q=q, A=A, b=np.array(b), cones=cones,
+                name=f"entropy_power_mix(exp={k_exp},pow={k_pow},seed={seed})")

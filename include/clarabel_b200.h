@@ -142,8 +142,12 @@ double cldl_time_solve_ms(cldl_t *h, int reps);
  * ==================================================================== */
 typedef struct cipm_handle cipm_t;
 
-/* SupportedConeT tags (supportedcone.rs:17-52); PSD reserved. */
-enum { CIPM_CONE_ZERO = 0, CIPM_CONE_NONNEG = 1, CIPM_CONE_SOC = 2, CIPM_CONE_PSD = 3 };
+/* SupportedConeT tags (supportedcone.rs:17-52).  ExponentialConeT() and PowerConeT(alpha) occupy 3 rows each;
+ * the exponent of a power cone travels in cone_params (cipm_create_ex).  GenPowerConeT is not built. */
+enum { CIPM_CONE_ZERO = 0, CIPM_CONE_NONNEG = 1, CIPM_CONE_SOC = 2, CIPM_CONE_PSD = 3, CIPM_CONE_EXP = 4,
+       CIPM_CONE_POW = 5 };
+/* ScalingStrategy (src/solver/core/cones/mod.rs) */
+enum { CIPM_SCALING_PRIMAL_DUAL = 0, CIPM_SCALING_DUAL = 1 };
 
 /* SolverStatus (src/solver/core/traits.rs / default/info.rs) */
 enum { CIPM_UNSOLVED = 0, CIPM_SOLVED, CIPM_PRIMAL_INFEASIBLE, CIPM_DUAL_INFEASIBLE, CIPM_ALMOST_SOLVED,
@@ -170,6 +174,8 @@ typedef struct {
   double iterative_refinement_reltol, iterative_refinement_abstol;
   int32_t iterative_refinement_max_iter;
   double iterative_refinement_stop_ratio;
+  /* nonsymmetric cones only (settings.rs:114-124) */
+  double linesearch_backtrack_step, min_switch_step_length;
 } cipm_settings;
 
 /* DefaultInfo (default/info.rs:13-64) + timers of core/solver.rs:330-396 + counters */
@@ -196,6 +202,14 @@ int cipm_create(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colptr, 
                 const double *A_nzval, const double *b, uint64_t ncones, const int32_t *cone_types,
                 const uint64_t *cone_dims, const cipm_settings *settings, const cldl_opts *ldl_opts,
                 const uint64_t *kkt_perm_or_null);
+/* Same, with one double per cone: the exponent alpha of a CIPM_CONE_POW entry (PowerConeT(alpha),
+ * supportedcone.rs:36-38; the Julia interface carries it the same way, julia/types.rs:19-26), ignored for the other
+ * cone types.  cone_params may be NULL when the problem has no power cones. */
+int cipm_create_ex(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colptr, const uint64_t *P_rowval,
+                   const double *P_nzval, const double *q, const uint64_t *A_colptr, const uint64_t *A_rowval,
+                   const double *A_nzval, const double *b, uint64_t ncones, const int32_t *cone_types,
+                   const uint64_t *cone_dims, const double *cone_params, const cipm_settings *settings,
+                   const cldl_opts *ldl_opts, const uint64_t *kkt_perm_or_null);
 void cipm_destroy(cipm_t *h);
 int cipm_solve(cipm_t *h);                                   /* IPSolver::solve */
 void cipm_get_info(const cipm_t *h, cipm_info *out);
@@ -240,6 +254,13 @@ int ccone_step_length(cipm_t *h, const double *dz, const double *ds, const doubl
                       double alpha_max, double *alpha_out);
 int ccone_margins(cipm_t *h, const double *z, double *min_margin, double *pos_margin);
 int ccone_scaled_unit_shift(cipm_t *h, double *z, double alpha, int primal);
+/* the parts of the trait only nonsymmetric problems use (cones/mod.rs:61-66, 94-101, 148-153) */
+int ccone_is_symmetric(const cipm_t *h);
+int ccone_unit_initialization(cipm_t *h, double *z, double *s);
+int ccone_update_scaling_ex(cipm_t *h, const double *s, const double *z, double mu, int strategy);   /* bool */
+int ccone_affine_ds_ex(cipm_t *h, double *ds, const double *s);
+int ccone_compute_barrier(cipm_t *h, const double *z, const double *s, const double *dz, const double *ds,
+                          double alpha, double *barrier_out);
 
 #ifdef __cplusplus
 }

@@ -805,7 +805,7 @@ static double cones_compute_barrier(oipm_t *S, const double *z_, const double *s
                 const double *x = pass == 0 ? z : s, *dx = pass == 0 ? dz : ds;
                 for (idx i = 0; i < n; i++) c->wv[i] = 1.0 * x[i] + a * dx[i];
                 svec_to_mat(c->W1, c->psd_n, c->wv);
-                if (chol_lower(c->W2, c->W1, c->psd_n)) { double ld = 0.0; for (idx i = 0; i < c->psd_n; i++) ld += logsafe(MAT(c->W2, c->psd_n, i, i)); b -= 2.0 * ld; }
+                if (chol_lower(c->W2, c->W1, c->psd_n) == 0) { double ld = 0.0; for (idx i = 0; i < c->psd_n; i++) ld += log(MAT(c->W2, c->psd_n, i, i)); b -= ld + ld; }
                 else b -= INFINITY;
             }
             barrier += b;

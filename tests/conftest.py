@@ -17,7 +17,8 @@ def _built():
     """Make sure both shared libraries exist (build is idempotent and quick)."""
     import subprocess
     need = [os.path.join(ROOT, "clarabel.rs_b200", "libclarabel_b200.so"),
-            os.path.join(ROOT, "oracle", "liboracle.so")]
+            os.path.join(ROOT, "oracle", "liboracle.so"),
+            os.path.join(ROOT, "tests", "host_harness", "libns3_host.so")]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call(["make", "-s", "-C", ROOT, "-j8"], stdout=subprocess.DEVNULL,
                               stderr=subprocess.DEVNULL)

@@ -1,0 +1,146 @@
+"""GPU: exponential / 3-D power cone kernels (cones_nonsym.cu) and the nonsymmetric branches of the device
+interior-point loop against (i) the reference's own known answers (tests/basic_expcone.rs, basic_powcone.rs,
+mixed_conic.rs) and (ii) the oracle on the same KKT permutation.  The per-cone arithmetic these kernels execute is
+also checked without a GPU in tests/test_nonsym_host.py."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import clarabel_rs_b200 as cb
+import oracle
+from helpers import workloads
+import test_oracle_nonsym as ref
+
+pytestmark = pytest.mark.gpu
+
+MIXED = [("zero", 2), ("exp", 3), ("nonneg", 40), ("pow", 0.3), ("soc", 3), ("soc", 7), ("exp", 3), ("psd", 3),
+         ("pow", 0.75)] + [("exp", 3), ("pow", 0.6), ("pow", 0.12)] * 50
+
+
+def pair(cones):
+    m = sum(3 if k in ("exp", "pow") else (d * (d + 1) // 2 if k == "psd" else d) for k, d in cones)
+    P, q, A, b = sp.csc_matrix((m, m)), np.zeros(m), -sp.identity(m, format="csc"), np.zeros(m)
+    st = dict(equilibrate_enable=0)
+    dev = cb.CudaSolver(P, q, A, b, cones, settings=cb.default_settings(**st))
+    ora = oracle.IPM(P, q, A, b, cones, settings=oracle.default_settings(**st))
+    return dev, ora, m
+
+
+def interior(ora, rng, m, spread):
+    z0, s0 = ora.unit_initialization()
+    zero = np.zeros(m)
+    for _ in range(200):
+        z, s = z0 + spread * rng.standard_normal(m), s0 + spread * rng.standard_normal(m)
+        if np.isfinite(ora.compute_barrier(z, s, zero, zero, 0.0)):
+            return z, s
+    raise RuntimeError("no interior point")
+
+
+def close(a, b, tol):
+    sc = max(1.0, float(np.max(np.abs(b)))) if np.size(b) else 1.0
+    return (np.max(np.abs(np.asarray(a) - np.asarray(b))) <= tol * sc) if np.size(b) else True
+
+
+def test_unit_initialization_and_symmetry_flag():
+    dev, ora, m = pair(MIXED)
+    assert not dev.cone_is_symmetric()
+    z, s = dev.cone_unit_initialization()
+    zo, so = ora.unit_initialization()
+    assert np.array_equal(z, zo) and np.array_equal(s, so)
+    dsym, _, _ = pair([("nonneg", 3), ("soc", 3)])
+    assert dsym.cone_is_symmetric()
+
+
+@pytest.mark.parametrize("strategy", [cb.SCALING_PRIMAL_DUAL, cb.SCALING_DUAL])
+def test_cone_ops_match_oracle(strategy):
+    dev, ora, m = pair(MIXED)
+    rng = np.random.default_rng(7 + strategy)
+    for trial in range(4):
+        z, s = interior(ora, rng, m, 0.05 + 0.04 * trial)
+        mu = float(s @ z) / 11.0
+        assert dev.cone_update_scaling_ex(s, z, mu, strategy) and ora.update_scaling_ex(s, z, mu, strategy)
+        assert close(dev.cone_get_Hs(), ora.get_Hs(), 1e-9)
+        x = rng.standard_normal(m)
+        assert close(dev.cone_mul_Hs(x), ora.mul_Hs(x), 1e-9)
+        assert close(dev.cone_affine_ds_ex(s), ora.affine_ds_ex(s), 1e-12)
+        dz, ds = 0.3 * rng.standard_normal(m), 0.3 * rng.standard_normal(m)
+        assert close(dev.cone_combined_ds_shift(dz, ds, 0.37 * mu), ora.combined_ds_shift(dz, ds, 0.37 * mu), 1e-9)
+        assert close(dev.cone_ds_from_dz_offset(ds, z), ora.ds_from_dz_offset(ds, z), 1e-9)
+        for al in (0.0, 0.4):
+            bd, bo = dev.cone_compute_barrier(z, s, 0.05 * dz, 0.05 * ds, al), ora.compute_barrier(z, s, 0.05 * dz, 0.05 * ds, al)
+            assert abs(bd - bo) <= 1e-9 * max(1.0, abs(bo))
+
+
+def test_step_length_is_the_sequential_composite_rule():
+    """independent per-cone backtracking counts + atomicMax == the reference's running alpha (compositecone.rs:289-332)"""
+    cones = [("exp", 3), ("pow", 0.6), ("pow", 0.1)] * 120
+    dev, ora, m = pair(cones)
+    rng = np.random.default_rng(23)
+    seen = set()
+    for trial in range(12):
+        z, s = interior(ora, rng, m, 0.1)
+        scale = [0.3, 1.0, 3.0, 10.0][trial % 4]
+        dz, ds = scale * rng.standard_normal(m), scale * rng.standard_normal(m)
+        for amax in (1.0, 0.61):
+            a, ao = dev.cone_step_length(dz, ds, z, s, amax), ora.step_length(dz, ds, z, s, amax)
+            assert a == ao, (trial, amax, a, ao)
+            seen.add(a)
+    assert len(seen) >= 3
+
+
+def both(P, q, A, b, cones, **kw):
+    dev = cb.CudaSolver(P, q, A, b, cones, settings=cb.default_settings(**kw) if kw else None)
+    rd = dev.solve()
+    o = oracle.IPM(P, q, A, b, cones, settings=oracle.default_settings(**kw) if kw else None)
+    o.set_perm(dev.kkt_perm())
+    return dev, rd, o, o.solve()
+
+
+def assert_parity(rd, ro, xtol=1e-6):
+    assert rd["status"] == ro["status"]
+    assert rd["iterations"] == ro["iterations"]
+    if rd["status"] == "Solved":
+        assert np.max(np.abs(rd["x"] - ro["x"])) <= xtol * max(1.0, np.max(np.abs(ro["x"])))
+        assert abs(rd["obj_val"] - ro["obj_val"]) <= xtol * max(1.0, abs(ro["obj_val"]))
+
+
+def test_expcone_known_answers():  # basic_expcone.rs:38-91
+    P, c, A, b, cones = ref.expcone_data()
+    _, rd, _, ro = both(P, c, A, b, cones)
+    assert rd["status"] == "Solved"
+    assert np.linalg.norm(rd["x"] - [5.0, 1.0, np.exp(5.0)]) <= 1e-6 and abs(rd["obj_val"] + 5.0) <= 1e-6
+    assert_parity(rd, ro)
+    b2 = b.copy(); b2[4] = -1.
+    _, rd, _, ro = both(P, c, A, b2, cones)
+    assert rd["status"] == "PrimalInfeasible" == ro["status"]
+    _, rd, _, ro = both(sp.csc_matrix((3, 3)), [-1., 0., 0.], -sp.identity(3, format="csc"), np.zeros(3), [("exp", 3)])
+    assert rd["status"] == "DualInfeasible" == ro["status"]
+
+
+def test_powcone_known_answer():  # basic_powcone.rs:5-52
+    n = 6
+    A = sp.vstack([-sp.identity(n, format="csc"),
+                   sp.csc_matrix(np.array([[1., 2., 0., 3., 0., 0.], [0., 0., 0., 0., 1., 0.]]))]).tocsc()
+    b = np.concatenate([np.zeros(n), [3., 1.]])
+    _, rd, _, ro = both(sp.csc_matrix((n, n)), np.array([0., 0., -1., 0., 0., -1.]), A, b,
+                        [("pow", 0.6), ("pow", 0.1), ("zero", 2)])
+    assert rd["status"] == "Solved" and abs(rd["obj_val"] + 1.8458) <= 1e-3
+    assert_parity(rd, ro)
+
+
+@pytest.mark.parametrize("kw", [{}, {"min_switch_step_length": 0.999}], ids=["primal-dual", "dual-strategy"])
+def test_mixed_conic_known_answer(kw):  # mixed_conic.rs:5-46 (the second run forces the dual scaling + barrier search)
+    _, rd, _, ro = both(*ref.mixed_conic_data(), **kw)
+    assert rd["status"] == "Solved" and abs(rd["obj_val"]) <= 1e-8
+    assert_parity(rd, ro)
+
+
+@pytest.mark.parametrize("ke,kp", [(20, 10), (300, 150)])
+def test_entropy_power_mix_same_trajectory(ke, kp):
+    pr = workloads.entropy_power_mix(ke, kp, n_eq=5, seed=6)
+    dev, rd, ora, ro = both(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"])
+    assert rd["status"] == "Solved"
+    assert_parity(rd, ro)
+    k = min(len(dev.trace), len(ora.trace))
+    assert np.allclose(dev.trace[:k, 0], ora.trace[:k, 0], rtol=1e-4, atol=1e-12)   # mu
+    assert np.allclose(dev.trace[1:k, 1], ora.trace[1:k, 1], rtol=1e-6)             # step lengths
