@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory_resource>
 #include <numeric>
 #include <chrono>
 
@@ -150,7 +151,6 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   for (int k = 0; k < n; k++) S.perm[k] = perm0[post[k]];
   for (int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
 
-  permuted_upper(n, Ap, Ai, S.iperm, Up, Ui);
   {
     // the tree of the post-ordered matrix is the old tree relabelled
     std::vector<int> ipost(n);
@@ -160,19 +160,30 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   }
   const std::vector<int>& parent = S.parent;
 
-  // strictly-lower pattern by columns (transpose of strict upper)
+  // strictly-lower pattern by columns of the post-ordered matrix, straight from the caller's entries (the column
+  // counts and the row-structure unions below do not depend on the order inside a column)
   std::vector<int64_t> Lo_ptr(n + 1, 0);
-  for (int k = 0; k < n; k++)
-    for (int64_t p = Up[k]; p < Up[k + 1]; p++)
-      if (Ui[p] != k) Lo_ptr[Ui[p] + 1]++;
+  for (int c = 0; c < n; c++) {
+    const int b = S.iperm[c];
+    for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
+      const int a = S.iperm[Ai[p]];
+      if (a != b) Lo_ptr[(a < b ? a : b) + 1]++;
+    }
+  }
   for (int j = 0; j < n; j++) Lo_ptr[j + 1] += Lo_ptr[j];
   std::vector<int> Lo_idx(Lo_ptr[n]);
   {
     std::vector<int64_t> pos(Lo_ptr.begin(), Lo_ptr.end() - 1);
-    for (int k = 0; k < n; k++)
-      for (int64_t p = Up[k]; p < Up[k + 1]; p++)
-        if (Ui[p] != k) Lo_idx[pos[Ui[p]]++] = k;
+    for (int c = 0; c < n; c++) {
+      const int b = S.iperm[c];
+      for (int64_t p = Ap[c]; p < Ap[c + 1]; p++) {
+        const int a = S.iperm[Ai[p]];
+        if (a != b) Lo_idx[pos[a < b ? a : b]++] = a < b ? b : a;
+      }
+    }
   }
+  std::vector<int64_t>().swap(Up);
+  std::vector<int>().swap(Ui);
   colcounts_postordered(n, parent, Lo_ptr, Lo_idx, S.colcount);
   S.nnzL_simplicial = 0;
   S.flops_simplicial = 0;
@@ -318,6 +329,11 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   S.nlevels = nlev;
   if (stats_only) return 0;
 
+  // The three remaining pieces -- (a) level schedule + children + relative index maps, (b) assembly map of the
+  // original entries, (c) update-matrix arena -- only read the supernode structure built above and write disjoint
+  // members of S: they run on three host threads.
+  int rc_a = 0, rc_b = 0;
+  auto part_a = [&]() {
   S.level_ptr.assign(nlev + 1, 0);
   for (int s = 0; s < nsup; s++) S.level_ptr[S.sn_level[s] + 1]++;
   for (int l = 0; l < nlev; l++) S.level_ptr[l + 1] += S.level_ptr[l];
@@ -352,13 +368,14 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
       int r = S.sn_rows[t];
       if (r < pl) { S.rel[t] = r - pf; continue; }
       while (q < qe && S.sn_rows[q] < r) q++;
-      if (q >= qe || S.sn_rows[q] != r) { std::fprintf(stderr, "symbolic: rel map failure\n"); return -10; }
+      if (q >= qe || S.sn_rows[q] != r) { std::fprintf(stderr, "symbolic: rel map failure\n"); rc_a = -10; return; }
       S.rel[t] = pns + (int)(q - S.sn_rowptr[p]);
     }
   }
+  };
 
-  TMARK("sym: levels+children+rel");
   // ---- assembly map of original entries ----
+  auto part_b = [&]() {
   S.asm_ptr.assign(nsup + 1, 0);
   int64_t nnz = Ap[n];
   std::vector<int> ent_task(nnz);
@@ -396,7 +413,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
       for (auto& x : th) x.join();
     }
     for (unsigned t = 0; t < nth; t++)
-      if (bad[t]) { std::fprintf(stderr, "symbolic: asm map failure\n"); return -11; }
+      if (bad[t]) { std::fprintf(stderr, "symbolic: asm map failure\n"); rc_b = -11; return; }
     for (int64_t p = 0; p < nnz; p++) S.asm_ptr[ent_task[p] + 1]++;
   }
   for (int s = 0; s < nsup; s++) S.asm_ptr[s + 1] += S.asm_ptr[s];
@@ -410,8 +427,8 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
       S.asm_dst[d] = ent_dst[p];
     }
   }
+  };
 
-  TMARK("sym: assembly map");
   // ---- update-matrix arena ----
   // U_s is written by front s and read by parent(s).  The numeric phase runs as a dataflow graph (a front
   // starts as soon as its children are complete, with no level barrier), so a block may only be reused by a
@@ -419,9 +436,12 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   // once s completes, and exactly the proper ancestors of s start after that.  Every front therefore hands
   // the blocks of its subtree that are dead at its completion to its parent (free lists merged small into
   // large); a front allocates from the lists of its children before growing the arena.
+  auto part_c = [&]() {
   S.upd_off.assign(nsup, 0);
   {
-    typedef std::multimap<int64_t, int64_t> FreeList;  // size -> offset
+    // size -> offset; the nodes come from a pool (the lists are built and torn down ~nsup times)
+    std::pmr::unsynchronized_pool_resource pool;
+    typedef std::pmr::multimap<int64_t, int64_t> FreeList;
     std::vector<FreeList*> fl(nsup, nullptr);
     int64_t top = 0;
     for (int s = 0; s < nsup; s++) {  // supernodes are numbered in postorder: children first
@@ -454,7 +474,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
       for (int c : kids[s]) {
         const int64_t nrc = S.sn_rowptr[c + 1] - S.sn_rowptr[c];
         if (nrc > 0) {
-          if (!mine) mine = new FreeList();
+          if (!mine) mine = new FreeList(&pool);
           mine->emplace(nrc * nrc, S.upd_off[c]);
         }
       }
@@ -463,7 +483,16 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
     for (FreeList* f : fl) delete f;
     S.upd_total = top;
   }
-  TMARK("sym: arena");
+  };
+  if (nsup < 2000) { part_a(); part_b(); part_c(); }
+  else {
+    std::thread tb(part_b), tc(part_c);
+    part_a();
+    tb.join(); tc.join();
+  }
+  TMARK("sym: schedule | assembly map | arena");
+  if (rc_a) return rc_a;
+  if (rc_b) return rc_b;
   return 0;
 }
 
