@@ -230,6 +230,7 @@ class Settings(C.Structure):
         ("iterative_refinement_max_iter", C.c_int32),
         ("iterative_refinement_stop_ratio", C.c_double),
         ("linesearch_backtrack_step", C.c_double), ("min_switch_step_length", C.c_double),
+        ("presolve_enable", C.c_int32),
     ]
 
 
@@ -280,6 +281,8 @@ def _ipm_lib():
         L.oipm_test_affine_ds_ex.restype = None
         L.oipm_kkt_dim.argtypes = [vp]
         L.oipm_kkt_dim.restype = C.c_int64
+        L.oipm_m_reduced.argtypes = [vp]
+        L.oipm_m_reduced.restype = C.c_int64
         L.oipm_kkt_nnz.argtypes = [vp]
         L.oipm_kkt_nnz.restype = C.c_int64
         for nm in ["oipm_kkt_colptr", "oipm_kkt_rowval"]:
@@ -363,6 +366,7 @@ class IPM:
             raise ValueError(f"oipm_new failed: {rc}")
         self._h = h
         self.N = int(L.oipm_kkt_dim(h))
+        self.m_reduced = int(L.oipm_m_reduced(h))     # rows left after the inf-bound presolve (== m without it)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -391,7 +395,7 @@ class IPM:
     def equilibration(self):
         L, h = self._L, self._h
         d = np.ctypeslib.as_array(L.oipm_equil(h, 0), shape=(max(self.n, 1),))[:self.n].copy()
-        e = np.ctypeslib.as_array(L.oipm_equil(h, 1), shape=(max(self.m, 1),))[:self.m].copy()
+        e = np.ctypeslib.as_array(L.oipm_equil(h, 1), shape=(max(self.m, 1),))[:self.m_reduced].copy()
         c = float(L.oipm_equil(h, 2)[0])
         return d, e, c
 

@@ -16,9 +16,10 @@
  * The reference holds NO unit-level known answers for cone numerics
  * (SURVEY.md section 4): those are pinned end-to-end only.
  *
- * Not restated (documented gaps): the inf-bound presolve row elimination
- * (presolver.rs) -- b is capped at 1e20 exactly as problemdata.rs:130-131 does
- * but rows are not dropped; chordal decomposition; the GenPow cone.
+ * Not restated (documented gaps): chordal decomposition; the GenPow cone.
+ * The inf-bound presolve (presolver.rs: nonnegative rows with b beyond the
+ * infinity bound are dropped, the solution is expanded again) is restated in
+ * oipm_new_ex / oipm_get_solution and pinned on tests/presolve.rs.
  * The exponential and 3-D power cones (nonsymmetric path: unit initialisation,
  * dual / primal-dual scaling, third-order correction, backtracking step
  * length, barrier line search, strategy checkpoints) live in nonsym_oracle.h
@@ -95,6 +96,7 @@ typedef struct {
     double iterative_refinement_stop_ratio;
     /* nonsymmetric cones only (settings.rs:114-124) */
     double linesearch_backtrack_step, min_switch_step_length;
+    int32_t presolve_enable;
 } oipm_settings;
 
 void oipm_default_settings(oipm_settings *s)
@@ -115,6 +117,7 @@ void oipm_default_settings(oipm_settings *s)
     s->iterative_refinement_abstol = 1e-12; s->iterative_refinement_max_iter = 10;
     s->iterative_refinement_stop_ratio = 5.0;
     s->linesearch_backtrack_step = 0.8; s->min_switch_step_length = 0.1;
+    s->presolve_enable = 1;
 }
 
 typedef struct {
@@ -140,6 +143,7 @@ typedef struct { idx m, n; idx *colptr, *rowval; double *nzval; } csc;
 
 typedef struct {
     idx n, m, p, N;
+    idx mfull; char *keep;   /* presolve: rows of the user's problem kept in the reduced one (NULL = all) */
     csc P, A;              /* internal (scaled) copies; P is triu */
     double *q, *b;
     double normq, normb;
@@ -1113,7 +1117,7 @@ static void equilibrate(oipm_t *S)
 void oipm_free(oipm_t *S)
 {
     if (!S) return;
-    csc_free(&S->P); csc_free(&S->A); free(S->q); free(S->b);
+    csc_free(&S->P); csc_free(&S->A); free(S->q); free(S->b); free(S->keep);
     for (idx k = 0; k < S->ncones; k++) { cone_t *c = &S->cones[k]; free(c->w); free(c->lam); free(c->u); free(c->v); free(c->map_u); free(c->map_v);
         free(c->R); free(c->Rinv); free(c->lisqrt); free(c->HsM); free(c->W1); free(c->W2); free(c->W3); free(c->wv); free(c->ns); }
     free(S->cones); free(S->d); free(S->dinv); free(S->e); free(S->einv);
@@ -1190,6 +1194,47 @@ int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
         }
     }
     S->ncones = nc;
+    /* presolve (presolver.rs:157-204, 75-125; problemdata.rs:86-93): nonnegative rows whose bound is infinite are
+       dropped from A, b and their cone.  b was capped at the bound above, which still compares as "beyond" it. */
+    S->mfull = m; S->keep = NULL;
+    if (S->set.presolve_enable) {
+        const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * 1e20;
+        char *keep = (char *)malloc((size_t)(m > 0 ? m : 1));
+        idx mred = m, r = 0;
+        for (idx i = 0; i < m; i++) keep[i] = 1;
+        for (idx c = 0; c < nc; c++) {
+            cone_t *cn = &S->cones[c];
+            if (cn->type == CONE_NONNEG) { for (idx i = 0; i < cn->dim; i++, r++) if (S->b[r] > thr) { keep[r] = 0; mred--; } }
+            else r += cn->dim;
+        }
+        if (r != m) { free(keep); oipm_free(S); return -1; }
+        if (mred < m) {
+            idx nc2 = 0; r = 0;
+            for (idx c = 0; c < nc; c++) {
+                cone_t cn = S->cones[c];
+                if (cn.type == CONE_NONNEG) {
+                    idx nk = 0;
+                    for (idx i = 0; i < cn.dim; i++) nk += keep[r + i];
+                    r += cn.dim;
+                    if (nk > 0) { cn.dim = nk; S->cones[nc2++] = cn; }
+                } else { r += cn.dim; S->cones[nc2++] = cn; }
+            }
+            for (idx c = nc2; c < nc; c++) memset(&S->cones[c], 0, sizeof(cone_t));
+            nc = nc2; S->ncones = nc;
+            idx *rowmap = ivec(m), nr = 0;
+            for (idx i = 0; i < m; i++) rowmap[i] = keep[i] ? nr++ : -1;
+            csc *A = &S->A; idx w = 0;
+            for (idx j = 0; j < n; j++) {
+                idx b0 = A->colptr[j]; A->colptr[j] = w;
+                for (idx q_ = b0; q_ < A->colptr[j + 1]; q_++)
+                    if (rowmap[A->rowval[q_]] >= 0) { A->rowval[w] = rowmap[A->rowval[q_]]; A->nzval[w] = A->nzval[q_]; w++; }
+            }
+            A->colptr[n] = w; A->m = mred;
+            for (idx i = 0; i < m; i++) if (keep[i]) S->b[rowmap[i]] = S->b[i];
+            free(rowmap);
+            S->keep = keep; m = mred; S->m = mred;
+        } else free(keep);
+    }
     idx off = 0; S->degree = 0; S->all_symmetric = 1;
     for (idx c = 0; c < nc; c++) {
         cone_t *cn = &S->cones[c];
@@ -1225,6 +1270,7 @@ int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
 
 /* KKT pattern for the ordering step (caller computes a permutation of size N) */
 idx oipm_kkt_dim(const oipm_t *S) { return S->N; }
+idx oipm_m_reduced(const oipm_t *S) { return S->m; }
 idx oipm_kkt_nnz(const oipm_t *S) { return S->K.colptr[S->N]; }
 const idx *oipm_kkt_colptr(const oipm_t *S) { return S->K.colptr; }
 const idx *oipm_kkt_rowval(const oipm_t *S) { return S->K.rowval; }
@@ -1576,8 +1622,16 @@ void oipm_get_solution(oipm_t *S, double *x, double *z, double *s, double *obj, 
     double scaleinv = infeas ? 1.0 / S->vkap : 1.0 / S->vtau;
     double cinv = 1.0 / S->c;
     for (idx i = 0; i < S->n; i++) x[i] = S->vx[i] * S->d[i] * scaleinv;
-    for (idx i = 0; i < S->m; i++) z[i] = S->vz[i] * S->e[i] * (scaleinv * cinv);
-    for (idx i = 0; i < S->m; i++) s[i] = S->vs[i] * S->einv[i] * scaleinv;
+    if (!S->keep) {
+        for (idx i = 0; i < S->m; i++) z[i] = S->vz[i] * S->e[i] * (scaleinv * cinv);
+        for (idx i = 0; i < S->m; i++) s[i] = S->vs[i] * S->einv[i] * scaleinv;
+    } else {   /* reverse_presolve (presolver.rs:127-150): dropped rows get s = infinity bound, z = 0 */
+        idx c = 0;
+        for (idx i = 0; i < S->mfull; i++) {
+            if (S->keep[i]) { z[i] = S->vz[c] * S->e[c] * (scaleinv * cinv); s[i] = S->vs[c] * S->einv[c] * scaleinv; c++; }
+            else { z[i] = 0.0; s[i] = 1e20; }
+        }
+    }
     *obj = infeas ? NAN : S->info.cost_primal;
     *obj_dual = infeas ? NAN : S->info.cost_dual;
 }

@@ -177,3 +177,50 @@ def test_kkt_missing_P_diagonal_gets_structural_zero():  # kkt_assembly.rs:69-70
     N, cp, rv, nz, ds = ipm.kkt()
     assert all(rv[cp[j + 1] - 1] == j for j in range(N))  # diagonal is the last entry of every column
     assert len(rv) == 1 + 3 + 3 + 3
+
+
+# ---- inf-bound presolve (tests/presolve.rs:29-105, data :7-27) ----
+def _presolve_data():
+    n = 3
+    P = sp.identity(n, format="csc")
+    A = (2.0 * sp.vstack([sp.identity(n), -sp.identity(n)])).tocsc()
+    return P, np.array([3., -2., 1.]), A, np.ones(2 * n), [("nonneg", 3), ("nonneg", 3)]
+
+
+def test_presolve_single_unbounded():  # presolve.rs:29-44
+    P, c, A, b, cones = _presolve_data()
+    b[3] = 1e30
+    ipm, r = solve(P, c, A, b, cones)
+    assert r["status"] == "Solved" and ipm.m_reduced == 5
+    assert r["z"][3] == 0.0 and r["s"][3] == 1e20
+
+
+def test_presolve_single_unbounded_2():  # presolve.rs:46-61
+    P, c, A, b, _ = _presolve_data()
+    b[4] = 1e30
+    ipm, r = solve(P, c, A, b, [("zero", 2), ("nonneg", 4)])
+    assert r["status"] == "Solved" and ipm.m_reduced == 5
+
+
+def test_presolve_completely_redundant_cone():  # presolve.rs:63-83
+    P, c, A, b, cones = _presolve_data()
+    b[:3] = 1e30
+    ipm, r = solve(P, c, A, b, cones)
+    assert r["status"] == "Solved" and ipm.m_reduced == 3
+    assert np.array_equal(r["z"][:3], np.zeros(3)) and np.array_equal(r["s"][:3], np.full(3, 1e20))
+    assert np.linalg.norm(r["x"] - [-0.5, 2., -0.5]) <= 1e-6
+
+
+def test_presolve_every_constraint_redundant():  # presolve.rs:85-101
+    P, c, A, b, cones = _presolve_data()
+    b[:] = 1e30
+    ipm, r = solve(P, c, A, b, cones)
+    assert r["status"] == "Solved" and ipm.m_reduced == 0
+    assert np.linalg.norm(r["x"] + c) <= 1e-6
+
+
+def test_presolve_disabled_keeps_the_rows():
+    P, c, A, b, cones = _presolve_data()
+    b[3] = 1e30
+    ipm, r = solve(P, c, A, b, cones, presolve_enable=0)
+    assert ipm.m_reduced == 6     # the row stays (capped at the bound, problemdata.rs:130-131); no claim on the status
