@@ -360,6 +360,7 @@ class cipm_settings(C.Structure):
         ("iterative_refinement_max_iter", C.c_int32),
         ("iterative_refinement_stop_ratio", C.c_double),
         ("linesearch_backtrack_step", C.c_double), ("min_switch_step_length", C.c_double),
+        ("presolve_enable", C.c_int32),
     ]
 
 
@@ -390,7 +391,7 @@ EXPORTED_SYMBOLS += [
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
-    "ccone_affine_ds_ex", "ccone_compute_barrier",
+    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced",
 ]
 
 _l2_ready = False
@@ -429,7 +430,7 @@ def _lib2():
     L.cipm_launch_count.restype = C.c_uint64
     L.cipm_time_ms.argtypes = [vp, C.c_int, C.c_int]
     L.cipm_time_ms.restype = C.c_double
-    for nm in ["cipm_kkt_dim", "cipm_kkt_nnz", "ccone_Hs_len"]:
+    for nm in ["cipm_kkt_dim", "cipm_kkt_nnz", "ccone_Hs_len", "cipm_m_reduced"]:
         getattr(L, nm).argtypes = [vp]
         getattr(L, nm).restype = C.c_uint64
     L.cipm_get_kkt.argtypes = [vp, u64p, u64p, f64p, i8p]
@@ -506,6 +507,7 @@ class CudaSolver:
         _check(rc, "cipm_create_ex")
         self._h = h
         self.N = int(L.cipm_kkt_dim(h))
+        self.m_reduced = int(L.cipm_m_reduced(h))    # rows left after the inf-bound presolve
 
     def update_data(self, P=None, q=None, A=None, b=None):
         """DefaultSolver::update_data (data_updating.rs:68-163): new values on the same sparsity patterns; the

@@ -565,6 +565,8 @@ enum { IST_UNSOLVED = 0, IST_SOLVED, IST_PINF, IST_DINF, IST_ALMOST_SOLVED, IST_
 class IPM {
  public:
   int n = 0, m = 0;
+  int mfull = 0;                 // rows of the caller's problem (m = rows left after the inf-bound presolve)
+  std::vector<char> keep;        // presolve row mask over the caller's rows, empty = nothing dropped
   cipm_settings set{};
   HostCsc P, A;  // equilibrated copies (host)
   std::vector<double> q, b, d, dinv, e, einv;
@@ -737,6 +739,7 @@ int IPM::upload_problem() {
 // patterns go through the STORED equilibration (P <- c D P D, A <- E A D, q <- c D q, b <- E b), the KKT values are
 // overwritten through the assembly maps, symbolic analysis and plans are kept.  Null pointer = unchanged.
 int IPM::update_data(const double* Pnz, const double* qv, const double* Anz, const double* bv) {
+  if (!keep.empty()) return CLDL_E_ARG;   // data updates are refused on a presolved problem (data_updating.rs:165-180)
   SCK(cudaSetDevice(kkt.ldl.device));
   if (Pnz) {
     for (int j = 0; j < n; j++)
@@ -808,6 +811,47 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   int tot = 0;
   for (auto& cc : cs) tot += cc.dim;
   if (tot != m) return CLDL_E_DIM;
+  // inf-bound presolve (presolver.rs:75-125, 157-204; problemdata.rs:86-93): rows of nonnegative cones whose bound
+  // is beyond the infinity bound (b was capped at it just above, which still compares as beyond) leave A, b and
+  // their cone; cipm_get_solution puts them back with s = bound, z = 0
+  mfull = m; keep.clear();
+  if (set.presolve_enable) {
+    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * 1e20;
+    std::vector<char> kp(m, 1);
+    int mred = m, r = 0;
+    for (auto& cc : cs) {
+      if (cc.type == CT_NONNEG) { for (int i = 0; i < cc.dim; i++, r++) if (b[r] > thr) { kp[r] = 0; mred--; } }
+      else r += cc.dim;
+    }
+    if (mred < m) {
+      std::vector<ConeSpec> cs2;
+      r = 0;
+      for (auto& cc : cs) {
+        if (cc.type == CT_NONNEG) {
+          int nk = 0;
+          for (int i = 0; i < cc.dim; i++) nk += kp[r + i];
+          r += cc.dim;
+          if (nk > 0) { ConeSpec c2 = cc; c2.dim = nk; cs2.push_back(c2); }
+        } else { r += cc.dim; cs2.push_back(cc); }
+      }
+      cs.swap(cs2);
+      std::vector<int> rowmap(m, -1);
+      int nr = 0;
+      for (int i = 0; i < m; i++) if (kp[i]) rowmap[i] = nr++;
+      int64_t w = 0;
+      for (int j = 0; j < n; j++) {
+        const int64_t b0 = A.colptr[j];
+        A.colptr[j] = w;
+        for (int64_t t = b0; t < A.colptr[j + 1]; t++)
+          if (rowmap[A.rowval[t]] >= 0) { A.rowval[w] = rowmap[A.rowval[t]]; A.nzval[w] = A.nzval[t]; w++; }
+      }
+      A.colptr[n] = w; A.rowval.resize(w); A.nzval.resize(w); A.m = mred;
+      for (int i = 0; i < m; i++) if (kp[i]) b[rowmap[i]] = b[i];
+      b.resize(mred);
+      keep.swap(kp);
+      m = mred;
+    }
+  }
   normq = 0; for (double v : q) normq = std::max(normq, std::fabs(v));
   normb = 0; for (double v : b) normb = std::max(normb, std::fabs(v));
   // cone set needs a stream: borrow the LDL's once it exists -> create ours first
@@ -1253,6 +1297,7 @@ void cipm_default_settings(cipm_settings* s) {
   s->iterative_refinement_abstol = 1e-12; s->iterative_refinement_max_iter = 10;
   s->iterative_refinement_stop_ratio = 5.0;
   s->linesearch_backtrack_step = 0.8; s->min_switch_step_length = 0.1;
+  s->presolve_enable = 1;
 }
 
 int cipm_create(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, const uint64_t* P_rowval,
@@ -1324,8 +1369,16 @@ int cipm_get_solution(cipm_t* h, double* x, double* z, double* s) {
   if (I.m && cudaMemcpy(hz.data(), I.z, (size_t)I.m * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CLDL_E_CUDA;
   if (I.m && cudaMemcpy(hs.data(), I.s, (size_t)I.m * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CLDL_E_CUDA;
   for (int i = 0; i < I.n; i++) x[i] = hx[i] * I.d[i] * scaleinv;
-  for (int i = 0; i < I.m; i++) z[i] = hz[i] * I.e[i] * (scaleinv * cinv);
-  for (int i = 0; i < I.m; i++) s[i] = hs[i] * I.einv[i] * scaleinv;
+  if (I.keep.empty()) {
+    for (int i = 0; i < I.m; i++) z[i] = hz[i] * I.e[i] * (scaleinv * cinv);
+    for (int i = 0; i < I.m; i++) s[i] = hs[i] * I.einv[i] * scaleinv;
+  } else {   // reverse_presolve (presolver.rs:127-150)
+    int c = 0;
+    for (int i = 0; i < I.mfull; i++) {
+      if (I.keep[i]) { z[i] = hz[c] * I.e[c] * (scaleinv * cinv); s[i] = hs[c] * I.einv[c] * scaleinv; c++; }
+      else { z[i] = 0.0; s[i] = 1e20; }
+    }
+  }
   return CLDL_OK;
 }
 
@@ -1365,6 +1418,7 @@ double cipm_time_ms(cipm_t* h, int which, int reps) {
   return (double)ms / reps;
 }
 
+uint64_t cipm_m_reduced(const cipm_t* h) { return h ? (uint64_t)h->ipm.m : 0; }
 uint64_t cipm_kkt_dim(const cipm_t* h) { return h ? (uint64_t)h->ipm.kkt.N : 0; }
 uint64_t cipm_kkt_nnz(const cipm_t* h) { return h ? (uint64_t)h->ipm.kkt.nnzK : 0; }
 

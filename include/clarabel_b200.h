@@ -176,6 +176,7 @@ typedef struct {
   double iterative_refinement_stop_ratio;
   /* nonsymmetric cones only (settings.rs:114-124) */
   double linesearch_backtrack_step, min_switch_step_length;
+  int32_t presolve_enable;   /* drop nonnegative rows with an infinite bound (presolver.rs); default 1 */
 } cipm_settings;
 
 /* DefaultInfo (default/info.rs:13-64) + timers of core/solver.rs:330-396 + counters */
@@ -221,6 +222,7 @@ uint64_t cipm_iter_ms(const cipm_t *h, double *out, uint64_t cap);
 uint64_t cipm_launch_count(void);
 /* device-timed (CUDA events) average ms of: 0 numeric refactor, 1 one LDL solve, 2 one KKT solve incl. IR */
 double cipm_time_ms(cipm_t *h, int which, int reps);                            /* kernels launched by this library so far */
+uint64_t cipm_m_reduced(const cipm_t *h);   /* rows left after the inf-bound presolve (== m when nothing was dropped) */
 uint64_t cipm_kkt_dim(const cipm_t *h);
 uint64_t cipm_kkt_nnz(const cipm_t *h);
 int cipm_get_kkt(const cipm_t *h, uint64_t *colptr, uint64_t *rowval, double *nzval, int8_t *dsigns);

@@ -144,3 +144,28 @@ def test_entropy_power_mix_same_trajectory(ke, kp):
     k = min(len(dev.trace), len(ora.trace))
     assert np.allclose(dev.trace[:k, 0], ora.trace[:k, 0], rtol=1e-4, atol=1e-12)   # mu
     assert np.allclose(dev.trace[1:k, 1], ora.trace[1:k, 1], rtol=1e-6)             # step lengths
+
+
+# ---- inf-bound presolve on the device path (tests/presolve.rs:29-101) ----
+def test_presolve_known_answers():
+    n = 3
+    P = sp.identity(n, format="csc")
+    A = (2.0 * sp.vstack([sp.identity(n), -sp.identity(n)])).tocsc()
+    c, cones = np.array([3., -2., 1.]), [("nonneg", 3), ("nonneg", 3)]
+    b = np.ones(2 * n); b[3] = 1e30
+    dev, rd, ora, ro = both(P, c, A, b, cones)
+    assert rd["status"] == "Solved" and dev.m_reduced == 5 == ora.m_reduced
+    assert rd["z"][3] == 0.0 and rd["s"][3] == 1e20
+    assert_parity(rd, ro)
+    assert np.allclose(rd["z"], ro["z"], atol=1e-7) and np.allclose(rd["s"], ro["s"], rtol=1e-7, atol=1e-7)
+    b = np.ones(2 * n); b[:3] = 1e30
+    dev, rd, ora, ro = both(P, c, A, b, cones)
+    assert rd["status"] == "Solved" and dev.m_reduced == 3
+    assert np.array_equal(rd["z"][:3], np.zeros(3)) and np.array_equal(rd["s"][:3], np.full(3, 1e20))
+    assert np.linalg.norm(rd["x"] - [-0.5, 2., -0.5]) <= 1e-6
+    assert_parity(rd, ro)
+    b = np.full(2 * n, 1e30)
+    dev, rd, ora, ro = both(P, c, A, b, cones)
+    assert rd["status"] == "Solved" and dev.m_reduced == 0 and np.linalg.norm(rd["x"] + c) <= 1e-6
+    with pytest.raises(cb.BackendError):
+        dev.update_data(q=c)          # data updates are refused on a presolved problem (data_updating.rs:165-180)
