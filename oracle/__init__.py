@@ -203,7 +203,7 @@ class QDLDL:
 # ---------------------------------------------------------------------------
 # IPM oracle (oracle/ipm_oracle.c)
 # ---------------------------------------------------------------------------
-CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3, "exp": 4, "pow": 5}
+CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3, "exp": 4, "pow": 5, "genpow": 6}
 STATUS_NAMES = ["Unsolved", "Solved", "PrimalInfeasible", "DualInfeasible", "AlmostSolved",
                 "AlmostPrimalInfeasible", "AlmostDualInfeasible", "MaxIterations", "MaxTime",
                 "NumericalError", "InsufficientProgress"]
@@ -266,6 +266,8 @@ def _ipm_lib():
                                f64p, f64p, C.c_int64, i32p, i64p, C.POINTER(Settings)]
         L.oipm_new_ex.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, i64p, i64p,
                                   f64p, f64p, C.c_int64, i32p, i64p, f64p, C.POINTER(Settings)]
+        L.oipm_new_gp.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, i64p, i64p,
+                                  f64p, f64p, C.c_int64, i32p, i64p, f64p, i64p, f64p, C.POINTER(Settings)]
         L.oipm_free.argtypes = [vp]
         L.oipm_free.restype = None
         L.oipm_test_update_scaling_ex.argtypes = [vp, f64p, f64p, C.c_double, C.c_int]
@@ -339,7 +341,8 @@ class IPM:
     P is any scipy sparse symmetric or upper-triangular matrix (converted to
     triu like problemdata.rs:79-81), A scipy sparse, cones a list of
     (kind, dim) with kind in {"zero","nonneg","soc","psd"}, ("exp", 3) for an
-    ExponentialConeT() or ("pow", alpha) for a PowerConeT(alpha).
+    ExponentialConeT(), ("pow", alpha) for a PowerConeT(alpha) or
+    ("genpow", (alphas, dim2)) for a GenPowerConeT(alphas, dim2).
     """
 
     def __init__(self, P, q, A, b, cones, settings=None):
@@ -353,14 +356,16 @@ class IPM:
         n, m = P.shape[0], A.shape[0]
         self.n, self.m = n, m
         ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
-        cd = I([3 if k in ("exp", "pow") else d for k, d in cones])
+        cd = I([3 if k in ("exp", "pow") else (len(d[0]) if k == "genpow" else d) for k, d in cones])
         cpar = F([float(d) if k == "pow" else 0.0 for k, d in cones])
+        gdim2 = I([int(d[1]) if k == "genpow" else 0 for k, d in cones])
+        galpha = F([a for k, d in cones if k == "genpow" for a in d[0]] or [0.0])
         self.settings = settings if settings is not None else default_settings()
         h = C.c_void_p()
         Pp, Pi, Px = I(P.indptr), I(P.indices), F(P.data)
         Ap, Ai, Ax = I(A.indptr), I(A.indices), F(A.data)
-        rc = L.oipm_new_ex(C.byref(h), n, m, P_(Pp), P_(Pi), P_(Px), P_(F(q)), P_(Ap), P_(Ai), P_(Ax), P_(F(b)),
-                           len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)), P_(cd), P_(cpar),
+        rc = L.oipm_new_gp(C.byref(h), n, m, P_(Pp), P_(Pi), P_(Px), P_(F(q)), P_(Ap), P_(Ai), P_(Ax), P_(F(b)),
+                           len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)), P_(cd), P_(cpar), P_(gdim2), P_(galpha),
                            C.byref(self.settings))
         if rc:
             raise ValueError(f"oipm_new failed: {rc}")

@@ -16,14 +16,16 @@
  * The reference holds NO unit-level known answers for cone numerics
  * (SURVEY.md section 4): those are pinned end-to-end only.
  *
- * Not restated (documented gaps): chordal decomposition; the GenPow cone.
+ * Not restated (documented gaps): chordal decomposition.
  * The inf-bound presolve (presolver.rs: nonnegative rows with b beyond the
  * infinity bound are dropped, the solution is expanded again) is restated in
  * oipm_new_ex / oipm_get_solution and pinned on tests/presolve.rs.
  * The exponential and 3-D power cones (nonsymmetric path: unit initialisation,
  * dual / primal-dual scaling, third-order correction, backtracking step
  * length, barrier line search, strategy checkpoints) live in nonsym_oracle.h
- * and are pinned on tests/basic_expcone.rs, basic_powcone.rs, mixed_conic.rs.
+ * and are pinned on tests/basic_expcone.rs, basic_powcone.rs, mixed_conic.rs;
+ * the generalised power cone (rank-3 sparse expansion, dual scaling only)
+ * likewise, pinned on tests/basic_genpowcone.rs.
  * The LDL ordering is passed in (see qdldl_oracle.c header).
  *
  * Function -> reference map (all under /root/reference/src)
@@ -69,7 +71,7 @@ int oq_dinv_is_finite(const oq_t *f);
 idx oq_nnzL(const oq_t *f);
 idx oq_regularize_count(const oq_t *f);
 
-enum { CONE_ZERO = 0, CONE_NONNEG = 1, CONE_SOC = 2, CONE_PSD = 3, CONE_EXP = 4, CONE_POW = 5 };
+enum { CONE_ZERO = 0, CONE_NONNEG = 1, CONE_SOC = 2, CONE_PSD = 3, CONE_EXP = 4, CONE_POW = 5, CONE_GENPOW = 6 };
 enum { SCALING_PRIMAL_DUAL = 0, SCALING_DUAL = 1 };
 enum { ST_UNSOLVED = 0, ST_SOLVED, ST_PRIMAL_INFEASIBLE, ST_DUAL_INFEASIBLE, ST_ALMOST_SOLVED,
        ST_ALMOST_PRIMAL_INFEASIBLE, ST_ALMOST_DUAL_INFEASIBLE, ST_MAX_ITERATIONS, ST_MAX_TIME,
@@ -137,6 +139,8 @@ typedef struct {
     idx psd_n; double *R, *Rinv, *lisqrt, *HsM, *W1, *W2, *W3, *wv;
     /* exponential / 3-D power cone state */
     ns3_t *ns;
+    /* generalised power cone state */
+    gp_t *gp;
 } cone_t;
 
 typedef struct { idx m, n; idx *colptr, *rowval; double *nzval; } csc;
@@ -147,7 +151,7 @@ typedef struct {
     csc P, A;              /* internal (scaled) copies; P is triu */
     double *q, *b;
     double normq, normb;
-    idx ncones; cone_t *cones; idx degree; int all_symmetric;
+    idx ncones; cone_t *cones; idx degree; int all_symmetric, allows_primal_dual;
     /* equilibration */
     double *d, *dinv, *e, *einv, c;
     /* KKT */
@@ -503,9 +507,12 @@ static void psd_lambda_inv_circ(cone_t *c, double *x, const double *z)
 }
 
 static int cone_is_sparse(const cone_t *c) { return c->type == CONE_SOC && c->sparse; }
-static int cone_Hs_diag(const cone_t *c) { return c->type == CONE_ZERO || c->type == CONE_NONNEG || (c->type == CONE_SOC && c->sparse); }
+/* number of extra KKT columns of a sparse-expandable cone (datamaps.rs:139-141, 245-247) */
+static idx cone_pdim(const cone_t *c) { return cone_is_sparse(c) ? 2 : (c->type == CONE_GENPOW ? 3 : 0); }
+static int cone_Hs_diag(const cone_t *c) { return c->type == CONE_ZERO || c->type == CONE_NONNEG || (c->type == CONE_SOC && c->sparse) || c->type == CONE_GENPOW; }
 static int cone_is_ns3(const cone_t *c) { return c->type == CONE_EXP || c->type == CONE_POW; }
-static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : (c->type == CONE_PSD ? c->psd_n : (cone_is_ns3(c) ? 3 : 1))); }
+static int cone_is_nonsym(const cone_t *c) { return cone_is_ns3(c) || c->type == CONE_GENPOW; }
+static idx cone_degree(const cone_t *c) { return c->type == CONE_ZERO ? 0 : (c->type == CONE_NONNEG ? c->dim : (c->type == CONE_PSD ? c->psd_n : (cone_is_ns3(c) ? 3 : (c->type == CONE_GENPOW ? c->gp->dim1 + 1 : 1)))); }
 
 /* Cone::unit_initialization of every cone type (zerocone.rs:71-74, nonnegativecone.rs:68-71, socone.rs:114-119,
    psdtrianglecone.rs:131-136, expcone.rs:88-94, powcone.rs:79-87) */
@@ -524,6 +531,9 @@ static void cones_unit_initialization(oipm_t *S, double *z_, double *s_)
             double a = c->ns->alpha;
             s[0] = sqrt(1.0 + a); s[1] = sqrt(1.0 + (1.0 - a)); s[2] = 0.0;
             z[0] = s[0]; z[1] = s[1]; z[2] = s[2];
+        } else if (c->type == CONE_GENPOW) {      /* genpowcone.rs:132-141 */
+            for (idx i = 0; i < c->gp->dim1; i++) s[i] = sqrt(1.0 + c->gp->alpha[i]);
+            for (idx i = 0; i < n; i++) z[i] = s[i];
         }
     }
 }
@@ -607,6 +617,10 @@ static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_, d
                 ns3_use_primal_dual_scaling(K, s, z, zt);
             }
             K->z[0] = z[0]; K->z[1] = z[1]; K->z[2] = z[2];
+        } else if (c->type == CONE_GENPOW) {      /* genpowcone.rs:149-163 */
+            if (!gp_update_dual_grad_H(c->gp, z)) return 0;
+            c->gp->mu = mu;
+            for (idx i = 0; i < n; i++) c->gp->z[i] = z[i];
         }
     }
     return 1;
@@ -635,6 +649,10 @@ static void cones_get_Hs(const oipm_t *S, double *Hs)
             idx N = c->dim, t = 0;     /* pack_triu, dense/types.rs:187-201 */
             for (idx col = 0; col < N; col++) for (idx row = 0; row <= col; row++) H[t++] = MAT(c->HsM, N, row, col);
         } else if (cone_is_ns3(c)) for (int i = 0; i < 6; i++) H[i] = c->ns->Hs[i];   /* expcone.rs:126-129 */
+        else if (c->type == CONE_GENPOW) {        /* genpowcone.rs:169-175: the diagonal D = [d1; d2] only */
+            for (idx i = 0; i < c->gp->dim1; i++) H[i] = c->gp->mu * c->gp->d1[i];
+            for (idx i = c->gp->dim1; i < n; i++) H[i] = c->gp->mu * c->gp->d2;
+        }
     }
 }
 
@@ -655,6 +673,7 @@ static void cones_mul_Hs(oipm_t *S, double *y_, const double *x_)
             psd_mul_Wx(c, 0, c->wv, x, 1.0, 0.0, c->R);     /* work = W x  */
             psd_mul_Wx(c, 1, y, c->wv, 1.0, 0.0, c->R);     /* y = W' work */
         } else if (cone_is_ns3(c)) sym3_mul(c->ns->Hs, y, x);
+        else if (c->type == CONE_GENPOW) gp_mul_Hs(c->gp, y, x);
     }
 }
 
@@ -666,7 +685,7 @@ static void cones_affine_ds(const oipm_t *S, double *ds_, const double *s_)
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) ds[i] = c->lam[i] * c->lam[i];
         else if (c->type == CONE_SOC) soc_circ(ds, c->lam, c->lam, n);
         else if (c->type == CONE_PSD) { for (idx i = 0; i < n; i++) ds[i] = 0.0; for (idx k = 0; k < c->psd_n; k++) ds[tri_index(k)] = c->lam[k] * c->lam[k]; }
-        else if (cone_is_ns3(c)) for (idx i = 0; i < n; i++) ds[i] = s_[c->off + i];      /* expcone.rs:135-137 */
+        else if (cone_is_nonsym(c)) for (idx i = 0; i < n; i++) ds[i] = s_[c->off + i];   /* expcone.rs:135-137 */
     }
 }
 
@@ -684,6 +703,7 @@ static void cones_combined_ds_shift(oipm_t *S, double *shift_, double *sz_, doub
             for (int i = 0; i < 3; i++) shift[i] = c->ns->grad[i] * sigmamu - eta[i];
             continue;
         }
+        if (c->type == CONE_GENPOW) { for (idx i = 0; i < n; i++) shift[i] = c->gp->grad[i] * sigmamu; continue; }   /* genpowcone.rs:208-213: no third-order term */
         double *tmp = shift;
         if (c->type == CONE_PSD) {
             memcpy(tmp, sz, (size_t)n * sizeof(double)); psd_mul_Wx(c, 0, sz, tmp, 1.0, 0.0, c->R);
@@ -711,7 +731,7 @@ static void cones_ds_from_dz_offset(oipm_t *S, double *out_, const double *ds_, 
         if (c->type == CONE_ZERO) for (idx i = 0; i < n; i++) out[i] = 0.0;
         else if (c->type == CONE_NONNEG) for (idx i = 0; i < n; i++) out[i] = ds[i] / z[i];
         else if (c->type == CONE_PSD) { psd_lambda_inv_circ(c, c->wv, ds); psd_mul_Wx(c, 1, out, c->wv, 1.0, 0.0, c->R); }
-        else if (cone_is_ns3(c)) for (idx i = 0; i < n; i++) out[i] = ds[i];              /* expcone.rs:150-152 */
+        else if (cone_is_nonsym(c)) for (idx i = 0; i < n; i++) out[i] = ds[i];           /* expcone.rs:150-152 */
         else {
             double resz = soc_residual(z, n);
             double l1ds1 = vdot(c->lam + 1, ds + 1, n - 1), w1ds1 = vdot(c->w + 1, ds + 1, n - 1);
@@ -732,10 +752,12 @@ static void cones_ds_from_dz_offset(oipm_t *S, double *out_, const double *ds_, 
 static double ns3_backtrack_search(const cone_t *c, const double *dq, const double *q, double a_init, double a_min,
                                    double step, int dual)
 {
-    double a = a_init, work[3];
+    double a = a_init, work3[3];
+    double *work = c->type == CONE_GENPOW ? c->gp->work : work3;
     for (;;) {
-        for (int i = 0; i < 3; i++) work[i] = 1.0 * q[i] + a * dq[i];
-        int ok = c->type == CONE_EXP ? (dual ? exp_is_dual_feasible(work) : exp_is_primal_feasible(work))
+        for (idx i = 0; i < c->dim; i++) work[i] = 1.0 * q[i] + a * dq[i];
+        int ok = c->type == CONE_GENPOW ? (dual ? gp_is_dual_feasible(c->gp, work) : gp_is_primal_feasible(c->gp, work))
+               : c->type == CONE_EXP ? (dual ? exp_is_dual_feasible(work) : exp_is_primal_feasible(work))
                                      : (dual ? pow_is_dual_feasible(work, c->ns->alpha) : pow_is_primal_feasible(work, c->ns->alpha));
         if (ok) break;
         a *= step;
@@ -750,7 +772,7 @@ static double cones_step_length(oipm_t *S, const double *dz_, const double *ds_,
     double alpha = amax;
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k]; idx n = c->dim;
-        if (cone_is_ns3(c)) continue;
+        if (cone_is_nonsym(c)) continue;
         const double *dz = dz_ + c->off, *ds = ds_ + c->off, *z = z_ + c->off, *s = s_ + c->off;
         double az = alpha, as = alpha;
         if (c->type == CONE_NONNEG) {
@@ -773,7 +795,7 @@ static double cones_step_length(oipm_t *S, const double *dz_, const double *ds_,
         if (ceil_ < alpha) alpha = ceil_;
         for (idx k = 0; k < S->ncones; k++) {
             cone_t *c = &S->cones[k];
-            if (!cone_is_ns3(c)) continue;
+            if (!cone_is_nonsym(c)) continue;
             const double *dz = dz_ + c->off, *ds = ds_ + c->off, *z = z_ + c->off, *s = s_ + c->off;
             /* expcone.rs:154-174 */
             double az = ns3_backtrack_search(c, dz, z, alpha, S->set.min_terminate_step_length, S->set.linesearch_backtrack_step, 1);
@@ -819,6 +841,13 @@ static double cones_compute_barrier(oipm_t *S, const double *z_, const double *s
             double b = 0.0;
             if (c->type == CONE_EXP) { b += exp_barrier_dual(cz); b += exp_barrier_primal(cs); }
             else { b += pow_barrier_dual(cz, c->ns->alpha); b += pow_barrier_primal(cs, c->ns->alpha); }
+            barrier += b;
+        } else if (c->type == CONE_GENPOW) {      /* genpowcone.rs:249-263: primal first, then dual */
+            double b = 0.0, *w = c->gp->work;
+            for (idx i = 0; i < n; i++) w[i] = 1.0 * s[i] + a * ds[i];
+            b += gp_barrier_primal(c->gp, w);
+            for (idx i = 0; i < n; i++) w[i] = 1.0 * z[i] + a * dz[i];
+            b += gp_barrier_dual(c->gp, w);
             barrier += b;
         }
     }
@@ -880,7 +909,7 @@ static void kkt_assemble(oipm_t *S)
         c->boff = nHs;
         c->blen = cone_Hs_diag(c) ? c->dim : c->dim * (c->dim + 1) / 2;
         nHs += c->blen;
-        if (cone_is_sparse(c)) { p += 2; nnz_vec += 2 * c->dim; }
+        if (cone_pdim(c)) { p += cone_pdim(c); nnz_vec += 2 * c->dim; }   /* SOC: u, v; GenPow: q (dim1) + r (dim2) + p (dim) */
     }
     S->p = p; S->nHs = nHs;
     idx N = n + m + p; S->N = N;
@@ -904,6 +933,9 @@ static void kkt_assemble(oipm_t *S)
         if (cone_Hs_diag(c)) for (idx i = 0; i < c->dim; i++) cp[row + i] += 1;
         else for (idx i = 0; i < c->dim; i++) cp[row + i] += i + 1;
         if (cone_is_sparse(c)) { cp[pcol] += c->dim; cp[pcol + 1] += c->dim; cp[pcol] += 1; cp[pcol + 1] += 1; pcol += 2; }
+        if (c->type == CONE_GENPOW) {   /* datamaps.rs:264-287: q, r, p columns + their diagonal entries */
+            cp[pcol] += c->gp->dim1 + 1; cp[pcol + 1] += c->gp->dim2 + 1; cp[pcol + 2] += c->dim + 1; pcol += 3;
+        }
     }
     /* counts -> pointers (next-fill positions) */
     { idx cur = 0; for (idx j = 0; j <= N; j++) { idx cnt = cp[j]; cp[j] = cur; cur += cnt; } }
@@ -939,6 +971,15 @@ static void kkt_assemble(oipm_t *S)
             for (idx i = 0; i < 2; i++) { idx col = pcol + i; idx dest = cp[col]++; K->rowval[dest] = col; K->nzval[dest] = 0.0; c->map_D[i] = dest; }
             pcol += 2;
         }
+        if (c->type == CONE_GENPOW) {   /* datamaps.rs:289-312 */
+            gp_t *g = c->gp;
+            g->map_q = ivec(g->dim1); g->map_r = ivec(g->dim2); g->map_p = ivec(c->dim);
+            for (idx i = 0; i < g->dim1; i++) { idx dest = cp[pcol]++; K->rowval[dest] = row + i; K->nzval[dest] = 0.0; g->map_q[i] = dest; }
+            for (idx i = 0; i < g->dim2; i++) { idx dest = cp[pcol + 1]++; K->rowval[dest] = row + g->dim1 + i; K->nzval[dest] = 0.0; g->map_r[i] = dest; }
+            for (idx i = 0; i < c->dim; i++) { idx dest = cp[pcol + 2]++; K->rowval[dest] = row + i; K->nzval[dest] = 0.0; g->map_p[i] = dest; }
+            for (idx i = 0; i < 3; i++) { idx col = pcol + i; idx dest = cp[col]++; K->rowval[dest] = col; K->nzval[dest] = 0.0; g->map_D[i] = dest; }
+            pcol += 3;
+        }
     }
     /* backshift */
     for (idx j = N; j > 0; j--) cp[j] = cp[j - 1];
@@ -950,7 +991,10 @@ static void kkt_assemble(oipm_t *S)
     for (idx i = 0; i < N; i++) S->dsigns[i] = 1;
     for (idx i = n; i < n + m; i++) S->dsigns[i] = -1;
     idx pp = n + m;
-    for (idx k = 0; k < S->ncones; k++) if (cone_is_sparse(&S->cones[k])) { S->dsigns[pp] = -1; S->dsigns[pp + 1] = 1; pp += 2; }
+    for (idx k = 0; k < S->ncones; k++) {
+        if (cone_is_sparse(&S->cones[k])) { S->dsigns[pp] = -1; S->dsigns[pp + 1] = 1; pp += 2; }
+        else if (S->cones[k].type == CONE_GENPOW) { S->dsigns[pp] = -1; S->dsigns[pp + 1] = -1; S->dsigns[pp + 2] = 1; pp += 3; }   /* datamaps.rs:252-254 */
+    }
     S->info.nnzK = nnzK;
 }
 
@@ -986,6 +1030,18 @@ static int kkt_update(oipm_t *S)
     kkt_update_values(S, S->map_Hs, S->Hs, S->nHs);
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k];
+        if (c->type == CONE_GENPOW) {   /* datamaps.rs:314-337: sqrt(mu) distributed to the off-diagonal vectors */
+            gp_t *g = c->gp; double sq = sqrt(g->mu);
+            kkt_update_values(S, g->map_q, g->q, g->dim1);
+            kkt_update_values(S, g->map_r, g->r, g->dim2);
+            kkt_update_values(S, g->map_p, g->p, c->dim);
+            kkt_scale_values(S, g->map_q, g->dim1, -sq);
+            kkt_scale_values(S, g->map_r, g->dim2, -sq);
+            kkt_scale_values(S, g->map_p, c->dim, -sq);
+            double d3[3] = {-1.0, -1.0, 1.0};
+            kkt_update_values(S, g->map_D, d3, 3);
+            continue;
+        }
         if (!cone_is_sparse(c)) continue;
         double e2 = c->eta * c->eta;
         kkt_update_values(S, c->map_u, c->u, c->dim);
@@ -1102,7 +1158,7 @@ static void equilibrate(oipm_t *S)
     for (idx i = 0; i < m; i++) ew[i] = 1.0;
     for (idx k = 0; k < S->ncones; k++) {
         cone_t *c = &S->cones[k];
-        if (c->type == CONE_SOC || c->type == CONE_PSD || cone_is_ns3(c)) {
+        if (c->type == CONE_SOC || c->type == CONE_PSD || cone_is_nonsym(c)) {
             double mean = vmean(e + c->off, c->dim);
             for (idx i = 0; i < c->dim; i++) ew[c->off + i] = (1.0 / e[c->off + i]) * mean;
             changed = 1;
@@ -1119,7 +1175,8 @@ void oipm_free(oipm_t *S)
     if (!S) return;
     csc_free(&S->P); csc_free(&S->A); free(S->q); free(S->b); free(S->keep);
     for (idx k = 0; k < S->ncones; k++) { cone_t *c = &S->cones[k]; free(c->w); free(c->lam); free(c->u); free(c->v); free(c->map_u); free(c->map_v);
-        free(c->R); free(c->Rinv); free(c->lisqrt); free(c->HsM); free(c->W1); free(c->W2); free(c->W3); free(c->wv); free(c->ns); }
+        free(c->R); free(c->Rinv); free(c->lisqrt); free(c->HsM); free(c->W1); free(c->W2); free(c->W3); free(c->wv); free(c->ns);
+        if (c->gp) { gp_t *g = c->gp; free(g->alpha); free(g->grad); free(g->z); free(g->p); free(g->q); free(g->r); free(g->d1); free(g->work); free(g->work_pb); free(g->map_p); free(g->map_q); free(g->map_r); free(g); } }
     free(S->cones); free(S->d); free(S->dinv); free(S->e); free(S->einv);
     if (S->K.colptr) csc_free(&S->K);
     free(S->map_P); free(S->map_A); free(S->map_Hs); free(S->map_diagP); free(S->map_diag_full);
@@ -1144,12 +1201,26 @@ int oipm_new(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const dou
 {
     return oipm_new_ex(out, n, m, Pp, Pi, Px, q, Ap, Ai, Ax, b, ncones_in, ctype, cdim, NULL, set);
 }
+int oipm_new_gp(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
+                const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
+                idx ncones_in, const int32_t *ctype, const idx *cdim, const double *cparam,
+                const idx *gp_dim2, const double *gp_alpha, const oipm_settings *set);
 /* cparam[k]: the exponent of a PowerConeT(alpha) (supportedcone.rs:36-38), ignored for the other cones */
 int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
                 const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
                 idx ncones_in, const int32_t *ctype, const idx *cdim, const double *cparam, const oipm_settings *set)
 {
+    return oipm_new_gp(out, n, m, Pp, Pi, Px, q, Ap, Ai, Ax, b, ncones_in, ctype, cdim, cparam, NULL, NULL, set);
+}
+/* GenPowerConeT(alpha, dim2) (supportedcone.rs:44): cdim[k] = len(alpha), gp_dim2[k] = dim2, the exponents of all
+   such cones concatenated in cone order in gp_alpha */
+int oipm_new_gp(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const double *Px,
+                const double *q, const idx *Ap, const idx *Ai, const double *Ax, const double *b,
+                idx ncones_in, const int32_t *ctype, const idx *cdim, const double *cparam,
+                const idx *gp_dim2, const double *gp_alpha, const oipm_settings *set)
+{
     *out = NULL;
+    idx gp_cursor = 0;
     oipm_t *S = (oipm_t *)calloc(1, sizeof(oipm_t));
     if (set) S->set = *set; else oipm_default_settings(&S->set);
     S->n = n; S->m = m;
@@ -1164,6 +1235,12 @@ int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
     while (k < ncones_in) {
         int t = ctype[k]; idx dm = cdim[k];
         if (t == CONE_EXP || t == CONE_POW) dm = 3;
+        idx gdim1 = 0, gdim2 = 0; const double *galpha = NULL;
+        if (t == CONE_GENPOW) {
+            if (!gp_dim2 || !gp_alpha) { oipm_free(S); return -3; }
+            gdim1 = cdim[k]; gdim2 = gp_dim2[k]; galpha = gp_alpha + gp_cursor; gp_cursor += gdim1;
+            dm = gdim1 + gdim2;
+        }
         idx numel = (t == CONE_PSD) ? dm * (dm + 1) / 2 : dm;
         if (numel == 0) { k++; continue; }
         int collapsible = (t == CONE_NONNEG) || (t == CONE_SOC && dm == 1) || (t == CONE_PSD && dm == 1);
@@ -1189,6 +1266,17 @@ int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
                 S->cones[nc].ns = (ns3_t *)calloc(1, sizeof(ns3_t));
                 S->cones[nc].ns->alpha = (t == CONE_POW && cparam) ? cparam[k] : 0.5;
                 if (t == CONE_POW && !(S->cones[nc].ns->alpha > 0.0 && S->cones[nc].ns->alpha < 1.0)) { oipm_free(S); return -3; }
+            }
+            if (t == CONE_GENPOW) {       /* GenPowerConeData::new (genpowcone.rs:41-60) */
+                gp_t *g = (gp_t *)calloc(1, sizeof(gp_t));
+                S->cones[nc].gp = g;
+                g->dim1 = gdim1; g->dim2 = gdim2;
+                g->alpha = dvec(gdim1); memcpy(g->alpha, galpha, (size_t)gdim1 * sizeof(double));
+                double asum = 0.0, asq = 0.0; int pos = 1;
+                for (idx i = 0; i < gdim1; i++) { asum += g->alpha[i]; asq += g->alpha[i] * g->alpha[i]; if (!(g->alpha[i] > 0.0)) pos = 0; }
+                if (!pos || gdim1 < 1 || !(fabs(1.0 - asum) < 2.220446049250313e-16 * (double)gdim1 * 0.5 + 1e-300)) { oipm_free(S); return -3; }
+                g->grad = dvec(dm); g->z = dvec(dm); g->p = dvec(dm); g->q = dvec(gdim1); g->r = dvec(gdim2); g->d1 = dvec(gdim1);
+                g->mu = 1.0; g->d2 = 0.0; g->psi = 1.0 / asq; g->work = dvec(dm); g->work_pb = dvec(dm);
             }
             nc++; k++;
         }
@@ -1235,13 +1323,14 @@ int oipm_new_ex(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
             S->keep = keep; m = mred; S->m = mred;
         } else free(keep);
     }
-    idx off = 0; S->degree = 0; S->all_symmetric = 1;
+    idx off = 0; S->degree = 0; S->all_symmetric = 1; S->allows_primal_dual = 1;
     for (idx c = 0; c < nc; c++) {
         cone_t *cn = &S->cones[c];
-        if (cone_is_ns3(cn)) S->all_symmetric = 0;
+        if (cone_is_nonsym(cn)) S->all_symmetric = 0;
+        if (cn->type == CONE_GENPOW) S->allows_primal_dual = 0;   /* genpowcone.rs:108-110 */
         cn->off = off; off += cn->dim;
         S->degree += cone_degree(cn);
-        if (cn->type != CONE_ZERO && !cone_is_ns3(cn)) { cn->w = dvec(cn->dim); cn->lam = dvec(cn->dim); }
+        if (cn->type != CONE_ZERO && !cone_is_nonsym(cn)) { cn->w = dvec(cn->dim); cn->lam = dvec(cn->dim); }
         if (cn->type == CONE_PSD) {
             idx n2 = cn->psd_n * cn->psd_n;
             cn->R = dvec(n2); cn->Rinv = dvec(n2); cn->lisqrt = dvec(cn->psd_n); cn->HsM = dvec(cn->dim * cn->dim);
@@ -1541,8 +1630,8 @@ int oipm_solve(oipm_t *S, double *trace, int32_t trace_cap)
         for (idx i = 0; i < n; i++) S->vx[i] = 0.0;
     }
     S->vtau = 1.0; S->vkap = 1.0;
-    /* every cone built here allows primal-dual scaling (only GenPow does not) */
-    int scaling = SCALING_PRIMAL_DUAL;
+    /* core/solver.rs:277-280: the dual-only scaling from the start when a cone (GenPow) has no primal-dual one */
+    int scaling = S->allows_primal_dual ? SCALING_PRIMAL_DUAL : SCALING_DUAL;
 
     for (;;) {
         residuals_update(S);

@@ -363,4 +363,130 @@ static void ns3_use_primal_dual_scaling(ns3_t *K, const double *s, const double 
     }
 }
 
+
+/* ------------------------------------------------------------------ generalised power cone (genpowcone.rs) */
+/* { (u, w) : prod u_i^alpha_i >= ||w|| }, u in R^dim1, w in R^dim2.  State of GenPowerConeData (genpowcone.rs:10-60)
+   plus the KKT maps of its rank-3 sparse expansion (datamaps.rs:226-243). */
+typedef struct {
+    idx dim1, dim2;
+    double *alpha;
+    double *grad, *z;           /* dual gradient, z at the scaling point */
+    double mu;
+    double *p, *q, *r, *d1;     /* Hs = mu (D + p p' - q q' - r r'),  D = diag(d1, d2 I) */
+    double d2, psi;
+    double *work, *work_pb;
+    idx *map_p, *map_q, *map_r; idx map_D[3];
+} gp_t;
+
+static double gp_sumsq(const double *x, idx n) { double s = 0.0; for (idx i = 0; i < n; i++) s += x[i] * x[i]; return s; }
+
+/* genpowcone.rs:267-286 */
+static int gp_is_primal_feasible(const gp_t *K, const double *s)
+{
+    for (idx i = 0; i < K->dim1; i++) if (!(s[i] > 0.0)) return 0;
+    double res = 0.0;
+    for (idx i = 0; i < K->dim1; i++) res = res + 2.0 * K->alpha[i] * logsafe(s[i]);
+    res = exp(res) - gp_sumsq(s + K->dim1, K->dim2);
+    return res > 0.0;
+}
+/* genpowcone.rs:289-308 */
+static int gp_is_dual_feasible(const gp_t *K, const double *z)
+{
+    for (idx i = 0; i < K->dim1; i++) if (!(z[i] > 0.0)) return 0;
+    double res = 0.0;
+    for (idx i = 0; i < K->dim1; i++) res = res + 2.0 * K->alpha[i] * logsafe(z[i] / K->alpha[i]);
+    res = exp(res) - gp_sumsq(z + K->dim1, K->dim2);
+    return res > 0.0;
+}
+/* genpowcone.rs:333-354 */
+static double gp_barrier_dual(const gp_t *K, const double *z)
+{
+    double res = 0.0;
+    for (idx i = 0; i < K->dim1; i++) res += 2.0 * K->alpha[i] * logsafe(z[i] / K->alpha[i]);
+    res = exp(res) - gp_sumsq(z + K->dim1, K->dim2);
+    double barrier = -logsafe(res);
+    for (idx i = 0; i < K->dim1; i++) barrier -= logsafe(z[i]) * (1.0 - K->alpha[i]);
+    return barrier;
+}
+/* genpowcone.rs:451-485 + nonsymmetric_common.rs:191-219 */
+static double gp_newton_raphson(double norm_r, const double *p, double phi, const double *alpha, idx dim1, double psi)
+{
+    double x = -1.0 / norm_r + (psi * norm_r + sqrt((phi / norm_r / norm_r + psi * psi - 1.0) * phi)) / (phi - norm_r * norm_r);
+    for (int iter = 0; iter < 100; iter++) {
+        double f1 = -(2.0 * x + 2.0 / norm_r) / (x * x + 2.0 * x / norm_r);
+        for (idx i = 0; i < dim1; i++) f1 = f1 + 2.0 * alpha[i] * norm_r / (norm_r * x + (1.0 + alpha[i]) / alpha[i]);
+        double f0 = -logsafe(2.0 * x / norm_r + x * x);
+        for (idx i = 0; i < dim1; i++) f0 = f0 + 2.0 * alpha[i] * (logsafe(x * norm_r + (1.0 + alpha[i]) / alpha[i]) - logsafe(p[i]));
+        double dx = -f0 / f1;
+        if ((dx < NS_EPS) || (fabs(dx / x) < sqrt(NS_EPS)) || (fabs(f1) < NS_EPS)) break;
+        x += dx;
+    }
+    return x;
+}
+/* genpowcone.rs:404-441.  NB the w-part of the gradient is formed from the cone's stored Hessian vector data.r,
+   not from the argument's own w-part (genpowcone.rs:426) -- restated as written. */
+static void gp_gradient_primal(const gp_t *K, double *g, const double *s)
+{
+    idx dim1 = K->dim1, dim2 = K->dim2;
+    double phi = 1.0;
+    for (idx i = 0; i < dim1; i++) phi = phi * pow(s[i], 2.0 * K->alpha[i]);
+    double norm_r = vnorm(s + dim1, dim2);
+    if (norm_r > NS_EPS) {
+        double g1 = gp_newton_raphson(norm_r, s, phi, K->alpha, dim1, K->psi);
+        for (idx i = 0; i < dim2; i++) g[dim1 + i] = (g1 / norm_r) * K->r[i];
+        for (idx i = 0; i < dim1; i++) g[i] = -(1.0 + K->alpha[i] + K->alpha[i] * g1 * norm_r) / s[i];
+    } else {
+        for (idx i = 0; i < dim2; i++) g[dim1 + i] = 0.0;
+        for (idx i = 0; i < dim1; i++) g[i] = -(1.0 + K->alpha[i]) / s[i];
+    }
+}
+/* genpowcone.rs:310-331 */
+static double gp_barrier_primal(gp_t *K, const double *s)
+{
+    double *g = K->work_pb; idx n = K->dim1 + K->dim2;
+    gp_gradient_primal(K, g, s);
+    for (idx i = 0; i < n; i++) g[i] = -g[i];
+    return -gp_barrier_dual(K, g) - (double)(K->dim1 + 1);
+}
+/* genpowcone.rs:360-399; returns 0 where the reference asserts zeta > 0 */
+static int gp_update_dual_grad_H(gp_t *K, const double *z)
+{
+    idx dim1 = K->dim1, dim2 = K->dim2;
+    double phi = 1.0;
+    for (idx i = 0; i < dim1; i++) phi = phi * pow(z[i] / K->alpha[i], 2.0 * K->alpha[i]);
+    double norm2w = gp_sumsq(z + dim1, dim2);
+    double zeta = phi - norm2w;
+    if (!(zeta > 0.0)) return 0;
+    double *tau = K->q;
+    for (idx i = 0; i < dim1; i++) {
+        tau[i] = 2.0 * K->alpha[i] / z[i];
+        K->grad[i] = -tau[i] * phi / zeta - (1.0 - K->alpha[i]) / z[i];
+    }
+    for (idx i = 0; i < dim2; i++) K->grad[dim1 + i] = (2.0 / zeta) * z[dim1 + i];
+    double p0 = sqrt(phi * (phi + norm2w) / 2.0);
+    double p1 = -2.0 * phi / p0;
+    double q0 = sqrt(zeta * phi / 2.0);
+    double r1 = 2.0 * sqrt(zeta / (phi + norm2w));
+    for (idx i = 0; i < dim1; i++) K->d1[i] = tau[i] * phi / (zeta * z[i]) + (1.0 - K->alpha[i]) / (z[i] * z[i]);
+    K->d2 = 2.0 / zeta;
+    for (idx i = 0; i < dim1; i++) K->p[i] = (p0 / zeta) * tau[i];
+    for (idx i = 0; i < dim2; i++) K->p[dim1 + i] = (p1 / zeta) * z[dim1 + i];
+    for (idx i = 0; i < dim1; i++) K->q[i] *= q0 / zeta;
+    for (idx i = 0; i < dim2; i++) K->r[i] = (r1 / zeta) * z[dim1 + i];
+    return 1;
+}
+/* genpowcone.rs:177-202 */
+static void gp_mul_Hs(const gp_t *K, double *y, const double *x)
+{
+    idx dim1 = K->dim1, dim2 = K->dim2, n = dim1 + dim2;
+    double coef_p = 0.0, coef_q = 0.0, coef_r = 0.0;
+    for (idx i = 0; i < n; i++) coef_p += K->p[i] * x[i];
+    for (idx i = 0; i < dim1; i++) coef_q += K->q[i] * x[i];
+    for (idx i = 0; i < dim2; i++) coef_r += K->r[i] * x[dim1 + i];
+    for (idx i = 0; i < dim1; i++) y[i] = K->d1[i] * x[i] - coef_q * K->q[i];
+    for (idx i = 0; i < dim2; i++) y[dim1 + i] = K->d2 * x[dim1 + i] - coef_r * K->r[i];
+    for (idx i = 0; i < n; i++) y[i] = coef_p * K->p[i] + 1.0 * y[i];
+    for (idx i = 0; i < n; i++) y[i] *= K->mu;
+}
+
 #endif

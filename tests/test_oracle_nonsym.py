@@ -148,3 +148,45 @@ def test_unit_initialization_is_interior_and_central():
         assert ipm.update_scaling_ex(s, z, 1.0, 1)
         g = ipm.ns3_state(0)["grad"]
         assert np.allclose(s, -(s @ z / 3.0) * g, atol=1e-6)
+
+
+# ---- generalised power cone ----
+def genpow_data():  # basic_genpowcone.rs:5-33
+    n = 6
+    P = sp.csc_matrix((n, n))
+    c = np.array([0., 0., -1., 0., 0., -1.])
+    A2 = sp.csc_matrix(np.array([[1., 2., 0., 3., 0., 0.], [0., 0., 0., 0., 1., 0.]]))
+    A = sp.vstack([-sp.identity(n, format="csc"), A2]).tocsc()
+    b = np.concatenate([np.zeros(n), [3., 1.]])
+    return P, c, A, b, [("genpow", ([0.6, 0.4], 1)), ("genpow", ([0.1, 0.9], 1)), ("zero", 2)]
+
+
+def test_genpowcone():  # basic_genpowcone.rs:35-45
+    _, r = solve(*genpow_data())
+    assert r["status"] == "Solved"
+    assert abs(r["obj_val"] + 1.8458) <= 1e-3
+
+
+def test_genpowcone_kkt_structure():
+    """rank-3 sparse expansion: 3 extra columns per cone (q, r, p) with signs (-1, -1, +1) (datamaps.rs:226-337)"""
+    ipm, _ = solve(*genpow_data())
+    N, cp, rv, nz, ds = ipm.kkt()
+    n, m = 6, 8
+    assert N == n + m + 6
+    assert list(ds[n + m:]) == [-1, -1, 1, -1, -1, 1]
+    K = sp.csc_matrix((nz, rv, cp), shape=(N, N)).toarray()
+    for k in range(2):
+        row, col = n + 3 * k, n + m + 3 * k
+        assert np.all(K[row:row + 2, col] != 0) and K[row + 2, col] == 0            # q: dim1 rows
+        assert K[row + 2, col + 1] != 0 and np.all(K[row:row + 2, col + 1] == 0)    # r: dim2 rows
+        assert np.all(K[row:row + 3, col + 2] != 0)                                 # p: all rows
+
+
+def test_genpow_equals_powcone_when_dim_is_3():
+    """GenPowerConeT([a, 1-a], 1) and PowerConeT(a) describe the same set; the optimal value agrees"""
+    P, c, A, b, _ = genpow_data()
+    _, r1 = solve(P, c, A, b, [("genpow", ([0.6, 0.4], 1)), ("genpow", ([0.1, 0.9], 1)), ("zero", 2)])
+    _, r2 = solve(P, c, A, b, [("pow", 0.6), ("pow", 0.1), ("zero", 2)])
+    assert r1["status"] == r2["status"] == "Solved"
+    assert abs(r1["obj_val"] - r2["obj_val"]) <= 1e-6
+    assert np.allclose(r1["x"], r2["x"], atol=1e-3)      # the optimal face is flat: x agrees to solver tolerance only
