@@ -331,7 +331,7 @@ def order(n, colptr, rowval, kind=ORDER_AMD, dense_scale=1.5, nd_leaf=200):
 # ===========================================================================
 # Level 2: device-resident solver (cipm_* / ckkt_* / ccone_*)
 # ===========================================================================
-CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3, "exp": 4, "pow": 5}
+CONE_CODES = {"zero": 0, "nonneg": 1, "soc": 2, "psd": 3, "exp": 4, "pow": 5, "genpow": 6}
 SCALING_PRIMAL_DUAL, SCALING_DUAL = 0, 1
 STATUS_NAMES = ["Unsolved", "Solved", "PrimalInfeasible", "DualInfeasible", "AlmostSolved",
                 "AlmostPrimalInfeasible", "AlmostDualInfeasible", "MaxIterations", "MaxTime",
@@ -391,7 +391,7 @@ EXPORTED_SYMBOLS += [
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
-    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced",
+    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_create_gp",
 ]
 
 _l2_ready = False
@@ -410,6 +410,9 @@ def _lib2():
                               C.POINTER(cldl_opts), u64p]
     L.cipm_create_ex.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p, u64p, u64p, f64p,
                                  f64p, C.c_uint64, C.POINTER(C.c_int32), u64p, f64p, C.POINTER(cipm_settings),
+                                 C.POINTER(cldl_opts), u64p]
+    L.cipm_create_gp.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p, u64p, u64p, f64p,
+                                 f64p, C.c_uint64, C.POINTER(C.c_int32), u64p, f64p, u64p, f64p, C.POINTER(cipm_settings),
                                  C.POINTER(cldl_opts), u64p]
     L.ccone_is_symmetric.argtypes = [vp]
     L.ccone_unit_initialization.argtypes = [vp, f64p, f64p]
@@ -473,8 +476,9 @@ class CudaSolver:
 
     P: scipy sparse (symmetric or upper triangle; converted to triu like
     problemdata.rs:79-81); A: scipy sparse; cones: list of (kind, dim) with kind in
-    {"zero", "nonneg", "soc", "psd"}, ("exp", 3) for an ExponentialConeT() and
-    ("pow", alpha) for a PowerConeT(alpha).
+    {"zero", "nonneg", "soc", "psd"}, ("exp", 3) for an ExponentialConeT(),
+    ("pow", alpha) for a PowerConeT(alpha) and ("genpow", (alphas, dim2)) for a
+    GenPowerConeT(alphas, dim2).
     """
 
     def __init__(self, P, q, A, b, cones, settings=None, *, ordering=ORDER_BEST, kkt_perm=None,
@@ -492,19 +496,21 @@ class CudaSolver:
         L.cldl_default_opts(C.byref(o))
         o.ordering, o.device, o.max_panel, o.nd_leaf = ordering, device, max_panel, nd_leaf
         ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
-        cd = _u64([3 if k in ("exp", "pow") else d for k, d in cones])
+        cd = _u64([3 if k in ("exp", "pow") else (len(d[0]) if k == "genpow" else d) for k, d in cones])
         cpar = _f64([float(d) if k == "pow" else 0.0 for k, d in cones])
+        gdim2 = _u64([int(d[1]) if k == "genpow" else 0 for k, d in cones])
+        galpha = _f64([a for k, d in cones if k == "genpow" for a in d[0]] or [0.0])
         Pp, Pi, Px = _u64(P.indptr), _u64(P.indices), _f64(P.data)
         Ap, Ai, Ax = _u64(A.indptr), _u64(A.indices), _f64(A.data)
         qq, bb = _f64(q), _f64(b)
         pm = _u64(kkt_perm) if kkt_perm is not None else None
         h = C.c_void_p()
-        rc = L.cipm_create_ex(C.byref(h), self.n, self.m, _p(Pp, C.c_uint64), _p(Pi, C.c_uint64), _p(Px, C.c_double),
+        rc = L.cipm_create_gp(C.byref(h), self.n, self.m, _p(Pp, C.c_uint64), _p(Pi, C.c_uint64), _p(Px, C.c_double),
                               _p(qq, C.c_double), _p(Ap, C.c_uint64), _p(Ai, C.c_uint64), _p(Ax, C.c_double),
                               _p(bb, C.c_double), len(cones), ct.ctypes.data_as(C.POINTER(C.c_int32)),
-                              _p(cd, C.c_uint64), _p(cpar, C.c_double), C.byref(self.settings), C.byref(o),
-                              _p(pm, C.c_uint64) if pm is not None else None)
-        _check(rc, "cipm_create_ex")
+                              _p(cd, C.c_uint64), _p(cpar, C.c_double), _p(gdim2, C.c_uint64), _p(galpha, C.c_double),
+                              C.byref(self.settings), C.byref(o), _p(pm, C.c_uint64) if pm is not None else None)
+        _check(rc, "cipm_create_gp")
         self._h = h
         self.N = int(L.cipm_kkt_dim(h))
         self.m_reduced = int(L.cipm_m_reduced(h))    # rows left after the inf-bound presolve

@@ -366,17 +366,29 @@ k_soc_step_length(ConeDev c, const double* __restrict__ dz_, const double* __res
 #define CCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "[clarabel_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -20; } } while (0)
 
 int ConeSet::collapse(const int32_t* types, const uint64_t* dims, uint64_t n, std::vector<ConeSpec>& out,
-                      const double* params) {
+                      const double* params, const uint64_t* gp_dim2, const double* gp_alpha) {
   out.clear();
-  uint64_t k = 0;
+  uint64_t k = 0, gp_cursor = 0;
   auto numel = [](int t, uint64_t d) { return t == CT_PSD ? d * (d + 1) / 2 : d; };
   while (k < n) {
     const int t = types[k];
-    if (t < 0 || t > CT_POW) return -21;
+    if (t < 0 || t > CT_GENPOW) return -21;
+    if (t == CT_GENPOW) {   // GenPowerConeT(alpha, dim2): dims[k] = len(alpha) (supportedcone.rs:44, genpowcone.rs:41-49)
+      if (!gp_dim2 || !gp_alpha || dims[k] < 1) return -21;
+      const uint64_t d1 = dims[k], d2 = gp_dim2[k];
+      ConeSpec cs{t, (int)(d1 + d2), 0, 0.0, std::vector<double>(gp_alpha + gp_cursor, gp_alpha + gp_cursor + d1)};
+      gp_cursor += d1;
+      double sum = 0.0;
+      for (double a : cs.alphas) { if (!(a > 0.0)) return -21; sum += a; }
+      if (!(std::fabs(1.0 - sum) < 2.220446049250313e-16 * (double)d1 * 0.5 + 1e-300)) return -21;
+      out.push_back(cs);
+      k++;
+      continue;
+    }
     if (t == CT_EXP || t == CT_POW) {   // 3 rows each, never merged (supportedcone.rs:105-161)
       const double a = (t == CT_POW && params) ? params[k] : 0.0;
       if (t == CT_POW && !(a > 0.0 && a < 1.0)) return -21;
-      out.push_back({t, 3, 0, a});
+      out.push_back({t, 3, 0, a, {}});
       k++;
       continue;
     }
@@ -396,11 +408,11 @@ int ConeSet::collapse(const int32_t* types, const uint64_t* dims, uint64_t n, st
         }
         k++;
       }
-      out.push_back({CT_NONNEG, (int)tot, 0});
+      out.push_back({CT_NONNEG, (int)tot, 0, 0.0, {}});
     } else {
       if (t == CT_SOC && d < 2) return -21;
-      if (t == CT_PSD) { if (d > (uint64_t)CB_PSD_MAX_N) return -21; out.push_back({t, (int)(d * (d + 1) / 2), (int)d}); }
-      else out.push_back({t, (int)d, 0});
+      if (t == CT_PSD) { if (d > (uint64_t)CB_PSD_MAX_N) return -21; out.push_back({t, (int)(d * (d + 1) / 2), (int)d, 0.0, {}}); }
+      else out.push_back({t, (int)d, 0, 0.0, {}});
       k++;
     }
   }
@@ -423,6 +435,7 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
   stream = st;
   const int nc = (int)cs.size();
   off.assign(nc, 0); boff.assign(nc, 0); sparse_flag.assign(nc, 0); soc_list.clear(); ns_list.clear(); all_symmetric = true;
+  gp_list.clear(); pdim.assign(nc, 0); allows_primal_dual = true;
   m = 0; nHs = 0; degree = 0; p = 0;
   std::vector<int> type(nc), dim(nc);
   for (int k = 0; k < nc; k++) {
@@ -430,15 +443,17 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
     off[k] = m; boff[k] = nHs;
     const bool sp = cs[k].type == CT_SOC && cs[k].dim > SOC_NO_EXPANSION_MAX_SIZE;
     sparse_flag[k] = sp ? 1 : 0;
-    const bool diag = cs[k].type == CT_ZERO || cs[k].type == CT_NONNEG || sp;
+    const bool diag = cs[k].type == CT_ZERO || cs[k].type == CT_NONNEG || sp || cs[k].type == CT_GENPOW;
     nHs += diag ? cs[k].dim : cs[k].dim * (cs[k].dim + 1) / 2;
     m += cs[k].dim;
     const bool ns3c = cs[k].type == CT_EXP || cs[k].type == CT_POW;
-    degree += cs[k].type == CT_ZERO ? 0 : (cs[k].type == CT_NONNEG ? cs[k].dim : (cs[k].type == CT_PSD ? cs[k].psd_n : (ns3c ? 3 : 1)));
+    const bool gpc = cs[k].type == CT_GENPOW;
+    degree += cs[k].type == CT_ZERO ? 0 : (cs[k].type == CT_NONNEG ? cs[k].dim : (cs[k].type == CT_PSD ? cs[k].psd_n : (ns3c ? 3 : (gpc ? (int)cs[k].alphas.size() + 1 : 1))));
     if (ns3c) { ns_list.push_back(k); all_symmetric = false; }
+    if (gpc) { gp_list.push_back(k); all_symmetric = false; allows_primal_dual = false; pdim[k] = 3; p += 3; }
     if (cs[k].type == CT_SOC) soc_list.push_back(k);
     if (cs[k].type == CT_PSD) psd_list.push_back(k);
-    if (sp) p += 2;
+    if (sp) { p += 2; pdim[k] = 2; }
   }
   std::vector<signed char> tag(m);
   std::vector<int> row2blk(m, 0);
@@ -485,6 +500,7 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
     std::vector<double> al(nc, 0.0);
     for (int k = 0; k < nc; k++) al[k] = cs[k].param;
     if (ns_prepare(al)) return -20;
+    if (gp_prepare()) return -20;
   }
   const size_t np = (size_t)RED_BLOCKS + soc_list.size() + psd_list.size() + 8;
   CCK(cudaMalloc((void**)&d_pmin, np * 8)); CCK(cudaMalloc((void**)&d_psum, np * 8));
@@ -499,6 +515,7 @@ void ConeSet::release() {
   fr(ws.partials); fr(ws.counter); fr(row2blk_dev); fr(d_pmin); fr(d_psum);
   fr(dev.psd_list); fr(dev.psd_n); fr(dev.psd_moff); fr(dev.psd_R); fr(dev.psd_Rinv); fr(dev.psd_RRt);
   ns_release();
+  gp_release();
 }
 
 #define EW_GRID ((m + 255) / 256)

@@ -17,7 +17,7 @@
 
 namespace cb {
 
-enum { CT_ZERO = 0, CT_NONNEG = 1, CT_SOC = 2, CT_PSD = 3, CT_EXP = 4, CT_POW = 5 };
+enum { CT_ZERO = 0, CT_NONNEG = 1, CT_SOC = 2, CT_PSD = 3, CT_EXP = 4, CT_POW = 5, CT_GENPOW = 6 };
 enum { SCALING_PRIMAL_DUAL = 0, SCALING_DUAL = 1 };   // ScalingStrategy (cones/mod.rs)
 constexpr int SOC_NO_EXPANSION_MAX_SIZE = 4;  // socone.rs:46
 
@@ -51,12 +51,22 @@ struct ConeDev {
   double *ns_Hd = nullptr, *ns_Hs = nullptr;     // [6*nns] dual Hessian, scaling block (packed triu)
   double *ns_grad = nullptr, *ns_z = nullptr;    // [3*nns] dual gradient, z at the scaling point
   int* ns_jmax = nullptr;            // backtracking count of the composite step length
+  // generalised power cones (cones_nonsym.cu): per-row state in m-length arrays (q in a cone's first dim1 rows of
+  // gp_qr, r in the rest), per-cone scalars in [ngp] arrays
+  int ngp = 0;
+  const int* gp_list = nullptr;      // cone ids
+  const int* gp_dim1 = nullptr;      // [ngp]
+  const double* gp_alpha = nullptr;  // [m]
+  const double* gp_psi = nullptr;    // [ngp]
+  double *gp_grad = nullptr, *gp_p = nullptr, *gp_qr = nullptr, *gp_d1 = nullptr, *gp_zc = nullptr;   // [m]
+  double *gp_d2 = nullptr, *gp_mu = nullptr;                                                            // [ngp]
 };
 
 constexpr int CB_PSD_MAX_N = 32;
 
 // dim = number of rows the cone occupies (numel); psd_n = matrix dimension of a PSD cone
-struct ConeSpec { int type; int dim; int psd_n = 0; double param = 0.0; };   // param: exponent of a power cone
+// param: exponent of a power cone; alphas: exponents of a generalised power cone (dim = alphas.size() + dim2)
+struct ConeSpec { int type; int dim; int psd_n = 0; double param = 0.0; std::vector<double> alphas; };
 
 class ConeSet {
  public:
@@ -72,7 +82,8 @@ class ConeSet {
 
   // collapse like SupportedConeT::new_collapsed (supportedcone.rs:105-161)
   static int collapse(const int32_t* types, const uint64_t* dims, uint64_t n, std::vector<ConeSpec>& out,
-                      const double* params = nullptr);
+                      const double* params = nullptr, const uint64_t* gp_dim2 = nullptr,
+                      const double* gp_alpha = nullptr);
   int init(const std::vector<ConeSpec>& cs, cudaStream_t st);
   void release();
 
@@ -93,6 +104,12 @@ class ConeSet {
   // nonsymmetric pieces (cones_nonsym.cu)
   std::vector<int> ns_list;
   bool all_symmetric = true;
+  bool allows_primal_dual = true;        // false as soon as a generalised power cone is present (genpowcone.rs:108-110)
+  std::vector<int> gp_list, pdim;        // pdim[k]: extra KKT columns of cone k (2 sparse SOC, 3 GenPow, else 0)
+  int gp_prepare();
+  void gp_release();
+  // the three KKT columns + diagonal entries of every generalised power cone (datamaps.rs:314-337)
+  void gp_kkt_fill(double* vals, const int* map_qr, const int* map_p, const int* map_D);
   double ns_amin = 1e-4, ns_step = 0.8;   // min_terminate_step_length, linesearch_backtrack_step
   int ns_prepare(const std::vector<double>& alpha_per_cone);
   void ns_release();
@@ -103,7 +120,7 @@ class ConeSet {
   void ns_copy_rows(double* out, const double* in);
   void ns_combined_shift(double* shift, const double* step_z, const double* step_s, double sigmamu);
   void ns_step_length(const double* dz, const double* ds, const double* z, const double* s, double* alpha_slot);
-  // out[0] = sum of the cones' barrier functions at (z + alpha dz, s + alpha ds); partial = 4 doubles of scratch
+  // out[0] = sum of the cones' barrier functions at (z + alpha dz, s + alpha ds); partial = 5 doubles of scratch
   void compute_barrier(const double* z, const double* s, const double* dz, const double* ds, double alpha,
                        double* partial, double* out);
 

@@ -497,4 +497,201 @@ CB_HD double body_barrier(const View& c, int k, const double* z, const double* s
 }
 
 }  // namespace ns3
+
+// ------------------------------------------------------------------------------------------------------------
+// Generalised power cone { (u, w) : prod u_i^alpha_i >= ||w|| }, u in R^dim1, w in R^dim2
+// (/root/reference/src/solver/core/cones/genpowcone.rs).  Hs = mu (D + p p' - q q' - r r') is never formed: its
+// diagonal D goes into the KKT block, p, q, r into three extra KKT columns (datamaps.rs:226-337).  One thread per
+// cone walks the cone's rows; all per-row state lives in m-length arrays indexed by row (q in the cone's first dim1
+// rows of `qr`, r in the remaining dim2 rows), so no per-cone offsets beyond off[] are needed.
+namespace gp {
+
+struct View {
+  int n;                 // number of generalised power cones
+  const int* list;       // [n] cone ids
+  const int* off;        // [ncones] first row
+  const int* dim;        // [ncones] rows
+  const int* boff;       // [ncones] first entry of the (diagonal) Hs block
+  const int* dim1;       // [n]
+  const double* alpha;   // [m] exponents, at the cone's first dim1 rows
+  const double* psi;     // [n] 1 / sum(alpha^2)
+  double *grad, *p, *qr, *d1, *zc;   // [m]
+  double *d2, *mu;       // [n]
+};
+using ns3::lsafe;
+using ns3::EPS;
+using ns3::SQRT_EPS;
+using ns3::J_ZERO;
+
+// 2-norm with the scaling of vecmath.rs:206-226
+CB_HD double norm2(const double* x, int n) {
+  double mx = 0.0;
+  for (int i = 0; i < n; i++) mx = fmax(mx, fabs(x[i]));
+  if (!(mx > 0.0)) return 0.0;
+  double ss = 0.0;
+  for (int i = 0; i < n; i++) { const double t = x[i] / mx; ss += t * t; }
+  return mx * sqrt(ss);
+}
+
+CB_HD void body_unit_init(const View& c, int k, double* z, double* s) {         // genpowcone.rs:132-141
+  const int id = c.list[k], o = c.off[id], n = c.dim[id], d1 = c.dim1[k];
+  for (int i = 0; i < n; i++) { const double v = i < d1 ? sqrt(1.0 + c.alpha[o + i]) : 0.0; s[o + i] = v; z[o + i] = v; }
+}
+
+// Cone::update_scaling = update_dual_grad_H + mu + copy of z (genpowcone.rs:149-163, 360-399); false where the
+// reference asserts zeta > 0
+CB_HD bool body_update_scaling(const View& c, int k, const double* z_, double mu) {
+  const int id = c.list[k], o = c.off[id], n = c.dim[id], d1 = c.dim1[k], d2n = n - d1;
+  const double* z = z_ + o;
+  const double* al = c.alpha + o;
+  double phi = 1.0;
+  for (int i = 0; i < d1; i++) phi *= pow(z[i] / al[i], 2.0 * al[i]);
+  double norm2w = 0.0;
+  for (int i = 0; i < d2n; i++) norm2w += z[d1 + i] * z[d1 + i];
+  const double zeta = phi - norm2w;
+  if (!(zeta > 0.0)) return false;
+  const double p0 = sqrt(phi * (phi + norm2w) / 2.0);
+  const double p1 = -2.0 * phi / p0;
+  const double q0 = sqrt(zeta * phi / 2.0);
+  const double r1 = 2.0 * sqrt(zeta / (phi + norm2w));
+  for (int i = 0; i < d1; i++) {
+    const double tau = 2.0 * al[i] / z[i];
+    c.grad[o + i] = -tau * phi / zeta - (1.0 - al[i]) / z[i];
+    c.d1[o + i] = tau * phi / (zeta * z[i]) + (1.0 - al[i]) / (z[i] * z[i]);
+    c.p[o + i] = (p0 / zeta) * tau;
+    c.qr[o + i] = tau * (q0 / zeta);
+  }
+  for (int i = d1; i < n; i++) {
+    c.grad[o + i] = (2.0 / zeta) * z[i];
+    c.p[o + i] = (p1 / zeta) * z[i];
+    c.qr[o + i] = (r1 / zeta) * z[i];
+  }
+  c.d2[k] = 2.0 / zeta;
+  c.mu[k] = mu;
+  for (int i = 0; i < n; i++) c.zc[o + i] = z[i];
+  return true;
+}
+CB_HD void body_get_Hs(const View& c, int k, double* Hs, double sign) {          // genpowcone.rs:169-175
+  const int id = c.list[k], o = c.off[id], b = c.boff[id], n = c.dim[id], d1 = c.dim1[k];
+  const double mu = c.mu[k], d2 = c.d2[k];
+  for (int i = 0; i < n; i++) Hs[b + i] = sign * (mu * (i < d1 ? c.d1[o + i] : d2));
+}
+CB_HD void body_mul_Hs(const View& c, int k, double* y_, const double* x_) {     // genpowcone.rs:177-202
+  const int id = c.list[k], o = c.off[id], n = c.dim[id], d1 = c.dim1[k];
+  const double* x = x_ + o;
+  double cp = 0.0, cq = 0.0, cr = 0.0;
+  for (int i = 0; i < n; i++) cp += c.p[o + i] * x[i];
+  for (int i = 0; i < d1; i++) cq += c.qr[o + i] * x[i];
+  for (int i = d1; i < n; i++) cr += c.qr[o + i] * x[i];
+  const double mu = c.mu[k], d2 = c.d2[k];
+  for (int i = 0; i < n; i++) {
+    const double base = i < d1 ? c.d1[o + i] * x[i] - cq * c.qr[o + i] : d2 * x[i] - cr * c.qr[o + i];
+    y_[o + i] = (cp * c.p[o + i] + base) * mu;
+  }
+}
+CB_HD void body_copy_rows(const View& c, int k, double* out, const double* in) {
+  const int id = c.list[k], o = c.off[id], n = c.dim[id];
+  for (int i = 0; i < n; i++) out[o + i] = in[o + i];
+}
+CB_HD void body_combined_shift(const View& c, int k, double* shift, double sigmamu) {   // genpowcone.rs:208-213
+  const int id = c.list[k], o = c.off[id], n = c.dim[id];
+  for (int i = 0; i < n; i++) shift[o + i] = c.grad[o + i] * sigmamu;
+}
+// the three KKT columns and their diagonal entries (datamaps.rs:314-337): -sqrt(mu) q, -sqrt(mu) r, -sqrt(mu) p,
+// diag (-1, -1, +1)
+CB_HD void body_kkt_fill(const View& c, int k, double* vals, const int* map_qr, const int* map_p, const int* map_D) {
+  const int id = c.list[k], o = c.off[id], n = c.dim[id];
+  const double sq = -sqrt(c.mu[k]);
+  for (int i = 0; i < n; i++) { vals[map_qr[o + i]] = c.qr[o + i] * sq; vals[map_p[o + i]] = c.p[o + i] * sq; }
+  vals[map_D[3 * k]] = -1.0; vals[map_D[3 * k + 1]] = -1.0; vals[map_D[3 * k + 2]] = 1.0;
+}
+// q + a*dq inside the primal / dual cone (genpowcone.rs:267-308)
+CB_HD bool feasible(const double* al, const double* q, const double* dq, double a, int d1, int n, bool dual) {
+  double res = 0.0;
+  for (int i = 0; i < d1; i++) {
+    const double v = q[i] + a * dq[i];
+    if (!(v > 0.0)) return false;
+    res += 2.0 * al[i] * lsafe(dual ? v / al[i] : v);
+  }
+  double ss = 0.0;
+  for (int i = d1; i < n; i++) { const double v = q[i] + a * dq[i]; ss += v * v; }
+  return exp(res) - ss > 0.0;
+}
+CB_HD int backtrack_count(const double* al, const double* q, const double* dq, int d1, int n, bool dual, double a0,
+                          double a_min, double step) {
+  double a = a0;
+  for (int j = 0; j < 4096; j++) {
+    if (feasible(al, q, dq, a, d1, n, dual)) return j;
+    a *= step;
+    if (a < a_min) return J_ZERO;
+  }
+  return J_ZERO;
+}
+CB_HD int body_step_count(const View& c, int k, const double* dz, const double* ds, const double* z, const double* s,
+                          double alpha_sym, double a_min, double step) {
+  const int id = c.list[k], o = c.off[id], n = c.dim[id], d1 = c.dim1[k];
+  const double a0 = fmin(alpha_sym, 1.0 - SQRT_EPS);
+  const int jz = backtrack_count(c.alpha + o, z + o, dz + o, d1, n, true, a0, a_min, step);
+  const int js = backtrack_count(c.alpha + o, s + o, ds + o, d1, n, false, a0, a_min, step);
+  return jz > js ? jz : js;
+}
+// dual barrier at q + a*dq (genpowcone.rs:333-354)
+CB_HD double barrier_dual_at(const double* al, const double* q, const double* dq, double a, int d1, int n) {
+  double res = 0.0, extra = 0.0, ss = 0.0;
+  for (int i = 0; i < d1; i++) { const double v = q[i] + a * dq[i]; res += 2.0 * al[i] * lsafe(v / al[i]); extra += lsafe(v) * (1.0 - al[i]); }
+  for (int i = d1; i < n; i++) { const double v = q[i] + a * dq[i]; ss += v * v; }
+  return -lsafe(exp(res) - ss) - extra;
+}
+// primal barrier at s + a*ds = -f*(-g(s)) - degree (genpowcone.rs:310-331, 404-485).  The w-part of the primal
+// gradient uses the cone's stored Hessian vector r (genpowcone.rs:426), exactly like the reference.
+CB_HD double barrier_primal_at(const View& c, int k, const double* s, const double* ds, double a) {
+  const int id = c.list[k], o = c.off[id], n = c.dim[id], d1 = c.dim1[k];
+  const double* al = c.alpha + o;
+  double phi = 1.0;
+  for (int i = 0; i < d1; i++) phi *= pow(s[o + i] + a * ds[o + i], 2.0 * al[i]);
+  double mx = 0.0;
+  for (int i = d1; i < n; i++) mx = fmax(mx, fabs(s[o + i] + a * ds[o + i]));
+  double norm_r = 0.0;
+  if (mx > 0.0) {
+    double ss = 0.0;
+    for (int i = d1; i < n; i++) { const double t = (s[o + i] + a * ds[o + i]) / mx; ss += t * t; }
+    norm_r = mx * sqrt(ss);
+  }
+  double g1 = 0.0;
+  const bool far = norm_r > EPS;
+  if (far) {   // one-sided Newton iteration (genpowcone.rs:451-485, nonsymmetric_common.rs:191-219)
+    const double psi = c.psi[k];
+    double x = -1.0 / norm_r + (psi * norm_r + sqrt((phi / norm_r / norm_r + psi * psi - 1.0) * phi)) / (phi - norm_r * norm_r);
+    for (int it = 0; it < 100; it++) {
+      double f1 = -(2.0 * x + 2.0 / norm_r) / (x * x + 2.0 * x / norm_r);
+      double f0 = -lsafe(2.0 * x / norm_r + x * x);
+      for (int i = 0; i < d1; i++) {
+        f1 += 2.0 * al[i] * norm_r / (norm_r * x + (1.0 + al[i]) / al[i]);
+        f0 += 2.0 * al[i] * (lsafe(x * norm_r + (1.0 + al[i]) / al[i]) - lsafe(s[o + i] + a * ds[o + i]));
+      }
+      const double dx = -f0 / f1;
+      if (dx < EPS || fabs(dx / x) < SQRT_EPS || fabs(f1) < EPS) break;
+      x += dx;
+    }
+    g1 = x;
+  }
+  // -f*(-g): dual barrier of the negated gradient, streamed
+  double res = 0.0, extra = 0.0, ss = 0.0;
+  for (int i = 0; i < d1; i++) {
+    const double si = s[o + i] + a * ds[o + i];
+    const double gi = far ? -(1.0 + al[i] + al[i] * g1 * norm_r) / si : -(1.0 + al[i]) / si;
+    res += 2.0 * al[i] * lsafe(-gi / al[i]);
+    extra += lsafe(-gi) * (1.0 - al[i]);
+  }
+  if (far) for (int i = d1; i < n; i++) { const double gi = (g1 / norm_r) * c.qr[o + i]; ss += gi * gi; }
+  const double bd = -lsafe(exp(res) - ss) - extra;
+  return -bd - (double)(d1 + 1);
+}
+CB_HD double body_barrier(const View& c, int k, const double* z, const double* s, const double* dz, const double* ds,
+                          double a) {                                            // genpowcone.rs:249-263
+  const int id = c.list[k], o = c.off[id], n = c.dim[id], d1 = c.dim1[k];
+  return barrier_primal_at(c, k, s, ds, a) + barrier_dual_at(c.alpha + o, z + o, dz + o, a, d1, n);
+}
+
+}  // namespace gp
 }  // namespace cb

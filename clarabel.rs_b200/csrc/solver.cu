@@ -112,7 +112,7 @@ static void dfree(const void* p) { if (p) cudaFree((void*)p); }
 // scalar slots shared between device reductions and the host
 enum Slot { S_NORMB = 0, S_NORME, S_MAXDIAG, S_QX, S_BZ, S_SZ, S_XPX, S_ALPHA, S_MARG0, S_MARG1,
             S_D0, S_D1, S_D2, S_D3, S_D4, S_D5, S_D6, S_D7, S_N0, S_N1, S_N2, S_N3, S_N4, S_N5, S_N6, S_N7,
-            S_NORMB2, S_NORME2, S_BARR, S_BP0, S_BP1, S_BP2, S_BP3, S_SZSH, S_COUNT = 40 };
+            S_NORMB2, S_NORME2, S_BARR, S_BP0, S_BP1, S_BP2, S_BP3, S_BP4, S_SZSH, S_COUNT = 40 };
 
 struct Scalars {
   double* d = nullptr;  // device [S_COUNT]
@@ -192,6 +192,8 @@ class KKTDevice {
   std::vector<double> Kx;
   std::vector<int8_t> dsigns;
   std::vector<int> map_P, map_A, map_Hs, map_u, map_v, map_D, map_diag;
+  std::vector<int> map_gqr, map_gp, map_gD;   // generalised power cones: q|r rows, p rows (by row), 3 diagonals per cone
+  int *d_map_gqr = nullptr, *d_map_gp = nullptr, *d_map_gD = nullptr;
   // device
   int *d_map_P = nullptr, *d_map_A = nullptr, *d_map_Hs = nullptr, *d_map_u = nullptr, *d_map_v = nullptr,
       *d_map_D = nullptr, *d_map_diag = nullptr;
@@ -238,9 +240,13 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
   for (int k = 0; k < nc; k++) {
     const ConeSpec& c = cones->cones[k];
     const int row = n + cones->off[k];
-    const bool diag = c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k];
+    const bool diag = c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k] || c.type == CT_GENPOW;
     for (int i = 0; i < c.dim; i++) cnt[row + i] += diag ? 1 : i + 1;
     if (cones->sparse_flag[k]) { cnt[pcol] += c.dim + 1; cnt[pcol + 1] += c.dim + 1; pcol += 2; }
+    if (c.type == CT_GENPOW) {   // q, r, p columns + their diagonal entries (datamaps.rs:264-287)
+      const int d1 = (int)c.alphas.size();
+      cnt[pcol] += d1 + 1; cnt[pcol + 1] += c.dim - d1 + 1; cnt[pcol + 2] += c.dim + 1; pcol += 3;
+    }
   }
   Kp.assign(N + 1, 0);
   for (int j = 0; j < N; j++) Kp[j + 1] = Kp[j] + cnt[j];
@@ -255,6 +261,8 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
   map_u.assign(m ? m : 1, 0);
   map_v.assign(m ? m : 1, 0);
   map_D.assign(2 * (nc ? nc : 1), 0);
+  map_gqr.assign(m ? m : 1, 0); map_gp.assign(m ? m : 1, 0); map_gD.assign(3 * (cones->gp_list.size() ? cones->gp_list.size() : 1), 0);
+  int gpk = 0;
   for (int i = 0; i < n; i++) {
     for (int64_t q = P.colptr[i]; q < P.colptr[i + 1]; q++) {
       int64_t d = nxt[i]++;
@@ -273,7 +281,7 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
     const ConeSpec& c = cones->cones[k];
     const int row = n + cones->off[k];
     int* blk = map_Hs.data() + cones->boff[k];
-    const bool diag = c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k];
+    const bool diag = c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k] || c.type == CT_GENPOW;
     if (diag) {
       for (int i = 0; i < c.dim; i++) { int64_t d = nxt[row + i]++; Ki[d] = row + i; blk[i] = (int)d; }
     } else {
@@ -288,13 +296,25 @@ int KKTDevice::assemble(const HostCsc& P, const HostCsc& A) {
       for (int i = 0; i < 2; i++) { int64_t d = nxt[pcol + i]++; Ki[d] = pcol + i; map_D[2 * k + i] = (int)d; }
       pcol += 2;
     }
+    if (c.type == CT_GENPOW) {   // datamaps.rs:289-312: q rows [0, dim1), r rows [dim1, dim), p all rows
+      const int o = cones->off[k], d1 = (int)c.alphas.size();
+      for (int i = 0; i < d1; i++) { int64_t d = nxt[pcol]++; Ki[d] = row + i; map_gqr[o + i] = (int)d; }
+      for (int i = d1; i < c.dim; i++) { int64_t d = nxt[pcol + 1]++; Ki[d] = row + i; map_gqr[o + i] = (int)d; }
+      for (int i = 0; i < c.dim; i++) { int64_t d = nxt[pcol + 2]++; Ki[d] = row + i; map_gp[o + i] = (int)d; }
+      for (int i = 0; i < 3; i++) { int64_t d = nxt[pcol + i]++; Ki[d] = pcol + i; map_gD[3 * gpk + i] = (int)d; }
+      gpk++;
+      pcol += 3;
+    }
   }
   map_diag.resize(N);
   for (int j = 0; j < N; j++) map_diag[j] = (int)(Kp[j + 1] - 1);
   dsigns.assign(N, 1);
   for (int i = n; i < n + m; i++) dsigns[i] = -1;
   int pp = n + m;
-  for (int k = 0; k < nc; k++) if (cones->sparse_flag[k]) { dsigns[pp] = -1; dsigns[pp + 1] = 1; pp += 2; }
+  for (int k = 0; k < nc; k++) {
+    if (cones->sparse_flag[k]) { dsigns[pp] = -1; dsigns[pp + 1] = 1; pp += 2; }
+    else if (cones->cones[k].type == CT_GENPOW) { dsigns[pp] = -1; dsigns[pp + 1] = -1; dsigns[pp + 2] = 1; pp += 3; }   // datamaps.rs:252-254
+  }
   return 0;
 }
 
@@ -317,7 +337,7 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
     int ngroups = 0;
     for (size_t k = 0; k < cones->cones.size(); k++) {
       const ConeSpec& c = cones->cones[k];
-      if (c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k] || c.dim <= 8) continue;
+      if (c.type == CT_ZERO || c.type == CT_NONNEG || cones->sparse_flag[k] || c.type == CT_GENPOW || c.dim <= 8) continue;
       for (int i = 0; i < c.dim; i++) group[n + cones->off[k] + i] = ngroups;
       ngroups++;
     }
@@ -359,7 +379,8 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
   }
   std::vector<signed char> ds8(dsigns.begin(), dsigns.end());
   if (upv(&d_map_P, map_P) || upv(&d_map_A, map_A) || upv(&d_map_Hs, map_Hs) || upv(&d_map_u, map_u) ||
-      upv(&d_map_v, map_v) || upv(&d_map_D, map_D) || upv(&d_map_diag, map_diag) || upv(&d_dsigns, ds8))
+      upv(&d_map_v, map_v) || upv(&d_map_D, map_D) || upv(&d_map_diag, map_diag) || upv(&d_dsigns, ds8) ||
+      upv(&d_map_gqr, map_gqr) || upv(&d_map_gp, map_gp) || upv(&d_map_gD, map_gD))
     return CLDL_E_CUDA;
   SCK(cudaMalloc((void**)&d_Hs, (size_t)(cones->nHs ? cones->nHs : 1) * 8));
   SCK(cudaMalloc((void**)&d_x, (size_t)N * 8)); SCK(cudaMalloc((void**)&d_b, (size_t)N * 8));
@@ -379,7 +400,7 @@ int KKTDevice::set_PA_values(const HostCsc& P, const HostCsc& A) {
 }
 
 void KKTDevice::release() {
-  dfree(d_map_P); dfree(d_map_A); dfree(d_map_Hs); dfree(d_map_u); dfree(d_map_v); dfree(d_map_D);
+  dfree(d_map_P); dfree(d_map_A); dfree(d_map_Hs); dfree(d_map_u); dfree(d_map_v); dfree(d_map_D); dfree(d_map_gqr); dfree(d_map_gp); dfree(d_map_gD);
   dfree(d_map_diag); dfree(d_dsigns); dfree(d_srow); dfree(d_scol); dfree(d_sidx); dfree(d_sval);
   dfree(d_Hs); dfree(d_x); dfree(d_b); dfree(d_w1); dfree(d_w2);
   dfree(d_x2); dfree(d_b2); dfree(d_w1b); dfree(d_w2b);
@@ -395,9 +416,11 @@ int KKTDevice::update() {
   // -W'W blocks straight into the KKT value array (get_Hs + negate + scatter)
   cones->get_Hs(d_Hs, true);
   update_vals(d_map_Hs, d_Hs, cones->nHs);
-  g_launches += (cones->p > 0) + (nnzS > 0) + (set.static_regularization_enable ? 3 : 0);
-  if (cones->p > 0)
+  const bool soc_exp = cones->p > 3 * (int)cones->gp_list.size();
+  g_launches += (soc_exp ? 1 : 0) + (nnzS > 0) + (set.static_regularization_enable ? 3 : 0);
+  if (soc_exp)
     k_sparse_soc_fill<<<cones->dev.nsoc, 128, 0, st>>>(cones->dev, vals, d_map_u, d_map_v, d_map_D);
+  cones->gp_kkt_fill(vals, d_map_gqr, d_map_gp, d_map_gD);
   // refresh the symmetric-CSR values used by iterative refinement (un-regularised K)
   if (nnzS) k_gather<<<(unsigned)((nnzS + 255) / 256), 256, 0, st>>>(d_sval, vals, d_sidx, (int)nnzS);
   // static regularisation (directldlkktsolver.rs:217-264): keep the true diagonal in w1
@@ -600,7 +623,8 @@ class IPM {
   int init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const double* Pxv, const double* q_,
            const uint64_t* Ap, const uint64_t* Ai, const double* Axv, const double* b_, uint64_t ncones,
            const int32_t* ctype, const uint64_t* cdim, const cipm_settings& s, const cldl_opts& lo,
-           const int* perm, const double* cparam = nullptr);
+           const int* perm, const double* cparam = nullptr, const uint64_t* gp_dim2 = nullptr,
+           const double* gp_alpha = nullptr);
   void release();
   void equilibrate();
   int upload_problem();
@@ -682,7 +706,7 @@ void IPM::equilibrate() {
   std::fill(ew.begin(), ew.end(), 1.0);
   for (size_t k = 0; k < cones.cones.size(); k++)
     if (cones.cones[k].type == CT_SOC || cones.cones[k].type == CT_PSD || cones.cones[k].type == CT_EXP ||
-        cones.cones[k].type == CT_POW) {  // scalar scaling inside these cones (socone.rs:97-101, psdtrianglecone.rs:98-101, expcone.rs:71-74, powcone.rs:63-66)
+        cones.cones[k].type == CT_POW || cones.cones[k].type == CT_GENPOW) {  // scalar scaling inside these cones (socone.rs:97-101, psdtrianglecone.rs:98-101, expcone.rs:71-74, powcone.rs:63-66)
       const int o = cones.off[k], dm = cones.cones[k].dim;
       double mean = 0.0;
       for (int i = 0; i < dm; i++) mean += e[o + i];
@@ -790,7 +814,7 @@ int IPM::update_data(const double* Pnz, const double* qv, const double* Anz, con
 int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const double* Pxv, const double* q_,
               const uint64_t* Ap, const uint64_t* Ai, const double* Axv, const double* b_, uint64_t ncones,
               const int32_t* ctype, const uint64_t* cdim, const cipm_settings& s_, const cldl_opts& lo,
-              const int* perm, const double* cparam) {
+              const int* perm, const double* cparam, const uint64_t* gp_dim2, const double* gp_alpha) {
   n = n_; m = m_; set = s_;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -805,7 +829,7 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   q.assign(q_, q_ + n); b.assign(b_, b_ + m);
   for (auto& v : b) v = std::min(v, 1e20);  // problemdata.rs:130-131
   std::vector<ConeSpec> cs;
-  int rc = ConeSet::collapse(ctype, cdim, ncones, cs, cparam);
+  int rc = ConeSet::collapse(ctype, cdim, ncones, cs, cparam, gp_dim2, gp_alpha);
   if (rc) return rc;
   cones.ns_amin = set.min_terminate_step_length; cones.ns_step = set.linesearch_backtrack_step;
   int tot = 0;
@@ -1111,7 +1135,7 @@ int IPM::variables_barrier(double a, double* out) {
     k_sum<<<red_grid(m), RED_THREADS, 0, st>>>(m, [=] __device__(int i) { return (ss[i] + a * ds[i]) * (zz[i] + a * dz[i]); },
                                               V.ws, sc.d + S_SZSH);
   } else SCK(cudaMemsetAsync(sc.d + S_SZSH, 0, 8, st));
-  cones.compute_barrier(z, s, lz, ls, a, sc.d + S_BP0, sc.d + S_BARR);
+  cones.compute_barrier(z, s, lz, ls, a, sc.d + S_BP0, sc.d + S_BARR);   // S_BP0..S_BP4: scratch
   int rc = sc.fetch();
   if (rc) return rc;
   auto lsafe = [](double v) { return v <= 0.0 ? -INFINITY : std::log(v); };
@@ -1171,8 +1195,8 @@ int IPM::solve() {
     V.zero(x, n);
   }
   tau = 1.0; kap = 1.0;
-  // every cone built here allows primal-dual scaling (only GenPow does not): core/solver.rs:277-280
-  int scaling = SCALING_PRIMAL_DUAL;
+  // core/solver.rs:277-280: dual-only scaling from the start when a cone (GenPow) has no primal-dual one
+  int scaling = cones.allows_primal_dual ? SCALING_PRIMAL_DUAL : SCALING_DUAL;
   const bool nonsym = !cones.all_symmetric;
 
   n_iter_ev = 0;
@@ -1202,7 +1226,7 @@ int IPM::solve() {
     SCK(cudaMemsetAsync(cones.dev.fail, 0, sizeof(int), st));
     cones.update_scaling(s, z, mu, scaling);
     int failflag = 0;
-    if (cones.dev.nsoc || cones.dev.npsd) {  // only SOC / PSD scalings can fail
+    if (cones.dev.nsoc || cones.dev.npsd || cones.dev.ngp) {  // only SOC / PSD / GenPow scalings can fail
       SCK(cudaMemcpyAsync(&failflag, cones.dev.fail, sizeof(int), cudaMemcpyDeviceToHost, st));
       SCK(cudaStreamSynchronize(st));
     }
@@ -1305,8 +1329,8 @@ int cipm_create(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, 
                 const double* A_nzval, const double* b, uint64_t ncones, const int32_t* cone_types,
                 const uint64_t* cone_dims, const cipm_settings* settings, const cldl_opts* ldl_opts,
                 const uint64_t* kkt_perm_or_null) {
-  return cipm_create_ex(out, n, m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones, cone_types,
-                        cone_dims, nullptr, settings, ldl_opts, kkt_perm_or_null);
+  return cipm_create_gp(out, n, m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones, cone_types,
+                        cone_dims, nullptr, nullptr, nullptr, settings, ldl_opts, kkt_perm_or_null);
 }
 
 int cipm_create_ex(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, const uint64_t* P_rowval,
@@ -1314,6 +1338,16 @@ int cipm_create_ex(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
                    const double* A_nzval, const double* b, uint64_t ncones, const int32_t* cone_types,
                    const uint64_t* cone_dims, const double* cone_params, const cipm_settings* settings,
                    const cldl_opts* ldl_opts, const uint64_t* kkt_perm_or_null) {
+  return cipm_create_gp(out, n, m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones, cone_types,
+                        cone_dims, cone_params, nullptr, nullptr, settings, ldl_opts, kkt_perm_or_null);
+}
+
+int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colptr, const uint64_t* P_rowval,
+                   const double* P_nzval, const double* q, const uint64_t* A_colptr, const uint64_t* A_rowval,
+                   const double* A_nzval, const double* b, uint64_t ncones, const int32_t* cone_types,
+                   const uint64_t* cone_dims, const double* cone_params, const uint64_t* genpow_dim2,
+                   const double* genpow_alpha, const cipm_settings* settings, const cldl_opts* ldl_opts,
+                   const uint64_t* kkt_perm_or_null) {
   if (!out) return CLDL_E_ARG;
   *out = nullptr;
   if (n == 0 || n > 0x7fffffffu || m > 0x7fffffffu) return CLDL_E_DIM;
@@ -1327,20 +1361,21 @@ int cipm_create_ex(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
   // the permutation length is only known after assembly; validate there
   if (kkt_perm_or_null) {
     // upper bound on N: n + m + 2*ncones
-    uint64_t cap = n + m + 2 * ncones;
+    uint64_t cap = n + m + 3 * ncones;
     perm.reserve(cap);
     for (uint64_t k = 0; k < cap; k++) perm.push_back((int)kkt_perm_or_null[k]);
   }
   // dimension of the KKT system must be known to slice the permutation: do a dry collapse
   if (kkt_perm_or_null) {
     std::vector<cb::ConeSpec> cs;
-    if (cb::ConeSet::collapse(cone_types, cone_dims, ncones, cs, cone_params)) { delete h; return CLDL_E_ARG; }
+    if (cb::ConeSet::collapse(cone_types, cone_dims, ncones, cs, cone_params, genpow_dim2, genpow_alpha)) { delete h; return CLDL_E_ARG; }
     uint64_t p = 0;
-    for (auto& c : cs) if (c.type == cb::CT_SOC && c.dim > cb::SOC_NO_EXPANSION_MAX_SIZE) p += 2;
+    for (auto& c : cs) { if (c.type == cb::CT_SOC && c.dim > cb::SOC_NO_EXPANSION_MAX_SIZE) p += 2; if (c.type == cb::CT_GENPOW) p += 3; }
     perm.resize(n + m + p);
   }
   int rc = h->ipm.init((int)n, (int)m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones,
-                       cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr, cone_params);
+                       cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr, cone_params, genpow_dim2,
+                       genpow_alpha);
   if (rc) { h->ipm.release(); delete h; return rc; }
   *out = h;
   return CLDL_OK;

@@ -143,9 +143,10 @@ double cldl_time_solve_ms(cldl_t *h, int reps);
 typedef struct cipm_handle cipm_t;
 
 /* SupportedConeT tags (supportedcone.rs:17-52).  ExponentialConeT() and PowerConeT(alpha) occupy 3 rows each;
- * the exponent of a power cone travels in cone_params (cipm_create_ex).  GenPowerConeT is not built. */
+ * the exponent of a power cone travels in cone_params (cipm_create_ex); GenPowerConeT(alpha, dim2) has
+ * cone_dims = len(alpha) and its dim2 / exponents in the two extra arrays of cipm_create_gp. */
 enum { CIPM_CONE_ZERO = 0, CIPM_CONE_NONNEG = 1, CIPM_CONE_SOC = 2, CIPM_CONE_PSD = 3, CIPM_CONE_EXP = 4,
-       CIPM_CONE_POW = 5 };
+       CIPM_CONE_POW = 5, CIPM_CONE_GENPOW = 6 };
 /* ScalingStrategy (src/solver/core/cones/mod.rs) */
 enum { CIPM_SCALING_PRIMAL_DUAL = 0, CIPM_SCALING_DUAL = 1 };
 
@@ -211,6 +212,15 @@ int cipm_create_ex(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colpt
                    const double *A_nzval, const double *b, uint64_t ncones, const int32_t *cone_types,
                    const uint64_t *cone_dims, const double *cone_params, const cipm_settings *settings,
                    const cldl_opts *ldl_opts, const uint64_t *kkt_perm_or_null);
+/* Same, with generalised power cones (GenPowerConeT(alpha, dim2), supportedcone.rs:44): for a CIPM_CONE_GENPOW entry
+ * cone_dims[k] = len(alpha), genpow_dim2[k] = dim2 (ignored for other cones) and genpow_alpha holds the exponents of
+ * all such cones concatenated in cone order (each set positive, summing to one). */
+int cipm_create_gp(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colptr, const uint64_t *P_rowval,
+                   const double *P_nzval, const double *q, const uint64_t *A_colptr, const uint64_t *A_rowval,
+                   const double *A_nzval, const double *b, uint64_t ncones, const int32_t *cone_types,
+                   const uint64_t *cone_dims, const double *cone_params, const uint64_t *genpow_dim2,
+                   const double *genpow_alpha, const cipm_settings *settings, const cldl_opts *ldl_opts,
+                   const uint64_t *kkt_perm_or_null);
 void cipm_destroy(cipm_t *h);
 int cipm_solve(cipm_t *h);                                   /* IPSolver::solve */
 void cipm_get_info(const cipm_t *h, cipm_info *out);

@@ -298,6 +298,9 @@ def _ipm_lib():
         L.oipm_map.restype = i64p
         L.oipm_sparse_map.argtypes = [vp, C.c_int64, C.c_int, i64p]
         L.oipm_sparse_map.restype = i64p
+        L.oipm_genpow_map.argtypes = [vp, C.c_int64, C.c_int, i64p]
+        L.oipm_genpow_map.restype = i64p
+        L.oipm_test_kkt_update.argtypes = [vp]
         L.oipm_equil.argtypes = [vp, C.c_int]
         L.oipm_equil.restype = f64p
         L.oipm_scaled_data.argtypes = [vp, C.c_int]
@@ -396,6 +399,15 @@ class IPM:
         ln = C.c_int64()
         p = self._L.oipm_sparse_map(self._h, k, {"u": 0, "v": 1, "D": 2}[which], C.byref(ln))
         return np.ctypeslib.as_array(p, shape=(max(ln.value, 1),))[:ln.value].copy()
+
+    def genpow_map(self, k, which):
+        ln = C.c_int64()
+        p = self._L.oipm_genpow_map(self._h, k, {"q": 0, "r": 1, "p": 2, "D": 3}[which], C.byref(ln))
+        return np.ctypeslib.as_array(p, shape=(max(ln.value, 1),))[:ln.value].copy()
+
+    def kkt_update(self):
+        """KKTSolver::update with the current cone scalings (set_perm first)"""
+        return bool(self._L.oipm_test_kkt_update(self._h))
 
     def equilibration(self):
         L, h = self._L, self._h

@@ -1392,6 +1392,25 @@ const idx *oipm_sparse_map(const oipm_t *S, idx ksparse, int which, idx *len)
     }
     *len = 0; return NULL;
 }
+/* maps of the k-th generalised power cone: which 0 q, 1 r, 2 p, 3 D (datamaps.rs:226-243) */
+const idx *oipm_genpow_map(const oipm_t *S, idx kgp, int which, idx *len)
+{
+    idx cnt = 0;
+    for (idx k = 0; k < S->ncones; k++) {
+        const cone_t *c = &S->cones[k];
+        if (c->type != CONE_GENPOW) continue;
+        if (cnt == kgp) {
+            if (which == 0) { *len = c->gp->dim1; return c->gp->map_q; }
+            if (which == 1) { *len = c->gp->dim2; return c->gp->map_r; }
+            if (which == 2) { *len = c->dim; return c->gp->map_p; }
+            *len = 3; return c->gp->map_D;
+        }
+        cnt++;
+    }
+    *len = 0; return NULL;
+}
+/* KKTSolver::update on the current cone scalings (needs set_perm); K values are then readable through oipm_kkt_nzval */
+int oipm_test_kkt_update(oipm_t *S) { return S->ldl ? kkt_update(S) : -1; }
 const double *oipm_equil(const oipm_t *S, int which) { return which == 0 ? S->d : (which == 1 ? S->e : &S->c); }
 const double *oipm_scaled_data(const oipm_t *S, int which)
 { return which == 0 ? S->P.nzval : which == 1 ? S->A.nzval : which == 2 ? S->q : S->b; }

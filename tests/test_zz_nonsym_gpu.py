@@ -169,3 +169,45 @@ def test_presolve_known_answers():
     assert rd["status"] == "Solved" and dev.m_reduced == 0 and np.linalg.norm(rd["x"] + c) <= 1e-6
     with pytest.raises(cb.BackendError):
         dev.update_data(q=c)          # data updates are refused on a presolved problem (data_updating.rs:165-180)
+
+
+# ---- generalised power cone (basic_genpowcone.rs) ----
+def test_genpowcone_known_answer_and_kkt_structure():
+    P, c, A, b, cones = ref.genpow_data()
+    dev, rd, ora, ro = both(P, c, A, b, cones)
+    assert rd["status"] == "Solved" and abs(rd["obj_val"] + 1.8458) <= 1e-3
+    assert_parity(rd, ro, xtol=1e-5)
+    N, cp, rv, nz, ds = dev.kkt()
+    No, cpo, rvo, _, dso = ora.kkt()
+    assert N == No == 6 + 8 + 6 and np.array_equal(cp, cpo) and np.array_equal(rv, rvo) and np.array_equal(ds, dso)
+    assert list(ds[14:]) == [-1, -1, 1, -1, -1, 1]
+
+
+def test_genpow_cone_ops_match_oracle():
+    cones = [("genpow", ([0.6, 0.4], 1)), ("zero", 2), ("genpow", ([0.2, 0.3, 0.5], 2)), ("nonneg", 3),
+             ("genpow", ([0.25, 0.25, 0.25, 0.25], 3)), ("exp", 3), ("soc", 3)] + [("genpow", ([0.7, 0.3], 2))] * 40
+    m = sum(3 if k == "exp" else (len(d[0]) + d[1] if k == "genpow" else d) for k, d in cones)
+    P, q, A, b = sp.csc_matrix((m, m)), np.zeros(m), -sp.identity(m, format="csc"), np.zeros(m)
+    st = dict(equilibrate_enable=0)
+    dev = cb.CudaSolver(P, q, A, b, cones, settings=cb.default_settings(**st))
+    ora = oracle.IPM(P, q, A, b, cones, settings=oracle.default_settings(**st))
+    assert not dev.cone_is_symmetric()
+    z, s = dev.cone_unit_initialization()
+    zo, so = ora.unit_initialization()
+    assert np.array_equal(z, zo) and np.array_equal(s, so)
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        z, s = interior(ora, rng, m, 0.05 + 0.03 * trial)
+        mu = 0.5 + 0.1 * trial
+        assert dev.cone_update_scaling_ex(s, z, mu, cb.SCALING_DUAL) and ora.update_scaling_ex(s, z, mu, 1)
+        assert close(dev.cone_get_Hs(), ora.get_Hs(), 1e-10)
+        x = rng.standard_normal(m)
+        assert close(dev.cone_mul_Hs(x), ora.mul_Hs(x), 1e-10)
+        dz, ds = 0.3 * rng.standard_normal(m), 0.3 * rng.standard_normal(m)
+        assert close(dev.cone_combined_ds_shift(dz, ds, 0.37 * mu), ora.combined_ds_shift(dz, ds, 0.37 * mu), 1e-9)
+        for amax in (1.0, 0.61):
+            # the second-order cone's own step differs in the last bits (block sums), so closeness, not equality, here
+            assert np.isclose(dev.cone_step_length(3 * dz, 3 * ds, z, s, amax), ora.step_length(3 * dz, 3 * ds, z, s, amax), rtol=1e-12, atol=0)
+        for al in (0.0, 0.4):
+            bd, bo = dev.cone_compute_barrier(z, s, 0.05 * dz, 0.05 * ds, al), ora.compute_barrier(z, s, 0.05 * dz, 0.05 * ds, al)
+            assert abs(bd - bo) <= 1e-9 * max(1.0, abs(bo))
