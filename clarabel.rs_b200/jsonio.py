@@ -17,7 +17,7 @@ import numpy as np
 import scipy.sparse as sp
 
 _TAGS = {"ZeroConeT": "zero", "NonnegativeConeT": "nonneg", "SecondOrderConeT": "soc", "PSDTriangleConeT": "psd",
-         "ExponentialConeT": "exp", "PowerConeT": "pow"}
+         "ExponentialConeT": "exp", "PowerConeT": "pow", "GenPowerConeT": "genpow"}
 _RTAGS = {v: k for k, v in _TAGS.items()}
 # settings the C ABI knows (cipm_settings); the reference's other fields (verbose, direct_solve_method, ...) are
 # printing / backend selection and are ignored on load
@@ -49,8 +49,6 @@ def _cone_from(c):
         tag, val = c, None
     else:
         (tag, val), = c.items()
-    if tag == "GenPowerConeT":
-        raise ValueError("GenPowerConeT is not implemented by this backend")
     if tag not in _TAGS:
         raise ValueError(f"unknown cone tag {tag!r}")
     kind = _TAGS[tag]
@@ -58,6 +56,8 @@ def _cone_from(c):
         return (kind, 3)
     if kind == "pow":
         return (kind, float(val))
+    if kind == "genpow":                        # serde tuple variant: [[alpha...], dim2]
+        return (kind, ([float(a) for a in val[0]], int(val[1])))
     return (kind, int(val))
 
 
@@ -66,6 +66,8 @@ def _cone_to(kind, val):
         return {_RTAGS[kind]: []}
     if kind == "pow":
         return {_RTAGS[kind]: float(val)}
+    if kind == "genpow":
+        return {_RTAGS[kind]: [[float(a) for a in val[0]], int(val[1])]}
     return {_RTAGS[kind]: int(val)}
 
 

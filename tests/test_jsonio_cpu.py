@@ -19,8 +19,8 @@ _spec.loader.exec_module(jsonio)
 
 def test_round_trip_all_cone_kinds(tmp_path):
     rng = np.random.default_rng(0)
-    cones = [("zero", 2), ("nonneg", 3), ("soc", 4), ("psd", 2), ("exp", 3), ("pow", 0.3)]
-    m, n = 2 + 3 + 4 + 3 + 3 + 3, 5
+    cones = [("zero", 2), ("nonneg", 3), ("soc", 4), ("psd", 2), ("exp", 3), ("pow", 0.3), ("genpow", ([0.5, 0.5], 2))]
+    m, n = 2 + 3 + 4 + 3 + 3 + 3 + 4, 5
     P = sp.random(n, n, density=0.5, random_state=1); P = (P + P.T + sp.identity(n)).tocsc()
     A = sp.random(m, n, density=0.4, random_state=2, format="csc")
     q, b = rng.standard_normal(n), rng.standard_normal(m)
@@ -32,13 +32,13 @@ def test_round_trip_all_cone_kinds(tmp_path):
     assert d["cones"] == cones
     assert d["settings"] == {"max_iter": 50, "time_limit": float("inf"), "tol_feas": 1e-7}
     raw = json.loads(path.read_text())
-    assert raw["cones"][0] == {"ZeroConeT": 2} and raw["cones"][4] == {"ExponentialConeT": []} and raw["cones"][5] == {"PowerConeT": 0.3}
+    assert raw["cones"][0] == {"ZeroConeT": 2} and raw["cones"][4] == {"ExponentialConeT": []} and raw["cones"][5] == {"PowerConeT": 0.3} and raw["cones"][6] == {"GenPowerConeT": [[0.5, 0.5], 2]}
 
 
-def test_rejects_unknown_and_unbuilt_cones(tmp_path):
+def test_rejects_unknown_cones(tmp_path):
     base = {"P": {"m": 1, "n": 1, "colptr": [0, 0], "rowval": [], "nzval": []}, "q": [0.0],
             "A": {"m": 3, "n": 1, "colptr": [0, 0], "rowval": [], "nzval": []}, "b": [0.0, 0.0, 0.0]}
-    for cone in ({"GenPowerConeT": [[0.5, 0.5], 1]}, {"FancyConeT": 3}):
+    for cone in ({"FancyConeT": 3},):
         p = tmp_path / "bad.json"
         p.write_text(json.dumps(dict(base, cones=[cone])))
         with pytest.raises(ValueError):
