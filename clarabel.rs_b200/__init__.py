@@ -317,6 +317,24 @@ class SymbolicAnalysis:
             L.csym_free(h)
 
 
+def shard_plan(sym, nranks):
+    """Subtree-to-rank mapping of one factorisation (csrc/symbolic.h ShardPlan): owner[s] = rank that
+    factors front s, -1 for the replicated top part; plus the flop split, what crosses ranks per refactor / solve and
+    the modelled speed-up  total / (largest rank share + top)."""
+    L = lib()
+    nsup = int(sym.nsup)
+    owner = np.empty(max(nsup, 1), dtype=np.int64)
+    stats = np.zeros(8)
+    f, rp, par = (np.ascontiguousarray(a, dtype=np.int64) for a in (sym.sn_first, sym.sn_rowptr, sym.sn_parent))
+    rc = L.csym_shard_plan(nsup, _p(f, C.c_int64), _p(rp, C.c_int64), _p(par, C.c_int64), int(nranks),
+                           _p(owner, C.c_int64), _p(stats, C.c_double))
+    if rc:
+        raise BackendError(f"csym_shard_plan failed: {rc}")
+    keys = ["total_flops", "top_flops", "max_rank_flops", "min_rank_flops", "exchange_doubles", "exchange_vec",
+            "top_levels", "model_speedup"]
+    return dict(owner=owner[:nsup], **dict(zip(keys, stats.tolist())))
+
+
 def order(n, colptr, rowval, kind=ORDER_AMD, dense_scale=1.5, nd_leaf=200):
     L = lib()
     cp, rv = _u64(colptr), _u64(rowval)

@@ -628,4 +628,95 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
   return build(n, Ap, Ai, perm0, opt, S, false);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Subtree-to-rank mapping (see symbolic.h).  Fronts are numbered in post-order, so children precede parents.
+int plan_shards(int nsup, const int* sn_first, const int64_t* sn_rowptr, const int* sn_parent, int nranks,
+                ShardPlan& out) {
+  if (nsup <= 0 || nranks < 1) return -1;
+  out = ShardPlan();
+  out.nranks = nranks;
+  std::vector<double> fl(nsup), sub(nsup);
+  std::vector<int> level(nsup, 0);
+  for (int s = 0; s < nsup; s++) {
+    const double ns = sn_first[s + 1] - sn_first[s], nr = (double)(sn_rowptr[s + 1] - sn_rowptr[s]);
+    fl[s] = ns * ns * ns / 3.0 + ns * ns * nr + ns * nr * nr;
+    sub[s] = fl[s];
+  }
+  for (int s = 0; s < nsup; s++) {
+    const int p = sn_parent[s];
+    if (p >= 0) { if (p <= s) return -2; sub[p] += sub[s]; }
+  }
+  std::vector<std::vector<int>> kids(nsup);
+  std::vector<int> roots;
+  for (int s = 0; s < nsup; s++) { if (sn_parent[s] >= 0) kids[sn_parent[s]].push_back(s); else roots.push_back(s); }
+  double total = 0.0;
+  for (int r : roots) total += sub[r];
+  out.total_flops = total;
+
+  // candidate set = subtree roots below the current top part, kept as a max-heap on subtree flops
+  auto cmp = [&](int a, int b) { return sub[a] < sub[b] || (sub[a] == sub[b] && a > b); };
+  std::vector<int> cand(roots);
+  std::make_heap(cand.begin(), cand.end(), cmp);
+  std::vector<char> in_top(nsup, 0);
+  double top = 0.0;
+  auto makespan = [&](const std::vector<int>& c) {
+    std::vector<int> srt(c);
+    std::sort(srt.begin(), srt.end(), [&](int a, int b) { return sub[a] > sub[b] || (sub[a] == sub[b] && a < b); });
+    std::vector<double> load(nranks, 0.0);
+    for (int s : srt) *std::min_element(load.begin(), load.end()) += sub[s];
+    return *std::max_element(load.begin(), load.end());
+  };
+  double best = top + makespan(cand);
+  std::vector<int> best_cand(cand);
+  std::vector<char> best_top(in_top);
+  double best_topfl = top;
+  int since = 0;
+  const int patience = 16 * nranks, max_cand = 4096;
+  while (nranks > 1 && !cand.empty() && since < patience && (int)cand.size() < max_cand) {
+    std::pop_heap(cand.begin(), cand.end(), cmp);
+    const int s = cand.back();
+    cand.pop_back();
+    if (kids[s].empty()) { cand.push_back(s); std::push_heap(cand.begin(), cand.end(), cmp); break; }   // largest is a leaf
+    in_top[s] = 1;
+    top += fl[s];
+    for (int c : kids[s]) { cand.push_back(c); std::push_heap(cand.begin(), cand.end(), cmp); }
+    const double t = top + makespan(cand);
+    if (t < best * (1.0 - 1e-9)) { best = t; best_cand = cand; best_top = in_top; best_topfl = top; since = 0; }
+    else since++;
+  }
+  // assignment of the best configuration
+  out.owner.assign(nsup, -1);
+  out.rank_flops.assign(nranks, 0.0);
+  std::sort(best_cand.begin(), best_cand.end(), [&](int a, int b) { return sub[a] > sub[b] || (sub[a] == sub[b] && a < b); });
+  for (int s : best_cand) {
+    const int g = (int)(std::min_element(out.rank_flops.begin(), out.rank_flops.end()) - out.rank_flops.begin());
+    out.rank_flops[g] += sub[s];
+    out.owner[s] = g;
+    if (sn_parent[s] >= 0) out.cut_roots.push_back(s);
+  }
+  std::sort(out.cut_roots.begin(), out.cut_roots.end());
+  // owners flow down the subtrees (parents have larger indices than children)
+  for (int s = nsup - 1; s >= 0; s--) {
+    const int p = sn_parent[s];
+    if (best_top[s]) { out.owner[s] = -1; continue; }
+    if (out.owner[s] < 0 && p >= 0) out.owner[s] = out.owner[p];
+  }
+  out.top_flops = best_topfl;
+  for (int s : out.cut_roots) {
+    const int64_t nr = sn_rowptr[s + 1] - sn_rowptr[s];
+    out.exchange_doubles += nr * nr;
+    out.exchange_vec += nr;
+  }
+  for (int s = 0; s < nsup; s++) {
+    if (!best_top[s]) continue;
+    int l = 0;
+    for (int c : kids[s]) if (best_top[c] && level[c] + 1 > l) l = level[c] + 1;
+    level[s] = l;
+    if (l + 1 > out.top_levels) out.top_levels = l + 1;
+  }
+  const double mx = *std::max_element(out.rank_flops.begin(), out.rank_flops.end());
+  out.model_speedup = total > 0.0 ? total / (mx + out.top_flops) : 1.0;
+  return 0;
+}
+
 }  // namespace cb

@@ -88,4 +88,24 @@ int order_with_groups(int n, const int64_t* Ap, const int32_t* Ai, const int* gr
 int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
             const SymbolicOptions& opt, Symbolic& S);
 
+// ---- multi-GPU: subtree-to-rank mapping of one factorisation ----
+// Independent subtrees of the assembly tree factor and solve independently; the fronts above the cut (the "top"
+// part, ancestors of more than one rank's subtrees) are replicated on every rank.  What crosses ranks is the update
+// matrix (refactor) and the update vector (solve) of every cut root, and the solution slices at the end.
+struct ShardPlan {
+  int nranks = 1;
+  std::vector<int> owner;          // [nsup] rank that factors front s, -1 = replicated top part
+  std::vector<int> cut_roots;      // fronts with an owner whose parent is in the top part
+  std::vector<double> rank_flops;  // [nranks] dense flops of the owned subtrees
+  double top_flops = 0, total_flops = 0;
+  int64_t exchange_doubles = 0;    // sum nr^2 over the cut roots: all-gathered once per refactor
+  int64_t exchange_vec = 0;        // sum nr over the cut roots: all-gathered once per solve sweep
+  int top_levels = 0;              // tree levels inside the top part (its critical path)
+  double model_speedup = 1.0;      // total_flops / (max rank_flops + top_flops)
+};
+// Greedy top-down splitting (largest subtree first) with longest-processing-time assignment of the subtrees to
+// ranks; keeps the configuration with the best modelled makespan.  Only reads the front sizes and the tree.
+int plan_shards(int nsup, const int* sn_first, const int64_t* sn_rowptr, const int* sn_parent, int nranks,
+                ShardPlan& out);
+
 }  // namespace cb

@@ -128,4 +128,21 @@ int csym_order(uint64_t n, const uint64_t* colptr, const uint64_t* rowval, int k
   return 0;
 }
 
+// subtree-to-rank mapping of one factorisation (symbolic.h: ShardPlan).  owner_out[nsup]; stats_out[8] =
+// {total_flops, top_flops, max rank flops, min rank flops, exchange_doubles, exchange_vec, top_levels, model_speedup}
+int csym_shard_plan(int64_t nsup, const int64_t* sn_first, const int64_t* sn_rowptr, const int64_t* sn_parent,
+                    int nranks, int64_t* owner_out, double* stats_out) {
+  std::vector<int> f(sn_first, sn_first + nsup + 1), par(sn_parent, sn_parent + nsup);
+  cb::ShardPlan P;
+  int rc = cb::plan_shards((int)nsup, f.data(), sn_rowptr, par.data(), nranks, P);
+  if (rc) return rc;
+  for (int64_t s = 0; s < nsup; s++) owner_out[s] = P.owner[s];
+  double mx = 0.0, mn = 1e300;
+  for (double v : P.rank_flops) { if (v > mx) mx = v; if (v < mn) mn = v; }
+  stats_out[0] = P.total_flops; stats_out[1] = P.top_flops; stats_out[2] = mx; stats_out[3] = mn;
+  stats_out[4] = (double)P.exchange_doubles; stats_out[5] = (double)P.exchange_vec; stats_out[6] = P.top_levels;
+  stats_out[7] = P.model_speedup;
+  return 0;
+}
+
 }  // extern "C"

@@ -3,6 +3,7 @@ level schedule): a numpy emulation of the device schedule (tests/mf_emulator.py)
 must reproduce the oracle's factors and solutions on the same permutation."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 import clarabel_rs_b200 as cb
 from clarabel_rs_b200 import pkg  # noqa: F401
@@ -150,3 +151,49 @@ def test_update_arena_is_safe_without_level_barriers(ordering):
             assert ok, (s, t)
         active.append(s)
     assert overlaps > 0                # the arena does recycle space
+
+
+# ---- subtree-to-rank mapping for one factorisation on several GPUs (csrc/symbolic.h ShardPlan) ----
+@pytest.mark.parametrize("nranks", [1, 2, 4, 8])
+def test_shard_plan_invariants(nranks):
+    pr = workloads.random_sparse_qp(n=6000, m=12000, nnz_per_row=4, seed=5, window=60)
+    N, cp, rv = workloads.kkt_triu(pr["P"], pr["A"], np.ones(pr["A"].shape[0]))[:3]
+    S = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_ND, nd_leaf=200)
+    P = cb.shard_plan(S, nranks)
+    owner, par = P["owner"], S.sn_parent
+    assert owner.min() >= -1 and owner.max() < nranks
+    ns = np.diff(S.sn_first).astype(float)
+    nr = np.diff(S.sn_rowptr).astype(float)
+    fl = ns ** 3 / 3 + ns ** 2 * nr + ns * nr ** 2
+    for s in range(S.nsup):
+        p = par[s]
+        if p < 0:
+            continue
+        if owner[p] >= 0:
+            assert owner[s] == owner[p]          # an owned front owns its whole subtree
+        if owner[s] == -1:
+            assert owner[p] == -1                # the replicated top part is closed upwards
+    assert np.isclose(fl.sum(), P["total_flops"], rtol=1e-12) and np.isclose(P["total_flops"], S.flops_stored, rtol=1e-9)
+    per_rank = np.array([fl[owner == g].sum() for g in range(nranks)])
+    assert np.isclose(per_rank.max(), P["max_rank_flops"], rtol=1e-12)
+    assert np.isclose(fl[owner == -1].sum(), P["top_flops"], rtol=1e-12, atol=1e-6)
+    cut = [s for s in range(S.nsup) if owner[s] >= 0 and par[s] >= 0 and owner[par[s]] == -1]
+    assert P["exchange_doubles"] == sum(int(nr[s]) ** 2 for s in cut) and P["exchange_vec"] == sum(int(nr[s]) for s in cut)
+    assert 1.0 - 1e-12 <= P["model_speedup"] <= nranks + 1e-9
+    if nranks == 1:
+        assert (owner == 0).all() and P["top_flops"] == 0.0
+    else:
+        assert P["model_speedup"] > 1.3          # a nested-dissection tree does shard
+        assert len(set(owner[owner >= 0])) == nranks
+
+
+def test_shard_plan_of_a_chain_is_replicas_only():
+    """an arrow / chain-shaped tree has no independent subtrees: the plan says speed-up 1"""
+    n = 400
+    rows = np.concatenate([np.arange(n), np.arange(n - 1)])          # tridiagonal: etree is a path
+    cols = np.concatenate([np.arange(n), np.arange(1, n)])
+    K = sp.csc_matrix((np.ones(rows.size), (rows, cols)), shape=(n, n))
+    K.sort_indices()
+    S = cb.SymbolicAnalysis(n, K.indptr, K.indices, perm=np.arange(n))
+    P = cb.shard_plan(S, 4)
+    assert P["model_speedup"] <= 1.0 + 1e-9
