@@ -39,3 +39,9 @@ HARNESS := tests/host_harness/libns3_host.so
 $(HARNESS): tests/host_harness/ns3_host.cpp $(CSRC)/cones_nonsym.cuh
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -o $@ $<
 all: $(HARNESS)
+
+# CUDA-runtime stand-in for LD_PRELOAD in a test subprocess (host-side setup checks without a GPU, see the file header)
+FAKERT := tests/host_harness/libfake_cudart.so
+$(FAKERT): tests/host_harness/fake_cudart.c
+	$(CC) -O1 -fPIC -shared -Wall -o $@ $<
+all: $(FAKERT)

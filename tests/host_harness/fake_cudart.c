@@ -1,0 +1,61 @@
+/* TEST INFRASTRUCTURE ONLY -- never shipped, never linked into the product library.
+ *
+ * A stand-in for the handful of CUDA runtime entry points libclarabel_b200.so imports, for LD_PRELOAD in a
+ * SUBPROCESS of the CPU test-suite (tests/test_host_setup_cpu.py): device memory is host memory, copies are
+ * memcpy, streams / events are tokens and KERNEL LAUNCHES ARE DROPPED.  Nothing numeric can be checked this way
+ * (no kernel runs); what it makes checkable without a GPU is the HOST side of cipm_create / cldl_create: cone
+ * collapsing, the inf-bound presolve, KKT assembly (pattern, signs, expansion columns), ordering, symbolic analysis
+ * and plan construction run to completion, do not crash, and produce the same KKT structure as the oracle.
+ * The product keeps failing loudly without a real device (tests/test_abi.py::test_no_cpu_fallback runs without
+ * this shim). */
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef int cudaError_t;
+struct dim3_ { unsigned x, y, z; };
+
+cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return 0; }
+cudaError_t cudaSetDevice(int d) { (void)d; return 0; }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+cudaError_t cudaFree(void *p) { free(p); return 0; }
+cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int kind) { (void)kind; if (n) memmove(d, s, n); return 0; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int kind, void *st) { (void)kind; (void)st; if (n) memmove(d, s, n); return 0; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, void *st) { (void)st; if (n) memset(d, v, n); return 0; }
+cudaError_t cudaStreamCreateWithFlags(void **s, unsigned f) { (void)f; *s = malloc(1); return 0; }
+cudaError_t cudaStreamDestroy(void *s) { free(s); return 0; }
+cudaError_t cudaStreamSynchronize(void *s) { (void)s; return 0; }
+cudaError_t cudaStreamWaitEvent(void *s, void *e, unsigned f) { (void)s; (void)e; (void)f; return 0; }
+cudaError_t cudaEventCreate(void **e) { *e = malloc(1); return 0; }
+cudaError_t cudaEventCreateWithFlags(void **e, unsigned f) { (void)f; *e = malloc(1); return 0; }
+cudaError_t cudaEventDestroy(void *e) { free(e); return 0; }
+cudaError_t cudaEventRecord(void *e, void *s) { (void)e; (void)s; return 0; }
+cudaError_t cudaEventSynchronize(void *e) { (void)e; return 0; }
+cudaError_t cudaEventElapsedTime(float *ms, void *a, void *b) { (void)a; (void)b; *ms = 0.0f; return 0; }
+cudaError_t cudaFuncSetAttribute(const void *f, int a, int v) { (void)f; (void)a; (void)v; return 0; }
+cudaError_t cudaDeviceGetAttribute(int *v, int attr, int dev)
+{
+    (void)dev;
+    *v = attr == 97 ? 232448 /* max opt-in shared memory per block (B200) */ : attr == 16 ? 148 /* SMs */ : 0;
+    return 0;
+}
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int *n, const void *f, int bs, size_t sm, unsigned fl)
+{ (void)f; (void)bs; (void)sm; (void)fl; *n = 2; return 0; }
+cudaError_t cudaGetLastError(void) { return 0; }
+const char *cudaGetErrorString(cudaError_t e) { (void)e; return "fake cudart (tests/host_harness)"; }
+cudaError_t cudaLaunchKernel(const void *f, struct dim3_ g, struct dim3_ b, void **args, size_t sm, void *st)
+{ (void)f; (void)g; (void)b; (void)args; (void)sm; (void)st; return 0; }
+/* launch stubs: "if (__cudaPushCallConfiguration(...) == 0) stub(args)": a non-zero return drops the launch */
+unsigned __cudaPushCallConfiguration(struct dim3_ g, struct dim3_ b, size_t sm, void *st) { (void)g; (void)b; (void)sm; (void)st; return 1; }
+cudaError_t __cudaPopCallConfiguration(struct dim3_ *g, struct dim3_ *b, size_t *sm, void *st) { (void)g; (void)b; (void)sm; (void)st; return 0; }
+static void *fat_handle[4];
+void **__cudaRegisterFatBinary(void *f) { (void)f; return fat_handle; }
+void __cudaRegisterFatBinaryEnd(void **h) { (void)h; }
+void __cudaUnregisterFatBinary(void **h) { (void)h; }
+void __cudaRegisterFunction(void **h, const char *hf, char *df, const char *dn, int tl, void *tid, void *bid, void *bd, void *gd, int *ws)
+{ (void)h; (void)hf; (void)df; (void)dn; (void)tl; (void)tid; (void)bid; (void)bd; (void)gd; (void)ws; }
+void __cudaRegisterVar(void **h, char *hv, char *da, const char *dn, int ext, size_t sz, int cst, int glb)
+{ (void)h; (void)hv; (void)da; (void)dn; (void)ext; (void)sz; (void)cst; (void)glb; }
