@@ -352,13 +352,12 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
       perm = perm_grp.data();
     }
   }
-  rc = ldl.init(N, Kp.data(), Ki32.data(), Kx.data(), dsigns.data(), o, perm);
-  if (rc) return rc;
-  st = ldl.stream;
-  V.st = st;
-  V.ws = cones->ws;
-  // full symmetric CSR of K with an index into the value array
-  {
+  // full symmetric CSR of K with an index into the value array (used by iterative refinement): only needs the
+  // assembled pattern, so it is built and uploaded on a host thread next to the ordering / symbolic analysis
+  int rc_csr = 0;
+  const int devid = lo.device;
+  auto build_sym_csr = [&]() -> int {
+    if (cudaSetDevice(devid) != cudaSuccess) return CLDL_E_CUDA;
     std::vector<int> rowcnt(N + 1, 0);
     for (int j = 0; j < N; j++)
       for (int64_t q = Kp[j]; q < Kp[j + 1]; q++) {
@@ -376,7 +375,17 @@ int KKTDevice::init(const HostCsc& P, const HostCsc& A, ConeSet* cs, const cipm_
       }
     if (upv(&d_srow, rowcnt) || upv(&d_scol, scol) || upv(&d_sidx, sidx)) return CLDL_E_CUDA;
     SCK(cudaMalloc((void**)&d_sval, (size_t)(nnzS ? nnzS : 1) * 8));
-  }
+    return 0;
+  };
+  std::thread th_csr([&]() { rc_csr = build_sym_csr(); });
+  struct ThJoin { std::thread* t; ~ThJoin() { if (t->joinable()) t->join(); } } th_csr_guard{&th_csr};
+  rc = ldl.init(N, Kp.data(), Ki32.data(), Kx.data(), dsigns.data(), o, perm);
+  if (rc) return rc;
+  st = ldl.stream;
+  V.st = st;
+  V.ws = cones->ws;
+  th_csr.join();
+  if (rc_csr) return rc_csr;
   std::vector<signed char> ds8(dsigns.begin(), dsigns.end());
   if (upv(&d_map_P, map_P) || upv(&d_map_A, map_A) || upv(&d_map_Hs, map_Hs) || upv(&d_map_u, map_u) ||
       upv(&d_map_v, map_v) || upv(&d_map_D, map_D) || upv(&d_map_diag, map_diag) || upv(&d_dsigns, ds8) ||
@@ -887,21 +896,27 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   // layer (assembly maps, ordering, symbolic analysis, plans); the values go in afterwards
   if ((rc = sc.init(st))) return rc;
   {
-    std::thread eq([this]() { equilibrate(); });
+    // ... and so does the upload of the scaled problem data (CSR forms of A, A', P and the vectors), which only
+    // needs the equilibrated values
+    int rc_up = 0;
+    const int devid = lo.device;
+    std::thread eq([this, &rc_up, devid]() {
+      equilibrate();
+      rc_up = cudaSetDevice(devid) == cudaSuccess ? upload_problem() : CLDL_E_CUDA;
+    });
     kkt.defer_values = true;
     rc = kkt.init(P, A, &cones, set, lo, perm, st, &sc);
     eq.join();
     if (rc) return rc;
+    if (rc_up) return rc_up;
     if ((rc = kkt.set_PA_values(P, A))) return rc;
   }
-  cb_tmark("ipm: equilibrate || kkt init");
+  cb_tmark("ipm: equilibrate + upload problem || kkt init");
   // single stream for everything: adopt the LDL object's stream
   cudaStreamDestroy(st);
   st = kkt.st;
   cones.stream = st; sc.st = st; V.st = st; V.ws = cones.ws;
   cb_tmark("ipm: kkt init total");
-  if ((rc = upload_problem())) return rc;
-  cb_tmark("ipm: upload problem");
   auto al = [&](double** pp, int len) { return cudaMalloc((void**)pp, (size_t)(len ? len : 1) * 8) == cudaSuccess && cudaMemset(*pp, 0, (size_t)(len ? len : 1) * 8) == cudaSuccess; };
   bool ok = al(&x, n) && al(&s, m) && al(&z, m) && al(&lx, n) && al(&ls, m) && al(&lz, m) && al(&rhx, n) &&
             al(&rhs_, m) && al(&rhz, m) && al(&px, n) && al(&ps, m) && al(&pz, m) && al(&rx, n) && al(&rz, m) &&

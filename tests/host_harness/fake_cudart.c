@@ -9,6 +9,8 @@
  * The product keeps failing loudly without a real device (tests/test_abi.py::test_no_cpu_fallback runs without
  * this shim). */
 #include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -21,8 +23,21 @@ cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *
 cudaError_t cudaFree(void *p) { free(p); return 0; }
 cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
 cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int kind) { (void)kind; if (n) memmove(d, s, n); return 0; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int kind, void *st) { (void)kind; (void)st; if (n) memmove(d, s, n); return 0; }
+/* FAKE_CUDART_LOG=<file>: one line "bytes fnv1a64" per host-to-device copy, so that a change of the host-side plan
+   builders can be checked to upload exactly the same arrays (compare the sorted logs) */
+static void log_h2d(const void *s, size_t n, int kind)
+{
+    static const char *path = (const char *)-1;
+    if (path == (const char *)-1) path = getenv("FAKE_CUDART_LOG");
+    if (!path || kind != 1 || n == 0) return;
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = (const unsigned char *)s;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    FILE *f = fopen(path, "a");
+    if (f) { fprintf(f, "%zu %016llx\n", n, (unsigned long long)h); fclose(f); }
+}
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int kind) { log_h2d(s, n, kind); if (n) memmove(d, s, n); return 0; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int kind, void *st) { (void)st; log_h2d(s, n, kind); if (n) memmove(d, s, n); return 0; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, void *st) { (void)st; if (n) memset(d, v, n); return 0; }
 cudaError_t cudaStreamCreateWithFlags(void **s, unsigned f) { (void)f; *s = malloc(1); return 0; }
