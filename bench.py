@@ -47,6 +47,13 @@ def load_workload(name, rank):
     elif name == "c4":
         pr = workloads.block_angular_qp(seed=3 + rank)
         desc = "block-angular sparse QP n=1e6 m=1.5e6, seed=%d" % (3 + rank)
+    elif name == "c5":
+        pr = workloads.block_sdp(seed=4 + rank)
+        desc = "block-diagonal SDP: 500 PSD(20) + linear constraints, n=2e4, seed=%d" % (4 + rank)
+    elif name == "expmix":
+        pr = workloads.entropy_power_mix(k_exp=100_000, k_pow=50_000, n_eq=10, seed=6 + rank)
+        desc = ("entropy maximisation + geometric-mean allocation: 1e5 exponential cones, 5e4 power cones, "
+                "11 equality rows, seed=%d" % (6 + rank))
     else:
         raise SystemExit("unknown workload " + name)
     return pr, desc
