@@ -2,6 +2,7 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -144,12 +145,15 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   std::vector<int64_t> Up;
   std::vector<int> Ui, parent0, post;
   permuted_upper(n, Ap, Ai, iperm0, Up, Ui, false);   // the elimination tree does not need sorted columns
+  TMARK("sym:   permuted upper");
   etree_upper(n, Up, Ui, parent0);
+  TMARK("sym:   etree");
   postorder(n, parent0, post);
   S.perm.resize(n);
   S.iperm.resize(n);
   for (int k = 0; k < n; k++) S.perm[k] = perm0[post[k]];
   for (int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+  TMARK("sym:   postorder");
 
   {
     // the tree of the post-ordered matrix is the old tree relabelled
@@ -184,7 +188,9 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   }
   std::vector<int64_t>().swap(Up);
   std::vector<int>().swap(Ui);
+  TMARK("sym:   lower pattern");
   colcounts_postordered(n, parent, Lo_ptr, Lo_idx, S.colcount);
+  TMARK("sym:   column counts");
   S.nnzL_simplicial = 0;
   S.flops_simplicial = 0;
   for (int j = 0; j < n; j++) {
@@ -274,32 +280,138 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
 
   TMARK("sym: supernode partition");
   // ---- row structures by bottom-up union, parents by min row ----
+  // Independent subtrees of the supernode tree are independent here too: the tree is cut into chunks (maximal
+  // subtrees below a work threshold; contiguous index ranges because supernodes are numbered in post-order) that
+  // host threads take from a shared counter, each into its own buffer; the part above the cut runs afterwards in
+  // index order exactly like the one-thread loop and the buffers are spliced in on the way, so the result is the
+  // one-thread result.  The chunking uses the parent predicted by the column etree (first row below a supernode =
+  // etree parent of its last column); should a computed parent ever leave its chunk, everything is redone on one
+  // thread.
   S.sn_rowptr.assign(nsup + 1, 0);
   S.sn_rows.clear();
   S.sn_parent.assign(nsup, -1);
   std::vector<std::vector<int>> kids(nsup);
-  {
+  // one supernode: rows >= l reached from its own columns and from its children (child rows through `child_rows`)
+  auto union_rows = [&](int s, std::vector<int>& mark, std::vector<int>& tmp, auto&& child_rows) {
+    const int f = S.sn_first[s], l = S.sn_first[s + 1];
+    tmp.clear();
+    for (int j = f; j < l; j++)
+      for (int64_t p = Lo_ptr[j]; p < Lo_ptr[j + 1]; p++) {
+        const int i = Lo_idx[p];
+        if (i >= l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
+      }
+    for (int c : kids[s]) {
+      const int *b = nullptr, *e = nullptr;
+      child_rows(c, b, e);
+      for (const int* q = b; q < e; q++) {
+        const int i = *q;
+        if (i >= l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
+      }
+    }
+    std::sort(tmp.begin(), tmp.end());
+  };
+  auto sequential_rows = [&]() {
+    S.sn_rows.clear();
+    for (auto& k : kids) k.clear();
+    std::fill(S.sn_parent.begin(), S.sn_parent.end(), -1);
     std::vector<int> mark(n, -1), tmp;
     for (int s = 0; s < nsup; s++) {
-      int f = S.sn_first[s], l = S.sn_first[s + 1];
-      tmp.clear();
-      for (int j = f; j < l; j++)
-        for (int64_t p = Lo_ptr[j]; p < Lo_ptr[j + 1]; p++) {
-          int i = Lo_idx[p];
-          if (i >= l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
-        }
-      for (int c : kids[s])
-        for (int64_t p = S.sn_rowptr[c]; p < S.sn_rowptr[c + 1]; p++) {
-          int i = S.sn_rows[p];
-          if (i >= l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
-        }
-      std::sort(tmp.begin(), tmp.end());
+      union_rows(s, mark, tmp, [&](int c, const int*& b, const int*& e) {
+        b = S.sn_rows.data() + S.sn_rowptr[c]; e = S.sn_rows.data() + S.sn_rowptr[c + 1];
+      });
       S.sn_rows.insert(S.sn_rows.end(), tmp.begin(), tmp.end());
       S.sn_rowptr[s + 1] = (int64_t)S.sn_rows.size();
       if (!tmp.empty()) {
-        int ps = S.col2sn[tmp[0]];
+        const int ps = S.col2sn[tmp[0]];
         S.sn_parent[s] = ps;
         kids[ps].push_back(s);
+      }
+    }
+  };
+  const unsigned hw_rows = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (nsup < 20000 || hw_rows < 2) {
+    sequential_rows();
+  } else {
+    // predicted tree, subtree work (entries of L below the diagonal blocks) and subtree sizes
+    std::vector<int> gpar(nsup, -1), cntsub(nsup, 1);
+    std::vector<double> wsub(nsup, 0.0);
+    double wtot = 0.0;
+    for (int s = 0; s < nsup; s++) {
+      const int last = S.sn_first[s + 1] - 1;
+      if (parent[last] >= 0) gpar[s] = S.col2sn[parent[last]];
+      for (int j = S.sn_first[s]; j <= last; j++) wsub[s] += (double)cc[j] + 1.0;
+      wtot += wsub[s];
+    }
+    for (int s = 0; s < nsup; s++) if (gpar[s] > s) { wsub[gpar[s]] += wsub[s]; cntsub[gpar[s]] += cntsub[s]; }
+    const double thr = wtot / (8.0 * hw_rows);
+    struct Chunk { int first, last; std::vector<int> rows; std::vector<int64_t> ptr; };   // ptr relative to rows
+    std::vector<Chunk> chunks;
+    std::vector<int> chunk_of(nsup, -1);
+    for (int s = 0; s < nsup; s++) {
+      const bool fits = wsub[s] <= thr;
+      const bool top = gpar[s] < 0 || wsub[gpar[s]] > thr;
+      if (fits && top && cntsub[s] > 1) {
+        Chunk c; c.first = s - cntsub[s] + 1; c.last = s;
+        for (int t = c.first; t <= c.last; t++) chunk_of[t] = (int)chunks.size();
+        chunks.push_back(std::move(c));
+      }
+    }
+    std::atomic<int> next{0};
+    std::atomic<int> escaped{0};
+    auto worker = [&]() {
+      std::vector<int> mark(n, -1), tmp;
+      for (;;) {
+        const int ci = next.fetch_add(1);
+        if (ci >= (int)chunks.size()) break;
+        Chunk& C = chunks[ci];
+        C.ptr.assign((size_t)(C.last - C.first + 2), 0);
+        for (int s2 = C.first; s2 <= C.last; s2++) {
+          union_rows(s2, mark, tmp, [&](int c, const int*& b, const int*& e) {
+            b = C.rows.data() + C.ptr[c - C.first]; e = C.rows.data() + C.ptr[c - C.first + 1];
+          });
+          C.rows.insert(C.rows.end(), tmp.begin(), tmp.end());
+          C.ptr[s2 - C.first + 1] = (int64_t)C.rows.size();
+          if (!tmp.empty()) {
+            const int ps = S.col2sn[tmp[0]];
+            S.sn_parent[s2] = ps;
+            if (ps <= C.last) { if (ps < C.first) escaped = 1; else kids[ps].push_back(s2); }
+            else if (s2 != C.last) escaped = 1;       // only the chunk root may point above the chunk
+          }
+        }
+      }
+    };
+    {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < hw_rows; t++) th.emplace_back(worker);
+      for (auto& x : th) x.join();
+    }
+    for (const Chunk& C : chunks)                    // a chunk root's parent must be above every chunk
+      if (S.sn_parent[C.last] >= 0 && chunk_of[S.sn_parent[C.last]] >= 0) escaped = 1;
+    if (escaped) {
+      sequential_rows();
+    } else {
+      std::vector<int> mark(n, -1), tmp;
+      for (int s = 0; s < nsup; s++) {
+        const int ci = chunk_of[s];
+        if (ci >= 0) {
+          const Chunk& C = chunks[ci];
+          const int64_t base = (int64_t)S.sn_rows.size();
+          S.sn_rows.insert(S.sn_rows.end(), C.rows.begin(), C.rows.end());
+          for (int t = C.first; t <= C.last; t++) S.sn_rowptr[t + 1] = base + C.ptr[t - C.first + 1];
+          if (S.sn_parent[C.last] >= 0) kids[S.sn_parent[C.last]].push_back(C.last);
+          s = C.last;
+          continue;
+        }
+        union_rows(s, mark, tmp, [&](int c, const int*& b, const int*& e) {
+          b = S.sn_rows.data() + S.sn_rowptr[c]; e = S.sn_rows.data() + S.sn_rowptr[c + 1];
+        });
+        S.sn_rows.insert(S.sn_rows.end(), tmp.begin(), tmp.end());
+        S.sn_rowptr[s + 1] = (int64_t)S.sn_rows.size();
+        if (!tmp.empty()) {
+          const int ps = S.col2sn[tmp[0]];
+          S.sn_parent[s] = ps;
+          kids[ps].push_back(s);
+        }
       }
     }
   }
