@@ -1925,28 +1925,69 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     small.assign(S.nsup, 0);
     struct Ent { int key; int dst; int src; };
     std::vector<Ent> pe, te;
-    for (int c = 0; c < S.nsup; c++) {
-      const int p = S.sn_parent[c];
-      if (p < 0 || big_pos[p] < 0) continue;
-      const int64_t b0 = S.sn_rowptr[c];
-      const int nrc = (int)(S.sn_rowptr[c + 1] - b0);
-      if (nrc > CB_SMALL_CHILD) continue;
-      if (S.upd_off[c] + (int64_t)nrc * nrc > 0x7fffffffLL) continue;   // int32 source indices
-      small[c] = 1;
-      const int pns = S.sn_first[p + 1] - S.sn_first[p];
-      const int pld = pns + (int)(S.sn_rowptr[p + 1] - S.sn_rowptr[p]);
-      for (int b = 0; b < nrc; b++)
-        for (int a = b; a < nrc; a++) {
-          const int ra = S.rel[b0 + a], rb = S.rel[b0 + b];
-          const int64_t src = S.upd_off[c] + (int64_t)b * nrc + a;
-          if (rb < pns) pe.push_back({big_pos[p], rb * pld + ra, (int)src});
-          else {
-            const int ti = (ra - pns) / TS, tj = (rb - pns) / TS;
-            te.push_back({tile_base[p] + ti * (ti + 1) / 2 + tj,
-                          (ra - pns - ti * TS) * (TS + 1) + (rb - pns - tj * TS), (int)src});
-          }
+    {
+      // two passes over the children on host threads: count (pe / te entries per child), prefix sums, fill -- the
+      // entry order (child, column b, row a) is the one of a single loop
+      const unsigned hc2 = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      const unsigned nth2 = S.nsup < 20000 ? 1u : hc2;
+      std::vector<int64_t> npe((size_t)S.nsup + 1, 0), nte((size_t)S.nsup + 1, 0);
+      auto eligible = [&](int c) {
+        const int p = S.sn_parent[c];
+        if (p < 0 || big_pos[p] < 0) return false;
+        const int nrc = (int)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
+        if (nrc > CB_SMALL_CHILD) return false;
+        if (S.upd_off[c] + (int64_t)nrc * nrc > 0x7fffffffLL) return false;   // int32 source indices
+        return true;
+      };
+      auto run = [&](auto&& fn) {
+        if (nth2 == 1) { fn(0, S.nsup); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth2; t++)
+          th.emplace_back([&, t]() { fn((int)((int64_t)S.nsup * t / nth2), (int)((int64_t)S.nsup * (t + 1) / nth2)); });
+        for (auto& x : th) x.join();
+      };
+      run([&](int c0, int c1) {
+        for (int c = c0; c < c1; c++) {
+          if (!eligible(c)) continue;
+          small[c] = 1;
+          const int p = S.sn_parent[c];
+          const int64_t b0 = S.sn_rowptr[c];
+          const int nrc = (int)(S.sn_rowptr[c + 1] - b0);
+          const int pns = S.sn_first[p + 1] - S.sn_first[p];
+          int64_t np_ = 0;
+          for (int b = 0; b < nrc; b++) if (S.rel[b0 + b] < pns) np_ += nrc - b;
+          npe[c + 1] = np_;
+          nte[c + 1] = (int64_t)nrc * (nrc + 1) / 2 - np_;
         }
+      });
+      for (int c = 0; c < S.nsup; c++) { npe[c + 1] += npe[c]; nte[c + 1] += nte[c]; }
+      pe.resize((size_t)npe[S.nsup]);
+      te.resize((size_t)nte[S.nsup]);
+      run([&](int c0, int c1) {
+        for (int c = c0; c < c1; c++) {
+          if (!small[c]) continue;
+          const int p = S.sn_parent[c];
+          const int64_t b0 = S.sn_rowptr[c];
+          const int nrc = (int)(S.sn_rowptr[c + 1] - b0);
+          const int pns = S.sn_first[p + 1] - S.sn_first[p];
+          const int pld = pns + (int)(S.sn_rowptr[p + 1] - S.sn_rowptr[p]);
+          Ent* wp = pe.data() + npe[c];
+          Ent* wt = te.data() + nte[c];
+          for (int b = 0; b < nrc; b++)
+            for (int a = b; a < nrc; a++) {
+              const int ra = S.rel[b0 + a], rb = S.rel[b0 + b];
+              const int64_t src = S.upd_off[c] + (int64_t)b * nrc + a;
+              if (rb < pns) *wp++ = Ent{big_pos[p], rb * pld + ra, (int)src};
+              else {
+                const int ti = (ra - pns) / TS, tj = (rb - pns) / TS;
+                *wt++ = Ent{tile_base[p] + ti * (ti + 1) / 2 + tj,
+                            (ra - pns - ti * TS) * (TS + 1) + (rb - pns - tj * TS), (int)src};
+              }
+            }
+        }
+      });
     }
+    cb_tmark("ldl:   small-child: entries");
     // bucket by key (counting sort keeps the child order inside a key), then order every bucket by dst with a
     // stable sort; buckets are independent, so host threads share them
     auto build = [&](std::vector<Ent>& v, size_t nkeys, std::vector<int>& ptr, std::vector<int>& src, std::vector<int>& dst) {
@@ -1969,18 +2010,23 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       src.resize(w.size() ? w.size() : 1); dst.resize(w.size() ? w.size() : 1);
       for (size_t i = 0; i < w.size(); i++) { src[i] = w[i].src; dst[i] = w[i].dst; }
     };
-    std::vector<int> ptr, src, dst;
+    // the panel lists and the tile lists are independent: the tile lists are built on a second host thread
+    std::vector<int> ptr, src, dst, tptr, tsrc, tdst;
     int* t1 = nullptr;
-    build(pe, big_tasks.size(), ptr, src, dst);
+    {
+      std::thread tb([&]() { build(te, tiles.size(), tptr, tsrc, tdst); });
+      build(pe, big_tasks.size(), ptr, src, dst);
+      tb.join();
+    }
+    cb_tmark("ldl:   small-child: panel + tile lists");
     h_sc_panel_ptr = ptr;
     if ((rc = upload(&t1, ptr))) return rc; dev.sc_panel_ptr = t1;
     if ((rc = upload(&t1, src))) return rc; dev.sc_panel_src = t1;
     if ((rc = upload(&t1, dst))) return rc; dev.sc_panel_dst = t1;
-    build(te, tiles.size(), ptr, src, dst);
-    h_sc_tile_ptr = ptr;
-    if ((rc = upload(&t1, ptr))) return rc; dev.sc_tile_ptr = t1;
-    if ((rc = upload(&t1, src))) return rc; dev.sc_tile_src = t1;
-    if ((rc = upload(&t1, dst))) return rc; dev.sc_tile_dst = t1;
+    h_sc_tile_ptr = tptr;
+    if ((rc = upload(&t1, tptr))) return rc; dev.sc_tile_ptr = t1;
+    if ((rc = upload(&t1, tsrc))) return rc; dev.sc_tile_src = t1;
+    if ((rc = upload(&t1, tdst))) return rc; dev.sc_tile_dst = t1;
     signed char* t8 = nullptr;
     if ((rc = upload(&t8, small))) return rc; dev.child_small = t8;
   }
