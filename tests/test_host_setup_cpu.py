@@ -88,3 +88,20 @@ def test_constructor_facts(results):
     assert not results["exp"]["symmetric"] and not results["genpow"]["symmetric"] and not results["mixed"]["symmetric"]
     assert results["genpow"]["N"] == 6 + 8 + 6                      # 3 expansion columns per generalised power cone
     assert results["presolve1"]["m_reduced"] == 5 and results["presolve3"]["m_reduced"] == 3 and results["presolve_all"]["m_reduced"] == 0
+
+
+def test_cpp_header_mirror_compiles_and_drives_the_c_abi(tmp_path):
+    """include/clarabel_b200.hpp (the reference's trait / solver names over the C ABI): builds with g++, constructs and
+    'solves' under the CUDA-runtime stand-in (host plumbing only), and fails loudly without a device."""
+    exe = str(tmp_path / "hpp_example")
+    lib_dir = os.path.join(ROOT, "clarabel.rs_b200")
+    cc = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-o", exe,
+                         os.path.join(ROOT, "tests", "host_harness", "hpp_example.cpp"),
+                         "-L" + lib_dir, "-lclarabel_b200", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    run = subprocess.run([exe], env=dict(os.environ, LD_PRELOAD=SHIM), capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and "created: kkt nnzA=17" in run.stdout and "mixed cones: ok" in run.stdout, run.stdout + run.stderr
+    import shutil
+    if shutil.which("nvidia-smi") is None:          # no device: the product path must refuse, not fall back
+        bare = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert bare.returncode == 2 and "SolverError" in bare.stdout
