@@ -1373,20 +1373,24 @@ int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
   cipm_handle* h = new (std::nothrow) cipm_handle();
   if (!h) return CLDL_E_ARG;
   std::vector<int> perm;
-  // the permutation length is only known after assembly; validate there
-  if (kkt_perm_or_null) {
-    // upper bound on N: n + m + 2*ncones
-    uint64_t cap = n + m + 3 * ncones;
-    perm.reserve(cap);
-    for (uint64_t k = 0; k < cap; k++) perm.push_back((int)kkt_perm_or_null[k]);
-  }
-  // dimension of the KKT system must be known to slice the permutation: do a dry collapse
+  // the permutation has the length of the KKT system the constructor will assemble: n + rows left after the inf-bound
+  // presolve + sparse expansion columns.  A dry collapse / presolve count gives it before anything is read.
   if (kkt_perm_or_null) {
     std::vector<cb::ConeSpec> cs;
     if (cb::ConeSet::collapse(cone_types, cone_dims, ncones, cs, cone_params, genpow_dim2, genpow_alpha)) { delete h; return CLDL_E_ARG; }
-    uint64_t p = 0;
-    for (auto& c : cs) { if (c.type == cb::CT_SOC && c.dim > cb::SOC_NO_EXPANSION_MAX_SIZE) p += 2; if (c.type == cb::CT_GENPOW) p += 3; }
-    perm.resize(n + m + p);
+    uint64_t p = 0, rows = 0, dropped = 0;
+    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * 1e20;
+    for (auto& c : cs) {
+      if (c.type == cb::CT_SOC && c.dim > cb::SOC_NO_EXPANSION_MAX_SIZE) p += 2;
+      if (c.type == cb::CT_GENPOW) p += 3;
+      if (c.type == cb::CT_NONNEG && s.presolve_enable && rows + (uint64_t)c.dim <= m)
+        for (int i = 0; i < c.dim; i++) if (b[rows + i] > thr) dropped++;
+      rows += (uint64_t)c.dim;
+    }
+    if (rows != m) { delete h; return CLDL_E_DIM; }
+    const uint64_t N = n + (m - dropped) + p;
+    perm.resize(N);
+    for (uint64_t k = 0; k < N; k++) perm[k] = (int)kkt_perm_or_null[k];
   }
   int rc = h->ipm.init((int)n, (int)m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones,
                        cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr, cone_params, genpow_dim2,

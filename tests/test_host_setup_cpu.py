@@ -60,6 +60,14 @@ for tag, idx, cn in [("presolve1", [3], [("nonneg", 3), ("nonneg", 3)]), ("preso
                      ("presolve3", [0, 1, 2], [("nonneg", 3), ("nonneg", 3)]), ("presolve_all", list(range(6)), [("nonneg", 3), ("nonneg", 3)])]:
     b = np.ones(2 * n); b[idx] = 1e30
     res.append(structure(tag, P, c, A, b, cn))
+# a caller-supplied KKT permutation has the length of the assembled system (presolved rows gone, expansion columns in)
+P6, c6, A6, b6, cones6 = ns.genpow_data()
+b6 = np.concatenate([b6, [1e30, 2.0]]); A6 = sp.vstack([A6, sp.csc_matrix(np.array([[1., 0, 0, 0, 0, 0], [0, 1., 0, 0, 0, 0]]))]).tocsc()
+cones6 = cones6 + [("nonneg", 2)]
+Nexp = 6 + (8 + 1) + 6
+devp = cb.CudaSolver(P6, c6, A6, b6, cones6, kkt_perm=np.arange(Nexp)[::-1].copy())
+res.append(dict(name="user_perm", N=int(devp.N), No=Nexp, same=bool(devp.N == Nexp), perm_ok=bool(np.array_equal(np.sort(devp.kkt_perm()), np.arange(Nexp))),
+                m_reduced=int(devp.m_reduced), m_reduced_o=9, symmetric=False, nnzL=0))
 print("RESULT " + json.dumps(res))
 '''
 
@@ -76,7 +84,7 @@ def results():
 
 
 @pytest.mark.parametrize("name", ["qp", "socp", "exp", "mixed", "genpow", "entropy_power_mix", "portfolio", "sdp",
-                                  "genpow_mix", "presolve1", "presolve2", "presolve3", "presolve_all"])
+                                  "genpow_mix", "presolve1", "presolve2", "presolve3", "presolve_all", "user_perm"])
 def test_kkt_structure_of_the_product_constructor_equals_the_oracle(results, name):
     r = results[name]
     assert r["same"], r
