@@ -55,6 +55,22 @@
 
 typedef int64_t idx;
 static double vnorm(const double *a, idx n);
+/* ORACLE_JITTER=<seed>: multiply the outputs of the nonsymmetric cones' arithmetic by (1 + k eps), |k| <= ORACLE_JITTER_ULP
+   (default 4), to
+   probe how sensitive the discrete decisions of the driver (backtracking counts, strategy switches, iteration
+   count) are to last-bit differences such as a GPU's libm against glibc (tests/test_oracle_nonsym.py).  Off unless
+   the variable is set. */
+static int jitter_on = -1;
+static uint64_t jitter_state = 0;
+static double jit(double x)
+{
+    if (jitter_on < 0) { const char *e = getenv("ORACLE_JITTER"); jitter_on = e ? 1 : 0; jitter_state = e ? (uint64_t)atoll(e) * 2654435761u + 88172645463325252ull : 0; }
+    if (!jitter_on) return x;
+    jitter_state ^= jitter_state << 13; jitter_state ^= jitter_state >> 7; jitter_state ^= jitter_state << 17;
+    const int64_t amp = getenv("ORACLE_JITTER_ULP") ? atoll(getenv("ORACLE_JITTER_ULP")) : 4;
+    const double k = (double)((int64_t)(jitter_state % (uint64_t)(2 * amp + 1)) - amp);
+    return x * (1.0 + k * 2.220446049250313e-16);
+}
 #include "nonsym_oracle.h"
 
 /* from qdldl_oracle.c */
@@ -617,10 +633,14 @@ static int cones_update_scaling(oipm_t *S, const double *s_, const double *z_, d
                 ns3_use_primal_dual_scaling(K, s, z, zt);
             }
             K->z[0] = z[0]; K->z[1] = z[1]; K->z[2] = z[2];
+            for (int i = 0; i < 6; i++) { K->Hs[i] = jit(K->Hs[i]); K->H_dual[i] = jit(K->H_dual[i]); }
+            for (int i = 0; i < 3; i++) K->grad[i] = jit(K->grad[i]);
         } else if (c->type == CONE_GENPOW) {      /* genpowcone.rs:149-163 */
             if (!gp_update_dual_grad_H(c->gp, z)) return 0;
             c->gp->mu = mu;
-            for (idx i = 0; i < n; i++) c->gp->z[i] = z[i];
+            for (idx i = 0; i < n; i++) { c->gp->z[i] = z[i]; c->gp->grad[i] = jit(c->gp->grad[i]); c->gp->p[i] = jit(c->gp->p[i]); }
+            for (idx i = 0; i < c->gp->dim1; i++) { c->gp->q[i] = jit(c->gp->q[i]); c->gp->d1[i] = jit(c->gp->d1[i]); }
+            for (idx i = 0; i < c->gp->dim2; i++) c->gp->r[i] = jit(c->gp->r[i]);
         }
     }
     return 1;
@@ -700,7 +720,7 @@ static void cones_combined_ds_shift(oipm_t *S, double *shift_, double *sz_, doub
             /* expcone.rs:139-148: third-order correction with the scaling-point z, inputs step_s, step_z */
             double eta[3] = {0, 0, 0};
             if (c->type == CONE_EXP) exp_higher_correction(c->ns, eta, ss, sz); else pow_higher_correction(c->ns, eta, ss, sz);
-            for (int i = 0; i < 3; i++) shift[i] = c->ns->grad[i] * sigmamu - eta[i];
+            for (int i = 0; i < 3; i++) shift[i] = jit(c->ns->grad[i] * sigmamu - eta[i]);
             continue;
         }
         if (c->type == CONE_GENPOW) { for (idx i = 0; i < n; i++) shift[i] = c->gp->grad[i] * sigmamu; continue; }   /* genpowcone.rs:208-213: no third-order term */
@@ -755,7 +775,7 @@ static double ns3_backtrack_search(const cone_t *c, const double *dq, const doub
     double a = a_init, work3[3];
     double *work = c->type == CONE_GENPOW ? c->gp->work : work3;
     for (;;) {
-        for (idx i = 0; i < c->dim; i++) work[i] = 1.0 * q[i] + a * dq[i];
+        for (idx i = 0; i < c->dim; i++) work[i] = jit(1.0 * q[i] + a * dq[i]);
         int ok = c->type == CONE_GENPOW ? (dual ? gp_is_dual_feasible(c->gp, work) : gp_is_primal_feasible(c->gp, work))
                : c->type == CONE_EXP ? (dual ? exp_is_dual_feasible(work) : exp_is_primal_feasible(work))
                                      : (dual ? pow_is_dual_feasible(work, c->ns->alpha) : pow_is_primal_feasible(work, c->ns->alpha));
@@ -841,7 +861,7 @@ static double cones_compute_barrier(oipm_t *S, const double *z_, const double *s
             double b = 0.0;
             if (c->type == CONE_EXP) { b += exp_barrier_dual(cz); b += exp_barrier_primal(cs); }
             else { b += pow_barrier_dual(cz, c->ns->alpha); b += pow_barrier_primal(cs, c->ns->alpha); }
-            barrier += b;
+            barrier += jit(b);
         } else if (c->type == CONE_GENPOW) {      /* genpowcone.rs:249-263: primal first, then dual */
             double b = 0.0, *w = c->gp->work;
             for (idx i = 0; i < n; i++) w[i] = 1.0 * s[i] + a * ds[i];
