@@ -45,3 +45,15 @@ FAKERT := tests/host_harness/libfake_cudart.so
 $(FAKERT): tests/host_harness/fake_cudart.c
 	$(CC) -O1 -fPIC -shared -Wall -o $@ $<
 all: $(FAKERT)
+
+# CUDA-on-CPU emulated build of the cone / KKT / IPM layer (test infrastructure, see tests/emu/cuda_emu.h)
+EMU     := tests/emu/libclarabel_emu.so
+EMU_GEN := tests/emu/gen/cones.cpp tests/emu/gen/cones_psd.cpp tests/emu/gen/cones_nonsym.cpp tests/emu/gen/solver.cpp
+tests/emu/gen/%.cpp: $(CSRC)/%.cu tests/emu/transform.py
+	@mkdir -p tests/emu/gen
+	python3 tests/emu/transform.py $< $@
+$(EMU): $(EMU_GEN) tests/emu/cuda_emu.cpp tests/emu/cuda_emu.h tests/emu/ldl_emu.cpp $(HDRS) $(CSRC)/cones_nonsym.cuh $(CSRC)/vec.cuh $(CPP_SRCS)
+	$(CXX) -O1 -g -std=c++17 -fPIC -shared -pthread -Wno-unknown-pragmas -Itests/emu/include -I$(CSRC) -o $@ \
+	  $(EMU_GEN) tests/emu/cuda_emu.cpp tests/emu/ldl_emu.cpp $(CPP_SRCS)
+emu: $(EMU)
+all: $(EMU)

@@ -1,0 +1,34 @@
+"""The product's cone kernels, KKT layer and IPM driver executed on the CPU.
+
+tests/emu builds clarabel.rs_b200/csrc/{cones,cones_psd,cones_nonsym,solver}.cu for the host (CUDA threads = fibers,
+see tests/emu/cuda_emu.h; the multifrontal LDL is replaced by a dense host factorisation with the same pivot rule,
+tests/emu/ldl_emu.cpp) and this test re-runs the GPU test modules of those layers against that build in a subprocess.
+It is how the code written while no GPU was available (exponential / power / generalised power cones, the
+nonsymmetric branches of the IPM loop, the inf-bound presolve) was exercised end to end before its first device run,
+and it acts as a race detector for warp-synchronous code: the emulator runs the lanes of a warp one after the other
+between synchronisation points, so a kernel that silently relies on lockstep execution computes something else (this
+is how a missing __syncwarp in the PSD Cholesky was found).  Not a statement about the GPU: the -m gpu run is."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MODULES = ["tests/test_cones_gpu.py", "tests/test_psd_gpu.py", "tests/test_ipm_gpu.py", "tests/test_zz_nonsym_gpu.py",
+           "tests/test_zz_golden.py"]
+# the dense stand-in for the LDL caps the KKT dimension at 3000
+TOO_BIG = ["tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[2000-4000-60-2]",
+           "tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[1500-2000-None-3]",
+           "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones"]
+
+
+def test_gpu_test_modules_pass_on_the_emulated_build():
+    lib = os.path.join(ROOT, "tests", "emu", "libclarabel_emu.so")
+    assert os.path.exists(lib), "tests/emu/libclarabel_emu.so missing: run `make`"
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + MODULES
+    for t in TOO_BIG:
+        cmd += ["--deselect", t]
+    out = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, CLARABEL_EMU="1"), capture_output=True, text=True, timeout=1800)
+    tail = out.stdout[-3000:]
+    assert out.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail, tail
