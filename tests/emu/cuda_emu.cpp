@@ -53,6 +53,7 @@ static const std::function<void()>* body_fn = nullptr;
 static std::vector<char> dyn;
 static std::vector<uint64_t> warp_slot;    // [nwarps][32]
 static int nthreads = 0;
+static const bool reverse_order = [] { const char* e = std::getenv("EMU_ORDER"); return e && e[0] == 'r'; }();
 
 uint3& cur_tid() { return cur ? cur->tid : g_threadIdx_dummy; }
 void* dyn_smem() { return dyn.data(); }
@@ -108,7 +109,10 @@ static void run_block() {
   for (int t = 0; t < nthreads; t++) prepare(fibers[t]);
   for (;;) {
     bool progressed = false, any_live = false;
-    for (int t = 0; t < nthreads; t++) {
+    for (int t0 = 0; t0 < nthreads; t0++) {
+      // EMU_ORDER=reverse runs the threads of a block (hence the lanes of a warp) in descending order between
+      // rendezvous points: code that is correct under the CUDA model gives the same answer either way
+      const int t = reverse_order ? nthreads - 1 - t0 : t0;
       Fiber& f = fibers[t];
       if (f.state != READY) { if (f.state != DONE) any_live = true; continue; }
       any_live = true;

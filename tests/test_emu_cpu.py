@@ -22,13 +22,19 @@ TOO_BIG = ["tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[2000-40
            "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones"]
 
 
-def test_gpu_test_modules_pass_on_the_emulated_build():
+import pytest
+
+
+@pytest.mark.parametrize("order", ["ascending", "reverse"])
+def test_gpu_test_modules_pass_on_the_emulated_build(order):
+    """`reverse` runs the threads of every block in descending order between synchronisation points: a kernel that is
+    correct under the CUDA execution model cannot tell the difference, one that relies on lockstep lanes can."""
     lib = os.path.join(ROOT, "tests", "emu", "libclarabel_emu.so")
     assert os.path.exists(lib), "tests/emu/libclarabel_emu.so missing: run `make`"
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + MODULES
     for t in TOO_BIG:
         cmd += ["--deselect", t]
-    out = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, CLARABEL_EMU="1"), capture_output=True, text=True, timeout=1800)
+    out = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, CLARABEL_EMU="1", EMU_ORDER=order), capture_output=True, text=True, timeout=1800)
     tail = out.stdout[-3000:]
     assert out.returncode == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
