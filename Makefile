@@ -46,14 +46,26 @@ $(FAKERT): tests/host_harness/fake_cudart.c
 	$(CC) -O1 -fPIC -shared -Wall -o $@ $<
 all: $(FAKERT)
 
-# CUDA-on-CPU emulated build of the cone / KKT / IPM layer (test infrastructure, see tests/emu/cuda_emu.h)
-EMU     := tests/emu/libclarabel_emu.so
-EMU_GEN := tests/emu/gen/cones.cpp tests/emu/gen/cones_psd.cpp tests/emu/gen/cones_nonsym.cpp tests/emu/gen/solver.cpp
+# CUDA-on-CPU emulated builds (test infrastructure, see tests/emu/cuda_emu.h): the .cu sources AND the csrc headers are
+# rewritten into tests/emu/gen/ (launch syntax, __shared__ storage); libclarabel_emu.so has a dense host LDL behind
+# the LDLObject interface, libclarabel_emu_full.so runs the multifrontal kernels of ldl.cu too.
+EMU      := tests/emu/libclarabel_emu.so
+EMU_FULL := tests/emu/libclarabel_emu_full.so
+EMU_HDRS := $(patsubst $(CSRC)/%,tests/emu/gen/%,$(wildcard $(CSRC)/*.h $(CSRC)/*.cuh))
+EMU_GEN  := tests/emu/gen/cones.cpp tests/emu/gen/cones_psd.cpp tests/emu/gen/cones_nonsym.cpp tests/emu/gen/solver.cpp
+EMU_FLAGS := -O1 -g -march=x86-64-v3 -ffp-contract=fast -std=c++17 -fPIC -shared -pthread -Wno-unknown-pragmas -Itests/emu/include -Itests/emu/gen -Iinclude -I$(CSRC)
 tests/emu/gen/%.cpp: $(CSRC)/%.cu tests/emu/transform.py
 	@mkdir -p tests/emu/gen
 	python3 tests/emu/transform.py $< $@
-$(EMU): $(EMU_GEN) tests/emu/cuda_emu.cpp tests/emu/cuda_emu.h tests/emu/ldl_emu.cpp $(HDRS) $(CSRC)/cones_nonsym.cuh $(CSRC)/vec.cuh $(CPP_SRCS)
-	$(CXX) -O1 -g -std=c++17 -fPIC -shared -pthread -Wno-unknown-pragmas -Itests/emu/include -I$(CSRC) -o $@ \
-	  $(EMU_GEN) tests/emu/cuda_emu.cpp tests/emu/ldl_emu.cpp $(CPP_SRCS)
-emu: $(EMU)
-all: $(EMU)
+tests/emu/gen/%.h: $(CSRC)/%.h tests/emu/transform.py
+	@mkdir -p tests/emu/gen
+	python3 tests/emu/transform.py $< $@
+tests/emu/gen/%.cuh: $(CSRC)/%.cuh tests/emu/transform.py
+	@mkdir -p tests/emu/gen
+	python3 tests/emu/transform.py $< $@
+$(EMU): $(EMU_GEN) $(EMU_HDRS) tests/emu/cuda_emu.cpp tests/emu/cuda_emu.h tests/emu/ldl_emu.cpp $(CPP_SRCS)
+	$(CXX) $(EMU_FLAGS) -o $@ $(EMU_GEN) tests/emu/cuda_emu.cpp tests/emu/ldl_emu.cpp $(CPP_SRCS)
+$(EMU_FULL): $(EMU_GEN) tests/emu/gen/ldl.cpp $(EMU_HDRS) tests/emu/cuda_emu.cpp tests/emu/cuda_emu.h $(CPP_SRCS)
+	$(CXX) $(EMU_FLAGS) -o $@ $(EMU_GEN) tests/emu/gen/ldl.cpp tests/emu/cuda_emu.cpp $(CPP_SRCS)
+emu: $(EMU) $(EMU_FULL)
+all: $(EMU) $(EMU_FULL)

@@ -678,9 +678,13 @@ __global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restr
 // No floating-point atomics: results are bit-identical to the level-synchronous kernels.
 // ------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long df_gtime() {
+#ifdef CB_EMU   /* host build of the test suite (tests/emu): no device clock */
+  return 0;
+#else
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+#endif
 }
 __device__ __forceinline__ void df_wait_zero(volatile int* p) {
   unsigned ns = 20;
@@ -1531,10 +1535,17 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
 #pragma unroll 4
     for (int k = kq; k < ns; k += 4) {
       const long long col = (long long)k * ld;
+#ifdef CB_EMU   /* host build of the test suite: the copy with zero fill, done synchronously */
+      (void)sa; (void)sb;
+      sAt[k * TS + rr] = za ? pa[col] : 0.0;
+      sBt[k * TS + rr] = zb ? pb[col] : 0.0;
+    }
+#else
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa + (unsigned)(k * TS + rr) * 8u), "l"(pa + col), "r"(za) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sb + (unsigned)(k * TS + rr) * 8u), "l"(pb + col), "r"(zb) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     if (tid < ns) sD[tid] = __ldcg(d.D + f + tid);
   }
   DF_STAMP(q, 6);
@@ -1577,7 +1588,9 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
     DF_STAMP(q, 8);
     df_ent_apply(sC, d.U, d.sc_tile_src, d.sc_tile_dst, tk[9], tk[10], pe, s_ed, s_ev, [&](int dd) -> long long { return dd; });
   }
+#ifndef CB_EMU
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
   __syncthreads();
   for (int idx = tid; idx < ns * TS; idx += DF_NT) sBt[idx] *= sD[idx >> 6];
   __syncthreads();
@@ -1625,8 +1638,10 @@ __global__ void __launch_bounds__(DF_NT, 2) k_factor_df(LDLDev d, DFFactor q) {
       const int qi = atomicAdd(q.qhead, 1);
       df_cur_qi = qi < q.ntask ? qi : -1;
       if (q.trace && df_cur_qi >= 0) {
-        unsigned smid;
+        unsigned smid = 0;
+#ifndef CB_EMU
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
         q.trace[10 * (size_t)qi] = df_gtime();
         q.trace[10 * (size_t)qi + 3] = smid;
       }

@@ -1,10 +1,15 @@
-// TEST INFRASTRUCTURE ONLY.  Fiber scheduler behind tests/emu/cuda_emu.h: one fiber per CUDA thread of the running
-// block, round-robin until every fiber has finished; __syncthreads / __syncwarp / shuffles park a fiber until its
-// block / warp has arrived.
+// TEST INFRASTRUCTURE ONLY.  Fiber scheduler behind tests/emu/cuda_emu.h.
+//
+// One fiber per CUDA thread.  Blocks of a launch run one after the other, unless the whole grid is small enough to
+// be resident at once (EMU_MAX_RESIDENT threads): then all its blocks run concurrently, which is what the persistent
+// dataflow kernels of ldl.cu need (their blocks wait on each other through counters in global memory and call
+// __nanosleep while they spin -- a yield point here).  __syncthreads / __syncwarp / shuffles / votes park a fiber
+// until its block / warp has arrived.  EMU_ORDER=reverse walks the fibers in descending order.
 #include "cuda_emu.h"
 
 #include <sys/mman.h>
 
+#include <map>
 #include <vector>
 
 extern "C" void emu_switch(void** from_sp, void* to_sp);
@@ -35,31 +40,46 @@ namespace emu {
 
 enum { READY = 0, DONE = 1, WAIT_BLOCK = 2, WAIT_WARP = 3 };
 constexpr size_t STACK_BYTES = 512 * 1024;
+constexpr int EMU_MAX_RESIDENT = 4096;
 
+struct Block {
+  uint3 idx{0, 0, 0};
+  int first = 0, nthreads = 0;               // fibers[first .. first+nthreads)
+  std::vector<char> dyn;                     // dynamic shared memory
+  std::vector<uint64_t> warp_slot;           // [nwarps][32]
+  std::map<int, void*> shared;               // static __shared__ variables by declaration site
+  ~Block() { for (auto& kv : shared) std::free(kv.second); }
+};
 struct Fiber {
   void* sp = nullptr;
   char* stack = nullptr;
   int state = DONE;
   uint3 tid{0, 0, 0};
-  int lin = 0;
+  int lin = 0;                               // linear thread index inside its block
+  Block* blk = nullptr;
 };
 
-uint3 g_blockIdx{0, 0, 0}, g_blockDim{1, 1, 1}, g_gridDim{1, 1, 1};
-uint3 g_threadIdx_dummy{0, 0, 0};
-static std::vector<Fiber> fibers;          // stacks are kept across launches
+uint3 g_blockDim{1, 1, 1}, g_gridDim{1, 1, 1};
+static uint3 zero3{0, 0, 0};
+static std::vector<Fiber> fibers;            // stacks are kept across launches
 static Fiber* cur = nullptr;
 static void* sched_sp = nullptr;
 static const std::function<void()>* body_fn = nullptr;
-static std::vector<char> dyn;
-static std::vector<uint64_t> warp_slot;    // [nwarps][32]
-static int nthreads = 0;
+static bool spun = false;                    // the running fiber yielded from a spin-wait
 static const bool reverse_order = [] { const char* e = std::getenv("EMU_ORDER"); return e && e[0] == 'r'; }();
 
-uint3& cur_tid() { return cur ? cur->tid : g_threadIdx_dummy; }
-void* dyn_smem() { return dyn.data(); }
+uint3& cur_tid() { return cur ? cur->tid : zero3; }
+uint3& cur_bid() { return cur ? cur->blk->idx : zero3; }
+void* dyn_smem() { return cur->blk->dyn.data(); }
 int lane_id() { return cur->lin & 31; }
+void* shared_slot(int id, size_t bytes) {
+  void*& p = cur->blk->shared[id];
+  if (!p) { if (posix_memalign(&p, 64, bytes ? bytes : 8)) std::abort(); std::memset(p, 0, bytes ? bytes : 8); }
+  return p;
+}
 
 static void yield_to_scheduler() { emu_switch(&cur->sp, sched_sp); }
+void spin_yield() { spun = true; yield_to_scheduler(); }
 
 static void fiber_main() {
   (*body_fn)();
@@ -76,7 +96,7 @@ static void prepare(Fiber& f) {
     f.stack = (char*)p;
   }
   uintptr_t top = ((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15;
-  void** base = (void**)(top - 64);      // 6 callee-saved registers, return address, 8 bytes of padding
+  void** base = (void**)(top - 64);          // 6 callee-saved registers, return address, 8 bytes of padding
   for (int i = 0; i < 6; i++) base[i] = nullptr;
   base[6] = (void*)&fiber_main;
   f.sp = base;
@@ -87,65 +107,70 @@ void sync_block() { cur->state = WAIT_BLOCK; yield_to_scheduler(); }
 void sync_warp() { cur->state = WAIT_WARP; yield_to_scheduler(); }
 
 uint64_t warp_exchange(uint64_t bits, int src_lane) {
+  Block* b = cur->blk;
   const int w = cur->lin >> 5;
-  warp_slot[(size_t)w * 32 + (cur->lin & 31)] = bits;
+  b->warp_slot[(size_t)w * 32 + (cur->lin & 31)] = bits;
   sync_warp();
-  const uint64_t r = warp_slot[(size_t)w * 32 + src_lane];
+  const uint64_t r = b->warp_slot[(size_t)w * 32 + src_lane];
   sync_warp();
   return r;
 }
 unsigned warp_vote(bool pred) {
+  Block* b = cur->blk;
   const int w = cur->lin >> 5;
-  warp_slot[(size_t)w * 32 + (cur->lin & 31)] = pred ? 1u : 0u;
+  b->warp_slot[(size_t)w * 32 + (cur->lin & 31)] = pred ? 1u : 0u;
   sync_warp();
   unsigned m = 0;
-  const int lo = w * 32, hi = lo + 32 < nthreads ? lo + 32 : nthreads;
-  for (int t = lo; t < hi; t++) if (fibers[t].state != DONE && warp_slot[(size_t)w * 32 + (t & 31)]) m |= 1u << (t & 31);
+  const int lo = w * 32, hi = lo + 32 < b->nthreads ? lo + 32 : b->nthreads;
+  for (int t = lo; t < hi; t++) if (fibers[b->first + t].state != DONE && b->warp_slot[(size_t)w * 32 + (t & 31)]) m |= 1u << (t & 31);
   sync_warp();
   return m;
 }
 
-static void run_block() {
-  for (int t = 0; t < nthreads; t++) prepare(fibers[t]);
+// run the fibers [0, total) (one or several blocks) to completion
+static void run_resident(std::vector<Block>& blocks, int total) {
+  for (int t = 0; t < total; t++) prepare(fibers[t]);
+  long long idle_passes = 0;
   for (;;) {
     bool progressed = false, any_live = false;
-    for (int t0 = 0; t0 < nthreads; t0++) {
-      // EMU_ORDER=reverse runs the threads of a block (hence the lanes of a warp) in descending order between
-      // rendezvous points: code that is correct under the CUDA model gives the same answer either way
-      const int t = reverse_order ? nthreads - 1 - t0 : t0;
+    for (int t0 = 0; t0 < total; t0++) {
+      const int t = reverse_order ? total - 1 - t0 : t0;
       Fiber& f = fibers[t];
       if (f.state != READY) { if (f.state != DONE) any_live = true; continue; }
       any_live = true;
-      progressed = true;
       cur = &f;
+      spun = false;
       emu_switch(&sched_sp, f.sp);
       cur = nullptr;
+      if (!spun) progressed = true;            // a fiber that only spun has not changed anything
     }
     if (!any_live) break;
-    // release complete warp rendezvous
-    const int nw = (nthreads + 31) / 32;
-    for (int w = 0; w < nw; w++) {
-      const int lo = w * 32, hi = lo + 32 < nthreads ? lo + 32 : nthreads;
-      bool all = true, some = false;
-      for (int t = lo; t < hi; t++) {
-        if (fibers[t].state == WAIT_WARP) some = true;
-        else if (fibers[t].state != DONE) all = false;
+    for (Block& b : blocks) {
+      const int nw = (b.nthreads + 31) / 32;
+      for (int w = 0; w < nw; w++) {           // complete warp rendezvous
+        const int lo = b.first + w * 32, hi = lo + 32 < b.first + b.nthreads ? lo + 32 : b.first + b.nthreads;
+        bool all = true, some = false;
+        for (int t = lo; t < hi; t++) {
+          if (fibers[t].state == WAIT_WARP) some = true;
+          else if (fibers[t].state != DONE) all = false;
+        }
+        if (some && all) { for (int t = lo; t < hi; t++) if (fibers[t].state == WAIT_WARP) fibers[t].state = READY; progressed = true; }
       }
-      if (some && all) { for (int t = lo; t < hi; t++) if (fibers[t].state == WAIT_WARP) fibers[t].state = READY; progressed = true; }
-    }
-    // release a complete block barrier
-    {
-      bool all = true, some = false;
-      for (int t = 0; t < nthreads; t++) {
+      bool all = true, some = false;           // complete block barrier
+      for (int t = b.first; t < b.first + b.nthreads; t++) {
         if (fibers[t].state == WAIT_BLOCK) some = true;
         else if (fibers[t].state != DONE) all = false;
       }
-      if (some && all) { for (int t = 0; t < nthreads; t++) if (fibers[t].state == WAIT_BLOCK) fibers[t].state = READY; progressed = true; }
+      if (some && all) { for (int t = b.first; t < b.first + b.nthreads; t++) if (fibers[t].state == WAIT_BLOCK) fibers[t].state = READY; progressed = true; }
     }
-    if (!progressed) {
-      std::fprintf(stderr, "[emu] deadlock: block (%u,%u,%u), states:", g_blockIdx.x, g_blockIdx.y, g_blockIdx.z);
-      for (int t = 0; t < nthreads && t < 64; t++) std::fprintf(stderr, " %d", fibers[t].state);
-      std::fprintf(stderr, "\n");
+    if (progressed) idle_passes = 0;
+    else if (++idle_passes > 200000) {
+      std::fprintf(stderr, "[emu] no progress: deadlock or a spin-wait nobody will satisfy (%zu resident blocks)\n", blocks.size());
+      for (Block& b : blocks) {
+        std::fprintf(stderr, "  block (%u,%u,%u):", b.idx.x, b.idx.y, b.idx.z);
+        for (int t = 0; t < b.nthreads && t < 40; t++) std::fprintf(stderr, " %d", fibers[b.first + t].state);
+        std::fprintf(stderr, "\n");
+      }
       std::abort();
     }
   }
@@ -153,24 +178,42 @@ static void run_block() {
 
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   if (cur) { std::fprintf(stderr, "[emu] nested launch\n"); std::abort(); }
-  nthreads = (int)(block.x * block.y * block.z);
-  if (nthreads <= 0 || grid.x * grid.y * grid.z == 0) return;
-  if ((int)fibers.size() < nthreads) fibers.resize(nthreads);
-  warp_slot.assign((size_t)((nthreads + 31) / 32) * 32, 0);
-  dyn.assign(smem + 64, 0);
+  const int bt = (int)(block.x * block.y * block.z);
+  const long long nblocks = (long long)grid.x * grid.y * grid.z;
+  if (bt <= 0 || nblocks == 0) return;
   body_fn = &body;
   g_blockDim = uint3{block.x, block.y, block.z};
   g_gridDim = uint3{grid.x, grid.y, grid.z};
+  const bool all_resident = nblocks * bt <= EMU_MAX_RESIDENT;
+  const int batch = all_resident ? (int)nblocks : 1;
+  if ((int)fibers.size() < batch * bt) fibers.resize((size_t)batch * bt);
+  std::vector<Block> blocks;
+  auto flush = [&]() {
+    if (blocks.empty()) return;
+    run_resident(blocks, (int)blocks.size() * bt);
+    blocks.clear();
+  };
+  blocks.reserve(batch);
   for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
-        g_blockIdx = uint3{bx, by, bz};
+        blocks.emplace_back();
+        Block& b = blocks.back();
+        b.idx = uint3{bx, by, bz};
+        b.first = ((int)blocks.size() - 1) * bt;
+        b.nthreads = bt;
+        b.dyn.assign(smem + 64, 0);
+        b.warp_slot.assign((size_t)((bt + 31) / 32) * 32, 0);
         int lin = 0;
         for (unsigned tz = 0; tz < block.z; tz++)
           for (unsigned ty = 0; ty < block.y; ty++)
-            for (unsigned tx = 0; tx < block.x; tx++, lin++) { fibers[lin].tid = uint3{tx, ty, tz}; fibers[lin].lin = lin; }
-        run_block();
+            for (unsigned tx = 0; tx < block.x; tx++, lin++) {
+              Fiber& f = fibers[b.first + lin];
+              f.tid = uint3{tx, ty, tz}; f.lin = lin; f.blk = &b;
+            }
+        if ((int)blocks.size() == batch) flush();
       }
+  flush();
   body_fn = nullptr;
 }
 

@@ -32,6 +32,8 @@ struct dim3 {
 };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
@@ -42,16 +44,18 @@ inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static          /* blocks run one after the other: one static copy is the block's copy */
+/* __shared__ declarations are rewritten by tests/emu/transform.py into per-block storage (emu::shared_slot) */
 
 // ------------------------------------------------------------------------------------------------ runtime
 namespace emu {
 struct Fiber;
 struct ThreadView { uint3 tid; };
-extern uint3 g_threadIdx_dummy;
 uint3& cur_tid();
-extern uint3 g_blockIdx, g_blockDim, g_gridDim;
+uint3& cur_bid();
+extern uint3 g_blockDim, g_gridDim;
 void* dyn_smem();
+void* shared_slot(int site, size_t bytes);   // per-block storage of one static __shared__ declaration, zeroed on first use
+void spin_yield();                           // a spin-wait lets every other resident fiber run
 void sync_block();
 void sync_warp();
 uint64_t warp_exchange(uint64_t bits, int src_lane);   // every live lane of the warp calls; returns src lane's bits
@@ -69,13 +73,14 @@ inline void run_grid_cfg(const Cfg& c, const std::function<void()>& body) { run_
 }  // namespace emu
 
 #define threadIdx (emu::cur_tid())
-#define blockIdx (emu::g_blockIdx)
+#define blockIdx (emu::cur_bid())
 #define blockDim (emu::g_blockDim)
 #define gridDim (emu::g_gridDim)
 #define warpSize 32
 
 inline void __syncthreads() { emu::sync_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync_warp(); }
+inline void __nanosleep(unsigned) { emu::spin_yield(); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 
@@ -99,6 +104,9 @@ inline unsigned __ballot_sync(unsigned, int p) { return emu::warp_vote(p != 0); 
 
 // atomics: one OS thread runs every fiber, so read-modify-write is already indivisible
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { T o = *p; *p = o - v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
@@ -109,10 +117,15 @@ inline long long __double_as_longlong(double x) { long long r; std::memcpy(&r, &
 inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dsqrt_rn(double x) { return std::sqrt(x); }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+using std::isfinite; using std::isnan; using std::isinf;
 using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::exp; using std::log; using std::pow;
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
