@@ -53,6 +53,8 @@ class cldl_opts(C.Structure):
         ("device", C.c_int32),
         ("max_panel", C.c_int32),
         ("nd_leaf", C.c_int32),
+        ("shard_nranks", C.c_int32),
+        ("shard_rank", C.c_int32),
     ]
 
 
@@ -124,6 +126,13 @@ def lib() -> C.CDLL:
     L.cldl_time_refactor_ms.restype = C.c_double
     L.cldl_time_solve_ms.argtypes = [vp, C.c_int]
     L.cldl_time_solve_ms.restype = C.c_double
+    L.cldl_shard_refactor_phase_dev.argtypes = [vp, C.c_int]
+    L.cldl_shard_solve_phase_dev.argtypes = [vp, vp, vp, C.c_int]
+    L.cldl_shard_count.argtypes = [vp, C.c_int, C.c_int]
+    L.cldl_shard_count.restype = C.c_uint64
+    L.cldl_shard_pack_dev.argtypes = [vp, C.c_int, vp, vp]
+    L.cldl_shard_unpack_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cldl_shard_counts.argtypes = [vp, u64p]
     # host-only symbolic API
     L.csym_analyse.argtypes = [C.POINTER(vp), C.c_uint64, u64p, u64p, u64p, C.c_int,
                                C.c_double, C.c_int, C.c_int]
@@ -187,12 +196,14 @@ class CudaLDLSolver:
 
     def __init__(self, n, colptr, rowval, nzval, dsigns, *, perm=None,
                  regularize_eps=1e-13, regularize_delta=2e-7, regularize_enable=True,
-                 amd_dense_scale=1.5, ordering=ORDER_BEST, device=0, max_panel=0, nd_leaf=0):
+                 amd_dense_scale=1.5, ordering=ORDER_BEST, device=0, max_panel=0, nd_leaf=0,
+                 shard_nranks=0, shard_rank=0):
         L = lib()
         self._L = L
         self.n = int(n)
         o = cldl_opts()
         L.cldl_default_opts(C.byref(o))
+        o.shard_nranks, o.shard_rank = int(shard_nranks), int(shard_rank)
         o.regularize_eps, o.regularize_delta = regularize_eps, regularize_delta
         o.regularize_enable = 1 if regularize_enable else 0
         o.amd_dense_scale, o.ordering, o.device = amd_dense_scale, ordering, device
@@ -317,6 +328,175 @@ class SymbolicAnalysis:
             L.csym_free(h)
 
 
+class _DevBuf:
+    """f64 device buffer for the sharded driver: a torch CUDA tensor, or (emulated build of the test-suite, where
+    device memory is host memory) a numpy array."""
+
+    def __init__(self, n, device, host=None):
+        n = max(int(n), 1)
+        self._torch = None
+        if os.environ.get("CLARABEL_EMU") == "1":
+            self.a = np.zeros(n) if host is None else np.ascontiguousarray(host, dtype=np.float64).copy()
+            self.ptr = self.a.ctypes.data
+        else:
+            import torch
+            self._torch = torch
+            dev = torch.device("cuda", int(device))
+            self.a = torch.zeros(n, dtype=torch.float64, device=dev) if host is None else \
+                torch.as_tensor(np.ascontiguousarray(host, dtype=np.float64), device=dev).clone()
+            self.ptr = self.a.data_ptr()
+
+    def to(self, device):
+        """copy on another device (same object when it already lives there / in the emulated build)"""
+        if self._torch is None or self.a.device.index == int(device):
+            return self
+        out = _DevBuf.__new__(_DevBuf)
+        out._torch = self._torch
+        out.a = self.a.to(self._torch.device("cuda", int(device)))
+        out.ptr = out.a.data_ptr()
+        return out
+
+    def numpy(self):
+        return self.a.copy() if self._torch is None else self.a.cpu().numpy()
+
+
+class ShardedLDLGroup:
+    """ONE factorisation split over several ranks, all driven from this process.
+
+    Every rank is its own handle (`cldl_opts.shard_rank`), on its own GPU when `devices` names several, on the same
+    GPU otherwise (which exercises exactly the same phases and exchanges -- the way the single-GPU test box checks the
+    sharded path).  The exchanges between the phases are device-to-device copies here; with one process per GPU they
+    are `torch.distributed` all-gathers of the same packed buffers (`ShardedLDLRank`).
+    """
+
+    def __init__(self, n, colptr, rowval, nzval, dsigns, nranks, devices=None, **kw):
+        self.n, self.nranks = int(n), int(nranks)
+        self.devices = list(devices) if devices is not None else [0] * self.nranks
+        self.ranks = [CudaLDLSolver(n, colptr, rowval, nzval, dsigns, device=self.devices[r], shard_nranks=self.nranks,
+                                    shard_rank=r, **kw) for r in range(self.nranks)]
+        self._L = self.ranks[0]._L
+
+    def _sync_streams(self):
+        if os.environ.get("CLARABEL_EMU") != "1":
+            import torch
+            for d in set(self.devices):
+                torch.cuda.synchronize(d)
+
+    def _exchange(self, what, xs=None):
+        L = self._L
+        bufs = []
+        for r, s in enumerate(self.ranks):
+            cnt = int(L.cldl_shard_count(s._h, what, r))
+            b = _DevBuf(cnt, self.devices[r])
+            _check(L.cldl_shard_pack_dev(s._h, what, b.ptr, xs[r].ptr if xs else None), "shard_pack")
+            bufs.append(b)
+        self._sync_streams()
+        for g, s in enumerate(self.ranks):
+            for r in range(self.nranks):
+                if r != g:
+                    src = bufs[r].to(self.devices[g])
+                    _check(L.cldl_shard_unpack_dev(s._h, what, r, src.ptr, xs[g].ptr if xs else None), "shard_unpack")
+        self._sync_streams()
+
+    def refactor(self):
+        L = self._L
+        for s in self.ranks:
+            _check(L.cldl_shard_refactor_phase_dev(s._h, 0), "refactor phase 0")
+        self._exchange(0)
+        for s in self.ranks:
+            _check(L.cldl_shard_refactor_phase_dev(s._h, 1), "refactor phase 1")
+        ok = True
+        for s in self.ranks:
+            ok = bool(_check(L.cldl_sync_status(s._h), "sync_status")) and ok
+        return ok
+
+    def solve(self, b):
+        L = self._L
+        bs = [_DevBuf(self.n, d, host=b) for d in self.devices]
+        xs = [_DevBuf(self.n, d) for d in self.devices]
+        for s, x, bb in zip(self.ranks, xs, bs):
+            _check(L.cldl_shard_solve_phase_dev(s._h, x.ptr, bb.ptr, 0), "solve phase 0")
+        self._exchange(1)
+        for s, x, bb in zip(self.ranks, xs, bs):
+            _check(L.cldl_shard_solve_phase_dev(s._h, x.ptr, bb.ptr, 1), "solve phase 1")
+        self._exchange(2, xs)
+        return [x.numpy()[:self.n] for x in xs]
+
+    def counts(self):
+        """global (regularize_count, positive_inertia): owned parts of every rank + the top part once"""
+        out = []
+        for s in self.ranks:
+            c = np.zeros(4, dtype=np.uint64)
+            _check(self._L.cldl_shard_counts(s._h, _p(c, C.c_uint64)), "shard_counts")
+            out.append(c.astype(np.int64))
+        top = out[0][2:] - out[0][:2]
+        tot = sum(c[:2] for c in out) + top
+        return int(tot[0]), int(tot[1])
+
+    def perm(self):
+        return self.ranks[0].perm()
+
+    def close(self):
+        for s in self.ranks:
+            s.close()
+
+
+class ShardedLDLRank:
+    """One rank of a sharded factorisation in a `torch.distributed` job (one process per GPU; NCCL over NVLink, or
+    gloo on host buffers in the emulated build of the test-suite).  The exchanges between the phases are all-gathers of
+    the packed contributions, padded to the largest one: update matrices of the cut roots per refactor, their update
+    vectors per solve, and the solution entries every rank computed -- the all-gather of x the north star names."""
+
+    def __init__(self, n, colptr, rowval, nzval, dsigns, device=0, **kw):
+        import torch.distributed as dist
+        self._dist = dist
+        self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
+        self.n, self.device = int(n), device
+        self.solver = CudaLDLSolver(n, colptr, rowval, nzval, dsigns, device=device, shard_nranks=self.nranks,
+                                    shard_rank=self.rank, **kw)
+        self._L = self.solver._L
+        self._counts = [[int(self._L.cldl_shard_count(self.solver._h, w, r)) for r in range(self.nranks)] for w in range(3)]
+
+    def _tensor(self, buf):
+        import torch
+        return buf.a if buf._torch is not None else torch.from_numpy(buf.a)
+
+    def _exchange(self, what, x=None):
+        import torch
+        L, h = self._L, self.solver._h
+        mx = max(max(self._counts[what]), 1)
+        mine = _DevBuf(mx, self.device)
+        _check(L.cldl_shard_pack_dev(h, what, mine.ptr, x.ptr if x is not None else None), "shard_pack")
+        if mine._torch is not None:
+            torch.cuda.synchronize(self.device)
+        allb = _DevBuf(mx * self.nranks, self.device)
+        self._dist.all_gather_into_tensor(self._tensor(allb), self._tensor(mine))
+        for r in range(self.nranks):
+            if r != self.rank:
+                _check(L.cldl_shard_unpack_dev(h, what, r, allb.ptr + 8 * mx * r, x.ptr if x is not None else None), "shard_unpack")
+        if mine._torch is not None:
+            torch.cuda.synchronize(self.device)
+
+    def refactor(self):
+        L, h = self._L, self.solver._h
+        _check(L.cldl_shard_refactor_phase_dev(h, 0), "refactor phase 0")
+        self._exchange(0)
+        _check(L.cldl_shard_refactor_phase_dev(h, 1), "refactor phase 1")
+        return bool(_check(L.cldl_sync_status(h), "sync_status"))
+
+    def solve(self, b):
+        L, h = self._L, self.solver._h
+        bb, x = _DevBuf(self.n, self.device, host=b), _DevBuf(self.n, self.device)
+        _check(L.cldl_shard_solve_phase_dev(h, x.ptr, bb.ptr, 0), "solve phase 0")
+        self._exchange(1)
+        _check(L.cldl_shard_solve_phase_dev(h, x.ptr, bb.ptr, 1), "solve phase 1")
+        self._exchange(2, x)
+        return x.numpy()[:self.n]
+
+    def close(self):
+        self.solver.close()
+
+
 def shard_plan(sym, nranks):
     """Subtree-to-rank mapping of one factorisation (csrc/symbolic.h ShardPlan): owner[s] = rank that
     factors front s, -1 for the replicated top part; plus the flop split, what crosses ranks per refactor / solve and
@@ -410,6 +590,8 @@ EXPORTED_SYMBOLS += [
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
     "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_create_gp",
+    "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
+    "cldl_shard_unpack_dev", "cldl_shard_counts",
 ]
 
 _l2_ready = False

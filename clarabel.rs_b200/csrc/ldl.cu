@@ -1750,6 +1750,21 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   if (rc == -3) return CLDL_E_NOT_TRIU;
   if (rc == -5) return CLDL_E_BAD_PERM;
   if (rc) return CLDL_E_ARG;
+  shard_nranks = o.shard_nranks > 1 ? o.shard_nranks : 1;
+  shard_rank = o.shard_rank;
+  if (sharded()) {
+    if (shard_rank < 0 || shard_rank >= shard_nranks) return CLDL_E_ARG;
+    std::vector<int> par(S.sn_parent);
+    if (plan_shards(S.nsup, S.sn_first.data(), S.sn_rowptr.data(), par.data(), shard_nranks, shard)) return CLDL_E_ARG;
+    shard_cut.assign(shard_nranks, {});
+    shard_xidx.assign(shard_nranks, {});
+    for (int s = 0; s < S.nsup; s++) {
+      const int g = shard.owner[s];
+      if (g < 0) continue;
+      if (S.sn_parent[s] >= 0 && shard.owner[S.sn_parent[s]] < 0) shard_cut[g].push_back(s);
+      for (int j = S.sn_first[s]; j < S.sn_first[s + 1]; j++) shard_xidx[g].push_back(S.perm[j]);
+    }
+  }
 
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
@@ -1879,10 +1894,12 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     int b = S.level_ptr[l], e = S.level_ptr[l + 1];
     std::vector<int> order[4];
     const size_t big0 = big_tasks.size(), tile0 = tiles.size();
+    std::vector<int> not_mine;       // sharded: fronts of other ranks are parked at the end of the level's range
     for (int t = b; t < e; t++) {
       const int s = S.level_tasks[t];
       const long long ns = S.sn_first[s + 1] - S.sn_first[s];
       const long long nr = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+      if (!mine(s) && !(nr >= CB_BIG_NR && ns <= CB_PB_MAXNS)) { not_mine.push_back(s); continue; }
       if (nr >= CB_BIG_NR && ns <= CB_PB_MAXNS) {
         big_tasks.push_back(s);
         const int nt = (int)((nr + TS - 1) / TS);
@@ -1908,6 +1925,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       for (int s : order[c]) S.level_tasks[pos++] = s;
     }
     for (size_t k = big0; k < big_tasks.size(); k++) S.level_tasks[pos++] = big_tasks[k];
+    for (int s : not_mine) S.level_tasks[pos++] = s;
     if (big_tasks.size() > big0) {
       LaunchSeg seg;
       seg.kind = 1; seg.level = l; seg.base = (int)big0; seg.count = (int)(big_tasks.size() - big0);
@@ -2127,24 +2145,33 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   // dataflow solve plan: tasks in level order; narrow fronts batched 8 per task
   {
     std::vector<int> t_first, t_cnt, t_kind, fronts, f2t(S.nsup, -1);
-    std::vector<std::vector<int>> lev_small(S.nlevels), lev_big(S.nlevels);
-    for (int s = 0; s < S.nsup; s++) {
-      const int ns = S.sn_first[s + 1] - S.sn_first[s];
-      (ns <= CB_SOLVE_SMALL_NS ? lev_small : lev_big)[S.sn_level[s]].push_back(s);
-    }
+    // sharded: the tasks of the owned subtrees come first (in level order), then the tasks of the replicated top part
+    // (in level order); fronts of other ranks get no task.  The forward sweep is launched once per phase with the
+    // cut roots' update vectors exchanged in between; the backward sweep walks the same list from the end in one
+    // launch (top first, then the owned subtrees: its dependencies point upwards only).
     const int per = SV_NT / 32;
-    for (int l = 0; l < S.nlevels; l++) {
-      for (size_t i = 0; i < lev_small[l].size(); i += per) {
-        const int c = (int)std::min<size_t>(per, lev_small[l].size() - i);
-        t_first.push_back((int)fronts.size()); t_cnt.push_back(c); t_kind.push_back(0);
-        for (int k = 0; k < c; k++) { f2t[lev_small[l][i + k]] = (int)t_first.size() - 1; fronts.push_back(lev_small[l][i + k]); }
+    for (int ph = 0; ph < (sharded() ? 2 : 1); ph++) {
+      if (ph == 1) df_ntask_owned = (int)t_first.size();
+      std::vector<std::vector<int>> lev_small(S.nlevels), lev_big(S.nlevels);
+      for (int s = 0; s < S.nsup; s++) {
+        if (sharded() && (ph == 0 ? !owned(s) : shard.owner[s] >= 0)) continue;
+        const int ns = S.sn_first[s + 1] - S.sn_first[s];
+        (ns <= CB_SOLVE_SMALL_NS ? lev_small : lev_big)[S.sn_level[s]].push_back(s);
       }
-      for (int s : lev_big[l]) {
-        t_first.push_back((int)fronts.size()); t_cnt.push_back(1); t_kind.push_back(1);
-        f2t[s] = (int)t_first.size() - 1; fronts.push_back(s);
+      for (int l = 0; l < S.nlevels; l++) {
+        for (size_t i = 0; i < lev_small[l].size(); i += per) {
+          const int c = (int)std::min<size_t>(per, lev_small[l].size() - i);
+          t_first.push_back((int)fronts.size()); t_cnt.push_back(c); t_kind.push_back(0);
+          for (int k = 0; k < c; k++) { f2t[lev_small[l][i + k]] = (int)t_first.size() - 1; fronts.push_back(lev_small[l][i + k]); }
+        }
+        for (int s : lev_big[l]) {
+          t_first.push_back((int)fronts.size()); t_cnt.push_back(1); t_kind.push_back(1);
+          f2t[s] = (int)t_first.size() - 1; fronts.push_back(s);
+        }
       }
     }
     const int nt = (int)t_first.size();
+    if (!sharded()) df_ntask_owned = nt;
     // chain children of wide fronts (followed block by block instead of awaited), block owners for the
     // backward sweep
     std::vector<int> chain_child(S.nsup, -1), col2sn(n, 0), blk_ptr(S.nsup + 1, 0), blk_owner;
@@ -2170,9 +2197,14 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     std::vector<int> pend(nt, 0);
     for (int s = 0; s < S.nsup; s++) {
       const int p = S.sn_parent[s];
-      if (p >= 0 && chain_child[p] != s) pend[f2t[p]]++;
+      if (p >= 0 && chain_child[p] != s && mine(s)) pend[f2t[p]]++;   // another rank's front is complete before its parent's phase starts
     }
     int* t1 = nullptr;
+    if (sharded()) {   // progress counters of the forward sweep: the other ranks' fronts count as finished
+      std::vector<int> prog0(S.nsup, 0);
+      for (int s = 0; s < S.nsup; s++) if (!mine(s)) prog0[s] = 1 << 28;
+      if ((rc = upload(&t1, prog0))) return rc; d_prog_init = t1;
+    }
     if ((rc = upload(&t1, t_first))) return rc; df.task_first = t1;
     if ((rc = upload(&t1, t_cnt))) return rc; df.task_cnt = t1;
     if ((rc = upload(&t1, t_kind))) return rc; df.task_kind = t1;
@@ -2236,7 +2268,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     for (int s = 0; s < S.nsup; s++) {
       const int p = S.sn_parent[s];
       const bool presolved = (S.sn_level[s] == 0 && !is_big(s));
-      if (p >= 0 && !presolved) pend[p]++;
+      if (p >= 0 && !presolved && mine(s)) pend[p]++;   // sharded: another rank's front is complete before the top phase starts
     }
     auto push_task = [&](int kind, int s, int a, int b, int d0, int d1, int e0, int e1) {
       const size_t o = tk.size();
@@ -2266,9 +2298,15 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       t[10] = rl[a0];
       t[11] = rl[b0];
     };
-    std::vector<std::vector<int>> lev(S.nlevels);
-    for (int s = 0; s < S.nsup; s++) lev[S.sn_level[s]].push_back(s);
+    // sharded: tasks of the owned subtrees first, then the tasks of the top part; nothing for other ranks' fronts
     std::vector<int> kidsbuf, tp;
+    for (int ph = 0; ph < (sharded() ? 2 : 1); ph++) {
+    if (ph == 1) dff_ntask_owned = (int)(tk.size() / 16);
+    std::vector<std::vector<int>> lev(S.nlevels);
+    for (int s = 0; s < S.nsup; s++) {
+      if (sharded() && (ph == 0 ? !owned(s) : shard.owner[s] >= 0)) continue;
+      lev[S.sn_level[s]].push_back(s);
+    }
     for (int l = 0; l < S.nlevels; l++) {
       for (int s : lev[l]) if (!is_big(s) && l > 0) push_task(0, s, 0, 0, 0, 0, 0, 0);
       // the children of a big front that go through child records (the small ones use the sorted entry lists)
@@ -2340,7 +2378,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
           }
       }
     }
+    }
     dff.ntask = (int)(tk.size() / 16);
+    if (!sharded()) dff_ntask_owned = dff.ntask;
     int4* t4 = nullptr;
     CK(cudaMalloc((void**)&t4, (tk.size() ? tk.size() : 16) * sizeof(int)));
     if (!tk.empty()) CK(cudaMemcpy(t4, tk.data(), tk.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -2369,12 +2409,19 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     }
   }
   cb_tmark("ldl: solve plan");
+  if (sharded()) {
+    d_shard_xidx.assign(shard_nranks, nullptr);
+    for (int g = 0; g < shard_nranks; g++) { int* t1 = nullptr; if ((rc = upload(&t1, shard_xidx[g]))) return rc; d_shard_xidx[g] = t1; }
+  }
   factored = false;
   return CLDL_OK;
 }
 
 void LDLObject::release() {
   cudaSetDevice(device);
+  for (int* p : d_shard_xidx) if (p) cudaFree(p);
+  d_shard_xidx.clear();
+  if (d_prog_init) { cudaFree(d_prog_init); d_prog_init = nullptr; }
   auto fr = [](const void* p) { if (p) cudaFree((void*)p); };
   fr(dev.sn_first); fr(dev.sn_rowptr); fr(dev.sn_rows); fr(dev.child_ptr); fr(dev.child_list);
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
@@ -2391,6 +2438,7 @@ void LDLObject::release() {
 }
 
 int LDLObject::refactor_async() {
+  if (sharded()) return CLDL_E_ARG;   // one rank of a sharded factorisation: use the phase entry points
   CK(cudaSetDevice(device));
   CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
   if (factor_dataflow) {
@@ -2460,6 +2508,7 @@ int LDLObject::join_slot1() {
 }
 
 int LDLObject::solve_async(double* d_x, const double* d_b, int slot, bool half) {
+  if (sharded()) return CLDL_E_ARG;
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
   if (use_dataflow) {
@@ -2506,6 +2555,143 @@ int LDLObject::solve_async(double* d_x, const double* d_b, int slot, bool half) 
     if (g.nsmall) k_bwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp, d_x);
   }
   CK(cudaGetLastError());
+  return CLDL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One factorisation on several GPUs.  This object is one rank: it owns some subtrees of the assembly tree
+// and replicates the top part above the cut.  Both dataflow queues list the owned tasks first, then the top tasks:
+//   refactor phase 0  level-0 kernel + k_factor_df over the owned tasks
+//            exchange the update matrix of every cut root goes to every rank (shard_pack / shard_unpack, what = 0)
+//            phase 1  k_factor_df continues with the top tasks (queue head preset to the first of them)
+//   solve    phase 0  permute b, forward sweep over the owned tasks
+//            exchange update vectors of the cut roots (what = 1)
+//            phase 1  forward sweep over the top tasks, backward sweep over everything (its dependencies point upwards)
+//            exchange every rank's own x entries (what = 2): the all-gather of the solution the north star names
+// The kernels are the single-GPU ones; only the host-side task lists, counter initialisation and launch sequence differ.
+__global__ void k_gather_idx(int n, const int* __restrict__ idx, const double* __restrict__ x, double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = x[idx[i]];
+}
+__global__ void k_scatter_idx(int n, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[idx[i]] = buf[i];
+}
+
+int LDLObject::refactor_phase_async(int phase) {
+  if (!sharded() || !factor_dataflow) return CLDL_E_ARG;
+  CK(cudaSetDevice(device));
+  if (phase == 0) {
+    CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
+    CK(cudaMemcpyAsync(d_dff_cnt, d_dff_init, dff_nsup4 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(dff.qhead, 0, sizeof(int), stream));
+    for (const LaunchSeg& g : plan) {
+      if (g.level != 0 || g.kind != 0 || g.count == 0) continue;
+      g_launches++;
+      if (g.threads == 64)
+        k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
+      else
+        k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
+    }
+    DFFactor q = dff;
+    q.ntask = dff_ntask_owned;
+    g_launches++;
+    k_factor_df<<<dff_grid, DF_NT, (size_t)DF_SMEM_DOUBLES * 8, stream>>>(dev, q);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    shard_count_owned[0] = (uint64_t)h_status[ST_REGCOUNT];
+    shard_count_owned[1] = (uint64_t)h_status[ST_POSINERTIA];
+    factored = false;
+    return CLDL_OK;
+  }
+  h_phase_start[0] = dff_ntask_owned;
+  CK(cudaMemcpyAsync(dff.qhead, &h_phase_start[0], sizeof(int), cudaMemcpyHostToDevice, stream));
+  g_launches++;
+  k_factor_df<<<dff_grid, DF_NT, (size_t)DF_SMEM_DOUBLES * 8, stream>>>(dev, dff);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  factored = true;
+  return CLDL_OK;
+}
+
+int LDLObject::solve_phase_async(double* d_x, const double* d_b, int phase) {
+  if (!sharded() || !use_dataflow) return CLDL_E_ARG;
+  if (!factored) return CLDL_E_NOT_FACTORED;
+  CK(cudaSetDevice(device));
+  DFPlan qv = df;
+  auto sweep = [&](bool fwd, const DFPlan& q) {
+    g_launches++;
+    if (solve_minb == 2) { if (fwd) k_solve_df<true, 2><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); else k_solve_df<false, 2><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); }
+    else if (solve_minb == 3) { if (fwd) k_solve_df<true, 3><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); else k_solve_df<false, 3><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); }
+    else { if (fwd) k_solve_df<true, 4><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); else k_solve_df<false, 4><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); }
+  };
+  if (phase == 0) {
+    g_launches++;
+    k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
+    CK(cudaMemcpyAsync(qv.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(qv.done, 0, (size_t)S.nsup * sizeof(int), stream));
+    CK(cudaMemcpyAsync(qv.prog, d_prog_init, (size_t)S.nsup * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(qv.qhead, 0, 2 * sizeof(int), stream));
+    qv.ntask = df_ntask_owned;
+    sweep(true, qv);
+  } else {
+    h_phase_start[1] = df_ntask_owned;
+    CK(cudaMemcpyAsync(qv.qhead, &h_phase_start[1], sizeof(int), cudaMemcpyHostToDevice, stream));
+    sweep(true, qv);
+    sweep(false, qv);
+  }
+  CK(cudaGetLastError());
+  return CLDL_OK;
+}
+
+uint64_t LDLObject::shard_count(int what, int rank) const {
+  if (!sharded() || rank < 0 || rank >= shard_nranks) return 0;
+  if (what == 2) return (uint64_t)shard_xidx[rank].size();
+  uint64_t t = 0;
+  for (int c : shard_cut[rank]) {
+    const uint64_t nr = (uint64_t)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
+    t += what == 0 ? nr * nr : nr;
+  }
+  return t;
+}
+// my contribution -> d_buf (contiguous, in the order of shard_cut[rank] / shard_xidx[rank])
+int LDLObject::shard_pack(int what, double* d_buf, const double* d_x) {
+  if (!sharded()) return CLDL_E_ARG;
+  CK(cudaSetDevice(device));
+  if (what == 2) {
+    const int cnt = (int)shard_xidx[shard_rank].size();
+    if (cnt) { g_launches++; k_gather_idx<<<(cnt + 255) / 256, 256, 0, stream>>>(cnt, d_shard_xidx[shard_rank], d_x, d_buf); }
+    return CLDL_OK;
+  }
+  size_t off = 0;
+  for (int c : shard_cut[shard_rank]) {
+    const size_t nr = (size_t)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
+    const size_t len = what == 0 ? nr * nr : nr;
+    const double* src = what == 0 ? dev.U + S.upd_off[c] : dev.u + S.sn_rowptr[c];
+    if (len) CK(cudaMemcpyAsync(d_buf + off, src, len * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    off += len;
+  }
+  return CLDL_OK;
+}
+// rank `rank`'s contribution (as packed there) -> this rank's arena / update vectors / x
+int LDLObject::shard_unpack(int what, int rank, const double* d_buf, double* d_x) {
+  if (!sharded() || rank < 0 || rank >= shard_nranks) return CLDL_E_ARG;
+  if (rank == shard_rank) return CLDL_OK;
+  CK(cudaSetDevice(device));
+  if (what == 2) {
+    const int cnt = (int)shard_xidx[rank].size();
+    if (cnt) { g_launches++; k_scatter_idx<<<(cnt + 255) / 256, 256, 0, stream>>>(cnt, d_shard_xidx[rank], d_buf, d_x); }
+    return CLDL_OK;
+  }
+  size_t off = 0;
+  for (int c : shard_cut[rank]) {
+    const size_t nr = (size_t)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
+    const size_t len = what == 0 ? nr * nr : nr;
+    double* dst = what == 0 ? dev.U + S.upd_off[c] : dev.u + S.sn_rowptr[c];
+    if (len) CK(cudaMemcpyAsync(dst, d_buf + off, len * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    off += len;
+  }
   return CLDL_OK;
 }
 
@@ -2718,6 +2904,18 @@ int cldl_solve_dev(cldl_t* h, double* d_x, const double* d_b) {
   return h ? h->obj.solve_async(d_x, d_b) : CLDL_E_ARG;
 }
 int cldl_sync_status(cldl_t* h) { return h ? h->obj.sync_status() : CLDL_E_ARG; }
+// ---- one factorisation on several GPUs: device-pointer phase API (see clarabel_b200.h) ----
+int cldl_shard_refactor_phase_dev(cldl_t* h, int phase) { return h ? h->obj.refactor_phase_async(phase) : CLDL_E_ARG; }
+int cldl_shard_solve_phase_dev(cldl_t* h, double* d_x, const double* d_b, int phase) { return h ? h->obj.solve_phase_async(d_x, d_b, phase) : CLDL_E_ARG; }
+uint64_t cldl_shard_count(const cldl_t* h, int what, int rank) { return h ? h->obj.shard_count(what, rank) : 0; }
+int cldl_shard_pack_dev(cldl_t* h, int what, double* d_buf, const double* d_x) { return h ? h->obj.shard_pack(what, d_buf, d_x) : CLDL_E_ARG; }
+int cldl_shard_unpack_dev(cldl_t* h, int what, int rank, const double* d_buf, double* d_x) { return h ? h->obj.shard_unpack(what, rank, d_buf, d_x) : CLDL_E_ARG; }
+int cldl_shard_counts(const cldl_t* h, uint64_t* out4) {
+  if (!h || !out4) return CLDL_E_ARG;
+  out4[0] = h->obj.shard_count_owned[0]; out4[1] = h->obj.shard_count_owned[1];
+  out4[2] = h->obj.regularize_count; out4[3] = h->obj.positive_inertia;
+  return CLDL_OK;
+}
 void* cldl_stream(cldl_t* h) { return h ? (void*)h->obj.stream : nullptr; }
 double* cldl_values_dev(cldl_t* h) { return h ? h->obj.dev.vals : nullptr; }
 

@@ -144,6 +144,25 @@ class LDLObject {
   std::vector<int> h_idx;
   bool factored = false;
   uint64_t regularize_count = 0, positive_inertia = 0;
+  // ---- one factorisation on several GPUs: this object is one rank (see ShardPlan in symbolic.h) ----
+  int shard_nranks = 1, shard_rank = 0;
+  ShardPlan shard;                       // owner[front] = rank or -1 (replicated top)
+  std::vector<std::vector<int>> shard_cut;   // per rank: its cut roots (fronts whose parent is in the top part)
+  std::vector<std::vector<int>> shard_xidx;  // per rank: caller-order indices of the x entries it computes
+  std::vector<int*> d_shard_xidx;            // the same lists on the device
+  int dff_ntask_owned = 0, df_ntask_owned = 0;   // tasks of the owned phase (they come first in both queues)
+  int* d_prog_init = nullptr;            // forward solve: progress counters with the other ranks' fronts pre-completed
+  int h_phase_start[2] = {0, 0};         // pinned-lifetime host copies of the queue heads the top phases start from
+  uint64_t shard_count_owned[2] = {0, 0};    // regularize_count / positive_inertia of the owned phase
+  bool sharded() const { return shard_nranks > 1; }
+  bool mine(int s) const { return !sharded() || shard.owner[s] == shard_rank || shard.owner[s] < 0; }
+  bool owned(int s) const { return !sharded() || shard.owner[s] == shard_rank; }
+  int refactor_phase_async(int phase);   // 0: owned subtrees, 1: top part (after the cut roots' update matrices arrived)
+  int solve_phase_async(double* d_x, const double* d_b, int phase);   // 0: permute + forward owned, 1: forward top + backward
+  // what: 0 update matrices of the cut roots (per refactor), 1 their update vectors (per solve), 2 x entries
+  uint64_t shard_count(int what, int rank) const;
+  int shard_pack(int what, double* d_buf, const double* d_x);
+  int shard_unpack(int what, int rank, const double* d_buf, double* d_x);
 
   int init(int n, const int64_t* Ap, const int32_t* Ai, const double* Ax, const int8_t* dsigns,
            const cldl_opts& o, const int* perm_in);

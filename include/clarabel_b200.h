@@ -55,6 +55,9 @@ typedef struct {
   int32_t device;           /* CUDA device ordinal                                    */
   int32_t max_panel;        /* 0 = default                                            */
   int32_t nd_leaf;          /* 0 = default                                            */
+  /* one factorisation on several GPUs: this handle is rank `shard_rank` of `shard_nranks`; it factors
+   * and solves the subtrees it owns plus the replicated top of the assembly tree.  0 / 1 ranks = whole tree. */
+  int32_t shard_nranks, shard_rank;
 } cldl_opts;
 
 /* LinearSolverInfo (kktsolvers/mod.rs:24-38) + factorisation counters
@@ -118,6 +121,27 @@ int cldl_solve_dev(cldl_t *h, double *d_x, const double *d_b);
 int cldl_sync_status(cldl_t *h);                             /* sync + refactor verdict (1/0/neg) */
 void *cldl_stream(cldl_t *h);                                /* cudaStream_t */
 double *cldl_values_dev(cldl_t *h);                          /* device copy of nzval, caller order */
+
+/* ---- one factorisation on several GPUs (cldl_opts.shard_nranks > 1) ----
+ * Every rank creates its handle from the same matrix with its own shard_rank; the symbolic analysis and the
+ * subtree-to-rank plan are deterministic, so all ranks agree on them.  A rank factors / solves the subtrees it owns
+ * and the replicated top of the assembly tree; between the two phases the caller moves the packed contributions of
+ * every rank to every other rank (NCCL all-gather / broadcast over NVLink, or plain copies when the handles share a
+ * device) -- the library only packs and unpacks DEVICE buffers:
+ *   what = 0  update matrices of the rank's cut roots   (between the refactor phases)
+ *   what = 1  update vectors of the rank's cut roots    (between the solve phases)
+ *   what = 2  the x entries the rank computed           (after solve phase 1: the all-gather of the solution)
+ * cldl_shard_count(h, what, r) = doubles rank r contributes.  cldl_refactor / cldl_solve refuse on such a handle.
+ *   refactor:  phase 0 on every rank -> pack(0) -> exchange -> unpack(0, r) for r != me -> phase 1 -> cldl_sync_status
+ *   solve:     phase 0 -> pack(1) -> exchange -> unpack(1, r) -> phase 1 -> pack(2, x) -> exchange -> unpack(2, r, x)
+ * cldl_shard_counts: {regularize_count, positive_inertia} of the owned phase, then of owned + top (after
+ * cldl_sync_status); the global count is sum_r owned_r + (total_0 - owned_0). */
+int cldl_shard_refactor_phase_dev(cldl_t *h, int phase);
+int cldl_shard_solve_phase_dev(cldl_t *h, double *d_x, const double *d_b, int phase);
+uint64_t cldl_shard_count(const cldl_t *h, int what, int rank);
+int cldl_shard_pack_dev(cldl_t *h, int what, double *d_buf, const double *d_x);
+int cldl_shard_unpack_dev(cldl_t *h, int what, int rank, const double *d_buf, double *d_x);
+int cldl_shard_counts(const cldl_t *h, uint64_t *out4);
 
 /* timing helper for benches: runs `reps` refactors (or solves) back to back
  * on the device and returns the average milliseconds measured with CUDA

@@ -138,6 +138,11 @@ int LDLObject::solve_async(double* d_x, const double* d_b, int, bool) {
   return CLDL_OK;
 }
 
+int LDLObject::refactor_phase_async(int) { return CLDL_E_ARG; }
+int LDLObject::solve_phase_async(double*, const double*, int) { return CLDL_E_ARG; }
+uint64_t LDLObject::shard_count(int, int) const { return 0; }
+int LDLObject::shard_pack(int, double*, const double*) { return CLDL_E_ARG; }
+int LDLObject::shard_unpack(int, int, const double*, double*) { return CLDL_E_ARG; }
 int LDLObject::ensure_tmp(size_t) { return 0; }
 int LDLObject::stage_index(const uint64_t*, uint64_t) { return 0; }
 
@@ -170,4 +175,10 @@ void* cldl_stream(cldl_t*) { return nullptr; }
 double* cldl_values_dev(cldl_t*) { return nullptr; }
 double cldl_time_refactor_ms(cldl_t*, int) { return -1.0; }
 double cldl_time_solve_ms(cldl_t*, int) { return -1.0; }
+int cldl_shard_refactor_phase_dev(cldl_t*, int) { return CLDL_E_CUDA; }
+int cldl_shard_solve_phase_dev(cldl_t*, double*, const double*, int) { return CLDL_E_CUDA; }
+uint64_t cldl_shard_count(const cldl_t*, int, int) { return 0; }
+int cldl_shard_pack_dev(cldl_t*, int, double*, const double*) { return CLDL_E_CUDA; }
+int cldl_shard_unpack_dev(cldl_t*, int, int, const double*, double*) { return CLDL_E_CUDA; }
+int cldl_shard_counts(const cldl_t*, uint64_t*) { return CLDL_E_CUDA; }
 }

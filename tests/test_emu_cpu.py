@@ -41,7 +41,7 @@ def test_gpu_test_modules_pass_on_the_emulated_build(order):
 
 
 # ---- the whole product, multifrontal kernels included (tests/emu/libclarabel_emu_full.so) ----
-FULL_MODULES = ["tests/test_ldl_gpu.py"] + MODULES
+FULL_MODULES = ["tests/test_ldl_gpu.py", "tests/test_shard_gpu.py"] + MODULES
 FULL_SKIP = [
     # minutes each under emulation (they pass: 68 of 68 in the complete run recorded in DESIGN.md)
     "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones",
@@ -77,4 +77,4 @@ def test_every_layer_including_the_multifrontal_kernels_on_the_emulated_build():
 
 
 def test_multifrontal_kernels_with_descending_thread_order():
-    _run_full(["tests/test_ldl_gpu.py"], "reverse")
+    _run_full(["tests/test_ldl_gpu.py", "tests/test_shard_gpu.py"], "reverse")
