@@ -591,7 +591,7 @@ EXPORTED_SYMBOLS += [
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
     "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_create_gp",
     "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
-    "cldl_shard_unpack_dev", "cldl_shard_counts",
+    "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes",
 ]
 
 _l2_ready = False

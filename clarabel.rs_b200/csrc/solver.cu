@@ -1450,6 +1450,8 @@ uint64_t cipm_iter_ms(const cipm_t* h, double* out, uint64_t cap) {
   return n;
 }
 uint64_t cipm_launch_count(void) { return cb::g_launches; }
+// sizes of the structs that cross the ABI, so that a binding can check its own mirror: {cldl_opts, cldl_info_t, cipm_settings, cipm_info}
+void cipm_abi_sizes(uint64_t* out4) { out4[0] = sizeof(cldl_opts); out4[1] = sizeof(cldl_info_t); out4[2] = sizeof(cipm_settings); out4[3] = sizeof(cipm_info); }
 
 // which: 0 = numeric refactor, 1 = one LDL solve (fwd+bwd), 2 = one KKTSolver::solve incl. iterative
 // refinement, on whatever values / right-hand side the handle currently holds.  CUDA events on the stream.

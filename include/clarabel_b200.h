@@ -254,6 +254,9 @@ uint64_t cipm_trace(const cipm_t *h, double *out, uint64_t cap_rows); /* rows of
  * every iteration; the last entry is the end of the solve. */
 uint64_t cipm_iter_ms(const cipm_t *h, double *out, uint64_t cap);
 uint64_t cipm_launch_count(void);
+/* sizeof of {cldl_opts, cldl_info_t, cipm_settings, cipm_info} as compiled into the library: a binding checks its
+ * own struct mirrors against them before the first call */
+void cipm_abi_sizes(uint64_t *out4);
 /* device-timed (CUDA events) average ms of: 0 numeric refactor, 1 one LDL solve, 2 one KKT solve incl. IR */
 double cipm_time_ms(cipm_t *h, int which, int reps);                            /* kernels launched by this library so far */
 uint64_t cipm_m_reduced(const cipm_t *h);   /* rows left after the inf-bound presolve (== m when nothing was dropped) */

@@ -42,3 +42,17 @@ def test_default_opts_match_reference_settings():
     cb.lib().cldl_default_opts(C.byref(o))
     assert o.regularize_eps == 1e-13 and o.regularize_delta == 2e-7   # default/settings.rs:155-161
     assert o.regularize_enable == 1 and o.amd_dense_scale == 1.5       # ldlsolvers/qdldl.rs:38-41
+
+
+def test_struct_mirrors_have_the_compiled_sizes():
+    """the ctypes mirrors of the four structs that cross the ABI are as large as the C structs the library was built with
+    (a mirror that is too small lets cldl_default_opts write past it)"""
+    import ctypes as C
+    import numpy as np
+    L = cb.lib()
+    out = np.zeros(4, dtype=np.uint64)
+    L.cipm_abi_sizes.argtypes = [C.POINTER(C.c_uint64)]
+    L.cipm_abi_sizes.restype = None
+    L.cipm_abi_sizes(out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert [int(v) for v in out] == [C.sizeof(cb.pkg.cldl_opts), C.sizeof(cb.pkg.cldl_info_t), C.sizeof(cb.pkg.cipm_settings),
+                                      C.sizeof(cb.pkg.cipm_info)]
