@@ -58,6 +58,10 @@ class cldl_opts(C.Structure):
     ]
 
 
+# cldl_allgather_fn: int (*)(void* ctx, const double* d_send, double* d_recv, uint64_t count)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
 class cldl_info_t(C.Structure):
     _fields_ = [
         ("name", C.c_char * 16),
@@ -133,6 +137,8 @@ def lib() -> C.CDLL:
     L.cldl_shard_pack_dev.argtypes = [vp, C.c_int, vp, vp]
     L.cldl_shard_unpack_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.cldl_shard_counts.argtypes = [vp, u64p]
+    L.cldl_set_transport.argtypes = [vp, ALLGATHER_FN, vp]
+    L.cldl_copy_dev.argtypes = [vp, vp, C.c_uint64]
     # host-only symbolic API
     L.csym_analyse.argtypes = [C.POINTER(vp), C.c_uint64, u64p, u64p, u64p, C.c_int,
                                C.c_double, C.c_int, C.c_int]
@@ -228,6 +234,12 @@ class CudaLDLSolver:
             self.close()
         except Exception:
             pass
+
+    def set_transport(self, transport):
+        """install the all-gather of a sharded handle (e.g. TorchDistTransport): refactor() / solve() then run their
+        phases and exchanges themselves"""
+        self._transport = transport
+        _check(self._L.cldl_set_transport(self._h, transport.fn, None), "set_transport")
 
     # --- DirectLDLSolver trait ---
     def update_values(self, index, values):
@@ -441,6 +453,45 @@ class ShardedLDLGroup:
             s.close()
 
 
+class TorchDistTransport:
+    """The all-gather a sharded handle calls between its phases, over `torch.distributed` (NCCL on GPUs; gloo on host
+    memory in the emulated build of the test-suite).  Keep the object alive as long as the handle uses it."""
+
+    def __init__(self, device=0):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist, self.device = torch, dist, device
+        self.world = dist.get_world_size()
+        self.emu = os.environ.get("CLARABEL_EMU") == "1"
+        self._send = self._recv = None
+        self.calls = 0
+        self.fn = ALLGATHER_FN(self._call)
+
+    def _call(self, ctx, d_send, d_recv, count):
+        try:
+            torch, n = self._torch, int(count)
+            self.calls += 1
+            if self.emu:      # device memory is host memory: wrap the library's buffers directly
+                send = torch.from_numpy(np.ctypeslib.as_array(C.cast(d_send, C.POINTER(C.c_double)), shape=(n,)))
+                recv = torch.from_numpy(np.ctypeslib.as_array(C.cast(d_recv, C.POINTER(C.c_double)), shape=(n * self.world,)))
+                self._dist.all_gather_into_tensor(recv, send)
+                return 0
+            if self._send is None or self._send.numel() < n:
+                dev = torch.device("cuda", self.device)
+                self._send = torch.empty(n + n // 4 + 64, dtype=torch.float64, device=dev)
+                self._recv = torch.empty(self._send.numel() * self.world, dtype=torch.float64, device=dev)
+            L = lib()
+            L.cldl_copy_dev(self._send.data_ptr(), d_send, 8 * n)
+            self._dist.all_gather_into_tensor(self._recv[:n * self.world], self._send[:n])
+            torch.cuda.synchronize(self.device)
+            L.cldl_copy_dev(d_recv, self._recv.data_ptr(), 8 * n * self.world)
+            return 0
+        except Exception as e:                     # never let an exception cross the C boundary
+            import sys
+            print("[clarabel_b200] transport failed:", repr(e), file=sys.stderr)
+            return -1
+
+
 class ShardedLDLRank:
     """One rank of a sharded factorisation in a `torch.distributed` job (one process per GPU; NCCL over NVLink, or
     gloo on host buffers in the emulated build of the test-suite).  The exchanges between the phases are all-gathers of
@@ -591,7 +642,8 @@ EXPORTED_SYMBOLS += [
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
     "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_create_gp",
     "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
-    "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes",
+    "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes", "cldl_set_transport", "cipm_set_transport",
+    "cldl_copy_dev",
 ]
 
 _l2_ready = False
@@ -619,6 +671,7 @@ def _lib2():
     L.ccone_update_scaling_ex.argtypes = [vp, f64p, f64p, C.c_double, C.c_int]
     L.ccone_affine_ds_ex.argtypes = [vp, f64p, f64p]
     L.ccone_compute_barrier.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double, f64p]
+    L.cipm_set_transport.argtypes = [vp, ALLGATHER_FN, vp]
     L.cipm_destroy.argtypes = [vp]
     L.cipm_destroy.restype = None
     L.cipm_solve.argtypes = [vp]
@@ -682,7 +735,7 @@ class CudaSolver:
     """
 
     def __init__(self, P, q, A, b, cones, settings=None, *, ordering=ORDER_BEST, kkt_perm=None,
-                 device=0, max_panel=0, nd_leaf=0):
+                 device=0, max_panel=0, nd_leaf=0, shard=None, transport=None):
         import scipy.sparse as sp
         L = _lib2()
         self._L = L
@@ -695,6 +748,8 @@ class CudaSolver:
         o = cldl_opts()
         L.cldl_default_opts(C.byref(o))
         o.ordering, o.device, o.max_panel, o.nd_leaf = ordering, device, max_panel, nd_leaf
+        if shard is not None:      # (nranks, rank): this process is one rank of a factorisation split over several GPUs
+            o.shard_nranks, o.shard_rank = int(shard[0]), int(shard[1])
         ct = np.ascontiguousarray([CONE_CODES[k] for k, _ in cones], dtype=np.int32)
         cd = _u64([3 if k in ("exp", "pow") else (len(d[0]) if k == "genpow" else d) for k, d in cones])
         cpar = _f64([float(d) if k == "pow" else 0.0 for k, d in cones])
@@ -714,6 +769,11 @@ class CudaSolver:
         self._h = h
         self.N = int(L.cipm_kkt_dim(h))
         self.m_reduced = int(L.cipm_m_reduced(h))    # rows left after the inf-bound presolve
+        if shard is not None:
+            # every rank runs the same interior-point iterations on identical data; the factorisation and the
+            # triangular solves are split and meet through this all-gather
+            self._transport = transport if transport is not None else TorchDistTransport(device)
+            _check(L.cipm_set_transport(h, self._transport.fn, None), "cipm_set_transport")
 
     def update_data(self, P=None, q=None, A=None, b=None):
         """DefaultSolver::update_data (data_updating.rs:68-163): new values on the same sparsity patterns; the

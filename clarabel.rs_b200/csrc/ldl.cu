@@ -2422,6 +2422,9 @@ void LDLObject::release() {
   for (int* p : d_shard_xidx) if (p) cudaFree(p);
   d_shard_xidx.clear();
   if (d_prog_init) { cudaFree(d_prog_init); d_prog_init = nullptr; }
+  if (d_xsend) { cudaFree(d_xsend); d_xsend = nullptr; }
+  if (d_xrecv) { cudaFree(d_xrecv); d_xrecv = nullptr; }
+  xbuf_cap = 0;
   auto fr = [](const void* p) { if (p) cudaFree((void*)p); };
   fr(dev.sn_first); fr(dev.sn_rowptr); fr(dev.sn_rows); fr(dev.child_ptr); fr(dev.child_list);
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
@@ -2438,7 +2441,7 @@ void LDLObject::release() {
 }
 
 int LDLObject::refactor_async() {
-  if (sharded()) return CLDL_E_ARG;   // one rank of a sharded factorisation: use the phase entry points
+  if (sharded()) return transport ? refactor_sharded() : CLDL_E_ARG;   // without a transport: the phase entry points
   CK(cudaSetDevice(device));
   CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
   if (factor_dataflow) {
@@ -2508,7 +2511,7 @@ int LDLObject::join_slot1() {
 }
 
 int LDLObject::solve_async(double* d_x, const double* d_b, int slot, bool half) {
-  if (sharded()) return CLDL_E_ARG;
+  if (sharded()) return (transport && slot == 0) ? solve_sharded(d_x, d_b) : CLDL_E_ARG;
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
   if (use_dataflow) {
@@ -2643,6 +2646,39 @@ int LDLObject::solve_phase_async(double* d_x, const double* d_b, int phase) {
   }
   CK(cudaGetLastError());
   return CLDL_OK;
+}
+
+// padded all-gather of one kind of contribution through the installed transport
+int LDLObject::exchange(int what, double* d_x) {
+  uint64_t cnt = 1;
+  for (int r = 0; r < shard_nranks; r++) cnt = std::max(cnt, shard_count(what, r));
+  if ((size_t)cnt > xbuf_cap) {
+    if (d_xsend) cudaFree(d_xsend);
+    if (d_xrecv) cudaFree(d_xrecv);
+    xbuf_cap = (size_t)cnt + (size_t)cnt / 4 + 64;
+    CK(cudaMalloc((void**)&d_xsend, xbuf_cap * sizeof(double)));
+    CK(cudaMalloc((void**)&d_xrecv, xbuf_cap * (size_t)shard_nranks * sizeof(double)));
+  }
+  int rc = shard_pack(what, d_xsend, d_x);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(stream));
+  if (transport(transport_ctx, d_xsend, d_xrecv, cnt) != 0) return CLDL_E_CUDA;
+  for (int r = 0; r < shard_nranks; r++)
+    if (r != shard_rank && (rc = shard_unpack(what, r, d_xrecv + (size_t)r * cnt, d_x))) return rc;
+  return CLDL_OK;
+}
+int LDLObject::refactor_sharded() {
+  int rc = refactor_phase_async(0);
+  if (rc) return rc;
+  if ((rc = exchange(0, nullptr))) return rc;
+  return refactor_phase_async(1);
+}
+int LDLObject::solve_sharded(double* d_x, const double* d_b) {
+  int rc = solve_phase_async(d_x, d_b, 0);
+  if (rc) return rc;
+  if ((rc = exchange(1, nullptr))) return rc;
+  if ((rc = solve_phase_async(d_x, d_b, 1))) return rc;
+  return exchange(2, d_x);
 }
 
 uint64_t LDLObject::shard_count(int what, int rank) const {
@@ -2910,6 +2946,14 @@ int cldl_shard_solve_phase_dev(cldl_t* h, double* d_x, const double* d_b, int ph
 uint64_t cldl_shard_count(const cldl_t* h, int what, int rank) { return h ? h->obj.shard_count(what, rank) : 0; }
 int cldl_shard_pack_dev(cldl_t* h, int what, double* d_buf, const double* d_x) { return h ? h->obj.shard_pack(what, d_buf, d_x) : CLDL_E_ARG; }
 int cldl_shard_unpack_dev(cldl_t* h, int what, int rank, const double* d_buf, double* d_x) { return h ? h->obj.shard_unpack(what, rank, d_buf, d_x) : CLDL_E_ARG; }
+int cldl_set_transport(cldl_t* h, cldl_allgather_fn fn, void* ctx) {
+  if (!h) return CLDL_E_ARG;
+  h->obj.transport = fn; h->obj.transport_ctx = ctx;
+  return CLDL_OK;
+}
+int cldl_copy_dev(void* d_dst, const void* d_src, uint64_t bytes) {
+  return bytes == 0 || cudaMemcpy(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+}
 int cldl_shard_counts(const cldl_t* h, uint64_t* out4) {
   if (!h || !out4) return CLDL_E_ARG;
   out4[0] = h->obj.shard_count_owned[0]; out4[1] = h->obj.shard_count_owned[1];

@@ -163,6 +163,14 @@ class LDLObject {
   uint64_t shard_count(int what, int rank) const;
   int shard_pack(int what, double* d_buf, const double* d_x);
   int shard_unpack(int what, int rank, const double* d_buf, double* d_x);
+  // transport (all-gather between ranks) and the self-driven sharded refactor / solve built on it
+  cldl_allgather_fn transport = nullptr;
+  void* transport_ctx = nullptr;
+  double *d_xsend = nullptr, *d_xrecv = nullptr;
+  size_t xbuf_cap = 0;
+  int exchange(int what, double* d_x);
+  int refactor_sharded();
+  int solve_sharded(double* d_x, const double* d_b);
 
   int init(int n, const int64_t* Ap, const int32_t* Ai, const double* Ax, const int8_t* dsigns,
            const cldl_opts& o, const int* perm_in);

@@ -841,6 +841,7 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   int rc = ConeSet::collapse(ctype, cdim, ncones, cs, cparam, gp_dim2, gp_alpha);
   if (rc) return rc;
   cones.ns_amin = set.min_terminate_step_length; cones.ns_step = set.linesearch_backtrack_step;
+  if (lo.shard_nranks > 1) pair_solves = false;   // a sharded factorisation runs its exchanges on one solve context
   int tot = 0;
   for (auto& cc : cs) tot += cc.dim;
   if (tot != m) return CLDL_E_DIM;
@@ -1397,6 +1398,12 @@ int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
                        genpow_alpha);
   if (rc) { h->ipm.release(); delete h; return rc; }
   *out = h;
+  return CLDL_OK;
+}
+
+int cipm_set_transport(cipm_t* h, cldl_allgather_fn fn, void* ctx) {
+  if (!h) return CLDL_E_ARG;
+  h->ipm.kkt.ldl.transport = fn; h->ipm.kkt.ldl.transport_ctx = ctx;
   return CLDL_OK;
 }
 

@@ -142,6 +142,15 @@ uint64_t cldl_shard_count(const cldl_t *h, int what, int rank);
 int cldl_shard_pack_dev(cldl_t *h, int what, double *d_buf, const double *d_x);
 int cldl_shard_unpack_dev(cldl_t *h, int what, int rank, const double *d_buf, double *d_x);
 int cldl_shard_counts(const cldl_t *h, uint64_t *out4);
+/* Transport for a sharded handle: an all-gather of `count` doubles per rank between DEVICE buffers (d_send: count
+ * doubles of this rank; d_recv: nranks * count doubles, rank r's block at r * count).  It is called from the host
+ * between the phases, after the send buffer is complete, and must return once d_recv is usable (0 = ok).  With a
+ * transport installed, cldl_refactor(_dev) / cldl_solve(_dev) and the whole cipm_* driver run their phases and
+ * exchanges themselves (contributions are padded to the largest one); every rank then executes the same interior
+ * point iterations on identical data and only the factorisation / triangular solves are split. */
+typedef int (*cldl_allgather_fn)(void *ctx, const double *d_send, double *d_recv, uint64_t count);
+int cldl_set_transport(cldl_t *h, cldl_allgather_fn fn, void *ctx);
+int cldl_copy_dev(void *d_dst, const void *d_src, uint64_t bytes);   /* device-to-device copy, for transports in bindings */
 
 /* timing helper for benches: runs `reps` refactors (or solves) back to back
  * on the device and returns the average milliseconds measured with CUDA
@@ -245,6 +254,8 @@ int cipm_create_gp(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colpt
                    const uint64_t *cone_dims, const double *cone_params, const uint64_t *genpow_dim2,
                    const double *genpow_alpha, const cipm_settings *settings, const cldl_opts *ldl_opts,
                    const uint64_t *kkt_perm_or_null);
+/* installs the all-gather of a sharded factorisation (cldl_opts.shard_nranks > 1 in ldl_opts) on the solver's LDL */
+int cipm_set_transport(cipm_t *h, cldl_allgather_fn fn, void *ctx);
 void cipm_destroy(cipm_t *h);
 int cipm_solve(cipm_t *h);                                   /* IPSolver::solve */
 void cipm_get_info(const cipm_t *h, cipm_info *out);

@@ -181,4 +181,6 @@ uint64_t cldl_shard_count(const cldl_t*, int, int) { return 0; }
 int cldl_shard_pack_dev(cldl_t*, int, double*, const double*) { return CLDL_E_CUDA; }
 int cldl_shard_unpack_dev(cldl_t*, int, int, const double*, double*) { return CLDL_E_CUDA; }
 int cldl_shard_counts(const cldl_t*, uint64_t*) { return CLDL_E_CUDA; }
+int cldl_set_transport(cldl_t*, cldl_allgather_fn, void*) { return CLDL_E_CUDA; }
+int cldl_copy_dev(void* d, const void* s, uint64_t n) { if (n) std::memmove(d, s, (size_t)n); return 0; }
 }
