@@ -643,7 +643,7 @@ EXPORTED_SYMBOLS += [
     "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_create_gp",
     "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
     "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes", "cldl_set_transport", "cipm_set_transport",
-    "cldl_copy_dev",
+    "cldl_copy_dev", "cipm_update_settings",
 ]
 
 _l2_ready = False
@@ -672,6 +672,7 @@ def _lib2():
     L.ccone_affine_ds_ex.argtypes = [vp, f64p, f64p]
     L.ccone_compute_barrier.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double, f64p]
     L.cipm_set_transport.argtypes = [vp, ALLGATHER_FN, vp]
+    L.cipm_update_settings.argtypes = [vp, C.POINTER(cipm_settings)]
     L.cipm_destroy.argtypes = [vp]
     L.cipm_destroy.restype = None
     L.cipm_solve.argtypes = [vp]
@@ -774,6 +775,14 @@ class CudaSolver:
             # triangular solves are split and meet through this all-gather
             self._transport = transport if transport is not None else TorchDistTransport(device)
             _check(L.cipm_set_transport(h, self._transport.fn, None), "cipm_set_transport")
+
+    def update_settings(self, **kw):
+        """Solver::update_settings (core/solver.rs:207-211); construction-time fields may not change"""
+        s = cipm_settings.from_buffer_copy(self.settings)
+        for k, v in kw.items():
+            setattr(s, k, v)
+        _check(self._L.cipm_update_settings(self._h, C.byref(s)), "cipm_update_settings")
+        self.settings = s
 
     def update_data(self, P=None, q=None, A=None, b=None):
         """DefaultSolver::update_data (data_updating.rs:68-163): new values on the same sparsity patterns; the

@@ -1401,6 +1401,22 @@ int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
   return CLDL_OK;
 }
 
+// Solver::update_settings (core/solver.rs:207-211): every field may change except the ones that only act at
+// construction (settings.rs:307-335: equilibration parameters, presolve_enable)
+int cipm_update_settings(cipm_t* h, const cipm_settings* s) {
+  if (!h || !s) return CLDL_E_ARG;
+  IPM& I = h->ipm;
+  const cipm_settings& p = I.set;
+  if (s->equilibrate_enable != p.equilibrate_enable || s->equilibrate_max_iter != p.equilibrate_max_iter ||
+      s->equilibrate_min_scaling != p.equilibrate_min_scaling || s->equilibrate_max_scaling != p.equilibrate_max_scaling ||
+      s->presolve_enable != p.presolve_enable)
+    return CLDL_E_ARG;
+  I.set = *s;
+  I.kkt.set = *s;
+  I.cones.ns_amin = s->min_terminate_step_length; I.cones.ns_step = s->linesearch_backtrack_step;
+  return CLDL_OK;
+}
+
 int cipm_set_transport(cipm_t* h, cldl_allgather_fn fn, void* ctx) {
   if (!h) return CLDL_E_ARG;
   h->ipm.kkt.ldl.transport = fn; h->ipm.kkt.ldl.transport_ctx = ctx;

@@ -256,6 +256,9 @@ int cipm_create_gp(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colpt
                    const uint64_t *kkt_perm_or_null);
 /* installs the all-gather of a sharded factorisation (cldl_opts.shard_nranks > 1 in ldl_opts) on the solver's LDL */
 int cipm_set_transport(cipm_t *h, cldl_allgather_fn fn, void *ctx);
+/* Solver::update_settings (core/solver.rs:207-211): new settings for the next cipm_solve; CLDL_E_ARG when a field that
+ * only acts at construction differs (equilibration parameters, presolve_enable: settings.rs:307-335). */
+int cipm_update_settings(cipm_t *h, const cipm_settings *settings);
 void cipm_destroy(cipm_t *h);
 int cipm_solve(cipm_t *h);                                   /* IPSolver::solve */
 void cipm_get_info(const cipm_t *h, cipm_info *out);

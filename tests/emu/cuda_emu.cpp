@@ -66,7 +66,17 @@ static Fiber* cur = nullptr;
 static void* sched_sp = nullptr;
 static const std::function<void()>* body_fn = nullptr;
 static bool spun = false;                    // the running fiber yielded from a spin-wait
-static const bool reverse_order = [] { const char* e = std::getenv("EMU_ORDER"); return e && e[0] == 'r'; }();
+// EMU_ORDER: "reverse" = descending thread order; "random[:seed]" = a fresh random permutation of the resident fibers in
+// every scheduling pass (the most adversarial schedule: lanes of a warp and blocks of a grid interleave arbitrarily
+// between their synchronisation points)
+static const bool reverse_order = [] { const char* e = std::getenv("EMU_ORDER"); return e && e[0] == 'r' && e[1] == 'e'; }();
+static const bool random_order = [] { const char* e = std::getenv("EMU_ORDER"); return e && e[0] == 'r' && e[1] == 'a'; }();
+static uint64_t rng_state = [] {
+  const char* e = std::getenv("EMU_ORDER");
+  const char* c = e ? std::strchr(e, ':') : nullptr;
+  return (uint64_t)(c ? std::atoll(c + 1) : 1) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+}();
+static inline uint64_t rng_next() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
 
 uint3& cur_tid() { return cur ? cur->tid : zero3; }
 uint3& cur_bid() { return cur ? cur->blk->idx : zero3; }
@@ -128,13 +138,18 @@ unsigned warp_vote(bool pred) {
 }
 
 // run the fibers [0, total) (one or several blocks) to completion
+static std::vector<int> order;
 static void run_resident(std::vector<Block>& blocks, int total) {
   for (int t = 0; t < total; t++) prepare(fibers[t]);
   long long idle_passes = 0;
   for (;;) {
     bool progressed = false, any_live = false;
+    if (random_order) {
+      if ((int)order.size() != total) { order.resize(total); for (int i = 0; i < total; i++) order[i] = i; }
+      for (int i = total - 1; i > 0; i--) { const int j = (int)(rng_next() % (uint64_t)(i + 1)); std::swap(order[i], order[j]); }
+    }
     for (int t0 = 0; t0 < total; t0++) {
-      const int t = reverse_order ? total - 1 - t0 : t0;
+      const int t = random_order ? order[t0] : (reverse_order ? total - 1 - t0 : t0);
       Fiber& f = fibers[t];
       if (f.state != READY) { if (f.state != DONE) any_live = true; continue; }
       any_live = true;

@@ -76,5 +76,8 @@ def test_every_layer_including_the_multifrontal_kernels_on_the_emulated_build():
     _run_full(FULL_MODULES, "ascending")
 
 
-def test_multifrontal_kernels_with_descending_thread_order():
-    _run_full(["tests/test_ldl_gpu.py", "tests/test_shard_gpu.py"], "reverse")
+def test_multifrontal_kernels_with_a_random_schedule():
+    """a fresh random permutation of all resident fibers in every scheduling pass: lanes of a warp and blocks of a
+    persistent kernel interleave arbitrarily between their synchronisation points -- results (including the bitwise
+    reproducibility and sharded bit-identity tests) must not change"""
+    _run_full(["tests/test_ldl_gpu.py", "tests/test_shard_gpu.py"], "random:7")

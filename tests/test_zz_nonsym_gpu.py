@@ -230,3 +230,18 @@ def test_genpow_cone_ops_match_oracle():
         for al in (0.0, 0.4):
             bd, bo = dev.cone_compute_barrier(z, s, 0.05 * dz, 0.05 * ds, al), ora.compute_barrier(z, s, 0.05 * dz, 0.05 * ds, al)
             assert abs(bd - bo) <= 1e-9 * max(1.0, abs(bo))
+
+
+def test_update_settings_then_solve_again():  # mixed_conic.rs:29-46: same solver object, new settings, second solve
+    dev = cb.CudaSolver(*ref.mixed_conic_data())
+    r1 = dev.solve()
+    assert r1["status"] == "Solved" and abs(r1["obj_val"]) <= 1e-8
+    dev.update_settings(min_switch_step_length=0.999)
+    r2 = dev.solve()
+    assert r2["status"] in ("Solved", "AlmostSolved", "InsufficientProgress") and abs(r2["info"].cost_primal) <= 1e-6
+    assert r2["iterations"] != r1["iterations"] or True      # the dual strategy takes another path; no claim on the count
+    dev.update_settings(max_iter=3)
+    r3 = dev.solve()
+    assert r3["status"] in ("MaxIterations", "AlmostSolved") and r3["iterations"] == 3
+    with pytest.raises(cb.BackendError):
+        dev.update_settings(equilibrate_enable=0)          # construction-time field (settings.rs:307-335)
