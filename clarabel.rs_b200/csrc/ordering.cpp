@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <numeric>
 #include <vector>
+#include <unordered_map>
 #include <atomic>
 #include <future>
 #include <thread>
@@ -74,8 +75,13 @@ enum : uint8_t { ST_VAR = 0, ST_ELEM = 1, ST_DEAD_ELEM = 2, ST_ABSORBED = 3, ST_
 // Approximate minimum degree on a general undirected graph given as CSR
 // adjacency (xadj/adj).  `order` receives the elimination sequence (perm:
 // order[k] = vertex eliminated k-th).
+// `halo` (optional): vertices that take part in the degree computations and in the elements but are never
+// eliminated and never emitted -- the boundary of a region whose interior is being ordered (halo-AMD: the separator
+// vertices a nested-dissection leaf touches will be eliminated later, so a leaf vertex next to many of them is more
+// expensive than its degree inside the leaf says).
 void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adjncy,
-               double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first) {
+               double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first,
+               const std::vector<char>* halo) {
   order.clear();
   order.reserve(n);
   if (n == 0) return;
@@ -95,7 +101,7 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
   std::vector<int> dense_nodes;
   for (int i = 0; i < n; i++) {
     int d = (int)(xadj[i + 1] - xadj[i]);
-    if ((double)d > dense && !(forced_first && (*forced_first)[i])) { status[i] = ST_DENSE; dense_nodes.push_back(i); }
+    if ((double)d > dense && !(forced_first && (*forced_first)[i]) && !(halo && (*halo)[i])) { status[i] = ST_DENSE; dense_nodes.push_back(i); }
   }
   for (int i = 0; i < n; i++) {
     if (status[i] == ST_DENSE) continue;
@@ -117,9 +123,10 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
     if (prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[d] = nxt[i];
     if (nxt[i] >= 0) prv[nxt[i]] = prv[i];
   };
-  int nlive = 0;
+  auto is_halo = [&](int i) { return halo && (*halo)[i]; };
+  int nlive = 0, nhalo = 0;
   for (int i = n - 1; i >= 0; i--)
-    if (status[i] == ST_VAR) { bucket_insert(i, degree[i]); nlive++; }
+    if (status[i] == ST_VAR) { if (is_halo(i)) nhalo++; else { bucket_insert(i, degree[i]); nlive++; } }
 
   int nel = 0, mindeg = 0;
   const int ntot = nlive;
@@ -144,7 +151,7 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
         degme += nv[i];
         nv[i] = -nv[i];
         Lp.push_back(i);
-        bucket_remove(i, degree[i]);
+        if (!is_halo(i)) bucket_remove(i, degree[i]);
       }
     };
     for (int i : adj[p]) take(i);
@@ -192,7 +199,7 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
         if (status[j] == ST_VAR && nv[j] > 0) { deg += nv[j]; ai[k++] = j; h += (unsigned)j; }
       }
       ai.resize(k);
-      if (ei.empty() && ai.empty()) {
+      if (ei.empty() && ai.empty() && !is_halo(i)) {
         // mass elimination: i has no neighbours outside Lp
         degme -= nvi; nvpiv += nvi; nel += nvi;
         nv[i] = 0; status[i] = ST_ABSORBED;
@@ -203,9 +210,11 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
         h += (unsigned)p;
         h %= (unsigned)n;
         hashv[i] = h;
-        if (bucket_of_hash[h] < 0) touched_hash.push_back((int)h);
-        hnext[i] = bucket_of_hash[h];
-        bucket_of_hash[h] = i;
+        if (!is_halo(i)) {     // halo vertices are never merged into supervariables
+          if (bucket_of_hash[h] < 0) touched_hash.push_back((int)h);
+          hnext[i] = bucket_of_hash[h];
+          bucket_of_hash[h] = i;
+        }
       }
     }
     wflg += (int64_t)n + 1;  // invalidate all w[e]
@@ -246,11 +255,13 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
       if (nvi <= 0) continue;
       nv[i] = nvi;
       int64_t deg = (int64_t)degree[i] + degme - nvi;
-      deg = std::min<int64_t>(deg, (int64_t)ntot - nel - nvi);
+      deg = std::min<int64_t>(deg, (int64_t)ntot + nhalo - nel - nvi);
       if (deg < 0) deg = 0;
       degree[i] = (int)deg;
-      bucket_insert(i, degree[i]);
-      if (degree[i] < mindeg) mindeg = degree[i];
+      if (!is_halo(i)) {
+        bucket_insert(i, degree[i]);
+        if (degree[i] < mindeg) mindeg = degree[i];
+      }
       Lpe.push_back(i);
     }
     nv[p] = nvpiv;
@@ -293,6 +304,7 @@ struct NDShared {
   std::atomic<int> next_region{1};
   int leaf_size = 200;
   int par_depth = 0;
+  bool halo = false;       // halo-AMD on the leaves (CB_ND_HALO)
 };
 
 // BFS restricted to vertices with part[v]==region; returns eccentricity, fills queue and level[].
@@ -323,6 +335,38 @@ void nd_leaf(NDShared& W, const std::vector<int>& verts, std::vector<int>& out) 
   if (m == 0) return;
   if (m <= 2) { for (int v : verts) out.push_back(v); return; }
   for (int k = 0; k < m; k++) W.local[verts[k]] = k;
+  if (W.halo) {
+    // halo-AMD: the separator vertices this region touches join the graph as vertices that are never eliminated.
+    // They get ids m, m+1, ... through a map private to this call (another thread may see the same separator vertex
+    // as the halo of ITS region at the same time, so the shared `local` array must not be used for them).
+    std::unordered_map<int, int> hid;
+    std::vector<std::vector<int>> hadj;          // halo vertex -> leaf neighbours
+    std::vector<int64_t> sx(m + 1, 0);
+    std::vector<int> sa, lorder;
+    for (int k = 0; k < m; k++) {
+      const int v = verts[k];
+      for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+        const int u = (*W.adj)[p];
+        if (W.local[u] >= 0) { sa.push_back(W.local[u]); continue; }
+        if (W.part[u] != -1) continue;           // only separators (dense rows withheld by the driver also carry -1)
+        auto it = hid.find(u);
+        int h;
+        if (it == hid.end()) { h = (int)hadj.size(); hid.emplace(u, h); hadj.emplace_back(); } else h = it->second;
+        hadj[h].push_back(k);
+        sa.push_back(m + h);
+      }
+      sx[k + 1] = (int64_t)sa.size();
+    }
+    const int nh = (int)hadj.size();
+    sx.resize(m + nh + 1);
+    for (int h = 0; h < nh; h++) { for (int k : hadj[h]) sa.push_back(k); sx[m + h + 1] = (int64_t)sa.size(); }
+    std::vector<char> halo(m + nh, 0);
+    for (int h = 0; h < nh; h++) halo[m + h] = 1;
+    amd_graph(m + nh, sx, sa, 1e9, lorder, nullptr, &halo);
+    for (int k : lorder) if (k < m) out.push_back(verts[k]);
+    for (int k = 0; k < m; k++) W.local[verts[k]] = -1;
+    return;
+  }
   std::vector<int64_t> sx(m + 1, 0);
   std::vector<int> sa, lorder;
   for (int k = 0; k < m; k++) {
@@ -550,6 +594,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
   W.level.assign(n, -1);
   W.local.assign(n, -1);
   W.leaf_size = leaf_size;
+  W.halo = std::getenv("CB_ND_HALO") != nullptr && std::atoi(std::getenv("CB_ND_HALO")) != 0;
   {
     unsigned hc = std::thread::hardware_concurrency();
     int d = 0;

@@ -14,7 +14,8 @@ namespace cb {
 
 // ---- orderings (ordering.cpp) ----
 void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adj,
-               double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first = nullptr);
+               double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first = nullptr,
+               const std::vector<char>* halo = nullptr);
 void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
                std::vector<int>& perm);
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,

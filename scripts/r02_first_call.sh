@@ -27,3 +27,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
   python bench.py --gpus 1 --steps 2 --warmup 1 --no-process-warmup > $O/r02_ncu_bench.log 2>&1
 echo "ncu launch list exit $?" >> $O/r02_summary.txt
 tail -3 $O/r02_nonsym_tests.log $O/r02_gpu_tests.log; cat $O/r02_summary.txt; head -c 600 $O/r02_bench_c2.json
+# 6. ordering knob written without a GPU: halo-AMD on the nested-dissection leaves (about 6 % fewer flops on C2 by the
+#    symbolic counts, one more level) -- same bench, knob on; adopt as the default only if ms_per_step drops
+CB_ND_HALO=1 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 > $O/r02_bench_c2_halo.json 2> $O/r02_bench_c2_halo.err
+echo "bench c2 halo exit $?" >> $O/r02_summary.txt
