@@ -444,6 +444,7 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
     const bool sp = cs[k].type == CT_SOC && cs[k].dim > SOC_NO_EXPANSION_MAX_SIZE;
     sparse_flag[k] = sp ? 1 : 0;
     const bool diag = cs[k].type == CT_ZERO || cs[k].type == CT_NONNEG || sp || cs[k].type == CT_GENPOW;
+    if ((long long)nHs + (diag ? (long long)cs[k].dim : (long long)cs[k].dim * (cs[k].dim + 1) / 2) > 2000000000LL) return -21;
     nHs += diag ? cs[k].dim : cs[k].dim * (cs[k].dim + 1) / 2;
     m += cs[k].dim;
     const bool ns3c = cs[k].type == CT_EXP || cs[k].type == CT_POW;
@@ -492,7 +493,9 @@ int ConeSet::init(const std::vector<ConeSpec>& cs, cudaStream_t st) {
     dev.npsd = (int)psd_list.size();
     if (up(&dev.psd_list, psd_list) || up(&dev.psd_n, pn) || up(&dev.psd_moff, mo)) return -20;
     const size_t tb = (size_t)(tot ? tot : 1) * 8;
+    psd_mat_total = tot;
     CCK(cudaMalloc((void**)&dev.psd_R, tb)); CCK(cudaMalloc((void**)&dev.psd_Rinv, tb)); CCK(cudaMalloc((void**)&dev.psd_RRt, tb));
+    CCK(cudaMalloc((void**)&dev.psd_bar, tb));
     CCK(cudaMemset(dev.psd_R, 0, tb)); CCK(cudaMemset(dev.psd_Rinv, 0, tb)); CCK(cudaMemset(dev.psd_RRt, 0, tb));
     if (dev.npsd && psd_prepare()) return -20;
   }
@@ -513,7 +516,7 @@ void ConeSet::release() {
   fr(dev.type); fr(dev.off); fr(dev.dim); fr(dev.boff); fr(dev.sparse); fr(dev.soc_list); fr(dev.rowtag);
   fr(dev.w); fr(dev.lam); fr(dev.u); fr(dev.v); fr(dev.eta); fr(dev.dd); fr(dev.fail);
   fr(ws.partials); fr(ws.counter); fr(row2blk_dev); fr(d_pmin); fr(d_psum);
-  fr(dev.psd_list); fr(dev.psd_n); fr(dev.psd_moff); fr(dev.psd_R); fr(dev.psd_Rinv); fr(dev.psd_RRt);
+  fr(dev.psd_list); fr(dev.psd_n); fr(dev.psd_moff); fr(dev.psd_R); fr(dev.psd_Rinv); fr(dev.psd_RRt); fr(dev.psd_ws); fr(dev.psd_bar);
   ns_release();
   gp_release();
 }

@@ -43,6 +43,8 @@ struct ConeDev {
   const int* psd_n = nullptr;      // [ncones] matrix dimension (0 for other cones)
   const long long* psd_moff = nullptr;  // [ncones] offset into the n x n matrix arenas
   double *psd_R = nullptr, *psd_Rinv = nullptr, *psd_RRt = nullptr;
+  double* psd_ws = nullptr;        // global scratch (8 matrices per cone) when the matrices do not fit shared memory
+  double* psd_bar = nullptr;       // one matrix per cone for the barrier's Cholesky
   // exponential / 3-D power cones (cones_nonsym.cu): state in structure-of-arrays form, component j of the
   // k-th nonsymmetric cone at [j*nns + k]
   int nns = 0;
@@ -62,7 +64,7 @@ struct ConeDev {
   double *gp_d2 = nullptr, *gp_mu = nullptr;                                                            // [ngp]
 };
 
-constexpr int CB_PSD_MAX_N = 32;
+constexpr int CB_PSD_MAX_N = 128;   // Hs block of one cone: tri(tri(128)) = 3.4e7 entries
 
 // dim = number of rows the cone occupies (numel); psd_n = matrix dimension of a PSD cone
 // param: exponent of a power cone; alphas: exponents of a generalised power cone (dim = alphas.size() + dim2)
@@ -126,7 +128,8 @@ class ConeSet {
 
   // PSD pieces (cones_psd.cu)
   std::vector<int> psd_list;
-  int psd_nmax = 0, psd_numel_max = 0;
+  int psd_nmax = 0, psd_numel_max = 0, psd_warps = 4;
+  long long psd_mat_total = 0;     // sum of n^2 over the PSD cones
   int psd_prepare();
   void psd_set_identity();
   void psd_update_scaling(const double* s, const double* z);

@@ -256,7 +256,7 @@ void ConeSet::compute_barrier(const double* z, const double* s, const double* dz
     g_launches++;
     k_sum<<<red_grid(c.npsd), RED_THREADS, 0, stream>>>(c.npsd, [=] __device__(int k) {
       const int id = c.psd_list[k], o = c.off[id], n = c.psd_n[id];
-      double W[CB_PSD_MAX_N * CB_PSD_MAX_N];
+      double* W = c.psd_bar + c.psd_moff[id];
       return ns3::psd_neg_logdet(z + o, dz + o, n, alpha, W) + ns3::psd_neg_logdet(s + o, ds + o, n, alpha, W);
     }, ws, partial + 2);
   }

@@ -177,7 +177,8 @@ typedef struct cipm_handle cipm_t;
 
 /* SupportedConeT tags (supportedcone.rs:17-52).  ExponentialConeT() and PowerConeT(alpha) occupy 3 rows each;
  * the exponent of a power cone travels in cone_params (cipm_create_ex); GenPowerConeT(alpha, dim2) has
- * cone_dims = len(alpha) and its dim2 / exponents in the two extra arrays of cipm_create_gp. */
+ * cone_dims = len(alpha) and its dim2 / exponents in the two extra arrays of cipm_create_gp.
+ * PSDTriangleConeT(n): cone_dims = n (matrix dimension, n (n + 1) / 2 rows); n <= 128, larger cones are refused. */
 enum { CIPM_CONE_ZERO = 0, CIPM_CONE_NONNEG = 1, CIPM_CONE_SOC = 2, CIPM_CONE_PSD = 3, CIPM_CONE_EXP = 4,
        CIPM_CONE_POW = 5, CIPM_CONE_GENPOW = 6 };
 /* ScalingStrategy (src/solver/core/cones/mod.rs) */

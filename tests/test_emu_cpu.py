@@ -19,7 +19,8 @@ MODULES = ["tests/test_cones_gpu.py", "tests/test_psd_gpu.py", "tests/test_ipm_g
 # the dense stand-in for the LDL caps the KKT dimension at 3000
 TOO_BIG = ["tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[2000-4000-60-2]",
            "tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[1500-2000-None-3]",
-           "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones"]
+           "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones",
+           "tests/test_psd_gpu.py::test_large_psd_cone_ops_match_oracle[global-scratch]"]     # runs in the full build below
 
 
 import pytest
