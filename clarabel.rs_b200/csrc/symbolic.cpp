@@ -6,6 +6,7 @@
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <map>
 #include <memory_resource>
 #include <numeric>
@@ -134,8 +135,11 @@ struct Eval { double flops; int64_t nnzL; };
 
 // flop_cap > 0: give up (return 1) right after the column counts when the simplicial flop count exceeds it --
 // used when comparing candidate orderings so that a hopeless candidate costs O(nnz), not O(nnz(L)).
+// go_on (optional) is asked once the statistics (flops_stored, nnzL_stored, nlevels) are known: false -> return 2
+// with the statistics only, true -> finish the analysis.
 static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<int>& perm0,
-                 const SymbolicOptions& opt, Symbolic& S, bool stats_only, double flop_cap = 0.0) {
+                 const SymbolicOptions& opt, Symbolic& S, bool stats_only, double flop_cap = 0.0,
+                 const std::function<bool(const Symbolic&)>* go_on = nullptr) {
   double t_last = tnow();
   S.n = n;
   S.nnzA = Ap[n];
@@ -440,6 +444,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   }
   S.nlevels = nlev;
   if (stats_only) return 0;
+  if (go_on && !(*go_on)(S)) return 2;
 
   // The three remaining pieces -- (a) level schedule + children + relative index maps, (b) assembly map of the
   // original entries, (c) update-matrix arena -- only read the supernode structure built above and write disjoint
@@ -719,19 +724,41 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
     TMARK("ordering: ND");
   } else {
     // ORDER_BEST: evaluate both, pick by a simple device-time model
-    std::vector<int> pa, pn;
-    amd_order(n, Ap, Ai, opt.amd_dense_scale, pa);
-    nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, pn);
-    Symbolic Sa, Sn;
-    int ra = build(n, Ap, Ai, pa, opt, Sa, true);
-    if (ra) return ra;
-    int rn = build(n, Ap, Ai, pn, opt, Sn, true, 30.0 * Sa.flops_simplicial + 1e9);
-    if (rn < 0) return rn;
-    if (rn == 1) { Sn.flops_stored = 1e300; Sn.nnzL_stored = 0; Sn.nlevels = 0; }   // hopeless: rejected early
     // model: dense flops at ~10 TF/s effective + memory at ~2 TB/s + 10 us per level
     auto model = [](const Symbolic& s) {
       return s.flops_stored / 1.0e13 + (double)s.nnzL_stored * 8.0 / 2.0e12 + 10e-6 * s.nlevels;
     };
+    // Nested dissection goes first (it runs on all host threads; minimum degree is one sequential pass that costs
+    // several times as much on a large graph) and the minimum-degree candidate is only produced when it could pay
+    // for itself: the most it can save per refactorisation is taken as 70 % of the ND candidate's flop + memory
+    // time plus half of its level latency (its fill is rarely below a third of ND's and its tree is never much
+    // shallower than a balanced dissection tree), a solve is taken as 25 refactorisations, and one minimum-degree
+    // pass as 1 us per vertex.  When that saving cannot cover the pass, the ND analysis is simply finished in
+    // place.  The rule reads the candidate's statistics only, so the choice is the same on every run and host;
+    // CB_ORDER_EXHAUSTIVE=1 always evaluates both.
+    static const bool exhaustive = std::getenv("CB_ORDER_EXHAUSTIVE") != nullptr && std::atoi(std::getenv("CB_ORDER_EXHAUSTIVE")) != 0;
+    std::vector<int> pa, pn;
+    nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, pn);
+    if ((int)pn.size() != n) return -6;
+    const std::function<bool(const Symbolic&)> amd_cannot_pay = [&](const Symbolic& sn) {
+      if (exhaustive) return false;
+      const double saving = 0.7 * (sn.flops_stored / 1.0e13 + (double)sn.nnzL_stored * 8.0 / 2.0e12) + 0.5 * 10e-6 * sn.nlevels;
+      return 25.0 * saving < 1e-6 * (double)n;
+    };
+    Symbolic Sn;
+    // a candidate beyond 1e12 simplicial flops is not analysed further before the other one is known
+    int rn = build(n, Ap, Ai, pn, opt, Sn, false, 1e12, &amd_cannot_pay);
+    if (rn < 0) return rn;
+    if (rn == 0) { S = std::move(Sn); S.ordering_used = ORDER_ND; return 0; }
+    amd_order(n, Ap, Ai, opt.amd_dense_scale, pa);
+    Symbolic Sa;
+    int ra = build(n, Ap, Ai, pa, opt, Sa, true);
+    if (ra) return ra;
+    if (rn == 1) {      // ND statistics still missing: same early rejection relative to the AMD candidate as before
+      rn = build(n, Ap, Ai, pn, opt, Sn, true, 30.0 * Sa.flops_simplicial + 1e9);
+      if (rn < 0) return rn;
+    } else if (Sn.flops_simplicial > 30.0 * Sa.flops_simplicial + 1e9) rn = 1;
+    if (rn == 1) { Sn.flops_stored = 1e300; Sn.nnzL_stored = 0; Sn.nlevels = 0; }   // hopeless: rejected early
     if (model(Sn) < model(Sa)) { perm0.swap(pn); kind = ORDER_ND; }
     else { perm0.swap(pa); kind = ORDER_AMD; }
   }
