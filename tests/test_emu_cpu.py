@@ -15,12 +15,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 MODULES = ["tests/test_cones_gpu.py", "tests/test_psd_gpu.py", "tests/test_ipm_gpu.py", "tests/test_zz_nonsym_gpu.py",
-           "tests/test_zz_golden.py"]
+           "tests/test_zz_golden.py", "tests/test_zz_psd_large_gpu.py"]
 # the dense stand-in for the LDL caps the KKT dimension at 3000
 TOO_BIG = ["tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[2000-4000-60-2]",
            "tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[1500-2000-None-3]",
            "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones",
-           "tests/test_psd_gpu.py::test_large_psd_cone_ops_match_oracle[global-scratch]"]     # runs in the full build below
+           "tests/test_zz_psd_large_gpu.py::test_large_psd_cone_ops_match_oracle[global-scratch]"]     # runs in the full build below
 
 
 import pytest
@@ -42,7 +42,7 @@ def test_gpu_test_modules_pass_on_the_emulated_build(order):
 
 
 # ---- the whole product, multifrontal kernels included (tests/emu/libclarabel_emu_full.so) ----
-FULL_MODULES = ["tests/test_ldl_gpu.py", "tests/test_shard_gpu.py"] + MODULES
+FULL_MODULES = ["tests/test_ldl_gpu.py", "tests/test_zz_shard_gpu.py"] + MODULES
 FULL_SKIP = [
     # minutes each under emulation (they pass: 68 of 68 in the complete run recorded in DESIGN.md)
     "tests/test_ipm_gpu.py::test_paired_solves_are_bitwise_the_unpaired_ones",
@@ -81,4 +81,4 @@ def test_multifrontal_kernels_with_a_random_schedule():
     """a fresh random permutation of all resident fibers in every scheduling pass: lanes of a warp and blocks of a
     persistent kernel interleave arbitrarily between their synchronisation points -- results (including the bitwise
     reproducibility and sharded bit-identity tests) must not change"""
-    _run_full(["tests/test_ldl_gpu.py", "tests/test_shard_gpu.py"], "random:7")
+    _run_full(["tests/test_ldl_gpu.py", "tests/test_zz_shard_gpu.py"], "random:7")
