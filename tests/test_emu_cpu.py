@@ -23,24 +23,6 @@ TOO_BIG = ["tests/test_ipm_gpu.py::test_random_sparse_qp_same_iterations[2000-40
            "tests/test_zz_psd_large_gpu.py::test_large_psd_cone_ops_match_oracle[global-scratch]"]     # runs in the full build below
 
 
-import pytest
-
-
-@pytest.mark.parametrize("order", ["ascending", "reverse"])
-def test_gpu_test_modules_pass_on_the_emulated_build(order):
-    """`reverse` runs the threads of every block in descending order between synchronisation points: a kernel that is
-    correct under the CUDA execution model cannot tell the difference, one that relies on lockstep lanes can."""
-    lib = os.path.join(ROOT, "tests", "emu", "libclarabel_emu.so")
-    assert os.path.exists(lib), "tests/emu/libclarabel_emu.so missing: run `make`"
-    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + MODULES
-    for t in TOO_BIG:
-        cmd += ["--deselect", t]
-    out = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, CLARABEL_EMU="1", EMU_ORDER=order), capture_output=True, text=True, timeout=1800)
-    tail = out.stdout[-3000:]
-    assert out.returncode == 0, tail
-    assert " passed" in tail and "failed" not in tail, tail
-
-
 # ---- the whole product, multifrontal kernels included (tests/emu/libclarabel_emu_full.so) ----
 FULL_MODULES = ["tests/test_ldl_gpu.py", "tests/test_zz_shard_gpu.py"] + MODULES
 FULL_SKIP = [
@@ -57,28 +39,73 @@ FULL_SKIP = [
 ]
 
 
-def _run_full(modules, order):
-    lib = os.path.join(ROOT, "tests", "emu", "libclarabel_emu_full.so")
-    assert os.path.exists(lib), "tests/emu/libclarabel_emu_full.so missing: run `make`"
+
+import pytest
+
+# The four runs are independent subprocesses; all of them are started when the first test asks for its result, so the
+# module costs about as long as its slowest run instead of the sum.
+_JOBS = {}
+
+
+def _reap():
+    for job in _JOBS.values():      # -x stopped the session early: do not leave the other runs behind
+        if job.poll() is None:
+            job.kill()
+
+
+import atexit
+atexit.register(_reap)
+
+
+def _spec(kind, order):
+    full = kind == "full" or kind == "full-ldl"
+    lib = os.path.join(ROOT, "tests", "emu", "libclarabel_emu_full.so" if full else "libclarabel_emu.so")
+    modules = {"dense": MODULES, "full": FULL_MODULES, "full-ldl": ["tests/test_ldl_gpu.py", "tests/test_zz_shard_gpu.py"]}[kind]
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + modules
-    for t in FULL_SKIP:
+    for t in (FULL_SKIP if full else TOO_BIG):
         cmd += ["--deselect", t]
-    out = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, CLARABEL_EMU="1", CLARABEL_EMU_FULL="1", EMU_ORDER=order),
-                         capture_output=True, text=True, timeout=3000)
-    tail = out.stdout[-3000:]
-    assert out.returncode == 0, tail
+    env = dict(os.environ, CLARABEL_EMU="1", EMU_ORDER=order)
+    if full:
+        env["CLARABEL_EMU_FULL"] = "1"
+    return lib, cmd, env
+
+
+ALL_RUNS = [("dense", "ascending"), ("dense", "reverse"), ("full", "ascending"), ("full-ldl", "random:7")]
+
+
+def _result(kind, order):
+    if not _JOBS:
+        for k, o in ALL_RUNS:
+            lib, cmd, env = _spec(k, o)
+            assert os.path.exists(lib), f"{lib} missing: run `make`"
+            _JOBS[(k, o)] = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    job = _JOBS[(kind, order)]
+    try:
+        out, _ = job.communicate(timeout=3000)
+    except subprocess.TimeoutExpired:
+        job.kill()
+        raise
+    tail = out[-3000:]
+    assert job.returncode == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
+
+
+@pytest.mark.parametrize("order", ["ascending", "reverse"])
+def test_gpu_test_modules_pass_on_the_emulated_build(order):
+    """`reverse` runs the threads of every block in descending order between synchronisation points: a kernel that is
+    correct under the CUDA execution model cannot tell the difference, one that relies on lockstep lanes can."""
+    _result("dense", order)
 
 
 def test_every_layer_including_the_multifrontal_kernels_on_the_emulated_build():
     """ldl.cu itself -- the level-0 kernel, the persistent dataflow factorisation with its spin-waits on dependency
     counters, the pipelined dataflow solves -- runs here: the blocks of those launches are resident together as
     fibers and __nanosleep is their yield point."""
-    _run_full(FULL_MODULES, "ascending")
+    _result("full", "ascending")
 
 
 def test_multifrontal_kernels_with_a_random_schedule():
     """a fresh random permutation of all resident fibers in every scheduling pass: lanes of a warp and blocks of a
     persistent kernel interleave arbitrarily between their synchronisation points -- results (including the bitwise
     reproducibility and sharded bit-identity tests) must not change"""
-    _run_full(["tests/test_ldl_gpu.py", "tests/test_zz_shard_gpu.py"], "random:7")
+    _result("full-ldl", "random:7")
