@@ -26,6 +26,38 @@ _LIBPATH = os.path.join(_HERE, "libclarabel_b200.so")
 _lib = None
 
 
+class BadInputData(ValueError):
+    """SolverError::BadInputData (src/solver/core/traits.rs): what DefaultSolver::new returns for inconsistent data"""
+
+
+def cone_nvars(kind, d):
+    """SupportedConeT::nvars (supportedcone.rs:54-71)"""
+    if kind in ("exp", "pow"):
+        return 3
+    if kind == "psd":
+        return int(d) * (int(d) + 1) // 2
+    if kind == "genpow":
+        return len(d[0]) + int(d[1])
+    return int(d)
+
+
+def check_dimensions(P, q, A, b, cones):
+    """check_dimensions of DefaultSolver::new (implementations/default/solver.rs:129-159): same tests, same order,
+    same messages; pinned by tests/api_dimension_checks.rs"""
+    m, n = len(b), len(q)
+    p = sum(cone_nvars(k, d) for k, d in cones)
+    if m != A.shape[0]:
+        raise BadInputData("A and b incompatible dimensions")
+    if p != m:
+        raise BadInputData("Constraint dimensions inconsistent with size of cones")
+    if n != A.shape[1]:
+        raise BadInputData("A and q incompatible dimensions")
+    if n != P.shape[1]:
+        raise BadInputData("P and q incompatible dimensions")
+    if P.shape[0] != P.shape[1]:
+        raise BadInputData("P not square")
+
+
 class BackendError(RuntimeError):
     pass
 
@@ -640,7 +672,7 @@ EXPORTED_SYMBOLS += [
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
-    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_create_gp",
+    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_get_equilibration", "cipm_create_gp",
     "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
     "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes", "cldl_set_transport", "cipm_set_transport",
     "cldl_copy_dev", "cipm_update_settings",
@@ -691,6 +723,8 @@ def _lib2():
         getattr(L, nm).argtypes = [vp]
         getattr(L, nm).restype = C.c_uint64
     L.cipm_get_kkt.argtypes = [vp, u64p, u64p, f64p, i8p]
+    L.cipm_get_equilibration.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double)]
+    L.cipm_get_equilibration.restype = C.c_int
     L.cipm_get_kkt_perm.argtypes = [vp, u64p]
     L.cipm_ldl_info.argtypes = [vp, C.POINTER(cldl_info_t)]
     L.cipm_ldl_info.restype = None
@@ -740,9 +774,10 @@ class CudaSolver:
         import scipy.sparse as sp
         L = _lib2()
         self._L = L
-        P = sp.triu(sp.csc_matrix(P), format="csc")
+        P, A = sp.csc_matrix(P), sp.csc_matrix(A)
+        check_dimensions(P, q, A, b, cones)
+        P = sp.triu(P, format="csc")
         P.sort_indices()
-        A = sp.csc_matrix(A)
         A.sort_indices()
         self.n, self.m = P.shape[0], A.shape[0]
         self.settings = settings if settings is not None else default_settings()
@@ -775,6 +810,12 @@ class CudaSolver:
             # triangular solves are split and meet through this all-gather
             self._transport = transport if transport is not None else TorchDistTransport(device)
             _check(L.cipm_set_transport(h, self._transport.fn, None), "cipm_set_transport")
+
+    def equilibration(self):
+        """(d, e, c) of DefaultProblemData::equilibration (problemdata.rs:229-312)"""
+        d, e, c = np.zeros(max(self.n, 1)), np.zeros(max(self.m_reduced, 1)), C.c_double(0.0)
+        _check(self._L.cipm_get_equilibration(self._h, _p(d, C.c_double), _p(e, C.c_double), C.byref(c)), "cipm_get_equilibration")
+        return d[:self.n], e[:self.m_reduced], c.value
 
     def update_settings(self, **kw):
         """Solver::update_settings (core/solver.rs:207-211); construction-time fields may not change"""

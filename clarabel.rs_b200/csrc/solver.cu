@@ -1498,6 +1498,16 @@ double cipm_time_ms(cipm_t* h, int which, int reps) {
 }
 
 uint64_t cipm_m_reduced(const cipm_t* h) { return h ? (uint64_t)h->ipm.m : 0; }
+
+// DefaultProblemData::equilibration (problemdata.rs:229-312): d [n], e [cipm_m_reduced] and the cost scaling c
+int cipm_get_equilibration(const cipm_t* h, double* d, double* e, double* c) {
+  if (!h) return CLDL_E_ARG;
+  const cb::IPM& I = h->ipm;
+  if (d) for (int i = 0; i < I.n; i++) d[i] = I.d[i];
+  if (e) for (int i = 0; i < I.m; i++) e[i] = I.e[i];
+  if (c) *c = I.c;
+  return CLDL_OK;
+}
 uint64_t cipm_kkt_dim(const cipm_t* h) { return h ? (uint64_t)h->ipm.kkt.N : 0; }
 uint64_t cipm_kkt_nnz(const cipm_t* h) { return h ? (uint64_t)h->ipm.kkt.nnzK : 0; }
 

@@ -275,6 +275,9 @@ void cipm_abi_sizes(uint64_t *out4);
 /* device-timed (CUDA events) average ms of: 0 numeric refactor, 1 one LDL solve, 2 one KKT solve incl. IR */
 double cipm_time_ms(cipm_t *h, int which, int reps);                            /* kernels launched by this library so far */
 uint64_t cipm_m_reduced(const cipm_t *h);   /* rows left after the inf-bound presolve (== m when nothing was dropped) */
+/* DefaultProblemData::equilibration (problemdata.rs:229-312; pinned by tests/equilibration_bounds.rs): the Ruiz
+ * scalings d [n], e [cipm_m_reduced] and the cost scaling c of the handle; any of the three pointers may be NULL. */
+int cipm_get_equilibration(const cipm_t* h, double* d, double* e, double* c);
 uint64_t cipm_kkt_dim(const cipm_t *h);
 uint64_t cipm_kkt_nnz(const cipm_t *h);
 int cipm_get_kkt(const cipm_t *h, uint64_t *colptr, uint64_t *rowval, double *nzval, int8_t *dsigns);

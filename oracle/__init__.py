@@ -338,6 +338,30 @@ def default_settings(**kw):
     return s
 
 
+def check_dimensions(P, q, A, b, cones):
+    """check_dimensions (src/solver/implementations/default/solver.rs:129-159), the order of the tests included;
+    SupportedConeT::nvars as in supportedcone.rs:54-71"""
+    def nvars(kind, d):
+        if kind in ("exp", "pow"):
+            return 3
+        if kind == "psd":
+            return int(d) * (int(d) + 1) // 2
+        if kind == "genpow":
+            return len(d[0]) + int(d[1])
+        return int(d)
+    m, n = len(b), len(q)
+    if m != A.shape[0]:
+        raise ValueError("A and b incompatible dimensions")
+    if sum(nvars(k, d) for k, d in cones) != m:
+        raise ValueError("Constraint dimensions inconsistent with size of cones")
+    if n != A.shape[1]:
+        raise ValueError("A and q incompatible dimensions")
+    if n != P.shape[1]:
+        raise ValueError("P and q incompatible dimensions")
+    if P.shape[0] != P.shape[1]:
+        raise ValueError("P not square")
+
+
 class IPM:
     """Oracle interior-point solver (mirrors DefaultSolver::new / solve()).
 
@@ -352,9 +376,10 @@ class IPM:
         import scipy.sparse as sp
         L = _ipm_lib()
         self._L = L
-        P = sp.triu(sp.csc_matrix(P), format="csc")
+        P, A = sp.csc_matrix(P), sp.csc_matrix(A)
+        check_dimensions(P, q, A, b, cones)
+        P = sp.triu(P, format="csc")
         P.sort_indices()
-        A = sp.csc_matrix(A)
         A.sort_indices()
         n, m = P.shape[0], A.shape[0]
         self.n, self.m = n, m
