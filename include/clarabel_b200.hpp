@@ -131,6 +131,10 @@ class DefaultSolver {
       alphas.insert(alphas.end(), c.alphas.begin(), c.alphas.end());
     }
     if (alphas.empty()) alphas.push_back(0.0);
+    // the part of check_dimensions (default/solver.rs:129-159) that can be seen through raw q / b pointers; the cone
+    // sizes against A.m are checked by cipm_create_gp
+    if (A.n != P.n) throw std::invalid_argument("A and q incompatible dimensions");
+    if (P.m != P.n) throw std::invalid_argument("P not square");
     n_ = P.n; m_ = A.m;
     check(cipm_create_gp(&h_, P.n, A.m, P.colptr, P.rowval, P.nzval, q, A.colptr, A.rowval, A.nzval, b, cones.size(),
                          tags.data(), dims.data(), params.data(), dim2.data(), alphas.data(), &settings, ldl_opts, nullptr),
@@ -157,6 +161,11 @@ class DefaultSolver {
   // DefaultSolver::update_data (data_updating.rs:68-163): nullptr = unchanged; false = refused (presolved problem)
   bool update_data(const double* P_nzval, const double* q, const double* A_nzval, const double* b) {
     return cipm_update_data(h_, P_nzval, q, A_nzval, b) == 0;
+  }
+  // DefaultProblemData::equilibration (problemdata.rs:229-312): d [n], e [rows left after the presolve], c
+  void equilibration(std::vector<double>& d, std::vector<double>& e, double& c) const {
+    d.assign(n_, 0.0); e.assign(cipm_m_reduced(h_), 0.0);
+    check(cipm_get_equilibration(h_, d.data(), e.data(), &c), "cipm_get_equilibration");
   }
   LinearSolverInfo linear_solver_info() const { LinearSolverInfo i; cipm_ldl_info(h_, &i); return i; }
   cipm_t* handle() { return h_; }
