@@ -8,6 +8,8 @@
 #include "cuda_emu.h"
 
 #include <sys/mman.h>
+#include <mutex>
+#include <utility>
 
 #include <map>
 #include <vector>
@@ -191,8 +193,58 @@ static void run_resident(std::vector<Block>& blocks, int total) {
   }
 }
 
+// ---- guarded device memory (EMU_GUARD=1) ----
+extern std::vector<std::pair<size_t, size_t>> g_blocks;      // (offset, bytes) of every allocation
+namespace {
+std::mutex g_mu;
+char* g_arena = nullptr;
+size_t g_cap = 0, g_top = 0;
+int g_open = 0;
+int guard_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("EMU_GUARD"); v = (e && std::atoi(e)) ? 1 : 0; }
+  return v;
+}
+}  // namespace
+
+void* dev_alloc(size_t n) {
+  if (!guard_mode()) return std::calloc(1, n ? n : 1);
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_arena) {
+    g_cap = (size_t)64 << 30;
+    void* a = mmap(nullptr, g_cap, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (a == MAP_FAILED) return nullptr;
+    g_arena = (char*)a;
+  }
+  const size_t need = ((n ? n : 1) + 4095) & ~(size_t)4095;
+  if (g_top + need > g_cap) return nullptr;
+  void* p = g_arena + g_top;
+  g_blocks.emplace_back(g_top, need);
+  g_top += need;
+  if (g_open > 0) mprotect(p, need, PROT_READ | PROT_WRITE);
+  return p;
+}
+void dev_free(void* p) {
+  if (guard_mode() && g_arena && (char*)p >= g_arena && (char*)p < g_arena + g_cap) return;   // never reused
+  std::free(p);
+}
+// open / close: one mprotect over the used part of the arena (a launch-heavy test makes ~1e5 of these calls)
+static void protect_all(int prot) { if (g_top) mprotect(g_arena, g_top, prot); }
+std::vector<std::pair<size_t, size_t>> g_blocks;
+void dev_open() {
+  if (!guard_mode()) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_open++ == 0 && g_arena) protect_all(PROT_READ | PROT_WRITE);
+}
+void dev_close() {
+  if (!guard_mode()) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (--g_open == 0 && g_arena) protect_all(PROT_NONE);
+}
+
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   if (cur) { std::fprintf(stderr, "[emu] nested launch\n"); std::abort(); }
+  DevScope dev_scope;
   const int bt = (int)(block.x * block.y * block.z);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   if (bt <= 0 || nblocks == 0) return;

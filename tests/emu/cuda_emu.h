@@ -146,14 +146,24 @@ enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedM
 
 inline cudaError_t cudaGetDeviceCount(int* c) { *c = 1; return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? 0 : 2; }
-inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+// EMU_GUARD=1: device memory comes from an arena the host may only touch inside copies, memsets and kernel launches
+// (cuda_emu.cpp); a host-side dereference of a device pointer -- invisible otherwise, device memory being host memory
+// here -- ends the process with SIGSEGV.
+namespace emu {
+void* dev_alloc(size_t n);
+void dev_free(void* p);
+void dev_open();
+void dev_close();
+struct DevScope { DevScope() { dev_open(); } ~DevScope() { dev_close(); } };
+}
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = emu::dev_alloc(n); return *p ? 0 : 2; }
+inline cudaError_t cudaFree(void* p) { emu::dev_free(p); return 0; }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? 0 : 2; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
-inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { if (n) std::memmove(d, s, n); return 0; }
-inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return 0; }
-inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return 0; }
-inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) std::memset(d, v, n); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { emu::DevScope o; if (n) std::memmove(d, s, n); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t = nullptr) { emu::DevScope o; if (n) std::memmove(d, s, n); return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { emu::DevScope o; if (n) std::memset(d, v, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { emu::DevScope o; if (n) std::memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(1); return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }

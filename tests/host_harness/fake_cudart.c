@@ -19,8 +19,67 @@ struct dim3_ { unsigned x, y, z; };
 
 cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return 0; }
 cudaError_t cudaSetDevice(int d) { (void)d; return 0; }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
-cudaError_t cudaFree(void *p) { free(p); return 0; }
+/* FAKE_CUDART_GUARD=1: "device" memory comes from one arena that the host may not touch (PROT_NONE) except inside the
+   copy / memset entry points below.  Kernel launches are dropped, so nothing legitimate ever dereferences a device
+   pointer on the host: a host-side read or write of device memory -- which the plain shim and the emulator cannot see,
+   device memory being ordinary host memory there -- ends the process with SIGSEGV. */
+#include <pthread.h>
+#include <sys/mman.h>
+static int guard_mode = -1;
+static char *arena; static size_t arena_cap, arena_top;
+static pthread_mutex_t arena_mu = PTHREAD_MUTEX_INITIALIZER;
+static int arena_open_count;
+static int guard_on(void)
+{
+    if (guard_mode < 0) { const char *e = getenv("FAKE_CUDART_GUARD"); guard_mode = (e && atoi(e)) ? 1 : 0; }
+    return guard_mode;
+}
+static void arena_open(void)
+{
+    if (!guard_on() || !arena) return;
+    pthread_mutex_lock(&arena_mu);
+    if (arena_open_count++ == 0) mprotect(arena, arena_top ? arena_top : 4096, PROT_READ | PROT_WRITE);
+    pthread_mutex_unlock(&arena_mu);
+}
+static void arena_close(void)
+{
+    if (!guard_on() || !arena) return;
+    pthread_mutex_lock(&arena_mu);
+    if (--arena_open_count == 0) mprotect(arena, arena_top ? arena_top : 4096, PROT_NONE);
+    pthread_mutex_unlock(&arena_mu);
+}
+cudaError_t cudaMalloc(void **p, size_t n)
+{
+    if (!guard_on()) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+    pthread_mutex_lock(&arena_mu);
+    if (!arena) {
+        arena_cap = (size_t)64 << 30;
+        arena = mmap(NULL, arena_cap, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (arena == MAP_FAILED) { arena = NULL; pthread_mutex_unlock(&arena_mu); return 2; }
+    }
+    const size_t need = ((n ? n : 1) + 4095) & ~(size_t)4095;      /* page granular: neighbours never share a page */
+    if (arena_top + need + 4096 > arena_cap) { pthread_mutex_unlock(&arena_mu); return 2; }
+    *p = arena + arena_top;
+    arena_top += need + 4096;                                       /* one guard page between allocations */
+    if (arena_open_count > 0) mprotect(arena, arena_top, PROT_READ | PROT_WRITE);
+    {   /* FAKE_CUDART_FILL=<byte>: what an unlaunched kernel "left" in device memory; 0x3f makes every double 4.8e-4
+           and every int32 about 1e9, so that the host drivers see non-converged, non-zero numbers and keep iterating */
+        const char *f = getenv("FAKE_CUDART_FILL");
+        if (f) {
+            mprotect(*p, need, PROT_READ | PROT_WRITE);
+            memset(*p, (int)strtol(f, NULL, 0), n);
+            if (arena_open_count == 0) mprotect(*p, need, PROT_NONE);
+        }
+    }
+    pthread_mutex_unlock(&arena_mu);
+    return 0;
+}
+cudaError_t cudaFree(void *p)
+{
+    if (guard_on() && arena && (char *)p >= arena && (char *)p < arena + arena_cap) return 0;   /* never reused */
+    free(p);
+    return 0;
+}
 cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
 cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 /* FAKE_CUDART_LOG=<file>: one line "bytes fnv1a64" per host-to-device copy, so that a change of the host-side plan
@@ -36,10 +95,10 @@ static void log_h2d(const void *s, size_t n, int kind)
     FILE *f = fopen(path, "a");
     if (f) { fprintf(f, "%zu %016llx\n", n, (unsigned long long)h); fclose(f); }
 }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int kind) { log_h2d(s, n, kind); if (n) memmove(d, s, n); return 0; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int kind, void *st) { (void)st; log_h2d(s, n, kind); if (n) memmove(d, s, n); return 0; }
-cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, void *st) { (void)st; if (n) memset(d, v, n); return 0; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int kind) { log_h2d(s, n, kind); arena_open(); if (n) memmove(d, s, n); arena_close(); return 0; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int kind, void *st) { (void)st; log_h2d(s, n, kind); arena_open(); if (n) memmove(d, s, n); arena_close(); return 0; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { arena_open(); if (n) memset(d, v, n); arena_close(); return 0; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, void *st) { (void)st; arena_open(); if (n) memset(d, v, n); arena_close(); return 0; }
 cudaError_t cudaStreamCreateWithFlags(void **s, unsigned f) { (void)f; *s = malloc(1); return 0; }
 cudaError_t cudaStreamDestroy(void *s) { free(s); return 0; }
 cudaError_t cudaStreamSynchronize(void *s) { (void)s; return 0; }
