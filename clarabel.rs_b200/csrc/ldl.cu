@@ -2139,6 +2139,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     if (!chains.empty()) CK(cudaMemcpy(t2, chains.data(), chains.size() * sizeof(int2), cudaMemcpyHostToDevice));
     d_solve_chains = t2;
   }
+  cb_tmark("ldl:   solve plan: level-sync part");
   // level_tasks was re-ordered inside levels: re-upload
   CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
                 cudaMemcpyHostToDevice));
@@ -2250,6 +2251,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       h_df_kind = t_kind;
     }
   }
+  cb_tmark("ldl:   solve plan: dataflow solve tasks");
   // dataflow factorisation plan (k_factor_df): level 0's small fronts keep their level-synchronous launch
   // (no dependencies, ~10^5 tiny CTAs); everything else becomes queue tasks in level order.  Every task
   // record carries the front's constants and the range of its child records, so a task starts with two
@@ -2357,13 +2359,34 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
           ctp[k].resize(nt + 1);
           for (int t = 0; t <= nt; t++) ctp[k][t] = (int)(std::lower_bound(rb, re, ns + t * TS) - rb);
         }
+        // the children that reach tile (ti, tj), in child order: bucketed per tile from each child's own tile rows
+        // (a front under hundreds of children and with hundreds of tile rows -- the linking block of a
+        // block-angular problem -- would otherwise test every child against every tile)
+        const int ntile = nt * (nt + 1) / 2;
+        std::vector<int> tile_ptr(ntile + 1, 0), tile_kid;
+        {
+          std::vector<std::vector<int>> trows(kidsbuf.size());
+          for (size_t k = 0; k < kidsbuf.size(); k++)
+            for (int t = 0; t < nt; t++) if (ctp[k][t + 1] > ctp[k][t]) trows[k].push_back(t);
+          for (size_t k = 0; k < kidsbuf.size(); k++)
+            for (size_t a = 0; a < trows[k].size(); a++)
+              for (size_t b = 0; b <= a; b++) tile_ptr[trows[k][a] * (trows[k][a] + 1) / 2 + trows[k][b] + 1]++;
+          for (int t = 0; t < ntile; t++) tile_ptr[t + 1] += tile_ptr[t];
+          tile_kid.resize(tile_ptr[ntile]);
+          std::vector<int> pos(tile_ptr.begin(), tile_ptr.end() - 1);
+          for (size_t k = 0; k < kidsbuf.size(); k++)
+            for (size_t a = 0; a < trows[k].size(); a++)
+              for (size_t b = 0; b <= a; b++) tile_kid[pos[trows[k][a] * (trows[k][a] + 1) / 2 + trows[k][b]]++] = (int)k;
+        }
         for (int ti = 0; ti < nt; ti++)
           for (int tj = 0; tj <= ti; tj++) {
             const int d0 = (int)(desc.size() / 12);
             // children whose block is contiguous in the tile go first: the tile task adds them in registers
             int ndense = 0;
+            const int tix = ti * (ti + 1) / 2 + tj;
             for (int pass = 0; pass < 2; pass++)
-              for (size_t k = 0; k < kidsbuf.size(); k++) {
+              for (int q = tile_ptr[tix]; q < tile_ptr[tix + 1]; q++) {
+                const size_t k = (size_t)tile_kid[q];
                 const int a0 = ctp[k][ti], a1 = ctp[k][ti + 1], b0 = ctp[k][tj], b1 = ctp[k][tj + 1];
                 if (!(a1 > a0 && b1 > b0)) continue;
                 const int* rl = S.rel.data() + S.sn_rowptr[kidsbuf[k]];
@@ -2379,6 +2402,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       }
     }
     }
+    cb_tmark("ldl:   solve plan: factor tasks built");
+    if (std::getenv("CB_TIMING")) std::fprintf(stderr, "[cb timing]     factor plan: %zu tasks, %zu child records, %zu big fronts, %zu tiles\n",
+                                                tk.size() / 16, desc.size() / 12, big_tasks.size(), tiles.size());
     dff.ntask = (int)(tk.size() / 16);
     if (!sharded()) dff_ntask_owned = dff.ntask;
     int4* t4 = nullptr;
