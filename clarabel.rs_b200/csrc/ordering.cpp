@@ -81,7 +81,7 @@ enum : uint8_t { ST_VAR = 0, ST_ELEM = 1, ST_DEAD_ELEM = 2, ST_ABSORBED = 3, ST_
 // expensive than its degree inside the leaf says).
 void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adjncy,
                double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first,
-               const std::vector<char>* halo) {
+               const std::vector<char>* halo, const std::atomic<bool>* cancel) {
   order.clear();
   order.reserve(n);
   if (n == 0) return;
@@ -136,6 +136,7 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
   std::vector<int> tmp;
 
   while (nel < ntot) {
+    if (cancel && cancel->load(std::memory_order_relaxed)) { order.clear(); return; }   // the caller no longer wants it
     while (mindeg <= n && head[mindeg] < 0) mindeg++;
     int p = head[mindeg];
     bucket_remove(p, mindeg);
@@ -280,11 +281,11 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
 }
 
 void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
-               std::vector<int>& perm) {
+               std::vector<int>& perm, const std::atomic<bool>* cancel) {
   std::vector<int64_t> xadj;
   std::vector<int> adj;
   full_adjacency(n, Ap, Ai, xadj, adj);
-  amd_graph(n, xadj, adj, dense_scale, perm);
+  amd_graph(n, xadj, adj, dense_scale, perm, nullptr, nullptr, cancel);
 }
 
 // ---------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 // dense panels, no per-entry row indices in the factor).
 #pragma once
 #include <cstdint>
+#include <atomic>
 #include <vector>
 
 namespace cb {
@@ -15,9 +16,10 @@ namespace cb {
 // ---- orderings (ordering.cpp) ----
 void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& adj,
                double dense_scale, std::vector<int>& order, const std::vector<char>* forced_first = nullptr,
-               const std::vector<char>* halo = nullptr);
+               const std::vector<char>* halo = nullptr, const std::atomic<bool>* cancel = nullptr);
+// cancel (optional): set by another thread to make the pass return early with an empty order
 void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
-               std::vector<int>& perm);
+               std::vector<int>& perm, const std::atomic<bool>* cancel = nullptr);
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
               int leaf_size, std::vector<int>& perm);
 
