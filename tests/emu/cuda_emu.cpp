@@ -247,7 +247,13 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
   DevScope dev_scope;
   const int bt = (int)(block.x * block.y * block.z);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
-  if (bt <= 0 || nblocks == 0) return;
+  // what the hardware refuses with "invalid configuration argument" must not pass silently here
+  if (bt <= 0 || bt > 1024 || nblocks == 0 || grid.y > 65535u || grid.z > 65535u || grid.x > 2147483647u || block.z > 64u ||
+      smem > 232448) {
+    std::fprintf(stderr, "[emu] invalid launch configuration: grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", grid.x, grid.y, grid.z,
+                 block.x, block.y, block.z, smem);
+    std::abort();
+  }
   body_fn = &body;
   g_blockDim = uint3{block.x, block.y, block.z};
   g_gridDim = uint3{grid.x, grid.y, grid.z};
