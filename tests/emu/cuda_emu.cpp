@@ -242,6 +242,20 @@ void dev_close() {
   if (--g_open == 0 && g_arena) protect_all(PROT_NONE);
 }
 
+static std::map<const void*, int> g_smem_optin;
+static std::mutex g_smem_mu;
+void note_smem_optin(const void* fn, int bytes) { std::lock_guard<std::mutex> lk(g_smem_mu); g_smem_optin[fn] = bytes; }
+void check_smem_optin(const void* fn, size_t smem) {
+  if (smem <= 48 * 1024) return;
+  std::lock_guard<std::mutex> lk(g_smem_mu);
+  auto it = g_smem_optin.find(fn);
+  if (it == g_smem_optin.end() || (size_t)it->second < smem) {
+    std::fprintf(stderr, "[emu] launch with %zu bytes of dynamic shared memory, opt-in %d: the device refuses this launch\n", smem,
+                 it == g_smem_optin.end() ? 0 : it->second);
+    std::abort();
+  }
+}
+
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   if (cur) { std::fprintf(stderr, "[emu] nested launch\n"); std::abort(); }
   DevScope dev_scope;

@@ -69,7 +69,13 @@ struct Cfg {
   Cfg(dim3 g, dim3 b, size_t s = 0, void* = nullptr) : grid(g), block(b), smem(s) {}
 };
 // a launch after tests/emu/transform.py: the kernel call sits in `body` and runs once per emulated thread
-inline void run_grid_cfg(const Cfg& c, const std::function<void()>& body) { run_grid(c.grid, c.block, c.smem, body); }
+void note_smem_optin(const void* fn, int bytes);     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
+void check_smem_optin(const void* fn, size_t smem);   // aborts when a launch exceeds 48 KB without (enough) opt-in
+template <class F> inline const void* fn_key(F f) { return (const void*)f; }
+inline void run_grid_cfg(const Cfg& c, const std::function<void()>& body, const void* fn = nullptr) {
+  if (fn) check_smem_optin(fn, c.smem);
+  run_grid(c.grid, c.block, c.smem, body);
+}
 }  // namespace emu
 
 #define threadIdx (emu::cur_tid())
@@ -176,6 +182,9 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA runtime (tests/emu)"; }
-template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int attr, int v) {
+  if (attr == 8) emu::note_smem_optin((const void*)f, v);      // cudaFuncAttributeMaxDynamicSharedMemorySize
+  return 0;
+}
 inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) { *v = attr == 97 ? 232448 : attr == 16 ? 2 : 0; return 0; }
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return 0; }

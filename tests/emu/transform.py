@@ -33,6 +33,22 @@ def match_close(s, i, open_ch, close_ch):
     raise ValueError("unbalanced " + open_ch)
 
 
+
+def split_top(text):
+    """split at commas that are not nested in (), <>, [] or {}"""
+    parts, depth, cur = [], 0, []
+    for ch in text:
+        if ch in "([{<":
+            depth += 1
+        elif ch in ")]}>":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append("".join(cur)); cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur))
+    return parts
+
 def name_start(s, i):
     """start of the kernel name that ends right before s[i:] == '<<<'"""
     k = i
@@ -73,7 +89,13 @@ def transform(src):
         q = match_close(src, p, "(", ")")
         name, args = src[ns:i], src[p + 1:q]
         out.append(src[pos:ns])
-        out.append("emu::run_grid_cfg(emu::Cfg(%s), [&]() { %s(%s); })" % (cfg, name, args))
+        # a launch that asks for dynamic shared memory also hands over the kernel's address, so that the emulator can
+        # check the opt-in (cudaFuncSetAttribute) the hardware insists on above 48 KB
+        parts = split_top(cfg)
+        if len(parts) >= 3 and parts[2].strip() not in ("0", ""):
+            out.append("emu::run_grid_cfg(emu::Cfg(%s), [&]() { %s(%s); }, emu::fn_key(%s))" % (cfg, name, args, name))
+        else:
+            out.append("emu::run_grid_cfg(emu::Cfg(%s), [&]() { %s(%s); })" % (cfg, name, args))
         pos = q + 1
     s = "".join(out)
     # dynamic shared memory: file scope -> accessor macro, inside a function -> local pointer
