@@ -1,10 +1,11 @@
 #!/bin/bash
 # Memory check of the product's kernels without a GPU: the emulated build (tests/emu) compiled with AddressSanitizer.
 # Device buffers, shared-memory slots and dynamic shared memory are heap blocks there, so an out-of-bounds access of a
-# kernel is reported like compute-sanitizer's memcheck would.  Run from the repo root after `make`:  bash scripts/emu_asan.sh
+# kernel is reported like compute-sanitizer's memcheck would; -fsanitize=alignment stops at a vector-type access (int2, int4,
+# double2) through a pointer the device would reject as misaligned.  Run from the repo root after `make`:  bash scripts/emu_asan.sh
 set -e
 mkdir -p /tmp/cb_asan
-g++ -O1 -g -fsanitize=address -fno-omit-frame-pointer -march=x86-64-v3 -ffp-contract=fast -std=c++17 -fPIC -shared -pthread \
+g++ -O1 -g -fsanitize=address,alignment -fno-sanitize-recover=alignment -fno-omit-frame-pointer -march=x86-64-v3 -ffp-contract=fast -std=c++17 -fPIC -shared -pthread \
   -Wno-unknown-pragmas -Itests/emu/include -Itests/emu/gen -Iinclude -Iclarabel.rs_b200/csrc -o /tmp/cb_asan/libclarabel_emu_asan.so \
   tests/emu/gen/cones.cpp tests/emu/gen/cones_psd.cpp tests/emu/gen/cones_nonsym.cpp tests/emu/gen/solver.cpp tests/emu/gen/ldl.cpp \
   tests/emu/cuda_emu.cpp clarabel.rs_b200/csrc/ordering.cpp clarabel.rs_b200/csrc/symbolic.cpp clarabel.rs_b200/csrc/symbolic_api.cpp
@@ -27,8 +28,11 @@ pr = workloads.portfolio_socp(n_assets=120, n_soc=6, soc_dim=9, block=30, seed=7
 print("socp", cb.CudaSolver(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"]).solve()["status"], flush=True)
 pr = workloads.block_sdp(n=60, n_psd=4, psd_dim=5, nnz_per_row=3, window=20, n_nonneg=10, seed=4)
 print("sdp", cb.CudaSolver(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"]).solve()["status"], flush=True)
+ne = 40 * 41 // 2
+import scipy.sparse as sp
+print("psd40", cb.CudaSolver(sp.identity(ne, format="csc"), np.ones(ne), -sp.identity(ne, format="csc"), np.zeros(ne), [("psd", 40)]).solve()["status"], flush=True)
 pr = workloads.random_sparse_qp(n=400, m=800, nnz_per_row=4, seed=2, window=30)
 print("qp", cb.CudaSolver(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"], ordering=cb.ORDER_ND, nd_leaf=60).solve()["status"], flush=True)
 PY
-ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python /tmp/cb_asan/run.py
+UBSAN_OPTIONS=print_stacktrace=1 ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python /tmp/cb_asan/run.py
 echo "asan run finished without a report"

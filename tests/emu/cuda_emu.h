@@ -30,9 +30,10 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-struct int2 { int x, y; };
-struct int4 { int x, y, z, w; };
-struct double2 { double x, y; };
+struct alignas(8) int2 { int x, y; };       // same alignment as the CUDA vector types: -fsanitize=alignment
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
