@@ -389,6 +389,9 @@ class _DevBuf:
             self.a = torch.zeros(n, dtype=torch.float64, device=dev) if host is None else \
                 torch.as_tensor(np.ascontiguousarray(host, dtype=np.float64), device=dev).clone()
             self.ptr = self.a.data_ptr()
+            # the fill / copy above runs on torch's stream, the library works on streams of its own that do not wait
+            # for it: the buffer is handed out only when it is complete
+            torch.cuda.synchronize(dev)
 
     def to(self, device):
         """copy on another device (same object when it already lives there / in the emulated build)"""
@@ -398,6 +401,8 @@ class _DevBuf:
         out._torch = self._torch
         out.a = self.a.to(self._torch.device("cuda", int(device)))
         out.ptr = out.a.data_ptr()
+        self._torch.cuda.synchronize(self.a.device)      # the peer copy is complete before a library stream reads it
+        self._torch.cuda.synchronize(out.a.device)
         return out
 
     def numpy(self):
@@ -554,6 +559,8 @@ class ShardedLDLRank:
             torch.cuda.synchronize(self.device)
         allb = _DevBuf(mx * self.nranks, self.device)
         self._dist.all_gather_into_tensor(self._tensor(allb), self._tensor(mine))
+        if mine._torch is not None:
+            torch.cuda.synchronize(self.device)      # the collective runs on NCCL's stream; the unpack kernels on the library's
         for r in range(self.nranks):
             if r != self.rank:
                 _check(L.cldl_shard_unpack_dev(h, what, r, allb.ptr + 8 * mx * r, x.ptr if x is not None else None), "shard_unpack")

@@ -2978,7 +2978,11 @@ int cldl_set_transport(cldl_t* h, cldl_allgather_fn fn, void* ctx) {
   return CLDL_OK;
 }
 int cldl_copy_dev(void* d_dst, const void* d_src, uint64_t bytes) {
-  return bytes == 0 || cudaMemcpy(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
+  if (bytes == 0) return CLDL_OK;
+  // a device-to-device cudaMemcpy is queued on the default stream and may return before it has run; the handles work
+  // on non-blocking streams that do not wait for the default stream, so the copy is completed here
+  if (cudaMemcpy(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) return CLDL_E_CUDA;
+  return cudaStreamSynchronize(nullptr) == cudaSuccess ? CLDL_OK : CLDL_E_CUDA;
 }
 int cldl_shard_counts(const cldl_t* h, uint64_t* out4) {
   if (!h || !out4) return CLDL_E_ARG;
