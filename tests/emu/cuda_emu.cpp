@@ -8,6 +8,7 @@
 #include "cuda_emu.h"
 
 #include <sys/mman.h>
+#include <cstring>
 #include <mutex>
 #include <utility>
 
@@ -207,8 +208,19 @@ int guard_mode() {
 }
 }  // namespace
 
+// cudaMalloc does not clear memory: new allocations are filled with 0xCB bytes (a double of about -6e57, an int of about
+// -875 million), so that code which silently relies on zeroed device memory shows here.  EMU_POISON=0 turns it off.
+static int poison_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("EMU_POISON"); v = (e && !std::atoi(e)) ? 0 : 1; }
+  return v;
+}
 void* dev_alloc(size_t n) {
-  if (!guard_mode()) return std::calloc(1, n ? n : 1);
+  if (!guard_mode()) {
+    void* p = std::malloc(n ? n : 1);
+    if (p) std::memset(p, poison_mode() ? 0xCB : 0, n ? n : 1);
+    return p;
+  }
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g_arena) {
     g_cap = (size_t)64 << 30;
@@ -221,7 +233,9 @@ void* dev_alloc(size_t n) {
   void* p = g_arena + g_top;
   g_blocks.emplace_back(g_top, need);
   g_top += need;
-  if (g_open > 0) mprotect(p, need, PROT_READ | PROT_WRITE);
+  mprotect(p, need, PROT_READ | PROT_WRITE);
+  if (poison_mode()) std::memset(p, 0xCB, need);
+  if (g_open == 0) mprotect(p, need, PROT_NONE);
   return p;
 }
 void dev_free(void* p) {
