@@ -85,9 +85,15 @@ uint3& cur_tid() { return cur ? cur->tid : zero3; }
 uint3& cur_bid() { return cur ? cur->blk->idx : zero3; }
 void* dyn_smem() { return cur->blk->dyn.data(); }
 int lane_id() { return cur->lin & 31; }
+// shared memory is not cleared at block start on the device: 0xCB here as well (EMU_POISON=0: zeros)
+static int shared_fill() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("EMU_POISON"); v = (e && !std::atoi(e)) ? 0 : 0xCB; }
+  return v;
+}
 void* shared_slot(int id, size_t bytes) {
   void*& p = cur->blk->shared[id];
-  if (!p) { if (posix_memalign(&p, 64, bytes ? bytes : 8)) std::abort(); std::memset(p, 0, bytes ? bytes : 8); }
+  if (!p) { if (posix_memalign(&p, 64, bytes ? bytes : 8)) std::abort(); std::memset(p, shared_fill(), bytes ? bytes : 8); }
   return p;
 }
 
@@ -303,7 +309,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
         b.idx = uint3{bx, by, bz};
         b.first = ((int)blocks.size() - 1) * bt;
         b.nthreads = bt;
-        b.dyn.assign(smem + 64, 0);
+        b.dyn.assign(smem + 64, (char)shared_fill());
         b.warp_slot.assign((size_t)((bt + 31) / 32) * 32, 0);
         int lin = 0;
         for (unsigned tz = 0; tz < block.z; tz++)
