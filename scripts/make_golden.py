@@ -82,6 +82,23 @@ def main():
     b = b.copy(); b[:3] = 1e30
     write("presolve_redundant_cone", (P, c, A, b, cones), "tests/presolve.rs:63-83", "Solved", x=[-0.5, 2., -0.5], xtol=1e-6,
           notes="rows 0..2 have an infinite bound: z[0:3] = 0 and s[0:3] = 1e20 in the solution")
+    import test_oracle_psd as psd
+    write("basic_sdp", psd.sdp_data(), "tests/basic_sdp.rs:44-58", "Solved", x=psd.REFSOL, xtol=1e-6, obj=psd.REFOBJ, objtol=1e-6)
+    P, q, A, b, cones = psd.sdp_data()
+    write("basic_sdp_primal_infeasible", (P, q, sp.vstack([A, -A]).tocsc(), list(b) + [0.0] * 6, cones + cones),
+          "tests/basic_sdp.rs:78-95", "PrimalInfeasible")
+    I3 = sp.identity(3, format="csc")
+    write("basic_eq_constrained", (I3, [0., 0., 0.], rp.eq_A1(), [2., 0.], [("zero", 2)]), "tests/basic_eq_constrained.rs:35-50",
+          "Solved", x=[0., 1., 1.], xtol=1e-6)
+    write("basic_eq_constrained_primal_infeasible", (I3, [0.] * 3, rp.eq_A2(), [1.] * 4, [("zero", 4)]),
+          "tests/basic_eq_constrained.rs:52-65", "PrimalInfeasible")
+    Pd = sp.csc_matrix((np.array([0., 1., 1.]), np.array([0, 1, 2]), np.array([0, 1, 2, 3])), shape=(3, 3))
+    write("basic_eq_constrained_dual_infeasible", (Pd, [1.] * 3, rp.eq_A1(), [2., 0.], [("zero", 2)]),
+          "tests/basic_eq_constrained.rs:67-83", "DualInfeasible")
+    write("basic_unconstrained", (I3, [1., 2., -3.], sp.csc_matrix((0, 3)), [], []), "tests/basic_unconstrained.rs:6-22", "Solved",
+          x=[-1., -2., 3.], xtol=1e-6)
+    write("basic_unconstrained_dual_infeasible", (sp.csc_matrix((3, 3)), [1., 0., 0.], sp.csc_matrix((0, 3)), [], []),
+          "tests/basic_unconstrained.rs:24-40", "DualInfeasible")
     print("wrote", len(os.listdir(OUT)), "files to", OUT)
 
 
