@@ -58,6 +58,10 @@ def check_dimensions(P, q, A, b, cones):
         raise BadInputData("P not square")
 
 
+class DataUpdateError(ValueError):
+    """DataUpdateError (data_updating.rs:9-33): PresolveIsActive, BadVectorDimension, BadFormat"""
+
+
 class BackendError(RuntimeError):
     pass
 
@@ -810,6 +814,7 @@ class CudaSolver:
                               C.byref(self.settings), C.byref(o), _p(pm, C.c_uint64) if pm is not None else None)
         _check(rc, "cipm_create_gp")
         self._h = h
+        self._cur = {"P": Px.copy(), "q": qq.copy(), "A": Ax.copy(), "b": bb.copy()}      # for the (index, values) update form
         self.N = int(L.cipm_kkt_dim(h))
         self.m_reduced = int(L.cipm_m_reduced(h))    # rows left after the inf-bound presolve
         if shard is not None:
@@ -832,24 +837,47 @@ class CudaSolver:
         _check(self._L.cipm_update_settings(self._h, C.byref(s)), "cipm_update_settings")
         self.settings = s
 
+    def is_data_update_allowed(self):
+        """DefaultSolver::is_data_update_allowed (data_updating.rs:165-180): not while the presolver has removed rows"""
+        return self.m_reduced == self.m
+
     def update_data(self, P=None, q=None, A=None, b=None):
         """DefaultSolver::update_data (data_updating.rs:68-163): new values on the same sparsity patterns; the
-        symbolic analysis, the device plans and the equilibration scalings of the handle are reused."""
+        symbolic analysis, the device plans and the equilibration scalings of the handle are reused.  Every argument
+        takes the reference's three forms: a matrix / full vector, the vector of nonzero values, or a pair
+        `(index, values)` that overwrites single entries (`zip(&index, &values)` there); `None` or an empty
+        sequence leaves that part alone."""
         import scipy.sparse as sp
+        if not self.is_data_update_allowed():
+            raise DataUpdateError("PresolveIsActive")
 
-        def vals(M, triu):
-            if M is None:
+        def new_values(arg, current, triu):
+            if arg is None:
                 return None
-            if sp.issparse(M):
-                M = sp.csc_matrix(sp.triu(M, format="csc") if triu else M)
+            if sp.issparse(arg):
+                M = sp.csc_matrix(sp.triu(arg, format="csc") if triu else arg)
                 M.sort_indices()
-                return _f64(M.data)
-            return _f64(M)
-        Pv, Av = vals(P, True), vals(A, False)
-        qv = _f64(q) if q is not None else None
-        bv = _f64(b) if b is not None else None
+                v = _f64(M.data)
+            elif isinstance(arg, tuple) and len(arg) == 2 and not np.isscalar(arg[0]):
+                idx, val = np.asarray(arg[0], dtype=np.int64), _f64(arg[1])
+                if idx.size == 0:
+                    return None
+                v = current.copy()
+                v[idx] = val
+            else:
+                v = _f64(arg)
+                if v.size == 0:
+                    return None
+            if v.size != current.size:
+                raise DataUpdateError("BadVectorDimension" if current.ndim == 1 else "BadFormat")
+            return v
+        Pv, qv = new_values(P, self._cur["P"], True), new_values(q, self._cur["q"], False)
+        Av, bv = new_values(A, self._cur["A"], False), new_values(b, self._cur["b"], False)
         f = lambda a: _p(a, C.c_double) if a is not None else None
         _check(self._L.cipm_update_data(self._h, f(Pv), f(qv), f(Av), f(bv)), "cipm_update_data")
+        for k, v in (("P", Pv), ("q", qv), ("A", Av), ("b", bv)):
+            if v is not None:
+                self._cur[k] = v.copy()
 
     def close(self):
         if getattr(self, "_h", None):

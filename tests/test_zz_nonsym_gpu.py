@@ -186,7 +186,7 @@ def test_presolve_known_answers():
     b = np.full(2 * n, 1e30)
     dev, rd, ora, ro = both(P, c, A, b, cones)
     assert rd["status"] == "Solved" and dev.m_reduced == 0 and np.linalg.norm(rd["x"] + c) <= 1e-6
-    with pytest.raises(cb.BackendError):
+    with pytest.raises(cb.DataUpdateError):
         dev.update_data(q=c)          # data updates are refused on a presolved problem (data_updating.rs:165-180)
 
 
