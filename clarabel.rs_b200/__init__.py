@@ -41,6 +41,26 @@ def cone_nvars(kind, d):
     return int(d)
 
 
+def get_infinity():
+    """get_infinity (src/utils/infbounds.rs)"""
+    L = _lib2()
+    L.cipm_get_infinity.restype = C.c_double
+    return float(L.cipm_get_infinity())
+
+
+def set_infinity(v):
+    L = _lib2()
+    L.cipm_set_infinity.argtypes = [C.c_double]
+    L.cipm_set_infinity.restype = None
+    L.cipm_set_infinity(float(v))
+
+
+def default_infinity():
+    L = _lib2()
+    L.cipm_default_infinity.restype = None
+    L.cipm_default_infinity()
+
+
 def check_dimensions(P, q, A, b, cones):
     """check_dimensions of DefaultSolver::new (implementations/default/solver.rs:129-159): same tests, same order,
     same messages; pinned by tests/api_dimension_checks.rs"""
@@ -683,7 +703,7 @@ EXPORTED_SYMBOLS += [
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
-    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_get_equilibration", "cipm_create_gp",
+    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_get_equilibration", "cipm_get_infinity", "cipm_set_infinity", "cipm_default_infinity", "cipm_create_gp",
     "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
     "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes", "cldl_set_transport", "cipm_set_transport",
     "cldl_copy_dev", "cipm_update_settings",

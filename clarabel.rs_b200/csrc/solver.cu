@@ -28,6 +28,10 @@
 #include "ldl_device.h"
 #include "vec.cuh"
 
+// the bound beyond which a constraint counts as absent (src/utils/infbounds.rs: INFINITY_DEFAULT = 1e20, process-wide,
+// settable: get_infinity / set_infinity / default_infinity)
+static std::atomic<double> g_infinity{1e20};
+
 namespace cb {
 
 #define SCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "[clarabel_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return CLDL_E_CUDA; } } while (0)
@@ -836,7 +840,7 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   for (int j = 0; j < n; j++)
     for (int64_t t = P.colptr[j]; t < P.colptr[j + 1]; t++) if (P.rowval[t] > j) return CLDL_E_NOT_TRIU;
   q.assign(q_, q_ + n); b.assign(b_, b_ + m);
-  for (auto& v : b) v = std::min(v, 1e20);  // problemdata.rs:130-131
+  for (auto& v : b) v = std::min(v, g_infinity.load());  // problemdata.rs:130-131
   std::vector<ConeSpec> cs;
   int rc = ConeSet::collapse(ctype, cdim, ncones, cs, cparam, gp_dim2, gp_alpha);
   if (rc) return rc;
@@ -850,7 +854,7 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   // their cone; cipm_get_solution puts them back with s = bound, z = 0
   mfull = m; keep.clear();
   if (set.presolve_enable) {
-    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * 1e20;
+    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * g_infinity.load();
     std::vector<char> kp(m, 1);
     int mred = m, r = 0;
     for (auto& cc : cs) {
@@ -1380,7 +1384,7 @@ int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
     std::vector<cb::ConeSpec> cs;
     if (cb::ConeSet::collapse(cone_types, cone_dims, ncones, cs, cone_params, genpow_dim2, genpow_alpha)) { delete h; return CLDL_E_ARG; }
     uint64_t p = 0, rows = 0, dropped = 0;
-    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * 1e20;
+    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * g_infinity.load();
     for (auto& c : cs) {
       if (c.type == cb::CT_SOC && c.dim > cb::SOC_NO_EXPANSION_MAX_SIZE) p += 2;
       if (c.type == cb::CT_GENPOW) p += 3;
@@ -1453,7 +1457,7 @@ int cipm_get_solution(cipm_t* h, double* x, double* z, double* s) {
     int c = 0;
     for (int i = 0; i < I.mfull; i++) {
       if (I.keep[i]) { z[i] = hz[c] * I.e[c] * (scaleinv * cinv); s[i] = hs[c] * I.einv[c] * scaleinv; c++; }
-      else { z[i] = 0.0; s[i] = 1e20; }
+      else { z[i] = 0.0; s[i] = g_infinity.load(); }
     }
   }
   return CLDL_OK;
@@ -1497,6 +1501,9 @@ double cipm_time_ms(cipm_t* h, int which, int reps) {
   return (double)ms / reps;
 }
 
+double cipm_get_infinity(void) { return g_infinity.load(); }
+void cipm_set_infinity(double v) { g_infinity.store(v); }
+void cipm_default_infinity(void) { g_infinity.store(1e20); }
 uint64_t cipm_m_reduced(const cipm_t* h) { return h ? (uint64_t)h->ipm.m : 0; }
 
 // DefaultProblemData::equilibration (problemdata.rs:229-312): d [n], e [cipm_m_reduced] and the cost scaling c

@@ -274,6 +274,12 @@ uint64_t cipm_launch_count(void);
 void cipm_abi_sizes(uint64_t *out4);
 /* device-timed (CUDA events) average ms of: 0 numeric refactor, 1 one LDL solve, 2 one KKT solve incl. IR */
 double cipm_time_ms(cipm_t *h, int which, int reps);                            /* kernels launched by this library so far */
+/* get_infinity / set_infinity / default_infinity (src/src/utils/infbounds.rs; tests/presolve.rs:107-114): the
+ * process-wide bound (default 1e20) beyond which a nonnegative-cone row counts as absent in the presolve; read when a
+ * handle is created and when its solution is expanded. */
+double cipm_get_infinity(void);
+void cipm_set_infinity(double v);
+void cipm_default_infinity(void);
 uint64_t cipm_m_reduced(const cipm_t *h);   /* rows left after the inf-bound presolve (== m when nothing was dropped) */
 /* DefaultProblemData::equilibration (problemdata.rs:229-312; pinned by tests/equilibration_bounds.rs): the Ruiz
  * scalings d [n], e [cipm_m_reduced] and the cost scaling c of the handle; any of the three pointers may be NULL. */

@@ -338,6 +338,21 @@ def default_settings(**kw):
     return s
 
 
+def get_infinity():
+    L = _ipm_lib(); L.oipm_get_infinity.restype = C.c_double
+    return float(L.oipm_get_infinity())
+
+
+def set_infinity(v):
+    L = _ipm_lib(); L.oipm_set_infinity.argtypes = [C.c_double]; L.oipm_set_infinity.restype = None
+    L.oipm_set_infinity(float(v))
+
+
+def default_infinity():
+    L = _ipm_lib(); L.oipm_default_infinity.restype = None
+    L.oipm_default_infinity()
+
+
 def check_dimensions(P, q, A, b, cones):
     """check_dimensions (src/solver/implementations/default/solver.rs:129-159), the order of the tests included;
     SupportedConeT::nvars as in supportedcone.rs:54-71"""

@@ -87,6 +87,12 @@ int oq_dinv_is_finite(const oq_t *f);
 idx oq_nnzL(const oq_t *f);
 idx oq_regularize_count(const oq_t *f);
 
+/* src/utils/infbounds.rs:10-40: the process-wide "infinite" bound, default 1e20 */
+static double g_infinity = 1e20;
+double oipm_get_infinity(void) { return g_infinity; }
+void oipm_set_infinity(double v) { g_infinity = v; }
+void oipm_default_infinity(void) { g_infinity = 1e20; }
+
 enum { CONE_ZERO = 0, CONE_NONNEG = 1, CONE_SOC = 2, CONE_PSD = 3, CONE_EXP = 4, CONE_POW = 5, CONE_GENPOW = 6 };
 enum { SCALING_PRIMAL_DUAL = 0, SCALING_DUAL = 1 };
 enum { ST_UNSOLVED = 0, ST_SOLVED, ST_PRIMAL_INFEASIBLE, ST_DUAL_INFEASIBLE, ST_ALMOST_SOLVED,
@@ -1248,7 +1254,7 @@ int oipm_new_gp(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
     csc_copy(&S->A, m, n, Ap, Ai, Ax);
     S->q = dvec(n); memcpy(S->q, q, (size_t)n * sizeof(double));
     S->b = dvec(m); memcpy(S->b, b, (size_t)m * sizeof(double));
-    for (idx i = 0; i < m; i++) if (S->b[i] > 1e20) S->b[i] = 1e20;
+    for (idx i = 0; i < m; i++) if (S->b[i] > g_infinity) S->b[i] = g_infinity;
     /* collapse cones */
     S->cones = (cone_t *)calloc((size_t)(ncones_in > 0 ? ncones_in : 1), sizeof(cone_t));
     idx nc = 0, k = 0;
@@ -1306,7 +1312,7 @@ int oipm_new_gp(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
        dropped from A, b and their cone.  b was capped at the bound above, which still compares as "beyond" it. */
     S->mfull = m; S->keep = NULL;
     if (S->set.presolve_enable) {
-        const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * 1e20;
+        const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * g_infinity;
         char *keep = (char *)malloc((size_t)(m > 0 ? m : 1));
         idx mred = m, r = 0;
         for (idx i = 0; i < m; i++) keep[i] = 1;
@@ -1757,7 +1763,7 @@ void oipm_get_solution(oipm_t *S, double *x, double *z, double *s, double *obj, 
         idx c = 0;
         for (idx i = 0; i < S->mfull; i++) {
             if (S->keep[i]) { z[i] = S->vz[c] * S->e[c] * (scaleinv * cinv); s[i] = S->vs[c] * S->einv[c] * scaleinv; c++; }
-            else { z[i] = 0.0; s[i] = 1e20; }
+            else { z[i] = 0.0; s[i] = g_infinity; }
         }
     }
     *obj = infeas ? NAN : S->info.cost_primal;

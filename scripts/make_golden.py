@@ -99,6 +99,12 @@ def main():
           x=[-1., -2., 3.], xtol=1e-6)
     write("basic_unconstrained_dual_infeasible", (sp.csc_matrix((3, 3)), [1., 0., 0.], sp.csc_matrix((0, 3)), [], []),
           "tests/basic_unconstrained.rs:24-40", "DualInfeasible")
+    I1 = sp.identity(1, format="csc")
+    write("basic_qp_univariate", (I1, [0.], I1, [1.], [("nonneg", 1)]), "tests/basic_qp.rs:80-97", "Solved", x=[0.], xtol=1e-6,
+          obj=0.0, objtol=1e-6)
+    Pd, cd, _, _, _ = rp.basic_qp_dual_inf()
+    write("basic_qp_dual_infeasible_ill_cond", (Pd, cd, sp.csc_matrix(np.array([[1., 1.]])), [1.], [("nonneg", 1)]),
+          "tests/basic_qp.rs:178-204", "DualInfeasible")
     print("wrote", len(os.listdir(OUT)), "files to", OUT)
 
 

@@ -56,3 +56,12 @@ def test_struct_mirrors_have_the_compiled_sizes():
     L.cipm_abi_sizes(out.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert [int(v) for v in out] == [C.sizeof(cb.pkg.cldl_opts), C.sizeof(cb.pkg.cldl_info_t), C.sizeof(cb.pkg.cipm_settings),
                                       C.sizeof(cb.pkg.cipm_info)]
+
+
+def test_settable_infinity_bound():      # presolve.rs:107-114 (host state of the library: no device needed)
+    cb.default_infinity()
+    d = cb.get_infinity()
+    cb.set_infinity(1e21)
+    assert cb.get_infinity() == 1e21
+    cb.default_infinity()
+    assert cb.get_infinity() == d == 1e20

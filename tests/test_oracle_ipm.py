@@ -33,6 +33,37 @@ def test_qp_singleton_cones_identical():  # basic_qp.rs:119-142 (bit-identical r
         assert np.array_equal(r["x"], r1["x"])
 
 
+def test_qp_univariate():  # basic_qp.rs:80-97
+    I1 = sp.identity(1, format="csc")
+    _, r = solve(I1, [0.], I1, [1.], [("nonneg", 1)])
+    assert r["status"] == "Solved"
+    assert abs(r["x"][0]) <= 1e-6 and abs(r["obj_val"]) <= 1e-6 and abs(r["info"].cost_dual) <= 1e-6
+
+
+def test_qp_dual_infeasible_ill_cond():  # basic_qp.rs:178-204
+    P, c, _, _, _ = rp.basic_qp_dual_inf()
+    _, r = solve(P, c, sp.csc_matrix(np.array([[1., 1.]])), [1.], [("nonneg", 1)])
+    assert r["status"] == "DualInfeasible"
+
+
+def test_presolve_settable_bound():  # presolve.rs:107-114
+    oracle.default_infinity()
+    d = oracle.get_infinity()
+    assert d == 1e20
+    oracle.set_infinity(1e21)
+    assert oracle.get_infinity() == 1e21
+    # the bound is what the presolve compares with: 5e20 is finite under 1e21 and infinite under 1e20
+    n = 3
+    P = sp.identity(n, format="csc"); A = (2.0 * sp.vstack([sp.identity(n), -sp.identity(n)])).tocsc()
+    b = np.ones(2 * n); b[3] = 5e20
+    ipm = oracle.IPM(P, [3., -2., 1.], A, b, [("nonneg", 3), ("nonneg", 3)])
+    assert ipm.m_reduced == 6
+    oracle.default_infinity()
+    assert oracle.get_infinity() == d
+    ipm = oracle.IPM(P, [3., -2., 1.], A, b, [("nonneg", 3), ("nonneg", 3)])
+    assert ipm.m_reduced == 5
+
+
 def test_qp_primal_infeasible():  # basic_qp.rs:144-160
     P, q, A, b, cones = rp.basic_qp()
     b = list(b); b[0] = -1.; b[3] = -1.

@@ -58,3 +58,21 @@ def test_scalings_equal_the_oracles_on_a_mixed_problem():
     ora = oracle.IPM(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"])
     for x, y in zip(dev.equilibration(), ora.equilibration()):
         assert np.array_equal(np.asarray(x), np.asarray(y))      # same host arithmetic, same order: bit for bit
+
+
+def test_presolve_settable_bound():      # presolve.rs:107-114, and what the bound does
+    import scipy.sparse as sp
+    cb.default_infinity()
+    d = cb.get_infinity()
+    assert d == 1e20
+    n = 3
+    P = sp.identity(n, format="csc"); A = (2.0 * sp.vstack([sp.identity(n), -sp.identity(n)])).tocsc()
+    b = np.ones(2 * n); b[3] = 5e20
+    try:
+        cb.set_infinity(1e21)
+        assert cb.get_infinity() == 1e21
+        assert cb.CudaSolver(P, [3., -2., 1.], A, b, [("nonneg", 3), ("nonneg", 3)]).m_reduced == 6
+    finally:
+        cb.default_infinity()
+    assert cb.get_infinity() == d
+    assert cb.CudaSolver(P, [3., -2., 1.], A, b, [("nonneg", 3), ("nonneg", 3)]).m_reduced == 5
