@@ -1793,3 +1793,19 @@ void oipm_test_affine_ds_ex(oipm_t *S, double *ds, const double *s) { cones_affi
 void oipm_test_combined_ds_shift(oipm_t *S, double *shift, double *sz, double *ss, double sm) { cones_combined_ds_shift(S, shift, sz, ss, sm); }
 void oipm_test_ds_from_dz_offset(oipm_t *S, double *out, const double *ds, const double *z) { cones_ds_from_dz_offset(S, out, ds, z); }
 double oipm_test_step_length(oipm_t *S, const double *dz, const double *ds, const double *z, const double *s, double amax) { return cones_step_length(S, dz, ds, z, s, amax); }
+
+
+/* ---- test hooks for the algebra kernels of SURVEY 8 rows a11 / a20, pinned on the reference's own known answers
+ * (src/algebra/tests/matrix.rs: test_gemv, test_symv, test_quad_form; src/algebra/tests/vector.rs: test_norm*,
+ * test_dot) by tests/test_oracle_algebra.py ---- */
+static csc hook_csc(idx m, idx n, const idx *cp, const idx *rv, const double *nz)
+{ csc A; A.m = m; A.n = n; A.colptr = (idx *)cp; A.rowval = (idx *)rv; A.nzval = (double *)nz; return A; }
+void oipm_test_symv(idx n, const idx *cp, const idx *rv, const double *nz, double *y, const double *x, double a, double b)
+{ csc A = hook_csc(n, n, cp, rv, nz); symv_tri(&A, y, x, a, b); }
+double oipm_test_quad_form(idx n, const idx *cp, const idx *rv, const double *nz, const double *y, const double *x)
+{ csc A = hook_csc(n, n, cp, rv, nz); return quad_form_triu(&A, y, x); }
+void oipm_test_gemv(idx m, idx n, const idx *cp, const idx *rv, const double *nz, int transposed, double *y, const double *x,
+                    double a, double b)
+{ csc A = hook_csc(m, n, cp, rv, nz); if (transposed) gemv_T(&A, y, x, a, b); else gemv_N(&A, y, x, a, b); }
+double oipm_test_vec(int what, const double *x, const double *v, idx n)
+{ return what == 0 ? vnorm(x, n) : what == 1 ? vnorm_inf(x, n) : what == 2 ? vnorm_scaled(x, v, n) : vdot(x, v, n); }
