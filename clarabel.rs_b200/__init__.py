@@ -703,7 +703,7 @@ EXPORTED_SYMBOLS += [
     "ccone_Hs_len", "ccone_get_Hs", "ccone_mul_Hs", "ccone_affine_ds", "ccone_combined_ds_shift",
     "ccone_ds_from_dz_offset", "ccone_step_length", "ccone_margins", "ccone_scaled_unit_shift",
     "cipm_create_ex", "ccone_is_symmetric", "ccone_unit_initialization", "ccone_update_scaling_ex",
-    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_get_equilibration", "cipm_get_infinity", "cipm_set_infinity", "cipm_default_infinity", "cipm_create_gp",
+    "ccone_affine_ds_ex", "ccone_compute_barrier", "cipm_m_reduced", "cipm_get_equilibration", "cipm_get_infinity", "cipm_set_infinity", "cipm_default_infinity", "cipm_test_spmv", "cipm_test_vec", "cipm_create_gp",
     "cldl_shard_refactor_phase_dev", "cldl_shard_solve_phase_dev", "cldl_shard_count", "cldl_shard_pack_dev",
     "cldl_shard_unpack_dev", "cldl_shard_counts", "cipm_abi_sizes", "cldl_set_transport", "cipm_set_transport",
     "cldl_copy_dev", "cipm_update_settings",
@@ -842,6 +842,23 @@ class CudaSolver:
             # triangular solves are split and meet through this all-gather
             self._transport = transport if transport is not None else TorchDistTransport(device)
             _check(L.cipm_set_transport(h, self._transport.fn, None), "cipm_set_transport")
+
+    def test_spmv(self, which, y, x, a, b):
+        """kernel-level check: which = 0  a P x + b y, 1  a A x + b y, 2  a A' x + b y on the handle's (equilibrated) data"""
+        y, x = _f64(y).copy(), _f64(x)
+        self._L.cipm_test_spmv.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double]
+        _check(self._L.cipm_test_spmv(self._h, which, _p(y, C.c_double), _p(x, C.c_double), a, b), "cipm_test_spmv")
+        return y
+
+    def test_vec(self, what, x, v=None):
+        """kernel-level check: what = 0  ||x||, 1  ||x||_inf, 2  ||x .* v||, 3  <x, v>"""
+        x = _f64(x)
+        v = _f64(v) if v is not None else x
+        out = C.c_double(0.0)
+        self._L.cipm_test_vec.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double)]
+        xx, vv = (x if x.size else np.zeros(1)), (v if v.size else np.zeros(1))
+        _check(self._L.cipm_test_vec(self._h, what, _p(xx, C.c_double), _p(vv, C.c_double), x.size, C.byref(out)), "cipm_test_vec")
+        return out.value
 
     def equilibration(self):
         """(d, e, c) of DefaultProblemData::equilibration (problemdata.rs:229-312)"""

@@ -1573,6 +1573,46 @@ int ckkt_solve(cipm_t* h, double* lhsx, double* lhsz) {
   if ((lhsx && d2h(lhsx, I.x1, I.n)) || (lhsz && d2h(lhsz, I.z1, I.m))) return CLDL_E_CUDA;
   return 1;
 }
+// The sparse products and reductions of the iteration body on caller data, for kernel-level parity tests
+// (algebra/csc/matrix_math.rs, algebra/vecmath.rs; the reference's own known answers are in src/algebra/tests).
+// which: 0  y = a P x + b y (P symmetric, the handle's equilibrated copy), 1  y = a A x + b y, 2  y = a A' x + b y
+int cipm_test_spmv(cipm_t* h, int which, double* y, const double* x, double a, double b) {
+  if (!h || which < 0 || which > 2) return CLDL_E_ARG;
+  IPM& I = h->ipm;
+  if (cudaSetDevice(I.kkt.ldl.device) != cudaSuccess) return CLDL_E_CUDA;
+  const int ny = which == 1 ? I.m : I.n, nx = which == 1 ? I.n : (which == 2 ? I.m : I.n);
+  double *dy = nullptr, *dx = nullptr;
+  if (cudaMalloc((void**)&dy, (size_t)(ny ? ny : 1) * 8) != cudaSuccess || cudaMalloc((void**)&dx, (size_t)(nx ? nx : 1) * 8) != cudaSuccess) return CLDL_E_CUDA;
+  int rc = (h2d(dy, y, ny) || h2d(dx, x, nx)) ? CLDL_E_CUDA : CLDL_OK;
+  if (!rc) {
+    I.spmv(which == 0 ? I.Psym : (which == 1 ? I.Acsr : I.Atcsr), dy, dx, a, b);
+    cudaStreamSynchronize(I.st);
+    rc = d2h(y, dy, ny) ? CLDL_E_CUDA : CLDL_OK;
+  }
+  cudaFree(dy); cudaFree(dx);
+  return rc;
+}
+// what: 0  ||x||_2, 1  ||x||_inf (NaN propagates), 2  ||x .* v||_2, 3  <x, v>
+int cipm_test_vec(cipm_t* h, int what, const double* x, const double* v, uint64_t n, double* out) {
+  if (!h || !out || what < 0 || what > 3) return CLDL_E_ARG;
+  IPM& I = h->ipm;
+  if (cudaSetDevice(I.kkt.ldl.device) != cudaSuccess) return CLDL_E_CUDA;
+  double *dx = nullptr, *dv = nullptr, *dout = nullptr;
+  const size_t nb = (size_t)(n ? n : 1) * 8;
+  if (cudaMalloc((void**)&dx, nb) != cudaSuccess || cudaMalloc((void**)&dv, nb) != cudaSuccess || cudaMalloc((void**)&dout, 8) != cudaSuccess) return CLDL_E_CUDA;
+  int rc = (h2d(dx, x, n) || h2d(dv, v ? v : x, n)) ? CLDL_E_CUDA : CLDL_OK;
+  if (!rc) {
+    if (what == 0) I.V.dot(dx, dx, (int)n, dout);
+    else if (what == 1) I.V.norm_inf(dx, (int)n, dout);
+    else if (what == 2) I.V.sumsq_scaled(dx, dv, (int)n, dout);
+    else I.V.dot(dx, dv, (int)n, dout);
+    cudaStreamSynchronize(I.st);
+    rc = d2h(out, dout, 1) ? CLDL_E_CUDA : CLDL_OK;
+    if (!rc && (what == 0 || what == 2)) *out = std::sqrt(*out);
+  }
+  cudaFree(dx); cudaFree(dv); cudaFree(dout);
+  return rc;
+}
 int cipm_update_data(cipm_t* h, const double* P_nzval, const double* q, const double* A_nzval, const double* b) {
   if (!h) return CLDL_E_ARG;
   return h->ipm.update_data(P_nzval, q, A_nzval, b);

@@ -274,6 +274,13 @@ uint64_t cipm_launch_count(void);
 void cipm_abi_sizes(uint64_t *out4);
 /* device-timed (CUDA events) average ms of: 0 numeric refactor, 1 one LDL solve, 2 one KKT solve incl. IR */
 double cipm_time_ms(cipm_t *h, int which, int reps);                            /* kernels launched by this library so far */
+/* Kernel-level test entry points: the sparse products and the reductions of the iteration body on caller data
+ * (src/algebra/csc/matrix_math.rs:178-343, src/algebra/vecmath.rs:83-226), so that they can be compared with the
+ * reference's own unit-test answers (src/algebra/tests/matrix.rs, vector.rs).
+ * cipm_test_spmv: which = 0  y = a P x + b y (the handle's symmetric P), 1  y = a A x + b y, 2  y = a A' x + b y.
+ * cipm_test_vec:  what = 0  ||x||_2, 1  ||x||_inf (NaN propagates), 2  ||x .* v||_2, 3  <x, v>. */
+int cipm_test_spmv(cipm_t *h, int which, double *y, const double *x, double a, double b);
+int cipm_test_vec(cipm_t *h, int what, const double *x, const double *v, uint64_t n, double *out);
 /* get_infinity / set_infinity / default_infinity (src/src/utils/infbounds.rs; tests/presolve.rs:107-114): the
  * process-wide bound (default 1e20) beyond which a nonnegative-cone row counts as absent in the presolve; read when a
  * handle is created and when its solution is expanded. */

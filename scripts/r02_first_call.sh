@@ -9,7 +9,7 @@ O=gpurun_out
 # 1. the tests that never ran on a device (nonsymmetric cones, generalised power cone, presolve), verbose, no -x
 timeout 600 python -m pytest tests/test_zz_nonsym_gpu.py -q -m gpu -rA > $O/r02_nonsym_tests.log 2>&1
 echo "nonsym tests exit $?" > $O/r02_summary.txt
-timeout 600 python -m pytest tests/test_zz_shard_gpu.py tests/test_zz_golden.py tests/test_zz_psd_large_gpu.py tests/test_zz_equilibration_gpu.py tests/test_zz_data_updating_gpu.py -q -m gpu -rA > $O/r02_shard_golden_tests.log 2>&1
+timeout 600 python -m pytest tests/test_zz_shard_gpu.py tests/test_zz_golden.py tests/test_zz_psd_large_gpu.py tests/test_zz_equilibration_gpu.py tests/test_zz_data_updating_gpu.py tests/test_zz_algebra_gpu.py -q -m gpu -rA > $O/r02_shard_golden_tests.log 2>&1
 echo "shard + golden tests exit $?" >> $O/r02_summary.txt
 # 2. the whole GPU suite as the driver runs it
 timeout 900 python -m pytest tests -x -q -m gpu > $O/r02_gpu_tests.log 2>&1
