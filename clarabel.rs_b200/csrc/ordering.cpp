@@ -306,6 +306,10 @@ struct NDShared {
   int leaf_size = 200;
   int par_depth = 0;
   bool halo = false;       // halo-AMD on the leaves (CB_ND_HALO)
+  // a separator of k vertices is a dense k x k block at the top of its subtree: k^3 / 3 flops.  Beyond this cap the whole
+  // dissection is given up (the caller falls back to minimum degree); 0 = never
+  double sep_flop_cap = 0.0;
+  std::atomic<bool> hopeless{false};
 };
 
 // BFS restricted to vertices with part[v]==region; returns eccentricity, fills queue and level[].
@@ -386,6 +390,7 @@ void nd_leaf(NDShared& W, const std::vector<int>& verts, std::vector<int>& out) 
 }
 
 void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& out) {
+  if (W.hopeless.load(std::memory_order_relaxed)) return;
   const double t_enter = onow();
   const size_t total = verts.size();
   if ((int)total <= W.leaf_size) { nd_leaf(W, verts, out); return; }
@@ -554,6 +559,10 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
   // (hub rows) give neither, and the region is then left to AMD as a whole
   const size_t smaller = std::min(L.size(), R.size());
   if (sep.size() * 5 > total || smaller * 20 < total) { nd_leaf(W, verts, out); return; }
+  if (W.sep_flop_cap > 0.0 && (double)sep.size() * (double)sep.size() * (double)sep.size() / 3.0 > W.sep_flop_cap) {
+    W.hopeless.store(true);
+    return;
+  }
   if (depth <= 2 && std::getenv("CB_TIMING")) std::fprintf(stderr, "[cb timing]   nd: depth %d bisection of %zu: %.4f s (sep %zu)\n", depth, total, onow() - t_enter, sep.size());
   for (int v : sep) W.part[v] = -1;
   std::vector<int>().swap(verts);
@@ -576,7 +585,7 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
 }  // namespace
 
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
-              int leaf_size, std::vector<int>& perm) {
+              int leaf_size, std::vector<int>& perm, double sep_flop_cap) {
   double ot_last = onow();
   std::vector<int64_t> xadj;
   std::vector<int> adj;
@@ -595,6 +604,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
   W.level.assign(n, -1);
   W.local.assign(n, -1);
   W.leaf_size = leaf_size;
+  W.sep_flop_cap = sep_flop_cap;
   W.halo = std::getenv("CB_ND_HALO") != nullptr && std::atoi(std::getenv("CB_ND_HALO")) != 0;
   {
     unsigned hc = std::thread::hardware_concurrency();
@@ -623,6 +633,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
         }
       }
       nd_rec(W, comp, 0, perm);
+      if (W.hopeless.load()) { perm.clear(); OMARK("dissection given up (separator beyond the flop cap)"); return; }
     }
   }
   OMARK("dissection + leaf AMD");

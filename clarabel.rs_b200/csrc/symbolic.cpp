@@ -754,7 +754,18 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
         if ((int)pa.size() == n && !amd_cancel.load()) ra = build(n, Ap, Ai, pa, opt, Sa, true);
       });
     struct Joiner { std::thread& t; std::atomic<bool>& c; ~Joiner() { if (t.joinable()) { c.store(true); t.join(); } } } joiner{amd_thread, amd_cancel};
-    nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, pn);
+    // the dissection stops by itself when a single separator is already beyond the flop cap used below (C4: the first
+    // cut of the 2.5e6-vertex graph has 3.3e5 vertices): minimum degree is then the only candidate
+    nd_order(n, Ap, Ai, opt.amd_dense_scale, opt.nd_leaf, pn, exhaustive ? 0.0 : 1e12);
+    if (pn.empty() && !exhaustive) {
+      if (speculative) amd_thread.join();
+      else {
+        amd_order(n, Ap, Ai, opt.amd_dense_scale, pa);
+      }
+      if ((int)pa.size() != n) return -6;
+      S.ordering_used = ORDER_AMD;
+      return build(n, Ap, Ai, pa, opt, S, false);
+    }
     if ((int)pn.size() != n) return -6;
     const std::function<bool(const Symbolic&)> amd_cannot_pay = [&](const Symbolic& sn) {
       if (exhaustive) return false;

@@ -20,8 +20,9 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
 // cancel (optional): set by another thread to make the pass return early with an empty order
 void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
                std::vector<int>& perm, const std::atomic<bool>* cancel = nullptr);
+// sep_flop_cap > 0: give up (empty perm) as soon as one separator alone costs more than that many flops as a dense block
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
-              int leaf_size, std::vector<int>& perm);
+              int leaf_size, std::vector<int>& perm, double sep_flop_cap = 0.0);
 
 enum OrderingKind { ORDER_GIVEN = 0, ORDER_AMD = 1, ORDER_ND = 2, ORDER_BEST = 3 };
 
