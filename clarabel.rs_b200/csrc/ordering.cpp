@@ -306,6 +306,7 @@ struct NDShared {
   int leaf_size = 200;
   int par_depth = 0;
   bool halo = false;       // halo-AMD on the leaves (CB_ND_HALO)
+  bool hubs = true;        // hub separators for small-world regions (CB_ND_HUBS=0 turns them off)
   // a separator of k vertices is a dense k x k block at the top of its subtree: k^3 / 3 flops.  Beyond this cap the whole
   // dissection is given up (the caller falls back to minimum degree); 0 = never
   double sep_flop_cap = 0.0;
@@ -389,6 +390,109 @@ void nd_leaf(NDShared& W, const std::vector<int>& verts, std::vector<int>& out) 
   for (int k = 0; k < m; k++) W.local[verts[k]] = -1;
 }
 
+
+// Hub separator for small-world regions.  A BFS level structure has no thin level when a few vertices (linking rows of
+// a block-angular problem, coupling constraints) join parts of the graph that are otherwise far apart.  Such vertices
+// have above-typical degree, so: withhold the top fraction of the region by degree, label the components of the rest,
+// and then give back every withheld vertex that touches at most one sizeable component (it joins that component; tiny
+// components it touches are merged in).  What cannot be given back is a vertex separator: the real connectors.  The
+// degree only proposes candidates; connectivity decides.  Returns true with `sep` filled when the remainder falls into
+// components none of which holds more than 70 % of the region and the separator is below 5 % of it.
+bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::vector<int>& sep) {
+  const int total = (int)verts.size();
+  std::vector<int> deg(total), comp(total), cpar, csize, stack, sorted;
+  for (int k = 0; k < total; k++) W.local[verts[k]] = k;
+  for (int k = 0; k < total; k++) {
+    const int v = verts[k];
+    int d = 0;
+    for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) if (W.part[(*W.adj)[p]] == region) d++;
+    deg[k] = d;
+  }
+  sorted = deg;
+  std::sort(sorted.begin(), sorted.end());
+  const int median = sorted[total / 2];
+  const int tiny = std::max(64, W.leaf_size / 8);
+  auto find = [&](int c) { while (cpar[c] != c) { cpar[c] = cpar[cpar[c]]; c = cpar[c]; } return c; };
+  bool ok = false;
+  int last_thr = -1;
+  const double fracs[] = {0.0005, 0.002, 0.005, 0.02, 0.05, 0.1, 0.2};
+  for (double f : fracs) {
+    int thr = sorted[std::min<int64_t>(total - 1, (int64_t)((1.0 - f) * total))];
+    if (thr <= median) thr = median + 1;
+    if (thr == last_thr) continue;
+    last_thr = thr;
+    int64_t ns0 = 0;
+    for (int k = 0; k < total; k++) { comp[k] = deg[k] >= thr ? -2 : -1; if (comp[k] == -2) ns0++; }
+    if (ns0 == 0) continue;
+    if (ns0 * 10 > (int64_t)total * 3) break;
+    cpar.clear(); csize.clear();
+    for (int k0 = 0; k0 < total; k0++) {
+      if (comp[k0] != -1) continue;
+      const int c = (int)cpar.size();
+      cpar.push_back(c); csize.push_back(0);
+      stack.clear(); stack.push_back(k0); comp[k0] = c;
+      while (!stack.empty()) {
+        const int k = stack.back(); stack.pop_back();
+        csize[c]++;
+        const int v = verts[k];
+        for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+          const int u = (*W.adj)[p];
+          if (W.part[u] != region) continue;
+          const int ku = W.local[u];
+          if (comp[ku] == -1) { comp[ku] = c; stack.push_back(ku); }
+        }
+      }
+    }
+    int64_t largest = 0;
+    for (int c : csize) largest = std::max<int64_t>(largest, c);
+    if (largest * 10 > (int64_t)total * 6) continue;            // the rest still hangs together: withhold more
+    // give back what is not a connector
+    for (int pass = 0; pass < 8; pass++) {
+      int64_t moved = 0;
+      for (int k = 0; k < total; k++) {
+        if (comp[k] != -2) continue;
+        const int v = verts[k];
+        int big = -1, small = -1;
+        bool two = false;
+        for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1] && !two; p++) {
+          const int u = (*W.adj)[p];
+          if (W.part[u] != region) continue;
+          const int cu = comp[W.local[u]];
+          if (cu < 0) continue;
+          const int r = find(cu);
+          if (csize[r] > tiny) { if (big >= 0 && big != r) two = true; big = r; }
+          else small = r;
+        }
+        if (two) continue;
+        int target = big >= 0 ? big : small;
+        if (target < 0) continue;                               // all neighbours withheld: decided in a later pass
+        for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
+          const int u = (*W.adj)[p];
+          if (W.part[u] != region) continue;
+          const int cu = comp[W.local[u]];
+          if (cu < 0) continue;
+          const int r = find(cu);
+          if (r != target) { cpar[r] = target; csize[target] += csize[r]; }
+        }
+        comp[k] = target; csize[target]++;
+        moved++;
+      }
+      if (!moved) break;
+    }
+    int64_t nsep = 0;
+    largest = 0;
+    for (int k = 0; k < total; k++) if (comp[k] == -2) nsep++;
+    for (size_t c = 0; c < cpar.size(); c++) if (cpar[c] == (int)c) largest = std::max<int64_t>(largest, csize[c]);
+    if (largest * 10 > (int64_t)total * 7 || nsep * 20 > (int64_t)total || nsep == 0) continue;
+    sep.clear();
+    for (int k = 0; k < total; k++) if (comp[k] == -2) sep.push_back(verts[k]);
+    ok = true;
+    break;
+  }
+  for (int v : verts) W.local[v] = -1;
+  return ok;
+}
+
 void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& out) {
   if (W.hopeless.load(std::memory_order_relaxed)) return;
   const double t_enter = onow();
@@ -418,6 +522,7 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
     // packed together into leaves (independent pieces cost AMD nothing extra)
     for (int v : verts) W.level[v] = -1;
     std::vector<int> pack, comp;
+    std::vector<std::vector<int>> bigs;
     for (int sv : verts) {
       if (W.level[sv] >= 0) continue;
       comp.clear(); comp.push_back(sv); W.level[sv] = 0;
@@ -429,14 +534,28 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
         }
       }
       if ((int)comp.size() > W.leaf_size) {
-        std::vector<int> sub = comp;
-        nd_rec(W, sub, depth + 1, out);
+        bigs.emplace_back(comp);
       } else {
         pack.insert(pack.end(), comp.begin(), comp.end());
         if ((int)pack.size() >= 4 * W.leaf_size) { nd_leaf(W, pack, out); pack.clear(); }
       }
     }
     if (!pack.empty()) nd_leaf(W, pack, out);
+    // the sizeable components are independent subproblems: ordered concurrently while the thread budget lasts
+    // (k components count as log2(k) levels of the recursion's thread tree)
+    int dd = depth + 1;
+    for (size_t k = 1; k < bigs.size(); k <<= 1) dd++;
+    if (bigs.size() > 1 && depth < W.par_depth) {
+      std::vector<std::vector<int>> outs(bigs.size());
+      std::vector<std::future<void>> futs;
+      for (size_t b = 1; b < bigs.size(); b++)
+        futs.push_back(std::async(std::launch::async, [&, b]() { nd_rec(W, bigs[b], dd, outs[b]); }));
+      nd_rec(W, bigs[0], dd, outs[0]);
+      for (auto& f : futs) f.get();
+      for (auto& o : outs) out.insert(out.end(), o.begin(), o.end());
+    } else {
+      for (auto& b : bigs) nd_rec(W, b, depth + 1, out);
+    }
     return;
   }
   if (e < 2) { nd_leaf(W, verts, out); return; }   // clique-like, cannot bisect
@@ -558,8 +677,27 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
   // a level-structure cut is only worth keeping when it is thin and roughly balanced; small-world graphs
   // (hub rows) give neither, and the region is then left to AMD as a whole
   const size_t smaller = std::min(L.size(), R.size());
-  if (sep.size() * 5 > total || smaller * 20 < total) { nd_leaf(W, verts, out); return; }
-  if (W.sep_flop_cap > 0.0 && (double)sep.size() * (double)sep.size() * (double)sep.size() / 3.0 > W.sep_flop_cap) {
+  const bool poor_cut = sep.size() * 5 > total || smaller * 20 < total;
+  const bool beyond_cap = W.sep_flop_cap > 0.0 && (double)sep.size() * (double)sep.size() * (double)sep.size() / 3.0 > W.sep_flop_cap;
+  // a separator above 2 % of a large region is fat: look for connectors before accepting it
+  if ((poor_cut || beyond_cap || sep.size() * 50 > total) && (int)total >= 50 * W.leaf_size && W.hubs) {
+    std::vector<int> hsep;
+    if (hub_separator(W, q, region, hsep) && (poor_cut || beyond_cap || hsep.size() * 2 < sep.size()) &&
+        !(W.sep_flop_cap > 0.0 && (double)hsep.size() * (double)hsep.size() * (double)hsep.size() / 3.0 > W.sep_flop_cap)) {
+      if (std::getenv("CB_TIMING")) std::fprintf(stderr, "[cb timing]   nd: depth %d hub separator of %zu: %zu connectors (level cut had %zu), %.4f s\n", depth, total, hsep.size(), sep.size(), onow() - t_enter);
+      for (int v : hsep) W.part[v] = -1;
+      std::vector<int> rest;
+      rest.reserve(total - hsep.size());
+      for (int v : q) if (W.part[v] == region) rest.push_back(v);
+      std::vector<int>().swap(verts);
+      std::vector<int>().swap(q);
+      nd_rec(W, rest, depth, out);                           // falls into its components there
+      nd_leaf(W, hsep, out);
+      return;
+    }
+  }
+  if (poor_cut) { nd_leaf(W, verts, out); return; }
+  if (beyond_cap) {
     W.hopeless.store(true);
     return;
   }
@@ -605,6 +743,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
   W.local.assign(n, -1);
   W.leaf_size = leaf_size;
   W.sep_flop_cap = sep_flop_cap;
+  if (const char* e = std::getenv("CB_ND_HUBS")) W.hubs = std::atoi(e) != 0;
   W.halo = std::getenv("CB_ND_HALO") != nullptr && std::atoi(std::getenv("CB_ND_HALO")) != 0;
   {
     unsigned hc = std::thread::hardware_concurrency();
