@@ -463,212 +463,6 @@ __global__ void k_permute_in(int n, const int* __restrict__ perm, const double* 
 }
 
 // ------------------------------------------------------------------------
-// Triangular solves.  Per tree level: fronts with a narrow pivot block
-// (ns <= CB_SOLVE_SMALL_NS) get one warp each; wider ones one CTA each with the
-// pivot block staged in shared memory so the ns sequential substitution steps
-// never wait on global memory.
-// ------------------------------------------------------------------------
-#define SV_NT 256
-
-// forward, small fronts: one warp per front
-__global__ void __launch_bounds__(SV_NT) k_fwd_small(LDLDev d, const int* __restrict__ tasks, int count,
-                                                     double* __restrict__ xp) {
-  const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * (SV_NT / 32) + (threadIdx.x >> 5);
-  if (wid >= count) return;
-  const int s = tasks[wid];
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  double* __restrict__ us = d.u + rp;
-  {
-    // children's update vectors, gathered per destination slot in fixed order
-    const int* __restrict__ gp = d.gat_ptr + (f + rp);
-    for (int p = lane; p < ld; p += 32) {
-      double acc = 0.0;
-      for (int e = gp[p]; e < gp[p + 1]; e++) acc += d.u[d.gat_src[e]];
-      if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
-    }
-  }
-  __syncwarp();
-  for (int j = 0; j + 1 < ns; j++) {
-    const double xj = xp[f + j];
-    for (int i = j + 1 + lane; i < ns; i += 32) xp[f + i] -= P[(long long)j * ld + i] * xj;
-    __syncwarp();
-  }
-  for (int a = lane; a < nr; a += 32) {
-    double acc = 0.0;
-    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * xp[f + j];
-    us[a] -= acc;
-  }
-}
-
-// forward, big fronts: one CTA per front
-// `chains[blockIdx.x]` = (first front, number of fronts): consecutive panels of one supernode whose row
-// sets nest exactly are swept by ONE CTA back to back, so a chain costs one launch instead of one per panel.
-__global__ void __launch_bounds__(SV_NT) k_fwd_big(LDLDev d, const int2* __restrict__ chains, double* __restrict__ xp) {
-  __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
-  __shared__ double sy[CB_PB_MAXNS];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int2 ch = chains[blockIdx.x];
-  for (int ci = 0; ci < ch.y; ci++) {
-  const int s = ch.x + ci;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  double* __restrict__ us = d.u + rp;
-  for (int idx = tid; idx < ns * ns; idx += SV_NT) {
-    const int j = idx / ns, i = idx - j * ns;
-    sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
-  }
-  {
-    const int* __restrict__ gp = d.gat_ptr + (f + rp);
-    for (int p = tid; p < ld; p += SV_NT) {
-      double acc = 0.0;
-      for (int e = gp[p]; e < gp[p + 1]; e++) acc += d.u[d.gat_src[e]];
-      if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
-    }
-  }
-  __syncthreads();
-  if (tid < 32) {
-    // ns <= 64: each lane owns entries lane and lane+32
-    double y0 = lane < ns ? xp[f + lane] : 0.0;
-    double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
-    __syncwarp();   // the shuffles below need a converged warp: a diverged one takes the slow per-thread path
-    for (int j = 0; j < ns; j++) {
-      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
-      const double* lj = sL + j * CB_PB_LD;
-      if (lane > j && lane < ns) y0 -= lj[lane] * xj;
-      if (lane + 32 > j && lane + 32 < ns) y1 -= lj[lane + 32] * xj;
-    }
-    if (lane < ns) { sy[lane] = y0; xp[f + lane] = y0; }
-    if (lane + 32 < ns) { sy[lane + 32] = y1; xp[f + lane + 32] = y1; }
-  }
-  __syncthreads();
-  // u = -L21 * y : every thread owns rows, 16 panel columns are fetched per batch so that many
-  // independent (coalesced) loads are in flight
-  for (int a = tid; a < nr; a += SV_NT) {
-    const double* __restrict__ pa = P + ns + a;
-    double acc = 0.0;
-    int j0 = 0;
-    for (; j0 + 16 <= ns; j0 += 16) {
-      double v[16];
-#pragma unroll
-      for (int jj = 0; jj < 16; jj++) v[jj] = pa[(long long)(j0 + jj) * ld];
-      asm volatile("" ::: "memory");   // keep all 16 loads in flight before the first use
-#pragma unroll
-      for (int jj = 0; jj < 16; jj++) acc += v[jj] * sy[j0 + jj];
-    }
-    for (; j0 < ns; j0++) acc += pa[(long long)j0 * ld] * sy[j0];
-    us[a] -= acc;
-  }
-  __syncthreads();   // u and xp of this front are visible to the next panel of the chain
-  }
-}
-
-// backward, small fronts: one warp per front
-__global__ void __launch_bounds__(SV_NT) k_bwd_small(LDLDev d, const int* __restrict__ tasks, int count,
-                                                     double* __restrict__ xp, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * (SV_NT / 32) + (threadIdx.x >> 5);
-  if (wid >= count) return;
-  const int s = tasks[wid];
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  const int* __restrict__ rows = d.sn_rows + rp;
-  for (int j = 0; j < ns; j++) {
-    const double* __restrict__ cj = P + (long long)j * ld + ns;
-    double acc = 0.0;
-    for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
-    __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
-  }
-  __syncwarp();
-  for (int j = ns - 1; j > 0; j--) {
-    const double xj = xp[f + j];
-    for (int i = lane; i < j; i += 32) xp[f + i] -= P[(long long)i * ld + j] * xj;
-    __syncwarp();
-  }
-  for (int j = lane; j < ns; j += 32) out[d.perm[f + j]] = xp[f + j];
-}
-
-// backward, big fronts: one CTA per front
-__global__ void __launch_bounds__(SV_NT) k_bwd_big(LDLDev d, const int2* __restrict__ chains, double* __restrict__ xp,
-                                                   double* __restrict__ out) {
-  __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
-  __shared__ double st[CB_PB_MAXNS];
-  __shared__ double sx[CB_SOLVE_STAGE];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SV_NT >> 5;
-  const int2 ch = chains[blockIdx.x];
-  for (int ci = ch.y - 1; ci >= 0; ci--) {
-  const int s = ch.x + ci;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  const int* __restrict__ rows = d.sn_rows + rp;
-  for (int idx = tid; idx < ns * ns; idx += SV_NT) {
-    const int j = idx / ns, i = idx - j * ns;
-    sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
-  }
-  const bool staged = nr <= CB_SOLVE_STAGE;
-  if (staged) for (int a = tid; a < nr; a += SV_NT) sx[a] = xp[rows[a]];
-  __syncthreads();
-  for (int j = warp; j < ns; j += nwarp) {
-    const double* __restrict__ cj = P + (long long)j * ld + ns;
-    double acc = 0.0;
-    if (staged) {
-      int a0 = 0;
-      for (; a0 + 256 <= nr; a0 += 256) {
-        double v[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = cj[a0 + q * 32 + lane];
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc += v[q] * sx[a0 + q * 32 + lane];
-      }
-      for (int a = a0 + lane; a < nr; a += 32) acc += cj[a] * sx[a];
-    } else {
-      for (int a = lane; a < nr; a += 32) acc += cj[a] * xp[rows[a]];
-    }
-    __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) st[j] = xp[f + j] * d.Dinv[f + j] - acc;
-  }
-  __syncthreads();
-  if (tid < 32) {
-    double y0 = lane < ns ? st[lane] : 0.0;
-    double y1 = lane + 32 < ns ? st[lane + 32] : 0.0;
-    __syncwarp();   // the shuffles below need a converged warp: a diverged one takes the slow per-thread path
-    for (int j = ns - 1; j > 0; j--) {
-      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
-      // L11[j][i] = sL[i*LD + j]
-      if (lane < j) y0 -= sL[lane * CB_PB_LD + j] * xj;
-      if (lane + 32 < j) y1 -= sL[(lane + 32) * CB_PB_LD + j] * xj;
-    }
-    if (lane < ns) { xp[f + lane] = y0; out[d.perm[f + lane]] = y0; }
-    if (lane + 32 < ns) { xp[f + lane + 32] = y1; out[d.perm[f + lane + 32]] = y1; }
-  }
-  __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------
 // Dataflow triangular solves: ONE persistent kernel per sweep.  CTAs pull tasks from a queue in
 // topological (level) order; a task waits on a counter (forward: number of unfinished child fronts;
 // backward: parent's done flag) instead of on a kernel boundary, so independent branches of the tree
@@ -695,328 +489,7 @@ __device__ __forceinline__ void df_wait_set(volatile int* p) {
   while (*p == 0) { __nanosleep(ns); if (ns < 640) ns <<= 1; }
 }
 
-__shared__ unsigned long long* df_trk;
-#define SV_STAMP(slot) do { if (threadIdx.x == 0 && df_trk) df_trk[slot] = df_gtime(); } while (0)
-__device__ void df_fwd_small(const LDLDev& d, int s, double* __restrict__ xp, int lane) {
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  double* us = d.u + rp;
-  const int* __restrict__ gp = d.gat_ptr + (f + rp);
-  for (int p = lane; p < ld; p += 32) {
-    double acc = 0.0;
-    for (int e = gp[p]; e < gp[p + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
-    if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
-  }
-  __syncwarp();
-  for (int j = 0; j + 1 < ns; j++) {
-    const double xj = xp[f + j];
-    for (int i = j + 1 + lane; i < ns; i += 32) xp[f + i] -= P[(long long)j * ld + i] * xj;
-    __syncwarp();
-  }
-  for (int a = lane; a < nr; a += 32) {
-    double acc = 0.0;
-    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * xp[f + j];
-    us[a] -= acc;
-  }
-}
-
-__device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, double* __restrict__ out, int lane) {
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  const int* __restrict__ rows = d.sn_rows + rp;
-  if (nr <= 8 * 32) {
-    // the ancestors' solution entries this front needs are fetched once (index -> value is a dependent pair of
-    // loads; doing it per pivot column put 2*ns round trips on every narrow front)
-    double xv[8];
-#pragma unroll
-    for (int q8 = 0; q8 < 8; q8++) {
-      const int a = lane + 32 * q8;
-      xv[q8] = a < nr ? __ldcg(xp + rows[a]) : 0.0;
-    }
-    for (int j = 0; j < ns; j++) {
-      const double* __restrict__ cj = P + (long long)j * ld + ns;
-      double acc = 0.0;
-#pragma unroll
-      for (int q8 = 0; q8 < 8; q8++) {
-        const int a = lane + 32 * q8;
-        if (a < nr) acc += cj[a] * xv[q8];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
-    }
-  } else {
-    for (int j = 0; j < ns; j++) {
-      const double* __restrict__ cj = P + (long long)j * ld + ns;
-      double acc = 0.0;
-      for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
-      __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
-    }
-  }
-  __syncwarp();
-  for (int j = ns - 1; j > 0; j--) {
-    const double xj = xp[f + j];
-    for (int i = lane; i < j; i += 32) xp[f + i] -= P[(long long)i * ld + j] * xj;
-    __syncwarp();
-  }
-  for (int j = lane; j < ns; j += 32) out[d.perm[f + j]] = xp[f + j];
-}
-
-// ---- wide fronts, pipelined along supernode chains ----
-// A wide front publishes its update vector in blocks of 64 rows (prog[s] = blocks finished).  The parent of a
-// chain child (rows(child) == cols(parent) + rows(parent)) follows that counter instead of waiting for the whole
-// child: it can factor out its pivot block as soon as the child's first rows are final, so a chain of D panels
-// with B row blocks costs ~(D + B) block steps instead of D * B.  The backward sweep does the same in the other
-// direction: a front folds in the rows owned by far ancestors while the near ones are still being solved; only
-// the last 64 rows and the pivot block sit on the critical path.
-#define SV_RB 64
-
-__device__ __forceinline__ void df_wait_ge(volatile int* p, int v) {
-  unsigned ns = 20;
-  while (*p < v) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
-}
-
-__device__ void df_fwd_wide(const LDLDev& d, const DFPlan& q, int s, int k, double* __restrict__ xp, double* sL,
-                            double* sy, double* sred) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  double* us = d.u + rp;
-  const int* __restrict__ gp = d.gat_ptr + (f + rp);
-  const int c = q.chain_child[s];
-  int cblk = 0;
-  if (c >= 0) cblk = ((int)(d.sn_rowptr[c + 1] - d.sn_rowptr[c]) + SV_RB - 1) / SV_RB;
-  if (tid == 0) {
-    df_wait_zero(q.pend + k);
-    if (c >= 0) df_wait_ge(q.prog + c, min(cblk, (ns - 1) / SV_RB + 1));
-    __threadfence();
-    if (df_trk) df_trk[1] = df_gtime();
-  }
-  __syncthreads();
-  const bool pure = q.pure_chain[s] != 0;       // only child = chain child: its row i is this front's index i
-  const double* uc = pure ? d.u + d.sn_rowptr[c] : nullptr;
-  if (tid < ns) {
-    double acc = 0.0;
-    if (pure) acc = __ldcg(uc + tid);
-    else for (int e = gp[tid]; e < gp[tid + 1]; e++) acc += __ldcg(d.u + d.gat_src[e]);
-    xp[f + tid] += acc;
-  }
-  __syncthreads();
-  SV_STAMP(3);
-  if (tid < 32) {
-    double y0 = lane < ns ? xp[f + lane] : 0.0;
-    double y1 = lane + 32 < ns ? xp[f + lane + 32] : 0.0;
-    __syncwarp();
-    for (int j = 0; j < ns; j++) {
-      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
-      const double* lj = sL + j * CB_PB_LD;
-      if (lane > j && lane < ns) y0 -= lj[lane] * xj;
-      if (lane + 32 > j && lane + 32 < ns) y1 -= lj[lane + 32] * xj;
-    }
-    sy[lane] = lane < ns ? y0 : 0.0;
-    sy[lane + 32] = lane + 32 < ns ? y1 : 0.0;
-    if (lane < ns) xp[f + lane] = y0;
-    if (lane + 32 < ns) xp[f + lane + 32] = y1;
-  }
-  __syncthreads();
-  SV_STAMP(4);
-  const int r = tid & (SV_RB - 1), cq = tid >> 6;      // row of the block, quarter of the pivot columns
-  const int nblk = (nr + SV_RB - 1) / SV_RB;
-  int seen = 0;                                         // thread 0: chain child's progress already observed
-  for (int b = 0; b < nblk; b++) {
-    const int r0 = b * SV_RB;
-    const int a = r0 + r;
-    // the panel is static: its loads go out before the wait on the child
-    double v[16];
-    const double* __restrict__ pa = P + ns + a + (long long)(16 * cq) * ld;
-#pragma unroll
-    for (int jj = 0; jj < 16; jj++) v[jj] = (a < nr && 16 * cq + jj < ns) ? pa[(long long)jj * ld] : 0.0;
-    if (c >= 0) {
-      const int need = min(cblk, (ns + min(nr, r0 + SV_RB) - 1) / SV_RB + 1);
-      if (tid == 0 && seen < need) { df_wait_ge(q.prog + c, need); seen = need; __threadfence(); }
-      __syncthreads();
-    }
-    double part = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < 16; jj++) part += v[jj] * sy[(16 * cq + jj) & (CB_PB_MAXNS - 1)];
-    double g = 0.0;
-    if (cq == 0 && a < nr) {
-      if (pure) g = __ldcg(uc + ns + a);
-      else for (int e = gp[ns + a]; e < gp[ns + a + 1]; e++) g += __ldcg(d.u + d.gat_src[e]);
-    }
-    sred[cq * SV_RB + r] = part;
-    __syncthreads();
-    if (cq == 0 && a < nr) us[a] = g - (((sred[r] + sred[SV_RB + r]) + sred[2 * SV_RB + r]) + sred[3 * SV_RB + r]);
-    __syncthreads();
-    if (tid == 0) { __threadfence(); atomicExch(q.prog + s, b + 1); }
-  }
-}
-
-__device__ void df_bwd_wide(const LDLDev& d, const DFPlan& q, int s, double* __restrict__ xp, double* __restrict__ out,
-                            double* sLt, double* st, double* sred) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const long long rp = d.sn_rowptr[s];
-  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
-  const int ld = ns + nr;
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  const int* __restrict__ rows = d.sn_rows + rp;
-  const int r = tid & (SV_RB - 1), cq = tid >> 6;
-  const int nblk = (nr + SV_RB - 1) / SV_RB;
-  const int* __restrict__ own = q.blk_owner + q.blk_ptr[s];
-  double acc[16];
-#pragma unroll
-  for (int jj = 0; jj < 16; jj++) acc[jj] = 0.0;
-  int last_owner = -1;
-  bool stamped = false;
-  for (int b = nblk - 1; b >= 0; b--) {
-    const int a = b * SV_RB + r;
-    double v[16];
-    const double* __restrict__ pa = P + ns + a + (long long)(16 * cq) * ld;
-#pragma unroll
-    for (int jj = 0; jj < 16; jj++) v[jj] = (a < nr && 16 * cq + jj < ns) ? pa[(long long)jj * ld] : 0.0;
-    const int row = a < nr ? rows[a] : 0;
-    const int o = own[b];
-    if (o != last_owner) {
-      if (tid == 0) { df_wait_set(q.done + o); __threadfence(); if (df_trk && !stamped) df_trk[1] = df_gtime(); }
-      stamped = true;
-      last_owner = o;
-      __syncthreads();
-    }
-    const double xv = a < nr ? __ldcg(xp + row) : 0.0;
-#pragma unroll
-    for (int jj = 0; jj < 16; jj++) acc[jj] += v[jj] * xv;
-  }
-  if (nblk == 0 && tid == 0) {
-    const int p = q.parent[s];
-    if (p >= 0) df_wait_set(q.done + p);
-    __threadfence();
-    if (df_trk) df_trk[1] = df_gtime();
-  }
-  SV_STAMP(3);
-  // column sums: butterfly over the 32 rows a warp holds, then the two row halves through shared memory
-  __syncwarp();
-#pragma unroll
-  for (int jj = 0; jj < 16; jj++) {
-    double t = acc[jj];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    acc[jj] = t;
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int jj = 0; jj < 16; jj++) sred[(warp & 1) * CB_PB_MAXNS + 16 * cq + jj] = acc[jj];
-  }
-  __syncthreads();
-  if (tid < ns) st[tid] = __ldcg(xp + f + tid) * d.Dinv[f + tid] - (sred[tid] + sred[CB_PB_MAXNS + tid]);
-  __syncthreads();
-  SV_STAMP(4);
-  if (tid < 32) {
-    double y0 = lane < ns ? st[lane] : 0.0;
-    double y1 = lane + 32 < ns ? st[lane + 32] : 0.0;
-    __syncwarp();
-    for (int j = ns - 1; j > 0; j--) {
-      const double xj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
-      const double* lj = sLt + j * CB_PB_LD;     // row j of L11: L[j][i], i < j
-      if (lane < j) y0 -= lj[lane] * xj;
-      if (lane + 32 < j) y1 -= lj[lane + 32] * xj;
-    }
-    if (lane < ns) { xp[f + lane] = y0; out[d.perm[f + lane]] = y0; }
-    if (lane + 32 < ns) { xp[f + lane + 32] = y1; out[d.perm[f + lane + 32]] = y1; }
-  }
-}
-
-// load the unit-lower pivot block of front s into shared memory (static data: can run before the wait);
-// TRANS stores row-major (sL[i][j] = L[i][j]) for the backward sweep, which walks rows
-template <bool TRANS>
-__device__ __forceinline__ void df_load_pivot(const LDLDev& d, int s, double* sL) {
-  const int f = d.sn_first[s];
-  const int ns = d.sn_first[s + 1] - f;
-  const int ld = ns + (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
-  const double* __restrict__ P = d.L + d.panel_off[s];
-  for (int idx = threadIdx.x; idx < ns * ns; idx += SV_NT) {
-    const int j = idx / ns, i = idx - j * ns;
-    if (TRANS) sL[i * CB_PB_LD + j] = P[(long long)j * ld + i];
-    else sL[j * CB_PB_LD + i] = P[(long long)j * ld + i];
-  }
-}
-
-template <bool FWD, int MINB>
-__global__ void __launch_bounds__(SV_NT, MINB) k_solve_df(LDLDev d, DFPlan q, double* __restrict__ xp, double* __restrict__ out) {
-  __shared__ double sL[CB_PB_MAXNS * CB_PB_LD];
-  __shared__ double sv[CB_PB_MAXNS];
-  __shared__ double sred[4 * SV_RB];
-  __shared__ int s_task, s_prev;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_prev = -1;
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      if (q.trace && s_prev >= 0) q.trace[6 * ((size_t)(FWD ? 0 : q.ntask) + s_prev) + 2] = df_gtime();
-      s_task = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
-      s_prev = s_task < q.ntask ? (FWD ? s_task : q.ntask - 1 - s_task) : -1;
-      if (q.trace && s_prev >= 0) q.trace[6 * ((size_t)(FWD ? 0 : q.ntask) + s_prev)] = df_gtime();
-    }
-    __syncthreads();
-    const int qi = s_task;
-    if (qi >= q.ntask) break;
-    const int k = FWD ? qi : q.ntask - 1 - qi;
-    if (tid == 0) df_trk = q.trace ? q.trace + 6 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
-    unsigned long long* trk = q.trace ? q.trace + 6 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
-    const int first = q.task_first[k], cnt = q.task_cnt[k], kind = q.task_kind[k];
-    if (kind == 1) {
-      const int s = q.fronts[first];
-      df_load_pivot<!FWD>(d, s, sL);               // overlaps with the waits inside
-      __syncthreads();
-      if (FWD) df_fwd_wide(d, q, s, k, xp, sL, sv, sred);
-      else df_bwd_wide(d, q, s, xp, out, sL, sv, sred);
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        if (FWD) { const int p = q.parent[s]; if (p >= 0 && q.chain_child[p] != s) atomicSub(q.pend + q.front2task[p], 1); }
-        else atomicExch(q.done + s, 1);
-      }
-    } else {
-      if (FWD) {
-        if (tid == 0) { df_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
-        __syncthreads();
-        if (warp < cnt) df_fwd_small(d, q.fronts[first + warp], xp, lane);
-        __syncthreads();
-        if (tid < cnt) {
-          __threadfence();
-          const int p = q.parent[q.fronts[first + tid]];
-          if (p >= 0) atomicSub(q.pend + q.front2task[p], 1);
-        }
-      } else {
-        if (warp < cnt) {
-          const int s = q.fronts[first + warp];
-          if (lane == 0) { const int p = q.parent[s]; if (p >= 0) df_wait_set(q.done + p); __threadfence(); }
-          __syncwarp();
-          df_bwd_small(d, s, xp, out, lane);
-          __syncwarp();
-          if (lane == 0) { __threadfence(); atomicExch(q.done + s, 1); }
-        }
-      }
-    }
-  }
-}
+#include "ldl_solve.cuh"
 
 // ------------------------------------------------------------------------
 // Dataflow numeric factorisation: ONE persistent kernel for everything above tree level 0.
@@ -1767,9 +1240,6 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   }
 
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
   CK(cudaMallocHost((void**)&h_status, ST_COUNT * sizeof(int)));
@@ -2066,119 +1536,84 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   th_child.join();
   if (rc_child) return rc_child;
   cb_tmark("ldl: small-child entry lists");
-  // solve plan.  Chains: consecutive panels s, s+1 with parent(s) == s+1 and rows(s) == cols(s+1) + rows(s+1)
-  // are swept by one CTA, so the schedule is levelled over chains, not over panels.  Single narrow fronts
-  // (ns <= CB_SOLVE_SMALL_NS) keep the warp-per-front kernels.
-  {
-    const int ns_ = S.nsup;
-    // Level-synchronous sweeps pay for the LONGEST chain of every level, so long chains lose against
-    // per-panel levels (measured on C2: 3.98 ms with unbounded chains vs 2.84 ms without).  Default: off.
-    int chain_max = 1;
-    if (const char* e = std::getenv("CB_SOLVE_CHAIN_MAX")) chain_max = std::max(1, std::atoi(e));
-    std::vector<int> chain_of(ns_, -1), chain_first, chain_cnt;
-    for (int s = 0; s < ns_; s++) {
-      if (chain_of[s] >= 0) continue;
-      const int id = (int)chain_first.size();
-      chain_first.push_back(s);
-      int t = s, cnt = 1;
-      chain_of[s] = id;
-      while (t + 1 < ns_ && S.sn_parent[t] == t + 1 &&
-             (S.sn_rowptr[t + 1] - S.sn_rowptr[t]) ==
-                 (int64_t)(S.sn_first[t + 2] - S.sn_first[t + 1]) + (S.sn_rowptr[t + 2] - S.sn_rowptr[t + 1]) &&
-             (S.sn_first[t + 1] - S.sn_first[t]) > CB_SOLVE_SMALL_NS && cnt < chain_max) {
-        t++; cnt++;
-        chain_of[t] = id;
-      }
-      chain_cnt.push_back(cnt);
-    }
-    const int nchain = (int)chain_first.size();
-    std::vector<int> clevel(nchain, 0);
-    int nlev = 0;
-    for (int s = 0; s < ns_; s++) {       // tasks are numbered children-before-parents
-      const int p = S.sn_parent[s];
-      if (p >= 0 && chain_of[p] != chain_of[s] && clevel[chain_of[p]] < clevel[chain_of[s]] + 1)
-        clevel[chain_of[p]] = clevel[chain_of[s]] + 1;
-    }
-    // a later member of a chain may have raised the chain's level after an earlier external child was seen;
-    // iterate to a fixed point (levels only grow, tree depth bounds the number of sweeps)
-    for (bool changed = true; changed;) {
-      changed = false;
-      for (int s = 0; s < ns_; s++) {
-        const int p = S.sn_parent[s];
-        if (p >= 0 && chain_of[p] != chain_of[s] && clevel[chain_of[p]] < clevel[chain_of[s]] + 1) {
-          clevel[chain_of[p]] = clevel[chain_of[s]] + 1; changed = true;
-        }
-      }
-    }
-    for (int c = 0; c < nchain; c++) nlev = std::max(nlev, clevel[c] + 1);
-    splan.assign(nlev, SolveSeg());
-    std::vector<std::vector<int>> small(nlev), big(nlev);
-    for (int c = 0; c < nchain; c++) {
-      const int s = chain_first[c];
-      const bool is_small = chain_cnt[c] == 1 && (S.sn_first[s + 1] - S.sn_first[s]) <= CB_SOLVE_SMALL_NS;
-      (is_small ? small : big)[clevel[c]].push_back(c);
-    }
-    std::vector<int> st;
-    std::vector<int2> chains;
-    solve_launches = 0;
-    for (int l = 0; l < nlev; l++) {
-      splan[l].base = (int)st.size();
-      splan[l].cbase = (int)chains.size();
-      splan[l].nsmall = (int)small[l].size();
-      splan[l].nbig = (int)big[l].size();
-      for (int c : small[l]) st.push_back(chain_first[c]);
-      for (int c : big[l]) chains.push_back(make_int2(chain_first[c], chain_cnt[c]));
-      solve_launches += 2 * ((splan[l].nsmall ? 1 : 0) + (splan[l].nbig ? 1 : 0));
-    }
-    solve_levels = nlev;
-    int* t1 = nullptr;
-    if ((rc = upload(&t1, st))) return rc;
-    d_solve_tasks = t1;
-    int2* t2 = nullptr;
-    CK(cudaMalloc((void**)&t2, (chains.size() ? chains.size() : 1) * sizeof(int2)));
-    if (!chains.empty()) CK(cudaMemcpy(t2, chains.data(), chains.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    d_solve_chains = t2;
-  }
-  cb_tmark("ldl:   solve plan: level-sync part");
+  // solve plan (ldl_solve.cuh): level-0 narrow fronts get plain kernels, everything else becomes queue tasks in level
+  // order -- batches of narrow fronts, and for every wide front a head task (pivot block + first rows) followed by row
+  // tasks when the panel exceeds the shared-memory slab.
   // level_tasks was re-ordered inside levels: re-upload
   CK(cudaMemcpy((void*)dev.level_tasks, S.level_tasks.data(), S.level_tasks.size() * sizeof(int),
                 cudaMemcpyHostToDevice));
-  // dataflow solve plan: tasks in level order; narrow fronts batched 8 per task
   {
-    std::vector<int> t_first, t_cnt, t_kind, fronts, f2t(S.nsup, -1);
-    // sharded: the tasks of the owned subtrees come first (in level order), then the tasks of the replicated top part
-    // (in level order); fronts of other ranks get no task.  The forward sweep is launched once per phase with the
-    // cut roots' update vectors exchanged in between; the backward sweep walks the same list from the end in one
-    // launch (top first, then the owned subtrees: its dependencies point upwards only).
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    // resident CTAs per SM and the slab size that goes with it (227 KB of shared memory per SM, 1 KB reserved per CTA)
+    solve_minb = 3;
+    if (const char* e = std::getenv("CB_SOLVE_MINB")) solve_minb = std::min(4, std::max(2, std::atoi(e)));
+    const size_t extra2 = (size_t)2 * (2 * CB_PB_MAXNS + SV_MAXROWS + 4 * CB_PB_MAXNS) * sizeof(double);   // NR = 2 vectors
+    {
+      const size_t per_cta = ((size_t)227 * 1024) / solve_minb - 1024 - 64;
+      sv_cap = (int)((per_cta - extra2) / sizeof(double));
+      sv_cap = std::min(sv_cap, 16384);
+      if (const char* e = std::getenv("CB_SOLVE_CAP")) sv_cap = std::max(CB_PB_MAXNS * (CB_PB_MAXNS + 9), std::atoi(e));
+    }
+    const int cap = sv_cap;
+    auto wide = [&](int s) { return S.sn_first[s + 1] - S.sn_first[s] > CB_SOLVE_SMALL_NS; };
+    auto has_kids = [&](int s) { return S.child_ptr[s + 1] > S.child_ptr[s]; };
+    // head rows / rows per row task of a wide front
+    auto split = [&](int ns, int nr, int& rh, int& nrt, int& chunk) {
+      int hmax = cap / ns;                       // staged rows with lds = rows | 1
+      if ((hmax | 1) * ns > cap) hmax--;
+      rh = std::min(std::min(nr, SV_MAXROWS), std::max(0, hmax - ns));
+      int rmax = cap / ns;
+      if ((rmax | 1) * ns > cap) rmax--;
+      rmax = std::min(rmax, SV_MAXROWS);
+      const int rest = nr - rh;
+      nrt = rest > 0 ? (rest + rmax - 1) / rmax : 0;
+      chunk = nrt ? (rest + nrt - 1) / nrt : 0;
+    };
+    std::vector<int> leaf1, leafn, fronts, f2t(S.nsup, -1), nrt_of(S.nsup, 0), rh_of(S.nsup, 0), chunk_of(S.nsup, 0);
+    std::vector<SVTask> tk;
     const int per = SV_NT / 32;
     for (int ph = 0; ph < (sharded() ? 2 : 1); ph++) {
-      if (ph == 1) df_ntask_owned = (int)t_first.size();
+      if (ph == 1) sv_ntask_owned = (int)tk.size();
       std::vector<std::vector<int>> lev_small(S.nlevels), lev_big(S.nlevels);
       for (int s = 0; s < S.nsup; s++) {
         if (sharded() && (ph == 0 ? !owned(s) : shard.owner[s] >= 0)) continue;
-        const int ns = S.sn_first[s + 1] - S.sn_first[s];
-        (ns <= CB_SOLVE_SMALL_NS ? lev_small : lev_big)[S.sn_level[s]].push_back(s);
+        if (!wide(s) && !has_kids(s)) { (S.sn_first[s + 1] - S.sn_first[s] == 1 ? leaf1 : leafn).push_back(s); continue; }
+        (wide(s) ? lev_big : lev_small)[S.sn_level[s]].push_back(s);
       }
       for (int l = 0; l < S.nlevels; l++) {
         for (size_t i = 0; i < lev_small[l].size(); i += per) {
           const int c = (int)std::min<size_t>(per, lev_small[l].size() - i);
-          t_first.push_back((int)fronts.size()); t_cnt.push_back(c); t_kind.push_back(0);
-          for (int k = 0; k < c; k++) { f2t[lev_small[l][i + k]] = (int)t_first.size() - 1; fronts.push_back(lev_small[l][i + k]); }
+          SVTask t{};
+          t.kind = 0; t.s = (int)fronts.size(); t.cnt = c; t.dep1 = -1; t.dep2 = -1; t.bowner = -1; t.ptask = -1; t.cuoff = -1;
+          for (int k = 0; k < c; k++) { f2t[lev_small[l][i + k]] = (int)tk.size(); fronts.push_back(lev_small[l][i + k]); }
+          tk.push_back(t);
         }
         for (int s : lev_big[l]) {
-          t_first.push_back((int)fronts.size()); t_cnt.push_back(1); t_kind.push_back(1);
-          f2t[s] = (int)t_first.size() - 1; fronts.push_back(s);
+          const int ns = S.sn_first[s + 1] - S.sn_first[s], nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
+          int rh, nrt, chunk;
+          split(ns, nr, rh, nrt, chunk);
+          rh_of[s] = rh; nrt_of[s] = nrt; chunk_of[s] = chunk;
+          f2t[s] = (int)tk.size();
+          for (int b = -1; b < nrt; b++) {
+            SVTask t{};
+            t.kind = b < 0 ? 1 : 2; t.s = s; t.f = S.sn_first[s]; t.ns = ns; t.nr = nr;
+            t.r0 = b < 0 ? 0 : rh + b * chunk;
+            t.r1 = b < 0 ? rh : std::min(nr, rh + (b + 1) * chunk);
+            t.poff = S.panel_off[s]; t.rp = S.sn_rowptr[s];
+            t.dep0 = 0; t.dep1 = -1; t.dep2 = -1; t.nrt = nrt; t.bowner = -1; t.bslot = 0; t.pure = 0; t.ptask = -1; t.cuoff = -1;
+            t.notify = 1;
+            tk.push_back(t);
+          }
         }
       }
     }
-    const int nt = (int)t_first.size();
-    if (!sharded()) df_ntask_owned = nt;
-    // chain children of wide fronts (followed block by block instead of awaited), block owners for the
-    // backward sweep
-    std::vector<int> chain_child(S.nsup, -1), col2sn(n, 0), blk_ptr(S.nsup + 1, 0), blk_owner;
+    const int nt = (int)tk.size();
+    if (!sharded()) sv_ntask_owned = nt;
+    // chain children of wide fronts: followed slab by slab instead of awaited as a whole
+    std::vector<int> chain_child(S.nsup, -1), col2sn(n, 0);
     for (int s = 0; s < S.nsup; s++)
       for (int j = S.sn_first[s]; j < S.sn_first[s + 1]; j++) col2sn[j] = s;
-    auto wide = [&](int s) { return S.sn_first[s + 1] - S.sn_first[s] > CB_SOLVE_SMALL_NS; };
     for (int c = 0; c < S.nsup; c++) {
       const int p = S.sn_parent[c];
       if (p < 0 || !wide(c) || !wide(p) || chain_child[p] >= 0) continue;
@@ -2186,70 +1621,95 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       const int64_t nsp = S.sn_first[p + 1] - S.sn_first[p], nrp = S.sn_rowptr[p + 1] - S.sn_rowptr[p];
       if (nrc == nsp + nrp) chain_child[p] = c;       // rows(c) is a subset of cols(p)+rows(p): equal sizes = equal sets
     }
-    std::vector<signed char> pure_chain(S.nsup, 0);
-    for (int s = 0; s < S.nsup; s++)
-      if (chain_child[s] >= 0 && S.child_ptr[s + 1] - S.child_ptr[s] == 1) pure_chain[s] = 1;
+    // task of front c covering its row i (of its L21 part)
+    auto task_of_row = [&](int c, int i) {
+      if (i < rh_of[c]) return f2t[c];
+      return f2t[c] + 1 + (i - rh_of[c]) / chunk_of[c];
+    };
+    int nslots = 0;
+    std::vector<int> pend(nt, 0), fleft(S.nsup, 0), bleft(S.nsup, 0);
     for (int s = 0; s < S.nsup; s++) {
-      blk_ptr[s] = (int)blk_owner.size();
-      if (!wide(s)) continue;
-      for (int64_t t = S.sn_rowptr[s]; t < S.sn_rowptr[s + 1]; t += 64) blk_owner.push_back(col2sn[S.sn_rows[t]]);
+      if (f2t[s] < 0 || !wide(s)) continue;
+      const int ns = S.sn_first[s + 1] - S.sn_first[s], nr = (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
+      const int h = f2t[s], nrt = nrt_of[s], p = S.sn_parent[s];
+      fleft[s] = 1 + nrt; bleft[s] = nrt;
+      const int c = chain_child[s];
+      const bool follow = c >= 0 && f2t[c] >= 0;      // a chain child of another rank is complete before this phase starts
+      const bool pure = c >= 0 && S.child_ptr[s + 1] - S.child_ptr[s] == 1;
+      for (int b = -1; b < nrt; b++) {
+        SVTask& t = tk[h + 1 + b];
+        t.ptask = p >= 0 ? f2t[p] : -1;
+        t.notify = (p >= 0 && chain_child[p] == s) ? 0 : 1;
+        t.pure = pure ? 1 : 0;
+        t.cuoff = pure ? (long long)S.sn_rowptr[c] : -1;
+        t.bslot = b < 0 ? nslots : nslots + b;
+        if (t.r1 > t.r0) t.bowner = col2sn[S.sn_rows[S.sn_rowptr[s] + t.r0]];
+        if (follow) {
+          if (b < 0) {
+            t.dep0 = task_of_row(c, 0); t.dep1 = task_of_row(c, ns - 1);
+            t.dep2 = t.r1 > 0 ? task_of_row(c, ns + t.r1 - 1) : t.dep1;
+          } else {
+            t.dep0 = task_of_row(c, ns + t.r0); t.dep1 = task_of_row(c, ns + t.r1 - 1);
+          }
+        }
+      }
+      nslots += nrt;
+      (void)nr;
     }
-    blk_ptr[S.nsup] = (int)blk_owner.size();
-    std::vector<int> pend(nt, 0);
     for (int s = 0; s < S.nsup; s++) {
       const int p = S.sn_parent[s];
-      if (p >= 0 && chain_child[p] != s && mine(s)) pend[f2t[p]]++;   // another rank's front is complete before its parent's phase starts
+      if (p >= 0 && f2t[s] >= 0 && chain_child[p] != s) pend[f2t[p]]++;   // leaves and other ranks' fronts are complete before the sweep starts
     }
+    // wide fronts whose pivot block is inverted after every refactorisation (all that this rank factors)
+    std::vector<int> wlist;
+    for (int s = 0; s < S.nsup; s++) if (wide(s) && mine(s)) wlist.push_back(s);
+    sv_nwide = (int)wlist.size();
+    sv_nleaf1 = (int)leaf1.size(); sv_nleafn = (int)leafn.size();
     int* t1 = nullptr;
-    if (sharded()) {   // progress counters of the forward sweep: the other ranks' fronts count as finished
-      std::vector<int> prog0(S.nsup, 0);
-      for (int s = 0; s < S.nsup; s++) if (!mine(s)) prog0[s] = 1 << 28;
-      if ((rc = upload(&t1, prog0))) return rc; d_prog_init = t1;
+    if ((rc = upload(&t1, wlist))) return rc; d_sv_wide = t1;
+    if ((rc = upload(&t1, leaf1))) return rc; d_sv_leaf1 = t1;
+    if ((rc = upload(&t1, leafn))) return rc; d_sv_leafn = t1;
+    if ((rc = upload(&t1, fronts))) return rc; sv.fronts = t1;
+    if ((rc = upload(&t1, f2t))) return rc; sv.front2task = t1;
+    if ((rc = upload(&t1, S.sn_parent))) return rc; sv.parent = t1;
+    {
+      static_assert(sizeof(SVTask) == 96, "SVTask is 6 x int4");
+      int4* t4 = nullptr;
+      CK(cudaMalloc((void**)&t4, (size_t)(nt ? nt : 1) * sizeof(SVTask)));
+      if (nt) CK(cudaMemcpy(t4, tk.data(), (size_t)nt * sizeof(SVTask), cudaMemcpyHostToDevice));
+      sv.tasks = t4;
     }
-    if ((rc = upload(&t1, t_first))) return rc; df.task_first = t1;
-    if ((rc = upload(&t1, t_cnt))) return rc; df.task_cnt = t1;
-    if ((rc = upload(&t1, t_kind))) return rc; df.task_kind = t1;
-    if ((rc = upload(&t1, fronts))) return rc; df.fronts = t1;
-    if ((rc = upload(&t1, f2t))) return rc; df.front2task = t1;
-    if ((rc = upload(&t1, S.sn_parent))) return rc; df.parent = t1;
-    if ((rc = upload(&t1, pend))) return rc; d_pend_init = t1;
-    if ((rc = upload(&t1, chain_child))) return rc; df.chain_child = t1;
-    { signed char* t8 = nullptr; if ((rc = upload(&t8, pure_chain))) return rc; df.pure_chain = t8; }
-    if ((rc = upload(&t1, blk_ptr))) return rc; df.blk_ptr = t1;
-    if ((rc = upload(&t1, blk_owner))) return rc; df.blk_owner = t1;
-    CK(cudaMalloc((void**)&df.prog, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
-    CK(cudaMalloc((void**)&df2_prog, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
-    CK(cudaMalloc((void**)&df2_done, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
-    CK(cudaMalloc((void**)&df2_pend, (size_t)(nt ? nt : 1) * sizeof(int)));
-    CK(cudaMalloc((void**)&df2_qhead, 2 * sizeof(int)));
-    CK(cudaMalloc((void**)&df.pend, (size_t)(nt ? nt : 1) * sizeof(int)));
-    CK(cudaMalloc((void**)&df.done, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int)));
-    CK(cudaMalloc((void**)&df.qhead, 2 * sizeof(int)));
-    df.ntask = nt;
-    int nsm = 0, occ = 0;
-    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-    // resident CTAs per SM of the sweep kernels: more CTAs keep more fronts in flight while others wait on
-    // their dependencies (the register budget is set through the launch bounds of the instantiation)
-    solve_minb = 4;   // C2: 2 / 3 / 4 resident CTAs per SM -> 1.56 / 1.38 / 1.32 ms per solve
-    if (const char* e = std::getenv("CB_SOLVE_MINB")) solve_minb = std::min(4, std::max(2, std::atoi(e)));
-    if (solve_minb == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true, 2>, SV_NT, 0));
-    else if (solve_minb == 3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true, 3>, SV_NT, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_df<true, 4>, SV_NT, 0));
-    int occ2 = 0;
-    if (solve_minb == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false, 2>, SV_NT, 0));
-    else if (solve_minb == 3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false, 3>, SV_NT, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve_df<false, 4>, SV_NT, 0));
-    occ = std::max(1, std::min(occ, occ2));
+    // counters: [pend(nt) | fleft(nsup) | bleft(nsup)] are copied from their initial values before every solve,
+    // [tdone(nt) | ydone(nsup) | done(nsup) | qhead(2)] are cleared
+    sv_ninit = (size_t)nt + 2 * (size_t)S.nsup;
+    sv_nzero = (size_t)nt + 2 * (size_t)S.nsup + 2;
+    std::vector<int> init(sv_ninit ? sv_ninit : 1, 0);
+    std::copy(pend.begin(), pend.end(), init.begin());
+    std::copy(fleft.begin(), fleft.end(), init.begin() + nt);
+    std::copy(bleft.begin(), bleft.end(), init.begin() + nt + S.nsup);
+    if ((rc = upload(&t1, init))) return rc; d_sv_init = t1;
+    CK(cudaMalloc((void**)&d_sv_cnt, (sv_ninit + sv_nzero) * sizeof(int)));
+    sv.pend = d_sv_cnt; sv.fleft = d_sv_cnt + nt; sv.bleft = sv.fleft + S.nsup;
+    sv.tdone = d_sv_cnt + sv_ninit; sv.ydone = sv.tdone + nt; sv.done = sv.ydone + S.nsup; sv.qhead = sv.done + S.nsup;
+    sv.bpart_stride = (long long)(nslots ? nslots : 1) * CB_PB_MAXNS;
+    CK(cudaMalloc((void**)&sv.bpart, (size_t)2 * sv.bpart_stride * sizeof(double)));
+    sv.ntask = nt;
+    // launch geometry: dynamic shared memory = slab + vectors for one or two right-hand sides
+    for (int nr2 = 1; nr2 <= 2; nr2++)
+      sv_smem[nr2 - 1] = ((size_t)cap + (size_t)nr2 * (2 * CB_PB_MAXNS + SV_MAXROWS + 4 * CB_PB_MAXNS)) * sizeof(double);
+    if ((rc = sv_configure())) return rc;
+    int occ = sv_occupancy();
+    if (occ < 1) return CLDL_E_CUDA;
     df_grid = nsm * occ;
     if (const char* e = std::getenv("CB_DF_GRID")) df_grid = std::max(1, std::atoi(e));
-    use_dataflow = std::getenv("CB_SOLVE_LEVELSYNC") == nullptr;
+    use_dataflow = true;
     if (std::getenv("CB_DF_TRACE_SOLVE") && nt > 0) {
-      CK(cudaMalloc((void**)&df.trace, (size_t)nt * 12 * sizeof(unsigned long long)));
-      CK(cudaMemset(df.trace, 0, (size_t)nt * 12 * sizeof(unsigned long long)));
-      h_df_fronts_first.resize(nt);
-      for (int i = 0; i < nt; i++) h_df_fronts_first[i] = fronts[t_first[i]];
-      h_df_kind = t_kind;
+      CK(cudaMalloc((void**)&sv.trace, (size_t)nt * 8 * sizeof(unsigned long long)));
+      CK(cudaMemset(sv.trace, 0, (size_t)nt * 8 * sizeof(unsigned long long)));
+      h_sv_tasks.assign((const int*)tk.data(), (const int*)tk.data() + (size_t)nt * 24);
     }
+    if (std::getenv("CB_TIMING") != nullptr) std::fprintf(stderr, "[cb timing]     solve plan: %d tasks (%d leaf columns, %d narrow leaves, %d wide fronts, %d row slabs), slab %d doubles, %d CTAs\n",
+                                     nt, sv_nleaf1, sv_nleafn, sv_nwide, nslots, cap, df_grid);
   }
   cb_tmark("ldl:   solve plan: dataflow solve tasks");
   // dataflow factorisation plan (k_factor_df): level 0's small fronts keep their level-synchronous launch
@@ -2447,7 +1907,6 @@ void LDLObject::release() {
   cudaSetDevice(device);
   for (int* p : d_shard_xidx) if (p) cudaFree(p);
   d_shard_xidx.clear();
-  if (d_prog_init) { cudaFree(d_prog_init); d_prog_init = nullptr; }
   if (d_xsend) { cudaFree(d_xsend); d_xsend = nullptr; }
   if (d_xrecv) { cudaFree(d_xrecv); d_xrecv = nullptr; }
   xbuf_cap = 0;
@@ -2456,13 +1915,10 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(d_solve_tasks); fr(d_solve_chains); fr(df.task_first); fr(df.task_cnt); fr(df.task_kind); fr(df.fronts); fr(df.front2task); fr(df.parent); fr(df.pend); fr(df.done); fr(df.qhead); fr(df.trace); fr(d_xp2); fr(d_u2); fr(df2_pend); fr(df2_done); fr(df2_prog); fr(df2_qhead); fr(df.chain_child); fr(df.pure_chain); fr(df.blk_ptr); fr(df.blk_owner); fr(df.prog); fr(d_pend_init); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(sv.tasks); fr(sv.fronts); fr(sv.front2task); fr(sv.parent); fr(sv.bpart); fr(sv.trace); fr(d_sv_cnt); fr(d_sv_init); fr(d_sv_wide); fr(d_sv_leaf1); fr(d_sv_leafn); fr(d_xp2); fr(d_u2); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
-  if (ev_fork) cudaEventDestroy(ev_fork);
-  if (ev_join) cudaEventDestroy(ev_join);
-  if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -2483,6 +1939,7 @@ int LDLObject::refactor_async() {
     }
     g_launches++;
     k_factor_df<<<dff_grid, DF_NT, (size_t)DF_SMEM_DOUBLES * 8, stream>>>(dev, dff);
+    invert_pivots();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
     factored = true;
@@ -2499,10 +1956,18 @@ int LDLObject::refactor_async() {
     else
       k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
   }
+  invert_pivots();
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
   factored = true;
   return CLDL_OK;
+}
+
+// the solves multiply by the inverse of every wide pivot block (ldl_solve.cuh): strictly lower triangle replaced in place
+void LDLObject::invert_pivots() {
+  if (!sv_nwide) return;
+  g_launches++;
+  k_invert_pivots<<<sv_nwide, 64, 0, stream>>>(dev, d_sv_wide, sv_nwide);
 }
 
 int LDLObject::sync_status() {
@@ -2525,64 +1990,90 @@ int LDLObject::sync_status() {
   return h_status[ST_NONFINITE] ? 0 : 1;
 }
 
-int LDLObject::fork_slot1() {
-  CK(cudaEventRecord(ev_fork, stream));
-  CK(cudaStreamWaitEvent(stream2, ev_fork, 0));
+// opt-in to the dynamic shared memory of the sweep kernels (every instantiation that can be launched)
+template <bool FWD, int NR, int MINB>
+static cudaError_t sv_attr(size_t bytes) {
+  return cudaFuncSetAttribute(k_solve2<FWD, NR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+int LDLObject::sv_configure() {
+  for (int nr = 1; nr <= 2; nr++) {
+    const size_t b = sv_smem[nr - 1];
+    cudaError_t e = cudaSuccess;
+    if (solve_minb == 2) { e = nr == 1 ? sv_attr<true, 1, 2>(b) : sv_attr<true, 2, 2>(b); if (e == cudaSuccess) e = nr == 1 ? sv_attr<false, 1, 2>(b) : sv_attr<false, 2, 2>(b); }
+    else if (solve_minb == 3) { e = nr == 1 ? sv_attr<true, 1, 3>(b) : sv_attr<true, 2, 3>(b); if (e == cudaSuccess) e = nr == 1 ? sv_attr<false, 1, 3>(b) : sv_attr<false, 2, 3>(b); }
+    else { e = nr == 1 ? sv_attr<true, 1, 4>(b) : sv_attr<true, 2, 4>(b); if (e == cudaSuccess) e = nr == 1 ? sv_attr<false, 1, 4>(b) : sv_attr<false, 2, 4>(b); }
+    CK(e);
+  }
   return CLDL_OK;
 }
-int LDLObject::join_slot1() {
-  CK(cudaEventRecord(ev_join, stream2));
-  CK(cudaStreamWaitEvent(stream, ev_join, 0));
+int LDLObject::sv_occupancy() {
+  int occ = 1 << 30;
+  for (int fwd = 0; fwd < 2; fwd++) {
+    int o = 0;
+    cudaError_t e;
+    // the two-right-hand-side instantiation needs the most shared memory: it decides how many CTAs are co-resident
+    if (solve_minb == 2) e = fwd ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_solve2<true, 2, 2>, SV_NT, sv_smem[1]) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_solve2<false, 2, 2>, SV_NT, sv_smem[1]);
+    else if (solve_minb == 3) e = fwd ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_solve2<true, 2, 3>, SV_NT, sv_smem[1]) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_solve2<false, 2, 3>, SV_NT, sv_smem[1]);
+    else e = fwd ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_solve2<true, 2, 4>, SV_NT, sv_smem[1]) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_solve2<false, 2, 4>, SV_NT, sv_smem[1]);
+    if (e != cudaSuccess) return 0;
+    occ = std::min(occ, o);
+  }
+  return occ;
+}
+
+template <bool FWD, int NR>
+static void sv_launch(int minb, int grid, size_t smem, cudaStream_t st, const LDLDev& d, const SVPlan& q, const SVRhs& r, int cap) {
+  if (minb == 2) k_solve2<FWD, NR, 2><<<grid, SV_NT, smem, st>>>(d, q, r, cap);
+  else if (minb == 3) k_solve2<FWD, NR, 3><<<grid, SV_NT, smem, st>>>(d, q, r, cap);
+  else k_solve2<FWD, NR, 4><<<grid, SV_NT, smem, st>>>(d, q, r, cap);
+}
+
+// one sweep kernel over the task queue as it stands (queue heads / counters are prepared by the caller)
+void LDLObject::sv_sweep(bool fwd, int nrhs, const SVPlan& q, const SVRhs& r) {
+  g_launches++;
+  const size_t smem = sv_smem[nrhs - 1];
+  if (fwd) { if (nrhs == 1) sv_launch<true, 1>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); else sv_launch<true, 2>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); }
+  else { if (nrhs == 1) sv_launch<false, 1>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); else sv_launch<false, 2>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); }
+}
+// the level-0 narrow fronts: before the forward sweep, after the backward sweep
+void LDLObject::sv_leaves(bool fwd, int nrhs, const SVRhs& r) {
+  if (fwd) {
+    if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_fwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_fwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
+    if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
+  } else {
+    if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
+    if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_bwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_bwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
+  }
+}
+int LDLObject::sv_reset() {
+  CK(cudaMemcpyAsync(d_sv_cnt, d_sv_init, sv_ninit * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  CK(cudaMemsetAsync(d_sv_cnt + sv_ninit, 0, sv_nzero * sizeof(int), stream));
   return CLDL_OK;
 }
 
-int LDLObject::solve_async(double* d_x, const double* d_b, int slot, bool half) {
-  if (sharded()) return (transport && slot == 0) ? solve_sharded(d_x, d_b) : CLDL_E_ARG;
+// one right-hand side (d_x1 == nullptr) or two through the same sweeps (the panels are read once for both)
+int LDLObject::solve_async(double* d_x, const double* d_b, double* d_x1, const double* d_b1) {
+  const int nrhs = d_x1 ? 2 : 1;
+  if (sharded()) {
+    if (!transport) return CLDL_E_ARG;
+    int rc = solve_sharded(d_x, d_b);
+    if (rc || nrhs == 1) return rc;
+    return solve_sharded(d_x1, d_b1);
+  }
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
-  if (use_dataflow) {
-    cudaStream_t sst = slot ? stream2 : stream;
-    LDLDev dv = dev;
-    DFPlan qv = df;
-    double* xp = d_xp;
-    if (slot) {
-      dv.u = d_u2; xp = d_xp2;
-      qv.pend = df2_pend; qv.done = df2_done; qv.prog = df2_prog; qv.qhead = df2_qhead; qv.trace = nullptr;
-    }
-    const int grid = half ? std::max(1, df_grid / 2) : df_grid;
-    g_launches += 3;
-    k_permute_in<<<(n + 255) / 256, 256, 0, sst>>>(n, dev.perm, d_b, xp);
-    CK(cudaMemcpyAsync(qv.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, sst));
-    CK(cudaMemsetAsync(qv.done, 0, (size_t)S.nsup * sizeof(int), sst));
-    CK(cudaMemsetAsync(qv.prog, 0, (size_t)S.nsup * sizeof(int), sst));
-    CK(cudaMemsetAsync(qv.qhead, 0, 2 * sizeof(int), sst));
-    if (solve_minb == 2) {
-      k_solve_df<true, 2><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-      k_solve_df<false, 2><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-    } else if (solve_minb == 3) {
-      k_solve_df<true, 3><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-      k_solve_df<false, 3><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-    } else {
-      k_solve_df<true, 4><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-      k_solve_df<false, 4><<<grid, SV_NT, 0, sst>>>(dv, qv, xp, d_x);
-    }
-    CK(cudaGetLastError());
-    return CLDL_OK;
-  }
-  // level-synchronous fallback: one context only, slot 1 simply runs on the main stream after slot 0
-  if (slot) { CK(cudaStreamSynchronize(stream2)); }
-  g_launches += 1 + solve_launches;
+  SVRhs r;
+  r.xp[0] = d_xp; r.u[0] = dev.u; r.out[0] = d_x;
+  r.xp[1] = nrhs == 2 ? d_xp2 : d_xp; r.u[1] = nrhs == 2 ? d_u2 : dev.u; r.out[1] = nrhs == 2 ? d_x1 : d_x;
+  g_launches += nrhs;
   k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
-  for (int l = 0; l < solve_levels; l++) {
-    const SolveSeg& g = splan[l];
-    if (g.nsmall) k_fwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp);
-    if (g.nbig) k_fwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_chains + g.cbase, d_xp);
-  }
-  for (int l = solve_levels - 1; l >= 0; l--) {
-    const SolveSeg& g = splan[l];
-    if (g.nbig) k_bwd_big<<<g.nbig, SV_NT, 0, stream>>>(dev, d_solve_chains + g.cbase, d_xp, d_x);
-    if (g.nsmall) k_bwd_small<<<(g.nsmall + SV_NT / 32 - 1) / (SV_NT / 32), SV_NT, 0, stream>>>(dev, d_solve_tasks + g.base, g.nsmall, d_xp, d_x);
-  }
+  if (nrhs == 2) k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b1, d_xp2);
+  int rc = sv_reset();
+  if (rc) return rc;
+  sv_leaves(true, nrhs, r);
+  sv_sweep(true, nrhs, sv, r);
+  sv_sweep(false, nrhs, sv, r);
+  sv_leaves(false, nrhs, r);
   CK(cudaGetLastError());
   return CLDL_OK;
 }
@@ -2638,6 +2129,7 @@ int LDLObject::refactor_phase_async(int phase) {
   CK(cudaMemcpyAsync(dff.qhead, &h_phase_start[0], sizeof(int), cudaMemcpyHostToDevice, stream));
   g_launches++;
   k_factor_df<<<dff_grid, DF_NT, (size_t)DF_SMEM_DOUBLES * 8, stream>>>(dev, dff);
+  invert_pivots();
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(h_status, dev.status, ST_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
   factored = true;
@@ -2645,30 +2137,26 @@ int LDLObject::refactor_phase_async(int phase) {
 }
 
 int LDLObject::solve_phase_async(double* d_x, const double* d_b, int phase) {
-  if (!sharded() || !use_dataflow) return CLDL_E_ARG;
+  if (!sharded()) return CLDL_E_ARG;
   if (!factored) return CLDL_E_NOT_FACTORED;
   CK(cudaSetDevice(device));
-  DFPlan qv = df;
-  auto sweep = [&](bool fwd, const DFPlan& q) {
-    g_launches++;
-    if (solve_minb == 2) { if (fwd) k_solve_df<true, 2><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); else k_solve_df<false, 2><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); }
-    else if (solve_minb == 3) { if (fwd) k_solve_df<true, 3><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); else k_solve_df<false, 3><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); }
-    else { if (fwd) k_solve_df<true, 4><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); else k_solve_df<false, 4><<<df_grid, SV_NT, 0, stream>>>(dev, q, d_xp, d_x); }
-  };
+  SVPlan qv = sv;
+  SVRhs r;
+  r.xp[0] = r.xp[1] = d_xp; r.u[0] = r.u[1] = dev.u; r.out[0] = r.out[1] = d_x;
   if (phase == 0) {
     g_launches++;
     k_permute_in<<<(n + 255) / 256, 256, 0, stream>>>(n, dev.perm, d_b, d_xp);
-    CK(cudaMemcpyAsync(qv.pend, d_pend_init, (size_t)df.ntask * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-    CK(cudaMemsetAsync(qv.done, 0, (size_t)S.nsup * sizeof(int), stream));
-    CK(cudaMemcpyAsync(qv.prog, d_prog_init, (size_t)S.nsup * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-    CK(cudaMemsetAsync(qv.qhead, 0, 2 * sizeof(int), stream));
-    qv.ntask = df_ntask_owned;
-    sweep(true, qv);
+    int rc = sv_reset();
+    if (rc) return rc;
+    sv_leaves(true, 1, r);
+    qv.ntask = sv_ntask_owned;
+    sv_sweep(true, 1, qv, r);
   } else {
-    h_phase_start[1] = df_ntask_owned;
+    h_phase_start[1] = sv_ntask_owned;
     CK(cudaMemcpyAsync(qv.qhead, &h_phase_start[1], sizeof(int), cudaMemcpyHostToDevice, stream));
-    sweep(true, qv);
-    sweep(false, qv);
+    sv_sweep(true, 1, qv, r);
+    sv_sweep(false, 1, qv, r);
+    sv_leaves(false, 1, r);
   }
   CK(cudaGetLastError());
   return CLDL_OK;
@@ -2905,14 +2393,13 @@ int cldl_solve(cldl_t* h, double* x, const double* b) {
   if (rc) return rc;
   if (cudaMemcpyAsync(x, o.d_bx + o.n, bytes, cudaMemcpyDeviceToHost, o.stream) != cudaSuccess) return CLDL_E_CUDA;
   if (cudaStreamSynchronize(o.stream) != cudaSuccess) return CLDL_E_CUDA;
-  if (o.df.trace && o.use_dataflow) {   // diagnostic: CB_DF_TRACE_SOLVE=<file> dumps the last solve's task timeline
-    const long long nt = o.df.ntask;
-    std::vector<unsigned long long> tr((size_t)nt * 12);
-    cudaMemcpy(tr.data(), o.df.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (o.sv.trace) {   // diagnostic: CB_DF_TRACE_SOLVE=<file> dumps the last solve's task timeline (scripts/df_trace_solve.py)
+    const long long nt = o.sv.ntask;
+    std::vector<unsigned long long> tr((size_t)nt * 8);
+    cudaMemcpy(tr.data(), o.sv.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (FILE* fp = std::fopen(std::getenv("CB_DF_TRACE_SOLVE"), "wb")) {
       std::fwrite(&nt, sizeof(nt), 1, fp);
-      std::fwrite(o.h_df_fronts_first.data(), sizeof(int), (size_t)nt, fp);
-      std::fwrite(o.h_df_kind.data(), sizeof(int), (size_t)nt, fp);
+      std::fwrite(o.h_sv_tasks.data(), sizeof(int), (size_t)nt * 24, fp);
       std::fwrite(tr.data(), sizeof(unsigned long long), tr.size(), fp);
       std::fclose(fp);
     }

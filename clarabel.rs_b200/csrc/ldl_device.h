@@ -7,6 +7,7 @@
 
 #include "../../include/clarabel_b200.h"
 #include "symbolic.h"
+#include "ldl_solve_plan.h"
 
 #define CB_MAX_PANEL 128
 #define CB_PB_MAXNS 64     /* widest panel (columns) of a front */
@@ -61,27 +62,6 @@ struct LaunchSeg {
   int level, base, count, smem_doubles, threads;
 };
 
-// dataflow solve plan (see k_solve_df in ldl.cu)
-struct DFPlan {
-  int ntask = 0;
-  const int* task_first = nullptr;   // into fronts[]
-  const int* task_cnt = nullptr;
-  const int* task_kind = nullptr;    // 0 = batch of narrow fronts, 1 = one wide front
-  const int* fronts = nullptr;
-  const int* front2task = nullptr;
-  const int* parent = nullptr;       // sn_parent
-  int* pend = nullptr;               // forward counters (reset from pend_init before every sweep)
-  int* done = nullptr;               // backward: per front done flag
-  int* qhead = nullptr;              // [2] queue heads (forward, backward)
-  const int* chain_child = nullptr;  // [nsup] wide child whose rows are exactly cols+rows of this front, or -1
-  int* prog = nullptr;               // [nsup] forward: 64-row blocks of the update vector already final
-  const signed char* pure_chain = nullptr;  // [nsup] 1: the chain child is the only child (gather = shifted copy)
-  const int* blk_ptr = nullptr;      // [nsup+1] into blk_owner
-  const int* blk_owner = nullptr;    // per 64-row block of a wide front: front owning the block's first row
-  unsigned long long* trace = nullptr;  // optional [2][ntask][4]: grab, ready, end (globaltimer ns), mid
-};
-
-
 // dataflow factorisation plan (see k_factor_df in ldl.cu)
 struct DFFactor {
   int ntask = 0;
@@ -99,29 +79,29 @@ struct DFFactor {
 };
 
 
-struct SolveSeg {
-  int base = 0, cbase = 0, nsmall = 0, nbig = 0;
-};
-
 class LDLObject {
  public:
-  std::vector<SolveSeg> splan;
-  int* d_solve_tasks = nullptr;
-  int2* d_solve_chains = nullptr;
-  DFPlan df;
+  // triangular solves (ldl_solve.cuh): task queue, counters, level-0 leaf lists, wide fronts whose pivot block is inverted
+  SVPlan sv;
+  int *d_sv_init = nullptr, *d_sv_cnt = nullptr, *d_sv_wide = nullptr, *d_sv_leaf1 = nullptr, *d_sv_leafn = nullptr;
+  size_t sv_ninit = 0, sv_nzero = 0, sv_smem[2] = {0, 0};
+  int sv_cap = 0, sv_nwide = 0, sv_nleaf1 = 0, sv_nleafn = 0, sv_ntask_owned = 0;
+  std::vector<int> h_sv_tasks;
+  int sv_configure();
+  int sv_occupancy();
+  int sv_reset();
+  void sv_sweep(bool fwd, int nrhs, const SVPlan& q, const SVRhs& r);
+  void sv_leaves(bool fwd, int nrhs, const SVRhs& r);
+  void invert_pivots();
   DFFactor dff;
   int *d_dff_init = nullptr, *d_dff_cnt = nullptr;
   std::vector<int> h_dff_tasks;
-  std::vector<int> h_df_fronts_first, h_df_kind;
   int dff_grid = 0;
   size_t dff_nsup4 = 0;
   bool factor_dataflow = true;
-  int* d_pend_init = nullptr;
   int df_grid = 0;
   int solve_minb = 4;
   bool use_dataflow = true;
-  int solve_levels = 0;
-  unsigned long long solve_launches = 0;
   int n = 0;
   int64_t nnzA = 0;
   int device = 0;
@@ -150,8 +130,7 @@ class LDLObject {
   std::vector<std::vector<int>> shard_cut;   // per rank: its cut roots (fronts whose parent is in the top part)
   std::vector<std::vector<int>> shard_xidx;  // per rank: caller-order indices of the x entries it computes
   std::vector<int*> d_shard_xidx;            // the same lists on the device
-  int dff_ntask_owned = 0, df_ntask_owned = 0;   // tasks of the owned phase (they come first in both queues)
-  int* d_prog_init = nullptr;            // forward solve: progress counters with the other ranks' fronts pre-completed
+  int dff_ntask_owned = 0;               // tasks of the owned phase (they come first in the queue)
   int h_phase_start[2] = {0, 0};         // pinned-lifetime host copies of the queue heads the top phases start from
   uint64_t shard_count_owned[2] = {0, 0};    // regularize_count / positive_inertia of the owned phase
   bool sharded() const { return shard_nranks > 1; }
@@ -177,16 +156,9 @@ class LDLObject {
   void release();
   int refactor_async();
   int sync_status();
-  // slot 1 is a second, independent solve context (own stream, work vectors and dataflow counters): two
-  // right-hand sides can be in flight at once; `half` launches the sweeps on half of the co-resident CTAs so
-  // that two concurrent solves share the machine instead of queueing behind each other
-  int solve_async(double* d_x, const double* d_b, int slot = 0, bool half = false);
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  double *d_xp2 = nullptr, *d_u2 = nullptr;
-  int *df2_pend = nullptr, *df2_done = nullptr, *df2_prog = nullptr, *df2_qhead = nullptr;
-  int fork_slot1();   // stream2 waits for everything issued on `stream` so far
-  int join_slot1();   // `stream` waits for everything issued on stream2 so far
+  // one right-hand side, or two swept together (d_x1 / d_b1 non-null): the panels are read once for both
+  int solve_async(double* d_x, const double* d_b, double* d_x1 = nullptr, const double* d_b1 = nullptr);
+  double *d_xp2 = nullptr, *d_u2 = nullptr;   // work vectors of the second right-hand side
   int ensure_tmp(size_t len);
   int stage_index(const uint64_t* index, uint64_t len);
 };

@@ -1,0 +1,464 @@
+// Triangular solves of the multifrontal LDL^T (device code, included by ldl.cu).
+//
+//   x <- b[perm];  forward: L y = x (leaves -> root);  backward: x = L^-T D^-1 y (root -> leaves);  out[perm] <- x
+//   (reference: qdldl.rs:116-138 solve, :708-719 _lsolve, :737-752 _dltsolve -- column by column on one thread)
+//
+// Layout the sweeps rely on.  A front s with ns pivots and nr rows below stores its panel (ns+nr) x ns column-major
+// in d.L.  For wide fronts (ns > CB_SOLVE_SMALL_NS) the strictly lower triangle of the pivot block holds
+// L11^-1 (unit diagonal implied), written by k_invert_pivots at the end of every refactorisation: the ns dependent
+// substitution steps of a pivot block become one ns x ns matrix-vector product.  Narrow fronts keep L11.
+//
+// Schedule.  Tree level 0 has no dependencies: its narrow fronts are swept by plain kernels before (forward) and
+// after (backward) the dataflow kernel -- one THREAD per single-column front, one warp per front otherwise.
+// Everything else is ONE persistent kernel per sweep; CTAs pull 96-byte task records from a queue in level order:
+//   narrow batch   up to 8 narrow fronts, one warp each (substitution in registers / global memory)
+//   head           one wide front: pivot block + its first rh rows.  The slab (<= cap doubles) goes to shared memory
+//                  with cp.async BEFORE the task waits for its dependencies, so the wait hides the load
+//   rows           a further slab of rows of a wide front whose panel exceeds cap: several CTAs stream one front
+// Dependencies are counters / flags in global memory (release: stores -> __syncthreads -> one thread fences and
+// sets the flag; acquire: one thread spins, fences, __syncthreads, consumers read with ld.global.cg).  A chain
+// child (rows(c) = cols(p) + rows(p)) is followed slab by slab: the parent's head starts as soon as the child's
+// tasks covering the parent's pivot rows are done.  Every sum has a fixed order: no floating-point atomics, two
+// solves of the same right-hand side are bit-identical, and a right-hand side gives the same bits whether it is
+// swept alone (NR = 1) or next to a second one (NR = 2: the panels are read once for both).
+#pragma once
+
+#include "ldl_solve_plan.h"
+
+__device__ __forceinline__ void sv_cp8(double* smem_dst, const double* gsrc) {
+#ifdef CB_EMU
+  *smem_dst = *gsrc;
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void sv_cp_commit_wait() {
+#ifndef CB_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// ---- narrow fronts (ns <= CB_SOLVE_SMALL_NS): one warp, substitution ----
+__device__ void df_fwd_small(const LDLDev& d, double* __restrict__ u, int s, double* __restrict__ xp, int lane) {
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  double* us = u + rp;
+  const int* __restrict__ gp = d.gat_ptr + (f + rp);
+  for (int p = lane; p < ld; p += 32) {
+    double acc = 0.0;
+    for (int e = gp[p]; e < gp[p + 1]; e++) acc += __ldcg(u + d.gat_src[e]);
+    if (p < ns) xp[f + p] += acc; else us[p - ns] = acc;
+  }
+  __syncwarp();
+  for (int j = 0; j + 1 < ns; j++) {
+    const double xj = xp[f + j];
+    for (int i = j + 1 + lane; i < ns; i += 32) xp[f + i] -= P[(long long)j * ld + i] * xj;
+    __syncwarp();
+  }
+  for (int a = lane; a < nr; a += 32) {
+    double acc = 0.0;
+    for (int j = 0; j < ns; j++) acc += P[(long long)j * ld + ns + a] * xp[f + j];
+    us[a] -= acc;
+  }
+}
+
+__device__ void df_bwd_small(const LDLDev& d, int s, double* __restrict__ xp, double* __restrict__ out, int lane) {
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  const int* __restrict__ rows = d.sn_rows + rp;
+  if (nr <= 8 * 32) {
+    // the ancestors' solution entries this front needs are fetched once (index -> value is a dependent pair of loads)
+    double xv[8];
+#pragma unroll
+    for (int q8 = 0; q8 < 8; q8++) {
+      const int a = lane + 32 * q8;
+      xv[q8] = a < nr ? __ldcg(xp + rows[a]) : 0.0;
+    }
+    for (int j = 0; j < ns; j++) {
+      const double* __restrict__ cj = P + (long long)j * ld + ns;
+      double acc = 0.0;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; q8++) {
+        const int a = lane + 32 * q8;
+        if (a < nr) acc += cj[a] * xv[q8];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+    }
+  } else {
+    for (int j = 0; j < ns; j++) {
+      const double* __restrict__ cj = P + (long long)j * ld + ns;
+      double acc = 0.0;
+      for (int a = lane; a < nr; a += 32) acc += cj[a] * __ldcg(xp + rows[a]);
+      __syncwarp();   // lanes leave the strided loop at different trip counts: reconverge before the shuffles
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) xp[f + j] = xp[f + j] * d.Dinv[f + j] - acc;
+    }
+  }
+  __syncwarp();
+  for (int j = ns - 1; j > 0; j--) {
+    const double xj = xp[f + j];
+    for (int i = lane; i < j; i += 32) xp[f + i] -= P[(long long)i * ld + j] * xj;
+    __syncwarp();
+  }
+  for (int j = lane; j < ns; j += 32) out[d.perm[f + j]] = xp[f + j];
+}
+
+// ---- tree level 0, narrow fronts: no dependencies, plain kernels around the dataflow sweep ----
+// single-column leaves: one thread per front (ones[] lists them)
+template <int NR>
+__global__ void __launch_bounds__(256) k_fwd_leaf1(LDLDev d, const int* __restrict__ ones, int count, SVRhs r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int s = ones[i];
+  const int f = d.sn_first[s];
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const double* __restrict__ P = d.L + d.panel_off[s] + 1;
+#pragma unroll
+  for (int h = 0; h < NR; h++) {
+    const double x = r.xp[h][f];
+    double* us = r.u[h] + rp;
+    for (int a = 0; a < nr; a++) us[a] = -(P[a] * x);
+  }
+}
+template <int NR>
+__global__ void __launch_bounds__(256) k_bwd_leaf1(LDLDev d, const int* __restrict__ ones, int count, SVRhs r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int s = ones[i];
+  const int f = d.sn_first[s];
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const double* __restrict__ P = d.L + d.panel_off[s] + 1;
+  const int* __restrict__ rows = d.sn_rows + rp;
+  const double di = d.Dinv[f];
+  const int pf = d.perm[f];
+#pragma unroll
+  for (int h = 0; h < NR; h++) {
+    double acc = 0.0;
+    for (int a = 0; a < nr; a++) acc += P[a] * r.xp[h][rows[a]];
+    const double x = r.xp[h][f] * di - acc;
+    r.xp[h][f] = x;
+    r.out[h][pf] = x;
+  }
+}
+// other narrow leaves: one warp per front
+template <int NR, bool FWD>
+__global__ void __launch_bounds__(256) k_leaf_small(LDLDev d, const int* __restrict__ list, int count, SVRhs r) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const int s = list[w];
+#pragma unroll
+  for (int h = 0; h < NR; h++) {
+    if (FWD) df_fwd_small(d, r.u[h], s, r.xp[h], lane);
+    else df_bwd_small(d, s, r.xp[h], r.out[h], lane);
+    __syncwarp();
+  }
+}
+
+// ---- pivot-block inverses (end of every refactorisation) ----
+// One CTA of 64 threads per wide front: thread j builds column j of X = L11^-1 by forward substitution on e_j
+// (X[j][j] = 1, X[i][j] = -sum_{k=j..i-1} L[i][k] X[k][j]); the strictly lower triangle of X replaces that of L11.
+__global__ void __launch_bounds__(64) k_invert_pivots(LDLDev d, const int* __restrict__ wide, int count) {
+  // one array: L11 row-major in the strictly lower triangle (sA[i][k], k < i), column j of X in ROW j of the upper
+  // triangle (sA[j][i], i > j) -- both conflict-free for the access pattern below
+  __shared__ double sA[CB_PB_MAXNS * (CB_PB_MAXNS + 1)];
+  const int s = wide[blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const int ld = ns + (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
+  double* __restrict__ P = d.L + d.panel_off[s];
+  const int tid = threadIdx.x;
+  const int LDS = CB_PB_MAXNS + 1;
+  for (int j = 0; j < ns; j++)
+    for (int i = j + 1 + tid; i < ns; i += 64) sA[i * LDS + j] = P[(long long)j * ld + i];
+  __syncthreads();
+  if (tid < ns) {
+    const int j = tid;
+    double* X = sA + j * LDS;          // X[i] = (L11^-1)[i][j] for i > j
+    for (int i = j + 1; i < ns; i++) {
+      const double* Li = sA + i * LDS;
+      double acc = Li[j];              // k = j term: L[i][j] * X[j][j], X[j][j] = 1
+      for (int k = j + 1; k < i; k++) acc += Li[k] * X[k];
+      X[i] = -acc;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < ns; j++)
+    for (int i = j + 1 + tid; i < ns; i += 64) P[(long long)j * ld + i] = sA[j * LDS + i];
+}
+
+// ---- the dataflow sweep ----
+__device__ __forceinline__ void sv_wait_zero(volatile int* p) {
+  unsigned ns = 20;
+  while (*p > 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
+}
+__device__ __forceinline__ void sv_wait_set(volatile int* p) {
+  unsigned ns = 20;
+  while (*p == 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
+}
+
+// slab -> shared memory, column-major with leading dimension lds: columns [0, ns), panel rows [row0, row0 + rows)
+__device__ __forceinline__ void sv_stage(double* slab, const double* __restrict__ P, int ld, int ns, int row0, int rows, int lds) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < ns; j += SV_NT / 32) {
+    const double* __restrict__ src = P + (long long)j * ld + row0;
+    double* dst = slab + j * lds;
+    for (int i = lane; i < rows; i += 32) sv_cp8(dst + i, src + i);
+  }
+}
+
+template <bool FWD, int NR, int MINB>
+__global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRhs r, int cap) {
+  extern __shared__ double sv_smem[];
+  double* slab = sv_smem;                       // cap doubles
+  double* sw = slab + cap;                      // NR * 64: gathered right-hand side of the pivot block / D^-1 y - sums
+  double* sy = sw + NR * CB_PB_MAXNS;           // NR * 64: pivot solution
+  double* sx = sy + NR * CB_PB_MAXNS;           // NR * SV_MAXROWS: backward, x at the slab's rows
+  double* sred = sx + NR * SV_MAXROWS;          // NR * 4 * 64: backward, partial column sums of the four row quarters
+  __shared__ int4 s_rec[6];
+  __shared__ int s_task;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_task = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
+    __syncthreads();
+    const int qi = s_task;
+    if (qi >= q.ntask) break;
+    const int k = FWD ? qi : q.ntask - 1 - qi;
+    unsigned long long* trk = q.trace ? q.trace + 4 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
+    if (trk && tid == 0) trk[0] = df_gtime();
+    if (tid < 6) s_rec[tid] = q.tasks[6 * (size_t)k + tid];
+    __syncthreads();
+    const SVTask& T = *reinterpret_cast<const SVTask*>(s_rec);
+    const int kind = T.kind;
+    if (kind == 0) {
+      // ---------------- batch of narrow fronts ----------------
+      const int first = T.s, cnt = T.cnt;
+      if (FWD) {
+        if (tid == 0) { sv_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
+        __syncthreads();
+        if (warp < cnt) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) { df_fwd_small(d, r.u[h], q.fronts[first + warp], r.xp[h], lane); __syncwarp(); }
+        }
+        __syncthreads();
+        if (tid < cnt) {
+          __threadfence();
+          const int p = q.parent[q.fronts[first + tid]];
+          if (p >= 0) atomicSub(q.pend + q.front2task[p], 1);
+        }
+      } else {
+        if (warp < cnt) {
+          const int s = q.fronts[first + warp];
+          if (lane == 0) { const int p = q.parent[s]; if (p >= 0) sv_wait_set(q.done + p); __threadfence(); }
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < NR; h++) { df_bwd_small(d, s, r.xp[h], r.out[h], lane); __syncwarp(); }
+          if (lane == 0) { __threadfence(); atomicExch(q.done + s, 1); }
+        }
+      }
+      if (trk && tid == 0) trk[2] = df_gtime();
+      continue;
+    }
+    // ---------------- wide front: head (pivot block + first rows) or a further slab of rows ----------------
+    const int s = T.s, f = T.f, ns = T.ns, nr = T.nr, r0 = T.r0, r1 = T.r1;
+    const int ld = ns + nr;
+    const int rows = r1 - r0;                                   // rows of L21 in this slab
+    const bool head = kind == 1;
+    const int srows = head ? ns + rows : rows;                  // rows of the staged slab
+    const int lds = srows | 1;                                  // odd: the transposed reads of the backward sweep spread over the banks
+    const int l21 = head ? ns : 0;                              // where the L21 rows start inside the slab
+    const double* __restrict__ P = d.L + T.poff;
+    sv_stage(slab, P, ld, ns, head ? 0 : ns + r0, srows, lds);  // in flight while the task waits below
+    const long long rp = T.rp;
+    if (FWD) {
+      const int* __restrict__ gp = d.gat_ptr + (f + rp);
+      const bool pure = T.pure != 0;
+      // static gather ranges: fetched before the wait
+      int ga0 = 0, ga1 = 0, gb0[2] = {0, 0}, gb1[2] = {0, 0};
+      if (!pure) {
+        if (head && tid < ns) { ga0 = gp[tid]; ga1 = gp[tid + 1]; }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const int a = tid + t * SV_NT;
+          if (a < rows) { gb0[t] = gp[ns + r0 + a]; gb1[t] = gp[ns + r0 + a + 1]; }
+        }
+      }
+      if (tid == 0) {
+        if (head) sv_wait_zero(q.pend + k); else sv_wait_set(q.ydone + s);
+        for (int t = T.dep0; t <= T.dep1; t++) sv_wait_set(q.tdone + t);
+        __threadfence();
+        if (trk) trk[1] = df_gtime();
+      }
+      __syncthreads();
+      if (head) {
+        // phase A: y1 = L11^-1 (b1 + children)
+        if (tid < ns) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) {
+            double acc = 0.0;
+            if (pure) acc = __ldcg(r.u[h] + T.cuoff + tid);
+            else for (int e = ga0; e < ga1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
+            sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] + acc;
+          }
+        }
+        sv_cp_commit_wait();
+        __syncthreads();
+        if (tid < ns) {
+          double y[NR];
+#pragma unroll
+          for (int h = 0; h < NR; h++) y[h] = sw[h * CB_PB_MAXNS + tid];
+          for (int j = 0; j < tid; j++) {
+            const double l = slab[j * lds + tid];
+#pragma unroll
+            for (int h = 0; h < NR; h++) y[h] += l * sw[h * CB_PB_MAXNS + j];
+          }
+#pragma unroll
+          for (int h = 0; h < NR; h++) { sy[h * CB_PB_MAXNS + tid] = y[h]; r.xp[h][f + tid] = y[h]; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          if (T.nrt > 0) { __threadfence(); atomicExch(q.ydone + s, 1); }
+          if (T.dep2 > T.dep1) { for (int t = max(T.dep1 + 1, T.dep0); t <= T.dep2; t++) sv_wait_set(q.tdone + t); __threadfence(); }
+        }
+        if (T.dep2 > T.dep1) __syncthreads();
+      } else {
+        if (tid < ns) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) sy[h * CB_PB_MAXNS + tid] = __ldcg(r.xp[h] + f + tid);
+        }
+        sv_cp_commit_wait();
+        __syncthreads();
+      }
+      // phase B: u[rows] = children - L21 y1
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int a = tid + t * SV_NT;
+        if (a < rows) {
+          double g[NR], acc[NR];
+#pragma unroll
+          for (int h = 0; h < NR; h++) {
+            g[h] = 0.0; acc[h] = 0.0;
+            if (pure) g[h] = __ldcg(r.u[h] + T.cuoff + ns + r0 + a);
+            else for (int e = gb0[t]; e < gb1[t]; e++) g[h] += __ldcg(r.u[h] + d.gat_src[e]);
+          }
+          const double* __restrict__ col = slab + l21 + a;
+          for (int j = 0; j < ns; j++) {
+            const double l = col[j * lds];
+#pragma unroll
+            for (int h = 0; h < NR; h++) acc[h] += l * sy[h * CB_PB_MAXNS + j];
+          }
+#pragma unroll
+          for (int h = 0; h < NR; h++) r.u[h][rp + r0 + a] = g[h] - acc[h];
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicExch(q.tdone + k, 1);
+        if (atomicSub(q.fleft + s, 1) == 1 && T.notify && T.ptask >= 0) atomicSub(q.pend + T.ptask, 1);
+        if (trk) trk[2] = df_gtime();
+      }
+    } else {
+      // ---------------- backward ----------------
+      const int* __restrict__ rowsi = d.sn_rows + rp + r0;
+      int ri[2] = {0, 0};
+#pragma unroll
+      for (int t = 0; t < 2; t++) { const int a = tid + t * SV_NT; if (a < rows) ri[t] = rowsi[a]; }   // static: before the wait
+      if (tid == 0) {
+        if (head && T.nrt > 0) sv_wait_zero(q.bleft + s);
+        if (T.bowner >= 0) sv_wait_set(q.done + T.bowner);
+        __threadfence();
+        if (trk) trk[1] = df_gtime();
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int a = tid + t * SV_NT;
+        if (a < rows) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) sx[h * SV_MAXROWS + a] = __ldcg(r.xp[h] + ri[t]);
+        }
+      }
+      if (head && tid < ns) {
+        const double di = d.Dinv[f + tid];
+#pragma unroll
+        for (int h = 0; h < NR; h++) sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] * di;
+      }
+      sv_cp_commit_wait();
+      __syncthreads();
+      {
+        // column sums over the slab's rows: thread (j, quarter) walks rows quarter, quarter + 4, ...
+        const int j = tid & (CB_PB_MAXNS - 1), qd = tid >> 6;
+        double acc[NR];
+#pragma unroll
+        for (int h = 0; h < NR; h++) acc[h] = 0.0;
+        if (j < ns) {
+          const double* __restrict__ col = slab + j * lds + l21;
+          for (int a = qd; a < rows; a += 4) {
+            const double l = col[a];
+#pragma unroll
+            for (int h = 0; h < NR; h++) acc[h] += l * sx[h * SV_MAXROWS + a];
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < NR; h++) sred[(h * 4 + qd) * CB_PB_MAXNS + j] = acc[h];
+      }
+      __syncthreads();
+      if (!head) {
+        if (tid < ns) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) {
+            const double* sr = sred + h * 4 * CB_PB_MAXNS + tid;
+            q.bpart[h * q.bpart_stride + (long long)T.bslot * CB_PB_MAXNS + tid] =
+                ((sr[0] + sr[CB_PB_MAXNS]) + sr[2 * CB_PB_MAXNS]) + sr[3 * CB_PB_MAXNS];
+          }
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicSub(q.bleft + s, 1); if (trk) trk[2] = df_gtime(); }
+      } else {
+        if (tid < ns) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) {
+            const double* sr = sred + h * 4 * CB_PB_MAXNS + tid;
+            double t = sw[h * CB_PB_MAXNS + tid] - (((sr[0] + sr[CB_PB_MAXNS]) + sr[2 * CB_PB_MAXNS]) + sr[3 * CB_PB_MAXNS]);
+            for (int b = 0; b < T.nrt; b++) t -= __ldcg(q.bpart + h * q.bpart_stride + (long long)(T.bslot + b) * CB_PB_MAXNS + tid);
+            sy[h * CB_PB_MAXNS + tid] = t;
+          }
+        }
+        __syncthreads();
+        if (tid < ns) {
+          // x1 = L11^-T t:  x1[i] = t[i] + sum_{j > i} Linv[j][i] t[j]
+          double x[NR];
+#pragma unroll
+          for (int h = 0; h < NR; h++) x[h] = sy[h * CB_PB_MAXNS + tid];
+          const double* __restrict__ col = slab + tid * lds;
+          for (int j = tid + 1; j < ns; j++) {
+            const double l = col[j];
+#pragma unroll
+            for (int h = 0; h < NR; h++) x[h] += l * sy[h * CB_PB_MAXNS + j];
+          }
+          const int pf = d.perm[f + tid];
+#pragma unroll
+          for (int h = 0; h < NR; h++) { r.xp[h][f + tid] = x[h]; r.out[h][pf] = x[h]; }
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicExch(q.done + s, 1); if (trk) trk[2] = df_gtime(); }
+      }
+    }
+  }
+}

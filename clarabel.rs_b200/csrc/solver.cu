@@ -531,11 +531,8 @@ int KKTDevice::solve2(double* ax, double* az, double* bx, double* bz) {
   const int SB[2] = {S_NORMB, S_NORMB2}, SE[2] = {S_NORME, S_NORME2};
   const CsrDev K = symK();
   const unsigned grid = (N + 127) / 128;
-  // first solves, concurrently
-  if ((rc = ldl.fork_slot1())) return rc;
-  if ((rc = ldl.solve_async(X[0], B[0], 0, true))) return rc;
-  if ((rc = ldl.solve_async(X[1], B[1], 1, true))) return rc;
-  if ((rc = ldl.join_slot1())) return rc;
+  // first solves, together
+  if ((rc = ldl.solve_async(X[0], B[0], X[1], B[1]))) return rc;      // one sweep pair for both right-hand sides
   n_ldl_solve += 2;
   for (int k = 0; k < 2; k++) {
     V.norm_inf(B[k], N, sc->d + SB[k]);
@@ -553,13 +550,10 @@ int KKTDevice::solve2(double* ax, double* az, double* bx, double* bz) {
     if (!active[0] && !active[1]) break;
     const double last[2] = {norme[0], norme[1]};
     if (active[0] && active[1]) {
-      if ((rc = ldl.fork_slot1())) return rc;
-      if ((rc = ldl.solve_async(DX[0], E[0], 0, true))) return rc;
-      if ((rc = ldl.solve_async(DX[1], E[1], 1, true))) return rc;
-      if ((rc = ldl.join_slot1())) return rc;
+      if ((rc = ldl.solve_async(DX[0], E[0], DX[1], E[1]))) return rc;
     } else {
       const int k = active[0] ? 0 : 1;
-      if ((rc = ldl.solve_async(DX[k], E[k], 0, false))) return rc;
+      if ((rc = ldl.solve_async(DX[k], E[k]))) return rc;
     }
     for (int k = 0; k < 2; k++) {
       if (!active[k]) continue;

@@ -45,8 +45,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   if (rc == -5) return CLDL_E_BAD_PERM;
   if (rc) return CLDL_E_ARG;
   cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking);
-  cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev_fork); cudaEventCreate(&ev_join);
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   nnzA = Ap[n];
   cudaMalloc((void**)&dev.vals, (size_t)(nnzA ? nnzA : 1) * sizeof(double));
   std::memcpy(dev.vals, Ax, (size_t)nnzA * sizeof(double));
@@ -68,9 +67,8 @@ void LDLObject::release() {
   d_bx = nullptr;
   cudaFree(dev.vals); dev.vals = nullptr;
   if (stream) cudaStreamDestroy(stream);
-  if (stream2) cudaStreamDestroy(stream2);
-  for (cudaEvent_t* e : {&ev0, &ev1, &ev_fork, &ev_join}) if (*e) cudaEventDestroy(*e);
-  stream = stream2 = nullptr; ev0 = ev1 = ev_fork = ev_join = nullptr;
+  for (cudaEvent_t* e : {&ev0, &ev1}) if (*e) cudaEventDestroy(*e);
+  stream = nullptr; ev0 = ev1 = nullptr;
 }
 
 static int g_nonfinite = 0, g_zeropiv = 0;
@@ -113,11 +111,10 @@ int LDLObject::sync_status() {
   return g_nonfinite ? 0 : 1;
 }
 
-int LDLObject::fork_slot1() { return CLDL_OK; }
-int LDLObject::join_slot1() { return CLDL_OK; }
 
-int LDLObject::solve_async(double* d_x, const double* d_b, int, bool) {
+int LDLObject::solve_async(double* d_x, const double* d_b, double* d_x1, const double* d_b1) {
   if (!factored) return CLDL_E_NOT_FACTORED;
+  if (d_x1) { int rc = solve_async(d_x1, d_b1, nullptr, nullptr); if (rc) return rc; }
   Dense* d = dense_of(this);
   const int N = n;
   std::vector<double> y(N);
