@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark: IPM iterations/s (and KKT-solve / refactor ms)
-on BASELINE.json config C2 (random sparse QP n=1e5, m=2e5, nnz(A)=1e6, Nonneg cone).
+"""bench.py -- headline benchmark: IPM iterations/s (and KKT-solve / refactor ms).
+
+Default workload: BASELINE.json config C4, the configuration the north star quotes its target on (block-angular
+sparse QP, n = 1e6 variables, m = 1.5e6 rows, nnz(A) = 8e6; Zero + Nonneg cones).  `--workload c2|c3|c5|expmix`
+selects the other configurations.
 
 A "step" is one interior-point iteration = one pass of the hot path: cone
 scaling update, KKT value update + static regularisation + numeric LDL^T
@@ -14,8 +17,10 @@ refinement), step lengths, iterate update.
            events on the solver's stream, problem resident in HBM.
 `e2e`    : the same metric through the public API from HOST buffers:
            create (equilibrate + order + symbolic analysis + H2D) + solve + solution D2H.
-N > 1    : one process per GPU (torchrun), one independent problem per rank (seed+rank),
-           no data-path collective (replicas); value = N*K / max-over-ranks time.
+N > 1    : one process per GPU (torchrun).  Default: ONE problem, its LDL^T split over the N GPUs by elimination-tree
+           subtrees (cut roots' update matrices / vectors and the solution vector meet in NCCL
+           all-gathers) -- "scaling": "strong", value = K / max-over-ranks time.  `--replicas`: one independent
+           problem per rank (seed+rank), no data-path collective, "scaling": "weak", value = N*K / max time.
 """
 import argparse
 import json
@@ -121,10 +126,28 @@ def aggregate_over_ranks(dist, world, steps_local, seconds_local, device=None):
 
 
 def algorithmic_bytes(li, N, nnzK):
-    """DESIGN.md 'roofline accounting': bytes one launch sequence must move at minimum."""
-    refactor = 20 * nnzK + 8 * li.nnzL_stored + 16 * N          # read values+maps, write panels, D, Dinv
-    solve = 2 * 8 * li.nnzL_stored + 40 * N                      # panels read in both sweeps + vectors/perm
-    return refactor, solve
+    """Bytes one launch sequence must move at minimum.  `survey`: SURVEY.md section 8(d) / BASELINE.md section 5, the
+    reference's own data structures (CSC factor with indices: 24 B per entry of L over the two sweeps) -- the figure
+    the roofline fraction is quoted on.  `stored`: what this implementation actually has to read (dense panels
+    without indices, 8 B per STORED entry per sweep, zero padding of relaxed supernodes included)."""
+    survey = {"refactor": 12 * nnzK + 12 * li.nnzL + 16 * N, "solve": 24 * li.nnzL + 96 * N}
+    stored = {"refactor": 20 * nnzK + 8 * li.nnzL_stored + 16 * N, "solve": 2 * 8 * li.nnzL_stored + 40 * N}
+    return survey, stored
+
+
+def pin_rank(local_rank, local_world):
+    """Give every rank of a multi-process run its own slice of the host cores (and thereby size the thread pools of
+    the one-time analysis, csrc/symbolic.cpp host_threads()): ranks that each assume the whole box fight over it."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if local_world <= 1 or len(cores) < 2 * local_world:
+            return len(cores)
+        per = len(cores) // local_world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return os.cpu_count()
 
 
 def run_ours(args, rank, world):
@@ -136,9 +159,10 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev_index))
-    shard = bool(args.shard) and world > 1
-    # --shard: ONE problem, its LDL^T split over the N GPUs (subtree sharding); every rank builds the
-    # same data and runs the same iterations.  Default: one independent problem per rank (replicas).
+    shard = world > 1 and not args.replicas
+    # default for N > 1: ONE problem, its LDL^T split over the N GPUs (subtree sharding); every rank
+    # builds the same data and runs the same iterations.  --replicas: one independent problem per rank.
+    host_threads = pin_rank(dev_index, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     pr, desc = load_workload(args.workload, 0 if shard else rank)
     P, q, A, b, cones = pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"]
     n, m = P.shape[0], A.shape[0]
@@ -230,31 +254,39 @@ def run_ours(args, rank, world):
             refactor_ms = solver.time_ms("refactor", 5)
             ldl_solve_ms = solver.time_ms("ldl_solve", 20)
             kkt_solve_ms = solver.time_ms("kkt_solve", 5)
-        b_ref, b_sol = algorithmic_bytes(li, solver.N, int(info.nnzK))
+        b_survey, b_stored = algorithmic_bytes(li, solver.N, int(info.nnzK))
+        b_ref, b_sol = b_survey["refactor"], b_survey["solve"]
         solves_per_iter = info.n_ldl_solve / max(info.n_refactor, 1)
         share_ref = refactor_ms
         share_sol = ldl_solve_ms * solves_per_iter
-        rf_ref = {"kernel": "k_factor_df (+ k_factor_level for tree level 0): numeric LDL^T refactor", "bound": "hbm",
+        acct = ("algorithmic bytes per SURVEY.md 8(d): %s; the bytes this implementation has to read "
+                "(dense panels, padding included) are in algorithmic_bytes_stored / frac_stored")
+        rf_ref = {"kernel": "k_factor_level (tree level 0) + k_factor_df + k_invert_pivots: one numeric LDL^T refactor", "bound": "hbm",
                   "achieved": b_ref / (refactor_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                   "frac": b_ref / (refactor_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                  "algorithmic_bytes": b_ref, "ms": refactor_ms, "share_of_step_ms": share_ref,
+                  "algorithmic_bytes": b_ref, "algorithmic_bytes_stored": b_stored["refactor"],
+                  "frac_stored": b_stored["refactor"] / (refactor_ms * 1e-3) / 1e9 / hbm_peak,
+                  "accounting": acct % "12 nnzK + 12 nnzL + 16 N", "ms": refactor_ms, "share_of_step_ms": share_ref,
                   "fp64_gflops": li.flops / (refactor_ms * 1e-3) / 1e9, "peak_source": peak_src}
-        rf_sol = {"kernel": "k_solve_df<fwd> + k_solve_df<bwd>: one LDL solve (both sweeps)", "bound": "hbm",
+        rf_sol = {"kernel": "k_solve2<fwd> + k_solve2<bwd> (+ leaf kernels, permutation): one LDL solve, both sweeps", "bound": "hbm",
                   "achieved": b_sol / (ldl_solve_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                   "frac": b_sol / (ldl_solve_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                  "algorithmic_bytes": b_sol, "ms": ldl_solve_ms, "share_of_step_ms": share_sol,
+                  "algorithmic_bytes": b_sol, "algorithmic_bytes_stored": b_stored["solve"],
+                  "frac_stored": b_stored["solve"] / (ldl_solve_ms * 1e-3) / 1e9 / hbm_peak,
+                  "accounting": acct % "24 nnzL + 96 N", "ms": ldl_solve_ms, "share_of_step_ms": share_sol,
                   "peak_source": peak_src}
         # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/), if any
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tr.get("workload") == args.workload:
-                rf_ref["traffic"] = tr.get("refactor_dram_bytes")
-                rf_sol["traffic"] = tr.get("solve_dram_bytes")
-                rf_ref["traffic_source"] = rf_sol["traffic_source"] = tr.get("source")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(args.workload, {})
+            rf_ref["traffic"] = tr.get("refactor_dram_bytes")
+            rf_sol["traffic"] = tr.get("solve_dram_bytes")
+            rf_ref["traffic_source"] = rf_sol["traffic_source"] = tr.get("source")
         except Exception:
             pass
         dominant, other = (rf_ref, rf_sol) if share_ref >= share_sol else (rf_sol, rf_ref)
-        cpu = cpu_baseline(pr, sample_iters=args.cpu_sample_iters) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(pr, args.workload, sample_iters=args.cpu_sample_iters, perm=solver.kkt_perm())
         out = {
             "metric": "ipm_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True,
@@ -262,9 +294,10 @@ def run_ours(args, rank, world):
             "config": {"workload": desc, "n": n, "m": m, "nnzA": int(A.nnz), "nnzP_triu": int(P.nnz),
                        "kkt_dim": solver.N, "nnzK": int(info.nnzK), "nnzL": int(li.nnzL),
                        "nnzL_stored": int(li.nnzL_stored), "levels": int(li.n_levels),
-                       "supernodes": int(li.n_supernodes), "ordering": "nested dissection + AMD leaves",
+                       "supernodes": int(li.n_supernodes), "ordering": "nested dissection (hub separators, AMD leaves)",
+                       "host_threads_per_rank": host_threads,
                        "cache": "working set larger than L2 (factor panels %.0f MB)" % (li.nnzL_stored * 8 / 1e6),
-                       "parallelism": ("one problem, subtree-sharded LDL x%d" if shard else "replicas x%d") % world},
+                       "parallelism": ("one problem, subtree-sharded LDL x%d (NCCL all-gather of cut-root update matrices / vectors and of x)" if shard else "replicas x%d") % world},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d_bytes / max(iters_e2e, 1),
                     "d2h_bytes_per_step": d2h_bytes / max(iters_e2e, 1), "setup_s": t_setup,
@@ -287,31 +320,67 @@ def run_ours(args, rank, world):
     return out
 
 
-def cpu_solve(pr, max_iter):
-    """Reference algorithm on the host: oracle IPM + oracle qdldl, single thread, AMD ordering
-    (the reference orders with AMD at dense-scale 1.5; the `amd` crate is not vendored, ours stands in)."""
+def one_core():
+    """Pin the calling process to one core for the single-thread CPU legs; returns a restore function."""
+    try:
+        old = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, {sorted(old)[len(old) // 2]})
+        return lambda: os.sched_setaffinity(0, old)
+    except Exception:
+        return lambda: None
+
+
+def cpu_solve(pr, workload, max_iter, perm=None):
+    """Reference algorithm on the host: oracle IPM + oracle qdldl (line-faithful C port, oracle/), ONE thread pinned to
+    one core.  Ordering: the reference orders with AMD at dense-scale 1.5 (the `amd` crate is not vendored; the
+    repo's own AMD stands in).  On C4 that ordering costs the CPU 2.7e12 flops per refactorisation (about half an
+    hour, measured once: profiles/r02_cpu_c4_amd_container.json), so the CPU leg there gets the nested-dissection
+    ordering the GPU path uses -- 1.5e10 flops, the cheapest ordering known for the reference algorithm: a
+    conservative baseline."""
     import clarabel_rs_b200 as cb
     import oracle
+    os.environ.setdefault("ORACLE_NATIVE", "1")       # -O3 -march=native build of the port on this host, if gcc is here
     t0 = time.perf_counter()
     ipm = oracle.IPM(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"],
                      settings=oracle.default_settings(max_iter=max_iter))
     N, cp, rv, _, _ = ipm.kkt()
-    perm = cb.order(N, cp, rv, cb.ORDER_AMD, 1.5)
+    if workload == "c4":
+        order = "nested dissection (the GPU path's ordering; the reference's own AMD costs 180x the flops here)"
+        if perm is None:
+            perm = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_ND).perm
+    else:
+        order = "AMD (dense scale 1.5)"
+        perm = cb.order(N, cp, rv, cb.ORDER_AMD, 1.5)
     ipm.set_perm(perm)
     t_setup = time.perf_counter() - t0
-    r = ipm.solve()
+    restore = one_core()
+    try:
+        r = ipm.solve()
+    finally:
+        restore()
     t_total = time.perf_counter() - t0
-    return ipm, r, t_setup, t_total
+    return ipm, r, t_setup, t_total, order
 
 
-def cpu_baseline(pr, sample_iters=3):
-    ipm, r, t_setup, t_total = cpu_solve(pr, sample_iters)
+def cpu_baseline(pr, workload, sample_iters=0, perm=None):
+    if sample_iters <= 0:
+        sample_iters = 2 if workload == "c4" else 3
+    ipm, r, t_setup, t_total, order = cpu_solve(pr, workload, sample_iters, perm)
     i = r["info"]
     return {"value": r["iterations"] / i.solve_time, "unit": "iterations/s", "cores": 1, "kind": "port",
-            "sample": "first %d IPM iterations of the same problem (oracle IPM + oracle qdldl, AMD order, 1 thread)" % r["iterations"],
+            "sample": "first %d IPM iterations of the same problem (oracle IPM + oracle qdldl, 1 pinned thread); ordering: %s"
+                      % (r["iterations"], order),
             "host_cores_available": os.cpu_count(), "solve_s": i.solve_time, "setup_s": t_setup,
             "refactor_ms": 1e3 * i.t_kkt_update / max(i.n_refactor, 1), "nnzL": int(i.nnzL),
-            "kkt_solve_ms": 1e3 * i.t_kkt_solve / max(2 * r["iterations"], 1)}
+            "kkt_solve_ms": 1e3 * i.t_kkt_solve / max(2 * r["iterations"], 1), "oracle_build": _oracle_build()}
+
+
+def _oracle_build():
+    try:
+        import oracle
+        return oracle.build_flags()
+    except Exception:
+        return None
 
 
 def run_reference(args, rank, world):
@@ -319,21 +388,26 @@ def run_reference(args, rank, world):
         return None
     pr, desc = load_workload(args.workload, 0)
     W, K = args.warmup, args.steps
-    ipm, r, t_setup, t_total = cpu_solve(pr, W + K)
+    # bounded sample: the whole arm has to end within a few minutes; an iteration of the port costs ~12 s on C4
+    cap = {"c4": 6, "c5": 12}.get(args.workload, W + K)
+    ipm, r, t_setup, t_total, order = cpu_solve(pr, args.workload, min(W + K, cap))
     i = r["info"]
     iters = r["iterations"]
     value = iters / i.solve_time
     return {
         "impl": "reference", "metric": "ipm_iterations_per_sec", "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * i.solve_time / max(iters, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if (world > 1 and not args.replicas) else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "n": ipm.n, "m": ipm.m, "kkt_dim": ipm.N, "nnzK": int(i.nnzK),
-                   "nnzL": int(i.nnzL), "ordering": "AMD (dense scale 1.5)", "parallelism": "1 host thread"},
+                   "nnzL": int(i.nnzL), "ordering": order, "parallelism": "1 host thread"},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port",
-                         "sample": "first %d IPM iterations (max_iter=W+K) of the same problem; the reference is Rust "
-                                   "and cannot be built here, so this is the line-faithful C port (oracle/)" % iters,
+                         "sample": "first %d IPM iterations (min(W+K, %d)) of the same problem; the reference is Rust "
+                                   "and cannot be built here, so this is the line-faithful C port (oracle/), one pinned thread"
+                                   % (iters, cap),
                          "host_cores_available": os.cpu_count(), "setup_s": t_setup,
-                         "refactor_ms": 1e3 * i.t_kkt_update / max(i.n_refactor, 1)},
+                         "refactor_ms": 1e3 * i.t_kkt_update / max(i.n_refactor, 1),
+                         "kkt_solve_ms": 1e3 * i.t_kkt_solve / max(2 * iters, 1), "oracle_build": _oracle_build()},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iterations": iters, "status": r["status"],
     }
@@ -345,11 +419,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--cpu-sample-iters", type=int, default=3)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--cpu-sample-iters", type=int, default=0, help="0 = per workload (2 on c4, 3 elsewhere)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", action="store_true",
-                    help="with --gpus N > 1: split ONE problem's factorisation over the N GPUs instead of N replicas")
+    ap.add_argument("--shard", action="store_true", help="(default for --gpus N > 1; kept for old command lines)")
+    ap.add_argument("--replicas", action="store_true",
+                    help="with --gpus N > 1: N independent problems (weak scaling) instead of ONE problem split over the N GPUs")
     ap.add_argument("--no-process-warmup", action="store_true",
                     help="skip the tiny warm-up problem (for ncu launch lists: keeps the capture on the workload)")
     args = ap.parse_args()

@@ -835,6 +835,8 @@ class CudaSolver:
         _check(rc, "cipm_create_gp")
         self._h = h
         self._cur = {"P": Px.copy(), "q": qq.copy(), "A": Ax.copy(), "b": bb.copy()}      # for the (index, values) update form
+        self._pattern = {"P": (P.indptr.copy(), P.indices.copy()), "A": (A.indptr.copy(), A.indices.copy())}
+        self._shape = {"P": P.shape, "A": A.shape}
         self.N = int(L.cipm_kkt_dim(h))
         self.m_reduced = int(L.cipm_m_reduced(h))    # rows left after the inf-bound presolve
         if shard is not None:
@@ -894,6 +896,10 @@ class CudaSolver:
             if sp.issparse(arg):
                 M = sp.csc_matrix(sp.triu(arg, format="csc") if triu else arg)
                 M.sort_indices()
+                # CscMatrix::is_equal_sparsity (algebra/csc/core.rs:436-445): same pattern, not just the same count
+                ip, ix = self._pattern["P" if triu else "A"]
+                if M.shape != self._shape["P" if triu else "A"] or not (np.array_equal(M.indptr, ip) and np.array_equal(M.indices, ix)):
+                    raise DataUpdateError("SparsityPattern")
                 v = _f64(M.data)
             elif isinstance(arg, tuple) and len(arg) == 2 and not np.isscalar(arg[0]):
                 idx, val = np.asarray(arg[0], dtype=np.int64), _f64(arg[1])

@@ -143,11 +143,13 @@ __global__ void __launch_bounds__(SOC_NT) k_soc_margins(ConeDev c, const double*
   __shared__ double sh[32];
   const int id = c.soc_list[blockIdx.x];
   const int o = c.off[id], n = c.dim[id];
-  double q = 0.0;
-  for (int i = 1 + threadIdx.x; i < n; i += SOC_NT) { const double v = z[o + i]; q += v * v; }
-  q = block_sum(q, sh);
+  Blue3 q{0.0, 0.0, 0.0};     // z[1..].norm() is the reference's overflow-safe norm (socone.rs:105, vecmath.rs:206-226)
+  for (int i = 1 + threadIdx.x; i < n; i += SOC_NT) blue_add(q, z[o + i]);
+  q.big = block_sum(q.big, sh);
+  q.med = block_sum(q.med, sh);
+  q.sml = block_sum(q.sml, sh);
   if (threadIdx.x == 0) {
-    const double a = z[o] - sqrt(q);
+    const double a = z[o] - blue_norm(q);
     pmin[blockIdx.x] = a;
     psum[blockIdx.x] = fmax(a, 0.0);
   }
@@ -369,7 +371,8 @@ int ConeSet::collapse(const int32_t* types, const uint64_t* dims, uint64_t n, st
                       const double* params, const uint64_t* gp_dim2, const double* gp_alpha) {
   out.clear();
   uint64_t k = 0, gp_cursor = 0;
-  auto numel = [](int t, uint64_t d) { return t == CT_PSD ? d * (d + 1) / 2 : d; };
+  // rows a cone occupies; exponential / power cones are three rows whatever dims[] says (supportedcone.rs:54-71)
+  auto numel = [](int t, uint64_t d) -> uint64_t { return t == CT_PSD ? d * (d + 1) / 2 : (t == CT_EXP || t == CT_POW) ? 3 : (t == CT_GENPOW ? (d ? d : 1) : d); };
   while (k < n) {
     const int t = types[k];
     if (t < 0 || t > CT_GENPOW) return -21;

@@ -32,7 +32,7 @@
 
 namespace cb {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 // ------------------------------------------------------------------------
 // kernels
@@ -1431,7 +1431,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     {
       // two passes over the children on host threads: count (pe / te entries per child), prefix sums, fill -- the
       // entry order (child, column b, row a) is the one of a single loop
-      const unsigned hc2 = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      const unsigned hc2 = std::max(1u, std::min(16u, host_threads()));
       const unsigned nth2 = S.nsup < 20000 ? 1u : hc2;
       std::vector<int64_t> npe((size_t)S.nsup + 1, 0), nte((size_t)S.nsup + 1, 0);
       auto eligible = [&](int c) {
@@ -1502,7 +1502,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
         std::vector<int> pos(ptr.begin(), ptr.end() - 1);
         for (auto& e : v) w[pos[e.key]++] = e;
       }
-      const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      const unsigned hc = std::max(1u, std::min(16u, host_threads()));
       std::vector<std::thread> th;
       for (unsigned t = 0; t < hc; t++)
         th.emplace_back([&, t]() {
@@ -1546,7 +1546,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
     // resident CTAs per SM and the slab size that goes with it (227 KB of shared memory per SM, 1 KB reserved per CTA)
-    solve_minb = 3;
+    solve_minb = 3;      // C4 on a B200: 2 / 3 / 4 resident CTAs -> see profiles/ (r02 tuning)
     if (const char* e = std::getenv("CB_SOLVE_MINB")) solve_minb = std::min(4, std::max(2, std::atoi(e)));
     const size_t extra2 = (size_t)2 * (2 * CB_PB_MAXNS + SV_MAXROWS + 4 * CB_PB_MAXNS) * sizeof(double);   // NR = 2 vectors
     {
@@ -1570,7 +1570,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       nrt = rest > 0 ? (rest + rmax - 1) / rmax : 0;
       chunk = nrt ? (rest + nrt - 1) / nrt : 0;
     };
-    std::vector<int> leaf1, leafn, fronts, f2t(S.nsup, -1), nrt_of(S.nsup, 0), rh_of(S.nsup, 0), chunk_of(S.nsup, 0);
+    std::vector<int> leaf1, leafn, leafw, fronts, f2t(S.nsup, -1), nrt_of(S.nsup, 0), rh_of(S.nsup, 0), chunk_of(S.nsup, 0);
     std::vector<SVTask> tk;
     const int per = SV_NT / 32;
     for (int ph = 0; ph < (sharded() ? 2 : 1); ph++) {
@@ -1579,6 +1579,11 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       for (int s = 0; s < S.nsup; s++) {
         if (sharded() && (ph == 0 ? !owned(s) : shard.owner[s] >= 0)) continue;
         if (!wide(s) && !has_kids(s)) { (S.sn_first[s + 1] - S.sn_first[s] == 1 ? leaf1 : leafn).push_back(s); continue; }
+        if (wide(s) && !has_kids(s) && S.sn_rowptr[s + 1] - S.sn_rowptr[s] <= 1024) {
+          leafw.push_back(s);
+          sv_leafw_nrmax = std::max(sv_leafw_nrmax, (int)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]));
+          continue;
+        }
         (wide(s) ? lev_big : lev_small)[S.sn_level[s]].push_back(s);
       }
       for (int l = 0; l < S.nlevels; l++) {
@@ -1664,11 +1669,25 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     std::vector<int> wlist;
     for (int s = 0; s < S.nsup; s++) if (wide(s) && mine(s)) wlist.push_back(s);
     sv_nwide = (int)wlist.size();
-    sv_nleaf1 = (int)leaf1.size(); sv_nleafn = (int)leafn.size();
+    // sorted by pivot count, cut into at most 8 runs (each run is launched with the shared memory of its widest front)
+    std::stable_sort(wlist.begin(), wlist.end(), [&](int a, int b) { return S.sn_first[a + 1] - S.sn_first[a] < S.sn_first[b + 1] - S.sn_first[b]; });
+    sv_wide_runs.clear();
+    {
+      const int bounds[] = {16, 24, 32, 40, 48, 56, CB_PB_MAXNS};
+      int pos = 0;
+      for (int bd : bounds) {
+        int e = pos;
+        while (e < sv_nwide && S.sn_first[wlist[e] + 1] - S.sn_first[wlist[e]] <= bd) e++;
+        if (e > pos) { sv_wide_runs.push_back(pos); sv_wide_runs.push_back(bd); pos = e; }
+      }
+      sv_wide_runs.push_back(sv_nwide); sv_wide_runs.push_back(0);
+    }
+    sv_nleaf1 = (int)leaf1.size(); sv_nleafn = (int)leafn.size(); sv_nleafw = (int)leafw.size();
     int* t1 = nullptr;
     if ((rc = upload(&t1, wlist))) return rc; d_sv_wide = t1;
     if ((rc = upload(&t1, leaf1))) return rc; d_sv_leaf1 = t1;
     if ((rc = upload(&t1, leafn))) return rc; d_sv_leafn = t1;
+    if ((rc = upload(&t1, leafw))) return rc; d_sv_leafw = t1;
     if ((rc = upload(&t1, fronts))) return rc; sv.fronts = t1;
     if ((rc = upload(&t1, f2t))) return rc; sv.front2task = t1;
     if ((rc = upload(&t1, S.sn_parent))) return rc; sv.parent = t1;
@@ -1708,8 +1727,8 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       CK(cudaMemset(sv.trace, 0, (size_t)nt * 8 * sizeof(unsigned long long)));
       h_sv_tasks.assign((const int*)tk.data(), (const int*)tk.data() + (size_t)nt * 24);
     }
-    if (std::getenv("CB_TIMING") != nullptr) std::fprintf(stderr, "[cb timing]     solve plan: %d tasks (%d leaf columns, %d narrow leaves, %d wide fronts, %d row slabs), slab %d doubles, %d CTAs\n",
-                                     nt, sv_nleaf1, sv_nleafn, sv_nwide, nslots, cap, df_grid);
+    if (std::getenv("CB_TIMING") != nullptr) std::fprintf(stderr, "[cb timing]     solve plan: %d tasks (%d leaf columns, %d narrow leaves, %d wide leaves, %d wide fronts, %d row slabs), slab %d doubles, %d CTAs\n",
+                                     nt, sv_nleaf1, sv_nleafn, sv_nleafw, sv_nwide, nslots, cap, df_grid);
   }
   cb_tmark("ldl:   solve plan: dataflow solve tasks");
   // dataflow factorisation plan (k_factor_df): level 0's small fronts keep their level-synchronous launch
@@ -1915,7 +1934,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(sv.tasks); fr(sv.fronts); fr(sv.front2task); fr(sv.parent); fr(sv.bpart); fr(sv.trace); fr(d_sv_cnt); fr(d_sv_init); fr(d_sv_wide); fr(d_sv_leaf1); fr(d_sv_leafn); fr(d_xp2); fr(d_u2); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(sv.tasks); fr(sv.fronts); fr(sv.front2task); fr(sv.parent); fr(sv.bpart); fr(sv.trace); fr(d_sv_cnt); fr(d_sv_init); fr(d_sv_wide); fr(d_sv_leaf1); fr(d_sv_leafn); fr(d_sv_leafw); fr(d_xp2); fr(d_u2); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1967,7 +1986,11 @@ int LDLObject::refactor_async() {
 void LDLObject::invert_pivots() {
   if (!sv_nwide) return;
   g_launches++;
-  k_invert_pivots<<<sv_nwide, 64, 0, stream>>>(dev, d_sv_wide, sv_nwide);
+  // the list is sorted by pivot count: launched in runs of equal width so that each run asks for just its own shared memory
+  for (size_t g = 0; g + 2 < sv_wide_runs.size(); g += 2) {
+    const int first = sv_wide_runs[g], cnt = sv_wide_runs[g + 2] - first, ns = sv_wide_runs[g + 1];
+    k_invert_pivots<<<cnt, 64, (size_t)ns * (ns + 1) * sizeof(double), stream>>>(dev, d_sv_wide + first, cnt);
+  }
 }
 
 int LDLObject::sync_status() {
@@ -2040,7 +2063,14 @@ void LDLObject::sv_leaves(bool fwd, int nrhs, const SVRhs& r) {
   if (fwd) {
     if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_fwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_fwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
     if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
+    if (sv_nleafw) { g_launches++; if (nrhs == 1) k_fwd_leafw<1><<<sv_nleafw, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); else k_fwd_leafw<2><<<sv_nleafw, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); }
   } else {
+    if (sv_nleafw) {
+      g_launches++;
+      const size_t sm = (size_t)nrhs * (sv_leafw_nrmax + CB_PB_MAXNS) * sizeof(double);
+      if (nrhs == 1) k_bwd_leafw<1><<<sv_nleafw, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
+      else k_bwd_leafw<2><<<sv_nleafw, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
+    }
     if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
     if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_bwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_bwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
   }

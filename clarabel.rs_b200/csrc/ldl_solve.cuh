@@ -169,36 +169,171 @@ __global__ void __launch_bounds__(256) k_leaf_small(LDLDev d, const int* __restr
   }
 }
 
+// wide leaves (ns > CB_SOLVE_SMALL_NS, no children): one CTA of 128 threads per front, straight from global memory --
+// nothing to wait for, nothing to gather; many CTAs per SM hide the latency.  Same arithmetic, in the same order, as a
+// head task of the dataflow kernel would do for the front.
+#define SV_LEAF_NT 128
+template <int NR>
+__global__ void __launch_bounds__(SV_LEAF_NT) k_fwd_leafw(LDLDev d, const int* __restrict__ list, int count, SVRhs r) {
+  __shared__ double sb[NR * CB_PB_MAXNS], sy[NR * CB_PB_MAXNS];
+  const int s = list[blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr, tid = threadIdx.x;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  if (tid < ns) {
+#pragma unroll
+    for (int h = 0; h < NR; h++) sb[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] + 0.0;
+  }
+  __syncthreads();
+  if (tid < ns) {
+    double y[NR];
+#pragma unroll
+    for (int h = 0; h < NR; h++) y[h] = sb[h * CB_PB_MAXNS + tid];
+    for (int j = 0; j < tid; j++) {
+      const double l = P[(long long)j * ld + tid];
+#pragma unroll
+      for (int h = 0; h < NR; h++) y[h] += l * sb[h * CB_PB_MAXNS + j];
+    }
+#pragma unroll
+    for (int h = 0; h < NR; h++) { sy[h * CB_PB_MAXNS + tid] = y[h]; r.xp[h][f + tid] = y[h]; }
+  }
+  __syncthreads();
+  for (int a = tid; a < nr; a += SV_LEAF_NT) {
+    double acc[NR];
+#pragma unroll
+    for (int h = 0; h < NR; h++) acc[h] = 0.0;
+    const double* __restrict__ col = P + ns + a;
+    for (int j = 0; j < ns; j++) {
+      const double l = col[(long long)j * ld];
+#pragma unroll
+      for (int h = 0; h < NR; h++) acc[h] += l * sy[h * CB_PB_MAXNS + j];
+    }
+#pragma unroll
+    for (int h = 0; h < NR; h++) r.u[h][rp + a] = 0.0 - acc[h];
+  }
+}
+// backward: warp w owns the columns j = w, w + 4, ...; lanes run down a column (coalesced), one butterfly per column
+template <int NR>
+__global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* __restrict__ list, int count, SVRhs r, int nr_max) {
+  extern __shared__ double lw_smem[];
+  double* sx = lw_smem;                        // NR * nr_max: x at the front's rows
+  double* st = sx + NR * nr_max;               // NR * 64
+  const int s = list[blockIdx.x];
+  const int f = d.sn_first[s];
+  const int ns = d.sn_first[s + 1] - f;
+  const long long rp = d.sn_rowptr[s];
+  const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+  const int ld = ns + nr, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const double* __restrict__ P = d.L + d.panel_off[s];
+  const int* __restrict__ rows = d.sn_rows + rp;
+  for (int a = tid; a < nr; a += SV_LEAF_NT) {
+    const int ri = rows[a];
+#pragma unroll
+    for (int h = 0; h < NR; h++) sx[h * nr_max + a] = r.xp[h][ri];
+  }
+  __syncthreads();
+  for (int j = w; j < ns; j += SV_LEAF_NT / 32) {
+    const double* __restrict__ col = P + (long long)j * ld + ns;
+    double acc[NR];
+#pragma unroll
+    for (int h = 0; h < NR; h++) acc[h] = 0.0;
+    for (int a = lane; a < nr; a += 32) {
+      const double l = col[a];
+#pragma unroll
+      for (int h = 0; h < NR; h++) acc[h] += l * sx[h * nr_max + a];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < NR; h++) {
+      double t = acc[h];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) st[h * CB_PB_MAXNS + j] = r.xp[h][f + j] * d.Dinv[f + j] - t;
+    }
+  }
+  __syncthreads();
+  // x1 = L11^-T t: column i of the inverse below its diagonal, lanes down the column
+  for (int i = w; i < ns; i += SV_LEAF_NT / 32) {
+    const double* __restrict__ col = P + (long long)i * ld;
+    double acc[NR];
+#pragma unroll
+    for (int h = 0; h < NR; h++) acc[h] = 0.0;
+    for (int j = i + 1 + lane; j < ns; j += 32) {
+      const double l = col[j];
+#pragma unroll
+      for (int h = 0; h < NR; h++) acc[h] += l * st[h * CB_PB_MAXNS + j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < NR; h++) {
+      double t = acc[h];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) {
+        const double x = st[h * CB_PB_MAXNS + i] + t;
+        r.xp[h][f + i] = x;
+        r.out[h][d.perm[f + i]] = x;
+      }
+    }
+  }
+}
+
 // ---- pivot-block inverses (end of every refactorisation) ----
 // One CTA of 64 threads per wide front: thread j builds column j of X = L11^-1 by forward substitution on e_j
 // (X[j][j] = 1, X[i][j] = -sum_{k=j..i-1} L[i][k] X[k][j]); the strictly lower triangle of X replaces that of L11.
+// Shared memory holds ONE ns x (ns+1) array (dynamic, sized by the widest front of the launch): L11 row-major in the
+// strictly lower triangle (sA[i][k], k < i), column j of X in ROW j of the upper triangle (sA[j][i], i > j) -- both
+// patterns are conflict-free.  The launch is ordered by ns (host side) so that co-resident CTAs have similar work.
 __global__ void __launch_bounds__(64) k_invert_pivots(LDLDev d, const int* __restrict__ wide, int count) {
-  // one array: L11 row-major in the strictly lower triangle (sA[i][k], k < i), column j of X in ROW j of the upper
-  // triangle (sA[j][i], i > j) -- both conflict-free for the access pattern below
-  __shared__ double sA[CB_PB_MAXNS * (CB_PB_MAXNS + 1)];
+  extern __shared__ double sA[];
   const int s = wide[blockIdx.x];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const int ld = ns + (int)(d.sn_rowptr[s + 1] - d.sn_rowptr[s]);
   double* __restrict__ P = d.L + d.panel_off[s];
-  const int tid = threadIdx.x;
-  const int LDS = CB_PB_MAXNS + 1;
-  for (int j = 0; j < ns; j++)
-    for (int i = j + 1 + tid; i < ns; i += 64) sA[i * LDS + j] = P[(long long)j * ld + i];
-  __syncthreads();
-  if (tid < ns) {
-    const int j = tid;
-    double* X = sA + j * LDS;          // X[i] = (L11^-1)[i][j] for i > j
-    for (int i = j + 1; i < ns; i++) {
-      const double* Li = sA + i * LDS;
-      double acc = Li[j];              // k = j term: L[i][j] * X[j][j], X[j][j] = 1
-      for (int k = j + 1; k < i; k++) acc += Li[k] * X[k];
-      X[i] = -acc;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int LDS = ns | 1;             // odd
+  // columns two per pass and warp (independent loads in flight), lanes down the column
+  for (int j0 = 0; j0 < ns; j0 += 8) {
+    double v[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int j = j0 + 2 * c + w;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int i = lane + 32 * h;
+        v[c][h] = (j < ns && i > j && i < ns) ? P[(long long)j * ld + i] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int j = j0 + 2 * c + w;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int i = lane + 32 * h;
+        if (j < ns && i > j && i < ns) sA[i * LDS + j] = v[c][h];
+      }
     }
   }
   __syncthreads();
-  for (int j = 0; j < ns; j++)
-    for (int i = j + 1 + tid; i < ns; i += 64) P[(long long)j * ld + i] = sA[j * LDS + i];
+  if ((int)threadIdx.x < ns) {
+    const int j = threadIdx.x;
+    double* X = sA + j * LDS;          // X[i] = (L11^-1)[i][j] for i > j
+    for (int i = j + 1; i < ns; i++) {
+      const double* Li = sA + i * LDS;
+      double a0 = Li[j], a1 = 0.0;     // k = j term: L[i][j] * X[j][j], X[j][j] = 1
+      int k = j + 1;
+      for (; k + 1 < i; k += 2) { a0 += Li[k] * X[k]; a1 += Li[k + 1] * X[k + 1]; }
+      if (k < i) a0 += Li[k] * X[k];
+      X[i] = -(a0 + a1);
+    }
+  }
+  __syncthreads();
+  for (int j = w; j < ns; j += 2)
+    for (int i = j + 1 + lane; i < ns; i += 32) P[(long long)j * ld + i] = sA[j * LDS + i];
 }
 
 // ---- the dataflow sweep ----
@@ -229,21 +364,35 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
   double* sy = sw + NR * CB_PB_MAXNS;           // NR * 64: pivot solution
   double* sx = sy + NR * CB_PB_MAXNS;           // NR * SV_MAXROWS: backward, x at the slab's rows
   double* sred = sx + NR * SV_MAXROWS;          // NR * 4 * 64: backward, partial column sums of the four row quarters
-  __shared__ int4 s_rec[6];
-  __shared__ int s_task;
+  // the queue is read one task ahead: while a task runs, the next one's index and record are already on their way
+  // (the grab is an atomic + a dependent 96-byte load, ~1.5 us of pure latency per task otherwise).  Holding a task
+  // that is not started yet is safe: dependencies only point to earlier queue positions.
+  __shared__ int4 s_rec[2][6];
+  __shared__ int s_task[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int cur = 0;
+  if (tid == 0) s_task[0] = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
+  __syncthreads();
+  {
+    const int q0 = s_task[0];
+    if (q0 < q.ntask && tid < 6) s_rec[0][tid] = q.tasks[6 * (size_t)(FWD ? q0 : q.ntask - 1 - q0) + tid];
+  }
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_task = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
-    __syncthreads();
-    const int qi = s_task;
+    const int qi = s_task[cur];
     if (qi >= q.ntask) break;
     const int k = FWD ? qi : q.ntask - 1 - qi;
     unsigned long long* trk = q.trace ? q.trace + 4 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
     if (trk && tid == 0) trk[0] = df_gtime();
-    if (tid < 6) s_rec[tid] = q.tasks[6 * (size_t)k + tid];
-    __syncthreads();
-    const SVTask& T = *reinterpret_cast<const SVTask*>(s_rec);
+    // next task: index by one thread of warp 1, record by its first lanes (same warp, so no block-wide barrier)
+    if (warp == 1) {
+      int qn = 0;
+      if (lane == 0) { qn = atomicAdd(&q.qhead[FWD ? 0 : 1], 1); s_task[cur ^ 1] = qn; }
+      qn = __shfl_sync(0xffffffffu, qn, 0);
+      if (qn < q.ntask && lane < 6) s_rec[cur ^ 1][lane] = q.tasks[6 * (size_t)(FWD ? qn : q.ntask - 1 - qn) + lane];
+    }
+    const SVTask& T = *reinterpret_cast<const SVTask*>(s_rec[cur]);
+    cur ^= 1;
     const int kind = T.kind;
     if (kind == 0) {
       // ---------------- batch of narrow fronts ----------------

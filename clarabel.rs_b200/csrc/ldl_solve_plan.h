@@ -6,7 +6,7 @@
 namespace cb {
 
 #define SV_NT 256
-#define SV_MAXROWS 512      /* rows of L21 in one slab (bounds the staged x / the per-thread row count) */
+#define SV_MAXROWS 256      /* rows of L21 in one slab (bounds the staged x / the per-thread row count) */
 
 struct SVTask {             // 96 bytes = 6 x int4, built on the host (LDLObject::init)
   int kind, s, cnt, f;      // kind 0: narrow batch (s = first index into fronts[], cnt fronts); 1 head; 2 rows

@@ -746,7 +746,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
   if (const char* e = std::getenv("CB_ND_HUBS")) W.hubs = std::atoi(e) != 0;
   W.halo = std::getenv("CB_ND_HALO") != nullptr && std::atoi(std::getenv("CB_ND_HALO")) != 0;
   {
-    unsigned hc = std::thread::hardware_concurrency();
+    unsigned hc = host_threads();
     int d = 0;
     // concurrent subtrees: a few per hardware thread (leaf sizes vary, so oversubscription balances the load;
     // measured on 8 cores: 0.21 s with 8 subtrees, 0.165 s with 32), at most 128

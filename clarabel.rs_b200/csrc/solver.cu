@@ -152,11 +152,16 @@ struct Vec {
     g_launches++;
     k_max_nonneg<<<red_grid(n), RED_THREADS, 0, st>>>(n, [=] __device__(int i) { return x[i]; }, out);
   }
-  // sum of squares of x.*v (the host takes the square root)
-  void sumsq_scaled(const double* x, const double* v, int n, double* out) const {
+  // || x .* v ||_2 (norm_scaled, vecmath.rs:118-121), overflow-safe like the reference's stable_norm
+  void norm_scaled(const double* x, const double* v, int n, double* out) const {
     if (n == 0) { cudaMemsetAsync(out, 0, 8, st); return; }
     g_launches++;
-    k_sum<<<red_grid(n), RED_THREADS, 0, st>>>(n, [=] __device__(int i) { double t = x[i] * v[i]; return t * t; }, ws, out);
+    k_norm2<<<red_grid(n), RED_THREADS, 0, st>>>(n, [=] __device__(int i) { return x[i] * v[i]; }, ws, out);
+  }
+  void norm(const double* x, int n, double* out) const {
+    if (n == 0) { cudaMemsetAsync(out, 0, 8, st); return; }
+    g_launches++;
+    k_norm2<<<red_grid(n), RED_THREADS, 0, st>>>(n, [=] __device__(int i) { return x[i]; }, ws, out);
   }
   void axpby(double* y, double a, const double* x, double b, int n) const {  // y = a x + b y
     if (n == 0) return;
@@ -823,6 +828,28 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
               const int32_t* ctype, const uint64_t* cdim, const cipm_settings& s_, const cldl_opts& lo,
               const int* perm, const double* cparam, const uint64_t* gp_dim2, const double* gp_alpha) {
   n = n_; m = m_; set = s_;
+  // the sparse inputs as CscMatrix::check_format would see them (algebra/csc/core.rs): column pointers start at 0 and
+  // never decrease, row indices are in range and strictly increasing inside a column (sorted, no duplicates); P upper
+  // triangular.  The assembly below relies on it (the diagonal of a P column is its LAST entry, kkt_assembly.rs:20-60)
+  // and the equilibration indexes vectors by row: an unchecked caller would get a silently wrong KKT matrix or a
+  // write out of bounds.  Checked before a device is touched.
+  {
+    auto check = [](const uint64_t* cp, const uint64_t* ri, uint64_t rows, int cols, bool triu) {
+      if (!cp || cp[0] != 0) return (int)CLDL_E_ARG;
+      for (int j = 0; j < cols; j++) if (cp[j + 1] < cp[j]) return (int)CLDL_E_ARG;
+      if (cp[cols] > 0 && !ri) return (int)CLDL_E_ARG;
+      for (int j = 0; j < cols; j++)
+        for (uint64_t t = cp[j]; t < cp[j + 1]; t++) {
+          if (ri[t] >= rows) return (int)CLDL_E_DIM;
+          if (t > cp[j] && ri[t] <= ri[t - 1]) return (int)CLDL_E_ARG;
+          if (triu && ri[t] > (uint64_t)j) return (int)CLDL_E_NOT_TRIU;
+        }
+      return 0;
+    };
+    int vrc = check(Pp, Pi, (uint64_t)n, n, true);
+    if (vrc) return vrc;
+    if ((vrc = check(Ap, Ai, (uint64_t)m, n, false))) return vrc;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     std::fprintf(stderr, "[clarabel_b200] no CUDA device: this backend has no CPU fallback\n");
@@ -961,14 +988,14 @@ int IPM::residuals_update() {
   V.axpby(rx, 1.0, rx_inf, 1.0, n);
   V.waxpby(rz, 1.0, rz_inf, -tau, db, m);
   // norms for info.update (info.rs:112-180): sums of squares, roots on the host
-  V.sumsq_scaled(x, dd, n, sc.d + S_N0);
-  V.sumsq_scaled(z, de, m, sc.d + S_N1);
-  V.sumsq_scaled(s, deinv, m, sc.d + S_N2);
-  V.sumsq_scaled(rx_inf, ddinv, n, sc.d + S_N3);
-  V.sumsq_scaled(Px, ddinv, n, sc.d + S_N4);
-  V.sumsq_scaled(rz_inf, deinv, m, sc.d + S_N5);
-  V.sumsq_scaled(rz, deinv, m, sc.d + S_N6);
-  V.sumsq_scaled(rx, ddinv, n, sc.d + S_N7);
+  V.norm_scaled(x, dd, n, sc.d + S_N0);
+  V.norm_scaled(z, de, m, sc.d + S_N1);
+  V.norm_scaled(s, deinv, m, sc.d + S_N2);
+  V.norm_scaled(rx_inf, ddinv, n, sc.d + S_N3);
+  V.norm_scaled(Px, ddinv, n, sc.d + S_N4);
+  V.norm_scaled(rz_inf, deinv, m, sc.d + S_N5);
+  V.norm_scaled(rz, deinv, m, sc.d + S_N6);
+  V.norm_scaled(rx, ddinv, n, sc.d + S_N7);
   int rc = sc.fetch();
   if (rc) return rc;
   dot_qx = sc.h[S_QX]; dot_bz = sc.h[S_BZ]; dot_sz = sc.h[S_SZ]; dot_xPx = sc.h[S_XPX];
@@ -981,13 +1008,13 @@ void IPM::info_update(double t0) {
   const double xPx2 = dot_xPx * tinv * tinv / 2.0;
   info.cost_primal = (dot_qx * tinv + xPx2) * cinv;
   info.cost_dual = (-dot_bz * tinv - xPx2) * cinv;
-  double normx = std::sqrt(sc.h[S_N0]), normz = std::sqrt(sc.h[S_N1]) * cinv, norms = std::sqrt(sc.h[S_N2]);
-  info.res_primal_inf = (std::sqrt(sc.h[S_N3]) * cinv) / std::fmax(1.0, normz);
-  info.res_dual_inf = std::fmax(std::sqrt(sc.h[S_N4]) / std::fmax(1.0, normx),
-                                std::sqrt(sc.h[S_N5]) / std::fmax(1.0, normx + norms));
+  double normx = sc.h[S_N0], normz = sc.h[S_N1] * cinv, norms = sc.h[S_N2];
+  info.res_primal_inf = (sc.h[S_N3] * cinv) / std::fmax(1.0, normz);
+  info.res_dual_inf = std::fmax(sc.h[S_N4] / std::fmax(1.0, normx),
+                                sc.h[S_N5] / std::fmax(1.0, normx + norms));
   normx *= tinv; normz *= tinv; norms *= tinv;
-  info.res_primal = std::sqrt(sc.h[S_N6]) * tinv / std::fmax(1.0, normb + normx + norms);
-  info.res_dual = std::sqrt(sc.h[S_N7]) * tinv * cinv / std::fmax(1.0, normq + normx + normz);
+  info.res_primal = sc.h[S_N6] * tinv / std::fmax(1.0, normb + normx + norms);
+  info.res_dual = sc.h[S_N7] * tinv * cinv / std::fmax(1.0, normq + normx + normz);
   info.gap_abs = std::fabs(info.cost_primal - info.cost_dual);
   info.gap_rel = info.gap_abs / std::fmax(1.0, std::fmin(std::fabs(info.cost_primal), std::fabs(info.cost_dual)));
   info.ktratio = kap * tinv;
@@ -1470,7 +1497,7 @@ uint64_t cipm_iter_ms(const cipm_t* h, double* out, uint64_t cap) {
   if (out) for (uint64_t i = 0; i < std::min(n, cap); i++) out[i] = h->ipm.iter_ms[i];
   return n;
 }
-uint64_t cipm_launch_count(void) { return cb::g_launches; }
+uint64_t cipm_launch_count(void) { return cb::g_launches.load(std::memory_order_relaxed); }
 // sizes of the structs that cross the ABI, so that a binding can check its own mirror: {cldl_opts, cldl_info_t, cipm_settings, cipm_info}
 void cipm_abi_sizes(uint64_t* out4) { out4[0] = sizeof(cldl_opts); out4[1] = sizeof(cldl_info_t); out4[2] = sizeof(cipm_settings); out4[3] = sizeof(cipm_info); }
 
@@ -1596,13 +1623,12 @@ int cipm_test_vec(cipm_t* h, int what, const double* x, const double* v, uint64_
   if (cudaMalloc((void**)&dx, nb) != cudaSuccess || cudaMalloc((void**)&dv, nb) != cudaSuccess || cudaMalloc((void**)&dout, 8) != cudaSuccess) return CLDL_E_CUDA;
   int rc = (h2d(dx, x, n) || h2d(dv, v ? v : x, n)) ? CLDL_E_CUDA : CLDL_OK;
   if (!rc) {
-    if (what == 0) I.V.dot(dx, dx, (int)n, dout);
+    if (what == 0) I.V.norm(dx, (int)n, dout);
     else if (what == 1) I.V.norm_inf(dx, (int)n, dout);
-    else if (what == 2) I.V.sumsq_scaled(dx, dv, (int)n, dout);
+    else if (what == 2) I.V.norm_scaled(dx, dv, (int)n, dout);
     else I.V.dot(dx, dv, (int)n, dout);
     cudaStreamSynchronize(I.st);
     rc = d2h(out, dout, 1) ? CLDL_E_CUDA : CLDL_OK;
-    if (!rc && (what == 0 || what == 2)) *out = std::sqrt(*out);
   }
   cudaFree(dx); cudaFree(dv); cudaFree(dout);
   return rc;

@@ -1,5 +1,8 @@
 // Symbolic analysis: see symbolic.h.  All integer work, host only, one-time.
 #include "symbolic.h"
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -13,6 +16,17 @@
 #include <chrono>
 
 namespace cb {
+unsigned host_threads() {
+  unsigned n = std::thread::hardware_concurrency();
+#ifdef __linux__
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) n = (unsigned)c; }
+#endif
+  if (const char* e = std::getenv("CB_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0 && (unsigned)v < n) n = (unsigned)v; }
+  return n ? n : 1u;
+}
+
 
 static double tnow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool timing_on() { static int v = -1; if (v < 0) v = std::getenv("CB_TIMING") ? 1 : 0; return v == 1; }
@@ -332,7 +346,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
       }
     }
   };
-  const unsigned hw_rows = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned hw_rows = std::max(1u, std::min(16u, host_threads()));
   if (nsup < 20000 || hw_rows < 2) {
     sequential_rows();
   } else {
@@ -499,7 +513,7 @@ static int build(int n, const int64_t* Ap, const int32_t* Ai, const std::vector<
   std::vector<int64_t> ent_dst(nnz);
   {
     // entries are independent: host threads take column ranges (one binary search per entry)
-    const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned hc = std::max(1u, std::min(16u, host_threads()));
     const unsigned nth = nnz < 200000 ? 1u : hc;
     std::vector<int> bad(nth, 0);
     auto work = [&](unsigned t) {
@@ -746,7 +760,7 @@ int analyse(int n, const int64_t* Ap, const int32_t* Ai, const int* perm_in,
     std::thread amd_thread;
     // only where a spare core is certain: on a small host the extra thread takes time from the dissection's own
     // threads (8 cores, C2: 0.33 s -> 0.37 s when the pass is not needed, 1.30 s -> 0.97 s when it is)
-    bool speculative = std::thread::hardware_concurrency() >= 16;
+    bool speculative = host_threads() >= 16;
     if (const char* e = std::getenv("CB_ORDER_SPECULATIVE")) speculative = std::atoi(e) != 0;
     if (speculative)
       amd_thread = std::thread([&]() {

@@ -24,6 +24,11 @@ void amd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
 void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
               int leaf_size, std::vector<int>& perm, double sep_flop_cap = 0.0);
 
+// host threads this process may use for the one-time analysis: the CPUs of its affinity mask (a launcher that pins
+// every rank to its own cores -- taskset, sched_setaffinity -- thereby also sizes the thread pools), capped by
+// CB_HOST_THREADS when set.  Ranks that share a box must not each assume all of its cores.
+unsigned host_threads();
+
 enum OrderingKind { ORDER_GIVEN = 0, ORDER_AMD = 1, ORDER_ND = 2, ORDER_BEST = 3 };
 
 struct SymbolicOptions {

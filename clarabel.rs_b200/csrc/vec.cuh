@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 
 #include <chrono>
@@ -29,7 +30,7 @@ inline void cb_tmark(const char* label) {
 }
 
 // number of kernels launched by this library (bench.py reports it as gpu_launches)
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;   // bumped from several host threads (per-rank threads, helper threads)
 
 constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
 constexpr int RED_THREADS = 256;
@@ -101,6 +102,73 @@ __global__ void __launch_bounds__(RED_THREADS) k_sum(int n, F f, ReduceWS ws, do
     for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) a += ((volatile double*)ws.partials)[i];
     a = block_sum(a, sh);
     if (threadIdx.x == 0) out[0] = a;
+  }
+}
+
+// ---- overflow-safe 2-norm (the reference's stable_norm, vecmath.rs:206-226) ----
+// The reference threads a running (scale, sumsq) pair through the vector; a parallel reduction cannot, so the same
+// guarantee comes from Blue's three accumulators (the scheme of LAPACK's dnrm2): squares of large entries are summed
+// after scaling by 2^-538, squares of tiny ones after scaling by 2^537, the rest unscaled.  No intermediate overflows
+// or underflows for any finite input, the result is sqrt(sum x_i^2) to a few ulps, NaN propagates, and the three
+// sums are deterministic like every other sum here.
+struct Blue3 { double big, med, sml; };
+__device__ __forceinline__ void blue_add(Blue3& a, double x) {
+  const double tsml = 1.4916681462400413e-154, tbig = 1.9979190722022350e+146;   // 2^-511, 2^486
+  const double ssml = 4.4989137945431964e+161, sbig = 1.1113793747425387e-162;   // 2^537, 2^-538
+  const double ax = fabs(x);
+  if (ax > tbig) { const double t = ax * sbig; a.big += t * t; }
+  else if (ax < tsml) { const double t = ax * ssml; a.sml += t * t; }
+  else a.med += ax * ax;                                                          // NaN lands here and propagates
+}
+__device__ __forceinline__ double blue_norm(const Blue3& a) {
+  const double ssml = 4.4989137945431964e+161, sbig = 1.1113793747425387e-162;
+  if (a.big > 0.0) {
+    double s = a.big;
+    if (a.med > 0.0 || a.med != a.med) s += (a.med * sbig) * sbig;
+    return sqrt(s) / sbig;
+  }
+  if (a.sml > 0.0) {
+    if (a.med > 0.0 || a.med != a.med) {
+      const double m = sqrt(a.med), l = sqrt(a.sml) / ssml;
+      const double ymin = fmin(m, l), ymax = fmax(m, l);
+      return ymax * sqrt(1.0 + (ymin / ymax) * (ymin / ymax));
+    }
+    return sqrt(a.sml) / ssml;
+  }
+  return sqrt(a.med);
+}
+
+// out[0] = || f(i) ||_2 over i < n, overflow-safe and deterministic
+template <class F>
+__global__ void __launch_bounds__(RED_THREADS) k_norm2(int n, F f, ReduceWS ws, double* out) {
+  __shared__ double sh[32];
+  __shared__ bool last;
+  Blue3 a{0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) blue_add(a, f(i));
+  a.big = block_sum(a.big, sh);
+  a.med = block_sum(a.med, sh);
+  a.sml = block_sum(a.sml, sh);
+  if (threadIdx.x == 0) {
+    ws.partials[blockIdx.x] = a.big;
+    ws.partials[RED_BLOCKS + blockIdx.x] = a.med;
+    ws.partials[2 * RED_BLOCKS + blockIdx.x] = a.sml;
+    __threadfence();
+    unsigned t = atomicInc(ws.counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    Blue3 b{0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) {
+      b.big += ((volatile double*)ws.partials)[i];
+      b.med += ((volatile double*)ws.partials)[RED_BLOCKS + i];
+      b.sml += ((volatile double*)ws.partials)[2 * RED_BLOCKS + i];
+    }
+    b.big = block_sum(b.big, sh);
+    b.med = block_sum(b.med, sh);
+    b.sml = block_sum(b.sml, sh);
+    if (threadIdx.x == 0) out[0] = blue_norm(b);
   }
 }
 

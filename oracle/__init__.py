@@ -15,10 +15,50 @@ f64p = C.POINTER(C.c_double)
 i8p = C.POINTER(C.c_int8)
 
 
+_build = "-O3 -march=x86-64-v3 (oracle/liboracle.so, portable build of the Makefile)"
+
+
+def build_flags():
+    """How the loaded library was compiled (the CPU-baseline legs of bench.py report it)."""
+    lib()
+    return _build
+
+
+def _native_path():
+    """ORACLE_NATIVE=1 (set by bench.py's CPU legs): compile the port for THIS host, `gcc -O3 -march=native`
+    (BASELINE.md section 3), into oracle/_native/ (git-ignored).  The portable library stays the fallback: a library
+    built with -march=native on one machine may not run on another, so it is never shipped."""
+    import subprocess
+    import glob
+    if os.environ.get("ORACLE_NATIVE", "0") != "1":
+        return None
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "liboracle_native.so")
+    srcs = sorted(glob.glob(os.path.join(_HERE, "*.c")))
+    deps = srcs + sorted(glob.glob(os.path.join(_HERE, "*.h")))
+    try:
+        stamp = os.path.join(out_dir, "host.txt")
+        host = open("/proc/cpuinfo").read().split("model name", 2)[1].split("\n")[0] if os.path.exists("/proc/cpuinfo") else ""
+        fresh = (os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == host
+                 and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps))
+        if not fresh:
+            os.makedirs(out_dir, exist_ok=True)
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", out] + srcs + ["-lm"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+            open(stamp, "w").write(host)
+        return out
+    except Exception:
+        return None
+
+
 def lib():
-    global _lib
+    global _lib, _build
     if _lib is None:
         path = os.path.join(_HERE, "liboracle.so")
+        native = _native_path()
+        if native is not None:
+            path = native
+            _build = "-O3 -march=native, compiled on this host (oracle/_native/)"
         if not os.path.exists(path):
             raise RuntimeError("oracle/liboracle.so missing: run `make` (or __graft_entry__.build())")
         L = C.CDLL(path)

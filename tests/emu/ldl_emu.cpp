@@ -15,7 +15,7 @@
 
 namespace cb {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 namespace {
 struct Dense {

@@ -65,3 +65,37 @@ def test_settable_infinity_bound():      # presolve.rs:107-114 (host state of th
     assert cb.get_infinity() == 1e21
     cb.default_infinity()
     assert cb.get_infinity() == d == 1e20
+
+
+def test_integration_md_rust_mirrors_match_the_header():
+    """INTEGRATION.md's `#[repr(C)]` mirrors are what a maintainer would paste: field count, order, types and total size
+    must be those of the C structs (round 1 shipped a CldlOpts that was two fields short of cldl_opts)."""
+    import ctypes as C
+    import re
+    import clarabel_rs_b200 as cb
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    rust = {"f64": C.c_double, "i32": C.c_int32, "u32": C.c_uint32, "u64": C.c_uint64, "i64": C.c_int64}
+
+    def mirror(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, text, re.S).group(1)
+        body = re.sub(r"//[^\n]*", "", body)
+        fields = []
+        for decl in body.split(","):
+            decl = decl.strip()
+            if not decl:
+                continue
+            nm, ty = [t.strip() for t in decl.split(":")]
+            arr = re.match(r"\[u8; (\d+)\]", ty)
+            fields.append((nm, C.c_char * int(arr.group(1)) if arr else rust[ty]))
+        return type("M_" + name, (C.Structure,), {"_fields_": fields})
+
+    for rname, cstruct in (("CldlOpts", cb.cldl_opts), ("CldlInfo", cb.cldl_info_t)):
+        m = mirror(rname)
+        assert len(m._fields_) == len(cstruct._fields_), rname
+        assert C.sizeof(m) == C.sizeof(cstruct), (rname, C.sizeof(m), C.sizeof(cstruct))
+        for (_, t1), (_, t2) in zip(m._fields_, cstruct._fields_):
+            assert C.sizeof(t1) == C.sizeof(t2), rname
+    sz = (C.c_uint64 * 4)()
+    cb.lib().cipm_abi_sizes(sz)
+    assert sz[0] == C.sizeof(cb.cldl_opts) and sz[1] == C.sizeof(cb.cldl_info_t)
+    assert "cipm_abi_sizes" in text and "size_of::<CldlOpts>()" in text

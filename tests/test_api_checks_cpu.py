@@ -96,3 +96,47 @@ def test_equilibrate_zero_rows_oracle():      # :89-104
     ipm.solve()
     _, e, _ = ipm.equilibration()
     assert np.all(e == 1.0)
+
+
+def _raw_create(Pp, Pi, Px, Ap, Ai, Ax, n, m):
+    """cipm_create_gp straight through the C ABI (no Python-side sorting / validation): what a Rust or C caller does"""
+    import ctypes as C
+    L = cb._lib2()
+    st = cb.default_settings()
+    o = cb.cldl_opts()
+    L.cldl_default_opts(C.byref(o))
+    u64 = lambda a: np.ascontiguousarray(a, dtype=np.uint64)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    Pp, Pi, Ap, Ai = u64(Pp), u64(Pi), u64(Ap), u64(Ai)
+    Px, Ax, q, b = f64(Px), f64(Ax), np.zeros(n), np.ones(m)
+    ct = np.array([1], dtype=np.int32)
+    cd, z64, zf = u64([m]), u64([0]), f64([0.0])
+    h = C.c_void_p()
+    pu, pd = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    return L.cipm_create_gp(C.byref(h), n, m, Pp.ctypes.data_as(pu), Pi.ctypes.data_as(pu), Px.ctypes.data_as(pd),
+                            q.ctypes.data_as(pd), Ap.ctypes.data_as(pu), Ai.ctypes.data_as(pu), Ax.ctypes.data_as(pd),
+                            b.ctypes.data_as(pd), 1, ct.ctypes.data_as(C.POINTER(C.c_int32)), cd.ctypes.data_as(pu),
+                            zf.ctypes.data_as(pd), z64.ctypes.data_as(pu), zf.ctypes.data_as(pd), C.byref(st), C.byref(o), None)
+
+
+def test_c_abi_rejects_malformed_sparse_input_before_touching_a_device():
+    """CscMatrix::check_format (algebra/csc/core.rs) on the C boundary: an unsorted upper-triangular P column used to be
+    accepted and produced a second structural diagonal entry; out-of-range rows of A wrote out of bounds
+    in the equilibration.  All of these fail with an argument error, and they do so without a GPU."""
+    E_ARG, E_DIM, E_TRIU = -21, -1, -3
+    good_P = ([0, 1, 3], [0, 0, 1], [1.0, 0.1, 1.0])        # 2 x 2 upper triangle, sorted
+    good_A = ([0, 2, 3], [0, 1, 1], [1.0, 1.0, 1.0])        # 2 x 2
+    cases = {
+        "unsorted P column": (([0, 1, 3], [0, 1, 0], [1.0, 1.0, 0.1]), good_A, E_ARG),
+        "duplicate entry in P": (([0, 1, 3], [0, 1, 1], [1.0, 1.0, 0.1]), good_A, E_ARG),
+        "lower-triangular entry in P": (([0, 2, 3], [0, 1, 1], [1.0, 0.1, 1.0]), good_A, E_TRIU),
+        "decreasing colptr of A": (good_P, ([0, 2, 1], [0, 1, 1], [1.0, 1.0, 1.0]), E_ARG),
+        "row of A out of range": (good_P, ([0, 2, 3], [0, 5, 1], [1.0, 1.0, 1.0]), E_DIM),
+        "unsorted A column": (good_P, ([0, 2, 3], [1, 0, 1], [1.0, 1.0, 1.0]), E_ARG),
+        "colptr of P not starting at 0": (([1, 1, 3], [0, 0, 1], [1.0, 0.1, 1.0]), good_A, E_ARG),
+    }
+    for name, (Pm, Am, want) in cases.items():
+        rc = _raw_create(*Pm, *Am, 2, 2)
+        assert rc == want, (name, rc)
+    # the well-formed problem gets past the checks: on this host it stops at "no CUDA device" (or succeeds on a GPU box)
+    assert _raw_create(*good_P, *good_A, 2, 2) in (0, -20)

@@ -69,3 +69,26 @@ def test_products_and_reductions_match_the_oracle_on_random_data():
     assert dev.test_vec(1, big) == np.max(np.abs(big))
     assert abs(dev.test_vec(2, big, w) - np.linalg.norm(big * w)) <= 1e-12 * np.linalg.norm(big * w)
     assert abs(dev.test_vec(3, big, w) - float(big @ w)) <= 1e-10 * np.linalg.norm(big) * np.linalg.norm(w)
+
+
+def test_two_norm_is_overflow_safe_like_stable_norm(handle):
+    """vecmath.rs:206-226: the reference's 2-norm never squares an entry unscaled.  sqrt(sum x^2) would return inf for
+    entries around 1e200 and 0 for entries around 1e-200; the device norms (k_norm2, Blue's three accumulators) must
+    return what the reference's stable_norm returns (here: the oracle's restatement, pinned on vector.rs)."""
+    cases = [[3e200, -4e200, 12e200], [3e-200, 4e-200, -12e-200], [1e200, 1.0, 1e-200], [1e-170, 1e-170, 3.0],
+             [5e153, 5e153], [2e-160] * 7, [1e308, 1e308]]
+    for x in cases:
+        got = handle.test_vec(0, x)
+        xa = np.ascontiguousarray(x, dtype=np.float64)
+        Lo = oracle._ipm_lib()
+        Lo.oipm_test_vec.restype = C.c_double
+        want = Lo.oipm_test_vec(C.c_int(0), xa.ctypes.data_as(C.POINTER(C.c_double)), xa.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(xa.size))
+        assert np.isfinite(got) and got > 0.0, (x, got)
+        assert abs(got - want) <= 4e-16 * want, (x, got, want)
+    # scaled variant and a long vector that mixes all three ranges
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rng.standard_normal(5000) * 1e180, rng.standard_normal(5000), rng.standard_normal(5000) * 1e-180])
+    w = rng.uniform(0.5, 2.0, v.size)
+    ref = np.max(np.abs(v * w)) * np.linalg.norm((v * w) / np.max(np.abs(v * w)))
+    assert abs(handle.test_vec(2, v, w) - ref) <= 1e-13 * ref
+    assert np.isnan(handle.test_vec(0, [1.0, np.nan, 2.0]))

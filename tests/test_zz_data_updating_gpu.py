@@ -102,3 +102,19 @@ def test_fail_on_presolve_enable():      # :311-357
         with pytest.raises(cb.DataUpdateError) as e:
             s.update_data(**kw)
         assert "PresolveIsActive" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_update_with_a_different_sparsity_pattern_is_refused():
+    """CscMatrix::is_equal_sparsity (algebra/csc/core.rs:436-445): a matrix with the same number of nonzeros in other
+    places is an error, not a silent write into the wrong KKT slots."""
+    import scipy.sparse as sp
+    P = sp.csc_matrix(np.array([[4.0, 1.0], [1.0, 2.0]]))
+    A = sp.csc_matrix(np.array([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]))
+    s = cb.CudaSolver(P, np.ones(2), A, np.ones(3), [("nonneg", 3)], settings=cb.default_settings(presolve_enable=0))
+    s.solve()
+    A2 = sp.csc_matrix(np.array([[1.0, 1.0], [0.0, 1.0], [1.0, 0.0]]))      # 4 nonzeros as well, elsewhere
+    with pytest.raises(cb.DataUpdateError):
+        s.update_data(A=A2)
+    s.update_data(A=A * 2.0)
+    assert s.solve()["status"] == "Solved"
