@@ -234,6 +234,12 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
 #pragma unroll
     for (int h = 0; h < NR; h++) sx[h * nr_max + a] = r.xp[h][ri];
   }
+  __shared__ double s0[NR * CB_PB_MAXNS];      // D^-1 y of the pivots, then the solution (written out together at the end)
+  if (tid < ns) {
+    const double di = d.Dinv[f + tid];
+#pragma unroll
+    for (int h = 0; h < NR; h++) s0[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] * di;
+  }
   __syncthreads();
   for (int j = w; j < ns; j += SV_LEAF_NT / 32) {
     const double* __restrict__ col = P + (long long)j * ld + ns;
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
       double t = acc[h];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) st[h * CB_PB_MAXNS + j] = r.xp[h][f + j] * d.Dinv[f + j] - t;
+      if (lane == 0) st[h * CB_PB_MAXNS + j] = s0[h * CB_PB_MAXNS + j] - t;
     }
   }
   __syncthreads();
@@ -272,12 +278,14 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
       double t = acc[h];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) {
-        const double x = st[h * CB_PB_MAXNS + i] + t;
-        r.xp[h][f + i] = x;
-        r.out[h][d.perm[f + i]] = x;
-      }
+      if (lane == 0) s0[h * CB_PB_MAXNS + i] = st[h * CB_PB_MAXNS + i] + t;
     }
+  }
+  __syncthreads();
+  if (tid < ns) {
+    const int pf = d.perm[f + tid];
+#pragma unroll
+    for (int h = 0; h < NR; h++) { const double x = s0[h * CB_PB_MAXNS + tid]; r.xp[h][f + tid] = x; r.out[h][pf] = x; }
   }
 }
 
@@ -364,9 +372,11 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
   double* sy = sw + NR * CB_PB_MAXNS;           // NR * 64: pivot solution
   double* sx = sy + NR * CB_PB_MAXNS;           // NR * SV_MAXROWS: backward, x at the slab's rows
   double* sred = sx + NR * SV_MAXROWS;          // NR * 4 * 64: backward, partial column sums of the four row quarters
-  // the queue is read one task ahead: while a task runs, the next one's index and record are already on their way
-  // (the grab is an atomic + a dependent 96-byte load, ~1.5 us of pure latency per task otherwise).  Holding a task
-  // that is not started yet is safe: dependencies only point to earlier queue positions.
+  // The queue is read one task ahead: the next index and its 96-byte record are fetched by warp 1 while the current
+  // task computes (an atomic + a dependent load, ~1.5 us of pure latency otherwise).  The fetch is issued only AFTER
+  // the current task's dependency wait: a task that is being held back must not hold a second one back with it.
+  // Holding a fetched task for the few microseconds of a compute phase is safe: dependencies point to earlier queue
+  // positions only.
   __shared__ int4 s_rec[2][6];
   __shared__ int s_task[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -377,22 +387,25 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
     const int q0 = s_task[0];
     if (q0 < q.ntask && tid < 6) s_rec[0][tid] = q.tasks[6 * (size_t)(FWD ? q0 : q.ntask - 1 - q0) + tid];
   }
+  __syncthreads();
+#define SV_FETCH_NEXT()                                                                                          \
+  do {                                                                                                           \
+    if (warp == 1) {                                                                                             \
+      int qn = 0;                                                                                                \
+      if (lane == 0) { qn = atomicAdd(&q.qhead[FWD ? 0 : 1], 1); s_task[cur ^ 1] = qn; }                         \
+      qn = __shfl_sync(0xffffffffu, qn, 0);                                                                      \
+      if (qn < q.ntask && lane < 6) s_rec[cur ^ 1][lane] = q.tasks[6 * (size_t)(FWD ? qn : q.ntask - 1 - qn) + lane]; \
+    }                                                                                                            \
+  } while (0)
   for (;;) {
-    __syncthreads();
+    // no barrier here: every path below ends with a barrier that follows all reads of the slab and the vectors, and
+    // what comes after it (thread 0 publishing the finished task) overlaps with the staging of the next one
     const int qi = s_task[cur];
     if (qi >= q.ntask) break;
     const int k = FWD ? qi : q.ntask - 1 - qi;
     unsigned long long* trk = q.trace ? q.trace + 4 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
     if (trk && tid == 0) trk[0] = df_gtime();
-    // next task: index by one thread of warp 1, record by its first lanes (same warp, so no block-wide barrier)
-    if (warp == 1) {
-      int qn = 0;
-      if (lane == 0) { qn = atomicAdd(&q.qhead[FWD ? 0 : 1], 1); s_task[cur ^ 1] = qn; }
-      qn = __shfl_sync(0xffffffffu, qn, 0);
-      if (qn < q.ntask && lane < 6) s_rec[cur ^ 1][lane] = q.tasks[6 * (size_t)(FWD ? qn : q.ntask - 1 - qn) + lane];
-    }
     const SVTask& T = *reinterpret_cast<const SVTask*>(s_rec[cur]);
-    cur ^= 1;
     const int kind = T.kind;
     if (kind == 0) {
       // ---------------- batch of narrow fronts ----------------
@@ -400,6 +413,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       if (FWD) {
         if (tid == 0) { sv_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
         __syncthreads();
+        SV_FETCH_NEXT();
         if (warp < cnt) {
 #pragma unroll
           for (int h = 0; h < NR; h++) { df_fwd_small(d, r.u[h], q.fronts[first + warp], r.xp[h], lane); __syncwarp(); }
@@ -411,6 +425,8 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           if (p >= 0) atomicSub(q.pend + q.front2task[p], 1);
         }
       } else {
+        __syncthreads();
+        SV_FETCH_NEXT();
         if (warp < cnt) {
           const int s = q.fronts[first + warp];
           if (lane == 0) { const int p = q.parent[s]; if (p >= 0) sv_wait_set(q.done + p); __threadfence(); }
@@ -419,14 +435,16 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           for (int h = 0; h < NR; h++) { df_bwd_small(d, s, r.xp[h], r.out[h], lane); __syncwarp(); }
           if (lane == 0) { __threadfence(); atomicExch(q.done + s, 1); }
         }
+        __syncthreads();
       }
       if (trk && tid == 0) trk[2] = df_gtime();
+      cur ^= 1;
       continue;
     }
     // ---------------- wide front: head (pivot block + first rows) or a further slab of rows ----------------
     const int s = T.s, f = T.f, ns = T.ns, nr = T.nr, r0 = T.r0, r1 = T.r1;
     const int ld = ns + nr;
-    const int rows = r1 - r0;                                   // rows of L21 in this slab
+    const int rows = r1 - r0;                                   // rows of L21 in this slab (<= SV_MAXROWS = SV_NT)
     const bool head = kind == 1;
     const int srows = head ? ns + rows : rows;                  // rows of the staged slab
     const int lds = srows | 1;                                  // odd: the transposed reads of the backward sweep spread over the banks
@@ -437,34 +455,61 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
     if (FWD) {
       const int* __restrict__ gp = d.gat_ptr + (f + rp);
       const bool pure = T.pure != 0;
-      // static gather ranges: fetched before the wait
-      int ga0 = 0, ga1 = 0, gb0[2] = {0, 0}, gb1[2] = {0, 0};
+      const int nrt = T.nrt, dep0 = T.dep0, dep1 = T.dep1, dep2 = T.dep2, t_notify = T.notify, t_ptask = T.ptask;
+      const long long cuoff = T.cuoff;
+      const bool rows_late = head && dep2 > dep1;               // the rows' contributions arrive after the pivots' (chain child followed slab by slab)
+      // static gather lists: ranges and the first two source indices of every destination are fetched before the wait
+      int ga0 = 0, ga1 = 0, gai0 = 0, gai1 = 0, gb0 = 0, gb1 = 0, gbi0 = 0, gbi1 = 0;
       if (!pure) {
         if (head && tid < ns) { ga0 = gp[tid]; ga1 = gp[tid + 1]; }
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-          const int a = tid + t * SV_NT;
-          if (a < rows) { gb0[t] = gp[ns + r0 + a]; gb1[t] = gp[ns + r0 + a + 1]; }
-        }
+        if (tid < rows) { gb0 = gp[ns + r0 + tid]; gb1 = gp[ns + r0 + tid + 1]; }
+        if (ga1 > ga0) gai0 = d.gat_src[ga0];
+        if (ga1 > ga0 + 1) gai1 = d.gat_src[ga0 + 1];
+        if (gb1 > gb0) gbi0 = d.gat_src[gb0];
+        if (gb1 > gb0 + 1) gbi1 = d.gat_src[gb0 + 1];
       }
       if (tid == 0) {
         if (head) sv_wait_zero(q.pend + k); else sv_wait_set(q.ydone + s);
-        for (int t = T.dep0; t <= T.dep1; t++) sv_wait_set(q.tdone + t);
+        for (int t = dep0; t <= dep1; t++) sv_wait_set(q.tdone + t);
         __threadfence();
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
+      SV_FETCH_NEXT();
+      auto gather_rows = [&](double* g) {
+        if (tid < rows) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) {
+            double acc = 0.0;
+            if (pure) acc = __ldcg(r.u[h] + cuoff + ns + r0 + tid);
+            else {
+              if (gb1 > gb0) acc += __ldcg(r.u[h] + gbi0);
+              if (gb1 > gb0 + 1) acc += __ldcg(r.u[h] + gbi1);
+              for (int e = gb0 + 2; e < gb1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
+            }
+            g[h] = acc;
+          }
+        }
+      };
+      double g[NR];
+#pragma unroll
+      for (int h = 0; h < NR; h++) g[h] = 0.0;
       if (head) {
         // phase A: y1 = L11^-1 (b1 + children)
         if (tid < ns) {
 #pragma unroll
           for (int h = 0; h < NR; h++) {
             double acc = 0.0;
-            if (pure) acc = __ldcg(r.u[h] + T.cuoff + tid);
-            else for (int e = ga0; e < ga1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
+            if (pure) acc = __ldcg(r.u[h] + cuoff + tid);
+            else {
+              if (ga1 > ga0) acc += __ldcg(r.u[h] + gai0);
+              if (ga1 > ga0 + 1) acc += __ldcg(r.u[h] + gai1);
+              for (int e = ga0 + 2; e < ga1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
+            }
             sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] + acc;
           }
         }
+        if (!rows_late) gather_rows(g);         // issued now, consumed after phase A
         sv_cp_commit_wait();
         __syncthreads();
         if (tid < ns) {
@@ -481,72 +526,68 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         }
         __syncthreads();
         if (tid == 0) {
-          if (T.nrt > 0) { __threadfence(); atomicExch(q.ydone + s, 1); }
-          if (T.dep2 > T.dep1) { for (int t = max(T.dep1 + 1, T.dep0); t <= T.dep2; t++) sv_wait_set(q.tdone + t); __threadfence(); }
+          if (nrt > 0) { __threadfence(); atomicExch(q.ydone + s, 1); }
+          if (rows_late) { for (int t = max(dep1 + 1, dep0); t <= dep2; t++) sv_wait_set(q.tdone + t); __threadfence(); }
         }
-        if (T.dep2 > T.dep1) __syncthreads();
+        if (rows_late) { __syncthreads(); gather_rows(g); }
       } else {
         if (tid < ns) {
 #pragma unroll
           for (int h = 0; h < NR; h++) sy[h * CB_PB_MAXNS + tid] = __ldcg(r.xp[h] + f + tid);
         }
+        gather_rows(g);
         sv_cp_commit_wait();
         __syncthreads();
       }
       // phase B: u[rows] = children - L21 y1
+      if (tid < rows) {
+        double acc[NR];
 #pragma unroll
-      for (int t = 0; t < 2; t++) {
-        const int a = tid + t * SV_NT;
-        if (a < rows) {
-          double g[NR], acc[NR];
+        for (int h = 0; h < NR; h++) acc[h] = 0.0;
+        const double* __restrict__ col = slab + l21 + tid;
+        for (int j = 0; j < ns; j++) {
+          const double l = col[j * lds];
 #pragma unroll
-          for (int h = 0; h < NR; h++) {
-            g[h] = 0.0; acc[h] = 0.0;
-            if (pure) g[h] = __ldcg(r.u[h] + T.cuoff + ns + r0 + a);
-            else for (int e = gb0[t]; e < gb1[t]; e++) g[h] += __ldcg(r.u[h] + d.gat_src[e]);
-          }
-          const double* __restrict__ col = slab + l21 + a;
-          for (int j = 0; j < ns; j++) {
-            const double l = col[j * lds];
-#pragma unroll
-            for (int h = 0; h < NR; h++) acc[h] += l * sy[h * CB_PB_MAXNS + j];
-          }
-#pragma unroll
-          for (int h = 0; h < NR; h++) r.u[h][rp + r0 + a] = g[h] - acc[h];
+          for (int h = 0; h < NR; h++) acc[h] += l * sy[h * CB_PB_MAXNS + j];
         }
+#pragma unroll
+        for (int h = 0; h < NR; h++) r.u[h][rp + r0 + tid] = g[h] - acc[h];
       }
       __syncthreads();
       if (tid == 0) {
         __threadfence();
         atomicExch(q.tdone + k, 1);
-        if (atomicSub(q.fleft + s, 1) == 1 && T.notify && T.ptask >= 0) atomicSub(q.pend + T.ptask, 1);
+        if (atomicSub(q.fleft + s, 1) == 1 && t_notify && t_ptask >= 0) atomicSub(q.pend + t_ptask, 1);
         if (trk) trk[2] = df_gtime();
       }
     } else {
       // ---------------- backward ----------------
       const int* __restrict__ rowsi = d.sn_rows + rp + r0;
-      int ri[2] = {0, 0};
-#pragma unroll
-      for (int t = 0; t < 2; t++) { const int a = tid + t * SV_NT; if (a < rows) ri[t] = rowsi[a]; }   // static: before the wait
+      const int nrt = T.nrt, bowner = T.bowner, bslot = T.bslot;
+      const int ri = tid < rows ? rowsi[tid] : 0;               // static: before the wait
+      const int pf = (head && tid < ns) ? d.perm[f + tid] : 0;
+      const double di = (head && tid < ns) ? d.Dinv[f + tid] : 0.0;
       if (tid == 0) {
-        if (head && T.nrt > 0) sv_wait_zero(q.bleft + s);
-        if (T.bowner >= 0) sv_wait_set(q.done + T.bowner);
+        if (head && nrt > 0) sv_wait_zero(q.bleft + s);
+        if (bowner >= 0) sv_wait_set(q.done + bowner);
         __threadfence();
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
+      SV_FETCH_NEXT();
+      if (tid < rows) {
 #pragma unroll
-      for (int t = 0; t < 2; t++) {
-        const int a = tid + t * SV_NT;
-        if (a < rows) {
-#pragma unroll
-          for (int h = 0; h < NR; h++) sx[h * SV_MAXROWS + a] = __ldcg(r.xp[h] + ri[t]);
-        }
+        for (int h = 0; h < NR; h++) sx[h * SV_MAXROWS + tid] = __ldcg(r.xp[h] + ri);
       }
-      if (head && tid < ns) {
-        const double di = d.Dinv[f + tid];
+      double part[NR];                                          // head: sum of the row tasks' partial column sums (fixed order)
 #pragma unroll
-        for (int h = 0; h < NR; h++) sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] * di;
+      for (int h = 0; h < NR; h++) part[h] = 0.0;
+      if (head && tid < ns) {
+#pragma unroll
+        for (int h = 0; h < NR; h++) {
+          sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] * di;
+          for (int b = 0; b < nrt; b++) part[h] += __ldcg(q.bpart + h * q.bpart_stride + (long long)(bslot + b) * CB_PB_MAXNS + tid);
+        }
       }
       sv_cp_commit_wait();
       __syncthreads();
@@ -573,7 +614,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
           for (int h = 0; h < NR; h++) {
             const double* sr = sred + h * 4 * CB_PB_MAXNS + tid;
-            q.bpart[h * q.bpart_stride + (long long)T.bslot * CB_PB_MAXNS + tid] =
+            q.bpart[h * q.bpart_stride + (long long)bslot * CB_PB_MAXNS + tid] =
                 ((sr[0] + sr[CB_PB_MAXNS]) + sr[2 * CB_PB_MAXNS]) + sr[3 * CB_PB_MAXNS];
           }
         }
@@ -584,9 +625,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
           for (int h = 0; h < NR; h++) {
             const double* sr = sred + h * 4 * CB_PB_MAXNS + tid;
-            double t = sw[h * CB_PB_MAXNS + tid] - (((sr[0] + sr[CB_PB_MAXNS]) + sr[2 * CB_PB_MAXNS]) + sr[3 * CB_PB_MAXNS]);
-            for (int b = 0; b < T.nrt; b++) t -= __ldcg(q.bpart + h * q.bpart_stride + (long long)(T.bslot + b) * CB_PB_MAXNS + tid);
-            sy[h * CB_PB_MAXNS + tid] = t;
+            sy[h * CB_PB_MAXNS + tid] = (sw[h * CB_PB_MAXNS + tid] - (((sr[0] + sr[CB_PB_MAXNS]) + sr[2 * CB_PB_MAXNS]) + sr[3 * CB_PB_MAXNS])) - part[h];
           }
         }
         __syncthreads();
@@ -601,7 +640,6 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
             for (int h = 0; h < NR; h++) x[h] += l * sy[h * CB_PB_MAXNS + j];
           }
-          const int pf = d.perm[f + tid];
 #pragma unroll
           for (int h = 0; h < NR; h++) { r.xp[h][f + tid] = x[h]; r.out[h][pf] = x[h]; }
         }
@@ -609,5 +647,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         if (tid == 0) { __threadfence(); atomicExch(q.done + s, 1); if (trk) trk[2] = df_gtime(); }
       }
     }
+    cur ^= 1;
   }
+#undef SV_FETCH_NEXT
 }
