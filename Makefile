@@ -12,7 +12,7 @@ CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
 CU_OBJS   := $(CU_SRCS:.cu=.o)
 CPP_OBJS  := $(CPP_SRCS:.cpp=.o)
-HDRS      := $(wildcard $(CSRC)/*.h) include/clarabel_b200.h
+HDRS      := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/clarabel_b200.h
 ORACLE_SRCS := $(wildcard oracle/*.c)
 
 all: $(LIB) $(ORACLE)
