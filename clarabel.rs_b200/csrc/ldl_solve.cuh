@@ -173,16 +173,19 @@ __global__ void __launch_bounds__(256) k_leaf_small(LDLDev d, const int* __restr
 // nothing to wait for, nothing to gather; many CTAs per SM hide the latency.  Same arithmetic, in the same order, as a
 // head task of the dataflow kernel would do for the front.
 #define SV_LEAF_NT 128
+#define SV_POLL 64          /* thread of a sweep CTA that polls the dependencies (thread 0 publishes the previous task meanwhile) */
 template <int NR>
 __global__ void __launch_bounds__(SV_LEAF_NT) k_fwd_leafw(LDLDev d, const int* __restrict__ list, int count, SVRhs r) {
   __shared__ double sb[NR * CB_PB_MAXNS], sy[NR * CB_PB_MAXNS];
-  const int s = list[blockIdx.x];
+  for (int it = blockIdx.x; it < count; it += gridDim.x) {
+  const int s = list[it];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
   const int nr = (int)(d.sn_rowptr[s + 1] - rp);
   const int ld = ns + nr, tid = threadIdx.x;
   const double* __restrict__ P = d.L + d.panel_off[s];
+  __syncthreads();            // the previous front's readers of sb / sy are done
   if (tid < ns) {
 #pragma unroll
     for (int h = 0; h < NR; h++) sb[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] + 0.0;
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_fwd_leafw(LDLDev d, const int* _
 #pragma unroll
     for (int h = 0; h < NR; h++) r.u[h][rp + a] = 0.0 - acc[h];
   }
+  }
 }
 // backward: warp w owns the columns j = w, w + 4, ...; lanes run down a column (coalesced), one butterfly per column
 template <int NR>
@@ -221,7 +225,9 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
   extern __shared__ double lw_smem[];
   double* sx = lw_smem;                        // NR * nr_max: x at the front's rows
   double* st = sx + NR * nr_max;               // NR * 64
-  const int s = list[blockIdx.x];
+  __shared__ double s0[NR * CB_PB_MAXNS];      // D^-1 y of the pivots, then the solution (written out together at the end)
+  for (int it = blockIdx.x; it < count; it += gridDim.x) {
+  const int s = list[it];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -229,12 +235,12 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
   const int ld = ns + nr, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const double* __restrict__ P = d.L + d.panel_off[s];
   const int* __restrict__ rows = d.sn_rows + rp;
+  __syncthreads();            // the previous front's readers of the shared vectors are done
   for (int a = tid; a < nr; a += SV_LEAF_NT) {
     const int ri = rows[a];
 #pragma unroll
     for (int h = 0; h < NR; h++) sx[h * nr_max + a] = r.xp[h][ri];
   }
-  __shared__ double s0[NR * CB_PB_MAXNS];      // D^-1 y of the pivots, then the solution (written out together at the end)
   if (tid < ns) {
     const double di = d.Dinv[f + tid];
 #pragma unroll
@@ -286,6 +292,7 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
     const int pf = d.perm[f + tid];
 #pragma unroll
     for (int h = 0; h < NR; h++) { const double x = s0[h * CB_PB_MAXNS + tid]; r.xp[h][f + tid] = x; r.out[h][pf] = x; }
+  }
   }
 }
 
@@ -388,15 +395,21 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
     if (q0 < q.ntask && tid < 6) s_rec[0][tid] = q.tasks[6 * (size_t)(FWD ? q0 : q.ntask - 1 - q0) + tid];
   }
   __syncthreads();
-#define SV_FETCH_NEXT()                                                                                          \
-  do {                                                                                                           \
-    if (warp == 1) {                                                                                             \
-      int qn = 0;                                                                                                \
-      if (lane == 0) { qn = atomicAdd(&q.qhead[FWD ? 0 : 1], 1); s_task[cur ^ 1] = qn; }                         \
-      qn = __shfl_sync(0xffffffffu, qn, 0);                                                                      \
-      if (qn < q.ntask && lane < 6) s_rec[cur ^ 1][lane] = q.tasks[6 * (size_t)(FWD ? qn : q.ntask - 1 - qn) + lane]; \
-    }                                                                                                            \
+  // three steps, spread over the task so that no step waits for the previous one's memory round trip: index (atomic),
+  // record (dependent load), record -> shared memory.  Warp 7 does it: its threads have the least other work.
+  int fq = 0;
+  int4 frec = make_int4(0, 0, 0, 0);
+#define SV_FETCH1() do { if (tid == SV_NT - 32) fq = atomicAdd(&q.qhead[FWD ? 0 : 1], 1); } while (0)
+#define SV_FETCH2()                                                                                     \
+  do {                                                                                                  \
+    if (warp == SV_NT / 32 - 1) {                                                                       \
+      fq = __shfl_sync(0xffffffffu, fq, 0);                                                             \
+      if (lane == 0) s_task[cur ^ 1] = fq;                                                              \
+      if (fq < q.ntask && lane < 6) frec = q.tasks[6 * (size_t)(FWD ? fq : q.ntask - 1 - fq) + lane];   \
+    }                                                                                                   \
   } while (0)
+#define SV_FETCH3() do { if (warp == SV_NT / 32 - 1 && lane < 6 && fq < q.ntask) s_rec[cur ^ 1][lane] = frec; } while (0)
+#define SV_FETCH_NEXT() do { SV_FETCH1(); SV_FETCH2(); SV_FETCH3(); } while (0)
   for (;;) {
     // no barrier here: every path below ends with a barrier that follows all reads of the slab and the vectors, and
     // what comes after it (thread 0 publishing the finished task) overlaps with the staging of the next one
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       // ---------------- batch of narrow fronts ----------------
       const int first = T.s, cnt = T.cnt;
       if (FWD) {
-        if (tid == 0) { sv_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
+        if (tid == SV_POLL) { sv_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
         __syncthreads();
         SV_FETCH_NEXT();
         if (warp < cnt) {
@@ -468,14 +481,14 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         if (gb1 > gb0) gbi0 = d.gat_src[gb0];
         if (gb1 > gb0 + 1) gbi1 = d.gat_src[gb0 + 1];
       }
-      if (tid == 0) {
+      if (tid == SV_POLL) {     // not thread 0: that one may still be publishing the previous task
         if (head) sv_wait_zero(q.pend + k); else sv_wait_set(q.ydone + s);
         for (int t = dep0; t <= dep1; t++) sv_wait_set(q.tdone + t);
         __threadfence();
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
-      SV_FETCH_NEXT();
+      SV_FETCH1();
       auto gather_rows = [&](double* g) {
         if (tid < rows) {
 #pragma unroll
@@ -512,6 +525,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         if (!rows_late) gather_rows(g);         // issued now, consumed after phase A
         sv_cp_commit_wait();
         __syncthreads();
+        if (trk && tid == 0) trk[3] = df_gtime();
         if (tid < ns) {
           double y[NR];
 #pragma unroll
@@ -525,6 +539,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           for (int h = 0; h < NR; h++) { sy[h * CB_PB_MAXNS + tid] = y[h]; r.xp[h][f + tid] = y[h]; }
         }
         __syncthreads();
+        SV_FETCH2();
         if (tid == 0) {
           if (nrt > 0) { __threadfence(); atomicExch(q.ydone + s, 1); }
           if (rows_late) { for (int t = max(dep1 + 1, dep0); t <= dep2; t++) sv_wait_set(q.tdone + t); __threadfence(); }
@@ -538,6 +553,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         gather_rows(g);
         sv_cp_commit_wait();
         __syncthreads();
+        SV_FETCH2();
       }
       // phase B: u[rows] = children - L21 y1
       if (tid < rows) {
@@ -553,11 +569,14 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
         for (int h = 0; h < NR; h++) r.u[h][rp + r0 + tid] = g[h] - acc[h];
       }
+      SV_FETCH3();
       __syncthreads();
       if (tid == 0) {
         __threadfence();
         atomicExch(q.tdone + k, 1);
-        if (atomicSub(q.fleft + s, 1) == 1 && t_notify && t_ptask >= 0) atomicSub(q.pend + t_ptask, 1);
+        // a front that is one task needs no count of its tasks: the parent hears of it at once (no atomic round trip)
+        if (nrt == 0) { if (t_notify && t_ptask >= 0) atomicSub(q.pend + t_ptask, 1); }
+        else if (atomicSub(q.fleft + s, 1) == 1 && t_notify && t_ptask >= 0) atomicSub(q.pend + t_ptask, 1);
         if (trk) trk[2] = df_gtime();
       }
     } else {
@@ -567,14 +586,14 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       const int ri = tid < rows ? rowsi[tid] : 0;               // static: before the wait
       const int pf = (head && tid < ns) ? d.perm[f + tid] : 0;
       const double di = (head && tid < ns) ? d.Dinv[f + tid] : 0.0;
-      if (tid == 0) {
+      if (tid == SV_POLL) {
         if (head && nrt > 0) sv_wait_zero(q.bleft + s);
         if (bowner >= 0) sv_wait_set(q.done + bowner);
         __threadfence();
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
-      SV_FETCH_NEXT();
+      SV_FETCH1();
       if (tid < rows) {
 #pragma unroll
         for (int h = 0; h < NR; h++) sx[h * SV_MAXROWS + tid] = __ldcg(r.xp[h] + ri);
@@ -608,6 +627,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
         for (int h = 0; h < NR; h++) sred[(h * 4 + qd) * CB_PB_MAXNS + j] = acc[h];
       }
+      SV_FETCH2();
       __syncthreads();
       if (!head) {
         if (tid < ns) {
@@ -618,6 +638,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
                 ((sr[0] + sr[CB_PB_MAXNS]) + sr[2 * CB_PB_MAXNS]) + sr[3 * CB_PB_MAXNS];
           }
         }
+        SV_FETCH3();
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicSub(q.bleft + s, 1); if (trk) trk[2] = df_gtime(); }
       } else {
@@ -643,6 +664,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
           for (int h = 0; h < NR; h++) { r.xp[h][f + tid] = x[h]; r.out[h][pf] = x[h]; }
         }
+        SV_FETCH3();
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicExch(q.done + s, 1); if (trk) trk[2] = df_gtime(); }
       }
@@ -650,4 +672,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
     cur ^= 1;
   }
 #undef SV_FETCH_NEXT
+#undef SV_FETCH1
+#undef SV_FETCH2
+#undef SV_FETCH3
 }

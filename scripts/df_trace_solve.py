@@ -31,6 +31,7 @@ for di, name in ((0, "forward"), (1, "backward")):
     t = tr[di]
     t0 = t[:, 0].min()
     grab, ready, end = [(t[:, i] - t0) / 1e3 for i in (0, 1, 2)]
+    landed = (t[:, 3] - t0) / 1e3
     rd = np.where(t[:, 1] > 0, ready, grab)
     print(f"== {name}: span {end.max():.1f} us, tasks {nt}")
     for k in (0, 1, 2):
@@ -45,7 +46,8 @@ for di, name in ((0, "forward"), (1, "backward")):
             ent = (ns + r1 - r0) * ns
             qq = q & (ent >= lo) & (ent < hi)
             if qq.any():
-                print(f"     head slabs {lo:5d}-{hi if hi < 1 << 29 else 99999:5d}: n={qq.sum():6d} busy mean {np.mean(end[qq]-rd[qq]):6.2f} us wait mean {np.mean(rd[qq]-grab[qq]):6.2f} us")
+                extra = f" | slab landed {np.mean(landed[qq]-rd[qq]):6.2f} us after ready" if di == 0 else ""
+                print(f"     head slabs {lo:5d}-{hi if hi < 1 << 29 else 99999:5d}: n={qq.sum():6d} busy mean {np.mean(end[qq]-rd[qq]):6.2f} us wait mean {np.mean(rd[qq]-grab[qq]):6.2f} us{extra}")
     nb = 20
     edges = np.linspace(0, end.max(), nb + 1)
     print("  slice(us) busyCTAs waitingCTAs")
