@@ -1270,7 +1270,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   nnzA = Ap[n];
   CK(cudaMalloc((void**)&dev.vals, (size_t)(nnzA ? nnzA : 1) * sizeof(double)));
   CK(cudaMemcpy(dev.vals, Ax, (size_t)nnzA * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMalloc((void**)&dev.L, (size_t)(S.L_alloc ? S.L_alloc : 1) * sizeof(double)));
+  CK(cudaMalloc((void**)&dev.L, ((size_t)(S.L_alloc ? S.L_alloc : 1) + 8) * sizeof(double)));   // + slack: a bulk copy of the last panel is rounded up to 16 bytes
   CK(cudaMalloc((void**)&dev.U, (size_t)(S.upd_total ? S.upd_total : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&dev.D, (size_t)n * sizeof(double)));
   CK(cudaMalloc((void**)&dev.Dinv, (size_t)n * sizeof(double)));
@@ -1551,21 +1551,23 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     const size_t extra2 = (size_t)2 * (2 * CB_PB_MAXNS + SV_MAXROWS + 4 * CB_PB_MAXNS) * sizeof(double);   // NR = 2 vectors
     {
       const size_t per_cta = ((size_t)227 * 1024) / solve_minb - 1024 - 64;
-      sv_cap = (int)((per_cta - extra2) / sizeof(double));
+      sv_cap = (int)((per_cta - extra2) / sizeof(double)) - 2;
+      sv_cap &= ~1;
       sv_cap = std::min(sv_cap, 16384);
-      if (const char* e = std::getenv("CB_SOLVE_CAP")) sv_cap = std::max(CB_PB_MAXNS * (CB_PB_MAXNS + 9), std::atoi(e));
+      if (const char* e = std::getenv("CB_SOLVE_CAP")) sv_cap = std::max(CB_PB_MAXNS * (CB_PB_MAXNS + 9), std::atoi(e)) & ~1;
     }
     const int cap = sv_cap;
     auto wide = [&](int s) { return S.sn_first[s + 1] - S.sn_first[s] > CB_SOLVE_SMALL_NS; };
     auto has_kids = [&](int s) { return S.child_ptr[s + 1] > S.child_ptr[s]; };
     // head rows / rows per row task of a wide front
     auto split = [&](int ns, int nr, int& rh, int& nrt, int& chunk) {
-      int hmax = cap / ns;                       // staged rows with lds = rows | 1
-      if ((hmax | 1) * ns > cap) hmax--;
-      rh = std::min(std::min(nr, SV_MAXROWS), std::max(0, hmax - ns));
-      int rmax = cap / ns;
-      if ((rmax | 1) * ns > cap) rmax--;
-      rmax = std::min(rmax, SV_MAXROWS);
+      // a panel that fits goes to shared memory whole (one bulk copy, leading dimension ld); otherwise the head takes
+      // the pivot block + as many rows as fit and row tasks take the rest (leading dimension sv_lds(rows, ld) <= rows + 3,
+      // one more double for the alignment offset)
+      const int rmax_all = (cap - 1) / ns - 3;
+      if (nr <= SV_MAXROWS && (long long)ns * (ns + nr) + 1 <= cap) { rh = nr; nrt = 0; chunk = 0; return; }
+      rh = std::min(std::min(nr, SV_MAXROWS), std::max(0, rmax_all - ns));
+      const int rmax = std::max(1, std::min(rmax_all, SV_MAXROWS));
       const int rest = nr - rh;
       nrt = rest > 0 ? (rest + rmax - 1) / rmax : 0;
       chunk = nrt ? (rest + nrt - 1) / nrt : 0;
@@ -1683,7 +1685,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
       sv_wide_runs.push_back(sv_nwide); sv_wide_runs.push_back(0);
     }
     sv_nleaf1 = (int)leaf1.size(); sv_nleafn = (int)leafn.size(); sv_nleafw = (int)leafw.size();
-    sv_leafw_grid = std::max(1, std::min(sv_nleafw, nsm * 12));      // CTAs loop over the fronts: no per-front block launch, no ragged tail
+    sv_leafw_grid = sv_nleafw;      // one CTA per front (a loop over fronts inside fewer CTAs was slower: 312 vs 189 us forward on C4)
     int* t1 = nullptr;
     if ((rc = upload(&t1, wlist))) return rc; d_sv_wide = t1;
     if ((rc = upload(&t1, leaf1))) return rc; d_sv_leaf1 = t1;
@@ -1716,7 +1718,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     sv.ntask = nt;
     // launch geometry: dynamic shared memory = slab + vectors for one or two right-hand sides
     for (int nr2 = 1; nr2 <= 2; nr2++)
-      sv_smem[nr2 - 1] = ((size_t)cap + (size_t)nr2 * (2 * CB_PB_MAXNS + SV_MAXROWS + 4 * CB_PB_MAXNS)) * sizeof(double);
+      sv_smem[nr2 - 1] = ((size_t)cap + 2 + (size_t)nr2 * (2 * CB_PB_MAXNS + SV_MAXROWS + 4 * CB_PB_MAXNS)) * sizeof(double);
     if ((rc = sv_configure())) return rc;
     int occ = sv_occupancy();
     if (occ < 1) return CLDL_E_CUDA;
@@ -2064,13 +2066,13 @@ void LDLObject::sv_leaves(bool fwd, int nrhs, const SVRhs& r) {
   if (fwd) {
     if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_fwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_fwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
     if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
-    if (sv_nleafw) { g_launches++; if (nrhs == 1) k_fwd_leafw<1><<<sv_leafw_grid, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); else k_fwd_leafw<2><<<sv_leafw_grid, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); }
+    if (sv_nleafw) { g_launches++; if (nrhs == 1) k_fwd_leafw<1><<<sv_nleafw, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); else k_fwd_leafw<2><<<sv_nleafw, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); }
   } else {
     if (sv_nleafw) {
       g_launches++;
       const size_t sm = (size_t)nrhs * (sv_leafw_nrmax + CB_PB_MAXNS) * sizeof(double);
-      if (nrhs == 1) k_bwd_leafw<1><<<sv_leafw_grid, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
-      else k_bwd_leafw<2><<<sv_leafw_grid, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
+      if (nrhs == 1) k_bwd_leafw<1><<<sv_nleafw, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
+      else k_bwd_leafw<2><<<sv_nleafw, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
     }
     if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
     if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_bwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_bwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }

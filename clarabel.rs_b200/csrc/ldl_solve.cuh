@@ -32,6 +32,43 @@ __device__ __forceinline__ void sv_cp8(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 #endif
 }
+__device__ __forceinline__ void sv_cp16(double* smem_dst, const double* gsrc) {   // both 16-byte aligned; bypasses L1
+#ifdef CB_EMU
+  smem_dst[0] = gsrc[0]; smem_dst[1] = gsrc[1];
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+// ---- TMA bulk copy (cp.async.bulk, completion on an mbarrier): a panel that fits the slab is ONE contiguous block of
+// global memory, so one thread hands the whole transfer to the copy engine -- no per-element instructions, no
+// registers, no L1.  dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void sv_mbar_init(unsigned long long* mbar) {
+#ifndef CB_EMU
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void sv_bulk_load(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* mbar) {
+#ifdef CB_EMU
+  for (unsigned i = 0; i < bytes / 8; i++) smem_dst[i] = gsrc[i];
+#else
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of the slab are ordered before the engine's writes
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(mb) : "memory");
+#endif
+}
+__device__ __forceinline__ void sv_mbar_wait(unsigned long long* mbar, unsigned phase) {
+#ifndef CB_EMU
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+  unsigned ok = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(mb), "r"(phase) : "memory");
+  } while (!ok);
+#endif
+}
 __device__ __forceinline__ void sv_cp_commit_wait() {
 #ifndef CB_EMU
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -177,8 +214,8 @@ __global__ void __launch_bounds__(256) k_leaf_small(LDLDev d, const int* __restr
 template <int NR>
 __global__ void __launch_bounds__(SV_LEAF_NT) k_fwd_leafw(LDLDev d, const int* __restrict__ list, int count, SVRhs r) {
   __shared__ double sb[NR * CB_PB_MAXNS], sy[NR * CB_PB_MAXNS];
-  for (int it = blockIdx.x; it < count; it += gridDim.x) {
-  const int s = list[it];
+  {
+  const int s = list[blockIdx.x];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -226,8 +263,8 @@ __global__ void __launch_bounds__(SV_LEAF_NT) k_bwd_leafw(LDLDev d, const int* _
   double* sx = lw_smem;                        // NR * nr_max: x at the front's rows
   double* st = sx + NR * nr_max;               // NR * 64
   __shared__ double s0[NR * CB_PB_MAXNS];      // D^-1 y of the pivots, then the solution (written out together at the end)
-  for (int it = blockIdx.x; it < count; it += gridDim.x) {
-  const int s = list[it];
+  {
+  const int s = list[blockIdx.x];
   const int f = d.sn_first[s];
   const int ns = d.sn_first[s + 1] - f;
   const long long rp = d.sn_rowptr[s];
@@ -361,21 +398,28 @@ __device__ __forceinline__ void sv_wait_set(volatile int* p) {
   while (*p == 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
 }
 
-// slab -> shared memory, column-major with leading dimension lds: columns [0, ns), panel rows [row0, row0 + rows)
-__device__ __forceinline__ void sv_stage(double* slab, const double* __restrict__ P, int ld, int ns, int row0, int rows, int lds) {
+// slab -> shared memory, column-major with leading dimension lds: columns [0, ns), `rows` panel rows starting at src0.
+// lds has the parity of ld and the slab starts at an element whose parity is that of src0's offset in d.L (see
+// sv_lds / boff at the call site), so source and destination of every column are 16-byte aligned at the same
+// elements: the body of a column goes in 16-byte cp.async.cg pieces (L2 only), a leading / trailing single in 8 bytes.
+__device__ __forceinline__ void sv_stage(double* sl, int boff, const double* __restrict__ src0, int ld, int ns, int rows, int lds) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int j = warp; j < ns; j += SV_NT / 32) {
-    const double* __restrict__ src = P + (long long)j * ld + row0;
-    double* dst = slab + j * lds;
-    for (int i = lane; i < rows; i += 32) sv_cp8(dst + i, src + i);
+    const double* __restrict__ src = src0 + (long long)j * ld;
+    double* dst = sl + j * lds;
+    const int i0 = (boff + j * lds) & 1;                 // first element of the column that is 16-byte aligned
+    if (i0 && lane == 0 && rows > 0) sv_cp8(dst, src);
+    const int npairs = (rows - i0) >> 1;
+    for (int t = lane; t < npairs; t += 32) sv_cp16(dst + i0 + 2 * t, src + i0 + 2 * t);
+    if (((rows - i0) & 1) && rows > i0 && lane == 31) sv_cp8(dst + rows - 1, src + rows - 1);
   }
 }
 
 template <bool FWD, int NR, int MINB>
 __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRhs r, int cap) {
-  extern __shared__ double sv_smem[];
-  double* slab = sv_smem;                       // cap doubles
-  double* sw = slab + cap;                      // NR * 64: gathered right-hand side of the pivot block / D^-1 y - sums
+  extern __shared__ __align__(16) double sv_smem[];
+  double* slab = sv_smem;                       // cap doubles (+ 2 of slack: a bulk copy is rounded up to 16 bytes)
+  double* sw = slab + cap + 2;                  // NR * 64: gathered right-hand side of the pivot block / D^-1 y - sums
   double* sy = sw + NR * CB_PB_MAXNS;           // NR * 64: pivot solution
   double* sx = sy + NR * CB_PB_MAXNS;           // NR * SV_MAXROWS: backward, x at the slab's rows
   double* sred = sx + NR * SV_MAXROWS;          // NR * 4 * 64: backward, partial column sums of the four row quarters
@@ -386,8 +430,11 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
   // positions only.
   __shared__ int4 s_rec[2][6];
   __shared__ int s_task[2];
+  __shared__ __align__(8) unsigned long long s_mbar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int cur = 0;
+  unsigned mph = 0;                              // phase of the bulk-copy barrier: flips with every bulk copy (all threads see the same tasks)
+  if (tid == 0) sv_mbar_init(&s_mbar);
   if (tid == 0) s_task[0] = atomicAdd(&q.qhead[FWD ? 0 : 1], 1);
   __syncthreads();
   {
@@ -460,10 +507,18 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
     const int rows = r1 - r0;                                   // rows of L21 in this slab (<= SV_MAXROWS = SV_NT)
     const bool head = kind == 1;
     const int srows = head ? ns + rows : rows;                  // rows of the staged slab
-    const int lds = srows | 1;                                  // odd: the transposed reads of the backward sweep spread over the banks
     const int l21 = head ? ns : 0;                              // where the L21 rows start inside the slab
     const double* __restrict__ P = d.L + T.poff;
-    sv_stage(slab, P, ld, ns, head ? 0 : ns + r0, srows, lds);  // in flight while the task waits below
+    // in flight while the task waits below: the whole panel in one TMA bulk copy when it fits (it is contiguous),
+    // otherwise the slab's piece of every column with 16-byte cp.async
+    const bool contig = head && rows == nr;
+    const int row0 = head ? 0 : ns + r0;
+    const int lds = contig ? ld : sv_lds(srows, ld);
+    const int boff = contig ? 0 : (int)((T.poff + row0) & 1);
+    double* const sl = slab + boff;
+    if (contig) { if (tid == SV_POLL) sv_bulk_load(slab, P, (unsigned)(((ns * ld + 1) & ~1) * 8), &s_mbar); }
+    else sv_stage(sl, boff, P + row0, ld, ns, srows, lds);
+#define SV_SLAB_WAIT() do { if (contig) { sv_mbar_wait(&s_mbar, mph); mph ^= 1; } else sv_cp_commit_wait(); } while (0)
     const long long rp = T.rp;
     if (FWD) {
       const int* __restrict__ gp = d.gat_ptr + (f + rp);
@@ -523,7 +578,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           }
         }
         if (!rows_late) gather_rows(g);         // issued now, consumed after phase A
-        sv_cp_commit_wait();
+        SV_SLAB_WAIT();
         __syncthreads();
         if (trk && tid == 0) trk[3] = df_gtime();
         if (tid < ns) {
@@ -531,7 +586,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
           for (int h = 0; h < NR; h++) y[h] = sw[h * CB_PB_MAXNS + tid];
           for (int j = 0; j < tid; j++) {
-            const double l = slab[j * lds + tid];
+            const double l = sl[j * lds + tid];
 #pragma unroll
             for (int h = 0; h < NR; h++) y[h] += l * sw[h * CB_PB_MAXNS + j];
           }
@@ -551,7 +606,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           for (int h = 0; h < NR; h++) sy[h * CB_PB_MAXNS + tid] = __ldcg(r.xp[h] + f + tid);
         }
         gather_rows(g);
-        sv_cp_commit_wait();
+        SV_SLAB_WAIT();
         __syncthreads();
         SV_FETCH2();
       }
@@ -560,7 +615,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         double acc[NR];
 #pragma unroll
         for (int h = 0; h < NR; h++) acc[h] = 0.0;
-        const double* __restrict__ col = slab + l21 + tid;
+        const double* __restrict__ col = sl + l21 + tid;
         for (int j = 0; j < ns; j++) {
           const double l = col[j * lds];
 #pragma unroll
@@ -608,7 +663,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           for (int b = 0; b < nrt; b++) part[h] += __ldcg(q.bpart + h * q.bpart_stride + (long long)(bslot + b) * CB_PB_MAXNS + tid);
         }
       }
-      sv_cp_commit_wait();
+      SV_SLAB_WAIT();
       __syncthreads();
       {
         // column sums over the slab's rows: thread (j, quarter) walks rows quarter, quarter + 4, ...
@@ -617,7 +672,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
 #pragma unroll
         for (int h = 0; h < NR; h++) acc[h] = 0.0;
         if (j < ns) {
-          const double* __restrict__ col = slab + j * lds + l21;
+          const double* __restrict__ col = sl + j * lds + l21;
           for (int a = qd; a < rows; a += 4) {
             const double l = col[a];
 #pragma unroll
@@ -655,7 +710,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           double x[NR];
 #pragma unroll
           for (int h = 0; h < NR; h++) x[h] = sy[h * CB_PB_MAXNS + tid];
-          const double* __restrict__ col = slab + tid * lds;
+          const double* __restrict__ col = sl + tid * lds;
           for (int j = tid + 1; j < ns; j++) {
             const double l = col[j];
 #pragma unroll
@@ -669,6 +724,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         if (tid == 0) { __threadfence(); atomicExch(q.done + s, 1); if (trk) trk[2] = df_gtime(); }
       }
     }
+#undef SV_SLAB_WAIT
     cur ^= 1;
   }
 #undef SV_FETCH_NEXT

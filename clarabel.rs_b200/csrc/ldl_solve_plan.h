@@ -8,6 +8,15 @@ namespace cb {
 #define SV_NT 256
 #define SV_MAXROWS 256      /* rows of L21 in one slab (bounds the staged x / the per-thread row count) */
 
+// leading dimension of a staged slab of `srows` rows cut out of a panel with leading dimension ld: the parity of ld (so
+// that source and destination are 16-byte aligned at the same elements of every column) and, when even, not a multiple
+// of 4 (the transposed reads of the backward sweep would pile up on a few shared-memory banks)
+__host__ __device__ inline int sv_lds(int srows, int ld) {
+  int L = srows + ((srows ^ ld) & 1);
+  if (!(L & 1) && !(L & 3)) L += 2;
+  return L;
+}
+
 struct SVTask {             // 96 bytes = 6 x int4, built on the host (LDLObject::init)
   int kind, s, cnt, f;      // kind 0: narrow batch (s = first index into fronts[], cnt fronts); 1 head; 2 rows
   int ns, nr, r0, r1;       // slab = rows [r0, r1) of L21 (head: r0 = 0, r1 = rh, plus the pivot block)
