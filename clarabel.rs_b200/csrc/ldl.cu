@@ -135,6 +135,53 @@ __global__ void __launch_bounds__(NT) k_factor_level(LDLDev d, int task_base, in
   }
 }
 
+// Single-column leaves (no children: tree level 0; on KKT matrices these are the constraint rows eliminated first,
+// 5e5 of them on config C4): ONE THREAD per front instead of one CTA.  Same arithmetic as the fused kernel above does
+// for such a front: d = a_jj (sign test, regularisation), l = a_:j / d, U = 0 - l (l d)^T on the lower triangle.
+// The inertia / regularisation counters are aggregated per warp before they touch global memory.
+__global__ void __launch_bounds__(256) k_factor_leaf1(LDLDev d, int task_base, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = i < count;
+  int pos = 0, reg = 0;
+  if (on) {
+    const int s = d.level_tasks[task_base + i];
+    const int f = d.sn_first[s];
+    const long long rp = d.sn_rowptr[s];
+    const int nr = (int)(d.sn_rowptr[s + 1] - rp);
+    const int ld = 1 + nr;
+    double* __restrict__ P = d.L + d.panel_off[s];
+    double* __restrict__ U = d.U + d.upd_off[s];
+    for (int a = 0; a < ld; a++) P[a] = 0.0;
+    for (long long e = d.asm_ptr[s]; e < d.asm_ptr[s + 1]; e++) P[d.asm_dst[e]] = d.vals[d.asm_src[e]];
+    double dj = P[0];
+    if (d.reg_enable) {
+      const double sg = (double)d.dsigns[f];
+      if (dj * sg < d.reg_eps) { dj = d.reg_delta * sg; reg = 1; }
+    }
+    if (dj == 0.0) atomicExch(&d.status[ST_ZEROPIV], 1);
+    pos = dj > 0.0 ? 1 : 0;
+    const double inv = 1.0 / dj;
+    if (!isfinite(inv)) atomicExch(&d.status[ST_NONFINITE], 1);
+    d.D[f] = dj;
+    d.Dinv[f] = inv;
+    P[0] = dj;
+    for (int a = 1; a < ld; a++) P[a] *= inv;
+    for (int b = 0; b < nr; b++) {
+      const double t = P[1 + b] * dj;
+      for (int a = b; a < nr; a++) {
+        double acc = 0.0;
+        acc += P[1 + a] * t;
+        U[(long long)b * nr + a] = 0.0 - acc;
+      }
+    }
+  }
+  const unsigned mp = __ballot_sync(0xffffffffu, pos != 0), mr = __ballot_sync(0xffffffffu, reg != 0);
+  if ((threadIdx.x & 31) == 0) {
+    if (mp) atomicAdd(&d.status[ST_POSINERTIA], __popc(mp));
+    if (mr) atomicAdd(&d.status[ST_REGCOUNT], __popc(mr));
+  }
+}
+
 // ------------------------------------------------------------------------
 // Big fronts: two kernels per level.
 //   k_panel_big   : one CTA per front.  Assembles the ns panel columns (original
@@ -1358,11 +1405,12 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   CK(cudaFuncSetAttribute(k_update_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tiles));
   const long long classes[3] = {1024, 5632, cap_big};  // 8 KB, 44 KB, ~225 KB panels
   plan.clear();
+  const bool leaf1_kernel = std::getenv("CB_FACTOR_LEAF1") == nullptr || std::atoi(std::getenv("CB_FACTOR_LEAF1")) != 0;
   std::vector<int> big_tasks;
   std::vector<int4> tiles;
   for (int l = 0; l < S.nlevels; l++) {
     int b = S.level_ptr[l], e = S.level_ptr[l + 1];
-    std::vector<int> order[4];
+    std::vector<int> order[4], order1;
     const size_t big0 = big_tasks.size(), tile0 = tiles.size();
     std::vector<int> not_mine;       // sharded: fronts of other ranks are parked at the end of the level's range
     for (int t = b; t < e; t++) {
@@ -1377,11 +1425,18 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
           for (int tj = 0; tj <= ti; tj++) tiles.push_back(make_int4(s, ti, tj, 0));
         continue;
       }
+      if (l == 0 && ns == 1 && leaf1_kernel) { order1.push_back(s); continue; }
       const long long p = (ns + nr) * ns;
       int c = p <= classes[0] ? 0 : p <= classes[1] ? 1 : p <= classes[2] ? 2 : 3;
       order[c].push_back(s);
     }
     int pos = b;
+    if (!order1.empty()) {      // single-column leaves: one thread each (k_factor_leaf1)
+      LaunchSeg seg;
+      seg.kind = 3; seg.level = l; seg.base = pos; seg.count = (int)order1.size(); seg.smem_doubles = 0; seg.threads = 256;
+      plan.push_back(seg);
+      for (int s : order1) S.level_tasks[pos++] = s;
+    }
     for (int c = 3; c >= 0; c--) {
       if (order[c].empty()) continue;
       LaunchSeg seg;
@@ -1952,9 +2007,10 @@ int LDLObject::refactor_async() {
     CK(cudaMemcpyAsync(d_dff_cnt, d_dff_init, dff_nsup4 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemsetAsync(dff.qhead, 0, sizeof(int), stream));
     for (const LaunchSeg& g : plan) {
-      if (g.level != 0 || g.kind != 0) continue;
+      if (g.level != 0 || (g.kind != 0 && g.kind != 3)) continue;
       g_launches++;
-      if (g.threads == 64)
+      if (g.kind == 3) k_factor_leaf1<<<(g.count + 255) / 256, 256, 0, stream>>>(dev, g.base, g.count);
+      else if (g.threads == 64)
         k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
       else
         k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
@@ -1969,7 +2025,9 @@ int LDLObject::refactor_async() {
   }
   g_launches += plan.size();
   for (const LaunchSeg& g : plan) {
-    if (g.kind == 1)
+    if (g.kind == 3)
+      k_factor_leaf1<<<(g.count + 255) / 256, 256, 0, stream>>>(dev, g.base, g.count);
+    else if (g.kind == 1)
       k_panel_big<<<g.count, PB_NT, (size_t)g.smem_doubles * 8, stream>>>(dev, d_big_tasks + g.base, g.base);
     else if (g.kind == 2)
       k_update_tiles<<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, d_tiles + g.base, g.base);
@@ -2139,9 +2197,10 @@ int LDLObject::refactor_phase_async(int phase) {
     CK(cudaMemcpyAsync(d_dff_cnt, d_dff_init, dff_nsup4 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemsetAsync(dff.qhead, 0, sizeof(int), stream));
     for (const LaunchSeg& g : plan) {
-      if (g.level != 0 || g.kind != 0 || g.count == 0) continue;
+      if (g.level != 0 || (g.kind != 0 && g.kind != 3) || g.count == 0) continue;
       g_launches++;
-      if (g.threads == 64)
+      if (g.kind == 3) k_factor_leaf1<<<(g.count + 255) / 256, 256, 0, stream>>>(dev, g.base, g.count);
+      else if (g.threads == 64)
         k_factor_level<64><<<g.count, 64, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);
       else
         k_factor_level<256><<<g.count, 256, (size_t)g.smem_doubles * 8, stream>>>(dev, g.base, g.smem_doubles);

@@ -389,13 +389,49 @@ __global__ void __launch_bounds__(64) k_invert_pivots(LDLDev d, const int* __res
 }
 
 // ---- the dataflow sweep ----
-__device__ __forceinline__ void sv_wait_zero(volatile int* p) {
-  unsigned ns = 20;
-  while (*p > 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
+// Flags and counters between CTAs.  Publishing: all threads store their results, __syncthreads, then ONE thread issues
+// a release operation at device scope (st.release / red.release: the ordering travels with the operation, the thread
+// does not stall on a fence and is free for the next task at once).  Consuming: one thread polls with ld.acquire,
+// __syncthreads, then everybody reads (ld.global.cg: L1 is not coherent).
+__device__ __forceinline__ int sv_ld_acquire(const int* p) {
+#ifdef CB_EMU
+  return *(volatile const int*)p;
+#else
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
 }
-__device__ __forceinline__ void sv_wait_set(volatile int* p) {
+__device__ __forceinline__ void sv_set_release(int* p) {          // *p = 1
+#ifdef CB_EMU
+  __threadfence(); atomicExch(p, 1);
+#else
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(1) : "memory");
+#endif
+}
+__device__ __forceinline__ void sv_dec_release(int* p) {          // *p -= 1, result not needed
+#ifdef CB_EMU
+  __threadfence(); atomicSub(p, 1);
+#else
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(-1) : "memory");
+#endif
+}
+__device__ __forceinline__ int sv_dec_acq_rel(int* p) {           // returns the value before the decrement
+#ifdef CB_EMU
+  __threadfence(); return atomicSub(p, 1);
+#else
+  int v;
+  asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "r"(-1) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void sv_wait_zero(const int* p) {
   unsigned ns = 20;
-  while (*p == 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
+  while (sv_ld_acquire(p) > 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
+}
+__device__ __forceinline__ void sv_wait_set(const int* p) {
+  unsigned ns = 20;
+  while (sv_ld_acquire(p) == 0) { __nanosleep(ns); if (ns < 320) ns <<= 1; }
 }
 
 // slab -> shared memory, column-major with leading dimension lds: columns [0, ns), `rows` panel rows starting at src0.
@@ -471,7 +507,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       // ---------------- batch of narrow fronts ----------------
       const int first = T.s, cnt = T.cnt;
       if (FWD) {
-        if (tid == SV_POLL) { sv_wait_zero(q.pend + k); __threadfence(); if (trk) trk[1] = df_gtime(); }
+        if (tid == SV_POLL) { sv_wait_zero(q.pend + k); if (trk) trk[1] = df_gtime(); }
         __syncthreads();
         SV_FETCH_NEXT();
         if (warp < cnt) {
@@ -480,20 +516,19 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         }
         __syncthreads();
         if (tid < cnt) {
-          __threadfence();
           const int p = q.parent[q.fronts[first + tid]];
-          if (p >= 0) atomicSub(q.pend + q.front2task[p], 1);
+          if (p >= 0) sv_dec_release(q.pend + q.front2task[p]);
         }
       } else {
         __syncthreads();
         SV_FETCH_NEXT();
         if (warp < cnt) {
           const int s = q.fronts[first + warp];
-          if (lane == 0) { const int p = q.parent[s]; if (p >= 0) sv_wait_set(q.done + p); __threadfence(); }
+          if (lane == 0) { const int p = q.parent[s]; if (p >= 0) sv_wait_set(q.done + p); }
           __syncwarp();
 #pragma unroll
           for (int h = 0; h < NR; h++) { df_bwd_small(d, s, r.xp[h], r.out[h], lane); __syncwarp(); }
-          if (lane == 0) { __threadfence(); atomicExch(q.done + s, 1); }
+          if (lane == 0) sv_set_release(q.done + s);
         }
         __syncthreads();
       }
@@ -539,7 +574,6 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       if (tid == SV_POLL) {     // not thread 0: that one may still be publishing the previous task
         if (head) sv_wait_zero(q.pend + k); else sv_wait_set(q.ydone + s);
         for (int t = dep0; t <= dep1; t++) sv_wait_set(q.tdone + t);
-        __threadfence();
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
@@ -596,8 +630,8 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         __syncthreads();
         SV_FETCH2();
         if (tid == 0) {
-          if (nrt > 0) { __threadfence(); atomicExch(q.ydone + s, 1); }
-          if (rows_late) { for (int t = max(dep1 + 1, dep0); t <= dep2; t++) sv_wait_set(q.tdone + t); __threadfence(); }
+          if (nrt > 0) sv_set_release(q.ydone + s);
+          if (rows_late) { for (int t = max(dep1 + 1, dep0); t <= dep2; t++) sv_wait_set(q.tdone + t); }
         }
         if (rows_late) { __syncthreads(); gather_rows(g); }
       } else {
@@ -627,11 +661,10 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       SV_FETCH3();
       __syncthreads();
       if (tid == 0) {
-        __threadfence();
-        atomicExch(q.tdone + k, 1);
+        sv_set_release(q.tdone + k);
         // a front that is one task needs no count of its tasks: the parent hears of it at once (no atomic round trip)
-        if (nrt == 0) { if (t_notify && t_ptask >= 0) atomicSub(q.pend + t_ptask, 1); }
-        else if (atomicSub(q.fleft + s, 1) == 1 && t_notify && t_ptask >= 0) atomicSub(q.pend + t_ptask, 1);
+        if (nrt == 0) { if (t_notify && t_ptask >= 0) sv_dec_release(q.pend + t_ptask); }
+        else if (sv_dec_acq_rel(q.fleft + s) == 1 && t_notify && t_ptask >= 0) sv_dec_release(q.pend + t_ptask);
         if (trk) trk[2] = df_gtime();
       }
     } else {
@@ -644,7 +677,6 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       if (tid == SV_POLL) {
         if (head && nrt > 0) sv_wait_zero(q.bleft + s);
         if (bowner >= 0) sv_wait_set(q.done + bowner);
-        __threadfence();
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
@@ -695,7 +727,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         }
         SV_FETCH3();
         __syncthreads();
-        if (tid == 0) { __threadfence(); atomicSub(q.bleft + s, 1); if (trk) trk[2] = df_gtime(); }
+        if (tid == 0) { sv_dec_release(q.bleft + s); if (trk) trk[2] = df_gtime(); }
       } else {
         if (tid < ns) {
 #pragma unroll
@@ -721,7 +753,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         }
         SV_FETCH3();
         __syncthreads();
-        if (tid == 0) { __threadfence(); atomicExch(q.done + s, 1); if (trk) trk[2] = df_gtime(); }
+        if (tid == 0) { sv_set_release(q.done + s); if (trk) trk[2] = df_gtime(); }
       }
     }
 #undef SV_SLAB_WAIT
