@@ -24,7 +24,7 @@ $(CSRC)/%.o: $(CSRC)/%.cpp $(HDRS)
 	$(CXX) -O3 -std=c++17 -fPIC -Wall -pthread -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(CPP_OBJS)
-	$(NVCC) -shared $(GENCODE) -o $@ $^ -lcudart -lpthread
+	$(NVCC) -shared $(GENCODE) -o $@ $^ -lcudart -lpthread -ldl
 
 $(ORACLE): $(ORACLE_SRCS) $(wildcard oracle/*.h)
 	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS) -lm

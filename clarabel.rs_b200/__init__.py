@@ -553,6 +553,47 @@ class TorchDistTransport:
             return -1
 
 
+def loaded_nccl_path():
+    """Path of the libnccl this process has mapped (torch's bundled one once torch.distributed runs on NCCL), or None."""
+    try:
+        for line in open("/proc/self/maps"):
+            if "libnccl" in line and ".so" in line:
+                return line.split()[-1]
+    except OSError:
+        pass
+    return None
+
+
+def nccl_direct_setup(set_fn, handle, nranks, rank, device):
+    """Give a sharded handle its own NCCL communicator (cldl_set_nccl / cipm_set_nccl), so that its all-gathers are
+    stream-ordered calls issued by the library -- no Python callback, no host synchronisation per exchange.  Rank 0 draws
+    the unique id, `torch.distributed` (already initialised by the launcher) broadcasts it.  Returns False (and leaves
+    the handle to a callback transport) when the job does not run on NCCL or CB_SHARD_TRANSPORT=torch asks for the
+    callback path."""
+    import torch
+    import torch.distributed as dist
+    if os.environ.get("CB_SHARD_TRANSPORT", "nccl") == "torch" or os.environ.get("CLARABEL_EMU") == "1":
+        return False
+    if not (dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"):
+        return False
+    L = lib()
+    idt = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", device))
+    dist.all_reduce(idt)                              # makes sure NCCL itself is up (and its library mapped) on every rank
+    path = loaded_nccl_path()
+    pb = path.encode() if path else None
+    idb = (C.c_ubyte * 128)()
+    if rank == 0:
+        L.cldl_nccl_unique_id.argtypes = [C.c_char_p, C.POINTER(C.c_ubyte)]
+        _check(L.cldl_nccl_unique_id(pb, idb), "cldl_nccl_unique_id")
+        idt = torch.tensor(list(idb), dtype=torch.uint8, device=torch.device("cuda", device))
+    dist.broadcast(idt, src=0)
+    torch.cuda.synchronize(device)
+    idb = (C.c_ubyte * 128)(*[int(v) for v in idt.cpu().tolist()])
+    set_fn.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int]
+    _check(set_fn(handle, pb, idb, int(nranks), int(rank)), "set_nccl")
+    return True
+
+
 class ShardedLDLRank:
     """One rank of a sharded factorisation in a `torch.distributed` job (one process per GPU; NCCL over NVLink, or
     gloo on host buffers in the emulated build of the test-suite).  The exchanges between the phases are all-gathers of
@@ -568,6 +609,9 @@ class ShardedLDLRank:
                                     shard_rank=self.rank, **kw)
         self._L = self.solver._L
         self._counts = [[int(self._L.cldl_shard_count(self.solver._h, w, r)) for r in range(self.nranks)] for w in range(3)]
+        # on NCCL the library issues the all-gathers itself, stream-ordered (cldl_set_nccl); otherwise (gloo in the CPU
+        # tests, CB_SHARD_TRANSPORT=torch) this class moves the packed buffers through torch.distributed
+        self.nccl_direct = nccl_direct_setup(self._L.cldl_set_nccl, self.solver._h, self.nranks, self.rank, device)
 
     def _tensor(self, buf):
         import torch
@@ -593,6 +637,9 @@ class ShardedLDLRank:
 
     def refactor(self):
         L, h = self._L, self.solver._h
+        if self.nccl_direct:
+            _check(L.cldl_refactor_dev(h), "refactor")
+            return bool(_check(L.cldl_sync_status(h), "sync_status"))
         _check(L.cldl_shard_refactor_phase_dev(h, 0), "refactor phase 0")
         self._exchange(0)
         _check(L.cldl_shard_refactor_phase_dev(h, 1), "refactor phase 1")
@@ -601,6 +648,10 @@ class ShardedLDLRank:
     def solve(self, b):
         L, h = self._L, self.solver._h
         bb, x = _DevBuf(self.n, self.device, host=b), _DevBuf(self.n, self.device)
+        if self.nccl_direct:
+            _check(L.cldl_solve_dev(h, x.ptr, bb.ptr), "solve")
+            _check(L.cldl_sync_status(h), "sync_status")
+            return x.numpy()[:self.n]
         _check(L.cldl_shard_solve_phase_dev(h, x.ptr, bb.ptr, 0), "solve phase 0")
         self._exchange(1)
         _check(L.cldl_shard_solve_phase_dev(h, x.ptr, bb.ptr, 1), "solve phase 1")
@@ -842,8 +893,10 @@ class CudaSolver:
         if shard is not None:
             # every rank runs the same interior-point iterations on identical data; the factorisation and the
             # triangular solves are split and meet through this all-gather
-            self._transport = transport if transport is not None else TorchDistTransport(device)
-            _check(L.cipm_set_transport(h, self._transport.fn, None), "cipm_set_transport")
+            self.nccl_direct = transport is None and nccl_direct_setup(L.cipm_set_nccl, h, shard[0], shard[1], device)
+            if not self.nccl_direct:
+                self._transport = transport if transport is not None else TorchDistTransport(device)
+                _check(L.cipm_set_transport(h, self._transport.fn, None), "cipm_set_transport")
 
     def test_spmv(self, which, y, x, a, b):
         """kernel-level check: which = 0  a P x + b y, 1  a A x + b y, 2  a A' x + b y on the handle's (equilibrated) data"""

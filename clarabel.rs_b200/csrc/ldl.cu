@@ -17,6 +17,7 @@
 // order, panel scaling, Schur update.  No atomics on floating point data:
 // every sum has a fixed order, so refactor/solve are bit-reproducible run to run.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -33,6 +34,41 @@
 namespace cb {
 
 std::atomic<unsigned long long> g_launches{0};
+
+// ---- NCCL on the handle's own stream -------------------------------------------------------------------------
+// The all-gathers between the phases are stream-ordered NCCL calls: pack kernel -> ncclAllGather -> unpack kernels on
+// `stream`, no host synchronisation in between.  The library is NOT linked against NCCL: the process that drives the
+// ranks (one per GPU, torch.distributed) already has a libnccl mapped, and two different NCCL builds in one process
+// do not mix -- so the binding passes the path of the one that is loaded and the five entry points are taken from it
+// with dlsym.  Only these five, with their long-stable signatures, are used (no nccl.h: its version may differ).
+typedef struct ncclComm* cb_ncclComm_t;
+typedef struct { char internal[128]; } cb_ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(cb_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(cb_ncclComm_t*, int, cb_ncclUniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, cb_ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(cb_ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api(const char* libpath) {
+  static NcclApi api;
+  static bool tried = false;
+  if (api.lib) return &api;
+  if (tried && !libpath) return nullptr;
+  tried = true;
+  void* h = dlopen(libpath && *libpath ? libpath : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { std::fprintf(stderr, "[clarabel_b200] dlopen(%s) failed: %s\n", libpath ? libpath : "libnccl.so.2", dlerror()); return nullptr; }
+  api.GetUniqueId = (int (*)(cb_ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(cb_ncclComm_t*, int, cb_ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, cb_ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+  api.CommDestroy = (int (*)(cb_ncclComm_t))dlsym(h, "ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) return nullptr;
+  api.lib = h;
+  return &api;
+}
+
 
 // ------------------------------------------------------------------------
 // kernels
@@ -1992,6 +2028,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   cb_tmark("ldl: solve plan");
   if (sharded()) {
     d_shard_xidx.assign(shard_nranks, nullptr);
+    for (int w = 0; w < 2; w++) { d_shard_segs[w].assign(shard_nranks, nullptr); shard_nsegs[w].assign(shard_nranks, 0); }
     for (int g = 0; g < shard_nranks; g++) { int* t1 = nullptr; if ((rc = upload(&t1, shard_xidx[g]))) return rc; d_shard_xidx[g] = t1; }
   }
   factored = false;
@@ -2000,8 +2037,10 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
 
 void LDLObject::release() {
   cudaSetDevice(device);
+  for (auto& w : d_shard_segs) for (auto& p : w) if (p) { cudaFree(p); p = nullptr; }
   for (int* p : d_shard_xidx) if (p) cudaFree(p);
   d_shard_xidx.clear();
+  if (nccl_comm) { if (NcclApi* a = nccl_api(nullptr)) a->CommDestroy((cb_ncclComm_t)nccl_comm); nccl_comm = nullptr; }
   if (d_xsend) { cudaFree(d_xsend); d_xsend = nullptr; }
   if (d_xrecv) { cudaFree(d_xrecv); d_xrecv = nullptr; }
   xbuf_cap = 0;
@@ -2018,7 +2057,7 @@ void LDLObject::release() {
 }
 
 int LDLObject::refactor_async() {
-  if (sharded()) return transport ? refactor_sharded() : CLDL_E_ARG;   // without a transport: the phase entry points
+  if (sharded()) return has_transport() ? refactor_sharded() : CLDL_E_ARG;   // without a transport: the phase entry points
   CK(cudaSetDevice(device));
   CK(cudaMemsetAsync(dev.status, 0, ST_COUNT * sizeof(int), stream));
   if (factor_dataflow) {
@@ -2164,7 +2203,7 @@ int LDLObject::sv_reset() {
 int LDLObject::solve_async(double* d_x, const double* d_b, double* d_x1, const double* d_b1) {
   const int nrhs = d_x1 ? 2 : 1;
   if (sharded()) {
-    if (!transport) return CLDL_E_ARG;
+    if (!has_transport()) return CLDL_E_ARG;
     int rc = solve_sharded(d_x, d_b);
     if (rc || nrhs == 1) return rc;
     return solve_sharded(d_x1, d_b1);
@@ -2272,6 +2311,20 @@ int LDLObject::solve_phase_async(double* d_x, const double* d_b, int phase) {
   return CLDL_OK;
 }
 
+int LDLObject::set_nccl(const char* libpath, const unsigned char* id128, int nranks, int rank) {
+  if (!sharded() || nranks != shard_nranks || rank != shard_rank) return CLDL_E_ARG;
+  NcclApi* a = nccl_api(libpath);
+  if (!a) return CLDL_E_CUDA;
+  CK(cudaSetDevice(device));
+  cb_ncclUniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  cb_ncclComm_t c = nullptr;
+  const int r = a->CommInitRank(&c, nranks, id, rank);
+  if (r != 0) { std::fprintf(stderr, "[clarabel_b200] ncclCommInitRank: %s\n", a->GetErrorString ? a->GetErrorString(r) : "error"); return CLDL_E_CUDA; }
+  nccl_comm = c;
+  return CLDL_OK;
+}
+
 // padded all-gather of one kind of contribution through the installed transport
 int LDLObject::exchange(int what, double* d_x) {
   uint64_t cnt = 1;
@@ -2285,8 +2338,15 @@ int LDLObject::exchange(int what, double* d_x) {
   }
   int rc = shard_pack(what, d_xsend, d_x);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(stream));
-  if (transport(transport_ctx, d_xsend, d_xrecv, cnt) != 0) return CLDL_E_CUDA;
+  if (nccl_comm) {      // stream-ordered: the unpack kernels below simply follow the collective on `stream`
+    NcclApi* a = nccl_api(nullptr);
+    const int r = a->AllGather(d_xsend, d_xrecv, (size_t)cnt, /* ncclFloat64 */ 8, (cb_ncclComm_t)nccl_comm, stream);
+    if (r != 0) { std::fprintf(stderr, "[clarabel_b200] ncclAllGather: %s\n", a->GetErrorString ? a->GetErrorString(r) : "error"); return CLDL_E_CUDA; }
+    n_collectives++;
+  } else {
+    CK(cudaStreamSynchronize(stream));
+    if (transport(transport_ctx, d_xsend, d_xrecv, cnt) != 0) return CLDL_E_CUDA;
+  }
   for (int r = 0; r < shard_nranks; r++)
     if (r != shard_rank && (rc = shard_unpack(what, r, d_xrecv + (size_t)r * cnt, d_x))) return rc;
   return CLDL_OK;
@@ -2315,6 +2375,34 @@ uint64_t LDLObject::shard_count(int what, int rank) const {
   }
   return t;
 }
+// a list of contiguous segments copied by one launch (one CTA per segment): the cut roots' update matrices / vectors
+// between the arena and the packed exchange buffer (64 separate cudaMemcpyAsync per exchange on C4 otherwise)
+__global__ void k_copy_segs(const long long* __restrict__ seg, double* __restrict__ arena, double* __restrict__ buf, int to_buf) {
+  const long long a = seg[3 * blockIdx.x], b = seg[3 * blockIdx.x + 1], len = seg[3 * blockIdx.x + 2];
+  if (to_buf) for (long long i = threadIdx.x; i < len; i += blockDim.x) buf[b + i] = arena[a + i];
+  else for (long long i = threadIdx.x; i < len; i += blockDim.x) arena[a + i] = buf[b + i];
+}
+int LDLObject::shard_seglist(int what, int rank, const long long** d_out, int* nseg) {
+  auto& slot = d_shard_segs[what][rank];
+  if (!slot) {
+    std::vector<long long> h;
+    long long off = 0;
+    for (int c : shard_cut[rank]) {
+      const long long nr = S.sn_rowptr[c + 1] - S.sn_rowptr[c];
+      const long long len = what == 0 ? nr * nr : nr;
+      if (len) { h.push_back(what == 0 ? (long long)S.upd_off[c] : (long long)S.sn_rowptr[c]); h.push_back(off); h.push_back(len); }
+      off += len;
+    }
+    shard_nsegs[what][rank] = (int)(h.size() / 3);
+    if (h.empty()) h.assign(3, 0);
+    long long* dp = nullptr;
+    CK(cudaMalloc((void**)&dp, h.size() * sizeof(long long)));
+    CK(cudaMemcpy(dp, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    slot = dp;
+  }
+  *d_out = slot; *nseg = shard_nsegs[what][rank];
+  return CLDL_OK;
+}
 // my contribution -> d_buf (contiguous, in the order of shard_cut[rank] / shard_xidx[rank])
 int LDLObject::shard_pack(int what, double* d_buf, const double* d_x) {
   if (!sharded()) return CLDL_E_ARG;
@@ -2324,14 +2412,11 @@ int LDLObject::shard_pack(int what, double* d_buf, const double* d_x) {
     if (cnt) { g_launches++; k_gather_idx<<<(cnt + 255) / 256, 256, 0, stream>>>(cnt, d_shard_xidx[shard_rank], d_x, d_buf); }
     return CLDL_OK;
   }
-  size_t off = 0;
-  for (int c : shard_cut[shard_rank]) {
-    const size_t nr = (size_t)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
-    const size_t len = what == 0 ? nr * nr : nr;
-    const double* src = what == 0 ? dev.U + S.upd_off[c] : dev.u + S.sn_rowptr[c];
-    if (len) CK(cudaMemcpyAsync(d_buf + off, src, len * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-    off += len;
-  }
+  const long long* segs = nullptr;
+  int nseg = 0;
+  int rc = shard_seglist(what, shard_rank, &segs, &nseg);
+  if (rc) return rc;
+  if (nseg) { g_launches++; k_copy_segs<<<nseg, 256, 0, stream>>>(segs, what == 0 ? dev.U : dev.u, d_buf, 1); }
   return CLDL_OK;
 }
 // rank `rank`'s contribution (as packed there) -> this rank's arena / update vectors / x
@@ -2344,14 +2429,11 @@ int LDLObject::shard_unpack(int what, int rank, const double* d_buf, double* d_x
     if (cnt) { g_launches++; k_scatter_idx<<<(cnt + 255) / 256, 256, 0, stream>>>(cnt, d_shard_xidx[rank], d_buf, d_x); }
     return CLDL_OK;
   }
-  size_t off = 0;
-  for (int c : shard_cut[rank]) {
-    const size_t nr = (size_t)(S.sn_rowptr[c + 1] - S.sn_rowptr[c]);
-    const size_t len = what == 0 ? nr * nr : nr;
-    double* dst = what == 0 ? dev.U + S.upd_off[c] : dev.u + S.sn_rowptr[c];
-    if (len) CK(cudaMemcpyAsync(dst, d_buf + off, len * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-    off += len;
-  }
+  const long long* segs = nullptr;
+  int nseg = 0;
+  int rc = shard_seglist(what, rank, &segs, &nseg);
+  if (rc) return rc;
+  if (nseg) { g_launches++; k_copy_segs<<<nseg, 256, 0, stream>>>(segs, what == 0 ? dev.U : dev.u, const_cast<double*>(d_buf), 0); }
   return CLDL_OK;
 }
 
@@ -2569,6 +2651,17 @@ int cldl_shard_solve_phase_dev(cldl_t* h, double* d_x, const double* d_b, int ph
 uint64_t cldl_shard_count(const cldl_t* h, int what, int rank) { return h ? h->obj.shard_count(what, rank) : 0; }
 int cldl_shard_pack_dev(cldl_t* h, int what, double* d_buf, const double* d_x) { return h ? h->obj.shard_pack(what, d_buf, d_x) : CLDL_E_ARG; }
 int cldl_shard_unpack_dev(cldl_t* h, int what, int rank, const double* d_buf, double* d_x) { return h ? h->obj.shard_unpack(what, rank, d_buf, d_x) : CLDL_E_ARG; }
+int cldl_nccl_unique_id(const char* libpath, unsigned char* id128) {
+  cb::NcclApi* a = cb::nccl_api(libpath);
+  if (!a || !id128) return CLDL_E_CUDA;
+  cb::cb_ncclUniqueId id;
+  if (a->GetUniqueId(&id) != 0) return CLDL_E_CUDA;
+  std::memcpy(id128, id.internal, 128);
+  return CLDL_OK;
+}
+int cldl_set_nccl(cldl_t* h, const char* libpath, const unsigned char* id128, int nranks, int rank) {
+  return h ? h->obj.set_nccl(libpath, id128, nranks, rank) : CLDL_E_ARG;
+}
 int cldl_set_transport(cldl_t* h, cldl_allgather_fn fn, void* ctx) {
   if (!h) return CLDL_E_ARG;
   h->obj.transport = fn; h->obj.transport_ctx = ctx;

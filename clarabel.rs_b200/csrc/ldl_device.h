@@ -132,6 +132,9 @@ class LDLObject {
   std::vector<std::vector<int>> shard_cut;   // per rank: its cut roots (fronts whose parent is in the top part)
   std::vector<std::vector<int>> shard_xidx;  // per rank: caller-order indices of the x entries it computes
   std::vector<int*> d_shard_xidx;            // the same lists on the device
+  std::vector<long long*> d_shard_segs[2];   // per what (0 update matrices, 1 update vectors) and rank: (arena offset, buffer offset, length) of its cut roots
+  std::vector<int> shard_nsegs[2];
+  int shard_seglist(int what, int rank, const long long** d_out, int* nseg);
   int dff_ntask_owned = 0;               // tasks of the owned phase (they come first in the queue)
   int h_phase_start[2] = {0, 0};         // pinned-lifetime host copies of the queue heads the top phases start from
   uint64_t shard_count_owned[2] = {0, 0};    // regularize_count / positive_inertia of the owned phase
@@ -146,6 +149,10 @@ class LDLObject {
   int shard_unpack(int what, int rank, const double* d_buf, double* d_x);
   // transport (all-gather between ranks) and the self-driven sharded refactor / solve built on it
   cldl_allgather_fn transport = nullptr;
+  void* nccl_comm = nullptr;             // own NCCL communicator: exchanges are stream-ordered (set_nccl)
+  unsigned long long n_collectives = 0;  // NCCL all-gathers issued by this handle
+  bool has_transport() const { return transport != nullptr || nccl_comm != nullptr; }
+  int set_nccl(const char* libpath, const unsigned char* id128, int nranks, int rank);
   void* transport_ctx = nullptr;
   double *d_xsend = nullptr, *d_xrecv = nullptr;
   size_t xbuf_cap = 0;

@@ -1442,6 +1442,10 @@ int cipm_update_settings(cipm_t* h, const cipm_settings* s) {
   return CLDL_OK;
 }
 
+int cipm_set_nccl(cipm_t* h, const char* libpath, const unsigned char* id128, int nranks, int rank) {
+  return h ? h->ipm.kkt.ldl.set_nccl(libpath, id128, nranks, rank) : CLDL_E_ARG;
+}
+uint64_t cipm_collective_count(const cipm_t* h) { return h ? h->ipm.kkt.ldl.n_collectives : 0; }
 int cipm_set_transport(cipm_t* h, cldl_allgather_fn fn, void* ctx) {
   if (!h) return CLDL_E_ARG;
   h->ipm.kkt.ldl.transport = fn; h->ipm.kkt.ldl.transport_ctx = ctx;

@@ -150,6 +150,13 @@ int cldl_shard_counts(const cldl_t *h, uint64_t *out4);
  * point iterations on identical data and only the factorisation / triangular solves are split. */
 typedef int (*cldl_allgather_fn)(void *ctx, const double *d_send, double *d_recv, uint64_t count);
 int cldl_set_transport(cldl_t *h, cldl_allgather_fn fn, void *ctx);
+/* The same exchanges as stream-ordered NCCL all-gathers issued by the library itself on the handle's stream (no host
+ * synchronisation between pack, collective and unpack).  The library is not linked against NCCL: `libpath` names the
+ * libnccl.so.2 the calling process has loaded already (two NCCL builds in one process do not mix; NULL = the loader's
+ * default).  Rank 0 draws the 128-byte unique id and the binding broadcasts it; cldl_set_nccl is collective (it
+ * calls ncclCommInitRank).  Takes precedence over a callback transport. */
+int cldl_nccl_unique_id(const char *libpath, unsigned char *id128);
+int cldl_set_nccl(cldl_t *h, const char *libpath, const unsigned char *id128, int nranks, int rank);
 int cldl_copy_dev(void *d_dst, const void *d_src, uint64_t bytes);   /* device-to-device copy, for transports in bindings */
 
 /* timing helper for benches: runs `reps` refactors (or solves) back to back
@@ -257,6 +264,8 @@ int cipm_create_gp(cipm_t **out, uint64_t n, uint64_t m, const uint64_t *P_colpt
                    const uint64_t *kkt_perm_or_null);
 /* installs the all-gather of a sharded factorisation (cldl_opts.shard_nranks > 1 in ldl_opts) on the solver's LDL */
 int cipm_set_transport(cipm_t *h, cldl_allgather_fn fn, void *ctx);
+int cipm_set_nccl(cipm_t *h, const char *libpath, const unsigned char *id128, int nranks, int rank);
+uint64_t cipm_collective_count(const cipm_t *h);      /* NCCL all-gathers the handle has issued so far */
 /* Solver::update_settings (core/solver.rs:207-211): new settings for the next cipm_solve; CLDL_E_ARG when a field that
  * only acts at construction differs (equilibration parameters, presolve_enable: settings.rs:307-335). */
 int cipm_update_settings(cipm_t *h, const cipm_settings *settings);

@@ -135,10 +135,12 @@ int LDLObject::solve_async(double* d_x, const double* d_b, double* d_x1, const d
   return CLDL_OK;
 }
 
+int LDLObject::set_nccl(const char*, const unsigned char*, int, int) { return CLDL_E_ARG; }
 int LDLObject::refactor_phase_async(int) { return CLDL_E_ARG; }
 int LDLObject::solve_phase_async(double*, const double*, int) { return CLDL_E_ARG; }
 uint64_t LDLObject::shard_count(int, int) const { return 0; }
 int LDLObject::shard_pack(int, double*, const double*) { return CLDL_E_ARG; }
+int LDLObject::shard_seglist(int, int, const long long**, int*) { return CLDL_E_ARG; }
 int LDLObject::shard_unpack(int, int, const double*, double*) { return CLDL_E_ARG; }
 int LDLObject::ensure_tmp(size_t) { return 0; }
 int LDLObject::stage_index(const uint64_t*, uint64_t) { return 0; }
