@@ -1420,24 +1420,6 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     if ((rc = upload(&t1, child_nb))) return rc; dev.child_nb = t1;
     if ((rc = upload(&t1, gptr))) return rc; dev.gat_ptr = t1;
     if ((rc = upload(&t1, gsrc))) return rc; dev.gat_src = t1;
-    {
-      // the same lists in a fixed-width form for the wide fronts of the solves: the first two sources of every
-      // destination side by side (-1: none), so that a task reaches its children's values through ONE index load
-      // whose address it knows from its record (and can prefetch); a destination with more than two sources marks
-      // the second slot with -2 and falls back to the CSR above for the rest
-      const size_t nd = gptr.size() - 1;
-      std::vector<int2> g2(nd ? nd : 1, make_int2(-1, -1));
-      for (size_t i = 0; i < nd; i++) {
-        const int a = gptr[i], b = gptr[i + 1];
-        if (b > a) g2[i].x = gsrc[a];
-        if (b > a + 1) g2[i].y = gsrc[a + 1];
-        if (b > a + 2) g2[i].y = -2;
-      }
-      int2* t2g = nullptr;
-      CK(cudaMalloc((void**)&t2g, g2.size() * sizeof(int2)));
-      CK(cudaMemcpy(t2g, g2.data(), g2.size() * sizeof(int2), cudaMemcpyHostToDevice));
-      dev.gat2 = t2g;
-    }
     int2* t2 = nullptr;
     CK(cudaMalloc((void**)&t2, (size_t)(S.nsup ? S.nsup : 1) * sizeof(int2)));
     CK(cudaMemcpy(t2, child_tr.data(), (size_t)S.nsup * sizeof(int2), cudaMemcpyHostToDevice));
@@ -1835,8 +1817,8 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     if (const char* e = std::getenv("CB_DF_GRID")) df_grid = std::max(1, std::atoi(e));
     use_dataflow = true;
     if (std::getenv("CB_DF_TRACE_SOLVE") && nt > 0) {
-      CK(cudaMalloc((void**)&sv.trace, (size_t)nt * 16 * sizeof(unsigned long long)));
-      CK(cudaMemset(sv.trace, 0, (size_t)nt * 16 * sizeof(unsigned long long)));
+      CK(cudaMalloc((void**)&sv.trace, (size_t)nt * 8 * sizeof(unsigned long long)));
+      CK(cudaMemset(sv.trace, 0, (size_t)nt * 8 * sizeof(unsigned long long)));
       h_sv_tasks.assign((const int*)tk.data(), (const int*)tk.data() + (size_t)nt * 24);
     }
     if (std::getenv("CB_TIMING") != nullptr) std::fprintf(stderr, "[cb timing]     solve plan: %d tasks (%d leaf columns, %d narrow leaves, %d wide leaves, %d wide fronts, %d row slabs), slab %d doubles, %d CTAs\n",
@@ -2049,7 +2031,7 @@ void LDLObject::release() {
   fr(dev.rel); fr(dev.panel_off); fr(dev.upd_off); fr(dev.asm_ptr); fr(dev.asm_src);
   fr(dev.asm_dst); fr(dev.level_tasks); fr(dev.perm); fr(dev.dsigns); fr(dev.vals); fr(dev.L);
   fr(dev.U); fr(dev.D); fr(dev.Dinv); fr(dev.u); fr(dev.status); fr(d_xp); fr(d_bx);
-  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(sv.tasks); fr(sv.fronts); fr(sv.front2task); fr(sv.parent); fr(sv.bpart); fr(sv.trace); fr(d_sv_cnt); fr(d_sv_init); fr(d_sv_wide); fr(d_sv_leaf1); fr(d_sv_leafn); fr(d_sv_leafw); fr(d_xp2); fr(d_u2); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.gat2); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
+  fr(d_tmp_idx); fr(d_tmp_val); fr(d_tmp_sgn); fr(d_big_tasks); fr(d_tiles); fr(sv.tasks); fr(sv.fronts); fr(sv.front2task); fr(sv.parent); fr(sv.bpart); fr(sv.trace); fr(d_sv_cnt); fr(d_sv_init); fr(d_sv_wide); fr(d_sv_leaf1); fr(d_sv_leafn); fr(d_sv_leafw); fr(d_xp2); fr(d_u2); fr(dff.tasks); fr(dff.desc); fr(d_dff_init); fr(d_dff_cnt); fr(dff.qhead); fr(dff.parent); fr(dff.big_pos); fr(dff.tile_base); fr(dff.trace); fr(dev.child_nb); fr(dev.child_trange); fr(dev.gat_ptr); fr(dev.gat_src); fr(dev.child_tptr); fr(dev.child_tptr_off); fr(dev.sc_panel_ptr); fr(dev.sc_panel_src); fr(dev.sc_panel_dst); fr(dev.sc_tile_ptr); fr(dev.sc_tile_src); fr(dev.sc_tile_dst); fr(dev.child_small);
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -2587,7 +2569,7 @@ int cldl_solve(cldl_t* h, double* x, const double* b) {
   if (cudaStreamSynchronize(o.stream) != cudaSuccess) return CLDL_E_CUDA;
   if (o.sv.trace) {   // diagnostic: CB_DF_TRACE_SOLVE=<file> dumps the last solve's task timeline (scripts/df_trace_solve.py)
     const long long nt = o.sv.ntask;
-    std::vector<unsigned long long> tr((size_t)nt * 16);
+    std::vector<unsigned long long> tr((size_t)nt * 8);
     cudaMemcpy(tr.data(), o.sv.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (FILE* fp = std::fopen(std::getenv("CB_DF_TRACE_SOLVE"), "wb")) {
       std::fwrite(&nt, sizeof(nt), 1, fp);

@@ -44,7 +44,6 @@ struct LDLDev {
   const int *sc_tile_ptr = nullptr, *sc_tile_src = nullptr, *sc_tile_dst = nullptr;     // per update tile
   const int* gat_ptr = nullptr;       // solves: per front slot, CSR of contributing child update-vector entries
   const int* gat_src = nullptr;
-  const int2* gat2 = nullptr;         // solves, wide fronts: first two sources per destination (-1 none; .y == -2: more, see gat_ptr)
   const int* perm = nullptr;
   const signed char* dsigns = nullptr;  // permuted order
   double* vals = nullptr;               // KKT values, caller's CSC order

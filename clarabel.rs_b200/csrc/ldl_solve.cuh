@@ -69,11 +69,6 @@ __device__ __forceinline__ void sv_mbar_wait(unsigned long long* mbar, unsigned 
   } while (!ok);
 #endif
 }
-__device__ __forceinline__ void sv_prefetch_l2(const void* p) {
-#ifndef CB_EMU
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
 __device__ __forceinline__ void sv_cp_commit_wait() {
 #ifndef CB_EMU
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -496,28 +491,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       if (fq < q.ntask && lane < 6) frec = q.tasks[6 * (size_t)(FWD ? fq : q.ntask - 1 - fq) + lane];   \
     }                                                                                                   \
   } while (0)
-#define SV_FETCH3()                                                                                                   \
-  do {                                                                                                                \
-    if (warp == SV_NT / 32 - 1) {                                                                                     \
-      if (lane < 6 && fq < q.ntask) s_rec[cur ^ 1][lane] = frec;                                                      \
-      /* the next task's static index data -> L2: its gather pairs (forward) / row indices (backward) */             \
-      const int nk = __shfl_sync(0xffffffffu, frec.x, 0), nf = __shfl_sync(0xffffffffu, frec.w, 0);                   \
-      const int nns = __shfl_sync(0xffffffffu, frec.x, 1), nr0 = __shfl_sync(0xffffffffu, frec.z, 1), nr1 = __shfl_sync(0xffffffffu, frec.w, 1); \
-      const unsigned rlo = (unsigned)__shfl_sync(0xffffffffu, frec.z, 2), rhi = (unsigned)__shfl_sync(0xffffffffu, frec.w, 2);                    \
-      if (fq < q.ntask && nk != 0) {                                                                                  \
-        const long long nrp = (long long)(((unsigned long long)rhi << 32) | rlo);                                     \
-        if (FWD) {                                                                                                    \
-          const char* b0 = (const char*)(d.gat2 + (nf + nrp) + (nk == 1 ? 0 : nns + nr0));                            \
-          const int nbytes = (nk == 1 ? nns + (nr1 - nr0) : (nr1 - nr0)) * 8;                                          \
-          for (int o = lane * 128; o < nbytes; o += 32 * 128) sv_prefetch_l2(b0 + o);                                 \
-        } else {                                                                                                      \
-          const char* b0 = (const char*)(d.sn_rows + nrp + nr0);                                                      \
-          const int nbytes = (nr1 - nr0) * 4;                                                                         \
-          for (int o = lane * 128; o < nbytes; o += 32 * 128) sv_prefetch_l2(b0 + o);                                 \
-        }                                                                                                             \
-      }                                                                                                               \
-    }                                                                                                                 \
-  } while (0)
+#define SV_FETCH3() do { if (warp == SV_NT / 32 - 1 && lane < 6 && fq < q.ntask) s_rec[cur ^ 1][lane] = frec; } while (0)
 #define SV_FETCH_NEXT() do { SV_FETCH1(); SV_FETCH2(); SV_FETCH3(); } while (0)
   for (;;) {
     // no barrier here: every path below ends with a barrier that follows all reads of the slab and the vectors, and
@@ -525,7 +499,7 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
     const int qi = s_task[cur];
     if (qi >= q.ntask) break;
     const int k = FWD ? qi : q.ntask - 1 - qi;
-    unsigned long long* trk = q.trace ? q.trace + 8 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
+    unsigned long long* trk = q.trace ? q.trace + 4 * ((size_t)(FWD ? 0 : q.ntask) + k) : nullptr;
     if (trk && tid == 0) trk[0] = df_gtime();
     const SVTask& T = *reinterpret_cast<const SVTask*>(s_rec[cur]);
     const int kind = T.kind;
@@ -587,13 +561,15 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       const int nrt = T.nrt, dep0 = T.dep0, dep1 = T.dep1, dep2 = T.dep2, t_notify = T.notify, t_ptask = T.ptask;
       const long long cuoff = T.cuoff;
       const bool rows_late = head && dep2 > dep1;               // the rows' contributions arrive after the pivots' (chain child followed slab by slab)
-      // static gather lists (first two sources of every destination, one 8-byte load each; prefetched into L2 by the
-      // previous task of this CTA), fetched before the wait
-      const int2* __restrict__ g2 = d.gat2 + (f + rp);
-      int2 ga = make_int2(-1, -1), gb = make_int2(-1, -1);
+      // static gather lists: ranges and the first two source indices of every destination are fetched before the wait
+      int ga0 = 0, ga1 = 0, gai0 = 0, gai1 = 0, gb0 = 0, gb1 = 0, gbi0 = 0, gbi1 = 0;
       if (!pure) {
-        if (head && tid < ns) ga = g2[tid];
-        if (tid < rows) gb = g2[ns + r0 + tid];
+        if (head && tid < ns) { ga0 = gp[tid]; ga1 = gp[tid + 1]; }
+        if (tid < rows) { gb0 = gp[ns + r0 + tid]; gb1 = gp[ns + r0 + tid + 1]; }
+        if (ga1 > ga0) gai0 = d.gat_src[ga0];
+        if (ga1 > ga0 + 1) gai1 = d.gat_src[ga0 + 1];
+        if (gb1 > gb0) gbi0 = d.gat_src[gb0];
+        if (gb1 > gb0 + 1) gbi1 = d.gat_src[gb0 + 1];
       }
       if (tid == SV_POLL) {     // not thread 0: that one may still be publishing the previous task
         if (head) sv_wait_zero(q.pend + k); else sv_wait_set(q.ydone + s);
@@ -601,7 +577,6 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
         if (trk) trk[1] = df_gtime();
       }
       __syncthreads();
-      if (trk && tid == 0) trk[4] = df_gtime();          // all threads past the dependency barrier
       SV_FETCH1();
       auto gather_rows = [&](double* g) {
         if (tid < rows) {
@@ -610,9 +585,9 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
             double acc = 0.0;
             if (pure) acc = __ldcg(r.u[h] + cuoff + ns + r0 + tid);
             else {
-              if (gb.x >= 0) acc += __ldcg(r.u[h] + gb.x);
-              if (gb.y >= 0) acc += __ldcg(r.u[h] + gb.y);
-              else if (gb.y == -2) for (int e = gp[ns + r0 + tid] + 1; e < gp[ns + r0 + tid + 1]; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
+              if (gb1 > gb0) acc += __ldcg(r.u[h] + gbi0);
+              if (gb1 > gb0 + 1) acc += __ldcg(r.u[h] + gbi1);
+              for (int e = gb0 + 2; e < gb1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
             }
             g[h] = acc;
           }
@@ -629,17 +604,15 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
             double acc = 0.0;
             if (pure) acc = __ldcg(r.u[h] + cuoff + tid);
             else {
-              if (ga.x >= 0) acc += __ldcg(r.u[h] + ga.x);
-              if (ga.y >= 0) acc += __ldcg(r.u[h] + ga.y);
-              else if (ga.y == -2) for (int e = gp[tid] + 1; e < gp[tid + 1]; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
+              if (ga1 > ga0) acc += __ldcg(r.u[h] + gai0);
+              if (ga1 > ga0 + 1) acc += __ldcg(r.u[h] + gai1);
+              for (int e = ga0 + 2; e < ga1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
             }
             sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] + acc;
           }
         }
         if (!rows_late) gather_rows(g);         // issued now, consumed after phase A
-        if (trk && tid == 0) trk[5] = df_gtime();        // thread 0: gathers done
         SV_SLAB_WAIT();
-        if (trk && tid == 0) trk[6] = df_gtime();        // thread 0: slab landed
         __syncthreads();
         if (trk && tid == 0) trk[3] = df_gtime();
         if (tid < ns) {
@@ -687,7 +660,6 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       }
       SV_FETCH3();
       __syncthreads();
-      if (trk && tid == 0) trk[7] = df_gtime();          // phase B done, before publishing
       if (tid == 0) {
         sv_set_release(q.tdone + k);
         // a front that is one task needs no count of its tasks: the parent hears of it at once (no atomic round trip)

@@ -25,7 +25,7 @@ raw = open(os.environ["CB_DF_TRACE_SOLVE"], "rb").read()
 nt = struct.unpack("q", raw[:8])[0]
 rec = np.frombuffer(raw, dtype=np.int32, count=24 * nt, offset=8).reshape(nt, 24)
 kind, front, ns, nr, r0, r1, nrt = rec[:, 0], rec[:, 1], rec[:, 4], rec[:, 5], rec[:, 6], rec[:, 7], rec[:, 15]
-tr = np.frombuffer(raw, dtype=np.uint64, count=16 * nt, offset=8 + 96 * nt).reshape(2, nt, 8).astype(np.int64)
+tr = np.frombuffer(raw, dtype=np.uint64, count=8 * nt, offset=8 + 96 * nt).reshape(2, nt, 4).astype(np.int64)
 names = {0: "narrow x8", 1: "head", 2: "rows"}
 for di, name in ((0, "forward"), (1, "backward")):
     t = tr[di]
@@ -46,11 +46,7 @@ for di, name in ((0, "forward"), (1, "backward")):
             ent = (ns + r1 - r0) * ns
             qq = q & (ent >= lo) & (ent < hi)
             if qq.any():
-                extra = ""
-                if di == 0:
-                    st = [(t[qq, i] - t0) / 1e3 for i in range(8)]
-                    extra = (f" | from ready: barrier {np.mean(st[4]-rd[qq]):5.2f} gathers {np.mean(st[5]-rd[qq]):5.2f} landed(t0) {np.mean(st[6]-rd[qq]):5.2f} "
-                             f"landed(all) {np.mean(st[3]-rd[qq]):5.2f} phaseB done {np.mean(st[7]-rd[qq]):5.2f} published {np.mean(st[2]-rd[qq]):5.2f}; start->ready {np.mean(rd[qq]-st[0]):5.2f}")
+                extra = f" | slab landed {np.mean(landed[qq]-rd[qq]):6.2f} us after ready" if di == 0 else ""
                 print(f"     head slabs {lo:5d}-{hi if hi < 1 << 29 else 99999:5d}: n={qq.sum():6d} busy mean {np.mean(end[qq]-rd[qq]):6.2f} us wait mean {np.mean(rd[qq]-grab[qq]):6.2f} us{extra}")
     nb = 20
     edges = np.linspace(0, end.max(), nb + 1)
