@@ -1,0 +1,20 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 600 python -m pytest tests/test_ldl_gpu.py tests/test_zz_shard_gpu.py tests/test_ipm_gpu.py -x -q -m gpu > $O/r02_call13_tests.log 2>&1
+echo "tests exit $?" > $O/r02_call13_summary.txt
+for wl in c2 c4; do
+CB_SOLVE_MINB=3 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --workload $wl --no-cpu-baseline > $O/r02_c13_${wl}.json 2> $O/r02_c13_${wl}.err
+echo "bench $wl exit $?" >> $O/r02_call13_summary.txt
+done
+cat $O/r02_call13_summary.txt; tail -n 3 $O/r02_call13_tests.log
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r02_c13_*.json")):
+    try:
+        d=json.load(open(f)); print(f, "it/s %.2f ms/it %.2f refactor %.3f ldl %.3f kkt %.3f e2e %.2f setup %.2f solves/it %.2f %s %d" % (d["value"], d["ms_per_step"], d["refactor_ms"], d["ldl_solve_ms"], d["kkt_solve_ms"], d["e2e"]["value"], d["e2e"]["setup_s"], d["ldl_solves_per_iteration"], d["status"], d["iterations"]))
+    except Exception as e: print(f, "ERR", e)
+PY
+CB_SOLVE_MINB=3 timeout 600 python scripts/df_trace_solve.py c4 > $O/r02_trace_solve_c4.txt 2>&1
+head -9 $O/r02_trace_solve_c4.txt | cut -c1-330
