@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
       }
       __syncthreads();
       SV_FETCH1();
-      auto gather_rows = [&](double* g) {
+      // children's contributions to the slab's rows -> sx (phase B reads them with a different thread mapping)
+      auto gather_rows = [&]() {
         if (tid < rows) {
 #pragma unroll
           for (int h = 0; h < NR; h++) {
@@ -589,13 +590,13 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
               if (gb1 > gb0 + 1) acc += __ldcg(r.u[h] + gbi1);
               for (int e = gb0 + 2; e < gb1; e++) acc += __ldcg(r.u[h] + d.gat_src[e]);
             }
-            g[h] = acc;
+            sx[h * SV_MAXROWS + tid] = acc;
           }
         }
       };
-      double g[NR];
-#pragma unroll
-      for (int h = 0; h < NR; h++) g[h] = 0.0;
+      // the dot products of both phases are split four ways: thread (i, q) = (tid / 4, tid % 4) takes the terms
+      // j = q, q + 4, ... of row i, the quad adds its partial sums with two shuffles (fixed order)
+      const int qi_row = tid >> 2, qd = tid & 3;
       if (head) {
         // phase A: y1 = L11^-1 (b1 + children)
         if (tid < ns) {
@@ -611,21 +612,28 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
             sw[h * CB_PB_MAXNS + tid] = r.xp[h][f + tid] + acc;
           }
         }
-        if (!rows_late) gather_rows(g);         // issued now, consumed after phase A
+        if (!rows_late) gather_rows();          // issued now, consumed in phase B
         SV_SLAB_WAIT();
         __syncthreads();
         if (trk && tid == 0) trk[3] = df_gtime();
-        if (tid < ns) {
+        {
           double y[NR];
 #pragma unroll
-          for (int h = 0; h < NR; h++) y[h] = sw[h * CB_PB_MAXNS + tid];
-          for (int j = 0; j < tid; j++) {
-            const double l = sl[j * lds + tid];
+          for (int h = 0; h < NR; h++) y[h] = 0.0;
+          if (qi_row < ns) {
+            for (int j = qd; j < qi_row; j += 4) {
+              const double l = sl[j * lds + qi_row];
 #pragma unroll
-            for (int h = 0; h < NR; h++) y[h] += l * sw[h * CB_PB_MAXNS + j];
+              for (int h = 0; h < NR; h++) y[h] += l * sw[h * CB_PB_MAXNS + j];
+            }
           }
+          __syncwarp();
 #pragma unroll
-          for (int h = 0; h < NR; h++) { sy[h * CB_PB_MAXNS + tid] = y[h]; r.xp[h][f + tid] = y[h]; }
+          for (int h = 0; h < NR; h++) {
+            y[h] += __shfl_xor_sync(0xffffffffu, y[h], 1);
+            y[h] += __shfl_xor_sync(0xffffffffu, y[h], 2);
+            if (qd == 0 && qi_row < ns) { const double v = sw[h * CB_PB_MAXNS + qi_row] + y[h]; sy[h * CB_PB_MAXNS + qi_row] = v; r.xp[h][f + qi_row] = v; }
+          }
         }
         __syncthreads();
         SV_FETCH2();
@@ -633,30 +641,38 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           if (nrt > 0) sv_set_release(q.ydone + s);
           if (rows_late) { for (int t = max(dep1 + 1, dep0); t <= dep2; t++) sv_wait_set(q.tdone + t); }
         }
-        if (rows_late) { __syncthreads(); gather_rows(g); }
+        if (rows_late) { __syncthreads(); gather_rows(); __syncthreads(); }
       } else {
         if (tid < ns) {
 #pragma unroll
           for (int h = 0; h < NR; h++) sy[h * CB_PB_MAXNS + tid] = __ldcg(r.xp[h] + f + tid);
         }
-        gather_rows(g);
+        gather_rows();
         SV_SLAB_WAIT();
         __syncthreads();
         SV_FETCH2();
       }
-      // phase B: u[rows] = children - L21 y1
-      if (tid < rows) {
+      // phase B: u[rows] = children - L21 y1, 64 rows per pass
+      for (int base = 0; base < rows; base += SV_NT / 4) {
+        const int a = base + qi_row;
         double acc[NR];
 #pragma unroll
         for (int h = 0; h < NR; h++) acc[h] = 0.0;
-        const double* __restrict__ col = sl + l21 + tid;
-        for (int j = 0; j < ns; j++) {
-          const double l = col[j * lds];
+        if (a < rows) {
+          const double* __restrict__ col = sl + l21 + a;
+          for (int j = qd; j < ns; j += 4) {
+            const double l = col[j * lds];
 #pragma unroll
-          for (int h = 0; h < NR; h++) acc[h] += l * sy[h * CB_PB_MAXNS + j];
+            for (int h = 0; h < NR; h++) acc[h] += l * sy[h * CB_PB_MAXNS + j];
+          }
         }
+        __syncwarp();
 #pragma unroll
-        for (int h = 0; h < NR; h++) r.u[h][rp + r0 + tid] = g[h] - acc[h];
+        for (int h = 0; h < NR; h++) {
+          acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+          acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
+          if (qd == 0 && a < rows) r.u[h][rp + r0 + a] = sx[h * SV_MAXROWS + a] - acc[h];
+        }
       }
       SV_FETCH3();
       __syncthreads();
@@ -737,19 +753,32 @@ __global__ void __launch_bounds__(SV_NT, MINB) k_solve2(LDLDev d, SVPlan q, SVRh
           }
         }
         __syncthreads();
-        if (tid < ns) {
-          // x1 = L11^-T t:  x1[i] = t[i] + sum_{j > i} Linv[j][i] t[j]
+        {
+          // x1 = L11^-T t:  x1[i] = t[i] + sum_{j > i} Linv[j][i] t[j], four threads per row
+          const int i = tid >> 2, qd4 = tid & 3;
           double x[NR];
 #pragma unroll
-          for (int h = 0; h < NR; h++) x[h] = sy[h * CB_PB_MAXNS + tid];
-          const double* __restrict__ col = sl + tid * lds;
-          for (int j = tid + 1; j < ns; j++) {
-            const double l = col[j];
+          for (int h = 0; h < NR; h++) x[h] = 0.0;
+          if (i < ns) {
+            const double* __restrict__ col = sl + i * lds;
+            for (int j = i + 1 + qd4; j < ns; j += 4) {
+              const double l = col[j];
 #pragma unroll
-            for (int h = 0; h < NR; h++) x[h] += l * sy[h * CB_PB_MAXNS + j];
+              for (int h = 0; h < NR; h++) x[h] += l * sy[h * CB_PB_MAXNS + j];
+            }
           }
+          __syncwarp();
 #pragma unroll
-          for (int h = 0; h < NR; h++) { r.xp[h][f + tid] = x[h]; r.out[h][pf] = x[h]; }
+          for (int h = 0; h < NR; h++) {
+            x[h] += __shfl_xor_sync(0xffffffffu, x[h], 1);
+            x[h] += __shfl_xor_sync(0xffffffffu, x[h], 2);
+            if (qd4 == 0 && i < ns) sw[h * CB_PB_MAXNS + i] = sy[h * CB_PB_MAXNS + i] + x[h];
+          }
+        }
+        __syncthreads();
+        if (tid < ns) {
+#pragma unroll
+          for (int h = 0; h < NR; h++) { const double v = sw[h * CB_PB_MAXNS + tid]; r.xp[h][f + tid] = v; r.out[h][pf] = v; }
         }
         SV_FETCH3();
         __syncthreads();
