@@ -309,6 +309,9 @@ def run_ours(args, rank, world):
             "gpu_launches": launches_timed,
             "roofline": dominant, "roofline_other": other,
             "kkt_solve_ms": kkt_solve_ms, "ldl_solve_ms": ldl_solve_ms, "refactor_ms": refactor_ms,
+            "other_ms_per_step": max(0.0, 1e3 * t_max / K - refactor_ms - ldl_solve_ms * solves_per_iter) if not shard else None,
+            "collectives": ({"transport": "stream-ordered ncclAllGather issued by the library" if getattr(solver, "nccl_direct", False) else "torch.distributed all_gather_into_tensor (callback)",
+                             "count_total": int(cb._lib2().cipm_collective_count(solver._h))} if shard else None),
             "ldl_solves_per_iteration": solves_per_iter,
             "status": status_all[0], "iterations": iters_e2e,
             "cpu_baseline": cpu,

@@ -764,6 +764,7 @@ _l2_ready = False
 
 
 def _lib2():
+    # (argtypes of the level-2 entry points; cipm_collective_count returns uint64)
     global _l2_ready
     L = lib()
     if _l2_ready:
@@ -799,6 +800,8 @@ def _lib2():
     L.cipm_iter_ms.restype = C.c_uint64
     L.cipm_launch_count.argtypes = []
     L.cipm_launch_count.restype = C.c_uint64
+    L.cipm_collective_count.argtypes = [C.c_void_p]
+    L.cipm_collective_count.restype = C.c_uint64
     L.cipm_time_ms.argtypes = [vp, C.c_int, C.c_int]
     L.cipm_time_ms.restype = C.c_double
     for nm in ["cipm_kkt_dim", "cipm_kkt_nnz", "ccone_Hs_len", "cipm_m_reduced"]:

@@ -269,8 +269,12 @@ void amd_graph(int n, const std::vector<int64_t>& xadj, const std::vector<int>& 
     esize[p] = degme;
     if (degme == 0) { status[p] = ST_DEAD_ELEM; std::vector<int>().swap(Le[p]); }
 
-    // emit p and everything absorbed into it
-    for (int v = p; v >= 0; v = sv_next[v]) order.push_back(v);
+    // emit everything absorbed into p (mass-eliminated and indistinguishable variables), then p itself: the convention
+    // of the AMD the reference calls, whose output lists the non-principal variables of a pivot before the pivot
+    // (src/qdldl/test.rs:124-129 pins [3, 0, 1, 2] on its 4 x 4 matrix).  Same fill either way: these variables have no
+    // neighbours outside the pivot's clique.
+    for (int v = sv_next[p]; v >= 0; v = sv_next[v]) order.push_back(v);
+    order.push_back(p);
   }
   // dense rows last, lowest degree first
   std::sort(dense_nodes.begin(), dense_nodes.end(), [&](int a, int b) {

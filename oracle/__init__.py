@@ -501,6 +501,12 @@ class IPM:
         if rc:
             raise QDLDLError(rc)
 
+    def regularize_count(self):
+        """dynamically regularised pivots of the last refactorisation"""
+        self._L.oipm_regularize_count.restype = C.c_int64
+        self._L.oipm_regularize_count.argtypes = [C.c_void_p]
+        return int(self._L.oipm_regularize_count(self._h))
+
     def solve(self, trace_cap=256):
         tr = np.zeros((trace_cap, 6))
         rc = self._L.oipm_solve(self._h, P_(tr.reshape(-1)), trace_cap)

@@ -1385,6 +1385,8 @@ int oipm_new_gp(oipm_t **out, idx n, idx m, const idx *Pp, const idx *Pi, const 
 
 /* KKT pattern for the ordering step (caller computes a permutation of size N) */
 idx oipm_kkt_dim(const oipm_t *S) { return S->N; }
+/* dynamically regularised pivots of the LAST refactorisation (qdldl.rs:104-112 regularize_count) */
+idx oipm_regularize_count(const oipm_t *S) { return S->ldl ? oq_regularize_count(S->ldl) : 0; }
 idx oipm_m_reduced(const oipm_t *S) { return S->m; }
 idx oipm_kkt_nnz(const oipm_t *S) { return S->K.colptr[S->N]; }
 const idx *oipm_kkt_colptr(const oipm_t *S) { return S->K.colptr; }

@@ -140,3 +140,33 @@ def test_data_update_matches_fresh_solver():
         out.append(np.concatenate([x, zz]))
     assert np.max(np.abs(out[0] - out[1])) <= 1e-10 * max(1.0, np.max(np.abs(out[1])))
     assert np.allclose(dev.kkt_values(), fresh.kkt_values(), rtol=1e-14, atol=0)
+
+
+def _opening_iterations_match(pr, iters):
+    """Full-size parity beyond optimality of the end point: the first `iters` interior-point iterations of the device
+    path against the CPU oracle run ON THE SAME PERMUTATION -- barrier parameter and step lengths to 1e-7, same number
+    of dynamically regularised pivots in every refactorisation (qdldl.rs:645-651 applies to the same pivots in the same
+    order when the elimination order is the same)."""
+    st = cb.default_settings(max_iter=iters)
+    dev = cb.CudaSolver(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"], settings=st)
+    r = dev.solve()
+    ora = oracle.IPM(pr["P"], pr["q"], pr["A"], pr["b"], pr["cones"], settings=oracle.default_settings(max_iter=iters))
+    ora.set_perm(dev.kkt_perm())
+    ro = ora.solve()
+    assert r["iterations"] == ro["iterations"] == iters and r["status"] == ro["status"] == "MaxIterations"
+    k = min(len(dev.trace), len(ora.trace))
+    assert k >= iters
+    assert np.allclose(dev.trace[:k, 0], ora.trace[:k, 0], rtol=1e-7, atol=1e-13), (dev.trace[:k, 0], ora.trace[:k, 0])      # mu
+    assert np.allclose(dev.trace[1:k, 1], ora.trace[1:k, 1], rtol=1e-7), (dev.trace[1:k, 1], ora.trace[1:k, 1])              # step lengths
+    assert dev.linear_solver_info().regularize_count == ora.regularize_count()
+    assert np.max(np.abs(r["x"] - ro["x"])) <= 1e-7 * max(1.0, np.max(np.abs(ro["x"])))
+
+
+def test_c2_full_size_opening_iterations_match_oracle():
+    _opening_iterations_match(workloads.random_sparse_qp(n=100_000, m=200_000, nnz_per_row=5, seed=1, window=200), 3)
+
+
+def test_c4_full_size_first_iteration_matches_oracle():
+    """the north-star configuration (n = 1e6): one iteration of the CPU port costs about 12 s on the hub-separator
+    ordering, so the comparison stops after the first one"""
+    _opening_iterations_match(workloads.block_angular_qp(), 1)

@@ -197,3 +197,14 @@ def test_shard_plan_of_a_chain_is_replicas_only():
     S = cb.SymbolicAnalysis(n, K.indptr, K.indices, perm=np.arange(n))
     P = cb.shard_plan(S, 4)
     assert P["model_speedup"] <= 1.0 + 1e-9
+
+
+def test_amd_matches_reference_pin():
+    """src/qdldl/test.rs:124-129 -- the one ordering the reference pins: AMD (dense scale 1.5) of its 4 x 4 test matrix
+    is perm = [3, 0, 1, 2], iperm = [1, 2, 3, 0].  The `amd` crate is third-party and absent from /root/reference; the
+    repo's own AMD (csrc/ordering.cpp) must reproduce it, tie-breaks and output convention included."""
+    Ap, Ai = [0, 1, 3, 6, 8], [0, 0, 1, 0, 1, 2, 2, 3]          # test_matrix_4x4, test.rs:5-21
+    perm = cb.order(4, Ap, Ai, cb.ORDER_AMD, 1.5)
+    assert perm.tolist() == [3, 0, 1, 2]
+    iperm = np.empty(4, dtype=np.int64); iperm[perm] = np.arange(4)
+    assert iperm.tolist() == [1, 2, 3, 0]
