@@ -691,6 +691,28 @@ def order(n, colptr, rowval, kind=ORDER_AMD, dense_scale=1.5, nd_leaf=200):
     return out.astype(np.int64)
 
 
+def order_groups(N, colptr, rowval, cones, n, ordering=ORDER_BEST):
+    """Host-only ordering of a KKT matrix whose cone list has dense Hs blocks (PSD cones, SOC cones kept dense): every
+    block is one group of KKT vertices (rows n + offset .. of the cone), contracted for the ordering and eliminated
+    first (csrc/symbolic.cpp order_with_groups -- what cipm_create does internally)."""
+    L = lib()
+    group = np.full(int(N), -1, dtype=np.int32)
+    off, g = int(n), 0
+    for kind, d in cones:
+        rows = cone_nvars(kind, d)
+        if kind == "psd":
+            group[off:off + rows] = g
+            g += 1
+        off += rows
+    cp, rv = _u64(colptr), _u64(rowval)
+    out = np.empty(int(N), dtype=np.uint64)
+    L.csym_order_groups.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.c_int32, C.c_int, C.POINTER(C.c_uint64)]
+    rc = L.csym_order_groups(int(N), _p(cp, C.c_uint64), _p(rv, C.c_uint64), group.ctypes.data_as(C.POINTER(C.c_int32)), g, ordering, _p(out, C.c_uint64))
+    if rc < 0:
+        raise BackendError("grouped ordering failed")
+    return out.astype(np.int64)
+
+
 # ===========================================================================
 # Level 2: device-resident solver (cipm_* / ckkt_* / ccone_*)
 # ===========================================================================

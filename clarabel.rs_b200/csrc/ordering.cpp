@@ -574,6 +574,25 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
   const int64_t half = (int64_t)total / 2;
   int cut = 0;
   while (cut < e - 1 && pre[cut + 1] < half) cut++;      // levels 0..cut hold at least half (or cut = e-1)
+  // small-world signature: the levels around the balance point are fat (more than 4 % of the region each), so every
+  // candidate cut below would be fat too -- look for connector vertices first and save the matchings on huge boundary
+  // sets (C4: 1.1 s of Hopcroft-Karp on 3.3e5 boundary vertices for a cut that is then thrown away)
+  if (W.hubs && (int)total >= 50 * W.leaf_size && cntl[cut] * 25 > (int64_t)total && cntl[std::min(cut + 1, e)] * 25 > (int64_t)total) {
+    std::vector<int> hsep;
+    if (hub_separator(W, q, region, hsep) &&
+        !(W.sep_flop_cap > 0.0 && (double)hsep.size() * (double)hsep.size() * (double)hsep.size() / 3.0 > W.sep_flop_cap)) {
+      if (std::getenv("CB_TIMING")) std::fprintf(stderr, "[cb timing]   nd: depth %d hub separator of %zu: %zu connectors (levels around the balance point hold %lld and %lld vertices), %.4f s\n", depth, total, hsep.size(), (long long)cntl[cut], (long long)cntl[std::min(cut + 1, e)], onow() - t_enter);
+      for (int v : hsep) W.part[v] = -1;
+      std::vector<int> rest;
+      rest.reserve(total - hsep.size());
+      for (int v : q) if (W.part[v] == region) rest.push_back(v);
+      std::vector<int>().swap(verts);
+      std::vector<int>().swap(q);
+      nd_rec(W, rest, depth, out);
+      nd_leaf(W, hsep, out);
+      return;
+    }
+  }
   std::vector<int> sep, bestsep;
   int bestc = -1;
   double bestscore = 1e300;
