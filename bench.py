@@ -377,7 +377,7 @@ def cpu_solve(pr, workload, max_iter, perm=None):
 
 def cpu_baseline(pr, workload, sample_iters=0, perm=None):
     if sample_iters <= 0:
-        sample_iters = 2 if workload == "c4" else 3
+        sample_iters = 2 if workload in ("c4", "c5") else 3
     ipm, r, t_setup, t_total, order = cpu_solve(pr, workload, sample_iters, perm)
     i = r["info"]
     return {"value": r["iterations"] / i.solve_time, "unit": "iterations/s", "cores": 1, "kind": "port",
@@ -402,7 +402,7 @@ def run_reference(args, rank, world):
     pr, desc = load_workload(args.workload, 0)
     W, K = args.warmup, args.steps
     # bounded sample: the whole arm has to end within a few minutes; an iteration of the port costs ~12 s on C4
-    cap = {"c4": 6, "c5": 12}.get(args.workload, W + K)
+    cap = {"c4": 6, "c5": 4}.get(args.workload, W + K)
     ipm, r, t_setup, t_total, order = cpu_solve(pr, args.workload, min(W + K, cap))
     i = r["info"]
     iters = r["iterations"]
