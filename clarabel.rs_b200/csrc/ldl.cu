@@ -1149,8 +1149,15 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
 #endif
   __syncthreads();
   for (int idx = tid; idx < ns * TS; idx += DF_NT) sBt[idx] *= sD[idx >> 6];
+#ifndef CB_EMU
+  {   // the tensor-core product below walks K in steps of 4: rows ns .. of both operands count as zero
+    const int ns4 = (ns + 3) & ~3;
+    for (int idx = ns * TS + tid; idx < ns4 * TS; idx += DF_NT) { sAt[idx] = 0.0; sBt[idx] = 0.0; }
+  }
+#endif
   __syncthreads();
   DF_STAMP(q, 4);
+#ifdef CB_EMU   /* host build of the test suite: the same product with scalar FMAs */
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -1166,6 +1173,48 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
   }
+#else
+  // The 64 x 64 x ns product L21_I (D L21_J)^T on the FP64 tensor path: mma.sync.aligned.m8n8k4 (SASS DMMA) -- the
+  // only FP64 MMA sm_100a has (tcgen05 has no FP64 kind).  On C5 these tiles ARE the dense Schur blocks of the PSD
+  // cones' Hs blocks (the north star's "tensor cores only for the dense Schur blocks arising from SDP cones").
+  // scripts/ubench/dmma_tile.cu: 24.5 TFLOP/s against 12.4 for the 4 x 4 FMA register tile on this tile shape.
+  // Warp w owns rows 32 (w & 1) .., columns 16 (w >> 1) .. as 4 x 2 fragments of 8 x 8; the result goes through shared
+  // memory (the operand tiles are dead by then) back to the (tx, ty) ownership of the extend-add and the store.
+  double* sP = sm;                       // [TS][TS+1], over sAt and the head of sBt
+  {
+    const int lane = tid & 31, w = tid >> 5;
+    const int r0w = (w & 1) * 32, c0w = (w >> 1) * 16, lk = lane & 3, lr = lane >> 2;
+    double c2[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) { c2[i][j][0] = 0.0; c2[i][j][1] = 0.0; }
+    const int ns4 = (ns + 3) & ~3;
+#pragma unroll 2
+    for (int k = 0; k < ns4; k += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = sAt[(k + lk) * TS + r0w + 8 * i + lr];
+#pragma unroll
+      for (int j = 0; j < 2; j++) b[j] = sBt[(k + lk) * TS + c0w + 8 * j + lr];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c2[i][j][0]), "+d"(c2[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();                     // every warp is done with the operand tiles
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        double* o = sP + (r0w + 8 * i + lr) * (TS + 1) + c0w + 8 * j + 2 * lk;
+        o[0] = c2[i][j][0]; o[1] = c2[i][j][1];
+      }
+    __syncthreads();
+  }
+#endif
   DF_STAMP(q, 5);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -1173,8 +1222,13 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int cc = ty + 16 * j;
+#ifdef CB_EMU
+      const double prod = acc[i][j];
+#else
+      const double prod = sP[rr * (TS + 1) + cc];
+#endif
       if (rr < ni && cc < nj && (i0 + rr >= j0 + cc))
-        U[(long long)(j0 + cc) * nr + (i0 + rr)] = (use_sc ? creg[i][j] + sC[rr * (TS + 1) + cc] : creg[i][j]) - acc[i][j];
+        U[(long long)(j0 + cc) * nr + (i0 + rr)] = (use_sc ? creg[i][j] + sC[rr * (TS + 1) + cc] : creg[i][j]) - prod;
     }
   }
 }
