@@ -1106,8 +1106,19 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
   }
   DF_STAMP(q, 6);
   // children that are contiguous in this tile (the previous panel of the same separator) are added in
-  // registers, straight from their update matrix: thread (tx, ty) owns rows tx+16i, columns ty+16j of the tile
+  // registers, straight from their update matrix.  A thread owns 4 x 4 entries of the tile, (OWN_R(i), OWN_C(j)):
+  // on the device the ones the tensor-core fragments of the product below leave in its registers (warp w: rows
+  // 32 (w & 1) .., columns 16 (w >> 1) ..; lane: row lane / 4 of every 8 x 8 fragment, columns 2 (lane % 4), +1), in the
+  // host build of the test suite rows tx + 16 i, columns ty + 16 j
+#ifdef CB_EMU
   const int tx = tid & 15, ty = tid >> 4;
+#define OWN_R(i) (tx + 16 * (i))
+#define OWN_C(j) (ty + 16 * (j))
+#else
+  const int lk = tid & 3, lr = (tid & 31) >> 2, r0w = ((tid >> 5) & 1) * 32, c0w = (tid >> 6) * 16;
+#define OWN_R(i) (r0w + 8 * (i) + lr)
+#define OWN_C(j) (c0w + 8 * ((j) >> 1) + 2 * lk + ((j) & 1))
+#endif
   double creg[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -1123,10 +1134,10 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
     double v[4][4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int b = ty + 16 * j + rb;
+      const int b = OWN_C(j) + rb;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int a = tx + 16 * i + ra;
+        const int a = OWN_R(i) + ra;
         v[i][j] = (a >= a0 && a < a1 && b >= b0 && b < b1 && a >= b) ? __ldcg(Uc + (long long)b * nrc + a) : 0.0;
       }
     }
@@ -1178,13 +1189,10 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
   // only FP64 MMA sm_100a has (tcgen05 has no FP64 kind).  On C5 these tiles ARE the dense Schur blocks of the PSD
   // cones' Hs blocks (the north star's "tensor cores only for the dense Schur blocks arising from SDP cones").
   // scripts/ubench/dmma_tile.cu: 24.5 TFLOP/s against 12.4 for the 4 x 4 FMA register tile on this tile shape.
-  // Warp w owns rows 32 (w & 1) .., columns 16 (w >> 1) .. as 4 x 2 fragments of 8 x 8; the result goes through shared
-  // memory (the operand tiles are dead by then) back to the (tx, ty) ownership of the extend-add and the store.
-  double* sP = sm;                       // [TS][TS+1], over sAt and the head of sBt
+  // Warp w owns rows 32 (w & 1) .., columns 16 (w >> 1) .. as 4 x 2 fragments of 8 x 8; the extend-add above and the store
+  // below use the same ownership, so the product never leaves the registers.
+  double c2[4][2][2];
   {
-    const int lane = tid & 31, w = tid >> 5;
-    const int r0w = (w & 1) * 32, c0w = (w >> 1) * 16, lk = lane & 3, lr = lane >> 2;
-    double c2[4][2][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -1204,33 +1212,26 @@ __device__ void dff_tile(const LDLDev& d, const DFFactor& q, const int* tk, doub
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                        : "+d"(c2[i][j][0]), "+d"(c2[i][j][1]) : "d"(a[i]), "d"(b[j]));
     }
-    __syncthreads();                     // every warp is done with the operand tiles
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        double* o = sP + (r0w + 8 * i + lr) * (TS + 1) + c0w + 8 * j + 2 * lk;
-        o[0] = c2[i][j][0]; o[1] = c2[i][j][1];
-      }
-    __syncthreads();
   }
 #endif
   DF_STAMP(q, 5);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const int rr = tx + 16 * i;
+    const int rr = OWN_R(i);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int cc = ty + 16 * j;
+      const int cc = OWN_C(j);
 #ifdef CB_EMU
       const double prod = acc[i][j];
 #else
-      const double prod = sP[rr * (TS + 1) + cc];
+      const double prod = c2[i][j >> 1][j & 1];
 #endif
       if (rr < ni && cc < nj && (i0 + rr >= j0 + cc))
         U[(long long)(j0 + cc) * nr + (i0 + rr)] = (use_sc ? creg[i][j] + sC[rr * (TS + 1) + cc] : creg[i][j]) - prod;
     }
   }
+#undef OWN_R
+#undef OWN_C
 }
 
 __global__ void __launch_bounds__(DF_NT, 2) k_factor_df(LDLDev d, DFFactor q) {
