@@ -2068,6 +2068,7 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     for (int w = 0; w < 2; w++) { d_shard_segs[w].assign(shard_nranks, nullptr); shard_nsegs[w].assign(shard_nranks, 0); }
     for (int g = 0; g < shard_nranks; g++) { int* t1 = nullptr; if ((rc = upload(&t1, shard_xidx[g]))) return rc; d_shard_xidx[g] = t1; }
   }
+  CK(cudaDeviceSynchronize());      // the uploads above are cudaMemcpy from pageable memory (staged, not necessarily landed); `stream` does not wait for the default stream
   factored = false;
   return CLDL_OK;
 }
@@ -2435,6 +2436,7 @@ int LDLObject::shard_seglist(int what, int rank, const long long** d_out, int* n
     long long* dp = nullptr;
     CK(cudaMalloc((void**)&dp, h.size() * sizeof(long long)));
     CK(cudaMemcpy(dp, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
     slot = dp;
   }
   *d_out = slot; *nseg = shard_nsegs[what][rank];

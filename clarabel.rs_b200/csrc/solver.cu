@@ -820,6 +820,7 @@ int IPM::update_data(const double* Pnz, const double* qv, const double* Anz, con
     for (int i = 0; i < m; i++) { b[i] = bv[i] * e[i]; normb = std::max(normb, std::fabs(b[i] * einv[i])); }
     if (m) SCK(cudaMemcpy((void*)db, b.data(), (size_t)m * 8, cudaMemcpyHostToDevice));
   }
+  SCK(cudaDeviceSynchronize());      // pageable-memory copies above: landed before anything on the solver's streams reads them
   return 0;
 }
 
@@ -1571,7 +1572,14 @@ void cipm_ldl_info(const cipm_t* h, cldl_info_t* info) {
 }
 
 // ---- KKTSolver trait (kktsolvers/mod.rs:7-19) on the handle's KKT object; host buffers ----
-static int h2d(double* d, const double* h, size_t n) { return n == 0 || cudaMemcpy(d, h, n * 8, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : CLDL_E_CUDA; }
+// cudaMemcpy from pageable host memory returns once the data is STAGED; the DMA to the device may still be in flight, and
+// the kernels that consume it run on non-blocking streams that do not wait for the default stream -- so the copy is
+// completed here (a flaky dot product in tests/test_zz_algebra_gpu.py was exactly this race)
+static int h2d(double* d, const double* h, size_t n) {
+  if (n == 0) return 0;
+  if (cudaMemcpy(d, h, n * 8, cudaMemcpyHostToDevice) != cudaSuccess) return CLDL_E_CUDA;
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : CLDL_E_CUDA;
+}
 static int d2h(double* h, const double* d, size_t n) { return n == 0 || cudaMemcpy(h, d, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CLDL_E_CUDA; }
 
 int ckkt_update(cipm_t* h) {
@@ -1762,7 +1770,7 @@ int ccone_step_length(cipm_t* h, const double* dz, const double* ds, const doubl
                       double alpha_max, double* alpha_out) {
   CONE_PRE
   if (h2d(I.ps, dz, m) || h2d(I.pz, ds, m) || h2d(I.workz, z, m) || h2d(I.work_conic, s, m)) return CLDL_E_CUDA;
-  if (cudaMemcpy(I.sc.d + cb::S_ALPHA, &alpha_max, 8, cudaMemcpyHostToDevice) != cudaSuccess) return CLDL_E_CUDA;
+  if (cudaMemcpy(I.sc.d + cb::S_ALPHA, &alpha_max, 8, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return CLDL_E_CUDA;
   I.cones.step_length(I.ps, I.pz, I.workz, I.work_conic, I.sc.d + cb::S_ALPHA);
   cudaStreamSynchronize(I.st);
   return d2h(alpha_out, I.sc.d + cb::S_ALPHA, 1);

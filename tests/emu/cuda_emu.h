@@ -174,6 +174,7 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(1); return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = std::malloc(1); return 0; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = std::malloc(1); return 0; }

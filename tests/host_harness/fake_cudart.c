@@ -102,6 +102,7 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, void *st) { (void)st; aren
 cudaError_t cudaStreamCreateWithFlags(void **s, unsigned f) { (void)f; *s = malloc(1); return 0; }
 cudaError_t cudaStreamDestroy(void *s) { free(s); return 0; }
 cudaError_t cudaStreamSynchronize(void *s) { (void)s; return 0; }
+cudaError_t cudaDeviceSynchronize(void) { return 0; }
 cudaError_t cudaStreamWaitEvent(void *s, void *e, unsigned f) { (void)s; (void)e; (void)f; return 0; }
 cudaError_t cudaEventCreate(void **e) { *e = malloc(1); return 0; }
 cudaError_t cudaEventCreateWithFlags(void **e, unsigned f) { (void)f; *e = malloc(1); return 0; }
