@@ -1378,6 +1378,11 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   }
 
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  if (std::getenv("CB_LEAF_STREAMS") == nullptr || std::atoi(std::getenv("CB_LEAF_STREAMS")) != 0) {
+    CK(cudaStreamCreateWithFlags(&stream_a, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&stream_b, cudaStreamNonBlocking));
+    for (auto& e : ev_leaf) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
   CK(cudaMallocHost((void**)&h_status, ST_COUNT * sizeof(int)));
@@ -2091,6 +2096,9 @@ void LDLObject::release() {
   if (h_status) cudaFreeHost(h_status);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  for (auto& e : ev_leaf) if (e) { cudaEventDestroy(e); e = nullptr; }
+  if (stream_a) { cudaStreamDestroy(stream_a); stream_a = nullptr; }
+  if (stream_b) { cudaStreamDestroy(stream_b); stream_b = nullptr; }
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -2214,11 +2222,20 @@ void LDLObject::sv_sweep(bool fwd, int nrhs, const SVPlan& q, const SVRhs& r) {
   if (fwd) { if (nrhs == 1) sv_launch<true, 1>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); else sv_launch<true, 2>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); }
   else { if (nrhs == 1) sv_launch<false, 1>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); else sv_launch<false, 2>(solve_minb, df_grid, smem, stream, dev, q, r, sv_cap); }
 }
-// the level-0 narrow fronts: before the forward sweep, after the backward sweep
+// the level-0 fronts: before the forward sweep, after the backward sweep.  The three kernels touch disjoint fronts and
+// none depends on another, so the two narrow-leaf kernels run on side streams next to the wide-leaf kernel
+// (C4: 24 + 48 + 186 us one after the other -> ~190 us together)
 void LDLObject::sv_leaves(bool fwd, int nrhs, const SVRhs& r) {
+  const bool side = stream_a && stream_b && ((sv_nleaf1 ? 1 : 0) + (sv_nleafn ? 1 : 0) + (sv_nleafw ? 1 : 0)) > 1;
+  cudaStream_t s1 = side ? stream_a : stream, sn = side ? stream_b : stream;
+  if (side) {
+    cudaEventRecord(ev_leaf[0], stream);
+    cudaStreamWaitEvent(s1, ev_leaf[0], 0);
+    cudaStreamWaitEvent(sn, ev_leaf[0], 0);
+  }
   if (fwd) {
-    if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_fwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_fwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
-    if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, true><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
+    if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_fwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, s1>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_fwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, s1>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
+    if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, true><<<(sv_nleafn + 7) / 8, 256, 0, sn>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, true><<<(sv_nleafn + 7) / 8, 256, 0, sn>>>(dev, d_sv_leafn, sv_nleafn, r); }
     if (sv_nleafw) { g_launches++; if (nrhs == 1) k_fwd_leafw<1><<<sv_nleafw, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); else k_fwd_leafw<2><<<sv_nleafw, SV_LEAF_NT, 0, stream>>>(dev, d_sv_leafw, sv_nleafw, r); }
   } else {
     if (sv_nleafw) {
@@ -2227,8 +2244,14 @@ void LDLObject::sv_leaves(bool fwd, int nrhs, const SVRhs& r) {
       if (nrhs == 1) k_bwd_leafw<1><<<sv_nleafw, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
       else k_bwd_leafw<2><<<sv_nleafw, SV_LEAF_NT, sm, stream>>>(dev, d_sv_leafw, sv_nleafw, r, sv_leafw_nrmax);
     }
-    if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, false><<<(sv_nleafn + 7) / 8, 256, 0, stream>>>(dev, d_sv_leafn, sv_nleafn, r); }
-    if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_bwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_bwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, stream>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
+    if (sv_nleafn) { g_launches++; if (nrhs == 1) k_leaf_small<1, false><<<(sv_nleafn + 7) / 8, 256, 0, sn>>>(dev, d_sv_leafn, sv_nleafn, r); else k_leaf_small<2, false><<<(sv_nleafn + 7) / 8, 256, 0, sn>>>(dev, d_sv_leafn, sv_nleafn, r); }
+    if (sv_nleaf1) { g_launches++; if (nrhs == 1) k_bwd_leaf1<1><<<(sv_nleaf1 + 255) / 256, 256, 0, s1>>>(dev, d_sv_leaf1, sv_nleaf1, r); else k_bwd_leaf1<2><<<(sv_nleaf1 + 255) / 256, 256, 0, s1>>>(dev, d_sv_leaf1, sv_nleaf1, r); }
+  }
+  if (side) {
+    cudaEventRecord(ev_leaf[1], s1);
+    cudaEventRecord(ev_leaf[2], sn);
+    cudaStreamWaitEvent(stream, ev_leaf[1], 0);
+    cudaStreamWaitEvent(stream, ev_leaf[2], 0);
   }
 }
 int LDLObject::sv_reset() {

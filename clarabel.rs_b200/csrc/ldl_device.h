@@ -111,6 +111,8 @@ class LDLObject {
   LDLDev dev;
   std::vector<LaunchSeg> plan;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_a = nullptr, stream_b = nullptr;   // side streams of the narrow-leaf solve kernels
+  cudaEvent_t ev_leaf[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int* h_status = nullptr;
   double* d_xp = nullptr;  // permuted work vector
