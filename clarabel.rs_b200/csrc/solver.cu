@@ -601,6 +601,7 @@ class IPM {
  public:
   int n = 0, m = 0;
   int mfull = 0;                 // rows of the caller's problem (m = rows left after the inf-bound presolve)
+  double infbound = 1e20;        // the infinity bound at construction (presolver.rs:51,150): what reverse_presolve writes into s, whatever set_infinity did since
   std::vector<char> keep;        // presolve row mask over the caller's rows, empty = nothing dropped
   cipm_settings set{};
   HostCsc P, A;  // equilibrated copies (host)
@@ -862,7 +863,8 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   for (int j = 0; j < n; j++)
     for (int64_t t = P.colptr[j]; t < P.colptr[j + 1]; t++) if (P.rowval[t] > j) return CLDL_E_NOT_TRIU;
   q.assign(q_, q_ + n); b.assign(b_, b_ + m);
-  for (auto& v : b) v = std::min(v, g_infinity.load());  // problemdata.rs:130-131
+  infbound = g_infinity.load();
+  for (auto& v : b) v = std::min(v, infbound);  // problemdata.rs:130-131
   std::vector<ConeSpec> cs;
   int rc = ConeSet::collapse(ctype, cdim, ncones, cs, cparam, gp_dim2, gp_alpha);
   if (rc) return rc;
@@ -876,7 +878,7 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
   // their cone; cipm_get_solution puts them back with s = bound, z = 0
   mfull = m; keep.clear();
   if (set.presolve_enable) {
-    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * g_infinity.load();
+    const double thr = (1.0 - 2.220446049250313e-16 * 10.0) * infbound;
     std::vector<char> kp(m, 1);
     int mred = m, r = 0;
     for (auto& cc : cs) {
@@ -1483,7 +1485,7 @@ int cipm_get_solution(cipm_t* h, double* x, double* z, double* s) {
     int c = 0;
     for (int i = 0; i < I.mfull; i++) {
       if (I.keep[i]) { z[i] = hz[c] * I.e[c] * (scaleinv * cinv); s[i] = hs[c] * I.einv[c] * scaleinv; c++; }
-      else { z[i] = 0.0; s[i] = g_infinity.load(); }
+      else { z[i] = 0.0; s[i] = I.infbound; }
     }
   }
   return CLDL_OK;
