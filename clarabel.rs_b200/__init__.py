@@ -910,8 +910,12 @@ class CudaSolver:
                               C.byref(self.settings), C.byref(o), _p(pm, C.c_uint64) if pm is not None else None)
         _check(rc, "cipm_create_gp")
         self._h = h
-        self._cur = {"P": Px.copy(), "q": qq.copy(), "A": Ax.copy(), "b": bb.copy()}      # for the (index, values) update form
-        self._pattern = {"P": (P.indptr.copy(), P.indices.copy()), "A": (A.indptr.copy(), A.indices.copy())}
+        # for the (index, values) update form.  P is this constructor's own upper-triangle copy, so its arrays are kept as
+        # they are; q, b and A's values may alias the caller's arrays (which the caller is free to overwrite) and are copied
+        self._cur = {"P": Px, "q": qq.copy(), "A": Ax.copy(), "b": bb.copy()}
+        # sparsity patterns for the matrix form of update_data (index arrays only; no copies: a caller that rewrites the
+        # index arrays of the matrix it passed in has a different matrix)
+        self._pattern = {"P": (P.indptr, P.indices), "A": (A.indptr, A.indices)}
         self._shape = {"P": P.shape, "A": A.shape}
         self.N = int(L.cipm_kkt_dim(h))
         self.m_reduced = int(L.cipm_m_reduced(h))    # rows left after the inf-bound presolve

@@ -404,32 +404,43 @@ void nd_leaf(NDShared& W, const std::vector<int>& verts, std::vector<int>& out) 
 // components none of which holds more than 70 % of the region and the separator is below 5 % of it.
 bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::vector<int>& sep) {
   const int total = (int)verts.size();
-  std::vector<int> deg(total), comp(total), cpar, csize, stack, sorted;
+  std::vector<int> deg(total);
   for (int k = 0; k < total; k++) W.local[verts[k]] = k;
+  int dmax = 0;
   for (int k = 0; k < total; k++) {
     const int v = verts[k];
     int d = 0;
     for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) if (W.part[(*W.adj)[p]] == region) d++;
     deg[k] = d;
+    dmax = std::max(dmax, d);
   }
-  sorted = deg;
-  std::sort(sorted.begin(), sorted.end());
-  const int median = sorted[total / 2];
+  // degree quantiles from a histogram (degrees are small integers)
+  std::vector<int64_t> hist(dmax + 2, 0);
+  for (int k = 0; k < total; k++) hist[deg[k]]++;
+  auto quantile = [&](double f) {          // smallest degree d with  #{deg > d} <= f * total
+    int64_t above = 0;
+    int d = dmax;
+    while (d > 0 && above + hist[d] <= (int64_t)(f * total)) { above += hist[d]; d--; }
+    return d + 1;
+  };
+  int median = 0;
+  { int64_t below = 0; while (median < dmax && below + hist[median] <= total / 2) { below += hist[median]; median++; } }
   const int tiny = std::max(64, W.leaf_size / 8);
-  auto find = [&](int c) { while (cpar[c] != c) { cpar[c] = cpar[cpar[c]]; c = cpar[c]; } return c; };
-  bool ok = false;
-  int last_thr = -1;
+  std::vector<int> thrs;
   const double fracs[] = {0.0005, 0.002, 0.005, 0.02, 0.05, 0.1, 0.2};
   for (double f : fracs) {
-    int thr = sorted[std::min<int64_t>(total - 1, (int64_t)((1.0 - f) * total))];
-    if (thr <= median) thr = median + 1;
-    if (thr == last_thr) continue;
-    last_thr = thr;
+    int thr = std::max(quantile(f), median + 1);
+    if (thr > dmax) continue;
     int64_t ns0 = 0;
-    for (int k = 0; k < total; k++) { comp[k] = deg[k] >= thr ? -2 : -1; if (comp[k] == -2) ns0++; }
-    if (ns0 == 0) continue;
-    if (ns0 * 10 > (int64_t)total * 3) break;
-    cpar.clear(); csize.clear();
+    for (int d = thr; d <= dmax; d++) ns0 += hist[d];
+    if (ns0 == 0 || ns0 * 10 > (int64_t)total * 3) continue;
+    if (thrs.empty() || thrs.back() != thr) thrs.push_back(thr);
+  }
+  // one attempt: withhold deg >= thr, label the components of the rest, give back what is not a connector
+  auto attempt = [&](int thr, std::vector<int>& out) -> bool {
+    std::vector<int> comp(total), cpar, csize, stack;
+    auto find = [&](int c) { while (cpar[c] != c) { cpar[c] = cpar[cpar[c]]; c = cpar[c]; } return c; };
+    for (int k = 0; k < total; k++) comp[k] = deg[k] >= thr ? -2 : -1;
     for (int k0 = 0; k0 < total; k0++) {
       if (comp[k0] != -1) continue;
       const int c = (int)cpar.size();
@@ -446,11 +457,8 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
           if (comp[ku] == -1) { comp[ku] = c; stack.push_back(ku); }
         }
       }
+      if ((int64_t)csize[c] * 10 > (int64_t)total * 6) return false;   // the rest still hangs together: withhold more
     }
-    int64_t largest = 0;
-    for (int c : csize) largest = std::max<int64_t>(largest, c);
-    if (largest * 10 > (int64_t)total * 6) continue;            // the rest still hangs together: withhold more
-    // give back what is not a connector
     for (int pass = 0; pass < 8; pass++) {
       int64_t moved = 0;
       for (int k = 0; k < total; k++) {
@@ -468,7 +476,7 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
           else small = r;
         }
         if (two) continue;
-        int target = big >= 0 ? big : small;
+        const int target = big >= 0 ? big : small;
         if (target < 0) continue;                               // all neighbours withheld: decided in a later pass
         for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1]; p++) {
           const int u = (*W.adj)[p];
@@ -483,15 +491,28 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
       }
       if (!moved) break;
     }
-    int64_t nsep = 0;
-    largest = 0;
+    int64_t nsep = 0, largest = 0;
     for (int k = 0; k < total; k++) if (comp[k] == -2) nsep++;
     for (size_t c = 0; c < cpar.size(); c++) if (cpar[c] == (int)c) largest = std::max<int64_t>(largest, csize[c]);
-    if (largest * 10 > (int64_t)total * 7 || nsep * 20 > (int64_t)total || nsep == 0) continue;
-    sep.clear();
-    for (int k = 0; k < total; k++) if (comp[k] == -2) sep.push_back(verts[k]);
-    ok = true;
-    break;
+    if (largest * 10 > (int64_t)total * 7 || nsep * 20 > (int64_t)total || nsep == 0) return false;
+    out.clear();
+    for (int k = 0; k < total; k++) if (comp[k] == -2) out.push_back(verts[k]);
+    return true;
+  };
+  // the attempts are independent and read-only on the shared arrays: on a large region they run side by side on the
+  // host threads (this is the top of the recursion, the other cores are idle), and the FIRST threshold of the list that
+  // succeeds is taken -- the same answer as trying them one after the other
+  bool ok = false;
+  if (total >= 200000 && host_threads() > 1 && thrs.size() > 1) {
+    std::vector<std::vector<int>> outs(thrs.size());
+    std::vector<std::future<bool>> futs;
+    for (size_t t = 0; t < thrs.size(); t++)
+      futs.push_back(std::async(std::launch::async, [&, t]() { return attempt(thrs[t], outs[t]); }));
+    std::vector<char> good(thrs.size(), 0);
+    for (size_t t = 0; t < thrs.size(); t++) good[t] = futs[t].get() ? 1 : 0;
+    for (size_t t = 0; t < thrs.size() && !ok; t++) if (good[t]) { sep.swap(outs[t]); ok = true; }
+  } else {
+    for (size_t t = 0; t < thrs.size() && !ok; t++) ok = attempt(thrs[t], sep);
   }
   for (int v : verts) W.local[v] = -1;
   return ok;
