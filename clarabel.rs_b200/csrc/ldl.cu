@@ -1713,12 +1713,15 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     // head rows / rows per row task of a wide front
     auto split = [&](int ns, int nr, int& rh, int& nrt, int& chunk) {
       // a panel that fits goes to shared memory whole (one bulk copy, leading dimension ld); otherwise the head takes
-      // the pivot block + as many rows as fit and row tasks take the rest (leading dimension sv_lds(rows, ld) <= rows + 3,
-      // one more double for the alignment offset)
-      const int rmax_all = (cap - 1) / ns - 3;
-      if (nr <= SV_MAXROWS && (long long)ns * (ns + nr) + 1 <= cap) { rh = nr; nrt = 0; chunk = 0; return; }
-      rh = std::min(std::min(nr, SV_MAXROWS), std::max(0, rmax_all - ns));
-      const int rmax = std::max(1, std::min(rmax_all, SV_MAXROWS));
+      // the pivot block + as many rows as fit and row tasks take the rest: a slab of r staged rows needs
+      // sv_lds(r, ld) * ns doubles + one for the alignment offset
+      const int ld = ns + nr;
+      if (nr <= SV_MAXROWS && (long long)ns * ld + 1 <= cap) { rh = nr; nrt = 0; chunk = 0; return; }
+      auto fits = [&](int staged) { return (long long)sv_lds(staged, ld) * ns + 1 <= (long long)cap; };
+      rh = std::min(nr, SV_MAXROWS);
+      while (rh > 0 && !fits(ns + rh)) rh--;
+      int rmax = SV_MAXROWS;
+      while (rmax > 1 && !fits(rmax)) rmax--;
       const int rest = nr - rh;
       nrt = rest > 0 ? (rest + rmax - 1) / rmax : 0;
       chunk = nrt ? (rest + nrt - 1) / nrt : 0;
