@@ -436,11 +436,55 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
     if (ns0 == 0 || ns0 * 10 > (int64_t)total * 3) continue;
     if (thrs.empty() || thrs.back() != thr) thrs.push_back(thr);
   }
-  // one attempt: withhold deg >= thr, label the components of the rest, give back what is not a connector
+  // Second proposal rule, for connectors of unremarkable degree (a linking row that touches 4 blocks has FEWER
+  // neighbours than an ordinary row): locality.  In a graph with locality two neighbours of a vertex are usually
+  // adjacent or share another neighbour (two variables of one constraint row appear together in other rows of the
+  // same window); the neighbours of a connector lie in parts that only it joins.  Candidates = vertices of degree
+  // >= 2 none of whose neighbour pairs (among the first 8 neighbours) is adjacent or has a common neighbour besides
+  // the vertex itself.  Ordinary vertices leave the test at the first close pair, so the pass is cheap; whatever it
+  // proposes wrongly is given back by the connectivity step.
+  std::vector<char> cellcand;
+  auto propose_by_locality = [&]() {
+    std::vector<int> mark(total, -1);
+    cellcand.assign(total, 0);
+    int64_t nc = 0;
+    int nb[8];
+    for (int k = 0; k < total; k++) {
+      const int v = verts[k];
+      int cnt = 0;
+      for (int64_t p = (*W.xadj)[v]; p < (*W.xadj)[v + 1] && cnt < 8; p++) {
+        const int u = (*W.adj)[p];
+        if (W.part[u] == region) nb[cnt++] = u;
+      }
+      if (cnt < 2) continue;
+      bool close = false;
+      for (int i = 0; i + 1 < cnt && !close; i++) {
+        const int ui = nb[i];
+        const int stamp = k * 8 + i;
+        for (int64_t p = (*W.xadj)[ui]; p < (*W.xadj)[ui + 1]; p++) {
+          const int w = (*W.adj)[p];
+          if (W.part[w] == region) mark[W.local[w]] = stamp;
+        }
+        for (int j = i + 1; j < cnt && !close; j++) {
+          const int uj = nb[j];
+          if (mark[W.local[uj]] == stamp) { close = true; break; }
+          for (int64_t p = (*W.xadj)[uj]; p < (*W.xadj)[uj + 1]; p++) {
+            const int w = (*W.adj)[p];
+            if (w != v && W.part[w] == region && mark[W.local[w]] == stamp) { close = true; break; }
+          }
+        }
+      }
+      if (!close) { cellcand[k] = 1; nc++; }
+    }
+    return nc;
+  };
+  // one attempt: withhold the candidates (deg >= thr, or the locality rule when thr < 0), label the components of the rest,
+  // give back what is not a connector
   auto attempt = [&](int thr, std::vector<int>& out) -> bool {
     std::vector<int> comp(total), cpar, csize, stack;
     auto find = [&](int c) { while (cpar[c] != c) { cpar[c] = cpar[cpar[c]]; c = cpar[c]; } return c; };
-    for (int k = 0; k < total; k++) comp[k] = deg[k] >= thr ? -2 : -1;
+    if (thr >= 0) for (int k = 0; k < total; k++) comp[k] = deg[k] >= thr ? -2 : -1;
+    else for (int k = 0; k < total; k++) comp[k] = cellcand[k] ? -2 : -1;
     for (int k0 = 0; k0 < total; k0++) {
       if (comp[k0] != -1) continue;
       const int c = (int)cpar.size();
@@ -457,7 +501,10 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
           if (comp[ku] == -1) { comp[ku] = c; stack.push_back(ku); }
         }
       }
-      if ((int64_t)csize[c] * 10 > (int64_t)total * 6) return false;   // the rest still hangs together: withhold more
+      if ((int64_t)csize[c] * 10 > (int64_t)total * 6) {                // the rest still hangs together: withhold more
+        if (thr < 0 && std::getenv("CB_ND_DEBUG")) std::fprintf(stderr, "[nd debug] locality rule: component of %d of %d after withholding\n", csize[c], total);
+        return false;
+      }
     }
     for (int pass = 0; pass < 8; pass++) {
       int64_t moved = 0;
@@ -494,6 +541,7 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
     int64_t nsep = 0, largest = 0;
     for (int k = 0; k < total; k++) if (comp[k] == -2) nsep++;
     for (size_t c = 0; c < cpar.size(); c++) if (cpar[c] == (int)c) largest = std::max<int64_t>(largest, csize[c]);
+    if (thr < 0 && std::getenv("CB_ND_DEBUG")) std::fprintf(stderr, "[nd debug] locality rule: after give-back largest %lld, separator %lld of %d\n", (long long)largest, (long long)nsep, total);
     if (largest * 10 > (int64_t)total * 7 || nsep * 20 > (int64_t)total || nsep == 0) return false;
     out.clear();
     for (int k = 0; k < total; k++) if (comp[k] == -2) out.push_back(verts[k]);
@@ -513,6 +561,11 @@ bool hub_separator(NDShared& W, const std::vector<int>& verts, int region, std::
     for (size_t t = 0; t < thrs.size() && !ok; t++) if (good[t]) { sep.swap(outs[t]); ok = true; }
   } else {
     for (size_t t = 0; t < thrs.size() && !ok; t++) ok = attempt(thrs[t], sep);
+  }
+  if (!ok) {     // no degree threshold isolates the connectors: propose by locality
+    const int64_t nc = propose_by_locality();
+    if (nc > 0 && nc * 10 <= (int64_t)total * 3) ok = attempt(-1, sep);
+    if (std::getenv("CB_TIMING")) std::fprintf(stderr, "[cb timing]   nd: hub separator, locality rule: %lld candidates of %d -> %s (%zu connectors)\n", (long long)nc, total, ok ? "ok" : "no", sep.size());
   }
   for (int v : verts) W.local[v] = -1;
   return ok;

@@ -208,3 +208,27 @@ def test_amd_matches_reference_pin():
     assert perm.tolist() == [3, 0, 1, 2]
     iperm = np.empty(4, dtype=np.int64); iperm[perm] = np.arange(4)
     assert iperm.tolist() == [1, 2, 3, 0]
+
+
+@pytest.mark.parametrize("nblocks,link_blocks,rule", [(12, 12, "degree"), (8, 4, "locality")])
+def test_hub_separator_finds_the_linking_rows_of_a_block_angular_problem(nblocks, link_blocks, rule):
+    """Round 2, csrc/ordering.cpp hub_separator: a block-angular QP (banded blocks + a few linking rows that touch random
+    blocks) is a small-world graph -- no BFS level is thin.  The nested dissection must find the linking rows as its
+    top separator (they end up LAST in the permutation) and fall into the blocks below it.  Two proposal rules feed the
+    connectivity step: above-typical degree (rows that touch 12 blocks) and, when no degree threshold works (rows that
+    touch 4 blocks have FEWER neighbours than an ordinary row), locality -- no two neighbours of a connector are
+    adjacent or share another neighbour.  Either way exactly the 120 linking rows must come out."""
+    from helpers import workloads
+    pr = workloads.block_angular_qp(n=48_000, nblocks=nblocks, nlink=120, link_blocks=link_blocks, window=48, seed=5)
+    A = pr["A"]
+    n, m = A.shape[1], A.shape[0]
+    N, cp, rv, _, _ = workloads.kkt_triu(pr["P"], A, np.ones(m))
+    nd = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_ND)
+    amd = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_AMD)
+    assert sorted(nd.perm.tolist()) == list(range(N))
+    link_vertices = set(range(n + m - 120, n + m))            # the linking rows are the last 120 rows of A
+    tail = set(nd.perm[-120:].tolist())
+    assert tail == link_vertices, (rule, len(tail & link_vertices), "of 120 linking rows at the end of the ordering")
+    assert nd.flops < 1.05 * amd.flops and nd.nlevels * 2 < amd.nlevels      # never more work than minimum degree, a much shorter tree
+    best = cb.SymbolicAnalysis(N, cp, rv, ordering=cb.ORDER_BEST)
+    assert best.ordering_used == cb.ORDER_ND
