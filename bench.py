@@ -46,6 +46,12 @@ def load_workload(name, rank):
     elif name == "c2small":
         pr = workloads.random_sparse_qp(n=10_000, m=20_000, nnz_per_row=5, seed=1 + rank, window=200)
         desc = "random sparse QP n=1e4 m=2e4 nnz(A)=1e5, Nonneg, seed=%d" % (1 + rank)
+    elif name == "c2u":
+        # SURVEY 8(d)'s wording of C2 (columns of A drawn uniformly from all n columns: the KKT graph is an expander and the
+        # factor essentially dense) at a tenth of the size -- at full size a single CPU refactorisation would take a day
+        # (DESIGN.md section 7); the window variant above is the headline C2
+        pr = workloads.random_sparse_qp(n=10_000, m=20_000, nnz_per_row=5, seed=1 + rank, window=None)
+        desc = "random sparse QP n=1e4 m=2e4 nnz(A)=1e5, columns drawn uniformly (expander), Nonneg, seed=%d" % (1 + rank)
     elif name == "c3":
         pr = workloads.portfolio_socp(seed=2 + rank)
         desc = "portfolio SOCP 5000 assets, 200 SOC(26), seed=%d" % (2 + rank)

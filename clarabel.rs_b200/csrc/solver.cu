@@ -601,6 +601,7 @@ class IPM {
  public:
   int n = 0, m = 0;
   int mfull = 0;                 // rows of the caller's problem (m = rows left after the inf-bound presolve)
+  double setup_time = 0.0;       // seconds spent in cipm_create: the reference's time limit runs on setup + solve
   double infbound = 1e20;        // the infinity bound at construction (presolver.rs:51,150): what reverse_presolve writes into s, whatever set_infinity did since
   std::vector<char> keep;        // presolve row mask over the caller's rows, empty = nothing dropped
   cipm_settings set{};
@@ -1049,7 +1050,7 @@ bool IPM::check_termination(int iter) {
   }
   if (info.status == IST_UNSOLVED) {
     if (set.max_iter == (int32_t)info.iterations) info.status = IST_MAXIT;
-    else if (info.solve_time > set.time_limit) info.status = IST_MAXTIME;
+    else if (info.solve_time + setup_time > set.time_limit) info.status = IST_MAXTIME;   // timers.total_time() = setup + solve (solver.rs:447-452, info.rs:46-60)
   }
   return info.status != IST_UNSOLVED;
 }
@@ -1421,10 +1422,12 @@ int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
     perm.resize(N);
     for (uint64_t k = 0; k < N; k++) perm[k] = (int)kkt_perm_or_null[k];
   }
+  const double t_create0 = wall();
   int rc = h->ipm.init((int)n, (int)m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones,
                        cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr, cone_params, genpow_dim2,
                        genpow_alpha);
   if (rc) { h->ipm.release(); delete h; return rc; }
+  h->ipm.setup_time = wall() - t_create0;
   *out = h;
   return CLDL_OK;
 }
