@@ -1422,12 +1422,12 @@ int cipm_create_gp(cipm_t** out, uint64_t n, uint64_t m, const uint64_t* P_colpt
     perm.resize(N);
     for (uint64_t k = 0; k < N; k++) perm[k] = (int)kkt_perm_or_null[k];
   }
-  const double t_create0 = wall();
+  const double t_create0 = cb::wall();
   int rc = h->ipm.init((int)n, (int)m, P_colptr, P_rowval, P_nzval, q, A_colptr, A_rowval, A_nzval, b, ncones,
                        cone_types, cone_dims, s, lo, kkt_perm_or_null ? perm.data() : nullptr, cone_params, genpow_dim2,
                        genpow_alpha);
   if (rc) { h->ipm.release(); delete h; return rc; }
-  h->ipm.setup_time = wall() - t_create0;
+  h->ipm.setup_time = cb::wall() - t_create0;
   *out = h;
   return CLDL_OK;
 }
