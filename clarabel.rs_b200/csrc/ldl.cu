@@ -1413,14 +1413,24 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
   nnzA = Ap[n];
   CK(cudaMalloc((void**)&dev.vals, (size_t)(nnzA ? nnzA : 1) * sizeof(double)));
   CK(cudaMemcpy(dev.vals, Ax, (size_t)nnzA * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMalloc((void**)&dev.L, ((size_t)(S.L_alloc ? S.L_alloc : 1) + 8) * sizeof(double)));   // + slack: a bulk copy of the last panel is rounded up to 16 bytes
-  CK(cudaMalloc((void**)&dev.U, (size_t)(S.upd_total ? S.upd_total : 1) * sizeof(double)));
+  // The factor panels, the update-matrix arena and the update vectors are gigabytes (C4: 1.7 + 2.8 + 0.25 GB) and
+  // cudaMalloc of that size takes a few tenths of a second: a helper thread allocates them while this one builds and
+  // uploads the plans below (nothing in init touches these buffers; the first refactor does).  Joined before init returns.
+  big_alloc_rc = 0;
+  big_alloc = std::thread([this]() {
+    if (cudaSetDevice(device) != cudaSuccess) { big_alloc_rc = 1; return; }
+    const size_t nu = S.sn_rows.size() ? S.sn_rows.size() : 1;
+    if (cudaMalloc((void**)&dev.L, ((size_t)(S.L_alloc ? S.L_alloc : 1) + 8) * sizeof(double)) != cudaSuccess ||   // + slack: a bulk copy of the last panel is rounded up to 16 bytes
+        cudaMalloc((void**)&dev.U, (size_t)(S.upd_total ? S.upd_total : 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&dev.u, nu * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_u2, nu * sizeof(double)) != cudaSuccess)
+      big_alloc_rc = 1;
+  });
+  struct BigJoin { std::thread& t; ~BigJoin() { if (t.joinable()) t.join(); } } big_join{big_alloc};
   CK(cudaMalloc((void**)&dev.D, (size_t)n * sizeof(double)));
   CK(cudaMalloc((void**)&dev.Dinv, (size_t)n * sizeof(double)));
-  CK(cudaMalloc((void**)&dev.u, (size_t)(S.sn_rows.size() ? S.sn_rows.size() : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&d_xp, (size_t)n * sizeof(double)));
   CK(cudaMalloc((void**)&d_xp2, (size_t)n * sizeof(double)));
-  CK(cudaMalloc((void**)&d_u2, (size_t)(S.sn_rows.size() ? S.sn_rows.size() : 1) * sizeof(double)));
   CK(cudaMalloc((void**)&d_bx, (size_t)2 * n * sizeof(double)));
   CK(cudaMalloc((void**)&dev.status, ST_COUNT * sizeof(int)));
   CK(cudaMemset(dev.status, 0, ST_COUNT * sizeof(int)));
@@ -2076,6 +2086,9 @@ int LDLObject::init(int n_, const int64_t* Ap, const int32_t* Ai, const double* 
     for (int w = 0; w < 2; w++) { d_shard_segs[w].assign(shard_nranks, nullptr); shard_nsegs[w].assign(shard_nranks, 0); }
     for (int g = 0; g < shard_nranks; g++) { int* t1 = nullptr; if ((rc = upload(&t1, shard_xidx[g]))) return rc; d_shard_xidx[g] = t1; }
   }
+  if (big_alloc.joinable()) big_alloc.join();
+  if (big_alloc_rc) { std::fprintf(stderr, "[clarabel_b200] device allocation of the factor storage failed\n"); return CLDL_E_CUDA; }
+  cb_tmark("ldl: big allocations joined");
   CK(cudaDeviceSynchronize());      // the uploads above are cudaMemcpy from pageable memory (staged, not necessarily landed); `stream` does not wait for the default stream
   factored = false;
   return CLDL_OK;

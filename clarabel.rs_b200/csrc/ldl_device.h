@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 #include "../../include/clarabel_b200.h"
@@ -110,6 +111,8 @@ class LDLObject {
   Symbolic S;
   LDLDev dev;
   std::vector<LaunchSeg> plan;
+  std::thread big_alloc;                 // init: allocates the factor storage beside the plan building
+  int big_alloc_rc = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_a = nullptr, stream_b = nullptr;   // side streams of the narrow-leaf solve kernels
   cudaEvent_t ev_leaf[3] = {nullptr, nullptr, nullptr};
