@@ -934,12 +934,14 @@ int IPM::init(int n_, int m_, const uint64_t* Pp, const uint64_t* Pi, const doub
       equilibrate();
       rc_up = cudaSetDevice(devid) == cudaSuccess ? upload_problem() : CLDL_E_CUDA;
     });
+    // joined on every way out of this scope: an exception from kkt.init (std::bad_alloc of a host vector) with the
+    // thread still joinable would end the process in std::terminate
+    struct EqJoin { std::thread& t; ~EqJoin() { if (t.joinable()) t.join(); } } eq_guard{eq};
     kkt.defer_values = true;
     rc = kkt.init(P, A, &cones, set, lo, perm, st, &sc);
     eq.join();
-    if (rc) return rc;
-    if (rc_up) return rc_up;
-    if ((rc = kkt.set_PA_values(P, A))) return rc;
+    if (rc || rc_up) { cudaStreamDestroy(st); st = nullptr; return rc ? rc : rc_up; }      // the temporary stream does not leak on the error paths
+    if ((rc = kkt.set_PA_values(P, A))) { cudaStreamDestroy(st); st = nullptr; return rc; }
   }
   cb_tmark("ipm: equilibrate + upload problem || kkt init");
   // single stream for everything: adopt the LDL object's stream
