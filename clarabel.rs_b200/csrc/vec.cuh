@@ -21,12 +21,12 @@ namespace cb {
 
 // setup-phase timing to stderr when CB_TIMING is set
 inline void cb_tmark(const char* label) {
-  static double last = -1.0;
+  static std::atomic<double> last{-1.0};      // marks come from several host threads (per-rank drivers, helper threads)
   static const bool on = std::getenv("CB_TIMING") != nullptr;
   if (!on) return;
   const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-  if (label && last >= 0.0) std::fprintf(stderr, "[cb timing] %-34s %.3f s\n", label, t - last);
-  last = t;
+  const double prev = last.exchange(t);
+  if (label && prev >= 0.0) std::fprintf(stderr, "[cb timing] %-34s %.3f s\n", label, t - prev);
 }
 
 // number of kernels launched by this library (bench.py reports it as gpu_launches)
