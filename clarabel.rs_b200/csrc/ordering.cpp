@@ -583,6 +583,32 @@ void nd_rec(NDShared& W, std::vector<int>& verts, int depth, std::vector<int>& o
   // one sweep to find a far vertex, then the level structure is rooted there
   int root = verts[0];
   int e = nd_bfs(W, root, region, verts, q);
+  if (q.size() == total && W.hubs && (int)total >= 50 * W.leaf_size) {
+    // small-world signature already in the first sweep (the two levels around the balance point hold more than 4 % of
+    // the region each): no pseudo-peripheral root will make the levels thin -- go for the connectors at once and save
+    // the second sweep (0.12 s on C4)
+    std::vector<int64_t> c1(e + 1, 0);
+    for (int v : q) c1[W.level[v]]++;
+    int64_t acc = 0;
+    int cut1 = 0;
+    while (cut1 < e - 1 && acc + c1[cut1] < (int64_t)total / 2) acc += c1[cut1++];
+    if (e >= 1 && c1[cut1] * 25 > (int64_t)total && c1[std::min(cut1 + 1, e)] * 25 > (int64_t)total) {
+      std::vector<int> hsep;
+      if (hub_separator(W, q, region, hsep) &&
+          !(W.sep_flop_cap > 0.0 && (double)hsep.size() * (double)hsep.size() * (double)hsep.size() / 3.0 > W.sep_flop_cap)) {
+        if (std::getenv("CB_TIMING")) std::fprintf(stderr, "[cb timing]   nd: depth %d hub separator of %zu: %zu connectors (first sweep: levels around the balance point hold %lld and %lld vertices), %.4f s\n", depth, total, hsep.size(), (long long)c1[cut1], (long long)c1[std::min(cut1 + 1, e)], onow() - t_enter);
+        for (int v : hsep) W.part[v] = -1;
+        std::vector<int> rest;
+        rest.reserve(total - hsep.size());
+        for (int v : q) if (W.part[v] == region) rest.push_back(v);
+        std::vector<int>().swap(verts);
+        std::vector<int>().swap(q);
+        nd_rec(W, rest, depth, out);
+        nd_leaf(W, hsep, out);
+        return;
+      }
+    }
+  }
   if (q.size() == total) {
     int best = q.back();
     int64_t bestdeg = INT64_MAX;
@@ -847,7 +873,7 @@ void nd_order(int n, const int64_t* Ap, const int32_t* Ai, double dense_scale,
     int d = 0;
     // concurrent subtrees: a few per hardware thread (leaf sizes vary, so oversubscription balances the load;
     // measured on 8 cores: 0.21 s with 8 subtrees, 0.165 s with 32), at most 128
-    while ((1u << (d + 1)) <= 4 * std::max(1u, hc) && d < 7) d++;
+    while ((1u << (d + 1)) <= 4 * std::max(1u, hc) && d < (hc >= 64 ? 8 : 7)) d++;      // up to 256 concurrent subtrees on a 64+-thread host
     W.par_depth = (n >= 20000) ? d : 0;
     if (const char* e = std::getenv("CB_ND_THREADS_DEPTH")) W.par_depth = std::atoi(e);
   }
